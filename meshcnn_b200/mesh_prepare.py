@@ -1,0 +1,206 @@
+"""Edge-topology builder and the five input edge features (row N2 of SURVEY.md §8f, needed here to
+make benchmark / test inputs without the reference on the GPU box).
+
+Conventions reproduced (the reference is models/layers/mesh_prepare.py):
+  * faces are visited in file order, an edge id is assigned the first time its (sorted) vertex pair is
+    seen                                                              (mesh_prepare.py:129-146)
+  * ``gemm_edges[e]`` holds two slot pairs, (0,1) for the first face containing ``e`` and (2,3) for the
+    second; inside a pair: the face's next and next-next edge in winding order        (:148-152)
+  * ``sides[e, k]`` = slot of ``e`` inside ``gemm_edges[gemm_edges[e, k]]``            (:153-156)
+  * ``ve[v]`` lists the incident edge ids in creation order                            (:142-143)
+  * edge_areas[e] = sum over its faces of area/3, normalised by total area             (:147, :161)
+  * the 5 features: dihedral angle, 2 sorted opposite angles, 2 sorted height/base ratios (:310-427)
+
+This is an array-at-a-time restatement (no per-face dict loop), not a copy: edge ids come from a
+first-occurrence ``np.unique`` over packed vertex-pair keys and the slot tables from occurrence ranks.
+"""
+import ntpath
+
+import numpy as np
+
+
+class MeshData:
+    """Plain picklable container for one mesh's topology + features."""
+    __slots__ = ('vs', 'edges', 'gemm_edges', 'sides', 've', 'v_mask', 'edges_count', 'filename',
+                 'edge_lengths', 'edge_areas', 'features')
+
+
+def read_obj(path):
+    """OBJ reader: 'v x y z' and triangular 'f a b c' records, 1-based or negative indices, a/b/c forms
+    (mesh_prepare.py:65-87)."""
+    vs, faces = [], []
+    with open(path) as f:
+        for line in f:
+            tok = line.split()
+            if not tok:
+                continue
+            if tok[0] == 'v':
+                vs.append((float(tok[1]), float(tok[2]), float(tok[3])))
+            elif tok[0] == 'f':
+                ids = [int(t.split('/')[0]) for t in tok[1:]]
+                if len(ids) != 3:
+                    raise AssertionError('non-triangular face in %s' % path)
+                faces.append([i - 1 if i >= 0 else len(vs) + i for i in ids])
+    vs = np.asarray(vs, dtype=np.float64)
+    faces = np.asarray(faces, dtype=np.int64)
+    if faces.size and not ((faces >= 0) & (faces < len(vs))).all():
+        raise AssertionError('face index out of range in %s' % path)
+    return vs, faces
+
+
+def face_areas_of(vs, faces):
+    n = np.cross(vs[faces[:, 1]] - vs[faces[:, 0]], vs[faces[:, 2]] - vs[faces[:, 1]])
+    return 0.5 * np.sqrt((n ** 2).sum(1))
+
+
+def drop_non_manifold(vs, faces):
+    """Drop zero-area faces and faces repeating an already-used *directed* edge (mesh_prepare.py:90-113).
+    The acceptance of a face depends on the faces accepted before it, so this is a sequential sweep."""
+    areas = face_areas_of(vs, faces)
+    keep = np.ones(len(faces), dtype=bool)
+    seen = set()
+    nv = int(vs.shape[0]) + 1
+    for fi in range(len(faces)):
+        if areas[fi] == 0:
+            keep[fi] = False
+            continue
+        a, b, c = (int(t) for t in faces[fi])
+        k0, k1, k2 = a * nv + b, b * nv + c, c * nv + a
+        if k0 in seen or k1 in seen or k2 in seen:
+            keep[fi] = False
+            continue
+        seen.add(k0); seen.add(k1); seen.add(k2)
+    return faces[keep], areas[keep]
+
+
+def build_topology(vs, faces, face_areas=None):
+    """Returns edges[E,2] int32, gemm_edges[E,4] int64, sides[E,4] int64, ve (list of lists),
+    edge_areas[E] float32."""
+    nf = len(faces)
+    if face_areas is None:
+        face_areas = face_areas_of(vs, faces)
+    nv = int(vs.shape[0])
+    # half-edges in (face, corner) order == the reference's visiting order
+    a = faces.ravel()
+    b = faces[:, [1, 2, 0]].ravel()
+    lo, hi = np.minimum(a, b), np.maximum(a, b)
+    key = lo * (nv + 1) + hi
+    uniq, first, inv = np.unique(key, return_index=True, return_inverse=True)
+    order = np.argsort(first, kind='stable')           # unique keys by first appearance
+    rank = np.empty_like(order)
+    rank[order] = np.arange(len(order))
+    he_edge = rank[inv]                                 # edge id of each half-edge
+    E = len(uniq)
+    edges = np.stack([lo[first[order]], hi[first[order]]], 1).astype(np.int32)
+    # occurrence rank of each half-edge among the half-edges of its edge (0 = first face, 1 = second)
+    srt = np.argsort(he_edge, kind='stable')
+    start = np.r_[0, np.cumsum(np.bincount(he_edge, minlength=E))[:-1]]
+    occ = np.empty(3 * nf, dtype=np.int64)
+    occ[srt] = np.arange(3 * nf) - start[he_edge[srt]]
+    if occ.max(initial=0) > 1:
+        raise ValueError('edge shared by more than two faces (non-manifold input)')
+    he = he_edge.reshape(nf, 3)
+    base = (2 * occ).reshape(nf, 3)                     # slot-pair base of this face in each edge's row
+    nxt, nxt2 = he[:, [1, 2, 0]], he[:, [2, 0, 1]]
+    bn, bn2 = base[:, [1, 2, 0]], base[:, [2, 0, 1]]
+    gemm = -np.ones((E, 4), dtype=np.int64)
+    sides = -np.ones((E, 4), dtype=np.int64)
+    gemm[he.ravel(), base.ravel()] = nxt.ravel()
+    gemm[he.ravel(), base.ravel() + 1] = nxt2.ravel()
+    sides[he.ravel(), base.ravel()] = bn.ravel() + 1    # in next's row, e is the next-next entry
+    sides[he.ravel(), base.ravel() + 1] = bn2.ravel()   # in next-next's row, e is the next entry
+    # vertex -> incident edges in edge creation order
+    ev = edges.astype(np.int64).ravel()
+    eid = np.repeat(np.arange(E), 2)
+    o = np.argsort(ev, kind='stable')
+    cnt = np.bincount(ev, minlength=nv)
+    splits = np.cumsum(cnt)[:-1]
+    ve = [seg.tolist() for seg in np.split(eid[o], splits)]
+    # edge areas: sequential float64 accumulation order of the reference is face order; np.add.at keeps it
+    ea = np.zeros(E, dtype=np.float64)
+    np.add.at(ea, he.ravel(), np.repeat(face_areas / 3, 3))
+    # float32 array / float64 scalar: the result dtype follows numpy's promotion rules, as in the reference
+    edge_areas = ea.astype(np.float32) / np.sum(face_areas)
+    return edges, gemm, sides, ve, edge_areas
+
+
+def _div_eps(x, eps):
+    x = x.copy()
+    if eps == 0:
+        x[x == 0] = 0.1
+    else:
+        x += eps
+    return x
+
+
+def edge_points(edges, gemm):
+    """Four vertex ids per edge: its two endpoints (oriented) and the opposite vertex of each incident face
+    (mesh_prepare.py:361-399)."""
+    g = gemm
+    b_id = np.where(g[:, 0] == -1, g[:, 2], g[:, 0])
+    c_id = np.where(g[:, 0] == -1, g[:, 3], g[:, 1])
+    d_id = np.where(g[:, 2] == -1, g[:, 0], g[:, 2])
+    e_id = np.where(g[:, 2] == -1, g[:, 1], g[:, 3])
+    ea, eb, ec_, ed, ee = edges, edges[b_id], edges[c_id], edges[d_id], edges[e_id]
+    first = ((ea[:, 1] == eb[:, 0]) | (ea[:, 1] == eb[:, 1])).astype(np.int64)
+    second = ((eb[:, 1] == ec_[:, 0]) | (eb[:, 1] == ec_[:, 1])).astype(np.int64)
+    third = ((ed[:, 1] == ee[:, 0]) | (ed[:, 1] == ee[:, 1])).astype(np.int64)
+    r = np.arange(len(edges))
+    return np.stack([ea[r, first], ea[r, 1 - first], eb[r, second], ed[r, third]], 1).astype(np.int32)
+
+
+def extract_features(vs, edges, gemm):
+    """[5, E] float64 features + edge lengths (mesh_prepare.py:303-427)."""
+    ep = edge_points(edges, gemm)
+    lengths = np.linalg.norm(vs[ep[:, 0]] - vs[ep[:, 1]], axis=1)
+
+    def normals(side):
+        s = side // 2
+        n = np.cross(vs[ep[:, s + 2]] - vs[ep[:, s]], vs[ep[:, 1 - s]] - vs[ep[:, s]])
+        return n / _div_eps(np.linalg.norm(n, axis=1), 0.1)[:, None]
+
+    def opposite(side):
+        s = side // 2
+        ua = vs[ep[:, s]] - vs[ep[:, s + 2]]
+        ub = vs[ep[:, 1 - s]] - vs[ep[:, s + 2]]
+        ua = ua / _div_eps(np.linalg.norm(ua, axis=1), 0.1)[:, None]
+        ub = ub / _div_eps(np.linalg.norm(ub, axis=1), 0.1)[:, None]
+        return np.arccos(np.sum(ua * ub, axis=1).clip(-1, 1))
+
+    def ratio(side):
+        s = side // 2
+        base_len = np.linalg.norm(vs[ep[:, s]] - vs[ep[:, 1 - s]], axis=1)
+        po, pa, pb = vs[ep[:, s + 2]], vs[ep[:, s]], vs[ep[:, 1 - s]]
+        ab = pb - pa
+        proj = np.sum(ab * (po - pa), axis=1) / _div_eps(np.linalg.norm(ab, axis=1), 0.1)
+        closest = pa + (proj / base_len)[:, None] * ab
+        return np.linalg.norm(po - closest, axis=1) / base_len
+
+    with np.errstate(divide='raise'):
+        try:
+            dihedral = (np.pi - np.arccos(np.sum(normals(0) * normals(3), axis=1).clip(-1, 1)))[None]
+            ang = np.sort(np.stack([opposite(0), opposite(3)], 0), axis=0)
+            rat = np.sort(np.stack([ratio(0), ratio(3)], 0), axis=0)
+        except FloatingPointError as e:
+            raise ValueError('bad features') from e
+    return np.concatenate([dihedral, ang, rat], 0), lengths
+
+
+def from_arrays(vs, faces, filename='synthetic'):
+    """Full preparation of one mesh from vertex / face arrays (no augmentation)."""
+    vs = np.array(vs, dtype=np.float64)
+    faces = np.asarray(faces, dtype=np.int64)
+    faces, areas = drop_non_manifold(vs, faces)
+    d = MeshData()
+    d.vs = vs
+    d.v_mask = np.ones(len(vs), dtype=bool)
+    d.filename = filename
+    d.edges, d.gemm_edges, d.sides, d.ve, d.edge_areas = build_topology(vs, faces, areas)
+    d.edges_count = int(len(d.edges))
+    d.features, d.edge_lengths = extract_features(vs, d.edges, d.gemm_edges)
+    return d
+
+
+def from_obj(path):
+    vs, faces = read_obj(path)
+    return from_arrays(vs, faces, filename=ntpath.split(path)[1])
