@@ -1,0 +1,171 @@
+/*
+ * meshcnn_b200 -- C ABI of the B200 (sm_100a) implementation of MeshCNN's per-edge hot path.
+ *
+ * The reference (ranahanocka/MeshCNN) is pure Python and has no FFI; the boundary it offers is the Python
+ * class surface of models/layers/{mesh_conv,mesh_pool,mesh_union,mesh_unpool,mesh}.py.  The functions below
+ * are what a binding for that surface needs; each one cites the reference code it replaces.  The Python
+ * mirror (meshcnn_b200/*.py) binds them with ctypes; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host; sizes are element counts
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises
+ *   - no allocation, no global mutable state; safe to call from any host thread and under CUDA-graph capture
+ *   - return value: 0 = launched, otherwise a MCNN_E_* code (argument errors are detected on the host;
+ *     data-dependent errors of the collapse kernel are written to its per-mesh `status` array)
+ *
+ * Layouts (see DESIGN.md "Data layout in HBM")
+ *   features   x[B][E][C]  fp32, edge-major (the channel vector of one edge is contiguous) -- this is the
+ *              channels_last view of the reference's [B, C, E, 1] tensors
+ *   topology   gemm[B][E][4] int32 (one-ring neighbour ids, -1 = none), sides[B][E][4] int8,
+ *              ec[B] int32 (live edge count of every mesh; rows >= ec[b] are padding)
+ *   groups     CSR  (rowptr[B][T+1], cols[B][cap])  pooled edge -> old edges   (clamped MeshUnion rows)
+ *              CSC  (colptr[B][E+1], rows[B][cap])  old edge -> pooled edges
+ *              occ[B][E] fp32  un-clamped, un-masked column sums
+ */
+#ifndef MESHCNN_B200_H
+#define MESHCNN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCNN_OK 0
+#define MCNN_E_BADARG 1          /* null pointer / non-positive size / unsupported shape               */
+#define MCNN_E_TOO_LARGE 2       /* mesh does not fit the on-chip collapse state                        */
+#define MCNN_E_CUDA 3            /* a CUDA runtime call failed (see mcnn_last_cuda_error)               */
+
+/* per-mesh status words written by mcnn_pool_collapse (0 = fine).  The Python mirror turns them into the
+ * exception the reference would raise (failure row). */
+#define MCNN_ST_OK 0
+#define MCNN_ST_QUEUE_EMPTY 1    /* heappop on an empty heap -> IndexError      (mesh_pool.py:49-50)    */
+#define MCNN_ST_SHARED_ASSERT 2  /* assert len(shared_items) == 2               (mesh_pool.py:123)      */
+#define MCNN_ST_VERTEX_ASSERT 3  /* assert len(vertex) == 1                     (mesh_pool.py:181)      */
+#define MCNN_ST_VE_REMOVE 4      /* list.remove(x): x not in list -> ValueError (mesh.py:48)            */
+#define MCNN_ST_GROUP_OVERFLOW 5 /* sparse MeshUnion node pool exhausted (implementation limit)         */
+#define MCNN_ST_DEGENERATE 6     /* edge with identical endpoints reached merge_vertices (unsupported)  */
+#define MCNN_ST_NNZ_OVERFLOW 7   /* groups CSR capacity exceeded (implementation limit)                 */
+
+/* per-pop outcome codes of the optional collapse log */
+#define MCNN_POP_SKIP_MASKED 0
+#define MCNN_POP_REJ_BOUNDARY 1
+#define MCNN_POP_REJ_SIDE0 2
+#define MCNN_POP_REJ_SIDE2 3
+#define MCNN_POP_REJ_ONE_RING 4
+#define MCNN_POP_COLLAPSED 5
+
+int mcnn_version(void);
+/* number of kernel launches this library has enqueued since load (monotonic; bench.py reports its delta) */
+unsigned long long mcnn_launch_count(void);
+const char* mcnn_last_cuda_error(void);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * MeshConv  (models/layers/mesh_conv.py)
+ * ------------------------------------------------------------------------------------------------------ */
+
+/* Fused pad_gemm + create_GeMM + Conv2d(1x5)  (mesh_conv.py:20-26, :39-70, :72-84).
+ *   x      [B][E][Cin]     weight [Cout][Cin][1][5] (nn.Conv2d layout)     bias [Cout] or NULL
+ *   out    [B][E][Cout]
+ *   wt_ws  [5*Cin][Cout] scratch: the weight re-laid K-major by a first small kernel
+ * Rows e >= ec[b] gather edge 0 of mesh b for all five slots; -1 neighbours read zeros. */
+int mcnn_meshconv_fwd(const float* x, const int32_t* gemm, const int32_t* ec, const float* weight,
+                      const float* bias, float* out, float* wt_ws, int B, int E, int Cin, int Cout, void* stream);
+
+/* dx of the above (autograd of mesh_conv.py:47-69: conv2d dgrad, abs/add backward, index_select scatter).
+ *   dout [B][E][Cout]   dx [B][E][Cin]  -- must be ZERO on entry (the kernel accumulates with red.global) */
+int mcnn_meshconv_bwd_data(const float* dout, const float* x, const int32_t* gemm, const int32_t* ec,
+                           const float* weight, float* dx, int B, int E, int Cin, int Cout, void* stream);
+
+/* dW [Cout][Cin][1][5] and dbias [Cout] (NULL to skip); both must be ZERO on entry. */
+int mcnn_meshconv_bwd_weight(const float* dout, const float* x, const int32_t* gemm, const int32_t* ec,
+                             float* dweight, float* dbias, int B, int E, int Cin, int Cout, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * MeshPool / MeshUnion / Mesh.clean  (models/layers/mesh_pool.py, mesh_union.py, mesh.py:26-71,151-198)
+ * ------------------------------------------------------------------------------------------------------ */
+
+/* __build_queue's key: norms[b][e] = sum_c x[b][e][c]^2 in fp32, channels added in ascending order with a
+ * separate multiply and add (mesh_pool.py:186).  norms [B][E]. */
+int mcnn_pool_norms(const float* x, float* norms, int B, int E, int C, void* stream);
+
+typedef struct {
+    /* sizes */
+    int32_t B;            /* meshes in the batch                                                        */
+    int32_t E_in;         /* edge dimension of the incoming level (rows of gemm_in per mesh)            */
+    int32_t T;            /* pool target = edge dimension of the outgoing level                         */
+    int32_t V;            /* vertex capacity per mesh                                                   */
+    int32_t ve_cap;       /* capacity of ve_idx per mesh (2 * edges at level 0 suffices)                */
+    int32_t nnz_cap;      /* capacity of grp_cols / grp_rows per mesh                                   */
+    int32_t log_cap;      /* capacity of the optional logs per mesh (>= E_in for pops, unions)          */
+    int32_t reserved;
+    /* incoming level (read only) */
+    const int32_t* gemm_in;   /* [B][E_in][4] */
+    const int8_t* sides_in;   /* [B][E_in][4] */
+    const int32_t* ec_in;     /* [B]          */
+    const float* norms;       /* [B][E_in]    */
+    /* state carried across levels (read + overwritten with the cleaned state, Mesh.clean mesh.py:50-71) */
+    int32_t* edges;           /* [B][E_cap0][2] vertex ids per edge; row stride given by edges_stride    */
+    int32_t edges_stride;     /* rows per mesh in `edges`                                                */
+    int32_t reserved2;
+    int32_t* ve_ptr;          /* [B][V+1]  CSR of the per-vertex edge lists (a multiset with stale ids)  */
+    int32_t* ve_idx;          /* [B][ve_cap] */
+    uint8_t* v_mask;          /* [B][V]      */
+    double* vs;               /* [B][V][3] or NULL (positions are only needed for export, mesh.py:29-33) */
+    /* outgoing level */
+    int32_t* gemm_out;        /* [B][T][4] */
+    int8_t* sides_out;        /* [B][T][4] */
+    int32_t* ec_out;          /* [B]       */
+    /* MeshUnion result */
+    int32_t* grp_rowptr;      /* [B][T+1]     */
+    int32_t* grp_cols;        /* [B][nnz_cap] */
+    int32_t* grp_colptr;      /* [B][E_in+1]  */
+    int32_t* grp_rows;        /* [B][nnz_cap] */
+    float* occ;               /* [B][E_in]    */
+    int32_t* status;          /* [B]          */
+    /* optional logs (NULL to skip) */
+    int32_t* log_npops;       /* [B]             */
+    int32_t* log_pops;        /* [B][log_cap]    */
+    int8_t* log_outcome;      /* [B][log_cap]    */
+    int32_t* log_nunions;     /* [B]             */
+    int32_t* log_unions;      /* [B][8*log_cap][2] pairs (src, dst)                                      */
+    int32_t* edge_mask_out;   /* [B][E_in] survivor mask (1/0) or NULL                                   */
+} mcnn_pool_args;
+
+/* __pool_main for every mesh of the batch, one CTA per mesh (mesh_pool.py:41-203 + mesh.py:26-71 +
+ * mesh_union.py:9-25): sort by (norm, id), sequential collapse with all the reference's validity tests and
+ * side effects, Mesh.clean compaction / re-indexing, MeshUnion rows as CSR + CSC + occurrences. */
+int mcnn_pool_collapse(const mcnn_pool_args* args, void* stream);
+/* dynamic shared memory the collapse kernel needs for these sizes (bytes); > mcnn_pool_smem_limit() means
+ * MCNN_E_TOO_LARGE */
+size_t mcnn_pool_smem_bytes(int E_in, int V, int ve_cap, int with_vs);
+size_t mcnn_pool_smem_limit(void);
+
+/* rebuild_features_average (mesh_union.py:27-36):  out[b][r] = mean_{j in row r} x[b][j],  rows >= ec_out = 0
+ *   x [B][E_in][C]   out [B][T][C] */
+int mcnn_segmean_fwd(const float* x, const int32_t* grp_rowptr, const int32_t* grp_cols, const int32_t* ec_out,
+                     float* out, int B, int E_in, int T, int C, int nnz_cap, void* stream);
+/* its transpose: dx[b][j] = sum_{r containing j} dout[b][r] / len(r) */
+int mcnn_segmean_bwd(const float* dout, const int32_t* grp_rowptr, const int32_t* grp_colptr,
+                     const int32_t* grp_rows, const int32_t* ec_in, float* dx, int B, int E_in, int T, int C,
+                     int nnz_cap, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * MeshUnpool  (models/layers/mesh_unpool.py:30-41)
+ * ------------------------------------------------------------------------------------------------------ */
+/* out[b][i] = (sum_{r containing i} f[b][r]) / occ[b][i] for i < ec_hi[b]; 0 for i >= ec_hi[b]
+ *   f [B][E_lo][C]   out [B][E_hi][C];  the CSC/occ are the ones of the pool level being undone, whose
+ *   E_in was E_grp (E_hi >= E_grp; the extra columns are the reference's zero padding)                    */
+int mcnn_unpool_fwd(const float* f, const int32_t* grp_colptr, const int32_t* grp_rows, const float* occ,
+                    const int32_t* ec_hi, float* out, int B, int E_lo, int E_hi, int E_grp, int C, int nnz_cap,
+                    void* stream);
+/* df[b][r] = sum_{i in row r} dout[b][i] / occ[b][i]; rows r >= ec_lo[b] = 0 */
+int mcnn_unpool_bwd(const float* dout, const int32_t* grp_rowptr, const int32_t* grp_cols, const float* occ,
+                    const int32_t* ec_lo, float* df, int B, int E_lo, int E_hi, int E_grp, int C, int nnz_cap,
+                    void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MESHCNN_B200_H */

@@ -1,0 +1,90 @@
+"""ctypes binding of libmeshcnn_b200.so (the C ABI declared in include/meshcnn_b200.h).
+
+There is no CPU fallback: if the library is missing, ``lib()`` raises; every layer calls it on first use.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libmeshcnn_b200.so')
+
+_c_int = ctypes.c_int
+_c_vp = ctypes.c_void_p
+_c_sz = ctypes.c_size_t
+
+
+class PoolArgs(ctypes.Structure):
+    """mcnn_pool_args (include/meshcnn_b200.h)"""
+    _fields_ = [
+        ('B', ctypes.c_int32), ('E_in', ctypes.c_int32), ('T', ctypes.c_int32), ('V', ctypes.c_int32),
+        ('ve_cap', ctypes.c_int32), ('nnz_cap', ctypes.c_int32), ('log_cap', ctypes.c_int32), ('reserved', ctypes.c_int32),
+        ('gemm_in', _c_vp), ('sides_in', _c_vp), ('ec_in', _c_vp), ('norms', _c_vp),
+        ('edges', _c_vp), ('edges_stride', ctypes.c_int32), ('reserved2', ctypes.c_int32),
+        ('ve_ptr', _c_vp), ('ve_idx', _c_vp), ('v_mask', _c_vp), ('vs', _c_vp),
+        ('gemm_out', _c_vp), ('sides_out', _c_vp), ('ec_out', _c_vp),
+        ('grp_rowptr', _c_vp), ('grp_cols', _c_vp), ('grp_colptr', _c_vp), ('grp_rows', _c_vp), ('occ', _c_vp),
+        ('status', _c_vp),
+        ('log_npops', _c_vp), ('log_pops', _c_vp), ('log_outcome', _c_vp), ('log_nunions', _c_vp), ('log_unions', _c_vp),
+        ('edge_mask_out', _c_vp),
+    ]
+
+
+# name -> (restype, argtypes); must list every symbol of include/meshcnn_b200.h (tests/test_cabi.py checks it)
+SIGNATURES = {
+    'mcnn_version': (_c_int, []),
+    'mcnn_launch_count': (ctypes.c_ulonglong, []),
+    'mcnn_last_cuda_error': (ctypes.c_char_p, []),
+    'mcnn_meshconv_fwd': (_c_int, [_c_vp] * 7 + [_c_int] * 4 + [_c_vp]),
+    'mcnn_meshconv_bwd_data': (_c_int, [_c_vp] * 6 + [_c_int] * 4 + [_c_vp]),
+    'mcnn_meshconv_bwd_weight': (_c_int, [_c_vp] * 6 + [_c_int] * 4 + [_c_vp]),
+    'mcnn_pool_norms': (_c_int, [_c_vp, _c_vp, _c_int, _c_int, _c_int, _c_vp]),
+    'mcnn_pool_collapse': (_c_int, [ctypes.POINTER(PoolArgs), _c_vp]),
+    'mcnn_pool_smem_bytes': (_c_sz, [_c_int, _c_int, _c_int, _c_int]),
+    'mcnn_pool_smem_limit': (_c_sz, []),
+    'mcnn_segmean_fwd': (_c_int, [_c_vp] * 5 + [_c_int] * 5 + [_c_vp]),
+    'mcnn_segmean_bwd': (_c_int, [_c_vp] * 6 + [_c_int] * 5 + [_c_vp]),
+    'mcnn_unpool_fwd': (_c_int, [_c_vp] * 6 + [_c_int] * 6 + [_c_vp]),
+    'mcnn_unpool_bwd': (_c_int, [_c_vp] * 6 + [_c_int] * 6 + [_c_vp]),
+}
+
+_ERRORS = {1: 'MCNN_E_BADARG', 2: 'MCNN_E_TOO_LARGE', 3: 'MCNN_E_CUDA'}
+_lib = None
+
+
+def lib():
+    """The loaded shared library; raises if it has not been built (no fallback path exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                'meshcnn_b200: %s is missing. Build it with `python -c "import __graft_entry__ as g; g.build()"` '
+                'or `make -C meshcnn_b200/csrc`. There is no CPU fallback.' % LIB_PATH)
+        l = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = _ERRORS.get(rc, str(rc))
+        if rc == 3:
+            msg += ': ' + lib().mcnn_last_cuda_error().decode()
+        raise RuntimeError('%s failed with %s' % (what, msg))
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def current_stream():
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+def launch_count():
+    return int(lib().mcnn_launch_count())

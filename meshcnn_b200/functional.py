@@ -1,0 +1,119 @@
+"""autograd.Function wrappers over the C ABI.  All tensors here are edge-major [B, E, C] fp32 on a CUDA device;
+every call enqueues on the current stream and never synchronises."""
+import torch
+
+from . import _lib
+from . import profiler
+
+
+def _chk_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError('meshcnn_b200 layers run on CUDA only (no CPU fallback); got a %s tensor' % t.device)
+
+
+class MeshConvFn(torch.autograd.Function):
+    """Fused MeshConv (mesh_conv.py:20-26) with the backward of SURVEY.md Appendix A."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, level, wt_ws):
+        _chk_cuda(x, weight, bias)
+        B, E, Cin = x.shape
+        Cout = weight.shape[0]
+        x = x.contiguous()
+        w = weight.contiguous()
+        out = torch.empty(B, E, Cout, dtype=torch.float32, device=x.device)
+        L = _lib.lib()
+        with profiler.span('meshconv_fwd', B=B, E=E, Cin=Cin, Cout=Cout):
+            _lib.check(L.mcnn_meshconv_fwd(x.data_ptr(), level.gemm.data_ptr(), level.ec.data_ptr(), w.data_ptr(),
+                                           _lib.ptr(bias), out.data_ptr(), wt_ws.data_ptr(), B, E, Cin, Cout,
+                                           _lib.current_stream()), 'mcnn_meshconv_fwd')
+        ctx.save_for_backward(x, w)
+        ctx.level = level
+        ctx.has_bias = bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, w = ctx.saved_tensors
+        level = ctx.level
+        B, E, Cin = x.shape
+        Cout = w.shape[0]
+        dout = dout.contiguous()
+        L = _lib.lib()
+        st = _lib.current_stream()
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.zeros_like(x)
+            with profiler.span('meshconv_bwd_data', B=B, E=E, Cin=Cin, Cout=Cout):
+                _lib.check(L.mcnn_meshconv_bwd_data(dout.data_ptr(), x.data_ptr(), level.gemm.data_ptr(), level.ec.data_ptr(),
+                                                    w.data_ptr(), dx.data_ptr(), B, E, Cin, Cout, st), 'mcnn_meshconv_bwd_data')
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            dw = torch.zeros_like(w)
+            db = torch.zeros(Cout, dtype=torch.float32, device=x.device) if ctx.has_bias else None
+            with profiler.span('meshconv_bwd_weight', B=B, E=E, Cin=Cin, Cout=Cout):
+                _lib.check(L.mcnn_meshconv_bwd_weight(dout.data_ptr(), x.data_ptr(), level.gemm.data_ptr(), level.ec.data_ptr(),
+                                                      dw.data_ptr(), _lib.ptr(db), B, E, Cin, Cout, st), 'mcnn_meshconv_bwd_weight')
+        return dx, dw, db, None, None
+
+
+def pool_norms(x):
+    """fp32 squared feature norms [B, E] (mesh_pool.py:186); not differentiable by construction."""
+    B, E, C = x.shape
+    norms = torch.empty(B, E, dtype=torch.float32, device=x.device)
+    _lib.check(_lib.lib().mcnn_pool_norms(x.data_ptr(), norms.data_ptr(), B, E, C, _lib.current_stream()), 'mcnn_pool_norms')
+    return norms
+
+
+class SegMeanFn(torch.autograd.Function):
+    """rebuild_features_average (mesh_union.py:27-36) over the CSR groups of a PoolRecord."""
+
+    @staticmethod
+    def forward(ctx, x, rec, ec_in, ec_out):
+        _chk_cuda(x)
+        x = x.contiguous()
+        B, E_in, C = x.shape
+        out = torch.empty(B, rec.T, C, dtype=torch.float32, device=x.device)
+        _lib.check(_lib.lib().mcnn_segmean_fwd(x.data_ptr(), rec.rowptr.data_ptr(), rec.cols.data_ptr(), ec_out.data_ptr(),
+                                               out.data_ptr(), B, E_in, rec.T, C, rec.nnz_cap, _lib.current_stream()),
+                   'mcnn_segmean_fwd')
+        ctx.rec, ctx.ec_in, ctx.shape = rec, ec_in, (B, E_in, C)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        rec = ctx.rec
+        B, E_in, C = ctx.shape
+        dout = dout.contiguous()
+        dx = torch.empty(B, E_in, C, dtype=torch.float32, device=dout.device)
+        _lib.check(_lib.lib().mcnn_segmean_bwd(dout.data_ptr(), rec.rowptr.data_ptr(), rec.colptr.data_ptr(),
+                                               rec.rows.data_ptr(), ctx.ec_in.data_ptr(), dx.data_ptr(), B, E_in, rec.T, C,
+                                               rec.nnz_cap, _lib.current_stream()), 'mcnn_segmean_bwd')
+        return dx, None, None, None
+
+
+class UnpoolFn(torch.autograd.Function):
+    """MeshUnpool.forward's matmul with the saved groups / occurrences (mesh_unpool.py:30-41)."""
+
+    @staticmethod
+    def forward(ctx, f, rec, ec_hi, ec_lo, E_hi):
+        _chk_cuda(f)
+        f = f.contiguous()
+        B, E_lo, C = f.shape
+        out = torch.empty(B, E_hi, C, dtype=torch.float32, device=f.device)
+        _lib.check(_lib.lib().mcnn_unpool_fwd(f.data_ptr(), rec.colptr.data_ptr(), rec.rows.data_ptr(), rec.occ.data_ptr(),
+                                              ec_hi.data_ptr(), out.data_ptr(), B, E_lo, E_hi, rec.E_in, C, rec.nnz_cap,
+                                              _lib.current_stream()), 'mcnn_unpool_fwd')
+        ctx.rec, ctx.ec_lo, ctx.shape, ctx.E_hi = rec, ec_lo, (B, E_lo, C), E_hi
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        rec = ctx.rec
+        B, E_lo, C = ctx.shape
+        dout = dout.contiguous()
+        df = torch.empty(B, E_lo, C, dtype=torch.float32, device=dout.device)
+        _lib.check(_lib.lib().mcnn_unpool_bwd(dout.data_ptr(), rec.rowptr.data_ptr(), rec.cols.data_ptr(), rec.occ.data_ptr(),
+                                              ctx.ec_lo.data_ptr(), df.data_ptr(), B, E_lo, ctx.E_hi, rec.E_in, C,
+                                              rec.nnz_cap, _lib.current_stream()), 'mcnn_unpool_bwd')
+        return df, None, None, None, None

@@ -1,0 +1,397 @@
+"""Mesh (host object, drop-in for models/layers/mesh.py) and MeshBatch (device-resident topology).
+
+Reference behaviour mirrored here (file:line into the reference):
+  * ``Mesh(file, opt, hold_history, export_folder)`` with attributes ``vs, v_mask, filename, features,
+    edge_areas, edge_lengths, edges, gemm_edges, sides, ve, edges_count, pool_count, export_folder,
+    history_data``                                                                     mesh.py:12-21
+  * meshes are built in DataLoader workers and pickled (data/base_dataset.py:55-63), so a Mesh is
+    plain host data at birth; the device copy is made lazily, once per batch, by ``MeshBatch.of``
+  * a Mesh is single-use per forward: MeshUnpool restores only gemm_edges / edges_count
+                                                                                       mesh.py:194-198
+
+B200-first design: the topology of the whole batch lives in HBM as flat arrays (one upload per batch, one
+blob); MeshPool rewrites it on the device and the host attributes become lazy mirrors that are downloaded only
+when host code actually reads them (``Mesh.gemm_edges`` etc. are properties).
+"""
+import numpy as np
+import torch
+
+from . import mesh_prepare
+from . import _lib
+from . import profiler
+
+
+class PoolError(RuntimeError):
+    pass
+
+
+# status word -> exception the reference would have raised
+_STATUS_EXC = {
+    1: (IndexError, 'pop from an empty heap: the edge queue ran dry before the pool target was reached (mesh_pool.py:49-50)'),
+    2: (AssertionError, 'assert len(shared_items) == 2 (mesh_pool.py:123)'),
+    3: (AssertionError, 'assert len(vertex) == 1 (mesh_pool.py:181)'),
+    4: (ValueError, 'list.remove(x): x not in list (mesh.py:48)'),
+    5: (PoolError, 'MeshUnion node pool exhausted (implementation limit of the collapse kernel)'),
+    6: (PoolError, 'degenerate edge (identical endpoints) reached merge_vertices'),
+    7: (PoolError, 'groups CSR capacity exceeded'),
+}
+
+
+def _align(n, a=16):
+    return (n + a - 1) // a * a
+
+
+class Level:
+    """One resolution of the batch: one-ring tables + live edge counts, all on the device."""
+    __slots__ = ('E', 'gemm', 'sides', 'ec', 'padded')
+
+    def __init__(self, E, gemm, sides, ec):
+        self.E, self.gemm, self.sides, self.ec = E, gemm, sides, ec
+        self.padded = {}
+
+    def for_width(self, E):
+        """Tables for an activation tensor whose edge dimension is E >= self.E (the reference pads per call,
+        mesh_conv.py:82)."""
+        if E == self.E:
+            return self
+        if E < self.E:
+            raise ValueError('activation has %d edge slots but the mesh level has %d' % (E, self.E))
+        lv = self.padded.get(E)
+        if lv is None:
+            B = self.gemm.shape[0]
+            g = torch.zeros(B, E, 4, dtype=torch.int32, device=self.gemm.device)
+            s = torch.zeros(B, E, 4, dtype=torch.int8, device=self.gemm.device)
+            g[:, :self.E] = self.gemm
+            s[:, :self.E] = self.sides
+            lv = Level(E, g, s, self.ec)
+            self.padded[E] = lv
+        return lv
+
+
+class PoolRecord:
+    """What one MeshPool call leaves behind for MeshUnpool / backward: MeshUnion rows as CSR + CSC and the
+    un-clamped occurrences (mesh.py:182-192)."""
+    __slots__ = ('E_in', 'T', 'nnz_cap', 'rowptr', 'cols', 'colptr', 'rows', 'occ', 'status', 'level_in', 'level_out',
+                 'norms', 'logs', 'edge_mask')
+
+
+class MeshBatch:
+    """Device state of a batch of meshes."""
+
+    def __init__(self, meshes, E, device, with_vs=None):
+        meshes = list(meshes)
+        self.meshes = meshes
+        self.device = torch.device(device)
+        B = len(meshes)
+        hs = [m._host_state() for m in meshes]
+        ecs = [int(h['edges_count']) for h in hs]
+        if max(ecs) > E:
+            raise ValueError('mesh with %d edges does not fit an activation of width %d' % (max(ecs), E))
+        V = max(len(h['vs']) for h in hs)
+        nve = [int(len(h['ve_flat'])) for h in hs]
+        ve_cap = _align(max(2 * E, max(nve)), 8)
+        if with_vs is None:
+            with_vs = any(bool(m.export_folder) for m in meshes)
+        self.B, self.E0, self.V, self.ve_cap, self.with_vs = B, E, V, ve_cap, with_vs
+        # ---- pack everything into one pinned blob, one H2D copy ------------------------------------------
+        sizes = [('gemm', B * E * 4 * 4), ('sides', B * E * 4), ('ec', B * 4), ('edges', B * E * 2 * 4),
+                 ('ve_ptr', B * (V + 1) * 4), ('ve_idx', B * ve_cap * 4), ('v_mask', B * V),
+                 ('vs', B * V * 3 * 8 if with_vs else 0)]
+        offs, o = {}, 0
+        for k, s in sizes:
+            offs[k] = (o, s)
+            o = _align(o + s)
+        pin = torch.cuda.is_available()
+        host = torch.zeros(o, dtype=torch.uint8, pin_memory=pin)
+        hb = host.numpy()
+
+        def view(k, dtype, shape):
+            a, s = offs[k]
+            return hb[a:a + s].view(dtype).reshape(shape)
+
+        gemm = view('gemm', np.int32, (B, E, 4))
+        sides = view('sides', np.int8, (B, E, 4))
+        ec = view('ec', np.int32, (B,))
+        edges = view('edges', np.int32, (B, E, 2))
+        ve_ptr = view('ve_ptr', np.int32, (B, V + 1))
+        ve_idx = view('ve_idx', np.int32, (B, ve_cap))
+        v_mask = view('v_mask', np.uint8, (B, V))
+        vs = view('vs', np.float64, (B, V, 3)) if with_vs else None
+        for b, h in enumerate(hs):
+            n = ecs[b]
+            gemm[b, :n] = h['gemm_edges'][:n]
+            sides[b, :n] = h['sides'][:n]
+            ec[b] = n
+            edges[b, :n] = h['edges'][:n]
+            off = h['ve_off']
+            ve_ptr[b, :len(off)] = off
+            ve_ptr[b, len(off):] = off[-1]
+            ve_idx[b, :nve[b]] = h['ve_flat']
+            v_mask[b, :len(h['v_mask'])] = h['v_mask']
+            if with_vs:
+                vs[b, :len(h['vs'])] = h['vs']
+        self._host_blob = host
+        self.blob = host.to(self.device, non_blocking=True)
+        self._offs = offs
+
+        def dview(k, dtype, shape):
+            a, s = offs[k]
+            return self.blob[a:a + s].view(dtype).view(shape)
+
+        self.edges = dview('edges', torch.int32, (B, E, 2))
+        self.ve_ptr = dview('ve_ptr', torch.int32, (B, V + 1))
+        self.ve_idx = dview('ve_idx', torch.int32, (B, ve_cap))
+        self.v_mask = dview('v_mask', torch.uint8, (B, V))
+        self.vs = dview('vs', torch.float64, (B, V, 3)) if with_vs else None
+        self.level0 = Level(E, dview('gemm', torch.int32, (B, E, 4)), dview('sides', torch.int8, (B, E, 4)),
+                            dview('ec', torch.int32, (B,)))
+        self.levels = [self.level0]
+        self.cur = 0
+        self.stack = []            # PoolRecords not yet undone by MeshUnpool
+        self.records = []          # every PoolRecord of this forward, in order
+        self.version = 0
+        self._pristine = None
+        self.keep_logs = False
+        for i, m in enumerate(meshes):
+            m._attach(self, i)
+
+    # -- lookup ------------------------------------------------------------------------------------------
+    @staticmethod
+    def of(meshes, E, device):
+        """The MeshBatch the given meshes are attached to (created on first use: one upload per batch)."""
+        first = meshes[0]
+        bt = getattr(first, '_batch', None)
+        if bt is not None and bt.device == torch.device(device) and len(bt.meshes) == len(meshes) \
+                and all(getattr(m, '_batch', None) is bt and m._bi == i for i, m in enumerate(meshes)):
+            return bt
+        return MeshBatch(meshes, E, device)
+
+    def level(self, E=None):
+        lv = self.levels[self.cur]
+        return lv if E is None else lv.for_width(E)
+
+    # -- single-use handling for benchmarks ----------------------------------------------------------------
+    def snapshot(self):
+        """Keep a device copy of the carried state so the batch can be re-used (benchmarks, CUDA graphs)."""
+        a = self._offs['edges'][0]
+        self._pristine = self.blob[a:].clone()
+
+    def reset(self):
+        """Restore the state saved by snapshot(): level 0, original edges / ve / v_mask / vs."""
+        if self._pristine is None:
+            raise RuntimeError('MeshBatch.reset() without snapshot()')
+        a = self._offs['edges'][0]
+        self.blob[a:].copy_(self._pristine)
+        self.levels = [self.level0]
+        self.cur = 0
+        self.stack, self.records = [], []
+        self.version += 1
+        for m in self.meshes:
+            m.pool_count = 0
+
+    # -- pool / unpool bookkeeping -------------------------------------------------------------------------
+    def pool(self, norms, T):
+        """Run the collapse kernel for the current level; returns the PoolRecord (topology advanced)."""
+        L = _lib.lib()
+        lv = self.levels[self.cur]
+        B, E_in, dev = self.B, lv.E, self.device
+        need = L.mcnn_pool_smem_bytes(E_in, self.V, self.ve_cap, 1 if self.with_vs else 0)
+        if need > L.mcnn_pool_smem_limit():
+            raise PoolError('mesh level with %d edges / %d vertices needs %d bytes of collapse state; the on-chip '
+                            'limit is %d' % (E_in, self.V, need, L.mcnn_pool_smem_limit()))
+        nnz_cap = 3 * E_in
+        ints = torch.empty(B * (T * 4 + 1 + (T + 1) + (E_in + 1) + 2 * nnz_cap + 1), dtype=torch.int32, device=dev)
+        o = 0
+
+        def take(n, shape):
+            nonlocal o
+            t = ints[o:o + n].view(shape)
+            o += n
+            return t
+
+        gemm_out = take(B * T * 4, (B, T, 4))
+        ec_out = take(B, (B,))
+        rowptr = take(B * (T + 1), (B, T + 1))
+        colptr = take(B * (E_in + 1), (B, E_in + 1))
+        cols = take(B * nnz_cap, (B, nnz_cap))
+        rows = take(B * nnz_cap, (B, nnz_cap))
+        status = take(B, (B,))
+        sides_out = torch.empty(B, T, 4, dtype=torch.int8, device=dev)
+        occ = torch.empty(B, E_in, dtype=torch.float32, device=dev)
+        rec = PoolRecord()
+        rec.E_in, rec.T, rec.nnz_cap = E_in, T, nnz_cap
+        rec.rowptr, rec.cols, rec.colptr, rec.rows, rec.occ, rec.status = rowptr, cols, colptr, rows, occ, status
+        rec.norms = norms
+        rec.logs = None
+        rec.edge_mask = None
+        a = _lib.PoolArgs()
+        a.B, a.E_in, a.T, a.V, a.ve_cap, a.nnz_cap = B, E_in, T, self.V, self.ve_cap, nnz_cap
+        a.log_cap = 0
+        a.gemm_in, a.sides_in, a.ec_in, a.norms = lv.gemm.data_ptr(), lv.sides.data_ptr(), lv.ec.data_ptr(), norms.data_ptr()
+        a.edges, a.edges_stride = self.edges.data_ptr(), self.E0
+        a.ve_ptr, a.ve_idx, a.v_mask = self.ve_ptr.data_ptr(), self.ve_idx.data_ptr(), self.v_mask.data_ptr()
+        a.vs = self.vs.data_ptr() if self.with_vs else None
+        a.gemm_out, a.sides_out, a.ec_out = gemm_out.data_ptr(), sides_out.data_ptr(), ec_out.data_ptr()
+        a.grp_rowptr, a.grp_cols, a.grp_colptr, a.grp_rows = rowptr.data_ptr(), cols.data_ptr(), colptr.data_ptr(), rows.data_ptr()
+        a.occ, a.status = occ.data_ptr(), status.data_ptr()
+        if self.keep_logs:
+            cap = E_in
+            lg = {'npops': torch.zeros(B, dtype=torch.int32, device=dev),
+                  'pops': torch.zeros(B, cap, dtype=torch.int32, device=dev),
+                  'outcome': torch.zeros(B, cap, dtype=torch.int8, device=dev),
+                  'nunions': torch.zeros(B, dtype=torch.int32, device=dev),
+                  'unions': torch.zeros(B, cap * 8, 2, dtype=torch.int32, device=dev)}
+            rec.edge_mask = torch.zeros(B, E_in, dtype=torch.int32, device=dev)
+            a.log_cap = cap
+            a.log_npops, a.log_pops, a.log_outcome = lg['npops'].data_ptr(), lg['pops'].data_ptr(), lg['outcome'].data_ptr()
+            a.log_nunions, a.log_unions = lg['nunions'].data_ptr(), lg['unions'].data_ptr()
+            a.edge_mask_out = rec.edge_mask.data_ptr()
+            rec.logs = lg
+        with profiler.span('pool_collapse', B=B, E_in=E_in, T=T):
+            _lib.check(L.mcnn_pool_collapse(a, _lib.current_stream()), 'mcnn_pool_collapse')
+        new = Level(T, gemm_out, sides_out, ec_out)
+        rec.level_in = self.cur
+        self.levels = self.levels[:self.cur + 1] + [new]
+        self.cur += 1
+        rec.level_out = self.cur
+        self.stack.append(rec)
+        self.records.append(rec)
+        self.version += 1
+        for m in self.meshes:
+            m.pool_count += 1
+        return rec
+
+    def unroll(self):
+        """Mesh.get_groups / get_occurrences / unroll_gemm (mesh.py:176-198): pop one level."""
+        if not self.stack:
+            raise IndexError('pop from empty list')          # what history_data['groups'].pop() raises
+        rec = self.stack.pop()
+        self.cur = rec.level_in
+        self.version += 1
+        return rec
+
+    def check(self):
+        """Synchronise and raise the exception the reference would have raised inside MeshPool (deferred)."""
+        for rec in self.records:
+            st = rec.status.cpu().numpy()
+            bad = np.nonzero(st)[0]
+            if len(bad):
+                exc, msg = _STATUS_EXC.get(int(st[bad[0]]), (PoolError, 'status %d' % int(st[bad[0]])))
+                raise exc('MeshPool, mesh %d of the batch (%s): %s' % (int(bad[0]), self.meshes[int(bad[0])].filename, msg))
+
+    # -- host mirrors ----------------------------------------------------------------------------------------
+    def download(self, i):
+        """Current device state of mesh i as the reference's host attributes."""
+        self.check()
+        lv = self.levels[self.cur]
+        n = int(lv.ec[i].item())
+        out = {'edges_count': n, 'gemm_edges': lv.gemm[i, :n].cpu().numpy().astype(np.int64)}
+        # sides / edges / ve / v_mask / vs follow the most recent pool (they are not restored by unroll_gemm)
+        deep = self.levels[-1]
+        nd = int(deep.ec[i].item())
+        out['sides'] = deep.sides[i, :nd].cpu().numpy().astype(np.int64)
+        out['edges'] = self.edges[i, :nd].cpu().numpy().astype(np.int32)
+        nv = len(self.meshes[i]._h['vs'])
+        ptr = self.ve_ptr[i, :nv + 1].cpu().numpy()
+        out['ve_off'] = ptr.astype(np.int32)
+        out['ve_flat'] = self.ve_idx[i, :int(ptr[-1])].cpu().numpy().astype(np.int32)
+        out['v_mask'] = self.v_mask[i, :nv].cpu().numpy().astype(bool)
+        if self.with_vs:
+            out['vs'] = self.vs[i, :nv].cpu().numpy()
+        return out
+
+
+def _flatten_ve(lists):
+    off = np.zeros(len(lists) + 1, dtype=np.int32)
+    if len(lists):
+        off[1:] = np.cumsum([len(l) for l in lists])
+    flat = np.fromiter((e for l in lists for e in l), dtype=np.int32, count=int(off[-1]))
+    return flat, off
+
+
+class Mesh:
+    """Drop-in for models/layers/mesh.py:Mesh (host side)."""
+
+    _MIRRORED = ('gemm_edges', 'sides', 'edges', 'v_mask', 'vs', 'edges_count')
+
+    def __init__(self, file=None, opt=None, hold_history=False, export_folder='', data=None):
+        if data is None:
+            if file is None:
+                raise ValueError('Mesh needs an .obj file or prepared data')
+            data = mesh_prepare.from_obj(file)
+        self._h = {'vs': np.array(data.vs, dtype=np.float64), 'v_mask': np.array(data.v_mask, dtype=bool),
+                   'edges': np.array(data.edges, dtype=np.int32), 'gemm_edges': np.array(data.gemm_edges, dtype=np.int64),
+                   'sides': np.array(data.sides, dtype=np.int64), 'edges_count': int(data.edges_count)}
+        self._h['ve_flat'], self._h['ve_off'] = _flatten_ve(data.ve)
+        self.filename = data.filename
+        self.features = data.features
+        self.edge_areas = data.edge_areas
+        self.edge_lengths = data.edge_lengths
+        self.pool_count = 0
+        self.export_folder = export_folder
+        self.history_data = None
+        self._batch, self._bi, self._seen = None, -1, -1
+        if hold_history:
+            self.init_history()
+
+    # ---- device link -------------------------------------------------------------------------------------
+    def _attach(self, batch, i):
+        self._batch, self._bi, self._seen = batch, i, batch.version
+
+    def _sync(self):
+        bt = self._batch
+        if bt is not None and self._seen != bt.version:
+            self._h.update(bt.download(self._bi))
+            self._seen = bt.version
+
+    def _host_state(self):
+        self._sync()
+        return self._h
+
+    def __getstate__(self):
+        self._sync()
+        d = dict(self.__dict__)
+        d['_batch'], d['_bi'], d['_seen'] = None, -1, -1
+        return d
+
+    # ---- reference API -------------------------------------------------------------------------------------
+    @property
+    def ve(self):
+        """vertex -> incident edge ids as a list of lists (mesh_prepare.py:142-143); stored flat (CSR) internally so
+        that a batch can be packed for upload without touching Python lists."""
+        self._sync()
+        flat, off = self._h['ve_flat'], self._h['ve_off']
+        return [flat[off[v]:off[v + 1]].tolist() for v in range(len(off) - 1)]
+
+    @ve.setter
+    def ve(self, lists):
+        self._sync()
+        self._h['ve_flat'], self._h['ve_off'] = _flatten_ve(lists)
+
+    def extract_features(self):                      # mesh.py:23-24
+        return self.features
+
+    def get_edge_areas(self):                        # mesh.py:200-201
+        return self.edge_areas
+
+    def init_history(self):                          # mesh.py:151-162 (the unpool-relevant part lives on the device)
+        self.history_data = {'groups': [], 'gemm_edges': [self._h['gemm_edges'].copy()], 'occurrences': [],
+                             'edges_count': [self._h['edges_count']]}
+
+    def export(self, file=None, vcolor=None):
+        raise NotImplementedError('OBJ export (mesh.py:74-98) is outside the hot path; see DESIGN.md "out of scope"')
+
+
+def _mirror(name):
+    def get(self):
+        self._sync()
+        return self._h[name]
+
+    def set_(self, v):
+        self._sync()
+        self._h[name] = v
+    return property(get, set_)
+
+
+for _n in Mesh._MIRRORED:
+    setattr(Mesh, _n, _mirror(_n))

@@ -1,0 +1,36 @@
+"""Drop-in for models/layers/mesh_conv.py: same constructor, same ``conv`` sub-module (so checkpoints load,
+SURVEY F17), same call signature and output shape -- the work is one fused CUDA kernel instead of
+pad_gemm + create_GeMM + Conv2d."""
+import torch
+import torch.nn as nn
+
+from .functional import MeshConvFn
+from .layout import as_bce1, to_edge_major
+from .mesh import MeshBatch
+
+
+class MeshConv(nn.Module):
+    """Convolution between an edge and its 4 one-ring neighbours (mesh_conv.py:5-26).
+    x: [B, Cin, E] or [B, Cin, E, 1];  mesh: sequence of B Mesh objects;  returns [B, Cout, E, 1]."""
+
+    def __init__(self, in_channels, out_channels, k=5, bias=True):
+        super(MeshConv, self).__init__()
+        if k != 5:
+            raise NotImplementedError('the one-ring has 4 neighbours: k must be 5 (mesh_conv.py:12-15)')
+        # parameter container only (weight [Cout, Cin, 1, 5], bias [Cout]); its forward is never called
+        self.conv = nn.Conv2d(in_channels=in_channels, out_channels=out_channels, kernel_size=(1, k), bias=bias)
+        self.k = k
+        self._wt_ws = None
+
+    def __call__(self, edge_f, mesh):
+        return self.forward(edge_f, mesh)
+
+    def forward(self, x, mesh):
+        return as_bce1(self.forward_em(to_edge_major(x), MeshBatch.of(mesh, x.shape[2], x.device)))
+
+    def forward_em(self, x_em, batch):
+        """Edge-major entry used by meshcnn_b200.networks: [B, E, Cin] -> [B, E, Cout]."""
+        w = self.conv.weight
+        if self._wt_ws is None or self._wt_ws.device != x_em.device:
+            self._wt_ws = torch.empty(w.shape[1] * 5, w.shape[0], dtype=torch.float32, device=x_em.device)
+        return MeshConvFn.apply(x_em, w, self.conv.bias, batch.level(x_em.shape[1]), self._wt_ws)

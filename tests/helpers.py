@@ -41,3 +41,11 @@ def rel_err(a, b):
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def close(a, b, rtol, atol=0.0):
+    """max|a-b| <= rtol * max|b| + atol  (a norm-wise relative check; atol absorbs gradients that are
+    mathematically zero, e.g. a conv bias feeding an InstanceNorm)."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max()) <= rtol * float(np.abs(b).max()) + atol

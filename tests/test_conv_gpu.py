@@ -1,0 +1,92 @@
+"""MeshConv CUDA path (through the C ABI) vs the reference-generated golden vectors and vs the oracle.
+Tolerance: 1e-4 relative, norm-wise (BASELINE.json north_star, fp32)."""
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import close, golden, golden_names, prepared
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-4
+
+
+@pytest.mark.parametrize('name', golden_names('conv_'))
+def test_conv_golden(name):
+    from meshcnn_b200.mesh_conv import MeshConv
+    from tests.gpu_util import DEV, cuda, product_mesh
+    d = golden(name)
+    B = int(d['B'])
+    meshes = [product_mesh(d['M%d_vs0' % i], d['M%d_faces' % i]) for i in range(B)]
+    cout, cin = d['w'].shape[:2]
+    conv = MeshConv(cin, cout, bias='b' in d.files).to(DEV)
+    with torch.no_grad():
+        conv.conv.weight.copy_(cuda(d['w']))
+        if 'b' in d.files:
+            conv.conv.bias.copy_(cuda(d['b']))
+    x = cuda(d['x']).requires_grad_(True)
+    y = conv(x, meshes)
+    assert tuple(y.shape) == d['y'].shape
+    assert close(y.detach().cpu().numpy(), d['y'], RTOL)
+    y.backward(cuda(d['dy']))
+    assert close(x.grad.cpu().numpy(), d['dx'], RTOL)
+    assert close(conv.conv.weight.grad.cpu().numpy(), d['dw'], RTOL)
+    if 'b' in d.files:
+        assert close(conv.conv.bias.grad.cpu().numpy(), d['db'], RTOL)
+
+
+@pytest.mark.parametrize('cin,cout,bias', [(5, 64, False), (64, 64, False), (128, 256, True), (32, 8, True), (7, 9, True)])
+def test_conv_vs_oracle_random(cin, cout, bias):
+    """Config-sized layers on a mixed batch (closed meshes, one open mesh, short meshes -> padded slots)."""
+    from oracle import meshcnn_oracle as O
+    from meshcnn_b200 import synth
+    from meshcnn_b200.mesh_conv import MeshConv
+    from tests.gpu_util import DEV, cuda, product_mesh
+    specs = [('ico', dict(nu=5), 0), ('torus', dict(m=10, n=25), 1), ('grid', dict(m=12, n=14), 2), ('ico', dict(nu=4), 3)]
+    E = 750
+    rs = np.random.RandomState(cin * 1000 + cout)
+    prods, oracles = [], []
+    for kind, kw, seed in specs:
+        vs, faces = synth.make(kind, seed, **kw)
+        prods.append(product_mesh(vs, faces))
+        oracles.append(O.OracleMesh(prepared(vs, faces)))
+    B = len(prods)
+    xh = rs.randn(B, cin, E).astype(np.float32)
+    wh = (rs.randn(cout, cin, 1, 5) / np.sqrt(5 * cin)).astype(np.float32)
+    bh = rs.randn(cout).astype(np.float32) if bias else None
+    dyh = rs.randn(B, cout, E, 1).astype(np.float32)
+    xo = torch.from_numpy(xh).requires_grad_(True)
+    wo = torch.from_numpy(wh).requires_grad_(True)
+    bo = torch.from_numpy(bh).requires_grad_(True) if bias else None
+    yo = O.conv_forward(xo, oracles, wo, bo)
+    yo.backward(torch.from_numpy(dyh))
+    conv = MeshConv(cin, cout, bias=bias).to(DEV)
+    with torch.no_grad():
+        conv.conv.weight.copy_(cuda(wh))
+        if bias:
+            conv.conv.bias.copy_(cuda(bh))
+    x = cuda(xh).requires_grad_(True)
+    y = conv(x, prods)
+    y.backward(cuda(dyh))
+    assert close(y.detach().cpu().numpy(), yo.detach().numpy(), RTOL)
+    assert close(x.grad.cpu().numpy(), xo.grad.numpy(), RTOL)
+    assert close(conv.conv.weight.grad.cpu().numpy(), wo.grad.numpy(), RTOL)
+    if bias:
+        assert close(conv.conv.bias.grad.cpu().numpy(), bo.grad.numpy(), RTOL)
+    # gradients on padded slots are exactly zero
+    for b, m in enumerate(oracles):
+        assert float(x.grad[b, :, m.edges_count:].abs().max().item() if m.edges_count < E else 0.0) == 0.0
+
+
+def test_conv_linearity_full_size():
+    """Size-independent property at the bench configuration (B=64, 750 edges): conv(a x1 + x2) == a conv(x1) + conv(x2)
+    does NOT hold (|.| is not linear) but conv is positively homogeneous: conv(a x) = a conv(x) for a > 0, bias-free."""
+    from meshcnn_b200 import synth
+    from meshcnn_b200.mesh_conv import MeshConv
+    from tests.gpu_util import DEV, product_mesh
+    meshes = [product_mesh(*synth.make('ico', s, nu=5)) for s in range(64)]
+    conv = MeshConv(64, 128, bias=False).to(DEV)
+    x = torch.randn(64, 64, 750, device=DEV)
+    y1 = conv(x, meshes)
+    y2 = conv(2.5 * x, meshes)
+    assert torch.allclose(2.5 * y1, y2, rtol=1e-5, atol=1e-5)
+    assert y1.shape == (64, 128, 750, 1)
