@@ -1,0 +1,399 @@
+"""Benchmark of the MeshCNN per-edge hot path on B200 (contract: see the task statement / DESIGN.md "Measurement").
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config cubes|shrec|humanseg] [--impl ours|reference]
+
+One "step" = one full training step (zero_grad, forward incl. every MeshConv / MeshPool / MeshUnpool, loss, backward,
+gradient allreduce when N > 1, Adam) over one batch of synthetic meshes.  Default workload = BASELINE.json configs[1]
+(cubes: 64 x 750-edge meshes per GPU, ncf 64/128/256/256, pool_res 600/450/300/210, GroupNorm(16), resblocks 1).
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # BASELINE.json configs[1]; scripts/cubes/train.sh of the reference
+    'cubes': dict(arch='mconvnet', ncf=[64, 128, 256, 256], pool_res=[600, 450, 300, 210], E=750, B=64, nclasses=22,
+                  resblocks=1, fc_n=100, groups=16, lr=2e-4, mesh=('ico', dict(nu=5)), mesh2=('torus', dict(m=10, n=25))),
+    # configs[0]; scripts/shrec/train.sh
+    'shrec': dict(arch='mconvnet', ncf=[64, 128, 256, 256], pool_res=[600, 450, 300, 180], E=750, B=16, nclasses=30,
+                  resblocks=1, fc_n=100, groups=16, lr=2e-4, mesh=('ico', dict(nu=5)), mesh2=('torus', dict(m=10, n=25))),
+    # configs[2]; scripts/human_seg/train.sh
+    'humanseg': dict(arch='meshunet', ncf=[32, 64, 128, 256], pool_res=[1800, 1350, 600], E=2280, B=12, nclasses=8,
+                     resblocks=3, lr=1e-3, mesh=('torus', dict(m=20, n=38)), mesh2=('torus', dict(m=20, n=38))),
+    # configs[3]; scripts/coseg_seg/train.sh
+    'coseg': dict(arch='meshunet', ncf=[32, 64, 128, 256], pool_res=[1800, 1350, 600], E=2280, B=32, nclasses=4,
+                  resblocks=3, lr=1e-3, mesh=('torus', dict(m=20, n=38)), mesh2=('torus', dict(m=20, n=38))),
+}
+
+
+def make_inputs(cfg, B, first_seed):
+    """Synthetic manifold meshes -> prepared data, standardised fp32 features [B, 5, E], labels."""
+    from meshcnn_b200 import mesh_prepare, synth
+    datas = []
+    for i in range(B):
+        s = first_seed + i
+        kind, kw = cfg['mesh'] if s % 2 == 0 else cfg['mesh2']
+        vs, faces = synth.make(kind, s, **kw)
+        datas.append(mesh_prepare.from_arrays(vs, faces, filename='%s_%d.obj' % (kind, s)))
+    E = cfg['E']
+    x = np.zeros((B, 5, E), dtype=np.float64)
+    for i, d in enumerate(datas):
+        x[i, :, :d.edges_count] = d.features
+    mean = x.mean(axis=(0, 2), keepdims=True)
+    std = x.std(axis=(0, 2), keepdims=True)
+    x = ((x - mean) / std).astype(np.float32)
+    rs = np.random.RandomState(first_seed)
+    if cfg['arch'] == 'mconvnet':
+        labels = rs.randint(0, cfg['nclasses'], size=(B,)).astype(np.int64)
+    else:
+        labels = rs.randint(0, cfg['nclasses'], size=(B, E)).astype(np.int64)
+        for i, d in enumerate(datas):
+            labels[i, d.edges_count:] = -1
+    return datas, x, labels
+
+
+def build_net(cfg, impl):
+    torch.manual_seed(0)
+    if impl == 'ours':
+        from meshcnn_b200 import networks as N
+        if cfg['arch'] == 'mconvnet':
+            net = N.MeshConvNet(N.get_norm_layer('group', cfg['groups']), 5, cfg['ncf'], cfg['nclasses'], cfg['E'],
+                                cfg['pool_res'], cfg['fc_n'], cfg['resblocks'])
+        else:
+            net = N.MeshEncoderDecoder([cfg['E']] + cfg['pool_res'], [5] + cfg['ncf'], cfg['ncf'][::-1] + [cfg['nclasses']],
+                                       blocks=cfg['resblocks'], transfer_data=True)
+        N.init_weights(net, 'normal', 0.02)
+    else:
+        import functools
+        from oracle import networks_oracle as ON
+        from meshcnn_b200.networks import init_weights
+        if cfg['arch'] == 'mconvnet':
+            net = ON.OMeshConvNet(functools.partial(torch.nn.GroupNorm, cfg['groups']), 5, cfg['ncf'], cfg['nclasses'],
+                                  cfg['E'], cfg['pool_res'], cfg['fc_n'], cfg['resblocks'], dense=True)
+        else:
+            net = ON.OMeshEncoderDecoder([cfg['E']] + cfg['pool_res'], [5] + cfg['ncf'], cfg['ncf'][::-1] + [cfg['nclasses']],
+                                         blocks=cfg['resblocks'], dense=True)
+        init_weights(net, 'normal', 0.02)
+    return net
+
+
+def loss_fn_for(cfg):
+    return torch.nn.CrossEntropyLoss() if cfg['arch'] == 'mconvnet' else torch.nn.CrossEntropyLoss(ignore_index=-1)
+
+
+# -----------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's algorithm (dense MeshUnion, per-mesh Python collapse, torch-CPU conv)
+# -----------------------------------------------------------------------------------------------------------------
+def cpu_port_meshes_per_s(cfg, sample_B, steps, warmup):
+    from oracle import meshcnn_oracle as O
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    datas, x, labels = make_inputs(cfg, sample_B, 0)
+    net = build_net(cfg, 'reference').train()
+    opt = torch.optim.Adam(net.parameters(), lr=cfg['lr'], betas=(0.9, 0.999))
+    crit = loss_fn_for(cfg)
+    xt, lt = torch.from_numpy(x), torch.from_numpy(labels)
+    hold = cfg['arch'] == 'meshunet'
+    times = []
+    for it in range(warmup + steps):
+        meshes = [O.OracleMesh(d, hold_history=hold) for d in datas]       # fresh, outside the timed region (F11)
+        xin = xt.clone().requires_grad_(True)
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        out = net(xin, meshes)
+        loss = crit(out, lt)
+        loss.backward()
+        opt.step()
+        t1 = time.perf_counter()
+        if it >= warmup:
+            times.append(t1 - t0)
+    return sample_B * len(times) / sum(times), threads, sum(times) / len(times)
+
+
+# -----------------------------------------------------------------------------------------------------------------
+# helpers
+# -----------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+            'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(['nvidia-smi', '--query-gpu=' + self.QUERY, '--format=csv,noheader,nounits', '-lms', '100',
+                                       '-i', str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except Exception:
+            self.p.kill()
+            out = ''
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for line in out.strip().splitlines():
+            f = [t.strip() for t in line.split(',')]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+def algorithmic_bytes(name, m):
+    """SURVEY.md §8(d) per-launch algorithmic bytes (fp32 activations, int32 neighbour ids); see DESIGN.md."""
+    if name == 'meshconv_fwd':
+        return m['B'] * m['E'] * (4 * m['Cin'] + 4 * m['Cout'] + 16) + 4 * (5 * m['Cin'] * m['Cout'] + m['Cout'])
+    if name == 'meshconv_bwd_data':
+        return m['B'] * m['E'] * (4 * m['Cout'] + 8 * m['Cin'] + 16) + 20 * m['Cin'] * m['Cout']
+    if name == 'meshconv_bwd_weight':
+        return m['B'] * m['E'] * (4 * m['Cout'] + 4 * m['Cin'] + 16) + 20 * m['Cin'] * m['Cout']
+    if name == 'pool_collapse':
+        return 28 * m['B'] * (m['E_in'] + m['T'])
+    return 0
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+# -----------------------------------------------------------------------------------------------------------------
+def run_reference(args, cfg, rank, world):
+    """--impl reference: the reference's CPU algorithm (oracle port; the reference itself is Python and is not on
+    the GPU box) on a bounded sample of the same workload.  Rank 0 only."""
+    if rank != 0:
+        return
+    sample_B = min(cfg['B'], 16 if cfg['E'] <= 750 else 6)
+    v, threads, sec = cpu_port_meshes_per_s(cfg, sample_B, max(1, args.steps), max(0, args.warmup))
+    line = {'impl': 'reference', 'metric': 'train meshes/sec (fwd+bwd+pool)', 'value': v, 'unit': 'meshes/s', 'n_gpus': args.gpus,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': workload_name(args.config, cfg), 'sample': '%d meshes per step' % sample_B},
+            'cpu_baseline': {'value': v, 'unit': 'meshes/s', 'cores': threads, 'kind': 'port',
+                             'sample': '%d steps of %d meshes (of %d per batch); oracle port with the reference\'s dense MeshUnion '
+                                       'and op sequence, %d torch threads; the collapse loop is single-threaded Python as in the '
+                                       'reference' % (args.steps, sample_B, cfg['B'], threads)},
+            'e2e': {'value': v, 'unit': 'meshes/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line))
+
+
+def workload_name(name, cfg):
+    if cfg['arch'] == 'mconvnet':
+        return '%s: MeshConvNet ncf %s pool_res %s, %d-edge meshes, batch %d per GPU, GroupNorm(%d), resblocks %d' % (
+            name, '/'.join(map(str, cfg['ncf'])), '/'.join(map(str, cfg['pool_res'])), cfg['E'], cfg['B'], cfg['groups'], cfg['resblocks'])
+    return '%s: MeshEncoderDecoder ncf %s pool_res %s, %d-edge meshes, batch %d per GPU, resblocks %d' % (
+        name, '/'.join(map(str, cfg['ncf'])), '/'.join(map(str, cfg['pool_res'])), cfg['E'], cfg['B'], cfg['resblocks'])
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--config', default='cubes', choices=sorted(CONFIGS))
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--batch', type=int, default=0, help='override the per-GPU batch size')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    args = ap.parse_args()
+    cfg = dict(CONFIGS[args.config])
+    if args.batch:
+        cfg['B'] = args.batch
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.impl == 'reference':
+        run_reference(args, cfg, rank, world)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import torch.distributed as dist
+    from meshcnn_b200 import _lib, ddp, profiler
+    from meshcnn_b200.mesh import Mesh, MeshBatch
+
+    dev = torch.device('cuda', local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+    B, E = cfg['B'], cfg['E']
+    datas, x, labels = make_inputs(cfg, B, rank * B)
+    net = build_net(cfg, 'ours').to(dev).train()
+    if world > 1:
+        ddp.broadcast_parameters(net)
+    reducer = ddp.FlatGradReducer(net)                                  # grads are views into one flat buffer
+    opt = torch.optim.Adam(net.parameters(), lr=cfg['lr'], betas=(0.9, 0.999))
+    crit = loss_fn_for(cfg)
+    hold = cfg['arch'] == 'meshunet'
+
+    # ---- device-resident arm ---------------------------------------------------------------------------------------
+    meshes = [Mesh(data=d, hold_history=hold) for d in datas]
+    batch = MeshBatch(meshes, E, dev)
+    batch.snapshot()
+    x_dev = torch.from_numpy(x).to(dev).requires_grad_(True)           # the reference trains with requires_grad inputs
+    y_dev = torch.from_numpy(labels).to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def step():
+        batch.reset()
+        reducer.zero()
+        x_dev.grad = None
+        out = net(x_dev, meshes)
+        loss = crit(out, y_dev)
+        loss.backward()
+        reducer.allreduce()
+        opt.step()
+        return loss
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    batch.check()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local) if rank == 0 else None
+    profiler.enabled = True
+    profiler.reset()
+    launches0 = _lib.launch_count()
+    evs = []
+    for _ in range(args.steps):
+        flush.fill_(1)                                                  # L2 flush between timed steps (not timed)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        step()
+        b.record()
+        evs.append((a, b))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches = _lib.launch_count() - launches0
+    profiler.enabled = False
+    recs = profiler.collect()
+    clocks = sampler.stop() if sampler is not None else None
+    batch.check()
+    total_ms = sum(a.elapsed_time(b) for a, b in evs)
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    value = world * B * args.steps / (total_ms / 1e3)
+
+    # ---- end-to-end arm: host buffers in, loss out, every step ------------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        x_pin = torch.from_numpy(x).pin_memory()
+        y_pin = torch.from_numpy(labels).pin_memory()
+        k_e2e = args.steps
+        fresh = [[Mesh(data=d, hold_history=hold) for d in datas] for _ in range(k_e2e + 2)]   # the data loader's job (F11/F12)
+        h2d = 0
+
+        def e2e_step(ms):
+            nonlocal h2d
+            bt = MeshBatch(ms, E, dev)                                   # packs + uploads the topology blob (pinned)
+            xin = x_pin.to(dev, non_blocking=True).requires_grad_(True)
+            yin = y_pin.to(dev, non_blocking=True)
+            h2d = bt.blob.numel() + x_pin.numel() * 4 + y_pin.numel() * 8
+            reducer.zero()
+            out = net(xin, ms)
+            loss = crit(out, yin)
+            loss.backward()
+            reducer.allreduce()
+            opt.step()
+            return float(loss.item())                                    # D2H read of the step's result
+
+        for i in range(2):
+            e2e_step(fresh[i])
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for i in range(k_e2e):
+            e2e_step(fresh[2 + i])
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e = {'value': world * B * k_e2e / float(t.item()), 'unit': 'meshes/s', 'h2d_bytes_per_step': int(h2d),
+               'd2h_bytes_per_step': 4, 'timing': 'host wall clock between device synchronisations, max over ranks'}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (live CUDA-event timings collected inside the timed steps) ----------------
+    agg = {}
+    for name, meta, ms in recs:
+        key = (name, tuple(sorted(meta.items())))
+        tot, cnt = agg.get(key, (0.0, 0))
+        agg[key] = (tot + ms, cnt + 1)
+    by_kernel = {}
+    for (name, meta), (tot, cnt) in agg.items():
+        by_kernel[name] = by_kernel.get(name, 0.0) + tot
+    peak, peak_src = peaks()
+    roofline = None
+    if agg:
+        top_name = max(by_kernel, key=by_kernel.get)
+        (name, meta), (tot, cnt) = max(((k, v) for k, v in agg.items() if k[0] == top_name), key=lambda kv: kv[1][0])
+        m = dict(meta)
+        nbytes = algorithmic_bytes(name, m)
+        avg_ms = tot / cnt
+        ach = nbytes / (avg_ms * 1e-3) / 1e9
+        roofline = {'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak, 'traffic': None,
+                    'kernel': name, 'shape': m, 'avg_launch_ms': avg_ms, 'algorithmic_bytes': nbytes, 'peak_source': peak_src,
+                    'share_of_step': {k: v / total_ms for k, v in sorted(by_kernel.items())}}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        sample_B = min(B, 16 if E <= 750 else 6)
+        v, threads, sec = cpu_port_meshes_per_s(cfg, sample_B, 2, 1)
+        cpu = {'value': v, 'unit': 'meshes/s', 'cores': threads, 'kind': 'port',
+               'sample': '2 timed steps (+1 warm-up) of %d meshes of the same workload; oracle port with the reference\'s dense '
+                         'MeshUnion and op sequence; %.2f s/step' % (sample_B, sec)}
+
+    line = {'metric': 'train meshes/sec (fwd+bwd+pool)', 'value': value, 'unit': 'meshes/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': total_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': workload_name(args.config, cfg), 'global_batch': world * B,
+                       'parallelism': 'dp%d (meshes sharded, one flat NCCL gradient allreduce)' % world,
+                       'l2': 'flushed between timed steps (256 MiB write, untimed); per-step CUDA events, max over ranks',
+                       'optimizer': 'Adam (in the timed region)'},
+            'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()
