@@ -73,6 +73,13 @@ const char* mcnn_last_cuda_error(void);
 int mcnn_meshconv_fwd(const float* x, const int32_t* gemm, const int32_t* ec, const float* weight,
                       const float* bias, float* out, float* wt_ws, int B, int E, int Cin, int Cout, void* stream);
 
+/* Same contract as mcnn_meshconv_fwd, computed on the tensor cores (tcgen05.mma kind::tf32 with the 3xTF32 split, fp32
+ * accumulation in TMEM; results agree with the FFMA path to ~1e-6 relative).  Only for shapes where
+ * mcnn_meshconv_tc_supported(Cin, Cout) != 0 (Cin % 32 == 0, Cout % 64 == 0); wt_ws as above. */
+int mcnn_meshconv_tc_supported(int Cin, int Cout);
+int mcnn_meshconv_fwd_tc(const float* x, const int32_t* gemm, const int32_t* ec, const float* weight,
+                         const float* bias, float* out, float* wt_ws, int B, int E, int Cin, int Cout, void* stream);
+
 /* dx of the above (autograd of mesh_conv.py:47-69: conv2d dgrad, abs/add backward, index_select scatter).
  *   dout [B][E][Cout]   dx [B][E][Cin]  -- must be ZERO on entry (the kernel accumulates with red.global) */
 int mcnn_meshconv_bwd_data(const float* dout, const float* x, const int32_t* gemm, const int32_t* ec,

@@ -35,6 +35,8 @@ SIGNATURES = {
     'mcnn_launch_count': (ctypes.c_ulonglong, []),
     'mcnn_last_cuda_error': (ctypes.c_char_p, []),
     'mcnn_meshconv_fwd': (_c_int, [_c_vp] * 7 + [_c_int] * 4 + [_c_vp]),
+    'mcnn_meshconv_tc_supported': (_c_int, [_c_int, _c_int]),
+    'mcnn_meshconv_fwd_tc': (_c_int, [_c_vp] * 7 + [_c_int] * 4 + [_c_vp]),
     'mcnn_meshconv_bwd_data': (_c_int, [_c_vp] * 6 + [_c_int] * 4 + [_c_vp]),
     'mcnn_meshconv_bwd_weight': (_c_int, [_c_vp] * 6 + [_c_int] * 4 + [_c_vp]),
     'mcnn_pool_norms': (_c_int, [_c_vp, _c_vp, _c_int, _c_int, _c_int, _c_vp]),

@@ -1,9 +1,14 @@
 """autograd.Function wrappers over the C ABI.  All tensors here are edge-major [B, E, C] fp32 on a CUDA device;
 every call enqueues on the current stream and never synchronises."""
+import os
+
 import torch
 
 from . import _lib
 from . import profiler
+
+# tensor-core (tcgen05, 3xTF32) path for the layers that are real dense GEMMs; MESHCNN_B200_TC=0 forces the FFMA path
+USE_TC = os.environ.get('MESHCNN_B200_TC', '1') != '0'
 
 
 def _chk_cuda(*ts):
@@ -24,8 +29,10 @@ class MeshConvFn(torch.autograd.Function):
         w = weight.contiguous()
         out = torch.empty(B, E, Cout, dtype=torch.float32, device=x.device)
         L = _lib.lib()
-        with profiler.span('meshconv_fwd', B=B, E=E, Cin=Cin, Cout=Cout):
-            _lib.check(L.mcnn_meshconv_fwd(x.data_ptr(), level.gemm.data_ptr(), level.ec.data_ptr(), w.data_ptr(),
+        use_tc = USE_TC and L.mcnn_meshconv_tc_supported(Cin, Cout)
+        fwd = L.mcnn_meshconv_fwd_tc if use_tc else L.mcnn_meshconv_fwd
+        with profiler.span('meshconv_fwd_tc' if use_tc else 'meshconv_fwd', B=B, E=E, Cin=Cin, Cout=Cout):
+            _lib.check(fwd(x.data_ptr(), level.gemm.data_ptr(), level.ec.data_ptr(), w.data_ptr(),
                                            _lib.ptr(bias), out.data_ptr(), wt_ws.data_ptr(), B, E, Cin, Cout,
                                            _lib.current_stream()), 'mcnn_meshconv_fwd')
         ctx.save_for_backward(x, w)

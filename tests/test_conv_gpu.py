@@ -34,7 +34,8 @@ def test_conv_golden(name):
         assert close(conv.conv.bias.grad.cpu().numpy(), d['db'], RTOL)
 
 
-@pytest.mark.parametrize('cin,cout,bias', [(5, 64, False), (64, 64, False), (128, 256, True), (32, 8, True), (7, 9, True)])
+@pytest.mark.parametrize('cin,cout,bias', [(5, 64, False), (64, 64, False), (128, 256, True), (32, 8, True), (7, 9, True),
+                                           (256, 256, False), (64, 128, True), (32, 64, True)])
 def test_conv_vs_oracle_random(cin, cout, bias):
     """Config-sized layers on a mixed batch (closed meshes, one open mesh, short meshes -> padded slots)."""
     from oracle import meshcnn_oracle as O
@@ -90,3 +91,25 @@ def test_conv_linearity_full_size():
     y2 = conv(2.5 * x, meshes)
     assert torch.allclose(2.5 * y1, y2, rtol=1e-5, atol=1e-5)
     assert y1.shape == (64, 128, 750, 1)
+
+
+@pytest.mark.parametrize('cin,cout', [(64, 64), (128, 128), (256, 256), (128, 256)])
+def test_conv_tensor_core_path_matches_ffma_path(cin, cout):
+    """tcgen05 3xTF32 forward vs the exact-fp32 FFMA forward on a bench-sized batch: <= 3e-5 relative (both sides carry their own ~1e-6 rounding at K = 1280)."""
+    from meshcnn_b200 import functional as Fn
+    from meshcnn_b200 import synth
+    from meshcnn_b200.mesh_conv import MeshConv
+    from tests.gpu_util import DEV, product_mesh
+    B = 24
+    meshes = [product_mesh(*synth.make('ico' if s % 3 else 'torus', s, **(dict(nu=5) if s % 3 else dict(m=10, n=25)))) for s in range(B)]
+    torch.manual_seed(cin + cout)
+    conv = MeshConv(cin, cout, bias=True).to(DEV)
+    x = torch.randn(B, cin, 750, device=DEV)
+    assert Fn.USE_TC
+    y_tc = conv(x, meshes)
+    Fn.USE_TC = False
+    try:
+        y_ff = conv(x, meshes)
+    finally:
+        Fn.USE_TC = True
+    assert close(y_tc.detach().cpu().numpy(), y_ff.detach().cpu().numpy(), 3e-5)
