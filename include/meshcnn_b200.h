@@ -89,6 +89,19 @@ int mcnn_meshconv_bwd_data(const float* dout, const float* x, const int32_t* gem
 int mcnn_meshconv_bwd_weight(const float* dout, const float* x, const int32_t* gemm, const int32_t* ec,
                              float* dweight, float* dbias, int B, int E, int Cin, int Cout, void* stream);
 
+/* Tensor-core versions of the two backward kernels (tcgen05.mma kind::tf32, 3xTF32 split, TMEM accumulators).
+ *   bwd_data_tc  : Cin % 32 == 0 and Cout % 32 == 0; dx must be ZERO on entry (red.global.add.v4.f32 scatter);
+ *                  wtb_ws [5*Cin][Cout] scratch for the re-laid weight
+ *   bwd_weight_tc: Cin % 32 == 0 and Cout % 4 == 0; dweight / dbias are OVERWRITTEN (slab partials are written to
+ *                  `ws` and reduced by a second kernel: deterministic, no atomics); ws holds
+ *                  mcnn_meshconv_bwd_weight_tc_ws(B, E, Cin, Cout) floats */
+int mcnn_meshconv_bwd_data_tc(const float* dout, const float* x, const int32_t* gemm, const int32_t* ec,
+                              const float* weight, float* dx, float* wtb_ws, int B, int E, int Cin, int Cout,
+                              void* stream);
+size_t mcnn_meshconv_bwd_weight_tc_ws(int B, int E, int Cin, int Cout);
+int mcnn_meshconv_bwd_weight_tc(const float* dout, const float* x, const int32_t* gemm, const int32_t* ec,
+                                float* dweight, float* dbias, float* ws, int B, int E, int Cin, int Cout, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * MeshPool / MeshUnion / Mesh.clean  (models/layers/mesh_pool.py, mesh_union.py, mesh.py:26-71,151-198)
  * ------------------------------------------------------------------------------------------------------ */

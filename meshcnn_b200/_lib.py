@@ -39,6 +39,9 @@ SIGNATURES = {
     'mcnn_meshconv_fwd_tc': (_c_int, [_c_vp] * 7 + [_c_int] * 4 + [_c_vp]),
     'mcnn_meshconv_bwd_data': (_c_int, [_c_vp] * 6 + [_c_int] * 4 + [_c_vp]),
     'mcnn_meshconv_bwd_weight': (_c_int, [_c_vp] * 6 + [_c_int] * 4 + [_c_vp]),
+    'mcnn_meshconv_bwd_data_tc': (_c_int, [_c_vp] * 7 + [_c_int] * 4 + [_c_vp]),
+    'mcnn_meshconv_bwd_weight_tc_ws': (_c_sz, [_c_int] * 4),
+    'mcnn_meshconv_bwd_weight_tc': (_c_int, [_c_vp] * 7 + [_c_int] * 4 + [_c_vp]),
     'mcnn_pool_norms': (_c_int, [_c_vp, _c_vp, _c_int, _c_int, _c_int, _c_vp]),
     'mcnn_pool_collapse': (_c_int, [ctypes.POINTER(PoolArgs), _c_vp]),
     'mcnn_pool_smem_bytes': (_c_sz, [_c_int, _c_int, _c_int, _c_int]),

@@ -244,6 +244,414 @@ static int launch_fwd_tc(const float* x, const int32_t* gemm, const int32_t* ec,
     return after_launch();
 }
 
+
+// =============================================================================================================
+// backward, data:   dG[m][(k5, c)] = sum_o dout[m][o] * W[o][c][k5]   on tcgen05, then the abs/add backward and the
+// scatter-add to the gather rows in the epilogue.  One CTA = 128 edges x (5 x 32 channels) = N 160; K = Cout.
+//   A = dout rows (K-major as they lie in memory), B = weight re-laid as wtb[(cb*160 + k5*32 + cl)][o] (K-major).
+// =============================================================================================================
+constexpr int BD_N = 160;
+
+struct BdSmem {
+    static constexpr int A_BYTES = TC_M * 128;
+    static constexpr int B_BYTES = BD_N * 128;
+    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;     // 73728
+    static constexpr int STAGES = 3;
+    static constexpr int NB_OFF = STAGES * STAGE_BYTES;
+    static constexpr int BAR_OFF = NB_OFF + TC_M * 5 * 4;
+    static constexpr int TOTAL = BAR_OFF + 16 * 8 + 16 + 1024;
+};
+
+// weight [Cout][Cin][5] -> wtb[5*Cin][Cout], row = cb*160 + k5*32 + cl  (c = cb*32 + cl)
+__global__ void weight_tc_bwd_layout_kernel(const float* __restrict__ w, float* __restrict__ wtb, int Cin, int Cout) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= 5 * Cin * Cout) return;
+    const int row = idx / Cout, o = idx - row * Cout;
+    const int cb = row / BD_N, n = row - cb * BD_N;
+    const int k5 = n >> 5, c = cb * 32 + (n & 31);
+    wtb[idx] = w[((size_t)o * Cin + c) * 5 + k5];
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+meshconv_bwd_data_tc_kernel(const float* __restrict__ dout, const float* __restrict__ x, const int32_t* __restrict__ gemm,
+                            const int32_t* __restrict__ ec, const float* __restrict__ wtb, float* __restrict__ dx,
+                            int B, int E, int Cin, int Cout) {
+    using S = BdSmem;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    int (*nb)[5] = reinterpret_cast<int (*)[5]>(smem + S::NB_OFF);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
+    uint64_t* empty_bar = full_bar + S::STAGES;
+    uint64_t* accum_bar = empty_bar + S::STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int M = B * E;
+    const int m0 = blockIdx.x * TC_M, cb = blockIdx.y;
+    const int num_kb = Cout >> 5;
+
+    for (int i = tid; i < TC_M * 5; i += TC_THREADS) {
+        const int r = i / 5, k = i - r * 5;
+        const int m = m0 + r;
+        int idx = -1;
+        if (m < M) {
+            const int b = m / E, e = m - b * E;
+            if (e >= __ldg(ec + b)) idx = b * E;
+            else if (k == 0) idx = m;
+            else { const int g = __ldg(gemm + (size_t)m * 4 + (k - 1)); idx = g < 0 ? -1 : b * E + g; }
+        }
+        nb[r][k] = idx;
+    }
+    if (warp == TC_PRODUCER_WARPS) {
+        if (lane == 0) {
+            for (int s = 0; s < S::STAGES; ++s) { tc::mbar_init(full_bar + s, TC_PRODUCER_WARPS * 32); tc::mbar_init(empty_bar + s, 1); }
+            tc::mbar_init(accum_bar, 1);
+            tc::fence_barrier_init();
+        }
+        __syncwarp();
+        tc::tmem_alloc<256>(tmem_slot);
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < TC_PRODUCER_WARPS) {
+        const int pt = tid;
+        for (int kb = 0; kb < num_kb; ++kb) {
+            const int s = kb % S::STAGES;
+            const uint32_t ph = (kb / S::STAGES) & 1;
+            tc::mbar_wait(empty_bar + s, ph ^ 1);
+            unsigned char* a_hi = smem + s * S::STAGE_BYTES;
+            unsigned char* a_lo = a_hi + S::A_BYTES;
+            unsigned char* b_hi = a_lo + S::A_BYTES;
+            unsigned char* b_lo = b_hi + S::B_BYTES;
+#pragma unroll
+            for (int it = 0; it < (TC_M * 8) / 256; ++it) {
+                const int item = pt + it * 256;
+                const int r = item >> 3, q = item & 7;
+                const int m = m0 + r;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (m < M) v = __ldg(reinterpret_cast<const float4*>(dout + (size_t)m * Cout + (kb << 5) + (q << 2)));
+                float4 hi, lo;
+                tc::split4(v, hi, lo);
+                const uint32_t off = tc::sw128_off(r, q);
+                *reinterpret_cast<float4*>(a_hi + off) = hi;
+                *reinterpret_cast<float4*>(a_lo + off) = lo;
+            }
+#pragma unroll
+            for (int it = 0; it < (BD_N * 8) / 256; ++it) {
+                const int item = pt + it * 256;
+                const int r = item >> 3, q = item & 7;
+                const float4 v = __ldg(reinterpret_cast<const float4*>(wtb + (size_t)(cb * BD_N + r) * Cout + (kb << 5) + (q << 2)));
+                float4 hi, lo;
+                tc::split4(v, hi, lo);
+                const uint32_t off = tc::sw128_off(r, q);
+                *reinterpret_cast<float4*>(b_hi + off) = hi;
+                *reinterpret_cast<float4*>(b_lo + off) = lo;
+            }
+            tc::fence_proxy_async_smem();
+            tc::mbar_arrive(full_bar + s);
+        }
+        // ---- epilogue: abs/add backward + scatter ----------------------------------------------
+        tc::mbar_wait(accum_bar, 0);
+        tc::tc_fence_after();
+        const int lane_grp = warp & 3;
+        const int r = lane_grp * 32 + lane;
+        const int m = m0 + r;
+        const int cl0 = (warp >> 2) * 16;                     // the two warps of a lane group split the 32 channels
+        float g[5][16];
+#pragma unroll
+        for (int k5 = 0; k5 < 5; ++k5) tc::tmem_ld16(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(k5 * 32 + cl0), g[k5]);
+        if (m < M) {
+            const int b = m / E, e = m - b * E;
+            const int c0 = cb * 32 + cl0;
+            if (e >= __ldg(ec + b)) {
+                float* d = dx + (size_t)(b * E) * Cin + c0;
+#pragma unroll
+                for (int j = 0; j < 16; j += 4)
+                    tc::red_add_v4(d + j, g[0][j] + 2.f * (g[1][j] + g[2][j]), g[0][j + 1] + 2.f * (g[1][j + 1] + g[2][j + 1]),
+                                   g[0][j + 2] + 2.f * (g[1][j + 2] + g[2][j + 2]), g[0][j + 3] + 2.f * (g[1][j + 3] + g[2][j + 3]));
+            } else {
+                const int n1 = nb[r][1], n2 = nb[r][2], n3 = nb[r][3], n4 = nb[r][4];
+                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                    const float4 f1 = n1 >= 0 ? __ldg(reinterpret_cast<const float4*>(x + (size_t)n1 * Cin + c0 + j)) : z;
+                    const float4 f2 = n2 >= 0 ? __ldg(reinterpret_cast<const float4*>(x + (size_t)n2 * Cin + c0 + j)) : z;
+                    const float4 f3 = n3 >= 0 ? __ldg(reinterpret_cast<const float4*>(x + (size_t)n3 * Cin + c0 + j)) : z;
+                    const float4 f4 = n4 >= 0 ? __ldg(reinterpret_cast<const float4*>(x + (size_t)n4 * Cin + c0 + j)) : z;
+                    const float s13[4] = {sgn(f1.x - f3.x), sgn(f1.y - f3.y), sgn(f1.z - f3.z), sgn(f1.w - f3.w)};
+                    const float s24[4] = {sgn(f2.x - f4.x), sgn(f2.y - f4.y), sgn(f2.z - f4.z), sgn(f2.w - f4.w)};
+                    tc::red_add_v4(dx + (size_t)m * Cin + c0 + j, g[0][j], g[0][j + 1], g[0][j + 2], g[0][j + 3]);
+                    if (n1 >= 0) tc::red_add_v4(dx + (size_t)n1 * Cin + c0 + j, g[1][j] + s13[0] * g[3][j], g[1][j + 1] + s13[1] * g[3][j + 1],
+                                                g[1][j + 2] + s13[2] * g[3][j + 2], g[1][j + 3] + s13[3] * g[3][j + 3]);
+                    if (n3 >= 0) tc::red_add_v4(dx + (size_t)n3 * Cin + c0 + j, g[1][j] - s13[0] * g[3][j], g[1][j + 1] - s13[1] * g[3][j + 1],
+                                                g[1][j + 2] - s13[2] * g[3][j + 2], g[1][j + 3] - s13[3] * g[3][j + 3]);
+                    if (n2 >= 0) tc::red_add_v4(dx + (size_t)n2 * Cin + c0 + j, g[2][j] + s24[0] * g[4][j], g[2][j + 1] + s24[1] * g[4][j + 1],
+                                                g[2][j + 2] + s24[2] * g[4][j + 2], g[2][j + 3] + s24[3] * g[4][j + 3]);
+                    if (n4 >= 0) tc::red_add_v4(dx + (size_t)n4 * Cin + c0 + j, g[2][j] - s24[0] * g[4][j], g[2][j + 1] - s24[1] * g[4][j + 1],
+                                                g[2][j + 2] - s24[2] * g[4][j + 2], g[2][j + 3] - s24[3] * g[4][j + 3]);
+                }
+            }
+        }
+        tc::tc_fence_before();
+    } else {
+        constexpr uint32_t idesc = tc::make_idesc_tf32(BD_N);
+        for (int kb = 0; kb < num_kb; ++kb) {
+            const int s = kb % S::STAGES;
+            const uint32_t ph = (kb / S::STAGES) & 1;
+            tc::mbar_wait(full_bar + s, ph);
+            tc::tc_fence_after();
+            if (tc::elect_one()) {
+                const uint32_t a_hi = tc::smem_u32(smem + s * S::STAGE_BYTES);
+                const uint32_t a_lo = a_hi + S::A_BYTES;
+                const uint32_t b_hi = a_lo + S::A_BYTES;
+                const uint32_t b_lo = b_hi + S::B_BYTES;
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    const uint64_t dah = tc::make_desc_sw128(a_hi + kk * 32), dal = tc::make_desc_sw128(a_lo + kk * 32);
+                    const uint64_t dbh = tc::make_desc_sw128(b_hi + kk * 32), dbl = tc::make_desc_sw128(b_lo + kk * 32);
+                    tc::mma_tf32(tmem_base, dah, dbh, idesc, (kb | kk) != 0);
+                    tc::mma_tf32(tmem_base, dah, dbl, idesc, 1);
+                    tc::mma_tf32(tmem_base, dal, dbh, idesc, 1);
+                }
+                tc::mma_commit(empty_bar + s);
+                if (kb == num_kb - 1) tc::mma_commit(accum_bar);
+            }
+            __syncwarp();
+        }
+        tc::tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == TC_PRODUCER_WARPS) {
+        tc::tc_fence_after();
+        tc::tmem_dealloc<256>(tmem_base);
+    }
+}
+
+// =============================================================================================================
+// backward, weight:  dW[o][c][k5] = sum_m dout[m][o] * G_k5[m][c]   (reduction over all edge slots, padded ones included)
+// One CTA = 128 output channels x (5 x 32 input channels) over a slab of edges; K = edges.  Both operands are
+// MN-major exactly as they are produced: A[k=edge][o] = dout rows, B[k=edge][(k5, cl)] = G rows.  Slab partials go
+// to a workspace and are reduced by a second kernel (deterministic, no atomics).
+// =============================================================================================================
+struct BwSmem {
+    static constexpr int A_BYTES = 32 * 128 * 4;            // 32 edges x 128 o
+    static constexpr int B_BYTES = 32 * BD_N * 4;            // 32 edges x 160 cols
+    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;     // 73728
+    static constexpr int STAGES = 3;
+    static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+    static constexpr int TOTAL = BAR_OFF + 16 * 8 + 16 + 1024;
+    static constexpr uint32_t LBO = 4096;                    // 4 K-groups of 1024 bytes per M/N atom
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+meshconv_bwd_weight_tc_kernel(const float* __restrict__ dout, const float* __restrict__ x, const int32_t* __restrict__ gemm,
+                              const int32_t* __restrict__ ec, float* __restrict__ ws, int B, int E, int Cin, int Cout,
+                              int rows_per_split) {
+    using S = BwSmem;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
+    uint64_t* empty_bar = full_bar + S::STAGES;
+    uint64_t* accum_bar = empty_bar + S::STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int M = B * E;
+    const int split = blockIdx.x, o0 = blockIdx.y * 128, cb = blockIdx.z;
+    const int mbeg = split * rows_per_split, mend = min(M, mbeg + rows_per_split);
+    const int num_kb = (mend > mbeg) ? (mend - mbeg + 31) >> 5 : 0;
+
+    if (warp == TC_PRODUCER_WARPS) {
+        if (lane == 0) {
+            for (int s = 0; s < S::STAGES; ++s) { tc::mbar_init(full_bar + s, TC_PRODUCER_WARPS * 32); tc::mbar_init(empty_bar + s, 1); }
+            tc::mbar_init(accum_bar, 1);
+            tc::fence_barrier_init();
+        }
+        __syncwarp();
+        tc::tmem_alloc<256>(tmem_slot);
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < TC_PRODUCER_WARPS) {
+        const int pt = tid;
+        for (int kb = 0; kb < num_kb; ++kb) {
+            const int s = kb % S::STAGES;
+            const uint32_t ph = (kb / S::STAGES) & 1;
+            tc::mbar_wait(empty_bar + s, ph ^ 1);
+            unsigned char* a_hi = smem + s * S::STAGE_BYTES;
+            unsigned char* a_lo = a_hi + S::A_BYTES;
+            unsigned char* b_hi = a_lo + S::A_BYTES;
+            unsigned char* b_lo = b_hi + S::B_BYTES;
+            const int mb = mbeg + (kb << 5);
+            // A: dout[m][o0 + 4q .. ] for 32 edges x 32 chunks
+#pragma unroll
+            for (int it = 0; it < (32 * 32) / 256; ++it) {
+                const int item = pt + it * 256;
+                const int k = item >> 5, q = item & 31;
+                const int m = mb + k, o = o0 + (q << 2);
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (m < mend && o < Cout) v = __ldg(reinterpret_cast<const float4*>(dout + (size_t)m * Cout + o));
+                float4 hi, lo;
+                tc::split4(v, hi, lo);
+                const uint32_t off = tc::sw128_mn_off(k, q, S::LBO);
+                *reinterpret_cast<float4*>(a_hi + off) = hi;
+                *reinterpret_cast<float4*>(a_lo + off) = lo;
+            }
+            // B: G rows for 32 edges x 8 channel chunks (one item per thread)
+            {
+                const int k = pt >> 3, q = pt & 7;
+                const int m = mb + k;
+                const int c = cb * 32 + (q << 2);
+                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                float4 f0 = z, f1 = z, f2 = z, f3 = z, f4 = z;
+                if (m < mend) {
+                    const int b = m / E, e = m - b * E;
+                    int s0, s1, s2, s3, s4;
+                    if (e >= __ldg(ec + b)) { s0 = s1 = s2 = s3 = s4 = b * E; }
+                    else {
+                        const int4 g4 = __ldg(reinterpret_cast<const int4*>(gemm + (size_t)m * 4));
+                        s0 = m;
+                        s1 = g4.x < 0 ? -1 : b * E + g4.x; s2 = g4.y < 0 ? -1 : b * E + g4.y;
+                        s3 = g4.z < 0 ? -1 : b * E + g4.z; s4 = g4.w < 0 ? -1 : b * E + g4.w;
+                    }
+                    f0 = __ldg(reinterpret_cast<const float4*>(x + (size_t)s0 * Cin + c));
+                    if (s1 >= 0) f1 = __ldg(reinterpret_cast<const float4*>(x + (size_t)s1 * Cin + c));
+                    if (s2 >= 0) f2 = __ldg(reinterpret_cast<const float4*>(x + (size_t)s2 * Cin + c));
+                    if (s3 >= 0) f3 = __ldg(reinterpret_cast<const float4*>(x + (size_t)s3 * Cin + c));
+                    if (s4 >= 0) f4 = __ldg(reinterpret_cast<const float4*>(x + (size_t)s4 * Cin + c));
+                }
+                float4 gk[5];
+                gk[0] = f0;
+                gk[1] = make_float4(f1.x + f3.x, f1.y + f3.y, f1.z + f3.z, f1.w + f3.w);
+                gk[2] = make_float4(f2.x + f4.x, f2.y + f4.y, f2.z + f4.z, f2.w + f4.w);
+                gk[3] = make_float4(fabsf(f1.x - f3.x), fabsf(f1.y - f3.y), fabsf(f1.z - f3.z), fabsf(f1.w - f3.w));
+                gk[4] = make_float4(fabsf(f2.x - f4.x), fabsf(f2.y - f4.y), fabsf(f2.z - f4.z), fabsf(f2.w - f4.w));
+#pragma unroll
+                for (int k5 = 0; k5 < 5; ++k5) {
+                    float4 hi, lo;
+                    tc::split4(gk[k5], hi, lo);
+                    const uint32_t off = tc::sw128_mn_off(k, k5 * 8 + q, S::LBO);
+                    *reinterpret_cast<float4*>(b_hi + off) = hi;
+                    *reinterpret_cast<float4*>(b_lo + off) = lo;
+                }
+            }
+            tc::fence_proxy_async_smem();
+            tc::mbar_arrive(full_bar + s);
+        }
+        // ---- epilogue: slab partial -> ws[split][o][c][k5] ---------------------------------------------------------
+        const int lane_grp = warp & 3;
+        const int o = o0 + lane_grp * 32 + lane;
+        const int cl0 = (warp >> 2) * 16;
+        float g[5][16];
+        if (num_kb > 0) {
+            tc::mbar_wait(accum_bar, 0);
+            tc::tc_fence_after();
+#pragma unroll
+            for (int k5 = 0; k5 < 5; ++k5) tc::tmem_ld16(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(k5 * 32 + cl0), g[k5]);
+        } else {
+#pragma unroll
+            for (int k5 = 0; k5 < 5; ++k5)
+#pragma unroll
+                for (int j = 0; j < 16; ++j) g[k5][j] = 0.f;
+        }
+        if (o < Cout) {
+            float* dst = ws + (((size_t)split * Cout + o) * Cin + cb * 32 + cl0) * 5;      // 80 contiguous floats
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+                // (c, k5) interleave: 4 channels x 5 taps = 20 floats = 5 float4
+                float t[20];
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+                    for (int k5 = 0; k5 < 5; ++k5) t[jj * 5 + k5] = g[k5][j + jj];
+#pragma unroll
+                for (int v = 0; v < 5; ++v)
+                    *reinterpret_cast<float4*>(dst + j * 5 + v * 4) = make_float4(t[v * 4], t[v * 4 + 1], t[v * 4 + 2], t[v * 4 + 3]);
+            }
+        }
+        tc::tc_fence_before();
+    } else {
+        constexpr uint32_t idesc = tc::make_idesc_tf32_mn(BD_N);
+        for (int kb = 0; kb < num_kb; ++kb) {
+            const int s = kb % S::STAGES;
+            const uint32_t ph = (kb / S::STAGES) & 1;
+            tc::mbar_wait(full_bar + s, ph);
+            tc::tc_fence_after();
+            if (tc::elect_one()) {
+                const uint32_t a_hi = tc::smem_u32(smem + s * S::STAGE_BYTES);
+                const uint32_t a_lo = a_hi + S::A_BYTES;
+                const uint32_t b_hi = a_lo + S::A_BYTES;
+                const uint32_t b_lo = b_hi + S::B_BYTES;
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {                 // one 8-edge K group per MMA: +1024 bytes
+                    const uint64_t dah = tc::make_desc_sw128_mn(a_hi + kk * 1024, S::LBO), dal = tc::make_desc_sw128_mn(a_lo + kk * 1024, S::LBO);
+                    const uint64_t dbh = tc::make_desc_sw128_mn(b_hi + kk * 1024, S::LBO), dbl = tc::make_desc_sw128_mn(b_lo + kk * 1024, S::LBO);
+                    tc::mma_tf32(tmem_base, dah, dbh, idesc, (kb | kk) != 0);
+                    tc::mma_tf32(tmem_base, dah, dbl, idesc, 1);
+                    tc::mma_tf32(tmem_base, dal, dbh, idesc, 1);
+                }
+                tc::mma_commit(empty_bar + s);
+                if (kb == num_kb - 1) tc::mma_commit(accum_bar);
+            }
+            __syncwarp();
+        }
+        tc::tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == TC_PRODUCER_WARPS) {
+        tc::tc_fence_after();
+        tc::tmem_dealloc<256>(tmem_base);
+    }
+}
+
+// dW[i] = sum_s ws[s][i]
+__global__ void reduce_splits_kernel(const float* __restrict__ ws, float* __restrict__ dst, int n, int splits) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float acc = 0.f;
+    for (int s = 0; s < splits; ++s) acc += ws[(size_t)s * n + i];
+    dst[i] = acc;
+}
+
+// column sums of dout [M][Cout] in two deterministic stages: part[p][o], then reduce_splits_kernel
+constexpr int COLSUM_PARTS = 64;
+__global__ void colsum_part_kernel(const float* __restrict__ dout, float* __restrict__ part, int M, int Cout) {
+    __shared__ float red[8][33];
+    const int o = blockIdx.x * 32 + threadIdx.x;
+    const int p = blockIdx.y;
+    const int rows = (M + COLSUM_PARTS - 1) / COLSUM_PARTS;
+    const int mb = p * rows, me = min(M, mb + rows);
+    float acc = 0.f;
+    if (o < Cout)
+        for (int m = mb + threadIdx.y; m < me; m += 8) acc += __ldg(dout + (size_t)m * Cout + o);
+    red[threadIdx.y][threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.y == 0 && o < Cout) {
+        float t = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t += red[j][threadIdx.x];
+        part[(size_t)p * Cout + o] = t;
+    }
+}
+
+static int bw_splits(int M, int Cin, int Cout, int* rows_per_split) {
+    const int tiles = ceil_div(Cout, 128) * (Cin / 32);
+    int S = ceil_div(296, tiles);
+    const int maxS = max(1, M / 256);
+    if (S > maxS) S = maxS;
+    if (S < 1) S = 1;
+    int rows = ceil_div(ceil_div(M, S), 32) * 32;
+    S = ceil_div(M, rows);
+    *rows_per_split = rows;
+    return S;
+}
+
 }  // namespace mcnn
 
 using namespace mcnn;
@@ -264,4 +672,67 @@ extern "C" int mcnn_meshconv_fwd_tc(const float* x, const int32_t* gemm, const i
     if (Cout % 256 == 0 && mtiles >= 222) return launch_fwd_tc<256>(x, gemm, ec, wt_ws, bias, out, B, E, Cin, Cout, st);
     if (Cout % 128 == 0) return launch_fwd_tc<128>(x, gemm, ec, wt_ws, bias, out, B, E, Cin, Cout, st);
     return launch_fwd_tc<64>(x, gemm, ec, wt_ws, bias, out, B, E, Cin, Cout, st);
+}
+
+
+extern "C" int mcnn_meshconv_bwd_data_tc(const float* dout, const float* x, const int32_t* gemm, const int32_t* ec,
+                                         const float* weight, float* dx, float* wtb_ws, int B, int E, int Cin, int Cout,
+                                         void* stream) {
+    if (!dout || !x || !gemm || !ec || !weight || !dx || !wtb_ws || B <= 0 || E <= 0) return MCNN_E_BADARG;
+    if (!(Cin > 0 && Cin % 32 == 0 && Cout > 0 && Cout % 32 == 0)) return MCNN_E_BADARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int total = Cout * 5 * Cin;
+    weight_tc_bwd_layout_kernel<<<ceil_div(total, 256), 256, 0, st>>>(weight, wtb_ws, Cin, Cout);
+    int rc = after_launch();
+    if (rc) return rc;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(meshconv_bwd_data_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BdSmem::TOTAL);
+        if (e != cudaSuccess) { g_last_error = e; return MCNN_E_CUDA; }
+        configured = true;
+    }
+    dim3 grid(ceil_div(B * E, TC_M), Cin / 32);
+    meshconv_bwd_data_tc_kernel<<<grid, TC_THREADS, BdSmem::TOTAL, st>>>(dout, x, gemm, ec, wtb_ws, dx, B, E, Cin, Cout);
+    return after_launch();
+}
+
+/* floats of workspace mcnn_meshconv_bwd_weight_tc needs */
+extern "C" size_t mcnn_meshconv_bwd_weight_tc_ws(int B, int E, int Cin, int Cout) {
+    int rows;
+    const int S = bw_splits(B * E, Cin, Cout, &rows);
+    return (size_t)S * Cout * Cin * 5 + (size_t)COLSUM_PARTS * Cout;
+}
+
+extern "C" int mcnn_meshconv_bwd_weight_tc(const float* dout, const float* x, const int32_t* gemm, const int32_t* ec,
+                                           float* dweight, float* dbias, float* ws, int B, int E, int Cin, int Cout,
+                                           void* stream) {
+    if (!dout || !x || !gemm || !ec || !dweight || !ws || B <= 0 || E <= 0) return MCNN_E_BADARG;
+    if (!(Cin > 0 && Cin % 32 == 0 && Cout > 0 && Cout % 4 == 0)) return MCNN_E_BADARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(meshconv_bwd_weight_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BwSmem::TOTAL);
+        if (e != cudaSuccess) { g_last_error = e; return MCNN_E_CUDA; }
+        configured = true;
+    }
+    const int M = B * E;
+    int rows;
+    const int S = bw_splits(M, Cin, Cout, &rows);
+    dim3 grid(S, ceil_div(Cout, 128), Cin / 32);
+    meshconv_bwd_weight_tc_kernel<<<grid, TC_THREADS, BwSmem::TOTAL, st>>>(dout, x, gemm, ec, ws, B, E, Cin, Cout, rows);
+    int rc = after_launch();
+    if (rc) return rc;
+    const int n = Cout * Cin * 5;
+    reduce_splits_kernel<<<ceil_div(n, 256), 256, 0, st>>>(ws, dweight, n, S);
+    rc = after_launch();
+    if (rc) return rc;
+    if (dbias != nullptr) {
+        float* part = ws + (size_t)S * n;
+        colsum_part_kernel<<<dim3(ceil_div(Cout, 32), COLSUM_PARTS), dim3(32, 8), 0, st>>>(dout, part, M, Cout);
+        rc = after_launch();
+        if (rc) return rc;
+        reduce_splits_kernel<<<ceil_div(Cout, 256), 256, 0, st>>>(part, dbias, Cout, COLSUM_PARTS);
+        rc = after_launch();
+    }
+    return rc;
 }

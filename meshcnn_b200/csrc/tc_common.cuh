@@ -62,6 +62,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // ---- MMA ----------------------------------------------------------------------------------------------------
 // K-major operand tile in the canonical SWIZZLE_128B layout: rows of 128 bytes, 8-row atoms of 1024 bytes
 //   byte offset of (row r, 16-byte chunk q) = (r >> 3) * 1024 + (r & 7) * 128 + ((q ^ (r & 7)) << 4)
@@ -76,6 +90,28 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr_bytes) {
     d |= (uint64_t)1 << 46;                   // descriptor version (Blackwell)
     d |= (uint64_t)2 << 61;                   // SWIZZLE_128B
     return d;
+}
+
+// MN-major operand tile (the M/N index is contiguous in memory).  For 32-bit (tf32) operands the only MN-major layout
+// the tensor core accepts is SWIZZLE_128B_BASE32B (cutlass sm100_common.inl: "for mn-major tf32 operands, SW128_32B is
+// the only available smem layout"): atoms of 4 K-rows x 128 bytes (32 fp32 along M/N), Swizzle<2,5,2> = the 32-byte
+// chunk index is XORed with (K row & 3).  Consecutive M/N atoms are LBO bytes apart, consecutive 4-row K atoms SBO = 512.
+//   byte offset of (k, x) = (x >> 5) * LBO + k * 128 + ((((x & 31) >> 3) ^ (k & 3)) << 5) + (x & 7) * 4
+__device__ __forceinline__ uint32_t sw128_mn_off(int k, int x4 /* x / 4 */, uint32_t lbo) {
+    return (uint32_t)((x4 >> 3) * lbo + k * 128 + (((((x4 & 7) >> 1) ^ (k & 3)) << 5) | ((x4 & 1) << 4)));
+}
+__device__ __forceinline__ uint64_t make_desc_sw128_mn(uint32_t smem_addr_bytes, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr_bytes & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)(512 >> 4) << 32;          // SBO: next 4-row K atom
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)1 << 61;                   // SWIZZLE_128B_BASE32B
+    return d;
+}
+// kind::tf32, fp32 accumulate, both operands MN-major (bits 15 / 16), M = 128
+__host__ __device__ constexpr uint32_t make_idesc_tf32_mn(int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
 // instruction descriptor, kind::tf32, fp32 accumulate, both operands K-major, M = 128
@@ -97,6 +133,10 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64
 // arrives on the mbarrier once every previously issued tcgen05.mma of this thread has completed
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
 __device__ __forceinline__ bool elect_one() {

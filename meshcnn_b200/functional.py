@@ -50,17 +50,34 @@ class MeshConvFn(torch.autograd.Function):
         L = _lib.lib()
         st = _lib.current_stream()
         dx = dw = db = None
+        tc_ok = USE_TC and Cin % 32 == 0
         if ctx.needs_input_grad[0]:
             dx = torch.zeros_like(x)
-            with profiler.span('meshconv_bwd_data', B=B, E=E, Cin=Cin, Cout=Cout):
-                _lib.check(L.mcnn_meshconv_bwd_data(dout.data_ptr(), x.data_ptr(), level.gemm.data_ptr(), level.ec.data_ptr(),
-                                                    w.data_ptr(), dx.data_ptr(), B, E, Cin, Cout, st), 'mcnn_meshconv_bwd_data')
+            if tc_ok and Cout % 32 == 0:
+                wtb = torch.empty(5 * Cin, Cout, dtype=torch.float32, device=x.device)
+                with profiler.span('meshconv_bwd_data_tc', B=B, E=E, Cin=Cin, Cout=Cout):
+                    _lib.check(L.mcnn_meshconv_bwd_data_tc(dout.data_ptr(), x.data_ptr(), level.gemm.data_ptr(), level.ec.data_ptr(),
+                                                           w.data_ptr(), dx.data_ptr(), wtb.data_ptr(), B, E, Cin, Cout, st),
+                               'mcnn_meshconv_bwd_data_tc')
+            else:
+                with profiler.span('meshconv_bwd_data', B=B, E=E, Cin=Cin, Cout=Cout):
+                    _lib.check(L.mcnn_meshconv_bwd_data(dout.data_ptr(), x.data_ptr(), level.gemm.data_ptr(), level.ec.data_ptr(),
+                                                        w.data_ptr(), dx.data_ptr(), B, E, Cin, Cout, st), 'mcnn_meshconv_bwd_data')
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
-            dw = torch.zeros_like(w)
-            db = torch.zeros(Cout, dtype=torch.float32, device=x.device) if ctx.has_bias else None
-            with profiler.span('meshconv_bwd_weight', B=B, E=E, Cin=Cin, Cout=Cout):
-                _lib.check(L.mcnn_meshconv_bwd_weight(dout.data_ptr(), x.data_ptr(), level.gemm.data_ptr(), level.ec.data_ptr(),
-                                                      dw.data_ptr(), _lib.ptr(db), B, E, Cin, Cout, st), 'mcnn_meshconv_bwd_weight')
+            if tc_ok and Cout % 4 == 0:
+                dw = torch.empty_like(w)
+                db = torch.empty(Cout, dtype=torch.float32, device=x.device) if ctx.has_bias else None
+                ws = torch.empty(L.mcnn_meshconv_bwd_weight_tc_ws(B, E, Cin, Cout), dtype=torch.float32, device=x.device)
+                with profiler.span('meshconv_bwd_weight_tc', B=B, E=E, Cin=Cin, Cout=Cout):
+                    _lib.check(L.mcnn_meshconv_bwd_weight_tc(dout.data_ptr(), x.data_ptr(), level.gemm.data_ptr(), level.ec.data_ptr(),
+                                                             dw.data_ptr(), _lib.ptr(db), ws.data_ptr(), B, E, Cin, Cout, st),
+                               'mcnn_meshconv_bwd_weight_tc')
+            else:
+                dw = torch.zeros_like(w)
+                db = torch.zeros(Cout, dtype=torch.float32, device=x.device) if ctx.has_bias else None
+                with profiler.span('meshconv_bwd_weight', B=B, E=E, Cin=Cin, Cout=Cout):
+                    _lib.check(L.mcnn_meshconv_bwd_weight(dout.data_ptr(), x.data_ptr(), level.gemm.data_ptr(), level.ec.data_ptr(),
+                                                          dw.data_ptr(), _lib.ptr(db), B, E, Cin, Cout, st), 'mcnn_meshconv_bwd_weight')
         return dx, dw, db, None, None
 
 

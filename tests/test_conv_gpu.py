@@ -113,3 +113,19 @@ def test_conv_tensor_core_path_matches_ffma_path(cin, cout):
     finally:
         Fn.USE_TC = True
     assert close(y_tc.detach().cpu().numpy(), y_ff.detach().cpu().numpy(), 3e-5)
+    # backward: tensor-core dgrad / wgrad vs the FFMA kernels
+    dy = torch.randn_like(y_tc)
+    xg = x.clone().requires_grad_(True)
+    conv.zero_grad()
+    conv(xg, meshes).backward(dy)
+    g_tc = [xg.grad.clone(), conv.conv.weight.grad.clone(), conv.conv.bias.grad.clone()]
+    Fn.USE_TC = False
+    try:
+        xg2 = x.clone().requires_grad_(True)
+        conv.zero_grad()
+        conv(xg2, meshes).backward(dy)
+    finally:
+        Fn.USE_TC = True
+    g_ff = [xg2.grad, conv.conv.weight.grad, conv.conv.bias.grad]
+    for a, b in zip(g_tc, g_ff):
+        assert close(a.cpu().numpy(), b.cpu().numpy(), 3e-5)
