@@ -20,16 +20,15 @@
 
 namespace mcnn {
 
-typedef int16_t idx_t;           // shared-memory variant: n, V, node counts < 32768
+typedef int16_t idx_t;           // shared-memory variant: n, V, node counts < 32768 (0xFFFF = nil)
 typedef uint16_t cnt_t;
 
 constexpr int POOL_THREADS = 256;
 constexpr int GROUP_NODE_FACTOR = 3;     // group node pool = 3 n nodes
 
 struct PoolLayout {
-    size_t vs, keys, gemm, ev, sides, mask, order, rep, vhead, vtail, stampA, stampB, vn_edge, vn_next, ghead, gtail,
-        glen, gn_member, gn_mult, gn_next, scan, total;
-    int npow2, gn_cap;
+    size_t vs, keys, gemm, evp, sides, mask, order, rep, vhead, vtail, stamp, vn, ghead, gtail, glen, gn, ulog, scan, total;
+    int npow2, gn_cap, ulog_cap;
 };
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -39,31 +38,29 @@ __host__ __device__ inline PoolLayout pool_layout(int n, int V, int ve_cap, bool
     size_t o = 0;
     L.vs = o; o += with_vs ? sizeof(double) * 3 * (size_t)V : 0; o = align_up(o, 16);
     L.gemm = o; o += sizeof(idx_t) * 4 * (size_t)n; o = align_up(o, 16);
-    L.ev = o; o += sizeof(idx_t) * 2 * (size_t)n; o = align_up(o, 16);
+    L.evp = o; o += sizeof(uint32_t) * (size_t)n; o = align_up(o, 16);
     L.sides = o; o += 4 * (size_t)n; o = align_up(o, 16);
     L.mask = o; o += (size_t)n; o = align_up(o, 16);
     L.order = o; o += sizeof(idx_t) * (size_t)n; o = align_up(o, 16);
     L.rep = o; o += sizeof(idx_t) * (size_t)V; o = align_up(o, 16);
     L.vhead = o; o += sizeof(idx_t) * (size_t)V; o = align_up(o, 16);
     L.vtail = o; o += sizeof(idx_t) * (size_t)V; o = align_up(o, 16);
-    L.stampA = o; o += sizeof(cnt_t) * (size_t)V; o = align_up(o, 16);
-    L.stampB = o; o += sizeof(cnt_t) * (size_t)V; o = align_up(o, 16);
-    L.vn_edge = o; o += sizeof(idx_t) * (size_t)ve_cap; o = align_up(o, 16);
-    L.vn_next = o; o += sizeof(idx_t) * (size_t)ve_cap; o = align_up(o, 16);
+    L.stamp = o; o += sizeof(cnt_t) * (size_t)V; o = align_up(o, 16);
+    L.vn = o; o += sizeof(uint32_t) * (size_t)ve_cap; o = align_up(o, 16);
     L.ghead = o; o += sizeof(idx_t) * (size_t)n; o = align_up(o, 16);
     L.gtail = o; o += sizeof(idx_t) * (size_t)n; o = align_up(o, 16);
     L.glen = o; o += sizeof(cnt_t) * (size_t)n; o = align_up(o, 16);
+    L.ulog_cap = 2 * n + 16;                     // every union's source dies within the same attempt: <= 2 per dead edge
+    L.ulog = o; o += sizeof(uint32_t) * (size_t)L.ulog_cap; o = align_up(o, 16);
     int np2 = 1;
     while (np2 < n) np2 <<= 1;
     L.npow2 = np2;
     L.gn_cap = GROUP_NODE_FACTOR * n;
-    // the sort keys (uint64[npow2], npow2 < 2n) are dead before the group nodes (18 n bytes) are born
+    // the sort keys (uint64[npow2], npow2 < 2n) are dead before the group nodes (uint64[3n]) are born
     L.keys = o;
-    L.gn_member = o; o += sizeof(idx_t) * (size_t)L.gn_cap; o = align_up(o, 16);
-    L.gn_mult = o; o += sizeof(cnt_t) * (size_t)L.gn_cap; o = align_up(o, 16);
-    L.gn_next = o; o += sizeof(idx_t) * (size_t)L.gn_cap; o = align_up(o, 16);
+    L.gn = o; o += sizeof(unsigned long long) * (size_t)L.gn_cap; o = align_up(o, 16);
     if (o < L.keys + sizeof(unsigned long long) * (size_t)np2) o = align_up(L.keys + sizeof(unsigned long long) * (size_t)np2, 16);
-    L.scan = o; o += sizeof(int) * 40; o = align_up(o, 16);
+    L.scan = o; o += sizeof(int) * 48; o = align_up(o, 16);
     L.total = o;
     return L;
 }
@@ -97,61 +94,96 @@ __device__ __forceinline__ int block_scan_excl(int v, int* scratch, int& total) 
     return res;
 }
 
+constexpr unsigned NIL16 = 0xFFFFu;
+
+// group node: member [0,16) | multiplicity [16,32) | next [32,48)
+__device__ __forceinline__ unsigned long long gn_pack(unsigned member, unsigned mult, unsigned next) {
+    return (unsigned long long)member | ((unsigned long long)mult << 16) | ((unsigned long long)next << 32);
+}
+
+// MeshUnion rows, owned by the consumer thread (warp 1) while the collapse runs
+struct Groups {
+    idx_t *ghead, *gtail;
+    cnt_t* glen;
+    unsigned long long* gn;
+    int gn_count, gn_cap, status;
+
+    // MeshUnion.union (mesh_union.py:11-12): row t += row s, multiplicities kept
+    __device__ void row_add(int s, int t) {
+        if (s == t) {
+            for (unsigned nt = (unsigned short)ghead[t]; nt != NIL16;) {
+                const unsigned long long w = gn[nt];
+                const unsigned nx = (unsigned)(w >> 32) & 0xFFFFu;
+                gn[nt] = gn_pack((unsigned)w & 0xFFFFu, (((unsigned)w >> 16) & 0xFFFFu) * 2u, nx);
+                nt = nx;
+            }
+            return;
+        }
+        for (unsigned ns = (unsigned short)ghead[s]; ns != NIL16;) {
+            const unsigned long long ws = gn[ns];
+            const unsigned m = (unsigned)ws & 0xFFFFu, c = ((unsigned)ws >> 16) & 0xFFFFu;
+            ns = (unsigned)(ws >> 32) & 0xFFFFu;
+            bool found = false;
+            for (unsigned nt = (unsigned short)ghead[t]; nt != NIL16;) {
+                const unsigned long long wt = gn[nt];
+                if (((unsigned)wt & 0xFFFFu) == m) {
+                    gn[nt] = wt + ((unsigned long long)c << 16);
+                    found = true;
+                    break;
+                }
+                nt = (unsigned)(wt >> 32) & 0xFFFFu;
+            }
+            if (!found) {
+                if (gn_count >= gn_cap) { status = MCNN_ST_GROUP_OVERFLOW; return; }
+                const unsigned id = (unsigned)gn_count++;
+                gn[id] = gn_pack(m, c, NIL16);
+                const unsigned tl = (unsigned short)gtail[t];
+                gn[tl] = (gn[tl] & ~(0xFFFFull << 32)) | ((unsigned long long)id << 32);
+                gtail[t] = (idx_t)id;
+                glen[t] = (cnt_t)(glen[t] + 1);
+            }
+        }
+    }
+};
+
 struct Collapse {
-    idx_t *gemm, *ev, *order, *rep, *vhead, *vtail, *vn_edge, *vn_next, *ghead, *gtail, *gn_member, *gn_next;
-    cnt_t *stampA, *stampB, *gn_mult, *glen;
+    idx_t *gemm, *rep, *vhead, *vtail;
+    uint32_t *evp, *vn, *ulog;
+    cnt_t* stamp;
     int8_t* sides;
     uint8_t* mask;
     double* vs;               // shared copy or nullptr
     uint8_t* vmask_g;         // global v_mask of this mesh
     int32_t* log_unions;      // global or nullptr
-    int union_cap, nunions;
-    int ec, T, gn_count, gn_cap, status;
-    unsigned stamp;
+    int union_cap;
+    int nunions, ulog_cap;
+    int ec, T, status;
+    unsigned stamp_id;
 
     __device__ __forceinline__ int find(int v) {
         int p = rep[v];
         while (p != v) {
-            int gp = rep[p];
+            const int gp = rep[p];
             rep[v] = (idx_t)gp;
             v = gp;
             p = rep[v];
         }
         return v;
     }
+    __device__ __forceinline__ void ends(int e, int& v0, int& v1) {
+        const uint32_t w = evp[e];
+        const int a = (int)(w & 0xFFFFu), b = (int)(w >> 16);
+        const int ra = rep[a], rb = rep[b];                 // both loads in flight before either branch
+        v0 = (ra == a) ? a : find(a);
+        v1 = (rb == b) ? b : find(b);
+    }
 
-    // MeshUnion.union (mesh_union.py:11-12): row t += row s, multiplicities kept
-    __device__ void group_union(int s, int t) {
-        if (log_unions != nullptr) {
-            if (nunions < union_cap) { log_unions[2 * nunions] = s; log_unions[2 * nunions + 1] = t; }
-            ++nunions;
-        }
-        if (s == t) {
-            for (int nt = ghead[t]; nt >= 0; nt = gn_next[nt]) gn_mult[nt] = (cnt_t)(gn_mult[nt] * 2);
-            return;
-        }
-        for (int ns = ghead[s]; ns >= 0; ns = gn_next[ns]) {
-            const int m = gn_member[ns];
-            const unsigned c = gn_mult[ns];
-            bool found = false;
-            for (int nt = ghead[t]; nt >= 0; nt = gn_next[nt]) {
-                if (gn_member[nt] == m) {
-                    gn_mult[nt] = (cnt_t)(gn_mult[nt] + c);
-                    found = true;
-                    break;
-                }
-            }
-            if (!found) {
-                if (gn_count >= gn_cap) { status = MCNN_ST_GROUP_OVERFLOW; return; }
-                const int id = gn_count++;
-                gn_member[id] = (idx_t)m;
-                gn_mult[id] = (cnt_t)c;
-                gn_next[id] = -1;
-                gn_next[gtail[t]] = (idx_t)id;
-                gtail[t] = (idx_t)id;
-                glen[t] = (cnt_t)(glen[t] + 1);
-            }
-        }
+    // the union itself is applied by the consumer warp; the collapse only logs (source, target)
+    __device__ __forceinline__ void group_union(int s, int t) {
+        if (log_unions != nullptr && nunions < union_cap) { log_unions[2 * nunions] = s; log_unions[2 * nunions + 1] = t; }
+        if (nunions < ulog_cap) ulog[nunions] = (uint32_t)s | ((uint32_t)t << 16);
+        else status = MCNN_ST_GROUP_OVERFLOW;
+        ++nunions;
     }
 
     __device__ __forceinline__ bool row_has_hole(int e) const {
@@ -161,11 +193,13 @@ struct Collapse {
 
     // MeshPool.has_boundaries (mesh_pool.py:87-92)
     __device__ bool has_boundaries(int e) const {
-        if (row_has_hole(e)) return true;
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if (row_has_hole(gemm[4 * e + j])) return true;
-        return false;
+        const unsigned long long row = *reinterpret_cast<const unsigned long long*>(gemm + 4 * e);
+        if ((row & 0x8000800080008000ULL) != 0ULL) return true;
+        const unsigned long long r0 = *reinterpret_cast<const unsigned long long*>(gemm + 4 * (int)(row & 0xFFFF));
+        const unsigned long long r1 = *reinterpret_cast<const unsigned long long*>(gemm + 4 * (int)((row >> 16) & 0xFFFF));
+        const unsigned long long r2 = *reinterpret_cast<const unsigned long long*>(gemm + 4 * (int)((row >> 32) & 0xFFFF));
+        const unsigned long long r3 = *reinterpret_cast<const unsigned long long*>(gemm + 4 * (int)((row >> 48) & 0xFFFF));
+        return ((r0 | r1 | r2 | r3) & 0x8000800080008000ULL) != 0ULL;
     }
 
     struct Face { int ka, kb, sa, sb, osa, osb, oka0, oka1, okb0, okb1; };
@@ -230,9 +264,10 @@ struct Collapse {
 
     // __remove_triplete (mesh_pool.py:172-182): no remove_edge, the ve entries go stale
     __device__ void remove_triplet(const int tri[3]) {
-        const int a0 = find(ev[2 * tri[0]]), a1 = find(ev[2 * tri[0] + 1]);
-        const int b0 = find(ev[2 * tri[1]]), b1 = find(ev[2 * tri[1] + 1]);
-        const int c0 = find(ev[2 * tri[2]]), c1 = find(ev[2 * tri[2] + 1]);
+        int a0, a1, b0, b1, c0, c1;
+        ends(tri[0], a0, a1);
+        ends(tri[1], b0, b1);
+        ends(tri[2], c0, c1);
         mask[tri[0]] = 0; mask[tri[1]] = 0; mask[tri[2]] = 0;
         ec -= 3;
         int count = 0, v = -1;
@@ -258,26 +293,41 @@ struct Collapse {
         return status == 0;
     }
 
-    // __is_one_ring_valid (mesh_pool.py:95-100); the lists may hold stale / dead edge ids
+    // __is_one_ring_valid (mesh_pool.py:95-100); the lists may hold stale / dead edge ids.
+    // stamp[w] = (id << 2) | 1 marks w as a member of the first set, bit 1 = already counted in the intersection.
     __device__ bool one_ring_valid(int e) {
-        const int v0 = find(ev[2 * e]), v1 = find(ev[2 * e + 1]);
-        ++stamp;
-        const cnt_t s = (cnt_t)stamp;
-        for (int nd = vhead[v0]; nd >= 0; nd = vn_next[nd]) {
-            const int x = vn_edge[nd];
-            stampA[find(ev[2 * x])] = s;
-            stampA[find(ev[2 * x + 1])] = s;
+        int v0, v1;
+        ends(e, v0, v1);
+        ++stamp_id;
+        const unsigned tagA = (stamp_id << 2) | 1u;
+        unsigned nd = (unsigned short)vhead[v0];
+        if (nd != NIL16) {
+            uint32_t node = vn[nd];
+            while (true) {
+                const unsigned nx = node >> 16;
+                const uint32_t nextnode = (nx != NIL16) ? vn[nx] : 0u;      // next node in flight while this one is processed
+                int a, b;
+                ends((int)(node & 0xFFFFu), a, b);
+                stamp[a] = (cnt_t)tagA;
+                stamp[b] = (cnt_t)tagA;
+                if (nx == NIL16) break;
+                node = nextnode;
+            }
         }
         int shared = 0;
-        for (int nd = vhead[v1]; nd >= 0; nd = vn_next[nd]) {
-            const int x = vn_edge[nd];
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const int w = find(ev[2 * x + j]);
-                if (w != v0 && w != v1 && stampA[w] == s && stampB[w] != s) {
-                    stampB[w] = s;
-                    ++shared;
-                }
+        nd = (unsigned short)vhead[v1];
+        if (nd != NIL16) {
+            uint32_t node = vn[nd];
+            while (true) {
+                const unsigned nx = node >> 16;
+                const uint32_t nextnode = (nx != NIL16) ? vn[nx] : 0u;
+                int a, b;
+                ends((int)(node & 0xFFFFu), a, b);
+                const unsigned ta = stamp[a], tb = stamp[b];
+                if (a != v0 && a != v1 && ta == tagA) { stamp[a] = (cnt_t)(tagA | 2u); ++shared; }
+                if (b != a && b != v0 && b != v1 && tb == tagA) { stamp[b] = (cnt_t)(tagA | 2u); ++shared; }
+                if (nx == NIL16) break;
+                node = nextnode;
             }
         }
         return shared == 2;
@@ -285,14 +335,21 @@ struct Collapse {
 
     // list.remove(x) on ve[v] (mesh.py:48): first occurrence
     __device__ bool list_remove(int v, int x) {
-        int prev = -1;
-        for (int nd = vhead[v]; nd >= 0; prev = nd, nd = vn_next[nd]) {
-            if (vn_edge[nd] == x) {
-                const int nx = vn_next[nd];
-                if (prev < 0) vhead[v] = (idx_t)nx; else vn_next[prev] = (idx_t)nx;
-                if (vtail[v] == nd) vtail[v] = (idx_t)prev;
+        unsigned prev = NIL16;
+        unsigned nd = (unsigned short)vhead[v];
+        uint32_t node = (nd != NIL16) ? vn[nd] : 0u;
+        while (nd != NIL16) {
+            const unsigned nx = node >> 16;
+            if ((int)(node & 0xFFFFu) == x) {
+                if (prev == NIL16) vhead[v] = (idx_t)nx;
+                else vn[prev] = (vn[prev] & 0xFFFFu) | (nx << 16);
+                if ((unsigned short)vtail[v] == nd) vtail[v] = (idx_t)prev;
                 return true;
             }
+            const uint32_t nextnode = (nx != NIL16) ? vn[nx] : 0u;
+            prev = nd;
+            nd = nx;
+            node = nextnode;
         }
         status = MCNN_ST_VE_REMOVE;
         return false;
@@ -300,7 +357,8 @@ struct Collapse {
 
     // Mesh.remove_edge (mesh.py:42-48)
     __device__ bool remove_edge(int x) {
-        const int a = find(ev[2 * x]), b = find(ev[2 * x + 1]);
+        int a, b;
+        ends(x, a, b);
         if (!list_remove(a, x)) return false;
         return list_remove(b, x);
     }
@@ -321,7 +379,8 @@ struct Collapse {
     // Mesh.merge_vertices (mesh.py:26-37)
     __device__ void merge_vertices(int e) {
         if (!remove_edge(e)) return;
-        const int v0 = find(ev[2 * e]), v1 = find(ev[2 * e + 1]);
+        int v0, v1;
+        ends(e, v0, v1);
         if (v0 == v1) { status = MCNN_ST_DEGENERATE; return; }
         if (vs != nullptr) {
 #pragma unroll
@@ -329,10 +388,12 @@ struct Collapse {
         }
         vmask_g[v1] = 0;
         // ve[v0].extend(ve[v1]) : the nodes move (ve[v1] is unreachable once every row holding v1 reads v0)
-        if (vhead[v1] >= 0) {
-            if (vhead[v0] < 0) vhead[v0] = vhead[v1]; else vn_next[vtail[v0]] = vhead[v1];
+        const unsigned h1 = (unsigned short)vhead[v1];
+        if (h1 != NIL16) {
+            if ((unsigned short)vhead[v0] == NIL16) vhead[v0] = (idx_t)h1;
+            else { const unsigned t0 = (unsigned short)vtail[v0]; vn[t0] = (vn[t0] & 0xFFFFu) | (h1 << 16); }
             vtail[v0] = vtail[v1];
-            vhead[v1] = -1; vtail[v1] = -1;
+            vhead[v1] = (idx_t)NIL16; vtail[v1] = (idx_t)NIL16;
         }
         rep[v1] = (idx_t)v0;          // edges[edges == v1] = v0 over every row
     }
@@ -365,24 +426,21 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) pool_collapse_kernel(const mc
 
     double* vs_s = with_vs ? reinterpret_cast<double*>(smem + L.vs) : nullptr;
     idx_t* gemm = reinterpret_cast<idx_t*>(smem + L.gemm);
-    idx_t* ev = reinterpret_cast<idx_t*>(smem + L.ev);
+    uint32_t* evp = reinterpret_cast<uint32_t*>(smem + L.evp);
     int8_t* sides = reinterpret_cast<int8_t*>(smem + L.sides);
     uint8_t* mask = smem + L.mask;
     idx_t* order = reinterpret_cast<idx_t*>(smem + L.order);
     idx_t* rep = reinterpret_cast<idx_t*>(smem + L.rep);
     idx_t* vhead = reinterpret_cast<idx_t*>(smem + L.vhead);
     idx_t* vtail = reinterpret_cast<idx_t*>(smem + L.vtail);
-    cnt_t* stampA = reinterpret_cast<cnt_t*>(smem + L.stampA);
-    cnt_t* stampB = reinterpret_cast<cnt_t*>(smem + L.stampB);
-    idx_t* vn_edge = reinterpret_cast<idx_t*>(smem + L.vn_edge);
-    idx_t* vn_next = reinterpret_cast<idx_t*>(smem + L.vn_next);
+    cnt_t* stamp = reinterpret_cast<cnt_t*>(smem + L.stamp);
+    uint32_t* vn = reinterpret_cast<uint32_t*>(smem + L.vn);
     idx_t* ghead = reinterpret_cast<idx_t*>(smem + L.ghead);
     idx_t* gtail = reinterpret_cast<idx_t*>(smem + L.gtail);
     cnt_t* glen = reinterpret_cast<cnt_t*>(smem + L.glen);
+    uint32_t* ulog = reinterpret_cast<uint32_t*>(smem + L.ulog);
     unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem + L.keys);
-    idx_t* gn_member = reinterpret_cast<idx_t*>(smem + L.gn_member);
-    cnt_t* gn_mult = reinterpret_cast<cnt_t*>(smem + L.gn_mult);
-    idx_t* gn_next = reinterpret_cast<idx_t*>(smem + L.gn_next);
+    unsigned long long* gn = reinterpret_cast<unsigned long long*>(smem + L.gn);
     int* scan = reinterpret_cast<int*>(smem + L.scan);
 
     const int32_t* g_gemm = a.gemm_in + (size_t)b * E_in * 4;
@@ -399,18 +457,18 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) pool_collapse_kernel(const mc
         gemm[i] = (idx_t)g_gemm[i];
         sides[i] = g_sides[i];
     }
-    for (int i = tid; i < 2 * n; i += POOL_THREADS) ev[i] = (idx_t)g_edges[i];
-    for (int i = tid; i < n; i += POOL_THREADS) mask[i] = 1;
+    for (int i = tid; i < n; i += POOL_THREADS) {
+        evp[i] = (uint32_t)(g_edges[2 * i] & 0xFFFF) | ((uint32_t)(g_edges[2 * i + 1] & 0xFFFF) << 16);
+        mask[i] = 1;
+    }
     for (int v = tid; v < V; v += POOL_THREADS) {
         rep[v] = (idx_t)v;
-        stampA[v] = 0; stampB[v] = 0;
+        stamp[v] = 0;
         const int beg = g_ve_ptr[v], end = g_ve_ptr[v + 1];
-        vhead[v] = (idx_t)(beg < end ? beg : -1);
-        vtail[v] = (idx_t)(beg < end ? end - 1 : -1);
-        for (int i = beg; i < end; ++i) {
-            vn_edge[i] = (idx_t)g_ve_idx[i];
-            vn_next[i] = (idx_t)(i + 1 < end ? i + 1 : -1);
-        }
+        vhead[v] = (idx_t)(beg < end ? beg : (int)NIL16);
+        vtail[v] = (idx_t)(beg < end ? end - 1 : (int)NIL16);
+        for (int i = beg; i < end; ++i)
+            vn[i] = ((uint32_t)g_ve_idx[i] & 0xFFFFu) | ((uint32_t)(i + 1 < end ? i + 1 : (int)NIL16) << 16);
     }
     if (with_vs)
         for (int i = tid; i < 3 * V; i += POOL_THREADS) vs_s[i] = g_vs[i];
@@ -440,20 +498,20 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) pool_collapse_kernel(const mc
     // ---- phase C: MeshUnion = identity (mesh_union.py:9) -----------------------------------------------------
     for (int i = tid; i < n; i += POOL_THREADS) {
         ghead[i] = (idx_t)i; gtail[i] = (idx_t)i; glen[i] = 1;
-        gn_member[i] = (idx_t)i; gn_mult[i] = 1; gn_next[i] = -1;
+        gn[i] = gn_pack((unsigned)i, 1u, NIL16);
     }
+    __shared__ int s_status, s_ec, s_gstatus;
+    __shared__ volatile int s_pub, s_done;
+    if (tid == 0) { s_pub = 0; s_done = 0; s_gstatus = 0; }
     __syncthreads();
-    // ---- phase D: the sequential collapse (mesh_pool.py:41-53) -----------------------------------------------
-    __shared__ int s_status, s_ec;
+    // ---- phase D: the sequential collapse (mesh_pool.py:41-53); thread 32 applies the logged unions concurrently ----
     if (tid == 0) {
         Collapse c;
-        c.gemm = gemm; c.ev = ev; c.order = order; c.rep = rep; c.vhead = vhead; c.vtail = vtail;
-        c.vn_edge = vn_edge; c.vn_next = vn_next; c.ghead = ghead; c.gtail = gtail; c.gn_member = gn_member;
-        c.gn_next = gn_next; c.stampA = stampA; c.stampB = stampB; c.gn_mult = gn_mult; c.glen = glen;
-        c.sides = sides; c.mask = mask; c.vs = vs_s; c.vmask_g = g_vmask;
+        c.gemm = gemm; c.rep = rep; c.vhead = vhead; c.vtail = vtail; c.evp = evp; c.vn = vn; c.ulog = ulog;
+        c.stamp = stamp; c.sides = sides; c.mask = mask; c.vs = vs_s; c.vmask_g = g_vmask;
         c.log_unions = a.log_unions ? a.log_unions + (size_t)b * a.log_cap * 8 * 2 : nullptr;
-        c.union_cap = a.log_cap * 8; c.nunions = 0;
-        c.ec = n; c.T = T; c.gn_count = n; c.gn_cap = L.gn_cap; c.status = 0; c.stamp = 0;
+        c.union_cap = a.log_cap * 8; c.nunions = 0; c.ulog_cap = L.ulog_cap;
+        c.ec = n; c.T = T; c.status = 0; c.stamp_id = 0;
         int32_t* lp = a.log_pops ? a.log_pops + (size_t)b * a.log_cap : nullptr;
         int8_t* lo = a.log_outcome ? a.log_outcome + (size_t)b * a.log_cap : nullptr;
         int p = 0;
@@ -464,15 +522,39 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) pool_collapse_kernel(const mc
             if (lp && p < a.log_cap) lp[p] = e;
             if (lo && p < a.log_cap) lo[p] = (int8_t)outcome;
             ++p;
+            if (outcome == MCNN_POP_COLLAPSED || c.nunions != s_pub) {
+                __threadfence_block();
+                s_pub = min(c.nunions, c.ulog_cap);
+            }
             if (c.status) break;
         }
+        __threadfence_block();
+        s_pub = min(c.nunions, c.ulog_cap);
+        __threadfence_block();
+        s_done = 1;
         if (a.log_npops) a.log_npops[b] = p;
         if (a.log_nunions) a.log_nunions[b] = c.nunions;
         s_status = c.status;
         s_ec = c.ec;
+    } else if (tid == 32) {
+        Groups g;
+        g.ghead = ghead; g.gtail = gtail; g.glen = glen; g.gn = gn;
+        g.gn_count = n; g.gn_cap = L.gn_cap; g.status = 0;
+        int seen = 0;
+        while (true) {
+            const int d = s_done;
+            const int avail = s_pub;
+            while (seen < avail) {
+                const uint32_t w = ulog[seen++];
+                if (g.status == 0) g.row_add((int)(w & 0xFFFFu), (int)(w >> 16));
+            }
+            if (d) break;
+            __nanosleep(64);
+        }
+        s_gstatus = g.status;
     }
     __syncthreads();
-    int status = s_status;
+    int status = s_status ? s_status : s_gstatus;
     // ---- phase E: Mesh.clean (mesh.py:50-71) + group export ---------------------------------------------------
     // E1: survivor ranks; dead -> 0
     idx_t* newid = order;
@@ -501,7 +583,8 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) pool_collapse_kernel(const mc
             o_gemm[4 * r + j] = g < 0 ? -1 : (int)newid[g];
             o_sides[4 * r + j] = sides[4 * i + j];
         }
-        int v0 = ev[2 * i], v1 = ev[2 * i + 1];
+        const uint32_t w = evp[i];
+        int v0 = (int)(w & 0xFFFFu), v1 = (int)(w >> 16);
         while (rep[v0] != v0) v0 = rep[v0];
         while (rep[v1] != v1) v1 = rep[v1];
         g_edges[2 * r] = v0;
@@ -518,29 +601,35 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) pool_collapse_kernel(const mc
         const int v = base + tid;
         int len = 0;
         if (v < V)
-            for (int nd = vhead[v]; nd >= 0; nd = vn_next[nd]) ++len;
+            for (unsigned nd = (unsigned short)vhead[v]; nd != NIL16; nd = vn[nd] >> 16) ++len;
         int tot;
         const int pre = block_scan_excl(len, scan, tot);
         if (v < V) {
             int pos = carry + pre;
             g_ve_ptr[v] = pos;
-            for (int nd = vhead[v]; nd >= 0; nd = vn_next[nd]) g_ve_idx[pos++] = newid[vn_edge[nd]];
+            for (unsigned nd = (unsigned short)vhead[v]; nd != NIL16;) {
+                const uint32_t w = vn[nd];
+                g_ve_idx[pos++] = newid[w & 0xFFFFu];
+                nd = w >> 16;
+            }
         }
         carry += tot;
     }
     if (tid == 0) g_ve_ptr[V] = carry;
     __syncthreads();
-    // E4: groups.  the ve node arrays are free now: occ_cnt / col_cnt live there (2 * int32[n] <= 4 * ve_cap bytes)
-    int* occ_cnt = reinterpret_cast<int*>(smem + L.vn_edge);
+    // E4: groups.  the ve node array is free now: occ_cnt / col_cnt live there (2 * int32[n] <= 4 * ve_cap bytes)
+    int* occ_cnt = reinterpret_cast<int*>(smem + L.vn);
     int* col_cnt = occ_cnt + n;
     for (int i = tid; i < 2 * n; i += POOL_THREADS) occ_cnt[i] = 0;
     __syncthreads();
     for (int i = tid; i < n; i += POOL_THREADS) {
         const bool live = mask[i];
-        for (int nd = ghead[i]; nd >= 0; nd = gn_next[nd]) {
-            const int m = gn_member[nd];
-            atomicAdd(&occ_cnt[m], (int)gn_mult[nd]);       // every row, un-clamped
+        for (unsigned nd = (unsigned short)ghead[i]; nd != NIL16;) {
+            const unsigned long long w = gn[nd];
+            const int m = (int)((unsigned)w & 0xFFFFu);
+            atomicAdd(&occ_cnt[m], (int)(((unsigned)w >> 16) & 0xFFFFu));       // every row, un-clamped
             if (live) atomicAdd(&col_cnt[m], 1);
+            nd = (unsigned)(w >> 32) & 0xFFFFu;
         }
     }
     __syncthreads();
@@ -572,18 +661,19 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) pool_collapse_kernel(const mc
         o_rowptr[r] = start;
         if (!nnz_ok) continue;
         int len = 0;
-        for (int nd = ghead[i]; nd >= 0; nd = gn_next[nd]) {      // insertion sort, ascending member id
-            const int m = gn_member[nd];
+        for (unsigned nd = (unsigned short)ghead[i]; nd != NIL16;) {      // insertion sort, ascending member id
+            const unsigned long long w = gn[nd];
+            const int m = (int)((unsigned)w & 0xFFFFu);
             int p = start + len;
             while (p > start && o_cols[p - 1] > m) { o_cols[p] = o_cols[p - 1]; --p; }
             o_cols[p] = m;
             ++len;
+            nd = (unsigned)(w >> 32) & 0xFFFFu;
         }
     }
     for (int r = total + tid; r <= T; r += POOL_THREADS) o_rowptr[r] = nnz;
     __syncthreads();
-    // CSC: column pointers, then rows in ascending order (new ids ascend with old ids, so one ordered sweep
-    // per column would do; a counting fill followed by a per-column insertion sort keeps it simple)
+    // CSC: column pointers, then a counting fill followed by a per-column insertion sort (ascending pooled id)
     carry = 0;
     for (int base = 0; base < n; base += POOL_THREADS) {
         const int i = base + tid;
@@ -599,13 +689,14 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) pool_collapse_kernel(const mc
         for (int i = tid; i < n; i += POOL_THREADS) {
             if (!(mask[i] && newid[i] < T)) continue;
             const int r = newid[i];
-            for (int nd = ghead[i]; nd >= 0; nd = gn_next[nd]) {
-                const int pos = atomicAdd(&occ_cnt[gn_member[nd]], 1);
+            for (unsigned nd = (unsigned short)ghead[i]; nd != NIL16;) {
+                const unsigned long long w = gn[nd];
+                const int pos = atomicAdd(&occ_cnt[(int)((unsigned)w & 0xFFFFu)], 1);
                 o_rows[pos] = r;
+                nd = (unsigned)(w >> 32) & 0xFFFFu;
             }
         }
         __syncthreads();
-        __threadfence_block();
         for (int j = tid; j < n; j += POOL_THREADS) {
             const int beg = o_colptr[j], end = beg + col_cnt[j];
             for (int p = beg + 1; p < end; ++p) {
@@ -754,7 +845,7 @@ extern "C" int mcnn_pool_collapse(const mcnn_pool_args* a, void* stream) {
         !a->ec_out || !a->grp_rowptr || !a->grp_cols || !a->grp_colptr || !a->grp_rows || !a->occ || !a->status)
         return MCNN_E_BADARG;
     if (a->E_in > 10900 || a->V > 32767 || a->ve_cap > 32767 || a->ve_cap < 2 * 0) return MCNN_E_TOO_LARGE;
-    if ((size_t)a->ve_cap * 2 * sizeof(idx_t) < (size_t)a->E_in * 2 * sizeof(int)) return MCNN_E_BADARG;  // occ/col counters alias the ve nodes
+    if ((size_t)a->ve_cap * sizeof(uint32_t) < (size_t)a->E_in * 2 * sizeof(int)) return MCNN_E_BADARG;  // occ/col counters alias the ve nodes
     const size_t smem = pool_layout(a->E_in, a->V, a->ve_cap, a->vs != nullptr).total;
     if (smem > mcnn_pool_smem_limit()) return MCNN_E_TOO_LARGE;
     static size_t configured = 0;
