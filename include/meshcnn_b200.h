@@ -185,6 +185,29 @@ int mcnn_unpool_bwd(const float* dout, const int32_t* grp_rowptr, const int32_t*
                     const int32_t* ec_lo, float* df, int B, int E_lo, int E_hi, int E_grp, int C, int nnz_cap,
                     void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Fused normalisation blocks around MeshConv (reference: models/networks.py:149,
+ * :171-179 (BatchNorm2d in MResConv, GroupNorm after it), :222-233 / :276-288 (InstanceNorm2d + residual + relu)).
+ *     z = pre(x [+ a]);   y = post(gamma * (z - mean) * rstd + beta [+ r])          pre / post = relu or identity
+ * x, a, r, y: [nblocks * rows_per_block][C] edge-major; statistics per (block of rows) x (group of C/G channels):
+ *     BatchNorm2d: nblocks = 1, rows = B*E, G = C;  GroupNorm: nblocks = B, rows = E, G = groups;  InstanceNorm2d: G = C.
+ * mean / rstd: [nblocks][G] (written unless stats_given); part: mcnn_norm_ws() floats of scratch; running_* (NULL or
+ * [C]) get the BatchNorm momentum update.  Backward returns dx (== da), dr (NULL to skip), dgamma / dbeta (NULL ok);
+ * s1 / s2: [nblocks][G] scratch.
+ * ------------------------------------------------------------------------------------------------------ */
+size_t mcnn_norm_ws(int nblocks, int rows_per_block, int C, int G);
+int mcnn_norm_fwd(const float* x, const float* a, const float* r, const float* gamma, const float* beta, float* y,
+                  float* mean, float* rstd, float* part, float* running_mean, float* running_var, float momentum,
+                  float eps, int nblocks, int rows_per_block, int C, int G, int pre_relu, int post_relu, int stats_given,
+                  void* stream);
+int mcnn_norm_bwd(const float* dy, const float* y, const float* x, const float* a, const float* gamma, const float* mean,
+                  const float* rstd, float* dx, float* dr, float* dgamma, float* dbeta, float* part, float* s1, float* s2,
+                  int nblocks, int rows_per_block, int C, int G, int pre_relu, int post_relu, void* stream);
+
+/* torch.optim.Adam step (no amsgrad) over flat fp32 buffers: parameters, gradients, exp_avg, exp_avg_sq (mesh_classifier.py:38) */
+int mcnn_adam_flat(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+                   float weight_decay, int step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,340 @@
+// Fused normalisation blocks on edge-major activations x[rows][C] (row N1 of SURVEY.md §8f: the elementwise /
+// normalisation passes around MeshConv, networks.py:149, :171-179, :222-233, :276-288 of the reference).
+//
+//     z = pre(x [+ a])            pre  = relu or identity
+//     y = post(gamma * (z - mean) * rstd + beta [+ r])        post = relu or identity
+//
+// with statistics over (block of `rows_per_block` consecutive rows) x (group of C/G consecutive channels):
+//     BatchNorm2d    : one block of all B*E rows, G = C      (training-mode batch statistics; padded slots included, F8)
+//     GroupNorm(g)   : one block per mesh (E rows), G = g
+//     InstanceNorm2d : one block per mesh, G = C, gamma = 1, beta = 0
+// Three kernels forward (slab partial sums -> finalize in fp64 -> apply), three backward; every reduction is two-stage and
+// deterministic.  All HBM-bound: each activation is read twice and written once per direction.
+#include "common.cuh"
+
+namespace mcnn {
+
+constexpr int NT = 256;
+
+struct NormShape {
+    int nblocks, rows_per_block, C, G, slabs, rows_per_slab;
+};
+
+__device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// per-slab column sums of (u, v); FN supplies the two quantities for one float4 of columns
+template <typename FN>
+__device__ __forceinline__ void slab_colsums(const NormShape s, float* __restrict__ part, FN fn) {
+    extern __shared__ float sm[];                 // [rpp][2][C]
+    const int cq = s.C >> 2;
+    const int rpp = NT / cq;                       // rows per pass
+    const int tx = threadIdx.x % cq, ty = threadIdx.x / cq;
+    const int blk = blockIdx.x, slab = blockIdx.y;
+    const int r0 = slab * s.rows_per_slab, r1 = min(s.rows_per_block, r0 + s.rows_per_slab);
+    float u[4] = {0.f, 0.f, 0.f, 0.f}, v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (ty < rpp) {
+        for (int r = r0 + ty; r < r1; r += rpp) {
+            const size_t off = ((size_t)blk * s.rows_per_block + r) * s.C + (tx << 2);
+            float4 a, b;
+            fn(off, tx << 2, a, b);
+            u[0] += a.x; u[1] += a.y; u[2] += a.z; u[3] += a.w;
+            v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            sm[(ty * 2 + 0) * s.C + (tx << 2) + j] = u[j];
+            sm[(ty * 2 + 1) * s.C + (tx << 2) + j] = v[j];
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * s.C; i += NT) {
+        const int which = i / s.C, c = i - which * s.C;
+        float acc = 0.f;
+        for (int y = 0; y < rpp; ++y) acc += sm[(y * 2 + which) * s.C + c];
+        part[(((size_t)blk * s.slabs + slab) * 2 + which) * s.C + c] = acc;
+    }
+}
+
+__global__ void __launch_bounds__(NT) norm_stats_kernel(const float* __restrict__ x, const float* __restrict__ a, int pre_relu,
+                                                        float* __restrict__ part, NormShape s) {
+    slab_colsums(s, part, [&](size_t off, int, float4& u, float4& v) {
+        float4 z = ld4(x + off);
+        if (a != nullptr) { const float4 t = ld4(a + off); z.x += t.x; z.y += t.y; z.z += t.z; z.w += t.w; }
+        if (pre_relu) { z.x = fmaxf(z.x, 0.f); z.y = fmaxf(z.y, 0.f); z.z = fmaxf(z.z, 0.f); z.w = fmaxf(z.w, 0.f); }
+        u = z;
+        v = make_float4(z.x * z.x, z.y * z.y, z.z * z.z, z.w * z.w);
+    });
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
+}
+
+// mean / rstd per (block, group) from the slab partials, in fp64 (one warp per output); optional BatchNorm running-stat update
+__global__ void norm_finalize_kernel(const float* __restrict__ part, float* __restrict__ mean, float* __restrict__ rstd,
+                                     float* running_mean, float* running_var, float momentum, float eps, NormShape s) {
+    const int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (idx >= s.nblocks * s.G) return;
+    const int blk = idx / s.G, g = idx - blk * s.G;
+    const int cpg = s.C / s.G;
+    double su = 0.0, sv = 0.0;
+    const int items = s.slabs * cpg;
+    for (int it = lane; it < items; it += 32) {
+        const int sl = it / cpg, c = g * cpg + (it - sl * cpg);
+        su += (double)part[(((size_t)blk * s.slabs + sl) * 2 + 0) * s.C + c];
+        sv += (double)part[(((size_t)blk * s.slabs + sl) * 2 + 1) * s.C + c];
+    }
+    su = warp_sum(su);
+    sv = warp_sum(sv);
+    if (lane != 0) return;
+    const double n = (double)s.rows_per_block * cpg;
+    const double m = su / n;
+    double var = sv / n - m * m;
+    if (var < 0.0) var = 0.0;
+    mean[idx] = (float)m;
+    rstd[idx] = (float)(1.0 / sqrt(var + (double)eps));
+    if (running_mean != nullptr) {                       // BatchNorm2d training: unbiased variance into the running buffer
+        const double unb = n > 1.0 ? var * n / (n - 1.0) : var;
+        running_mean[g] = (1.f - momentum) * running_mean[g] + momentum * (float)m;
+        running_var[g] = (1.f - momentum) * running_var[g] + momentum * (float)unb;
+    }
+}
+
+__global__ void __launch_bounds__(NT) norm_apply_kernel(const float* __restrict__ x, const float* __restrict__ a,
+                                                        const float* __restrict__ r, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, const float* __restrict__ mean,
+                                                        const float* __restrict__ rstd, float* __restrict__ y, int pre_relu,
+                                                        int post_relu, NormShape s, long long total4) {
+    const long long i = (long long)blockIdx.x * NT + threadIdx.x;
+    if (i >= total4) return;
+    const int cq = s.C >> 2;
+    const long long row = i / cq;
+    const int c = (int)(i - row * cq) << 2;
+    const int blk = (int)(row / s.rows_per_block);
+    const size_t off = (size_t)row * s.C + c;
+    float4 z = ld4(x + off);
+    if (a != nullptr) { const float4 t = ld4(a + off); z.x += t.x; z.y += t.y; z.z += t.z; z.w += t.w; }
+    float zz[4] = {z.x, z.y, z.z, z.w};
+    float rr[4] = {0.f, 0.f, 0.f, 0.f};
+    if (r != nullptr) { const float4 t = ld4(r + off); rr[0] = t.x; rr[1] = t.y; rr[2] = t.z; rr[3] = t.w; }
+    const int cpg = s.C / s.G;
+    float out[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float v = pre_relu ? fmaxf(zz[j], 0.f) : zz[j];
+        const int g = (c + j) / cpg;
+        const float m = __ldg(mean + blk * s.G + g), rs = __ldg(rstd + blk * s.G + g);
+        v = (v - m) * rs;
+        if (gamma != nullptr) v = v * __ldg(gamma + c + j) + __ldg(beta + c + j);
+        v += rr[j];
+        out[j] = post_relu ? fmaxf(v, 0.f) : v;
+    }
+    *reinterpret_cast<float4*>(y + off) = make_float4(out[0], out[1], out[2], out[3]);
+}
+
+// backward stage 1: per-slab column sums of (dyh, dyh * xhat), dyh = dy * [y > 0 if post_relu]
+__global__ void __launch_bounds__(NT) norm_bwd_stats_kernel(const float* __restrict__ dy, const float* __restrict__ y,
+                                                            const float* __restrict__ x, const float* __restrict__ a,
+                                                            const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                            int pre_relu, int post_relu, float* __restrict__ part, NormShape s) {
+    const int cpg = s.C / s.G;
+    const int blk = blockIdx.x;
+    slab_colsums(s, part, [&](size_t off, int c, float4& u, float4& v) {
+        float4 d = ld4(dy + off);
+        if (post_relu) {
+            const float4 yy = ld4(y + off);
+            d.x = yy.x > 0.f ? d.x : 0.f; d.y = yy.y > 0.f ? d.y : 0.f; d.z = yy.z > 0.f ? d.z : 0.f; d.w = yy.w > 0.f ? d.w : 0.f;
+        }
+        float4 z = ld4(x + off);
+        if (a != nullptr) { const float4 t = ld4(a + off); z.x += t.x; z.y += t.y; z.z += t.z; z.w += t.w; }
+        if (pre_relu) { z.x = fmaxf(z.x, 0.f); z.y = fmaxf(z.y, 0.f); z.z = fmaxf(z.z, 0.f); z.w = fmaxf(z.w, 0.f); }
+        const float zz[4] = {z.x, z.y, z.z, z.w};
+        float xh[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int g = (c + j) / cpg;
+            xh[j] = (zz[j] - __ldg(mean + blk * s.G + g)) * __ldg(rstd + blk * s.G + g);
+        }
+        u = d;
+        v = make_float4(d.x * xh[0], d.y * xh[1], d.z * xh[2], d.w * xh[3]);
+    });
+}
+
+// backward stage 2 (one warp per output): per (block, group) s1 = sum gamma*A / n, s2 = sum gamma*Bc / n;
+// then dgamma[c] = sum_blocks Bc, dbeta[c] = sum_blocks A
+__global__ void norm_bwd_finalize_kernel(const float* __restrict__ part, const float* __restrict__ gamma, float* __restrict__ s1,
+                                         float* __restrict__ s2, float* __restrict__ dgamma, float* __restrict__ dbeta, NormShape s) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const int cpg = s.C / s.G;
+    const int ngroups = s.nblocks * s.G;
+    if (w < ngroups) {
+        const int blk = w / s.G, g = w - blk * s.G;
+        double a1 = 0.0, a2 = 0.0;
+        const int items = s.slabs * cpg;
+        for (int it = lane; it < items; it += 32) {
+            const int sl = it / cpg, c = g * cpg + (it - sl * cpg);
+            const double gm = gamma != nullptr ? (double)gamma[c] : 1.0;
+            a1 += gm * (double)part[(((size_t)blk * s.slabs + sl) * 2 + 0) * s.C + c];
+            a2 += gm * (double)part[(((size_t)blk * s.slabs + sl) * 2 + 1) * s.C + c];
+        }
+        a1 = warp_sum(a1);
+        a2 = warp_sum(a2);
+        if (lane == 0) {
+            const double n = (double)s.rows_per_block * cpg;
+            s1[w] = (float)(a1 / n);
+            s2[w] = (float)(a2 / n);
+        }
+    } else if (dgamma != nullptr && w < ngroups + s.C) {
+        const int c = w - ngroups;
+        double A = 0.0, Bc = 0.0;
+        const int items = s.nblocks * s.slabs;
+        for (int it = lane; it < items; it += 32) {
+            A += (double)part[((size_t)it * 2 + 0) * s.C + c];
+            Bc += (double)part[((size_t)it * 2 + 1) * s.C + c];
+        }
+        A = warp_sum(A);
+        Bc = warp_sum(Bc);
+        if (lane == 0) { dgamma[c] = (float)Bc; dbeta[c] = (float)A; }
+    }
+}
+
+// backward stage 3: dz = rstd * (gamma*dyh - s1 - xhat*s2); dx = da = dz * [z_pre > 0 if pre_relu]; dr = dyh
+__global__ void __launch_bounds__(NT) norm_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ y,
+                                                            const float* __restrict__ x, const float* __restrict__ a,
+                                                            const float* __restrict__ gamma, const float* __restrict__ mean,
+                                                            const float* __restrict__ rstd, const float* __restrict__ s1,
+                                                            const float* __restrict__ s2, float* __restrict__ dx,
+                                                            float* __restrict__ dr, int pre_relu, int post_relu, NormShape s,
+                                                            long long total4) {
+    const long long i = (long long)blockIdx.x * NT + threadIdx.x;
+    if (i >= total4) return;
+    const int cq = s.C >> 2;
+    const long long row = i / cq;
+    const int c = (int)(i - row * cq) << 2;
+    const int blk = (int)(row / s.rows_per_block);
+    const size_t off = (size_t)row * s.C + c;
+    float4 d4 = ld4(dy + off);
+    float d[4] = {d4.x, d4.y, d4.z, d4.w};
+    if (post_relu) {
+        const float4 yy = ld4(y + off);
+        const float yv[4] = {yy.x, yy.y, yy.z, yy.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) d[j] = yv[j] > 0.f ? d[j] : 0.f;
+    }
+    if (dr != nullptr) *reinterpret_cast<float4*>(dr + off) = make_float4(d[0], d[1], d[2], d[3]);
+    float4 z4 = ld4(x + off);
+    if (a != nullptr) { const float4 t = ld4(a + off); z4.x += t.x; z4.y += t.y; z4.z += t.z; z4.w += t.w; }
+    const float zr[4] = {z4.x, z4.y, z4.z, z4.w};
+    const int cpg = s.C / s.G;
+    float out[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int g = (c + j) / cpg;
+        const float m = __ldg(mean + blk * s.G + g), rs = __ldg(rstd + blk * s.G + g);
+        const float z = pre_relu ? fmaxf(zr[j], 0.f) : zr[j];
+        const float xh = (z - m) * rs;
+        const float gm = gamma != nullptr ? __ldg(gamma + c + j) : 1.f;
+        float dz = rs * (gm * d[j] - __ldg(s1 + blk * s.G + g) - xh * __ldg(s2 + blk * s.G + g));
+        if (pre_relu && !(zr[j] > 0.f)) dz = 0.f;
+        out[j] = dz;
+    }
+    *reinterpret_cast<float4*>(dx + off) = make_float4(out[0], out[1], out[2], out[3]);
+}
+
+// ---- flat Adam over contiguous parameter / gradient / moment buffers (torch.optim.Adam semantics, no amsgrad) ----------
+__global__ void adam_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                 long long n, float lr, float beta1, float beta2, float eps, float weight_decay, float bc1, float bc2_sqrt) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float gi = g[i];
+    const float pi = p[i];
+    if (weight_decay != 0.f) gi += weight_decay * pi;
+    const float mi = beta1 * m[i] + (1.f - beta1) * gi;
+    const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = pi - (lr / bc1) * (mi / denom);
+}
+
+static NormShape make_shape(int nblocks, int rows_per_block, int C, int G) {
+    NormShape s;
+    s.nblocks = nblocks; s.rows_per_block = rows_per_block; s.C = C; s.G = G;
+    int slabs = ceil_div(592, nblocks);                      // ~4 CTAs per SM in flight
+    const int max_slabs = max(1, rows_per_block / 64);
+    if (slabs > max_slabs) slabs = max_slabs;
+    if (slabs > 512) slabs = 512;
+    s.rows_per_slab = ceil_div(rows_per_block, slabs);
+    s.slabs = ceil_div(rows_per_block, s.rows_per_slab);
+    return s;
+}
+
+}  // namespace mcnn
+
+using namespace mcnn;
+
+static bool norm_args_ok(int nblocks, int rows, int C, int G) {
+    return nblocks > 0 && rows > 0 && C > 0 && (C % 4) == 0 && C <= 1024 && G > 0 && (C % G) == 0;
+}
+
+/* floats needed in `part` for a given shape */
+extern "C" size_t mcnn_norm_ws(int nblocks, int rows_per_block, int C, int G) {
+    if (!norm_args_ok(nblocks, rows_per_block, C, G)) return 0;
+    const NormShape s = make_shape(nblocks, rows_per_block, C, G);
+    return (size_t)nblocks * s.slabs * 2 * C;
+}
+
+extern "C" int mcnn_norm_fwd(const float* x, const float* a, const float* r, const float* gamma, const float* beta, float* y,
+                             float* mean, float* rstd, float* part, float* running_mean, float* running_var, float momentum,
+                             float eps, int nblocks, int rows_per_block, int C, int G, int pre_relu, int post_relu,
+                             int stats_given, void* stream) {
+    if (!x || !y || !mean || !rstd || !part || !norm_args_ok(nblocks, rows_per_block, C, G)) return MCNN_E_BADARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const NormShape s = make_shape(nblocks, rows_per_block, C, G);
+    const size_t smem = (size_t)(NT / (C / 4)) * 2 * C * sizeof(float);
+    int rc;
+    if (!stats_given) {
+        norm_stats_kernel<<<dim3(nblocks, s.slabs), NT, smem, st>>>(x, a, pre_relu, part, s);
+        if ((rc = after_launch())) return rc;
+        norm_finalize_kernel<<<ceil_div(nblocks * G * 32, 256), 256, 0, st>>>(part, mean, rstd, running_mean, running_var, momentum, eps, s);
+        if ((rc = after_launch())) return rc;
+    }
+    const long long total4 = (long long)nblocks * rows_per_block * (C / 4);
+    norm_apply_kernel<<<(unsigned)((total4 + NT - 1) / NT), NT, 0, st>>>(x, a, r, gamma, beta, mean, rstd, y, pre_relu, post_relu, s, total4);
+    return after_launch();
+}
+
+extern "C" int mcnn_norm_bwd(const float* dy, const float* y, const float* x, const float* a, const float* gamma,
+                             const float* mean, const float* rstd, float* dx, float* dr, float* dgamma, float* dbeta,
+                             float* part, float* s1, float* s2, int nblocks, int rows_per_block, int C, int G, int pre_relu,
+                             int post_relu, void* stream) {
+    if (!dy || !x || !mean || !rstd || !dx || !part || !s1 || !s2 || !norm_args_ok(nblocks, rows_per_block, C, G)) return MCNN_E_BADARG;
+    if (post_relu && !y) return MCNN_E_BADARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const NormShape s = make_shape(nblocks, rows_per_block, C, G);
+    const size_t smem = (size_t)(NT / (C / 4)) * 2 * C * sizeof(float);
+    int rc;
+    norm_bwd_stats_kernel<<<dim3(nblocks, s.slabs), NT, smem, st>>>(dy, y, x, a, mean, rstd, pre_relu, post_relu, part, s);
+    if ((rc = after_launch())) return rc;
+    const int nfin = nblocks * G + C;
+    norm_bwd_finalize_kernel<<<ceil_div(nfin * 32, 256), 256, 0, st>>>(part, gamma, s1, s2, dgamma, dbeta, s);
+    if ((rc = after_launch())) return rc;
+    const long long total4 = (long long)nblocks * rows_per_block * (C / 4);
+    norm_bwd_apply_kernel<<<(unsigned)((total4 + NT - 1) / NT), NT, 0, st>>>(dy, y, x, a, gamma, mean, rstd, s1, s2, dx, dr, pre_relu,
+                                                                             post_relu, s, total4);
+    return after_launch();
+}
+
+extern "C" int mcnn_adam_flat(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                              float eps, float weight_decay, int step, void* stream) {
+    if (!p || !g || !m || !v || n <= 0 || step <= 0) return MCNN_E_BADARG;
+    const float bc1 = 1.f - powf(beta1, (float)step);
+    const float bc2 = 1.f - powf(beta2, (float)step);
+    adam_flat_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay,
+                                                                                     bc1, sqrtf(bc2));
+    return after_launch();
+}

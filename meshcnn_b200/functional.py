@@ -141,3 +141,94 @@ class UnpoolFn(torch.autograd.Function):
                                               ctx.ec_lo.data_ptr(), df.data_ptr(), B, E_lo, ctx.E_hi, rec.E_in, C,
                                               rec.nnz_cap, _lib.current_stream()), 'mcnn_unpool_bwd')
         return df, None, None, None, None
+
+
+class FusedNormFn(torch.autograd.Function):
+    """y = post(gamma * (pre(x [+ a]) - mean) * rstd + beta [+ r]) with BatchNorm / GroupNorm / InstanceNorm statistics
+    (mcnn_norm_fwd / mcnn_norm_bwd); x, a, r: edge-major [B, E, C]."""
+
+    @staticmethod
+    def forward(ctx, x, a, r, gamma, beta, cfg):
+        _chk_cuda(x, a, r, gamma, beta)
+        x = x.contiguous()
+        a = None if a is None else a.contiguous()
+        r = None if r is None else r.contiguous()
+        B, E, C = x.shape
+        nblocks, rows, G = cfg['nblocks'], cfg['rows'], cfg['G']
+        L = _lib.lib()
+        dev = x.device
+        y = torch.empty_like(x)
+        stats_given = cfg.get('mean') is not None
+        if stats_given:
+            mean, rstd = cfg['mean'].contiguous(), cfg['rstd'].contiguous()
+        else:
+            mean = torch.empty(nblocks * G, dtype=torch.float32, device=dev)
+            rstd = torch.empty(nblocks * G, dtype=torch.float32, device=dev)
+        part = torch.empty(max(1, L.mcnn_norm_ws(nblocks, rows, C, G)), dtype=torch.float32, device=dev)
+        rm, rv = cfg.get('running_mean'), cfg.get('running_var')
+        with profiler.span('norm_fwd', nblocks=nblocks, rows=rows, C=C, G=G):
+            _lib.check(L.mcnn_norm_fwd(x.data_ptr(), _lib.ptr(a), _lib.ptr(r), _lib.ptr(gamma), _lib.ptr(beta), y.data_ptr(),
+                                       mean.data_ptr(), rstd.data_ptr(), part.data_ptr(), _lib.ptr(rm), _lib.ptr(rv),
+                                       float(cfg.get('momentum', 0.1)), float(cfg['eps']), nblocks, rows, C, G,
+                                       int(cfg['pre_relu']), int(cfg['post_relu']), int(stats_given), _lib.current_stream()),
+                       'mcnn_norm_fwd')
+        ctx.save_for_backward(x, a, gamma, mean, rstd, y)
+        ctx.cfg = (nblocks, rows, C, G, int(cfg['pre_relu']), int(cfg['post_relu']), stats_given, r is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, a, gamma, mean, rstd, y = ctx.saved_tensors
+        nblocks, rows, C, G, pre_relu, post_relu, stats_given, has_r = ctx.cfg
+        if stats_given:
+            raise NotImplementedError('backward through a norm layer running on fixed (eval-mode) statistics')
+        dy = dy.contiguous()
+        L = _lib.lib()
+        dev = dy.device
+        dx = torch.empty_like(x)
+        dr = torch.empty_like(x) if has_r else None
+        dgamma = torch.empty_like(gamma) if gamma is not None else None
+        dbeta = torch.empty_like(gamma) if gamma is not None else None
+        part = torch.empty(max(1, L.mcnn_norm_ws(nblocks, rows, C, G)), dtype=torch.float32, device=dev)
+        s12 = torch.empty(2, nblocks * G, dtype=torch.float32, device=dev)
+        with profiler.span('norm_bwd', nblocks=nblocks, rows=rows, C=C, G=G):
+            _lib.check(L.mcnn_norm_bwd(dy.data_ptr(), y.data_ptr(), x.data_ptr(), _lib.ptr(a), _lib.ptr(gamma), mean.data_ptr(),
+                                       rstd.data_ptr(), dx.data_ptr(), _lib.ptr(dr), _lib.ptr(dgamma), _lib.ptr(dbeta),
+                                       part.data_ptr(), s12[0].data_ptr(), s12[1].data_ptr(), nblocks, rows, C, G, pre_relu,
+                                       post_relu, _lib.current_stream()), 'mcnn_norm_bwd')
+        return dx, (dx if a is not None else None), dr, dgamma, dbeta, None
+
+
+def fused_norm(x, norm, pre_add=None, pre_relu=False, post_add=None, post_relu=False):
+    """Apply a torch norm module (BatchNorm2d / GroupNorm / InstanceNorm2d, the three the reference's networks use) to
+    edge-major x [B, E, C] with the surrounding add / relu fused in.  Returns None if `norm` is not one of those."""
+    import torch.nn as nn
+    B, E, C = x.shape
+    if C % 4 != 0:
+        return None
+    cfg = {'pre_relu': pre_relu, 'post_relu': post_relu, 'eps': norm.eps if hasattr(norm, 'eps') else 1e-5}
+    gamma = beta = None
+    if isinstance(norm, nn.GroupNorm):
+        cfg.update(nblocks=B, rows=E, G=norm.num_groups)
+        gamma, beta = norm.weight, norm.bias
+    elif isinstance(norm, nn.InstanceNorm2d):
+        if norm.track_running_stats:
+            return None
+        cfg.update(nblocks=B, rows=E, G=C)
+        gamma, beta = norm.weight, norm.bias
+    elif isinstance(norm, nn.BatchNorm2d):
+        cfg.update(nblocks=1, rows=B * E, G=C)
+        gamma, beta = norm.weight, norm.bias
+        if norm.training or not norm.track_running_stats:
+            if norm.track_running_stats:
+                if norm.momentum is None:
+                    return None
+                cfg.update(running_mean=norm.running_mean, running_var=norm.running_var, momentum=norm.momentum)
+                norm.num_batches_tracked.add_(1)
+        else:
+            cfg.update(mean=norm.running_mean, rstd=torch.rsqrt(norm.running_var + norm.eps))
+    else:
+        return None
+    if (gamma is None) != (beta is None):
+        return None
+    return FusedNormFn.apply(x, pre_add, post_add, gamma, beta, cfg)

@@ -41,6 +41,26 @@ def _align(n, a=16):
     return (n + a - 1) // a * a
 
 
+_PIN_POOL = {}          # size -> list of [pinned tensor, cuda event]; cudaHostAlloc per batch would cost milliseconds
+
+
+def _staging_buffer(nbytes, device):
+    """A pinned host buffer for the topology upload, recycled across batches (two per size, so packing batch k+1 can
+    overlap the copy of batch k)."""
+    if torch.device(device).type != 'cuda':
+        return torch.empty(nbytes, dtype=torch.uint8), None
+    slots = _PIN_POOL.setdefault(nbytes, [])
+    for slot in slots:
+        if slot[1].query():
+            return slot[0], slot
+    if len(slots) >= 2:
+        slots[0][1].synchronize()
+        return slots[0][0], slots[0]
+    slot = [torch.empty(nbytes, dtype=torch.uint8, pin_memory=True), torch.cuda.Event()]
+    slots.append(slot)
+    return slot[0], slot
+
+
 class Level:
     """One resolution of the batch: one-ring tables + live edge counts, all on the device."""
     __slots__ = ('E', 'gemm', 'sides', 'ec', 'padded')
@@ -101,9 +121,9 @@ class MeshBatch:
         for k, s in sizes:
             offs[k] = (o, s)
             o = _align(o + s)
-        pin = torch.cuda.is_available()
-        host = torch.zeros(o, dtype=torch.uint8, pin_memory=pin)
+        host, self._pin_slot = _staging_buffer(o, self.device)
         hb = host.numpy()
+        hb[:] = 0
 
         def view(k, dtype, shape):
             a, s = offs[k]
@@ -132,6 +152,8 @@ class MeshBatch:
                 vs[b, :len(h['vs'])] = h['vs']
         self._host_blob = host
         self.blob = host.to(self.device, non_blocking=True)
+        if self._pin_slot is not None:
+            self._pin_slot[1].record()                 # the staging buffer may be reused once this copy has completed
         self._offs = offs
 
         def dview(k, dtype, shape):

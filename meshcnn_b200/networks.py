@@ -20,6 +20,7 @@ import torch.nn.functional as F
 from torch.nn import init
 from torch.optim import lr_scheduler
 
+from .functional import fused_norm
 from .layout import as_bce, as_bce1, to_edge_major
 from .mesh import MeshBatch
 from .mesh_conv import MeshConv
@@ -131,10 +132,19 @@ def define_loss(opt):
 # ---------------------------------------------------------------------------------------------------------------
 # edge-major helpers
 # ---------------------------------------------------------------------------------------------------------------
-def _norm_em(norm, x_em):
-    """Apply a torch 2-D norm layer to edge-major data through its [B, C, E, 1] channels_last view."""
-    y = norm(as_bce1(x_em))
-    return to_edge_major(y)
+def _norm_em(norm, x, pre_add=None, pre_relu=False, post_add=None, post_relu=False):
+    """post(norm(pre(x [+ pre_add])) [+ post_add]) on edge-major data.  BatchNorm2d / GroupNorm / InstanceNorm2d run as one
+    fused CUDA block (mcnn_norm_fwd); anything else goes through torch on the [B, C, E, 1] channels_last view."""
+    y = fused_norm(x, norm, pre_add, pre_relu, post_add, post_relu)
+    if y is not None:
+        return y
+    z = x if pre_add is None else x + pre_add
+    if pre_relu:
+        z = F.relu(z)
+    y = to_edge_major(norm(as_bce1(z)))
+    if post_add is not None:
+        y = y + post_add
+    return F.relu(y) if post_relu else y
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -149,12 +159,15 @@ class MResConv(nn.Module):
             self.add_module('bn%d' % i, nn.BatchNorm2d(out_channels))
             self.add_module('conv%d' % i, MeshConv(out_channels, out_channels, bias=False))
 
-    def forward_em(self, x, batch):
+    def forward_em(self, x, batch, defer_tail=False):
+        """defer_tail=True returns (x, skip) and leaves the final relu(x + skip) to the caller's fused norm block."""
         x = self.conv0.forward_em(x, batch)
         skip = x
         for i in range(1, self.skips + 1):
-            x = _norm_em(getattr(self, 'bn%d' % i), F.relu(x))
+            x = _norm_em(getattr(self, 'bn%d' % i), x, pre_relu=True)
             x = getattr(self, 'conv%d' % i).forward_em(x, batch)
+        if defer_tail:
+            return x, skip
         return F.relu(x + skip)
 
     def forward(self, x, mesh):
@@ -181,8 +194,8 @@ class MeshConvNet(nn.Module):
         batch = MeshBatch.of(mesh, x.shape[2], x.device)
         x = to_edge_major(x)
         for i in range(len(self.k) - 1):
-            x = getattr(self, 'conv%d' % i).forward_em(x, batch)
-            x = F.relu(_norm_em(getattr(self, 'norm%d' % i), x))
+            x, skip = getattr(self, 'conv%d' % i).forward_em(x, batch, defer_tail=True)
+            x = _norm_em(getattr(self, 'norm%d' % i), x, pre_add=skip, pre_relu=True, post_relu=True)
             x = getattr(self, 'pool%d' % i).forward_em(x, batch)
         x = x.mean(dim=1)                       # AvgPool1d(res[-1]) over the whole (zero-padded) edge axis
         x = F.relu(self.fc1(x))
@@ -208,10 +221,9 @@ class DownConv(nn.Module):
         self.pool = MeshPool(pool) if pool else None
 
     def forward_em(self, x, batch):
-        x1 = F.relu(_norm_em(self.bn[0], self.conv1.forward_em(x, batch)))
+        x1 = _norm_em(self.bn[0], self.conv1.forward_em(x, batch), post_relu=True)
         for idx, conv in enumerate(self.conv2):
-            x2 = _norm_em(self.bn[idx + 1], conv.forward_em(x1, batch))
-            x1 = F.relu(x2 + x1)
+            x1 = _norm_em(self.bn[idx + 1], conv.forward_em(x1, batch), post_add=x1, post_relu=True)
         before_pool = None
         if self.pool is not None:
             before_pool = x1
@@ -242,16 +254,14 @@ class UpConv(nn.Module):
         if self.transfer_data:
             x1 = torch.cat((x1, from_down), 2)
         x1 = self.conv1.forward_em(x1, batch)
-        if len(self.bn):
-            x1 = _norm_em(self.bn[0], x1)
-        x1 = F.relu(x1)
+        x1 = _norm_em(self.bn[0], x1, post_relu=True) if len(self.bn) else F.relu(x1)
         for idx, conv in enumerate(self.conv2):
             x2 = conv.forward_em(x1, batch)
+            res = x1 if self.residual else None
             if len(self.bn):
-                x2 = _norm_em(self.bn[idx + 1], x2)
-            if self.residual:
-                x2 = x2 + x1
-            x1 = F.relu(x2)
+                x1 = _norm_em(self.bn[idx + 1], x2, post_add=res, post_relu=True)
+            else:
+                x1 = F.relu(x2 if res is None else x2 + res)
         return x1
 
     def forward(self, x, from_down=None):
