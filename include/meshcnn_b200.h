@@ -80,6 +80,9 @@ int mcnn_meshconv_tc_supported(int Cin, int Cout);
 int mcnn_meshconv_fwd_tc(const float* x, const int32_t* gemm, const int32_t* ec, const float* weight,
                          const float* bias, float* out, float* wt_ws, int B, int E, int Cin, int Cout, void* stream);
 
+/* diagnostics only: bottleneck-attribution knobs of the tensor-core forward kernel (0 = normal operation) */
+int mcnn_debug_set_tc(int flags);
+
 /* dx of the above (autograd of mesh_conv.py:47-69: conv2d dgrad, abs/add backward, index_select scatter).
  *   dout [B][E][Cout]   dx [B][E][Cin]  -- must be ZERO on entry (the kernel accumulates with red.global) */
 int mcnn_meshconv_bwd_data(const float* dout, const float* x, const int32_t* gemm, const int32_t* ec,

@@ -19,6 +19,10 @@
 
 namespace mcnn {
 
+// debug knobs for bottleneck attribution (tools/tc_knobs.py): bit 0 = producers skip global loads, bit 1 = MMA warp skips
+// the tcgen05.mma issue, bit 2 = producers skip the st.shared.  0 in normal operation.
+__device__ int g_tc_debug = 0;
+
 constexpr int TC_M = 128;
 constexpr int TC_PRODUCER_WARPS = 8;
 constexpr int TC_THREADS = (TC_PRODUCER_WARPS + 1) * 32;
@@ -72,6 +76,7 @@ meshconv_fwd_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ 
     const int m0 = blockIdx.x * TC_M, n0 = blockIdx.y * N_TILE;
     const int K = 5 * Cin;
     const int num_kb = K >> 5;
+    const int dbg = g_tc_debug;
 
     // ---- setup ------------------------------------------------------------------------------------------------
     for (int i = tid; i < TC_M * 5; i += TC_THREADS) {
@@ -88,7 +93,7 @@ meshconv_fwd_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ 
     }
     if (warp == TC_PRODUCER_WARPS) {
         if (lane == 0) {
-            for (int s = 0; s < S::STAGES; ++s) { tc::mbar_init(full_bar + s, TC_PRODUCER_WARPS * 32); tc::mbar_init(empty_bar + s, 1); }
+            for (int s = 0; s < S::STAGES; ++s) { tc::mbar_init(full_bar + s, TC_PRODUCER_WARPS); tc::mbar_init(empty_bar + s, 1); }
             tc::mbar_init(accum_bar, 1);
             tc::fence_barrier_init();
         }
@@ -102,59 +107,95 @@ meshconv_fwd_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ 
 
     if (warp < TC_PRODUCER_WARPS) {
         // ======================================== producers ========================================================
+        // Each thread owns the same tile rows for every K block, so its gather row ids live in registers and the global
+        // loads of K block kb+2 are issued before the shared-memory stores of block kb (register prefetch, distance 2):
+        // the L2 latency of the gathers is hidden behind two blocks of split / st.shared / MMA work.
         const int pt = tid;                                     // 0..255
-        for (int kb = 0; kb < num_kb; ++kb) {
+        constexpr int NB = N_TILE / 32;                         // B float4 per thread per block
+        int src0[4], srcA[2][2], srcB[2][2];                    // blk 0: 4 items (row, chunk); pair blocks: 2 items x 2 rows
+#pragma unroll
+        for (int it = 0; it < 4; ++it) src0[it] = nb[(pt + it * 256) >> 3][0];
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+            const int r = (pt + it * 256) >> 2;
+            srcA[it][0] = nb[r][1]; srcB[it][0] = nb[r][3];     // pair (f1, f3)
+            srcA[it][1] = nb[r][2]; srcB[it][1] = nb[r][4];     // pair (f2, f4)
+        }
+        struct Regs { float4 b[NB]; float4 a[4]; };
+        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        auto load_block = [&](int kb, Regs& R) {
+            const int cb = kb / 5, blk = kb - cb * 5;
+            if (dbg & 1) {
+#pragma unroll
+                for (int it = 0; it < NB; ++it) R.b[it] = zero4;
+#pragma unroll
+                for (int it = 0; it < 4; ++it) R.a[it] = zero4;
+                return;
+            }
+#pragma unroll
+            for (int it = 0; it < NB; ++it) {
+                const int item = pt + it * 256;
+                const int r = item >> 3, q = item & 7;
+                R.b[it] = (n0 + r < Cout) ? __ldg(reinterpret_cast<const float4*>(wt + (size_t)(n0 + r) * K + (kb << 5) + (q << 2))) : zero4;
+            }
+            if (blk == 0) {
+                const int c = cb * 32 + ((pt & 7) << 2);
+#pragma unroll
+                for (int it = 0; it < 4; ++it)
+                    R.a[it] = src0[it] >= 0 ? __ldg(reinterpret_cast<const float4*>(x + (size_t)src0[it] * Cin + c)) : zero4;
+            } else {
+                const int pr = (blk <= 2) ? 0 : 1;
+                const int c = cb * 32 + (((blk - 1) & 1) << 4) + ((pt & 3) << 2);
+#pragma unroll
+                for (int it = 0; it < 2; ++it) {
+                    const int sa = srcA[it][pr], sb = srcB[it][pr];
+                    R.a[2 * it] = sa >= 0 ? __ldg(reinterpret_cast<const float4*>(x + (size_t)sa * Cin + c)) : zero4;
+                    R.a[2 * it + 1] = sb >= 0 ? __ldg(reinterpret_cast<const float4*>(x + (size_t)sb * Cin + c)) : zero4;
+                }
+            }
+        };
+        auto store_block = [&](int kb, const Regs& R) {
             const int s = kb % S::STAGES;
             const uint32_t ph = (kb / S::STAGES) & 1;
-            tc::mbar_wait(empty_bar + s, ph ^ 1);
+            if (lane == 0) tc::mbar_wait(empty_bar + s, ph ^ 1);      // one poller per warp
+            __syncwarp();
             unsigned char* a_hi = smem + s * S::STAGE_BYTES;
             unsigned char* a_lo = a_hi + S::A_BYTES;
             unsigned char* b_hi = a_lo + S::A_BYTES;
             unsigned char* b_lo = b_hi + S::B_BYTES;
-            const int cb = kb / 5, blk = kb - cb * 5;
-            // ---- B tile: rows n0..n0+N_TILE of wt, K block kb (32 floats = 8 chunks) ------------------------------
+            const int blk = kb % 5;
+            float4 hi, lo;
+            if (dbg & 4) {
+                tc::fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(full_bar + s);
+                return;
+            }
 #pragma unroll
-            for (int it = 0; it < (N_TILE * 8) / (TC_PRODUCER_WARPS * 32); ++it) {
-                const int item = pt + it * (TC_PRODUCER_WARPS * 32);
-                const int r = item >> 3, q = item & 7;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (n0 + r < Cout) v = __ldg(reinterpret_cast<const float4*>(wt + (size_t)(n0 + r) * K + (kb << 5) + (q << 2)));
-                float4 hi, lo;
-                tc::split4(v, hi, lo);
-                const uint32_t off = tc::sw128_off(r, q);
+            for (int it = 0; it < NB; ++it) {
+                const int item = pt + it * 256;
+                const uint32_t off = tc::sw128_off(item >> 3, item & 7);
+                tc::split4(R.b[it], hi, lo);
                 *reinterpret_cast<float4*>(b_hi + off) = hi;
                 *reinterpret_cast<float4*>(b_lo + off) = lo;
             }
-            // ---- A tile ---------------------------------------------------------------------------------------------
             if (blk == 0) {
-                const int c0 = cb * 32;
 #pragma unroll
-                for (int it = 0; it < (TC_M * 8) / (TC_PRODUCER_WARPS * 32); ++it) {
-                    const int item = pt + it * (TC_PRODUCER_WARPS * 32);
-                    const int r = item >> 3, q = item & 7;
-                    const int src = nb[r][0];
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (src >= 0) v = __ldg(reinterpret_cast<const float4*>(x + (size_t)src * Cin + c0 + (q << 2)));
-                    float4 hi, lo;
-                    tc::split4(v, hi, lo);
-                    const uint32_t off = tc::sw128_off(r, q);
+                for (int it = 0; it < 4; ++it) {
+                    const int item = pt + it * 256;
+                    const uint32_t off = tc::sw128_off(item >> 3, item & 7);
+                    tc::split4(R.a[it], hi, lo);
                     *reinterpret_cast<float4*>(a_hi + off) = hi;
                     *reinterpret_cast<float4*>(a_lo + off) = lo;
                 }
             } else {
-                const int ka = (blk <= 2) ? 1 : 2;                         // neighbour slots (ka, ka+2)
-                const int c0 = cb * 32 + (((blk - 1) & 1) << 4);
 #pragma unroll
-                for (int it = 0; it < (TC_M * 4) / (TC_PRODUCER_WARPS * 32); ++it) {
-                    const int item = pt + it * (TC_PRODUCER_WARPS * 32);
+                for (int it = 0; it < 2; ++it) {
+                    const int item = pt + it * 256;
                     const int r = item >> 2, q = item & 3;
-                    const int sa = nb[r][ka], sb = nb[r][ka + 2];
-                    float4 fa = make_float4(0.f, 0.f, 0.f, 0.f), fb = fa;
-                    if (sa >= 0) fa = __ldg(reinterpret_cast<const float4*>(x + (size_t)sa * Cin + c0 + (q << 2)));
-                    if (sb >= 0) fb = __ldg(reinterpret_cast<const float4*>(x + (size_t)sb * Cin + c0 + (q << 2)));
+                    const float4 fa = R.a[2 * it], fb = R.a[2 * it + 1];
                     const float4 sum = make_float4(fa.x + fb.x, fa.y + fb.y, fa.z + fb.z, fa.w + fb.w);
                     const float4 dif = make_float4(fabsf(fa.x - fb.x), fabsf(fa.y - fb.y), fabsf(fa.z - fb.z), fabsf(fa.w - fb.w));
-                    float4 hi, lo;
                     tc::split4(sum, hi, lo);
                     uint32_t off = tc::sw128_off(r, q);
                     *reinterpret_cast<float4*>(a_hi + off) = hi;
@@ -165,8 +206,37 @@ meshconv_fwd_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ 
                     *reinterpret_cast<float4*>(a_lo + off) = lo;
                 }
             }
-            tc::fence_proxy_async_smem();
-            tc::mbar_arrive(full_bar + s);
+            tc::fence_proxy_async_smem();                                  // every writer fences its own stores ...
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(full_bar + s);                  // ... then one arrival per warp
+        };
+        if constexpr (N_TILE < 256) {                            // prefetch distance 2 (three register sets)
+            Regs R0, R1, R2;
+            load_block(0, R0);
+            if (num_kb > 1) load_block(1, R1);
+            for (int kb = 0; kb < num_kb; kb += 3) {
+                if (kb + 2 < num_kb) load_block(kb + 2, R2);
+                store_block(kb, R0);
+                if (kb + 1 < num_kb) {
+                    if (kb + 3 < num_kb) load_block(kb + 3, R0);
+                    store_block(kb + 1, R1);
+                }
+                if (kb + 2 < num_kb) {
+                    if (kb + 4 < num_kb) load_block(kb + 4, R1);
+                    store_block(kb + 2, R2);
+                }
+            }
+        } else {                                                 // N = 256: 48 registers per set, distance 1
+            Regs R0, R1;
+            load_block(0, R0);
+            for (int kb = 0; kb < num_kb; kb += 2) {
+                if (kb + 1 < num_kb) load_block(kb + 1, R1);
+                store_block(kb, R0);
+                if (kb + 1 < num_kb) {
+                    if (kb + 2 < num_kb) load_block(kb + 2, R0);
+                    store_block(kb + 1, R1);
+                }
+            }
         }
         // ======================================== epilogue ==========================================================
         tc::mbar_wait(accum_bar, 0);
@@ -208,7 +278,7 @@ meshconv_fwd_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ 
                 const uint32_t b_hi = a_lo + S::A_BYTES;
                 const uint32_t b_lo = b_hi + S::B_BYTES;
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {                 // 4 x (K = 8 tf32 = 32 bytes)
+                for (int kk = 0; kk < ((dbg & 2) ? 0 : 4); ++kk) {                 // 4 x (K = 8 tf32 = 32 bytes)
                     const uint64_t dah = tc::make_desc_sw128(a_hi + kk * 32), dal = tc::make_desc_sw128(a_lo + kk * 32);
                     const uint64_t dbh = tc::make_desc_sw128(b_hi + kk * 32), dbl = tc::make_desc_sw128(b_lo + kk * 32);
                     tc::mma_tf32(tmem_base, dah, dbh, idesc, (kb | kk) != 0);
@@ -304,7 +374,7 @@ meshconv_bwd_data_tc_kernel(const float* __restrict__ dout, const float* __restr
     }
     if (warp == TC_PRODUCER_WARPS) {
         if (lane == 0) {
-            for (int s = 0; s < S::STAGES; ++s) { tc::mbar_init(full_bar + s, TC_PRODUCER_WARPS * 32); tc::mbar_init(empty_bar + s, 1); }
+            for (int s = 0; s < S::STAGES; ++s) { tc::mbar_init(full_bar + s, TC_PRODUCER_WARPS); tc::mbar_init(empty_bar + s, 1); }
             tc::mbar_init(accum_bar, 1);
             tc::fence_barrier_init();
         }
@@ -321,7 +391,8 @@ meshconv_bwd_data_tc_kernel(const float* __restrict__ dout, const float* __restr
         for (int kb = 0; kb < num_kb; ++kb) {
             const int s = kb % S::STAGES;
             const uint32_t ph = (kb / S::STAGES) & 1;
-            tc::mbar_wait(empty_bar + s, ph ^ 1);
+            if (lane == 0) tc::mbar_wait(empty_bar + s, ph ^ 1);      // one poller per warp
+            __syncwarp();
             unsigned char* a_hi = smem + s * S::STAGE_BYTES;
             unsigned char* a_lo = a_hi + S::A_BYTES;
             unsigned char* b_hi = a_lo + S::A_BYTES;
@@ -350,8 +421,9 @@ meshconv_bwd_data_tc_kernel(const float* __restrict__ dout, const float* __restr
                 *reinterpret_cast<float4*>(b_hi + off) = hi;
                 *reinterpret_cast<float4*>(b_lo + off) = lo;
             }
-            tc::fence_proxy_async_smem();
-            tc::mbar_arrive(full_bar + s);
+            tc::fence_proxy_async_smem();                                  // every writer fences its own stores ...
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(full_bar + s);                  // ... then one arrival per warp
         }
         // ---- epilogue: abs/add backward + scatter ----------------------------------------------
         tc::mbar_wait(accum_bar, 0);
@@ -466,7 +538,7 @@ meshconv_bwd_weight_tc_kernel(const float* __restrict__ dout, const float* __res
 
     if (warp == TC_PRODUCER_WARPS) {
         if (lane == 0) {
-            for (int s = 0; s < S::STAGES; ++s) { tc::mbar_init(full_bar + s, TC_PRODUCER_WARPS * 32); tc::mbar_init(empty_bar + s, 1); }
+            for (int s = 0; s < S::STAGES; ++s) { tc::mbar_init(full_bar + s, TC_PRODUCER_WARPS); tc::mbar_init(empty_bar + s, 1); }
             tc::mbar_init(accum_bar, 1);
             tc::fence_barrier_init();
         }
@@ -483,7 +555,8 @@ meshconv_bwd_weight_tc_kernel(const float* __restrict__ dout, const float* __res
         for (int kb = 0; kb < num_kb; ++kb) {
             const int s = kb % S::STAGES;
             const uint32_t ph = (kb / S::STAGES) & 1;
-            tc::mbar_wait(empty_bar + s, ph ^ 1);
+            if (lane == 0) tc::mbar_wait(empty_bar + s, ph ^ 1);      // one poller per warp
+            __syncwarp();
             unsigned char* a_hi = smem + s * S::STAGE_BYTES;
             unsigned char* a_lo = a_hi + S::A_BYTES;
             unsigned char* b_hi = a_lo + S::A_BYTES;
@@ -541,8 +614,9 @@ meshconv_bwd_weight_tc_kernel(const float* __restrict__ dout, const float* __res
                     *reinterpret_cast<float4*>(b_lo + off) = lo;
                 }
             }
-            tc::fence_proxy_async_smem();
-            tc::mbar_arrive(full_bar + s);
+            tc::fence_proxy_async_smem();                                  // every writer fences its own stores ...
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(full_bar + s);                  // ... then one arrival per warp
         }
         // ---- epilogue: slab partial -> ws[split][o][c][k5] ---------------------------------------------------------
         const int lane_grp = warp & 3;
@@ -735,4 +809,10 @@ extern "C" int mcnn_meshconv_bwd_weight_tc(const float* dout, const float* x, co
         rc = after_launch();
     }
     return rc;
+}
+
+
+extern "C" int mcnn_debug_set_tc(int flags) {
+    cudaError_t e = cudaMemcpyToSymbol(g_tc_debug, &flags, sizeof(int));
+    return e == cudaSuccess ? MCNN_OK : MCNN_E_CUDA;
 }
