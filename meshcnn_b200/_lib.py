@@ -6,7 +6,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libmeshcnn_b200.so')
+LIB_PATH = os.environ.get('MESHCNN_B200_LIB') or os.path.join(_HERE, 'libmeshcnn_b200.so')   # override: diagnostics builds only
 
 _c_int = ctypes.c_int
 _c_vp = ctypes.c_void_p
@@ -25,7 +25,7 @@ class PoolArgs(ctypes.Structure):
         ('grp_rowptr', _c_vp), ('grp_cols', _c_vp), ('grp_colptr', _c_vp), ('grp_rows', _c_vp), ('occ', _c_vp),
         ('status', _c_vp),
         ('log_npops', _c_vp), ('log_pops', _c_vp), ('log_outcome', _c_vp), ('log_nunions', _c_vp), ('log_unions', _c_vp),
-        ('edge_mask_out', _c_vp),
+        ('edge_mask_out', _c_vp), ('dbg_clocks', _c_vp),
     ]
 
 

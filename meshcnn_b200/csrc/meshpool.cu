@@ -8,27 +8,36 @@
 //   gemm / sides / mask      int16[4n] / int8[4n] / uint8[n]      one-ring tables of the incoming level
 //   ev + rep                 original endpoints + a vertex union-find: `edges[edges == v1] = v0` over ALL rows
 //                            (mesh.py:35-37) is exactly rep[v1] = v0
-//   ve lists                 singly linked nodes (first-occurrence removal, O(1) tail concatenation); stale
-//                            entries are kept, as in the reference
-//   MeshUnion rows           linked (member, multiplicity) nodes -- `groups[t] += groups[s]` keeps
-//                            multiplicities because the unpool occurrences need them
+//   ve lists                 chains of slabs.  Every vertex owns the contiguous slab it arrives with (the CSR row of
+//                            the incoming level); `ve[v0].extend(ve[v1])` links v1's chain behind v0's (O(1)).
+//                            `list.remove(x)` turns the entry into a tombstone: every edge knows where its two entries
+//                            sit (epos), so a removal is two stores; only id 0 -- which the previous level's re-indexing
+//                            gives to every stale entry -- can occur more than once in a list and is
+//                            searched for its first occurrence.  Stale entries are kept, as in the reference.  Slabs
+//                            are arrays, so a warp walks a list 32 entries at a time (one-ring test).
+//   MeshUnion                only the (source -> target) log of `groups[t] += groups[s]`.  Every source dies within
+//                            the attempt that pours it and receives nothing between its (at most two) pours, so the
+//                            rows are the reachability sets of a DAG with out-degree <= 2: row t = {ancestors of t},
+//                            un-clamped occurrences of m = number of paths starting at m.  Both are
+//                            evaluated after the collapse by all threads.
 //
-// Phases: load -> bitonic sort of (norm bits, id) keys -> thread 0 runs the sequential collapse (order and side
-// effects identical to the reference, failed attempts included) -> all threads run Mesh.clean (compaction,
-// re-indexing with dead -> 0) and emit the groups as CSR + CSC + un-clamped occurrences.
+// Phases: load -> bitonic sort of (norm bits, id) keys -> lane 0 of warp 0 runs the sequential collapse (order and
+// side effects identical to the reference, failed attempts included) and calls in the other 31 lanes for every list
+// walk -> all threads run Mesh.clean (compaction, re-indexing with dead -> 0) and emit the groups as CSR + CSC +
+// un-clamped occurrences.
 #include "common.cuh"
 
 namespace mcnn {
 
-typedef int16_t idx_t;           // shared-memory variant: n, V, node counts < 32768 (0xFFFF = nil)
-typedef uint16_t cnt_t;
+typedef int16_t idx_t;           // shared-memory variant: n, V, list entries < 32768 (0xFFFF = nil)
 
 constexpr int POOL_THREADS = 256;
-constexpr int GROUP_NODE_FACTOR = 3;     // group node pool = 3 n nodes
+constexpr int POOL_BFS_CAP = 96;         // members of one MeshUnion row / column walked per thread (implementation limit)
 
 struct PoolLayout {
-    size_t vs, keys, gemm, evp, sides, mask, order, rep, vhead, vtail, stamp, vn, ghead, gtail, glen, gn, ulog, scan, total;
-    int npow2, gn_cap, ulog_cap;
+    size_t vs, gemm, evp, sides, mask, order, rep, stamp, slab_start, slab_len, slab_next, chain_tail, vmask, ve, eposa, eposb, ulog, cnt32,
+        keys, scan, total;
+    int npow2, ulog_cap;
 };
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -37,29 +46,29 @@ __host__ __device__ inline PoolLayout pool_layout(int n, int V, int ve_cap, bool
     PoolLayout L;
     size_t o = 0;
     L.vs = o; o += with_vs ? sizeof(double) * 3 * (size_t)V : 0; o = align_up(o, 16);
-    L.gemm = o; o += sizeof(idx_t) * 4 * (size_t)n; o = align_up(o, 16);
-    L.evp = o; o += sizeof(uint32_t) * (size_t)n; o = align_up(o, 16);
+    L.gemm = o; o += sizeof(idx_t) * 4 * (size_t)n; o = align_up(o, 16);          // later: column member pool (u16[3n]) + col_off
+    L.evp = o; o += sizeof(uint32_t) * (size_t)n; o = align_up(o, 16);            // evp + sides, later: row member pool (u16[3n]) + ...
     L.sides = o; o += 4 * (size_t)n; o = align_up(o, 16);
     L.mask = o; o += (size_t)n; o = align_up(o, 16);
     L.order = o; o += sizeof(idx_t) * (size_t)n; o = align_up(o, 16);
     L.rep = o; o += sizeof(idx_t) * (size_t)V; o = align_up(o, 16);
-    L.vhead = o; o += sizeof(idx_t) * (size_t)V; o = align_up(o, 16);
-    L.vtail = o; o += sizeof(idx_t) * (size_t)V; o = align_up(o, 16);
-    L.stamp = o; o += sizeof(cnt_t) * (size_t)V; o = align_up(o, 16);
-    L.vn = o; o += sizeof(uint32_t) * (size_t)ve_cap; o = align_up(o, 16);
-    L.ghead = o; o += sizeof(idx_t) * (size_t)n; o = align_up(o, 16);
-    L.gtail = o; o += sizeof(idx_t) * (size_t)n; o = align_up(o, 16);
-    L.glen = o; o += sizeof(cnt_t) * (size_t)n; o = align_up(o, 16);
+    L.stamp = o; o += sizeof(uint32_t) * (size_t)V; o = align_up(o, 16);
+    L.slab_start = o; o += sizeof(uint16_t) * (size_t)V; o = align_up(o, 16);
+    L.slab_len = o; o += sizeof(uint16_t) * (size_t)V; o = align_up(o, 16);
+    L.slab_next = o; o += sizeof(idx_t) * (size_t)V; o = align_up(o, 16);
+    L.chain_tail = o; o += sizeof(idx_t) * (size_t)V; o = align_up(o, 16);
+    L.vmask = o; o += (size_t)V; o = align_up(o, 16);
+    L.ve = o; o += sizeof(uint16_t) * (size_t)ve_cap; o = align_up(o, 16);
+    L.eposa = o; o += sizeof(uint16_t) * (size_t)n; o = align_up(o, 16);
+    L.eposb = o; o += sizeof(uint16_t) * (size_t)n; o = align_up(o, 16);
     L.ulog_cap = 2 * n + 16;                     // every union's source dies within the same attempt: <= 2 per dead edge
     L.ulog = o; o += sizeof(uint32_t) * (size_t)L.ulog_cap; o = align_up(o, 16);
+    L.cnt32 = o; o += sizeof(int) * 2 * (size_t)n; o = align_up(o, 16);           // out-degree, row length / cursor
     int np2 = 1;
     while (np2 < n) np2 <<= 1;
     L.npow2 = np2;
-    L.gn_cap = GROUP_NODE_FACTOR * n;
-    // the sort keys (uint64[npow2], npow2 < 2n) are dead before the group nodes (uint64[3n]) are born
-    L.keys = o;
-    L.gn = o; o += sizeof(unsigned long long) * (size_t)L.gn_cap; o = align_up(o, 16);
-    if (o < L.keys + sizeof(unsigned long long) * (size_t)np2) o = align_up(L.keys + sizeof(unsigned long long) * (size_t)np2, 16);
+    // the sort keys (uint64[npow2]) are dead before the group evaluation needs occ (int32[n]) + out0 / out1 (u16[n] each)
+    L.keys = o; o += sizeof(unsigned long long) * (size_t)np2; o = align_up(o, 16);
     L.scan = o; o += sizeof(int) * 48; o = align_up(o, 16);
     L.total = o;
     return L;
@@ -96,99 +105,180 @@ __device__ __forceinline__ int block_scan_excl(int v, int* scratch, int& total) 
 
 constexpr unsigned NIL16 = 0xFFFFu;
 
-// group node: member [0,16) | multiplicity [16,32) | next [32,48)
-__device__ __forceinline__ unsigned long long gn_pack(unsigned member, unsigned mult, unsigned next) {
-    return (unsigned long long)member | ((unsigned long long)mult << 16) | ((unsigned long long)next << 32);
+// The sequential collapse runs on thread 0.  Walks over vertex -> edge lists (the one-ring test, and the rare search for
+// the first occurrence of id 0) are handed to a helper warp (warp 1) through a small shared-memory ring: it walks a list 32
+// entries at a time and the collapse thread waits for the answer.
+struct WarpCtx {
+    uint16_t *ve, *slab_start, *slab_len;
+    idx_t *slab_next, *chain_tail, *rep;
+    uint32_t *evp, *stamp;
+};
+
+enum { WOP_EXIT = 0, WOP_ONE_RING = 1, WOP_REMOVE_SCAN = 2 };
+constexpr unsigned VE_TOMB = 0xFFFFu;          // removed list entry
+constexpr int WQ_CAP = 32;
+
+struct WorkQueue {
+    int ent[WQ_CAP][4];       // op, a0, a1, a2
+    int head;                 // entries posted   (written by the collapse thread)
+    int done;                 // entries finished (written by the helper warp)
+    int res;                  // result of the most recent operation
+    int res_seq;              // sequence number (1-based) that `res` belongs to
+};
+
+__device__ __forceinline__ int uf_find(idx_t* rep, int v) {
+    int p = rep[v];
+    while (p != v) {
+        const int gp = rep[p];
+        rep[v] = (idx_t)gp;                             // path halving; concurrent lanes only ever write ancestors
+        v = gp;
+        p = rep[v];
+    }
+    return v;
+}
+__device__ __forceinline__ void edge_ends(const uint32_t* evp, idx_t* rep, int e, int& v0, int& v1) {
+    const uint32_t w = evp[e];
+    const int a = (int)(w & 0xFFFFu), b = (int)(w >> 16);
+    const int ra = rep[a], rb = rep[b];                 // both loads in flight before either branch
+    v0 = (ra == a) ? a : uf_find(rep, a);
+    v1 = (rb == b) ? b : uf_find(rep, b);
 }
 
-// MeshUnion rows, owned by the consumer thread (warp 1) while the collapse runs
-struct Groups {
-    idx_t *ghead, *gtail;
-    cnt_t* glen;
-    unsigned long long* gn;
-    int gn_count, gn_cap, status;
-
-    // MeshUnion.union (mesh_union.py:11-12): row t += row s, multiplicities kept
-    __device__ void row_add(int s, int t) {
-        if (s == t) {
-            for (unsigned nt = (unsigned short)ghead[t]; nt != NIL16;) {
-                const unsigned long long w = gn[nt];
-                const unsigned nx = (unsigned)(w >> 32) & 0xFFFFu;
-                gn[nt] = gn_pack((unsigned)w & 0xFFFFu, (((unsigned)w >> 16) & 0xFFFFu) * 2u, nx);
-                nt = nx;
-            }
-            return;
+// __is_one_ring_valid (mesh_pool.py:95-100); the lists may hold stale / dead edge ids.  stamp[w] = tagA marks w as an
+// endpoint seen from v0; the lane that flips it to tagB counts it once.
+__device__ __forceinline__ int wop_one_ring(const WarpCtx& w, int lane, int v0, int v1, uint32_t tagA) {
+    const uint32_t tagB = tagA | 1u;
+    for (unsigned s = (unsigned)v0; s != NIL16; s = (unsigned short)w.slab_next[s]) {
+        const int start = w.slab_start[s], len = w.slab_len[s];
+        for (int i = lane; i < len; i += 32) {
+            const unsigned x = w.ve[start + i];
+            if (x == VE_TOMB) continue;
+            int a, b;
+            edge_ends(w.evp, w.rep, (int)x, a, b);
+            w.stamp[a] = tagA;
+            w.stamp[b] = tagA;
         }
-        for (unsigned ns = (unsigned short)ghead[s]; ns != NIL16;) {
-            const unsigned long long ws = gn[ns];
-            const unsigned m = (unsigned)ws & 0xFFFFu, c = ((unsigned)ws >> 16) & 0xFFFFu;
-            ns = (unsigned)(ws >> 32) & 0xFFFFu;
-            bool found = false;
-            for (unsigned nt = (unsigned short)ghead[t]; nt != NIL16;) {
-                const unsigned long long wt = gn[nt];
-                if (((unsigned)wt & 0xFFFFu) == m) {
-                    gn[nt] = wt + ((unsigned long long)c << 16);
-                    found = true;
-                    break;
-                }
-                nt = (unsigned)(wt >> 32) & 0xFFFFu;
+    }
+    __syncwarp();
+    int shared = 0;
+    for (unsigned s = (unsigned)v1; s != NIL16; s = (unsigned short)w.slab_next[s]) {
+        const int start = w.slab_start[s], len = w.slab_len[s];
+        for (int base = 0; base < len; base += 32) {
+            const int i = base + lane;
+            bool ha = false, hb = false;
+            const unsigned x = (i < len) ? (unsigned)w.ve[start + i] : VE_TOMB;
+            if (x != VE_TOMB) {
+                int a, b;
+                edge_ends(w.evp, w.rep, (int)x, a, b);
+                if (a != v0 && a != v1) ha = atomicCAS(&w.stamp[a], tagA, tagB) == tagA;
+                if (b != v0 && b != v1) hb = atomicCAS(&w.stamp[b], tagA, tagB) == tagA;
             }
-            if (!found) {
-                if (gn_count >= gn_cap) { status = MCNN_ST_GROUP_OVERFLOW; return; }
-                const unsigned id = (unsigned)gn_count++;
-                gn[id] = gn_pack(m, c, NIL16);
-                const unsigned tl = (unsigned short)gtail[t];
-                gn[tl] = (gn[tl] & ~(0xFFFFull << 32)) | ((unsigned long long)id << 32);
-                gtail[t] = (idx_t)id;
-                glen[t] = (cnt_t)(glen[t] + 1);
+            shared += __popc(__ballot_sync(0xffffffffu, ha)) + __popc(__ballot_sync(0xffffffffu, hb));
+        }
+    }
+    return shared;
+}
+
+// list.remove(x) on ve[v] (mesh.py:48) by search: the first occurrence in list order becomes a tombstone
+__device__ __forceinline__ bool wop_list_remove(const WarpCtx& w, int lane, int v, int x) {
+    for (unsigned s = (unsigned)v; s != NIL16; s = (unsigned short)w.slab_next[s]) {
+        const int start = w.slab_start[s], len = w.slab_len[s];
+        for (int base = 0; base < len; base += 32) {
+            const int i = base + lane;
+            const bool hit = (i < len) && ((int)w.ve[start + i] == x);
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            if (m != 0u) {
+                if (lane == __ffs(m) - 1) w.ve[start + i] = (uint16_t)VE_TOMB;
+                __syncwarp();
+                return true;
             }
         }
     }
-};
+    return false;
+}
 
+// Service loop of the helper warp: executes the posted operations in order until WOP_EXIT.
+__device__ void helper_warp_loop(const WarpCtx& w, WorkQueue* q, int lane, long long* hprof) {
+    volatile int* vhead = &q->head;
+    int seq = 0;                                             // operations finished so far
+    while (true) {
+        while (*vhead == seq) {}                             // all lanes poll the same word: no divergence
+        __syncwarp();
+        __threadfence_block();
+        volatile int* ep = q->ent[seq % WQ_CAP];
+        int4 rq;
+        rq.x = ep[0]; rq.y = ep[1]; rq.z = ep[2]; rq.w = ep[3];
+        ++seq;
+        if (rq.x == WOP_EXIT) break;
+#ifdef MCNN_POOL_PROF
+        const long long th_ = clock64();
+#endif
+        int r;
+        if (rq.x == WOP_ONE_RING) {
+            r = wop_one_ring(w, lane, rq.y, rq.z, (uint32_t)rq.w);
+        } else {                                             // WOP_REMOVE_SCAN: x leaves ve[a], then ve[b] (mesh.py:42-48)
+            r = wop_list_remove(w, lane, rq.z, rq.y) ? 1 : 0;
+            if (r) r = wop_list_remove(w, lane, rq.w, rq.y) ? 1 : 0;
+        }
+        if (lane == 0) {
+            *(volatile int*)&q->res = r;
+            __threadfence_block();
+            *(volatile int*)&q->res_seq = seq;
+        }
+        __syncwarp();
+        if (lane == 0) { __threadfence_block(); *(volatile int*)&q->done = seq; }
+#ifdef MCNN_POOL_PROF
+        if (lane == 0 && hprof) hprof[rq.x - 1] += clock64() - th_;
+#endif
+    }
+}
+
+// The collapse state as seen by lane 0 of warp 0 (the only thread that runs the reference's control flow).
 struct Collapse {
-    idx_t *gemm, *rep, *vhead, *vtail;
-    uint32_t *evp, *vn, *ulog;
-    cnt_t* stamp;
+    WorkQueue* q;             // list walks go to the helper warp
+    int posted;
+    idx_t *gemm, *rep, *slab_next, *chain_tail;
+    uint16_t *ve, *eposa, *eposb;
+    uint32_t *evp, *ulog;
     int8_t* sides;
     uint8_t* mask;
     double* vs;               // shared copy or nullptr
-    uint8_t* vmask_g;         // global v_mask of this mesh
+    uint8_t* vmask;           // shared copy of v_mask
     int32_t* log_unions;      // global or nullptr
     int union_cap;
     int nunions, ulog_cap;
     int ec, T, status;
     unsigned stamp_id;
 
-    __device__ __forceinline__ int find(int v) {
-        int p = rep[v];
-        while (p != v) {
-            const int gp = rep[p];
-            rep[v] = (idx_t)gp;
-            v = gp;
-            p = rep[v];
-        }
-        return v;
-    }
-    __device__ __forceinline__ void ends(int e, int& v0, int& v1) {
-        const uint32_t w = evp[e];
-        const int a = (int)(w & 0xFFFFu), b = (int)(w >> 16);
-        const int ra = rep[a], rb = rep[b];                 // both loads in flight before either branch
-        v0 = (ra == a) ? a : find(a);
-        v1 = (rb == b) ? b : find(b);
+#ifdef MCNN_POOL_PROF
+    long long prof[7] = {0, 0, 0, 0, 0, 0, 0};
+#define PROF_T(i, stmt) { const long long t_ = clock64(); stmt; prof[i] += clock64() - t_; }
+#else
+#define PROF_T(i, stmt) { stmt; }
+#endif
+    __device__ __forceinline__ void ends(int e, int& v0, int& v1) { edge_ends(evp, rep, e, v0, v1); }
+
+    __device__ __forceinline__ void post(int op, int a0, int a1, int a2) {
+        while (posted - *(volatile int*)&q->done >= WQ_CAP) {}
+#ifdef MCNN_POOL_PROF
+        const long long tp_ = clock64();
+#endif
+        volatile int* ep = q->ent[posted % WQ_CAP];
+        ep[0] = op; ep[1] = a0; ep[2] = a1; ep[3] = a2;
+        __threadfence_block();
+        *(volatile int*)&q->head = ++posted;
+#ifdef MCNN_POOL_PROF
+        prof[5] += clock64() - tp_;
+#endif
     }
 
-    // the union itself is applied by the consumer warp; the collapse only logs (source, target)
+    // MeshUnion.union (mesh_union.py:11-12) is only logged here; the rows are evaluated after the collapse
     __device__ __forceinline__ void group_union(int s, int t) {
         if (log_unions != nullptr && nunions < union_cap) { log_unions[2 * nunions] = s; log_unions[2 * nunions + 1] = t; }
+        if (s == t) status = MCNN_ST_DEGENERATE;
         if (nunions < ulog_cap) ulog[nunions] = (uint32_t)s | ((uint32_t)t << 16);
         else status = MCNN_ST_GROUP_OVERFLOW;
         ++nunions;
-    }
-
-    __device__ __forceinline__ bool row_has_hole(int e) const {
-        const unsigned long long row = *reinterpret_cast<const unsigned long long*>(gemm + 4 * e);
-        return (row & 0x8000800080008000ULL) != 0ULL;
     }
 
     // MeshPool.has_boundaries (mesh_pool.py:87-92)
@@ -231,24 +321,18 @@ struct Collapse {
     __device__ __forceinline__ static int other_side(int s) { return s + 1 - 2 * (s & 1); }
 
     // __get_invalids (mesh_pool.py:115-138): returns 0 or 3 edges; rewires around a valence-3 vertex
-    __device__ int get_invalids(int e, int side, int tri[3]) {
+    __device__ int get_invalids(int e, int side, int& t0, int& t1, int& t2) {
         const Face f = face_info(e, side);
-        const int oka[2] = {f.oka0, f.oka1}, okb[2] = {f.okb0, f.okb1};
-        int nsh = 0, si = 0, sj = 0;
-#pragma unroll
-        for (int i = 0; i < 2; ++i)
-#pragma unroll
-            for (int j = 0; j < 2; ++j)
-                if (oka[i] == okb[j]) {
-                    if (nsh == 0) { si = i; sj = j; }
-                    ++nsh;
-                }
+        int nsh = 0, mid = 0, ua = 0, ub = 0, usa = 0, usb = 0;
+        // shared items of (oka0, oka1) x (okb0, okb1), first match in the reference's iteration order
+        if (f.oka0 == f.okb0) { if (nsh == 0) { mid = f.oka0; ua = f.oka1; ub = f.okb1; usa = 1; usb = 1; } ++nsh; }
+        if (f.oka0 == f.okb1) { if (nsh == 0) { mid = f.oka0; ua = f.oka1; ub = f.okb0; usa = 1; usb = 0; } ++nsh; }
+        if (f.oka1 == f.okb0) { if (nsh == 0) { mid = f.oka1; ua = f.oka0; ub = f.okb1; usa = 0; usb = 1; } ++nsh; }
+        if (f.oka1 == f.okb1) { if (nsh == 0) { mid = f.oka1; ua = f.oka0; ub = f.okb0; usa = 0; usb = 0; } ++nsh; }
         if (nsh == 0) return 0;
         if (nsh != 1) { status = MCNN_ST_SHARED_ASSERT; return 0; }
-        const int mid = oka[si];
-        const int ua = oka[1 - si], ub = okb[1 - sj];
-        const int usa = sides[4 * f.ka + f.osa + 1 - si];
-        const int usb = sides[4 * f.kb + f.osb + 1 - sj];
+        usa = sides[4 * f.ka + f.osa + usa];
+        usb = sides[4 * f.kb + f.osb + usb];
         redirect(e, side, ua, usa);
         redirect(e, side + 1, ub, usb);
         redirect(ua, other_side(usa), ub, other_side(usb));
@@ -258,109 +342,75 @@ struct Collapse {
         group_union(mid, ua);
         group_union(f.kb, ub);
         group_union(mid, ub);
-        tri[0] = f.ka; tri[1] = f.kb; tri[2] = mid;
+        t0 = f.ka; t1 = f.kb; t2 = mid;
         return 3;
     }
 
     // __remove_triplete (mesh_pool.py:172-182): no remove_edge, the ve entries go stale
-    __device__ void remove_triplet(const int tri[3]) {
+    __device__ void remove_triplet(int t0, int t1, int t2) {
         int a0, a1, b0, b1, c0, c1;
-        ends(tri[0], a0, a1);
-        ends(tri[1], b0, b1);
-        ends(tri[2], c0, c1);
-        mask[tri[0]] = 0; mask[tri[1]] = 0; mask[tri[2]] = 0;
+        ends(t0, a0, a1);
+        ends(t1, b0, b1);
+        ends(t2, c0, c1);
+        mask[t0] = 0; mask[t1] = 0; mask[t2] = 0;
         ec -= 3;
         int count = 0, v = -1;
         if ((a0 == b0 || a0 == b1) && (a0 == c0 || a0 == c1)) { ++count; v = a0; }
         if (a1 != a0 && (a1 == b0 || a1 == b1) && (a1 == c0 || a1 == c1)) { ++count; v = a1; }
         if (count != 1) { status = MCNN_ST_VERTEX_ASSERT; return; }
-        vmask_g[v] = 0;
+        vmask[v] = 0;
     }
 
     // __clean_side (mesh_pool.py:74-85)
     __device__ bool clean_side(int e, int side) {
         if (ec <= T) return false;
-        int tri[3];
-        int n = get_invalids(e, side, tri);
+        int t0, t1, t2;
+        int n = get_invalids(e, side, t0, t1, t2);
         while (n != 0 && ec > T) {
             if (status) return false;
-            remove_triplet(tri);
+            remove_triplet(t0, t1, t2);
             if (status) return false;
             if (ec <= T) return false;
             if (has_boundaries(e)) return false;
-            n = get_invalids(e, side, tri);
+            n = get_invalids(e, side, t0, t1, t2);
         }
         return status == 0;
     }
 
-    // __is_one_ring_valid (mesh_pool.py:95-100); the lists may hold stale / dead edge ids.
-    // stamp[w] = (id << 2) | 1 marks w as a member of the first set, bit 1 = already counted in the intersection.
-    __device__ bool one_ring_valid(int e) {
+    __device__ __forceinline__ int wait_result() {
+#ifdef MCNN_POOL_PROF
+        const long long tw_ = clock64();
+#endif
+        while (*(volatile int*)&q->res_seq != posted) {}
+        __threadfence_block();
+#ifdef MCNN_POOL_PROF
+        prof[6] += clock64() - tw_;
+#endif
+        return *(volatile int*)&q->res;
+    }
+
+    // __is_one_ring_valid (mesh_pool.py:95-100), walked by the helper warp.  The answer depends on the vertex lists, the
+    // endpoints and the union-find only -- none of which __clean_side touches -- so it is requested before the side
+    // cleaning and collected after it.
+    __device__ void one_ring_request(int e) {
         int v0, v1;
         ends(e, v0, v1);
         ++stamp_id;
-        const unsigned tagA = (stamp_id << 2) | 1u;
-        unsigned nd = (unsigned short)vhead[v0];
-        if (nd != NIL16) {
-            uint32_t node = vn[nd];
-            while (true) {
-                const unsigned nx = node >> 16;
-                const uint32_t nextnode = (nx != NIL16) ? vn[nx] : 0u;      // next node in flight while this one is processed
-                int a, b;
-                ends((int)(node & 0xFFFFu), a, b);
-                stamp[a] = (cnt_t)tagA;
-                stamp[b] = (cnt_t)tagA;
-                if (nx == NIL16) break;
-                node = nextnode;
-            }
-        }
-        int shared = 0;
-        nd = (unsigned short)vhead[v1];
-        if (nd != NIL16) {
-            uint32_t node = vn[nd];
-            while (true) {
-                const unsigned nx = node >> 16;
-                const uint32_t nextnode = (nx != NIL16) ? vn[nx] : 0u;
-                int a, b;
-                ends((int)(node & 0xFFFFu), a, b);
-                const unsigned ta = stamp[a], tb = stamp[b];
-                if (a != v0 && a != v1 && ta == tagA) { stamp[a] = (cnt_t)(tagA | 2u); ++shared; }
-                if (b != a && b != v0 && b != v1 && tb == tagA) { stamp[b] = (cnt_t)(tagA | 2u); ++shared; }
-                if (nx == NIL16) break;
-                node = nextnode;
-            }
-        }
-        return shared == 2;
+        post(WOP_ONE_RING, v0, v1, (int)(stamp_id << 1));
     }
 
-    // list.remove(x) on ve[v] (mesh.py:48): first occurrence
-    __device__ bool list_remove(int v, int x) {
-        unsigned prev = NIL16;
-        unsigned nd = (unsigned short)vhead[v];
-        uint32_t node = (nd != NIL16) ? vn[nd] : 0u;
-        while (nd != NIL16) {
-            const unsigned nx = node >> 16;
-            if ((int)(node & 0xFFFFu) == x) {
-                if (prev == NIL16) vhead[v] = (idx_t)nx;
-                else vn[prev] = (vn[prev] & 0xFFFFu) | (nx << 16);
-                if ((unsigned short)vtail[v] == nd) vtail[v] = (idx_t)prev;
-                return true;
-            }
-            const uint32_t nextnode = (nx != NIL16) ? vn[nx] : 0u;
-            prev = nd;
-            nd = nx;
-            node = nextnode;
+    // Mesh.remove_edge (mesh.py:42-48): both list entries of x become tombstones
+    __device__ void remove_edge(int x) {
+        const unsigned ia = eposa[x], ib = eposb[x];
+        if (x != 0 && ia != NIL16 && ib != NIL16 && ve[ia] == x && ve[ib] == x) {
+            ve[ia] = (uint16_t)VE_TOMB;
+            ve[ib] = (uint16_t)VE_TOMB;
+            return;
         }
-        status = MCNN_ST_VE_REMOVE;
-        return false;
-    }
-
-    // Mesh.remove_edge (mesh.py:42-48)
-    __device__ bool remove_edge(int x) {
         int a, b;
         ends(x, a, b);
-        if (!list_remove(a, x)) return false;
-        return list_remove(b, x);
+        post(WOP_REMOVE_SCAN, x, a, b);
+        if (wait_result() != 1) status = MCNN_ST_VE_REMOVE;
     }
 
     // __pool_side (mesh_pool.py:102-113)
@@ -378,7 +428,7 @@ struct Collapse {
 
     // Mesh.merge_vertices (mesh.py:26-37)
     __device__ void merge_vertices(int e) {
-        if (!remove_edge(e)) return;
+        remove_edge(e);
         int v0, v1;
         ends(e, v0, v1);
         if (v0 == v1) { status = MCNN_ST_DEGENERATE; return; }
@@ -386,30 +436,29 @@ struct Collapse {
 #pragma unroll
             for (int k = 0; k < 3; ++k) vs[3 * v0 + k] = (vs[3 * v0 + k] + vs[3 * v1 + k]) / 2;
         }
-        vmask_g[v1] = 0;
-        // ve[v0].extend(ve[v1]) : the nodes move (ve[v1] is unreachable once every row holding v1 reads v0)
-        const unsigned h1 = (unsigned short)vhead[v1];
-        if (h1 != NIL16) {
-            if ((unsigned short)vhead[v0] == NIL16) vhead[v0] = (idx_t)h1;
-            else { const unsigned t0 = (unsigned short)vtail[v0]; vn[t0] = (vn[t0] & 0xFFFFu) | (h1 << 16); }
-            vtail[v0] = vtail[v1];
-            vhead[v1] = (idx_t)NIL16; vtail[v1] = (idx_t)NIL16;
-        }
+        vmask[v1] = 0;
+        // ve[v0].extend(ve[v1]) : v1's chain moves behind v0's (ve[v1] is unreachable once every row holding v1 reads v0)
+        slab_next[(unsigned short)chain_tail[v0]] = (idx_t)v1;
+        chain_tail[v0] = chain_tail[v1];
         rep[v1] = (idx_t)v0;          // edges[edges == v1] = v0 over every row
     }
 
     // __pool_edge (mesh_pool.py:58-72)
     __device__ int pool_edge(int e) {
-        if (has_boundaries(e)) return MCNN_POP_REJ_BOUNDARY;
-        if (!clean_side(e, 0)) return MCNN_POP_REJ_SIDE0;
-        if (!clean_side(e, 2)) return MCNN_POP_REJ_SIDE2;
-        if (!one_ring_valid(e)) return MCNN_POP_REJ_ONE_RING;
-        pool_side(e, 0);
+        bool r, side2 = false;
+        PROF_T(0, r = has_boundaries(e));
+        if (r) return MCNN_POP_REJ_BOUNDARY;
+        PROF_T(2, one_ring_request(e));
+        PROF_T(1, r = clean_side(e, 0));
+        if (r) PROF_T(1, r = clean_side(e, 2) ? true : (side2 = true, false));
+        const bool ring_ok = wait_result() == 2;             // always collected: the ring has one result slot
+        if (!r) return side2 ? MCNN_POP_REJ_SIDE2 : MCNN_POP_REJ_SIDE0;
+        if (!ring_ok) return MCNN_POP_REJ_ONE_RING;
+        PROF_T(3, pool_side(e, 0));
         if (status) return MCNN_POP_COLLAPSED;
-        pool_side(e, 2);
+        PROF_T(3, pool_side(e, 2));
         if (status) return MCNN_POP_COLLAPSED;
-        merge_vertices(e);
-        mask[e] = 0;
+        PROF_T(4, merge_vertices(e); mask[e] = 0);
         ec -= 1;
         return MCNN_POP_COLLAPSED;
     }
@@ -431,16 +480,17 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) pool_collapse_kernel(const mc
     uint8_t* mask = smem + L.mask;
     idx_t* order = reinterpret_cast<idx_t*>(smem + L.order);
     idx_t* rep = reinterpret_cast<idx_t*>(smem + L.rep);
-    idx_t* vhead = reinterpret_cast<idx_t*>(smem + L.vhead);
-    idx_t* vtail = reinterpret_cast<idx_t*>(smem + L.vtail);
-    cnt_t* stamp = reinterpret_cast<cnt_t*>(smem + L.stamp);
-    uint32_t* vn = reinterpret_cast<uint32_t*>(smem + L.vn);
-    idx_t* ghead = reinterpret_cast<idx_t*>(smem + L.ghead);
-    idx_t* gtail = reinterpret_cast<idx_t*>(smem + L.gtail);
-    cnt_t* glen = reinterpret_cast<cnt_t*>(smem + L.glen);
+    uint32_t* stamp = reinterpret_cast<uint32_t*>(smem + L.stamp);
+    uint16_t* slab_start = reinterpret_cast<uint16_t*>(smem + L.slab_start);
+    uint16_t* slab_len = reinterpret_cast<uint16_t*>(smem + L.slab_len);
+    idx_t* slab_next = reinterpret_cast<idx_t*>(smem + L.slab_next);
+    idx_t* chain_tail = reinterpret_cast<idx_t*>(smem + L.chain_tail);
+    uint8_t* vmask_s = smem + L.vmask;
+    uint16_t* ve = reinterpret_cast<uint16_t*>(smem + L.ve);
+    uint16_t* eposa = reinterpret_cast<uint16_t*>(smem + L.eposa);
+    uint16_t* eposb = reinterpret_cast<uint16_t*>(smem + L.eposb);
     uint32_t* ulog = reinterpret_cast<uint32_t*>(smem + L.ulog);
     unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem + L.keys);
-    unsigned long long* gn = reinterpret_cast<unsigned long long*>(smem + L.gn);
     int* scan = reinterpret_cast<int*>(smem + L.scan);
 
     const int32_t* g_gemm = a.gemm_in + (size_t)b * E_in * 4;
@@ -452,6 +502,8 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) pool_collapse_kernel(const mc
     double* g_vs = with_vs ? a.vs + (size_t)b * V * 3 : nullptr;
     const float* g_norms = a.norms + (size_t)b * E_in;
 
+    long long* clk = a.dbg_clocks ? a.dbg_clocks + (size_t)b * 16 : nullptr;
+    if (clk && tid == 0) clk[0] = clock64();
     // ---- phase A: load -----------------------------------------------------------------------------------
     for (int i = tid; i < 4 * n; i += POOL_THREADS) {
         gemm[i] = (idx_t)g_gemm[i];
@@ -460,18 +512,26 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) pool_collapse_kernel(const mc
     for (int i = tid; i < n; i += POOL_THREADS) {
         evp[i] = (uint32_t)(g_edges[2 * i] & 0xFFFF) | ((uint32_t)(g_edges[2 * i + 1] & 0xFFFF) << 16);
         mask[i] = 1;
+        eposa[i] = (uint16_t)NIL16;
+        eposb[i] = (uint16_t)NIL16;
     }
     for (int v = tid; v < V; v += POOL_THREADS) {
         rep[v] = (idx_t)v;
-        stamp[v] = 0;
+        stamp[v] = 0u;
+        vmask_s[v] = g_vmask[v];
         const int beg = g_ve_ptr[v], end = g_ve_ptr[v + 1];
-        vhead[v] = (idx_t)(beg < end ? beg : (int)NIL16);
-        vtail[v] = (idx_t)(beg < end ? end - 1 : (int)NIL16);
-        for (int i = beg; i < end; ++i)
-            vn[i] = ((uint32_t)g_ve_idx[i] & 0xFFFFu) | ((uint32_t)(i + 1 < end ? i + 1 : (int)NIL16) << 16);
+        slab_start[v] = (uint16_t)beg;
+        slab_len[v] = (uint16_t)(end - beg);
+        slab_next[v] = (idx_t)NIL16;
+        chain_tail[v] = (idx_t)v;
+    }
+    {
+        const int nve = min(g_ve_ptr[V], a.ve_cap);
+        for (int i = tid; i < nve; i += POOL_THREADS) ve[i] = (uint16_t)g_ve_idx[i];
     }
     if (with_vs)
         for (int i = tid; i < 3 * V; i += POOL_THREADS) vs_s[i] = g_vs[i];
+    if (clk && tid == 0) clk[1] = clock64();
     // ---- phase B: sort (norm bits, id) ascending == heapify + heappop order (mesh_pool.py:184-192, F2) ----
     const int np2 = L.npow2;
     for (int i = tid; i < np2; i += POOL_THREADS) {
@@ -494,21 +554,31 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) pool_collapse_kernel(const mc
         }
     }
     for (int i = tid; i < n; i += POOL_THREADS) order[i] = (idx_t)(keys[i] & 0xffffffffULL);
-    __syncthreads();
-    // ---- phase C: MeshUnion = identity (mesh_union.py:9) -----------------------------------------------------
-    for (int i = tid; i < n; i += POOL_THREADS) {
-        ghead[i] = (idx_t)i; gtail[i] = (idx_t)i; glen[i] = 1;
-        gn[i] = gn_pack((unsigned)i, 1u, NIL16);
+    // where the two list entries of every edge sit (the entry in the slab of its first / second endpoint)
+    for (int v = tid; v < V; v += POOL_THREADS) {
+        const int start = slab_start[v], len = slab_len[v];
+        for (int i = start; i < start + len; ++i) {
+            const int x = ve[i];
+            if (x >= n) continue;
+            const uint32_t w = evp[x];
+            if ((int)(w & 0xFFFFu) == v) eposa[x] = (uint16_t)i;
+            else if ((int)(w >> 16) == v) eposb[x] = (uint16_t)i;
+        }
     }
-    __shared__ int s_status, s_ec, s_gstatus;
-    __shared__ volatile int s_pub, s_done;
-    if (tid == 0) { s_pub = 0; s_done = 0; s_gstatus = 0; }
+    __shared__ int s_status, s_nunions, s_cursor, s_flag;
+    if (tid == 0) { s_cursor = 0; s_flag = 0; }
     __syncthreads();
-    // ---- phase D: the sequential collapse (mesh_pool.py:41-53); thread 32 applies the logged unions concurrently ----
+    if (clk && tid == 0) clk[2] = clock64();
+    // ---- phase D: the sequential collapse (mesh_pool.py:41-53) on thread 0; warp 1 serves the list operations ----------
+    __shared__ WorkQueue s_queue;
+    if (tid == 0) { s_queue.head = 0; s_queue.done = 0; s_queue.res = 0; s_queue.res_seq = 0; }
+    __syncthreads();
     if (tid == 0) {
         Collapse c;
-        c.gemm = gemm; c.rep = rep; c.vhead = vhead; c.vtail = vtail; c.evp = evp; c.vn = vn; c.ulog = ulog;
-        c.stamp = stamp; c.sides = sides; c.mask = mask; c.vs = vs_s; c.vmask_g = g_vmask;
+        c.q = &s_queue; c.posted = 0;
+        c.gemm = gemm; c.rep = rep; c.slab_next = slab_next; c.chain_tail = chain_tail; c.ve = ve; c.eposa = eposa; c.eposb = eposb;
+        c.evp = evp; c.ulog = ulog;
+        c.sides = sides; c.mask = mask; c.vs = vs_s; c.vmask = vmask_s;
         c.log_unions = a.log_unions ? a.log_unions + (size_t)b * a.log_cap * 8 * 2 : nullptr;
         c.union_cap = a.log_cap * 8; c.nunions = 0; c.ulog_cap = L.ulog_cap;
         c.ec = n; c.T = T; c.status = 0; c.stamp_id = 0;
@@ -522,40 +592,39 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) pool_collapse_kernel(const mc
             if (lp && p < a.log_cap) lp[p] = e;
             if (lo && p < a.log_cap) lo[p] = (int8_t)outcome;
             ++p;
-            if (outcome == MCNN_POP_COLLAPSED || c.nunions != s_pub) {
-                __threadfence_block();
-                s_pub = min(c.nunions, c.ulog_cap);
-            }
             if (c.status) break;
         }
-        __threadfence_block();
-        s_pub = min(c.nunions, c.ulog_cap);
-        __threadfence_block();
-        s_done = 1;
+        c.post(WOP_EXIT, 0, 0, 0);
         if (a.log_npops) a.log_npops[b] = p;
         if (a.log_nunions) a.log_nunions[b] = c.nunions;
         s_status = c.status;
-        s_ec = c.ec;
-    } else if (tid == 32) {
-        Groups g;
-        g.ghead = ghead; g.gtail = gtail; g.glen = glen; g.gn = gn;
-        g.gn_count = n; g.gn_cap = L.gn_cap; g.status = 0;
-        int seen = 0;
-        while (true) {
-            const int d = s_done;
-            const int avail = s_pub;
-            while (seen < avail) {
-                const uint32_t w = ulog[seen++];
-                if (g.status == 0) g.row_add((int)(w & 0xFFFFu), (int)(w >> 16));
-            }
-            if (d) break;
-            __nanosleep(64);
+        s_nunions = min(c.nunions, c.ulog_cap);
+        if (clk) {
+            clk[3] = clock64();
+            clk[7] = p;
+#ifdef MCNN_POOL_PROF
+            for (int i = 0; i < 5; ++i) clk[8 + i] = c.prof[i];
+            clk[5] = c.prof[5];
+            clk[6] = c.prof[6];
+#endif
         }
-        s_gstatus = g.status;
+    } else if (tid >= 32 && tid < 64) {
+        WarpCtx w;
+        w.ve = ve; w.slab_start = slab_start; w.slab_len = slab_len; w.slab_next = slab_next; w.chain_tail = chain_tail;
+        w.rep = rep; w.evp = evp; w.stamp = stamp;
+        helper_warp_loop(w, &s_queue, tid - 32, clk ? clk + 13 : nullptr);
     }
     __syncthreads();
-    int status = s_status ? s_status : s_gstatus;
+    int status = s_status;
+    const int U = s_nunions;
     // ---- phase E: Mesh.clean (mesh.py:50-71) + group export ---------------------------------------------------
+    // group evaluation scratch: occ / out-adjacency live where the sort keys were
+    int* occ = reinterpret_cast<int*>(smem + L.keys);                       // int32[n]
+    uint16_t* out0 = reinterpret_cast<uint16_t*>(occ + n);                  // u16[n]
+    uint16_t* out1 = out0 + n;                                               // u16[n]
+    int* outdeg = reinterpret_cast<int*>(smem + L.cnt32);                   // int32[n]  (later: column lengths)
+    int* rowlen = outdeg + n;                                                // int32[n]  (row lengths, then fill cursors)
+    for (int i = tid; i < n; i += POOL_THREADS) { occ[i] = 1; outdeg[i] = 0; rowlen[i] = 0; }
     // E1: survivor ranks; dead -> 0
     idx_t* newid = order;
     int carry = 0, total = 0;
@@ -569,6 +638,15 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) pool_collapse_kernel(const mc
     }
     total = carry;
     __syncthreads();
+    // out-adjacency of the pour DAG: every source has at most two targets
+    for (int k = tid; k < U; k += POOL_THREADS) {
+        const uint32_t w = ulog[k];
+        const int s = (int)(w & 0xFFFFu);
+        const int slot = atomicAdd(&outdeg[s], 1);
+        if (slot == 0) out0[s] = (uint16_t)(w >> 16);
+        else if (slot == 1) out1[s] = (uint16_t)(w >> 16);
+        else s_flag = MCNN_ST_GROUP_OVERFLOW;
+    }
     int32_t* o_gemm = a.gemm_out + (size_t)b * T * 4;
     int8_t* o_sides = a.sides_out + (size_t)b * T * 4;
     if (total > T) { status = status ? status : MCNN_ST_QUEUE_EMPTY; total = T; }   // only after an aborted collapse
@@ -595,121 +673,168 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) pool_collapse_kernel(const mc
         for (int i = tid; i < E_in; i += POOL_THREADS) a.edge_mask_out[(size_t)b * E_in + i] = (i < n) ? mask[i] : 0;
     if (with_vs)
         for (int i = tid; i < 3 * V; i += POOL_THREADS) g_vs[i] = vs_s[i];
-    // E3: ve lists -> CSR with re-indexed ids
+    for (int v = tid; v < V; v += POOL_THREADS) g_vmask[v] = vmask_s[v];
+    // E3: ve chains -> CSR with re-indexed ids (the list of a merged-away vertex is dropped: nothing can reach it)
     carry = 0;
     for (int base = 0; base < V; base += POOL_THREADS) {
         const int v = base + tid;
         int len = 0;
-        if (v < V)
-            for (unsigned nd = (unsigned short)vhead[v]; nd != NIL16; nd = vn[nd] >> 16) ++len;
+        const bool root = (v < V) && (rep[v] == v);
+        if (root)
+            for (unsigned s = (unsigned)v; s != NIL16; s = (unsigned short)slab_next[s]) {
+                const int start = slab_start[s], sl = slab_len[s];
+                for (int i = 0; i < sl; ++i) len += (ve[start + i] != VE_TOMB);
+            }
         int tot;
         const int pre = block_scan_excl(len, scan, tot);
         if (v < V) {
             int pos = carry + pre;
             g_ve_ptr[v] = pos;
-            for (unsigned nd = (unsigned short)vhead[v]; nd != NIL16;) {
-                const uint32_t w = vn[nd];
-                g_ve_idx[pos++] = newid[w & 0xFFFFu];
-                nd = w >> 16;
-            }
+            if (root)
+                for (unsigned s = (unsigned)v; s != NIL16; s = (unsigned short)slab_next[s]) {
+                    const int start = slab_start[s], sl = slab_len[s];
+                    for (int i = 0; i < sl; ++i) {
+                        const unsigned x = ve[start + i];
+                        if (x != VE_TOMB) g_ve_idx[pos++] = newid[x];
+                    }
+                }
         }
         carry += tot;
     }
     if (tid == 0) g_ve_ptr[V] = carry;
-    __syncthreads();
-    // E4: groups.  the ve node array is free now: occ_cnt / col_cnt live there (2 * int32[n] <= 4 * ve_cap bytes)
-    int* occ_cnt = reinterpret_cast<int*>(smem + L.vn);
-    int* col_cnt = occ_cnt + n;
-    for (int i = tid; i < 2 * n; i += POOL_THREADS) occ_cnt[i] = 0;
-    __syncthreads();
-    for (int i = tid; i < n; i += POOL_THREADS) {
-        const bool live = mask[i];
-        for (unsigned nd = (unsigned short)ghead[i]; nd != NIL16;) {
-            const unsigned long long w = gn[nd];
-            const int m = (int)((unsigned)w & 0xFFFFu);
-            atomicAdd(&occ_cnt[m], (int)(((unsigned)w >> 16) & 0xFFFFu));       // every row, un-clamped
-            if (live) atomicAdd(&col_cnt[m], 1);
-            nd = (unsigned)(w >> 32) & 0xFFFFu;
+    __syncthreads();                       // gemm / sides / evp are dead from here on; out-adjacency complete
+    // E4: MeshUnion.  (a) occurrences = number of paths starting at each edge: one reverse sweep over the log (a target is
+    // alive when it is poured into, so all of ITS pours come later in the log) by the last warp, while (b) the other warps
+    // walk the DAG forward from every old edge to the surviving rows that contain it (the CSC column).
+    uint16_t* cpool = reinterpret_cast<uint16_t*>(smem + L.gemm);           // u16[3n] column members, allocated by cursor
+    uint16_t* coff = cpool + 3 * n;                                          // u16[n]
+    uint16_t* rpool = reinterpret_cast<uint16_t*>(smem + L.evp);            // u16[<= 4n]: rows at their final CSR offsets
+    int* collen = reinterpret_cast<int*>(smem + L.ve);                      // int32[n]; the ve slabs were exported in E3
+    const int pool_cap = min(a.nnz_cap, 3 * n);
+    if (tid >= POOL_THREADS - 32) {
+        if (tid == POOL_THREADS - 32) {
+            uint32_t w = U > 0 ? ulog[U - 1] : 0u;
+            for (int k = U - 1; k >= 0; --k) {
+                const uint32_t wn = k > 0 ? ulog[k - 1] : 0u;
+                occ[w & 0xFFFFu] += occ[w >> 16];
+                w = wn;
+            }
+        }
+    } else {
+        uint16_t q[POOL_BFS_CAP], r[POOL_BFS_CAP];
+        for (int j = tid; j < n; j += POOL_THREADS - 32) {
+            int rn = 0;
+            if (mask[j]) {
+                if (newid[j] < T) r[rn++] = (uint16_t)newid[j];
+            } else {
+                int qn = 1;
+                q[0] = (uint16_t)j;
+                bool over = false;
+                for (int h = 0; h < qn; ++h) {
+                    const int x = q[h];
+                    const int d = min(outdeg[x], 2);
+                    for (int o = 0; o < d; ++o) {
+                        const int t = o ? out1[x] : out0[x];
+                        if (mask[t]) {
+                            const int nr = newid[t];
+                            if (nr >= T) continue;
+                            int k = 0;
+                            while (k < rn && r[k] != nr) ++k;
+                            if (k == rn) { if (rn < POOL_BFS_CAP) r[rn++] = (uint16_t)nr; else over = true; }
+                        } else {
+                            int k = 0;
+                            while (k < qn && q[k] != t) ++k;
+                            if (k == qn) { if (qn < POOL_BFS_CAP) q[qn++] = (uint16_t)t; else over = true; }
+                        }
+                    }
+                }
+                if (over) s_flag = MCNN_ST_GROUP_OVERFLOW;
+                for (int p = 1; p < rn; ++p) {                       // ascending pooled id
+                    const uint16_t v = r[p];
+                    int k = p;
+                    while (k > 0 && r[k - 1] > v) { r[k] = r[k - 1]; --k; }
+                    r[k] = v;
+                }
+            }
+            const int off = atomicAdd(&s_cursor, rn);
+            collen[j] = rn;
+            coff[j] = (uint16_t)min(off, 0xFFFF);
+            if (off + rn <= pool_cap)
+                for (int k = 0; k < rn; ++k) { cpool[off + k] = r[k]; atomicAdd(&rowlen[r[k]], 1); }
         }
     }
     __syncthreads();
+    if (status == 0 && s_flag) status = s_flag;
+    const int nnz = s_cursor;
+    const bool nnz_ok = nnz <= pool_cap;
+    if (!nnz_ok && status == 0) status = MCNN_ST_NNZ_OVERFLOW;
     float* o_occ = a.occ + (size_t)b * E_in;
-    for (int i = tid; i < E_in; i += POOL_THREADS) o_occ[i] = (i < n) ? (float)occ_cnt[i] : 1.f;
-    __syncthreads();
-    // CSR row pointers over the surviving rows (in new order == old order restricted to survivors)
+    for (int i = tid; i < E_in; i += POOL_THREADS) o_occ[i] = (i < n) ? (float)occ[i] : 1.f;
     int32_t* o_rowptr = a.grp_rowptr + (size_t)b * (T + 1);
     int32_t* o_cols = a.grp_cols + (size_t)b * a.nnz_cap;
     int32_t* o_colptr = a.grp_colptr + (size_t)b * (E_in + 1);
     int32_t* o_rows = a.grp_rows + (size_t)b * a.nnz_cap;
+    // CSC: column pointers + members (already ascending)
     carry = 0;
     for (int base = 0; base < n; base += POOL_THREADS) {
-        const int i = base + tid;
-        const int len = (i < n && mask[i] && newid[i] < T) ? glen[i] : 0;
-        int tot;
-        const int pre = block_scan_excl(len, scan, tot);
-        if (len) occ_cnt[i] = carry + pre;          // row start, reusing occ_cnt (already exported)
-        carry += tot;
-    }
-    const int nnz = carry;
-    __syncthreads();
-    const bool nnz_ok = nnz <= a.nnz_cap;
-    if (!nnz_ok && status == 0) status = MCNN_ST_NNZ_OVERFLOW;
-    for (int i = tid; i < n; i += POOL_THREADS) {
-        if (!(mask[i] && newid[i] < T)) continue;
-        const int r = newid[i];
-        const int start = occ_cnt[i];
-        o_rowptr[r] = start;
-        if (!nnz_ok) continue;
-        int len = 0;
-        for (unsigned nd = (unsigned short)ghead[i]; nd != NIL16;) {      // insertion sort, ascending member id
-            const unsigned long long w = gn[nd];
-            const int m = (int)((unsigned)w & 0xFFFFu);
-            int p = start + len;
-            while (p > start && o_cols[p - 1] > m) { o_cols[p] = o_cols[p - 1]; --p; }
-            o_cols[p] = m;
-            ++len;
-            nd = (unsigned)(w >> 32) & 0xFFFFu;
-        }
-    }
-    for (int r = total + tid; r <= T; r += POOL_THREADS) o_rowptr[r] = nnz;
-    __syncthreads();
-    // CSC: column pointers, then a counting fill followed by a per-column insertion sort (ascending pooled id)
-    carry = 0;
-    for (int base = 0; base < n; base += POOL_THREADS) {
-        const int i = base + tid;
-        const int cnt = (i < n) ? col_cnt[i] : 0;
+        const int j = base + tid;
+        const int cnt = (j < n) ? collen[j] : 0;
         int tot;
         const int pre = block_scan_excl(cnt, scan, tot);
-        if (i < n) { o_colptr[i] = carry + pre; occ_cnt[i] = carry + pre; }   // occ_cnt = fill cursor
+        if (j < n) {
+            o_colptr[j] = carry + pre;
+            if (nnz_ok) {
+                const int off = coff[j];
+                for (int k = 0; k < cnt; ++k) o_rows[carry + pre + k] = cpool[off + k];
+            }
+            collen[j] = carry + pre;                    // keep the column start for the row fill below
+        }
         carry += tot;
     }
     for (int i = n + tid; i <= E_in; i += POOL_THREADS) o_colptr[i] = nnz;
+    // CSR: row pointers over the surviving rows, fill through per-row cursors, sort each row, write out
+    carry = 0;
+    for (int base = 0; base < total; base += POOL_THREADS) {
+        const int r = base + tid;
+        const int len = (r < total) ? rowlen[r] : 0;
+        int tot;
+        const int pre = block_scan_excl(len, scan, tot);
+        if (r < total) {
+            o_rowptr[r] = carry + pre;
+            occ[r] = carry + pre;                       // occ is exported: reuse as row start ...
+            rowlen[r] = carry + pre;                    // ... and rowlen as the fill cursor
+        }
+        carry += tot;
+    }
+    for (int r = total + tid; r <= T; r += POOL_THREADS) o_rowptr[r] = nnz;
     __syncthreads();
     if (nnz_ok) {
-        for (int i = tid; i < n; i += POOL_THREADS) {
-            if (!(mask[i] && newid[i] < T)) continue;
-            const int r = newid[i];
-            for (unsigned nd = (unsigned short)ghead[i]; nd != NIL16;) {
-                const unsigned long long w = gn[nd];
-                const int pos = atomicAdd(&occ_cnt[(int)((unsigned)w & 0xFFFFu)], 1);
-                o_rows[pos] = r;
-                nd = (unsigned)(w >> 32) & 0xFFFFu;
+        for (int j = tid; j < n; j += POOL_THREADS) {
+            const int off = coff[j];
+            const int cnt = ((j + 1 < n) ? collen[j + 1] : nnz) - collen[j];
+            for (int k = 0; k < cnt; ++k) {
+                const int pos = atomicAdd(&rowlen[cpool[off + k]], 1);
+                rpool[pos] = (uint16_t)j;
             }
         }
         __syncthreads();
-        for (int j = tid; j < n; j += POOL_THREADS) {
-            const int beg = o_colptr[j], end = beg + col_cnt[j];
+        for (int r = tid; r < total; r += POOL_THREADS) {
+            const int beg = occ[r], end = rowlen[r];
             for (int p = beg + 1; p < end; ++p) {
-                const int v = o_rows[p];
-                int q = p;
-                while (q > beg && o_rows[q - 1] > v) { o_rows[q] = o_rows[q - 1]; --q; }
-                o_rows[q] = v;
+                const uint16_t v = rpool[p];
+                int k = p;
+                while (k > beg && rpool[k - 1] > v) { rpool[k] = rpool[k - 1]; --k; }
+                rpool[k] = v;
             }
         }
+        __syncthreads();
+        for (int i = tid; i < nnz; i += POOL_THREADS) o_cols[i] = rpool[i];
     }
+    if (clk) __syncthreads();
     if (tid == 0) {
         a.ec_out[b] = total;
         a.status[b] = status;
+        if (clk) clk[4] = clock64();
     }
 }
 
@@ -844,8 +969,8 @@ extern "C" int mcnn_pool_collapse(const mcnn_pool_args* a, void* stream) {
         !a->norms || !a->edges || !a->ve_ptr || !a->ve_idx || !a->v_mask || !a->gemm_out || !a->sides_out ||
         !a->ec_out || !a->grp_rowptr || !a->grp_cols || !a->grp_colptr || !a->grp_rows || !a->occ || !a->status)
         return MCNN_E_BADARG;
-    if (a->E_in > 10900 || a->V > 32767 || a->ve_cap > 32767 || a->ve_cap < 2 * 0) return MCNN_E_TOO_LARGE;
-    if ((size_t)a->ve_cap * sizeof(uint32_t) < (size_t)a->E_in * 2 * sizeof(int)) return MCNN_E_BADARG;  // occ/col counters alias the ve nodes
+    if (a->E_in > 10900 || a->V > 32767 || a->ve_cap > 65535) return MCNN_E_TOO_LARGE;      // 16-bit ids in shared memory
+    if (a->ve_cap < 2 * a->E_in) return MCNN_E_BADARG;                                        // the column lengths reuse the ve slabs
     const size_t smem = pool_layout(a->E_in, a->V, a->ve_cap, a->vs != nullptr).total;
     if (smem > mcnn_pool_smem_limit()) return MCNN_E_TOO_LARGE;
     static size_t configured = 0;

@@ -92,7 +92,7 @@ class PoolRecord:
     """What one MeshPool call leaves behind for MeshUnpool / backward: MeshUnion rows as CSR + CSC and the
     un-clamped occurrences (mesh.py:182-192)."""
     __slots__ = ('E_in', 'T', 'nnz_cap', 'rowptr', 'cols', 'colptr', 'rows', 'occ', 'status', 'level_in', 'level_out',
-                 'norms', 'logs', 'edge_mask')
+                 'norms', 'logs', 'edge_mask', 'clocks')
 
 
 class MeshBatch:
@@ -174,6 +174,7 @@ class MeshBatch:
         self.version = 0
         self._pristine = None
         self.keep_logs = False
+        self.keep_clocks = False
         for i, m in enumerate(meshes):
             m._attach(self, i)
 
@@ -269,6 +270,10 @@ class MeshBatch:
             a.log_nunions, a.log_unions = lg['nunions'].data_ptr(), lg['unions'].data_ptr()
             a.edge_mask_out = rec.edge_mask.data_ptr()
             rec.logs = lg
+        rec.clocks = None
+        if self.keep_clocks:
+            rec.clocks = torch.zeros(B, 16, dtype=torch.int64, device=dev)
+            a.dbg_clocks = rec.clocks.data_ptr()
         with profiler.span('pool_collapse', B=B, E_in=E_in, T=T):
             _lib.check(L.mcnn_pool_collapse(a, _lib.current_stream()), 'mcnn_pool_collapse')
         new = Level(T, gemm_out, sides_out, ec_out)

@@ -1,0 +1,42 @@
+"""Phase breakdown of the MeshPool collapse kernel (SM clocks at the phase boundaries of every mesh's CTA) on the pool
+chain of a bench config.  python tools/pool_phases.py [cubes|humanseg]"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+import bench
+from meshcnn_b200.mesh import Mesh, MeshBatch
+from meshcnn_b200.mesh_pool import MeshPool
+
+name = sys.argv[1] if len(sys.argv) > 1 else 'cubes'
+cfg = bench.CONFIGS[name]
+dev = torch.device('cuda:0')
+B, E = cfg['B'], cfg['E']
+datas, x, labels = bench.make_inputs(cfg, B, 0)
+meshes = [Mesh(data=d) for d in datas]
+batch = MeshBatch(meshes, E, dev)
+batch.keep_clocks = True
+torch.manual_seed(0)
+names = ['load', 'sort', 'collapse', 'clean + groups export']
+net = bench.build_net(cfg, 'ours').to(dev).train()
+xd = torch.from_numpy(x).to(dev)
+with torch.no_grad():
+    net(xd, meshes)
+torch.cuda.synchronize()
+batch.check()
+for rec in batch.records:
+    clk = rec.clocks.cpu().numpy().astype(np.float64)
+    d = np.diff(clk[:, :5], axis=1) / 1.965e3            # us at 1965 MHz
+    tot = (clk[:, 4] - clk[:, 0]) / 1.965e3
+    print('%s pool %d -> %d: CTA total mean %.1f max %.1f us' % (name, rec.E_in, rec.T, tot.mean(), tot.max()))
+    for i, nm in enumerate(names):
+        print('    %-14s mean %7.1f  max %7.1f us' % (nm, d[:, i].mean(), d[:, i].max()))
+    print('    pops mean %.1f max %d; removed edges %d' % (clk[:, 7].mean(), clk[:, 7].max(), rec.E_in - rec.T))
+    if clk[:, 8:13].sum() > 0:
+        for i, nm in enumerate(['has_boundaries', 'clean_side x2', 'one_ring_valid', 'pool_side x2', 'merge+kill']):
+            print('    . %-14s mean %7.1f us' % (nm, clk[:, 8 + i].mean() / 1.965e3))
+        print('    . post() %.1f us, one-ring wait %.1f us; helper busy: one_ring %.1f remove_edge %.1f concat %.1f us' % tuple(
+            clk[:, i].mean() / 1.965e3 for i in (5, 6, 13, 14, 15)))
