@@ -154,9 +154,9 @@ typedef struct {
     int32_t* log_nunions;     /* [B]             */
     int32_t* log_unions;      /* [B][8*log_cap][2] pairs (src, dst)                                      */
     int32_t* edge_mask_out;   /* [B][E_in] survivor mask (1/0) or NULL                                   */
-    long long* dbg_clocks;    /* [B][16] SM clock at the phase boundaries of each mesh's CTA (diagnostics) or NULL:
+    long long* dbg_clocks;    /* [B][24] SM clock at the phase boundaries of each mesh's CTA (diagnostics) or NULL:
                                  0 start, 1 loaded, 2 sorted, 3 collapse done, 4 unions applied, 5 topology written, 6 end;
-                                 7 = pops; 8..12 = cycles per collapse stage (only in -DMCNN_POOL_PROF builds)          */
+                                 7 = pops; 8..18 = cycles per collapse stage (only in -DMCNN_POOL_PROF builds)          */
 } mcnn_pool_args;
 
 /* __pool_main for every mesh of the batch, one CTA per mesh (mesh_pool.py:41-203 + mesh.py:26-71 +

@@ -145,35 +145,76 @@ __device__ __forceinline__ void edge_ends(const uint32_t* evp, idx_t* rep, int e
 }
 
 // __is_one_ring_valid (mesh_pool.py:95-100); the lists may hold stale / dead edge ids.  stamp[w] = tagA marks w as an
-// endpoint seen from v0; the lane that flips it to tagB counts it once.
-__device__ __forceinline__ int wop_one_ring(const WarpCtx& w, int lane, int v0, int v1, uint32_t tagA) {
+// endpoint seen from v0; the lane that flips it to tagB counts it once.  The first slab of both lists (the whole list
+// unless a vertex was merged within this level) is fetched and resolved together, so the two dependent load chains overlap.
+__device__ __forceinline__ int wop_one_ring(const WarpCtx& w, int lane, int v0, int v1, uint32_t tagA, long long* hp) {
     const uint32_t tagB = tagA | 1u;
-    for (unsigned s = (unsigned)v0; s != NIL16; s = (unsigned short)w.slab_next[s]) {
-        const int start = w.slab_start[s], len = w.slab_len[s];
-        for (int i = lane; i < len; i += 32) {
-            const unsigned x = w.ve[start + i];
-            if (x == VE_TOMB) continue;
-            int a, b;
-            edge_ends(w.evp, w.rep, (int)x, a, b);
-            w.stamp[a] = tagA;
-            w.stamp[b] = tagA;
+#ifdef MCNN_POOL_PROF
+    const long long t0_ = clock64();
+#endif
+    const int start0 = w.slab_start[v0], len0 = w.slab_len[v0];
+    const int start1 = w.slab_start[v1], len1 = w.slab_len[v1];
+    const unsigned next0 = (unsigned short)w.slab_next[v0], next1 = (unsigned short)w.slab_next[v1];
+    const unsigned x0 = (lane < len0) ? (unsigned)w.ve[start0 + lane] : VE_TOMB;
+    const unsigned x1 = (lane < len1) ? (unsigned)w.ve[start1 + lane] : VE_TOMB;
+    int a0 = 0, b0 = 0, a1 = 0, b1 = 0;
+    if (x0 != VE_TOMB) edge_ends(w.evp, w.rep, (int)x0, a0, b0);
+    if (x1 != VE_TOMB) edge_ends(w.evp, w.rep, (int)x1, a1, b1);
+    if (x0 != VE_TOMB) { w.stamp[a0] = tagA; w.stamp[b0] = tagA; }
+#ifdef MCNN_POOL_PROF
+    const long long t1_ = clock64();
+#endif
+    // the rest of the first list: entries 32.. of the first slab, then the slabs linked behind it
+    {
+        unsigned s = (unsigned)v0;
+        int start = start0, len = len0, first = 32;
+        while (true) {
+            for (int i = first + lane; i < len; i += 32) {
+                const unsigned x = w.ve[start + i];
+                if (x == VE_TOMB) continue;
+                int a, b;
+                edge_ends(w.evp, w.rep, (int)x, a, b);
+                w.stamp[a] = tagA;
+                w.stamp[b] = tagA;
+            }
+            s = (s == (unsigned)v0) ? next0 : (unsigned)(unsigned short)w.slab_next[s];
+            if (s == NIL16) break;
+            start = w.slab_start[s]; len = w.slab_len[s]; first = 0;
         }
     }
     __syncwarp();
-    int shared = 0;
-    for (unsigned s = (unsigned)v1; s != NIL16; s = (unsigned short)w.slab_next[s]) {
-        const int start = w.slab_start[s], len = w.slab_len[s];
-        for (int base = 0; base < len; base += 32) {
-            const int i = base + lane;
-            bool ha = false, hb = false;
-            const unsigned x = (i < len) ? (unsigned)w.ve[start + i] : VE_TOMB;
-            if (x != VE_TOMB) {
-                int a, b;
-                edge_ends(w.evp, w.rep, (int)x, a, b);
-                if (a != v0 && a != v1) ha = atomicCAS(&w.stamp[a], tagA, tagB) == tagA;
-                if (b != v0 && b != v1) hb = atomicCAS(&w.stamp[b], tagA, tagB) == tagA;
+#ifdef MCNN_POOL_PROF
+    const long long t2_ = clock64();
+#endif
+    bool ha = false, hb = false;
+    if (x1 != VE_TOMB) {
+        if (a1 != v0 && a1 != v1) ha = atomicCAS(&w.stamp[a1], tagA, tagB) == tagA;
+        if (b1 != v0 && b1 != v1) hb = atomicCAS(&w.stamp[b1], tagA, tagB) == tagA;
+    }
+    int shared = __popc(__ballot_sync(0xffffffffu, ha)) + __popc(__ballot_sync(0xffffffffu, hb));
+#ifdef MCNN_POOL_PROF
+    const long long t3_ = clock64();
+    if (lane == 0 && hp) { hp[0] += t1_ - t0_; hp[1] += t2_ - t1_; hp[2] += t3_ - t2_; }
+#endif
+    {
+        unsigned s = (unsigned)v1;
+        int start = start1, len = len1, first = 32;
+        while (true) {
+            for (int base = first; base < len; base += 32) {
+                const int i = base + lane;
+                const unsigned x = (i < len) ? (unsigned)w.ve[start + i] : VE_TOMB;
+                ha = false; hb = false;
+                if (x != VE_TOMB) {
+                    int a, b;
+                    edge_ends(w.evp, w.rep, (int)x, a, b);
+                    if (a != v0 && a != v1) ha = atomicCAS(&w.stamp[a], tagA, tagB) == tagA;
+                    if (b != v0 && b != v1) hb = atomicCAS(&w.stamp[b], tagA, tagB) == tagA;
+                }
+                shared += __popc(__ballot_sync(0xffffffffu, ha)) + __popc(__ballot_sync(0xffffffffu, hb));
             }
-            shared += __popc(__ballot_sync(0xffffffffu, ha)) + __popc(__ballot_sync(0xffffffffu, hb));
+            s = (s == (unsigned)v1) ? next1 : (unsigned)(unsigned short)w.slab_next[s];
+            if (s == NIL16) break;
+            start = w.slab_start[s]; len = w.slab_len[s]; first = 0;
         }
     }
     return shared;
@@ -215,7 +256,7 @@ __device__ void helper_warp_loop(const WarpCtx& w, WorkQueue* q, int lane, long 
 #endif
         int r;
         if (rq.x == WOP_ONE_RING) {
-            r = wop_one_ring(w, lane, rq.y, rq.z, (uint32_t)rq.w);
+            r = wop_one_ring(w, lane, rq.y, rq.z, (uint32_t)rq.w, hprof ? hprof + 3 : nullptr);
         } else {                                             // WOP_REMOVE_SCAN: x leaves ve[a], then ve[b] (mesh.py:42-48)
             r = wop_list_remove(w, lane, rq.z, rq.y) ? 1 : 0;
             if (r) r = wop_list_remove(w, lane, rq.w, rq.y) ? 1 : 0;
@@ -502,7 +543,7 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) pool_collapse_kernel(const mc
     double* g_vs = with_vs ? a.vs + (size_t)b * V * 3 : nullptr;
     const float* g_norms = a.norms + (size_t)b * E_in;
 
-    long long* clk = a.dbg_clocks ? a.dbg_clocks + (size_t)b * 16 : nullptr;
+    long long* clk = a.dbg_clocks ? a.dbg_clocks + (size_t)b * 24 : nullptr;
     if (clk && tid == 0) clk[0] = clock64();
     // ---- phase A: load -----------------------------------------------------------------------------------
     for (int i = tid; i < 4 * n; i += POOL_THREADS) {
@@ -565,8 +606,8 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) pool_collapse_kernel(const mc
             else if ((int)(w >> 16) == v) eposb[x] = (uint16_t)i;
         }
     }
-    __shared__ int s_status, s_nunions, s_cursor, s_flag;
-    if (tid == 0) { s_cursor = 0; s_flag = 0; }
+    __shared__ int s_status, s_nunions, s_cursor, s_flag, s_ndead;
+    if (tid == 0) { s_cursor = 0; s_flag = 0; s_ndead = 0; }
     __syncthreads();
     if (clk && tid == 0) clk[2] = clock64();
     // ---- phase D: the sequential collapse (mesh_pool.py:41-53) on thread 0; warp 1 serves the list operations ----------
@@ -647,6 +688,7 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) pool_collapse_kernel(const mc
         else if (slot == 1) out1[s] = (uint16_t)(w >> 16);
         else s_flag = MCNN_ST_GROUP_OVERFLOW;
     }
+    if (clk) { __syncthreads(); if (tid == 0) clk[19] = clock64(); }
     int32_t* o_gemm = a.gemm_out + (size_t)b * T * 4;
     int8_t* o_sides = a.sides_out + (size_t)b * T * 4;
     if (total > T) { status = status ? status : MCNN_ST_QUEUE_EMPTY; total = T; }   // only after an aborted collapse
@@ -674,6 +716,7 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) pool_collapse_kernel(const mc
     if (with_vs)
         for (int i = tid; i < 3 * V; i += POOL_THREADS) g_vs[i] = vs_s[i];
     for (int v = tid; v < V; v += POOL_THREADS) g_vmask[v] = vmask_s[v];
+    if (clk) { __syncthreads(); if (tid == 0) clk[20] = clock64(); }
     // E3: ve chains -> CSR with re-indexed ids (the list of a merged-away vertex is dropped: nothing can reach it)
     carry = 0;
     for (int base = 0; base < V; base += POOL_THREADS) {
@@ -703,30 +746,51 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) pool_collapse_kernel(const mc
     }
     if (tid == 0) g_ve_ptr[V] = carry;
     __syncthreads();                       // gemm / sides / evp are dead from here on; out-adjacency complete
-    // E4: MeshUnion.  (a) occurrences = number of paths starting at each edge: one reverse sweep over the log (a target is
-    // alive when it is poured into, so all of ITS pours come later in the log) by the last warp, while (b) the other warps
-    // walk the DAG forward from every old edge to the surviving rows that contain it (the CSC column).
+    if (clk) { __syncthreads(); if (tid == 0) clk[21] = clock64(); }
+    // E4: MeshUnion.  (a) occurrences = number of paths starting at each edge:  occ[s] = 1 + sum over the pours s -> t of
+    // occ[t].  A target is alive when it is poured into, so the pours form a DAG; sweeping all edges in parallel until
+    // nothing changes reaches its unique fixed point after (depth + 1) rounds.
     uint16_t* cpool = reinterpret_cast<uint16_t*>(smem + L.gemm);           // u16[3n] column members, allocated by cursor
     uint16_t* coff = cpool + 3 * n;                                          // u16[n]
     uint16_t* rpool = reinterpret_cast<uint16_t*>(smem + L.evp);            // u16[<= 4n]: rows at their final CSR offsets
     int* collen = reinterpret_cast<int*>(smem + L.ve);                      // int32[n]; the ve slabs were exported in E3
     const int pool_cap = min(a.nnz_cap, 3 * n);
-    if (tid >= POOL_THREADS - 32) {
-        if (tid == POOL_THREADS - 32) {
-            uint32_t w = U > 0 ? ulog[U - 1] : 0u;
-            for (int k = U - 1; k >= 0; --k) {
-                const uint32_t wn = k > 0 ? ulog[k - 1] : 0u;
-                occ[w & 0xFFFFu] += occ[w >> 16];
-                w = wn;
-            }
+    for (int round = 0; round <= n; ++round) {
+        int changed = 0;
+        for (int j = tid; j < n; j += POOL_THREADS) {
+            const int d = outdeg[j];
+            if (d == 0) continue;
+            int v = 1 + occ[out0[j]];
+            if (d > 1) v += occ[out1[j]];
+            if (v != occ[j]) { occ[j] = v; changed = 1; }
         }
-    } else {
-        uint16_t q[POOL_BFS_CAP], r[POOL_BFS_CAP];
-        for (int j = tid; j < n; j += POOL_THREADS - 32) {
+        if (!__syncthreads_or(changed)) break;
+    }
+    if (clk) { __syncthreads(); if (tid == 0) clk[22] = clock64(); }
+    // (b) the CSC column of every old edge: a survivor sits in its own row; a dead edge is walked forward through the DAG
+    // to the surviving rows that contain it.  Dead edges are compacted first so that every thread gets at most a few.
+    uint16_t* deadlist = reinterpret_cast<uint16_t*>(smem + L.ulog);        // u16[n]; the log is consumed
+    for (int j = tid; j < n; j += POOL_THREADS) {
+        if (mask[j]) {
+            const int nr = newid[j];
             int rn = 0;
-            if (mask[j]) {
-                if (newid[j] < T) r[rn++] = (uint16_t)newid[j];
-            } else {
+            if (nr < T) rn = 1;
+            const int off = atomicAdd(&s_cursor, rn);
+            collen[j] = rn;
+            coff[j] = (uint16_t)min(off, 0xFFFF);
+            if (rn && off + rn <= pool_cap) { cpool[off] = (uint16_t)nr; atomicAdd(&rowlen[nr], 1); }
+        } else {
+            deadlist[atomicAdd(&s_ndead, 1)] = (uint16_t)j;
+        }
+    }
+    __syncthreads();
+    {
+        uint16_t q[POOL_BFS_CAP], r[POOL_BFS_CAP];
+        const int ndead = s_ndead;
+        for (int di = tid; di < ndead; di += POOL_THREADS) {
+            const int j = deadlist[di];
+            int rn = 0;
+            {
                 int qn = 1;
                 q[0] = (uint16_t)j;
                 bool over = false;
@@ -768,6 +832,7 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) pool_collapse_kernel(const mc
     const int nnz = s_cursor;
     const bool nnz_ok = nnz <= pool_cap;
     if (!nnz_ok && status == 0) status = MCNN_ST_NNZ_OVERFLOW;
+    if (clk) { __syncthreads(); if (tid == 0) clk[23] = clock64(); }
     float* o_occ = a.occ + (size_t)b * E_in;
     for (int i = tid; i < E_in; i += POOL_THREADS) o_occ[i] = (i < n) ? (float)occ[i] : 1.f;
     int32_t* o_rowptr = a.grp_rowptr + (size_t)b * (T + 1);
@@ -818,17 +883,18 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) pool_collapse_kernel(const mc
             }
         }
         __syncthreads();
-        for (int r = tid; r < total; r += POOL_THREADS) {
-            const int beg = occ[r], end = rowlen[r];
-            for (int p = beg + 1; p < end; ++p) {
-                const uint16_t v = rpool[p];
-                int k = p;
-                while (k > beg && rpool[k - 1] > v) { rpool[k] = rpool[k - 1]; --k; }
-                rpool[k] = v;
+        // every (column j, row r) pair finds the rank of j inside row r and writes it to its sorted place
+        for (int j = tid; j < n; j += POOL_THREADS) {
+            const int off = coff[j];
+            const int cnt = ((j + 1 < n) ? collen[j + 1] : nnz) - collen[j];
+            for (int k = 0; k < cnt; ++k) {
+                const int r = cpool[off + k];
+                const int beg = occ[r], end = rowlen[r];
+                int rank = 0;
+                for (int p = beg; p < end; ++p) rank += (rpool[p] < j);
+                o_cols[beg + rank] = j;
             }
         }
-        __syncthreads();
-        for (int i = tid; i < nnz; i += POOL_THREADS) o_cols[i] = rpool[i];
     }
     if (clk) __syncthreads();
     if (tid == 0) {

@@ -272,7 +272,7 @@ class MeshBatch:
             rec.logs = lg
         rec.clocks = None
         if self.keep_clocks:
-            rec.clocks = torch.zeros(B, 16, dtype=torch.int64, device=dev)
+            rec.clocks = torch.zeros(B, 24, dtype=torch.int64, device=dev)
             a.dbg_clocks = rec.clocks.data_ptr()
         with profiler.span('pool_collapse', B=B, E_in=E_in, T=T):
             _lib.check(L.mcnn_pool_collapse(a, _lib.current_stream()), 'mcnn_pool_collapse')

@@ -40,3 +40,7 @@ for rec in batch.records:
             print('    . %-14s mean %7.1f us' % (nm, clk[:, 8 + i].mean() / 1.965e3))
         print('    . post() %.1f us, one-ring wait %.1f us; helper busy: one_ring %.1f remove_edge %.1f concat %.1f us' % tuple(
             clk[:, i].mean() / 1.965e3 for i in (5, 6, 13, 14, 15)))
+        e = [clk[:, 3]] + [clk[:, i] for i in (19, 20, 21, 22, 23)] + [clk[:, 4]]
+        print('    . export: E1+adjacency %.1f | E2 %.1f | E3 %.1f | occ %.1f | BFS columns %.1f | CSC/CSR write %.1f us (mean);  max %s' % (
+            tuple(((e[i + 1] - e[i]) / 1.965e3).mean() for i in range(6)) + (' '.join('%.0f' % ((e[i + 1] - e[i]) / 1.965e3).max() for i in range(6)),)))
+        print('    . one_ring inside: fetch+resolve+stamp %.1f, syncwarp %.1f, cas+ballot %.1f us' % tuple(clk[:, i].mean() / 1.965e3 for i in (16, 17, 18)))
