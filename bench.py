@@ -126,41 +126,49 @@ def cpu_port_meshes_per_s(cfg, sample_B, steps, warmup):
 # helpers
 # -----------------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    QUERY = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
-            'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+    """Samples SM clock + throttle reasons of one GPU through NVML from a background thread (every ~2 ms) while the timed
+    region runs; falls back to one nvidia-smi query if NVML is unavailable."""
+    REASONS = {'hw_slowdown': 0x8, 'sw_thermal_slowdown': 0x20, 'hw_thermal_slowdown': 0x40, 'sw_power_cap': 0x4}
 
     def __init__(self, index):
-        self.p = None
+        import threading
+        self.sm, self.reasons, self.max_mhz, self.err = [], set(), None, None
+        self._stop = threading.Event()
+        self._h = None
         try:
-            self.p = subprocess.Popen(['nvidia-smi', '--query-gpu=' + self.QUERY, '--format=csv,noheader,nounits', '-lms', '100',
-                                       '-i', str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-        except Exception:
-            self.p = None
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:                                       # noqa: BLE001
+            self.err = 'nvml: %s' % e
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+
+    def _run(self):
+        if self._h is None:
+            return
+        nv = self._nv
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
+                for name, bit in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception as e:                                   # noqa: BLE001
+                self.err = 'nvml: %s' % e
+                return
+            time.sleep(0.002)
 
     def stop(self):
-        if self.p is None:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        self.p.terminate()
-        try:
-            out, _ = self.p.communicate(timeout=5)
-        except Exception:
-            self.p.kill()
-            out = ''
-        sm, mx, reasons = [], [], set()
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for line in out.strip().splitlines():
-            f = [t.strip() for t in line.split(',')]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for n, v in zip(names, f[3:7]):
-                if v.lower().startswith('active'):
-                    reasons.add(n)
-        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'samples': len(sm), 'reasons': sorted(reasons)}
+        self._stop.set()
+        self._t.join(timeout=2)
+        if not self.sm:
+            return {'sm_mhz': None, 'sm_max_mhz': self.max_mhz, 'samples': 0, 'reasons': [self.err or 'no samples']}
+        return {'sm_mhz': statistics.median(self.sm), 'sm_max_mhz': self.max_mhz, 'samples': len(self.sm),
+                'reasons': sorted(self.reasons)}
 
 
 def algorithmic_bytes(name, m):
@@ -216,13 +224,14 @@ def workload_name(name, cfg):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--config', default='cubes', choices=sorted(CONFIGS))
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=0, help='override the per-GPU batch size')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='launch the step kernel by kernel instead of replaying a CUDA graph')
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
     if args.batch:
@@ -257,23 +266,40 @@ def main():
     hold = cfg['arch'] == 'meshunet'
 
     # ---- device-resident arm ---------------------------------------------------------------------------------------
+    from meshcnn_b200.graphed import GraphedTrainStep
     meshes = [Mesh(data=d, hold_history=hold) for d in datas]
-    batch = MeshBatch(meshes, E, dev)
-    batch.snapshot()
-    x_dev = torch.from_numpy(x).to(dev).requires_grad_(True)           # the reference trains with requires_grad inputs
-    y_dev = torch.from_numpy(labels).to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+    mode = 'eager' if args.no_graph else 'cuda-graph'
+    gs = None
+    launches_per_step = None
+    if not args.no_graph:
+        try:
+            l0 = _lib.launch_count()
+            gs = GraphedTrainStep(net, crit, reducer, opt, meshes, x, labels, E, source='device')
+            launches_per_step = (_lib.launch_count() - l0) // (gs.warmup_steps + 1)
+        except Exception as e:                                       # noqa: BLE001  (e.g. a collective that cannot be captured)
+            sys.stderr.write('CUDA-graph capture failed (%s); running eagerly\n' % (e,))
+            gs, mode = None, 'eager (graph capture failed)'
+            torch.cuda.synchronize()
+    if gs is not None:
+        batch = gs.batch
+        step = gs.run
+    else:
+        batch = MeshBatch(meshes, E, dev)
+        batch.snapshot()
+        x_dev = torch.from_numpy(x).to(dev).requires_grad_(True)       # the reference trains with requires_grad inputs
+        y_dev = torch.from_numpy(labels).to(dev)
 
-    def step():
-        batch.reset()
-        reducer.zero()
-        x_dev.grad = None
-        out = net(x_dev, meshes)
-        loss = crit(out, y_dev)
-        loss.backward()
-        reducer.allreduce()
-        opt.step()
-        return loss
+        def step():
+            batch.reset()
+            reducer.zero()
+            x_dev.grad = None
+            out = net(x_dev, meshes)
+            loss = crit(out, y_dev)
+            loss.backward()
+            reducer.allreduce()
+            opt.step()
+            return loss
 
     for _ in range(args.warmup):
         step()
@@ -283,8 +309,6 @@ def main():
         dist.barrier()
     torch.cuda.synchronize()
     sampler = ClockSampler(local) if rank == 0 else None
-    profiler.enabled = True
-    profiler.reset()
     launches0 = _lib.launch_count()
     evs = []
     for _ in range(args.steps):
@@ -297,10 +321,8 @@ def main():
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    launches = _lib.launch_count() - launches0
-    profiler.enabled = False
-    recs = profiler.collect()
     clocks = sampler.stop() if sampler is not None else None
+    launches = (_lib.launch_count() - launches0) if gs is None else launches_per_step * args.steps
     batch.check()
     total_ms = sum(a.elapsed_time(b) for a, b in evs)
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
@@ -309,50 +331,102 @@ def main():
     total_ms = float(t.item())
     value = world * B * args.steps / (total_ms / 1e3)
 
+    # ---- per-kernel CUDA-event timings: the same step launched kernel by kernel (events cannot bracket the nodes of a
+    # replayed graph), L2 flushed between steps as above -------------------------------------------------------------
+    pmeshes = [Mesh(data=d, hold_history=hold) for d in datas]
+    pbatch = MeshBatch(pmeshes, E, dev)
+    pbatch.snapshot()
+    px = torch.from_numpy(x).to(dev).requires_grad_(True)
+    py = torch.from_numpy(labels).to(dev)
+
+    def eager_step():
+        pbatch.reset()
+        reducer.zero()
+        px.grad = None
+        loss = crit(net(px, pmeshes), py)
+        loss.backward()
+        reducer.allreduce()
+        opt.step()
+
+    for _ in range(2):
+        eager_step()
+    torch.cuda.synchronize()
+    k_prof = min(args.steps, 10)
+    profiler.enabled = True
+    profiler.reset()
+    pe = []
+    for _ in range(k_prof):
+        flush.fill_(1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        eager_step()
+        b.record()
+        pe.append((a, b))
+    profiler.enabled = False
+    recs = profiler.collect()
+    eager_ms = sum(a.elapsed_time(b) for a, b in pe)
+    del pbatch, pmeshes
+
     # ---- end-to-end arm: host buffers in, loss out, every step ------------------------------------------------------
     e2e = None
     if not args.no_e2e:
-        x_pin = torch.from_numpy(x).pin_memory()
-        y_pin = torch.from_numpy(labels).pin_memory()
         k_e2e = args.steps
-        fresh = [[Mesh(data=d, hold_history=hold) for d in datas] for _ in range(k_e2e + 2)]   # the data loader's job (F11/F12)
-        h2d = 0
-
+        n_fresh = min(k_e2e + 2, 12)
+        fresh = [[Mesh(data=d, hold_history=hold) for d in datas] for _ in range(n_fresh)]   # the data loader's job (F11/F12)
         t_pack = [0.0]
+        if args.no_graph or gs is None:
+            x_pin = torch.from_numpy(x).pin_memory()
+            y_pin = torch.from_numpy(labels).pin_memory()
+            h2d = [0]
 
-        def e2e_step(ms):
-            nonlocal h2d
-            tp = time.perf_counter()
-            bt = MeshBatch(ms, E, dev)                                   # packs + uploads the topology blob (pinned)
-            t_pack[0] += time.perf_counter() - tp
-            xin = x_pin.to(dev, non_blocking=True).requires_grad_(True)
-            yin = y_pin.to(dev, non_blocking=True)
-            h2d = bt.blob.numel() + x_pin.numel() * 4 + y_pin.numel() * 8
-            reducer.zero()
-            out = net(xin, ms)
-            loss = crit(out, yin)
-            loss.backward()
-            reducer.allreduce()
-            opt.step()
-            return float(loss.item())                                    # D2H read of the step's result
+            def e2e_step(i):
+                ms = [Mesh(data=d, hold_history=hold) for d in datas] if i >= n_fresh else fresh[i]
+                tp = time.perf_counter()
+                bt = MeshBatch(ms, E, dev)                               # packs + uploads the topology blob (pinned)
+                t_pack[0] += time.perf_counter() - tp
+                xin = x_pin.to(dev, non_blocking=True).requires_grad_(True)
+                yin = y_pin.to(dev, non_blocking=True)
+                h2d[0] = bt.blob.numel() + x_pin.numel() * 4 + y_pin.numel() * 8
+                reducer.zero()
+                loss = crit(net(xin, ms), yin)
+                loss.backward()
+                reducer.allreduce()
+                opt.step()
+                return float(loss.item())                                # D2H read of the step's result
+            h2d_bytes = lambda: h2d[0]
+        else:
+            ge = GraphedTrainStep(net, crit, reducer, opt, fresh[0], x, labels, E, source='host')
+            x_np, y_np = torch.from_numpy(x), torch.from_numpy(labels)
+
+            def e2e_step(i):
+                ms = fresh[i % n_fresh]
+                for m in ms:                                             # a used Mesh is single-use (F11): hand the loader's
+                    m._batch = None                                      # pristine host copy to the step again
+                tp = time.perf_counter()
+                ge.stage(ms, x_np, y_np)                                 # pack topology + features + labels into pinned buffers
+                t_pack[0] += time.perf_counter() - tp
+                return float(ge.run().item())                            # H2D copies are graph nodes; D2H read of the loss
+            h2d_bytes = lambda: ge.h2d_bytes
 
         for i in range(2):
-            e2e_step(fresh[i])
+            e2e_step(i)
         torch.cuda.synchronize()
         t_pack[0] = 0.0
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
         for i in range(k_e2e):
-            e2e_step(fresh[2 + i])
+            e2e_step(2 + i)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         t = torch.tensor([dt], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e = {'value': world * B * k_e2e / float(t.item()), 'unit': 'meshes/s', 'h2d_bytes_per_step': int(h2d),
+        e2e = {'value': world * B * k_e2e / float(t.item()), 'unit': 'meshes/s', 'h2d_bytes_per_step': int(h2d_bytes()),
                'd2h_bytes_per_step': 4, 'timing': 'host wall clock between device synchronisations, max over ranks',
-               'host_pack_ms_per_step': 1e3 * t_pack[0] / k_e2e}
+               'host_pack_ms_per_step': 1e3 * t_pack[0] / k_e2e,
+               'api': 'meshcnn_b200.graphed.GraphedTrainStep(meshes, x, y) from host buffers' if gs is not None else
+                      'net(x, meshes) eager from host buffers'}
 
     if rank != 0:
         if world > 1:
@@ -379,7 +453,8 @@ def main():
         ach = nbytes / (avg_ms * 1e-3) / 1e9
         roofline = {'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak, 'traffic': None,
                     'kernel': name, 'shape': m, 'avg_launch_ms': avg_ms, 'algorithmic_bytes': nbytes, 'peak_source': peak_src,
-                    'share_of_step': {k: v / total_ms for k, v in sorted(by_kernel.items())}}
+                    'share_of_step': {k: v / eager_ms for k, v in sorted(by_kernel.items())},
+                    'timing': 'CUDA events around each C-ABI call in %d eagerly launched steps (%.3f ms/step) run right after the timed region' % (k_prof, eager_ms / k_prof)}
 
     cpu = None
     if not args.no_cpu_baseline:
@@ -395,7 +470,7 @@ def main():
             'config': {'workload': workload_name(args.config, cfg), 'global_batch': world * B,
                        'parallelism': 'dp%d (meshes sharded, one flat NCCL gradient allreduce)' % world,
                        'l2': 'flushed between timed steps (256 MiB write, untimed); per-step CUDA events, max over ranks',
-                       'optimizer': 'Adam (in the timed region)'},
+                       'optimizer': 'Adam (in the timed region)', 'launch': mode},
             'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks}
     print(json.dumps(line))
     if world > 1:

@@ -214,6 +214,11 @@ int mcnn_norm_bwd(const float* dy, const float* y, const float* x, const float* 
 int mcnn_adam_flat(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
                    float weight_decay, int step, void* stream);
 
+/* Same update with hyper-parameters and step counter in DEVICE memory, so that the launch can be captured in a CUDA graph
+ * and replayed:  state[8] = {lr, beta1, beta2, eps, weight_decay, step, 1 - beta1^step, sqrt(1 - beta2^step)}; the call
+ * first advances step (and the two bias corrections), then applies the update. */
+int mcnn_adam_flat_state(float* p, const float* g, float* m, float* v, long long n, float* state, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -261,6 +261,32 @@ __global__ void adam_flat_kernel(float* __restrict__ p, const float* __restrict_
     p[i] = pi - (lr / bc1) * (mi / denom);
 }
 
+// CUDA-graph friendly variant: the hyper-parameters and the step counter live in device memory, so a captured launch stays
+// valid when the learning rate changes or the step count advances.   state = {lr, beta1, beta2, eps, weight_decay, step,
+// 1 - beta1^step, sqrt(1 - beta2^step)}
+__global__ void adam_tick_kernel(float* __restrict__ state) {
+    const float step = state[5] + 1.f;
+    state[5] = step;
+    state[6] = 1.f - powf(state[1], step);
+    state[7] = sqrtf(1.f - powf(state[2], step));
+}
+__global__ void adam_flat_state_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                       long long n, const float* __restrict__ state) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float lr = state[0], beta1 = state[1], beta2 = state[2], eps = state[3], weight_decay = state[4];
+    const float bc1 = state[6], bc2_sqrt = state[7];
+    float gi = g[i];
+    const float pi = p[i];
+    if (weight_decay != 0.f) gi += weight_decay * pi;
+    const float mi = beta1 * m[i] + (1.f - beta1) * gi;
+    const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = pi - (lr / bc1) * (mi / denom);
+}
+
 static NormShape make_shape(int nblocks, int rows_per_block, int C, int G) {
     NormShape s;
     s.nblocks = nblocks; s.rows_per_block = rows_per_block; s.C = C; s.G = G;
@@ -326,6 +352,15 @@ extern "C" int mcnn_norm_bwd(const float* dy, const float* y, const float* x, co
     const long long total4 = (long long)nblocks * rows_per_block * (C / 4);
     norm_bwd_apply_kernel<<<(unsigned)((total4 + NT - 1) / NT), NT, 0, st>>>(dy, y, x, a, gamma, mean, rstd, s1, s2, dx, dr, pre_relu,
                                                                              post_relu, s, total4);
+    return after_launch();
+}
+
+extern "C" int mcnn_adam_flat_state(float* p, const float* g, float* m, float* v, long long n, float* state, void* stream) {
+    if (!p || !g || !m || !v || !state || n <= 0) return MCNN_E_BADARG;
+    adam_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state);
+    int rc = after_launch();
+    if (rc) return rc;
+    adam_flat_state_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, state);
     return after_launch();
 }
 

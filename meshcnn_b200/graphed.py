@@ -1,0 +1,111 @@
+"""Whole training step as ONE CUDA graph.
+
+A MeshCNN step at the reference's batch sizes is ~200 small kernels (36 MeshConv + norms + pools for the U-Net); on a
+B200 each lasts a few microseconds, so a step driven launch by launch from Python is bound by the host.  Nothing in the
+step needs the host: the live edge counts, the collapse order, the pooled topology, the MeshUnion groups and the Adam
+step counter all stay in HBM.  ``GraphedTrainStep`` captures
+
+    [topology blob + features + labels: pinned host -> device]  ->  forward (MeshConv / MeshPool / MeshUnpool ...)
+    -> loss -> backward -> flat gradient all-reduce (NCCL, when world > 1) -> Adam
+
+once and replays it.  Per step the host packs the next batch of meshes into the pinned staging buffers
+(``MeshBatch.pack``) and calls ``run()``.
+
+    step = GraphedTrainStep(net, criterion, reducer, optimizer, meshes0, x0, y0, E)
+    for meshes, x, y in loader:
+        loss = step(meshes, x, y)          # tensor on the device; .item() when the value is wanted
+"""
+import numpy as np
+import torch
+
+from .mesh import MeshBatch
+
+
+class GraphedTrainStep:
+    def __init__(self, net, criterion, reducer, optimizer, meshes, x, y, E, source='host', V_cap=0, ve_cap=0, warmup=3):
+        """meshes / x / y: a first batch that fixes the shapes (x: [B, C, E] fp32 host array or tensor, y: labels).
+        source='host': every replay starts with the host->device copies of the staged batch;
+        source='device': the batch given here stays resident and every replay restores its pristine topology
+        (benchmarking the device-side step alone)."""
+        if source not in ('host', 'device'):
+            raise ValueError(source)
+        self.net, self.criterion, self.reducer, self.opt, self.source = net, criterion, reducer, optimizer, source
+        dev = reducer.flat.device
+        self.device = dev
+        x = torch.as_tensor(np.asarray(x)) if not torch.is_tensor(x) else x
+        y = torch.as_tensor(np.asarray(y)) if not torch.is_tensor(y) else y
+        self.x_host = torch.empty(x.shape, dtype=torch.float32).pin_memory()
+        self.y_host = torch.empty(y.shape, dtype=y.dtype).pin_memory()
+        self.x_host.copy_(x)
+        self.y_host.copy_(y)
+        self.x_dev = torch.empty(x.shape, dtype=torch.float32, device=dev).requires_grad_(True)   # the reference feeds requires_grad inputs
+        self.y_dev = torch.empty(y.shape, dtype=y.dtype, device=dev)
+        meshes = list(meshes)
+        if not V_cap:
+            V_cap = int(1.25 * max(len(m._host_state()['vs']) for m in meshes)) + 8
+        probe = MeshBatch(meshes, E, 'cpu', V_cap=V_cap, ve_cap=ve_cap)          # sizes only
+        self.blob_host = torch.empty(probe.nbytes, dtype=torch.uint8).pin_memory()
+        self.batch = MeshBatch(meshes, E, dev, V_cap=V_cap, ve_cap=ve_cap, staging=self.blob_host)
+        with torch.no_grad():
+            self.x_dev.copy_(self.x_host)
+            self.y_dev.copy_(self.y_host)
+        if source == 'device':
+            self.batch.snapshot()
+        self.h2d_bytes = self.blob_host.numel() + self.x_host.numel() * 4 + self.y_host.numel() * self.y_host.element_size()
+        self.loss = None
+        self.graph = None
+        self._capture(warmup)
+
+    # the work of one step, enqueued on the current stream
+    def _enqueue(self):
+        bt = self.batch
+        if self.source == 'host':
+            bt.blob.copy_(self.blob_host[:bt.nbytes], non_blocking=True)
+            with torch.no_grad():
+                self.x_dev.copy_(self.x_host, non_blocking=True)
+                self.y_dev.copy_(self.y_host, non_blocking=True)
+            bt.rewind()
+        else:
+            bt.reset()
+        self.reducer.zero()
+        self.x_dev.grad = None
+        out = self.net(self.x_dev, bt.meshes)
+        loss = self.criterion(out, self.y_dev)
+        loss.backward()
+        self.reducer.allreduce()
+        self.opt.step_state()
+        return loss
+
+    def _capture(self, warmup):
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):
+                self._enqueue()
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        self.batch.check()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = self._enqueue()
+        self.warmup_steps = max(1, warmup)
+
+    def stage(self, meshes, x, y):
+        """Host side of a step: pack the next batch into the pinned staging buffers (no device work)."""
+        self.batch.pack(meshes)
+        self.x_host.copy_(torch.as_tensor(x) if not torch.is_tensor(x) else x)
+        self.y_host.copy_(torch.as_tensor(y) if not torch.is_tensor(y) else y)
+
+    def run(self):
+        """Replay the captured step; returns the (device) loss tensor of the graph's static output."""
+        self.opt.sync_lr()
+        self.graph.replay()
+        self.batch.version += 1                     # host mirrors of the meshes refresh lazily from the new state
+        return self.loss
+
+    def __call__(self, meshes, x, y):
+        if self.source != 'host':
+            raise RuntimeError("a source='device' step replays its resident batch: call run()")
+        self.stage(meshes, x, y)
+        return self.run()

@@ -98,22 +98,20 @@ class PoolRecord:
 class MeshBatch:
     """Device state of a batch of meshes."""
 
-    def __init__(self, meshes, E, device, with_vs=None):
+    def __init__(self, meshes, E, device, with_vs=None, V_cap=0, ve_cap=0, staging=None):
+        """meshes: B Mesh objects; E: edge slots of the level-0 activations.  V_cap / ve_cap reserve room for later
+        `load()` calls with other meshes (CUDA-graph replay); staging: a caller-owned pinned uint8 tensor to pack into
+        (so that the host->device copy can itself be a node of a captured graph)."""
         meshes = list(meshes)
-        self.meshes = meshes
         self.device = torch.device(device)
         B = len(meshes)
         hs = [m._host_state() for m in meshes]
-        ecs = [int(h['edges_count']) for h in hs]
-        if max(ecs) > E:
-            raise ValueError('mesh with %d edges does not fit an activation of width %d' % (max(ecs), E))
-        V = max(len(h['vs']) for h in hs)
-        nve = [int(len(h['ve_flat'])) for h in hs]
-        ve_cap = _align(max(2 * E, max(nve)), 8)
+        V = max(max(len(h['vs']) for h in hs), int(V_cap))
+        nve = max(int(len(h['ve_flat'])) for h in hs)
+        ve_cap = _align(max(2 * E, nve, int(ve_cap)), 8)
         if with_vs is None:
             with_vs = any(bool(m.export_folder) for m in meshes)
         self.B, self.E0, self.V, self.ve_cap, self.with_vs = B, E, V, ve_cap, with_vs
-        # ---- pack everything into one pinned blob, one H2D copy ------------------------------------------
         sizes = [('gemm', B * E * 4 * 4), ('sides', B * E * 4), ('ec', B * 4), ('edges', B * E * 2 * 4),
                  ('ve_ptr', B * (V + 1) * 4), ('ve_idx', B * ve_cap * 4), ('v_mask', B * V),
                  ('vs', B * V * 3 * 8 if with_vs else 0)]
@@ -121,8 +119,52 @@ class MeshBatch:
         for k, s in sizes:
             offs[k] = (o, s)
             o = _align(o + s)
-        host, self._pin_slot = _staging_buffer(o, self.device)
-        hb = host.numpy()
+        self._offs, self.nbytes = offs, o
+        self._staging = staging
+        if staging is not None and (staging.numel() < o or not staging.is_pinned()):
+            raise ValueError('staging buffer must be pinned and hold %d bytes' % o)
+        self.blob = torch.empty(o, dtype=torch.uint8, device=self.device)
+        self.meshes = []
+        self.version = 0
+        self._upload(meshes, hs)
+
+        def dview(k, dtype, shape):
+            a, s = offs[k]
+            return self.blob[a:a + s].view(dtype).view(shape)
+
+        self.edges = dview('edges', torch.int32, (B, E, 2))
+        self.ve_ptr = dview('ve_ptr', torch.int32, (B, V + 1))
+        self.ve_idx = dview('ve_idx', torch.int32, (B, ve_cap))
+        self.v_mask = dview('v_mask', torch.uint8, (B, V))
+        self.vs = dview('vs', torch.float64, (B, V, 3)) if with_vs else None
+        self.level0 = Level(E, dview('gemm', torch.int32, (B, E, 4)), dview('sides', torch.int8, (B, E, 4)),
+                            dview('ec', torch.int32, (B,)))
+        self.levels = [self.level0]
+        self.cur = 0
+        self.stack = []            # PoolRecords not yet undone by MeshUnpool
+        self.records = []          # every PoolRecord of this forward, in order
+        self._pristine = None
+        self.keep_logs = False
+        self.keep_clocks = False
+
+    def pack(self, meshes, hs=None):
+        """Pack the topology of `meshes` into the pinned staging buffer (one blob); returns it.  No device work."""
+        meshes = list(meshes)
+        B, E, V, ve_cap, with_vs, offs = self.B, self.E0, self.V, self.ve_cap, self.with_vs, self._offs
+        if len(meshes) != B:
+            raise ValueError('this MeshBatch holds %d meshes, got %d' % (B, len(meshes)))
+        if hs is None:
+            hs = [m._host_state() for m in meshes]
+        ecs = [int(h['edges_count']) for h in hs]
+        if max(ecs) > E:
+            raise ValueError('mesh with %d edges does not fit an activation of width %d' % (max(ecs), E))
+        if max(len(h['vs']) for h in hs) > V or max(len(h['ve_flat']) for h in hs) > ve_cap:
+            raise ValueError('mesh exceeds the vertex / list capacity this MeshBatch was built with (V_cap, ve_cap)')
+        if self._staging is not None:
+            host, self._pin_slot = self._staging, None
+        else:
+            host, self._pin_slot = _staging_buffer(self.nbytes, self.device)
+        hb = host.numpy()[:self.nbytes]
         hb[:] = 0
 
         def view(k, dtype, shape):
@@ -146,37 +188,39 @@ class MeshBatch:
             off = h['ve_off']
             ve_ptr[b, :len(off)] = off
             ve_ptr[b, len(off):] = off[-1]
-            ve_idx[b, :nve[b]] = h['ve_flat']
+            ve_idx[b, :len(h['ve_flat'])] = h['ve_flat']
             v_mask[b, :len(h['v_mask'])] = h['v_mask']
             if with_vs:
                 vs[b, :len(h['vs'])] = h['vs']
         self._host_blob = host
-        self.blob = host.to(self.device, non_blocking=True)
-        if self._pin_slot is not None:
-            self._pin_slot[1].record()                 # the staging buffer may be reused once this copy has completed
-        self._offs = offs
-
-        def dview(k, dtype, shape):
-            a, s = offs[k]
-            return self.blob[a:a + s].view(dtype).view(shape)
-
-        self.edges = dview('edges', torch.int32, (B, E, 2))
-        self.ve_ptr = dview('ve_ptr', torch.int32, (B, V + 1))
-        self.ve_idx = dview('ve_idx', torch.int32, (B, ve_cap))
-        self.v_mask = dview('v_mask', torch.uint8, (B, V))
-        self.vs = dview('vs', torch.float64, (B, V, 3)) if with_vs else None
-        self.level0 = Level(E, dview('gemm', torch.int32, (B, E, 4)), dview('sides', torch.int8, (B, E, 4)),
-                            dview('ec', torch.int32, (B,)))
-        self.levels = [self.level0]
-        self.cur = 0
-        self.stack = []            # PoolRecords not yet undone by MeshUnpool
-        self.records = []          # every PoolRecord of this forward, in order
-        self.version = 0
-        self._pristine = None
-        self.keep_logs = False
-        self.keep_clocks = False
+        for m in self.meshes:                                  # the previous occupants keep their last host mirror
+            if getattr(m, '_batch', None) is self:
+                m._batch = None
+        self.meshes = meshes
         for i, m in enumerate(meshes):
             m._attach(self, i)
+        return host
+
+    def _upload(self, meshes, hs=None):
+        host = self.pack(meshes, hs)
+        self.blob.copy_(host[:self.nbytes], non_blocking=True)
+        if self._pin_slot is not None:
+            self._pin_slot[1].record()                 # the staging buffer may be reused once this copy has completed
+
+    def load(self, meshes):
+        """Re-use the device buffers of this batch for another list of B meshes: one packed upload, state back at
+        level 0.  Everything that was computed from the previous occupants is dropped."""
+        self._upload(meshes)
+        self.rewind()
+
+    def rewind(self):
+        """Host-side bookkeeping back to level 0 (no device work)."""
+        self.levels = [self.level0]
+        self.cur = 0
+        self.stack, self.records = [], []
+        self.version += 1
+        for m in self.meshes:
+            m.pool_count = 0
 
     # -- lookup ------------------------------------------------------------------------------------------
     @staticmethod
@@ -205,12 +249,7 @@ class MeshBatch:
             raise RuntimeError('MeshBatch.reset() without snapshot()')
         a = self._offs['edges'][0]
         self.blob[a:].copy_(self._pristine)
-        self.levels = [self.level0]
-        self.cur = 0
-        self.stack, self.records = [], []
-        self.version += 1
-        for m in self.meshes:
-            m.pool_count = 0
+        self.rewind()
 
     # -- pool / unpool bookkeeping -------------------------------------------------------------------------
     def pool(self, norms, T):
