@@ -75,7 +75,9 @@ int mcnn_meshconv_fwd(const float* x, const int32_t* gemm, const int32_t* ec, co
 
 /* Same contract as mcnn_meshconv_fwd, computed on the tensor cores (tcgen05.mma kind::tf32 with the 3xTF32 split, fp32
  * accumulation in TMEM; results agree with the FFMA path to ~1e-6 relative).  Only for shapes where
- * mcnn_meshconv_tc_supported(Cin, Cout) != 0 (Cin % 32 == 0, Cout % 64 == 0); wt_ws as above. */
+ * mcnn_meshconv_tc_supported(Cin, Cout) != 0 (Cin % 32 == 0, Cout % 64 == 0).
+ *   wt_ws  2*5*Cin*Cout floats of scratch: a first small kernel writes the weight there as the ready-to-use B operand
+ *          (TF32 head + remainder, K-major SWIZZLE_128B atoms), which every CTA then fetches with bulk copies */
 int mcnn_meshconv_tc_supported(int Cin, int Cout);
 int mcnn_meshconv_fwd_tc(const float* x, const int32_t* gemm, const int32_t* ec, const float* weight,
                          const float* bias, float* out, float* wt_ws, int B, int E, int Cin, int Cout, void* stream);
@@ -94,7 +96,7 @@ int mcnn_meshconv_bwd_weight(const float* dout, const float* x, const int32_t* g
 
 /* Tensor-core versions of the two backward kernels (tcgen05.mma kind::tf32, 3xTF32 split, TMEM accumulators).
  *   bwd_data_tc  : Cin % 32 == 0 and Cout % 32 == 0; dx must be ZERO on entry (red.global.add.v4.f32 scatter);
- *                  wtb_ws [5*Cin][Cout] scratch for the re-laid weight
+ *                  wtb_ws 2*5*Cin*Cout floats of scratch for the B-operand image of the weight (head + remainder)
  *   bwd_weight_tc: Cin % 32 == 0 and Cout % 4 == 0; dweight / dbias are OVERWRITTEN (slab partials are written to
  *                  `ws` and reduced by a second kernel: deterministic, no atomics); ws holds
  *                  mcnn_meshconv_bwd_weight_tc_ws(B, E, Cin, Cout) floats */

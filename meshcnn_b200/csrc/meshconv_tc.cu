@@ -27,8 +27,11 @@ constexpr int TC_M = 128;
 constexpr int TC_PRODUCER_WARPS = 8;
 constexpr int TC_THREADS = (TC_PRODUCER_WARPS + 1) * 32;
 
-// weight [Cout][Cin][5] -> wt[Cout][5*Cin] in the permuted K order above
-__global__ void weight_tc_layout_kernel(const float* __restrict__ w, float* __restrict__ wt, int Cin, int Cout) {
+// weight [Cout][Cin][5] -> the B operand exactly as the tensor core wants it in shared memory, split into TF32 head and
+// remainder:  img[hi|lo][kb][Cout rows x 128 bytes, canonical K-major SWIZZLE_128B atoms], K in the permuted order above.
+// The rows n0 .. n0+N_TILE of one K block are N_TILE*128 contiguous bytes, so a CTA fetches its B tile with one bulk copy
+// per half instead of pushing it through registers.
+__global__ void weight_tc_layout_kernel(const float* __restrict__ w, float* __restrict__ img, int Cin, int Cout) {
     const int K = 5 * Cin;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= Cout * K) return;
@@ -42,7 +45,11 @@ __global__ void weight_tc_layout_kernel(const float* __restrict__ w, float* __re
         k5 = (p < 16) ? first : first + 2;
         c = cb * 32 + (((blk - 1) & 1) << 4) + (p & 15);
     }
-    wt[idx] = w[((size_t)o * Cin + c) * 5 + k5];
+    float hi, lo;
+    tc::split_tf32(w[((size_t)o * Cin + c) * 5 + k5], hi, lo);
+    const size_t off = (size_t)kb * Cout * 32 + (tc::sw128_off(o, p >> 2) >> 2) + (p & 3);
+    img[off] = hi;
+    img[(size_t)Cout * K + off] = lo;
 }
 
 template <int N_TILE>
@@ -51,6 +58,7 @@ struct TcSmem {
     static constexpr int B_BYTES = N_TILE * 128;
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
     static constexpr int STAGES = (N_TILE >= 256) ? 2 : ((N_TILE >= 128) ? 3 : 4);
+    static_assert(STAGES * STAGE_BYTES <= 200 * 1024, "stage ring too large");
     static constexpr int TILE_BYTES = STAGES * STAGE_BYTES;
     static constexpr int NB_OFF = TILE_BYTES;             // int nb[128][5]
     static constexpr int BAR_OFF = NB_OFF + TC_M * 5 * 4;
@@ -111,7 +119,6 @@ meshconv_fwd_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ 
         // loads of K block kb+2 are issued before the shared-memory stores of block kb (register prefetch, distance 2):
         // the L2 latency of the gathers is hidden behind two blocks of split / st.shared / MMA work.
         const int pt = tid;                                     // 0..255
-        constexpr int NB = N_TILE / 32;                         // B float4 per thread per block
         int src0[4], srcA[2][2], srcB[2][2];                    // blk 0: 4 items (row, chunk); pair blocks: 2 items x 2 rows
 #pragma unroll
         for (int it = 0; it < 4; ++it) src0[it] = nb[(pt + it * 256) >> 3][0];
@@ -121,22 +128,14 @@ meshconv_fwd_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ 
             srcA[it][0] = nb[r][1]; srcB[it][0] = nb[r][3];     // pair (f1, f3)
             srcA[it][1] = nb[r][2]; srcB[it][1] = nb[r][4];     // pair (f2, f4)
         }
-        struct Regs { float4 b[NB]; float4 a[4]; };
+        struct Regs { float4 a[4]; };
         const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
         auto load_block = [&](int kb, Regs& R) {
             const int cb = kb / 5, blk = kb - cb * 5;
             if (dbg & 1) {
 #pragma unroll
-                for (int it = 0; it < NB; ++it) R.b[it] = zero4;
-#pragma unroll
                 for (int it = 0; it < 4; ++it) R.a[it] = zero4;
                 return;
-            }
-#pragma unroll
-            for (int it = 0; it < NB; ++it) {
-                const int item = pt + it * 256;
-                const int r = item >> 3, q = item & 7;
-                R.b[it] = (n0 + r < Cout) ? __ldg(reinterpret_cast<const float4*>(wt + (size_t)(n0 + r) * K + (kb << 5) + (q << 2))) : zero4;
             }
             if (blk == 0) {
                 const int c = cb * 32 + ((pt & 7) << 2);
@@ -165,19 +164,17 @@ meshconv_fwd_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ 
             unsigned char* b_lo = b_hi + S::B_BYTES;
             const int blk = kb % 5;
             float4 hi, lo;
+            if (tid == 0) {                                               // the B tile of this K block: two bulk copies (TMA engine)
+                tc::mbar_expect_tx(full_bar + s, 2 * S::B_BYTES);
+                const float* src = wt + ((size_t)kb * Cout + n0) * 32;
+                tc::bulk_g2s(b_hi, src, S::B_BYTES, full_bar + s);
+                tc::bulk_g2s(b_lo, src + (size_t)Cout * K, S::B_BYTES, full_bar + s);
+            }
             if (dbg & 4) {
                 tc::fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(full_bar + s);
                 return;
-            }
-#pragma unroll
-            for (int it = 0; it < NB; ++it) {
-                const int item = pt + it * 256;
-                const uint32_t off = tc::sw128_off(item >> 3, item & 7);
-                tc::split4(R.b[it], hi, lo);
-                *reinterpret_cast<float4*>(b_hi + off) = hi;
-                *reinterpret_cast<float4*>(b_lo + off) = lo;
             }
             if (blk == 0) {
 #pragma unroll
@@ -210,7 +207,7 @@ meshconv_fwd_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ 
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(full_bar + s);                  // ... then one arrival per warp
         };
-        if constexpr (N_TILE < 256) {                            // prefetch distance 2 (three register sets)
+        {                                                        // prefetch distance 2 (three register sets)
             Regs R0, R1, R2;
             load_block(0, R0);
             if (num_kb > 1) load_block(1, R1);
@@ -224,17 +221,6 @@ meshconv_fwd_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ 
                 if (kb + 2 < num_kb) {
                     if (kb + 4 < num_kb) load_block(kb + 4, R1);
                     store_block(kb + 2, R2);
-                }
-            }
-        } else {                                                 // N = 256: 48 registers per set, distance 1
-            Regs R0, R1;
-            load_block(0, R0);
-            for (int kb = 0; kb < num_kb; kb += 2) {
-                if (kb + 1 < num_kb) load_block(kb + 1, R1);
-                store_block(kb, R0);
-                if (kb + 1 < num_kb) {
-                    if (kb + 2 < num_kb) load_block(kb + 2, R0);
-                    store_block(kb + 1, R1);
                 }
             }
         }
@@ -332,14 +318,20 @@ struct BdSmem {
     static constexpr int TOTAL = BAR_OFF + 16 * 8 + 16 + 1024;
 };
 
-// weight [Cout][Cin][5] -> wtb[5*Cin][Cout], row = cb*160 + k5*32 + cl  (c = cb*32 + cl)
-__global__ void weight_tc_bwd_layout_kernel(const float* __restrict__ w, float* __restrict__ wtb, int Cin, int Cout) {
+// weight [Cout][Cin][5] -> B operand image of the data-gradient GEMM, TF32 head / remainder:
+//   img[hi|lo][cb][kb][160 rows x 128 bytes swizzled],  row n = k5*32 + cl (c = cb*32 + cl),  K = output channels
+__global__ void weight_tc_bwd_layout_kernel(const float* __restrict__ w, float* __restrict__ img, int Cin, int Cout) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= 5 * Cin * Cout) return;
     const int row = idx / Cout, o = idx - row * Cout;
     const int cb = row / BD_N, n = row - cb * BD_N;
     const int k5 = n >> 5, c = cb * 32 + (n & 31);
-    wtb[idx] = w[((size_t)o * Cin + c) * 5 + k5];
+    const int kb = o >> 5, p = o & 31;
+    float hi, lo;
+    tc::split_tf32(w[((size_t)o * Cin + c) * 5 + k5], hi, lo);
+    const size_t off = ((size_t)cb * (Cout >> 5) + kb) * (BD_N * 32) + (tc::sw128_off(n, p >> 2) >> 2) + (p & 3);
+    img[off] = hi;
+    img[(size_t)5 * Cin * Cout + off] = lo;
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -410,16 +402,11 @@ meshconv_bwd_data_tc_kernel(const float* __restrict__ dout, const float* __restr
                 *reinterpret_cast<float4*>(a_hi + off) = hi;
                 *reinterpret_cast<float4*>(a_lo + off) = lo;
             }
-#pragma unroll
-            for (int it = 0; it < (BD_N * 8) / 256; ++it) {
-                const int item = pt + it * 256;
-                const int r = item >> 3, q = item & 7;
-                const float4 v = __ldg(reinterpret_cast<const float4*>(wtb + (size_t)(cb * BD_N + r) * Cout + (kb << 5) + (q << 2)));
-                float4 hi, lo;
-                tc::split4(v, hi, lo);
-                const uint32_t off = tc::sw128_off(r, q);
-                *reinterpret_cast<float4*>(b_hi + off) = hi;
-                *reinterpret_cast<float4*>(b_lo + off) = lo;
+            if (tid == 0) {                                               // B tile: two bulk copies of the pre-built image
+                tc::mbar_expect_tx(full_bar + s, 2 * S::B_BYTES);
+                const float* src = wtb + ((size_t)cb * num_kb + kb) * (BD_N * 32);
+                tc::bulk_g2s(b_hi, src, S::B_BYTES, full_bar + s);
+                tc::bulk_g2s(b_lo, src + (size_t)5 * Cin * Cout, S::B_BYTES, full_bar + s);
             }
             tc::fence_proxy_async_smem();                                  // every writer fences its own stores ...
             __syncwarp();
@@ -743,7 +730,8 @@ extern "C" int mcnn_meshconv_fwd_tc(const float* x, const int32_t* gemm, const i
     int rc = after_launch();
     if (rc) return rc;
     const int mtiles = ceil_div(B * E, TC_M);
-    if (Cout % 256 == 0 && mtiles >= 222) return launch_fwd_tc<256>(x, gemm, ec, wt_ws, bias, out, B, E, Cin, Cout, st);
+    (void)mtiles;
+    if (Cout % 256 == 0) return launch_fwd_tc<256>(x, gemm, ec, wt_ws, bias, out, B, E, Cin, Cout, st);
     if (Cout % 128 == 0) return launch_fwd_tc<128>(x, gemm, ec, wt_ws, bias, out, B, E, Cin, Cout, st);
     return launch_fwd_tc<64>(x, gemm, ec, wt_ws, bias, out, B, E, Cin, Cout, st);
 }

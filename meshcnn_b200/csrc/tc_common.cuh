@@ -28,6 +28,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity)
         : "memory");
 }
+// transaction-count side of an mbarrier: the bulk copies below complete `bytes` on it
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.expect_tx.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// 1-D bulk copy global -> shared through the async proxy (TMA engine, no tensor map): size is a multiple of 16 bytes, both
+// addresses 16-byte aligned; completion is signalled on the mbarrier as a transaction count
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
 // generic-proxy smem writes -> visible to the async proxy (tensor core reads operands through it)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 

@@ -54,7 +54,7 @@ class MeshConvFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = torch.zeros_like(x)
             if tc_ok and Cout % 32 == 0:
-                wtb = torch.empty(5 * Cin, Cout, dtype=torch.float32, device=x.device)
+                wtb = torch.empty(2 * 5 * Cin, Cout, dtype=torch.float32, device=x.device)
                 with profiler.span('meshconv_bwd_data_tc', B=B, E=E, Cin=Cin, Cout=Cout):
                     _lib.check(L.mcnn_meshconv_bwd_data_tc(dout.data_ptr(), x.data_ptr(), level.gemm.data_ptr(), level.ec.data_ptr(),
                                                            w.data_ptr(), dx.data_ptr(), wtb.data_ptr(), B, E, Cin, Cout, st),

@@ -32,5 +32,5 @@ class MeshConv(nn.Module):
         """Edge-major entry used by meshcnn_b200.networks: [B, E, Cin] -> [B, E, Cout]."""
         w = self.conv.weight
         if self._wt_ws is None or self._wt_ws.device != x_em.device:
-            self._wt_ws = torch.empty(w.shape[1] * 5, w.shape[0], dtype=torch.float32, device=x_em.device)
+            self._wt_ws = torch.empty(2 * w.shape[1] * 5, w.shape[0], dtype=torch.float32, device=x_em.device)
         return MeshConvFn.apply(x_em, w, self.conv.bias, batch.level(x_em.shape[1]), self._wt_ws)

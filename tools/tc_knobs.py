@@ -23,7 +23,7 @@ for E, cin, cout in shapes:
     from meshcnn_b200.mesh import Level
     level = Level(E, g, batch.level0.sides[:, :E].contiguous(), torch.full((B,), E, dtype=torch.int32, device=dev))
     out = torch.empty(B, E, cout, device=dev)
-    wt = torch.empty(5 * cin, cout, device=dev)
+    wt = torch.empty(2 * 5 * cin, cout, device=dev)
     res = []
     for knob in (0, 1, 2, 4, 3, 7):
         L.mcnn_debug_set_tc(knob)
