@@ -197,7 +197,7 @@ def run_reference(args, cfg, rank, world):
     """--impl reference: the reference's CPU algorithm (oracle port; the reference itself is Python and is not on
     the GPU box) on a bounded sample of the same workload.  Rank 0 only."""
     if rank != 0:
-        return
+        return None
     sample_B = min(cfg['B'], 16 if cfg['E'] <= 750 else 6)
     v, threads, sec = cpu_port_meshes_per_s(cfg, sample_B, max(1, args.steps), max(0, args.warmup))
     line = {'impl': 'reference', 'metric': 'train meshes/sec (fwd+bwd+pool)', 'value': v, 'unit': 'meshes/s', 'n_gpus': args.gpus,
@@ -210,7 +210,7 @@ def run_reference(args, cfg, rank, world):
                                        'reference' % (args.steps, sample_B, cfg['B'], threads)},
             'e2e': {'value': v, 'unit': 'meshes/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
-    print(json.dumps(line))
+    return line
 
 
 def workload_name(name, cfg):
@@ -221,7 +221,27 @@ def workload_name(name, cfg):
         name, '/'.join(map(str, cfg['ncf'])), '/'.join(map(str, cfg['pool_res'])), cfg['E'], cfg['B'], cfg['resblocks'])
 
 
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries (NCCL's version banner, torchrun notices) also write to fd 1, so
+    the real stdout is set aside for the result and fd 1 is pointed at stderr for everything else."""
+    sys.stdout.flush()
+    keep = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(keep, 'w')
+
+
+def _finish(out, line):
+    """Print the result and leave without running destructors: tearing an NCCL communicator down while CUDA graphs that
+    captured its collectives are still alive can block forever."""
+    if line is not None:
+        out.write(json.dumps(line) + '\n')
+        out.flush()
+    sys.stderr.flush()
+    os._exit(0)
+
+
 def main():
+    out = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=50)
@@ -240,8 +260,7 @@ def main():
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
     if args.impl == 'reference':
-        run_reference(args, cfg, rank, world)
-        return
+        _finish(out, run_reference(args, cfg, rank, world))
     if args.warmup < 3:
         args.warmup = 3
 
@@ -428,10 +447,11 @@ def main():
                'api': 'meshcnn_b200.graphed.GraphedTrainStep(meshes, x, y) from host buffers' if gs is not None else
                       'net(x, meshes) eager from host buffers'}
 
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        _finish(out, None)
 
     # ---- roofline of the dominant kernel (live CUDA-event timings collected inside the timed steps) ----------------
     agg = {}
@@ -443,18 +463,50 @@ def main():
     for (name, meta), (tot, cnt) in agg.items():
         by_kernel[name] = by_kernel.get(name, 0.0) + tot
     peak, peak_src = peaks()
-    roofline = None
+    roofline, pool_info = None, None
     if agg:
-        top_name = max(by_kernel, key=by_kernel.get)
+        dominant = max(by_kernel, key=by_kernel.get)
+        # The collapse kernel is a sequential algorithm (one edge after another, per mesh): it has no bandwidth or tensor
+        # roofline ("report us/collapse and x vs CPU").  It gets its own object; `roofline` describes the
+        # dominant THROUGHPUT kernel.
+        pools = [(k, v) for k, v in agg.items() if k[0] == 'pool_collapse']
+        if pools:
+            (name, meta), (tot, cnt) = max(pools, key=lambda kv: kv[1][0])
+            m = dict(meta)
+            us = 1e3 * tot / cnt
+            ncol = max(1, (m['E_in'] - m['T']) // 3)
+            pool_info = {'kernel': 'pool_collapse', 'bound': 'latency (sequential edge collapse, one CTA per mesh)', 'shape': m,
+                         'avg_launch_us': us, 'collapses_per_mesh': ncol, 'us_per_collapse': us / ncol,
+                         'us_per_mesh_per_level': us / m['B'], 'share_of_step': by_kernel['pool_collapse'] / eager_ms,
+                         'algorithmic_bytes': algorithmic_bytes('pool_collapse', m),
+                         'hbm_GBps': algorithmic_bytes('pool_collapse', m) / (us * 1e-6) / 1e9}
+        cands = {k: v for k, v in by_kernel.items() if k != 'pool_collapse'}
+        top_name = max(cands, key=cands.get) if cands else dominant
         (name, meta), (tot, cnt) = max(((k, v) for k, v in agg.items() if k[0] == top_name), key=lambda kv: kv[1][0])
         m = dict(meta)
-        nbytes = algorithmic_bytes(name, m)
+        base = name[:-3] if name.endswith('_tc') else name
+        nbytes = algorithmic_bytes(base, m)
         avg_ms = tot / cnt
-        ach = nbytes / (avg_ms * 1e-3) / 1e9
-        roofline = {'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak, 'traffic': None,
-                    'kernel': name, 'shape': m, 'avg_launch_ms': avg_ms, 'algorithmic_bytes': nbytes, 'peak_source': peak_src,
-                    'share_of_step': {k: v / eager_ms for k, v in sorted(by_kernel.items())},
-                    'timing': 'CUDA events around each C-ABI call in %d eagerly launched steps (%.3f ms/step) run right after the timed region' % (k_prof, eager_ms / k_prof)}
+        common = {'kernel': name, 'shape': m, 'avg_launch_ms': avg_ms, 'algorithmic_bytes': nbytes, 'traffic': None,
+                  'dominant_by_time': dominant,
+                  'share_of_step': {k: v / eager_ms for k, v in sorted(by_kernel.items())},
+                  'timing': 'CUDA events around each C-ABI call in %d eagerly launched steps (%.3f ms/step) run right after '
+                            'the timed region' % (k_prof, eager_ms / k_prof)}
+        if name.endswith('_tc'):
+            # tensor-core MeshConv: algorithmic flops of the contraction (fp32 result); the kernel issues 3 TF32 MMAs per
+            # algorithmic MMA (3xTF32 split), so the tensor pipe is busy for 3x the achieved figure.  Peak = TF32 dense rate,
+            # half the measured bf16 rate.
+            flops = (2.0 if 'fwd' in name else 2.0) * m['B'] * m['E'] * 5 * m['Cin'] * m['Cout']
+            ach = flops / (avg_ms * 1e-3) / 1e12
+            pk = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['bf16_tflops_sustained'] / 2.0 \
+                if os.path.exists(os.path.join(ROOT, 'MEASURED_PEAKS.json')) else 1125.0
+            roofline = dict(common, bound='tensor', achieved=ach, peak=pk, unit='TFLOP/s', frac=ach / pk,
+                            algorithmic_flops=flops, mma_passes=3, tensor_pipe_frac=3.0 * ach / pk,
+                            hbm_GBps=nbytes / (avg_ms * 1e-3) / 1e9,
+                            peak_source='TF32 dense = measured bf16 sustained (MEASURED_PEAKS.json) / 2')
+        else:
+            ach = nbytes / (avg_ms * 1e-3) / 1e9
+            roofline = dict(common, bound='hbm', achieved=ach, peak=peak, unit='GB/s', frac=ach / peak, peak_source=peak_src)
 
     cpu = None
     if not args.no_cpu_baseline:
@@ -471,10 +523,8 @@ def main():
                        'parallelism': 'dp%d (meshes sharded, one flat NCCL gradient allreduce)' % world,
                        'l2': 'flushed between timed steps (256 MiB write, untimed); per-step CUDA events, max over ranks',
                        'optimizer': 'Adam (in the timed region)', 'launch': mode},
-            'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks}
-    print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+            'roofline': roofline, 'pool_collapse': pool_info, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks}
+    _finish(out, line)
 
 
 if __name__ == '__main__':
