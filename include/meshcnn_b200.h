@@ -34,7 +34,7 @@ extern "C" {
 
 #define MCNN_OK 0
 #define MCNN_E_BADARG 1          /* null pointer / non-positive size / unsupported shape               */
-#define MCNN_E_TOO_LARGE 2       /* mesh does not fit the on-chip collapse state                        */
+#define MCNN_E_TOO_LARGE 2       /* mesh does not fit the on-chip collapse state and no workspace was given */
 #define MCNN_E_CUDA 3            /* a CUDA runtime call failed (see mcnn_last_cuda_error)               */
 
 /* per-mesh status words written by mcnn_pool_collapse (0 = fine).  The Python mirror turns them into the
@@ -156,6 +156,12 @@ typedef struct {
     int32_t* log_nunions;     /* [B]             */
     int32_t* log_unions;      /* [B][8*log_cap][2] pairs (src, dst)                                      */
     int32_t* edge_mask_out;   /* [B][E_in] survivor mask (1/0) or NULL                                   */
+    /* large meshes: when the collapse state of one mesh does not fit the shared memory of an SM (mcnn_pool_smem_bytes >
+     * mcnn_pool_smem_limit) the same kernel runs with 32-bit ids on this global-memory workspace, one slice per mesh */
+    void* workspace;          /* [B][workspace_stride] bytes or NULL                                     */
+    long long workspace_stride; /* >= mcnn_pool_workspace_bytes(E_in, V, ve_cap, with_vs)                */
+    int32_t force_workspace;  /* != 0: use the workspace variant even if the mesh would fit on chip (tests) */
+    int32_t reserved3;
     long long* dbg_clocks;    /* [B][24] SM clock at the phase boundaries of each mesh's CTA (diagnostics) or NULL:
                                  0 start, 1 loaded, 2 sorted, 3 collapse done, 4 unions applied, 5 topology written, 6 end;
                                  7 = pops; 8..18 = cycles per collapse stage (only in -DMCNN_POOL_PROF builds)          */
@@ -169,6 +175,8 @@ int mcnn_pool_collapse(const mcnn_pool_args* args, void* stream);
  * MCNN_E_TOO_LARGE */
 size_t mcnn_pool_smem_bytes(int E_in, int V, int ve_cap, int with_vs);
 size_t mcnn_pool_smem_limit(void);
+/* bytes of global-memory workspace PER MESH for the large-mesh variant */
+size_t mcnn_pool_workspace_bytes(int E_in, int V, int ve_cap, int with_vs);
 
 /* rebuild_features_average (mesh_union.py:27-36):  out[b][r] = mean_{j in row r} x[b][j],  rows >= ec_out = 0
  *   x [B][E_in][C]   out [B][T][C] */

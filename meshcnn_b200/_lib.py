@@ -25,7 +25,9 @@ class PoolArgs(ctypes.Structure):
         ('grp_rowptr', _c_vp), ('grp_cols', _c_vp), ('grp_colptr', _c_vp), ('grp_rows', _c_vp), ('occ', _c_vp),
         ('status', _c_vp),
         ('log_npops', _c_vp), ('log_pops', _c_vp), ('log_outcome', _c_vp), ('log_nunions', _c_vp), ('log_unions', _c_vp),
-        ('edge_mask_out', _c_vp), ('dbg_clocks', _c_vp),
+        ('edge_mask_out', _c_vp),
+        ('workspace', _c_vp), ('workspace_stride', ctypes.c_longlong), ('force_workspace', ctypes.c_int32), ('reserved3', ctypes.c_int32),
+        ('dbg_clocks', _c_vp),
     ]
 
 
@@ -47,6 +49,7 @@ SIGNATURES = {
     'mcnn_pool_collapse': (_c_int, [ctypes.POINTER(PoolArgs), _c_vp]),
     'mcnn_pool_smem_bytes': (_c_sz, [_c_int, _c_int, _c_int, _c_int]),
     'mcnn_pool_smem_limit': (_c_sz, []),
+    'mcnn_pool_workspace_bytes': (_c_sz, [_c_int, _c_int, _c_int, _c_int]),
     'mcnn_segmean_fwd': (_c_int, [_c_vp] * 5 + [_c_int] * 5 + [_c_vp]),
     'mcnn_segmean_bwd': (_c_int, [_c_vp] * 6 + [_c_int] * 5 + [_c_vp]),
     'mcnn_unpool_fwd': (_c_int, [_c_vp] * 6 + [_c_int] * 6 + [_c_vp]),

@@ -29,9 +29,33 @@
 
 namespace mcnn {
 
-typedef int16_t idx_t;           // shared-memory variant: n, V, list entries < 32768 (0xFFFF = nil)
+// Two instantiations of the same kernel:
+//   Narrow  16-bit ids, state in dynamic shared memory, 256 threads            (meshes up to a few thousand edges)
+//   Wide    32-bit ids, state in a per-mesh global-memory workspace (L2), 1024 threads  (no size limit: 170 k-edge meshes)
+struct Narrow {
+    typedef int16_t idx_t;
+    typedef uint16_t uidx_t;
+    typedef uint32_t pair_t;
+    static constexpr unsigned NIL = 0xFFFFu;
+    static constexpr int SHIFT = 16;
+    static constexpr int THREADS = 256;
+    static constexpr bool WIDE = false;
+};
+struct Wide {
+    typedef int32_t idx_t;
+    typedef uint32_t uidx_t;
+    typedef unsigned long long pair_t;
+    static constexpr unsigned NIL = 0xFFFFFFFFu;
+    static constexpr int SHIFT = 32;
+    static constexpr int THREADS = 1024;
+    static constexpr bool WIDE = true;
+};
+template <class P> __device__ __forceinline__ typename P::pair_t pr_pack(int a, int b) {
+    return (typename P::pair_t)(typename P::uidx_t)a | ((typename P::pair_t)(typename P::uidx_t)b << P::SHIFT);
+}
+template <class P> __device__ __forceinline__ int pr_lo(typename P::pair_t w) { return (int)(typename P::uidx_t)w; }
+template <class P> __device__ __forceinline__ int pr_hi(typename P::pair_t w) { return (int)(typename P::uidx_t)(w >> P::SHIFT); }
 
-constexpr int POOL_THREADS = 256;
 constexpr int POOL_BFS_CAP = 96;         // members of one MeshUnion row / column walked per thread (implementation limit)
 
 struct PoolLayout {
@@ -42,39 +66,47 @@ struct PoolLayout {
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+template <class P>
 __host__ __device__ inline PoolLayout pool_layout(int n, int V, int ve_cap, bool with_vs) {
+    typedef typename P::idx_t idx_t;
+    typedef typename P::uidx_t uidx_t;
+    typedef typename P::pair_t pair_t;
     PoolLayout L;
     size_t o = 0;
     L.vs = o; o += with_vs ? sizeof(double) * 3 * (size_t)V : 0; o = align_up(o, 16);
     L.gemm = o; o += sizeof(idx_t) * 4 * (size_t)n; o = align_up(o, 16);          // later: column member pool (u16[3n]) + col_off
-    L.evp = o; o += sizeof(uint32_t) * (size_t)n; o = align_up(o, 16);            // evp + sides, later: row member pool (u16[3n]) + ...
+    L.evp = o; o += sizeof(pair_t) * (size_t)n; o = align_up(o, 16);            // evp + sides, later: row member pool (u16[3n]) + ...
     L.sides = o; o += 4 * (size_t)n; o = align_up(o, 16);
     L.mask = o; o += (size_t)n; o = align_up(o, 16);
-    L.order = o; o += sizeof(idx_t) * (size_t)n; o = align_up(o, 16);
-    L.rep = o; o += sizeof(idx_t) * (size_t)V; o = align_up(o, 16);
+    L.order = o; o += sizeof(uidx_t) * (size_t)n; o = align_up(o, 16);
+    L.rep = o; o += sizeof(uidx_t) * (size_t)V; o = align_up(o, 16);
     L.stamp = o; o += sizeof(uint32_t) * (size_t)V; o = align_up(o, 16);
-    L.slab_start = o; o += sizeof(uint16_t) * (size_t)V; o = align_up(o, 16);
-    L.slab_len = o; o += sizeof(uint16_t) * (size_t)V; o = align_up(o, 16);
-    L.slab_next = o; o += sizeof(idx_t) * (size_t)V; o = align_up(o, 16);
-    L.chain_tail = o; o += sizeof(idx_t) * (size_t)V; o = align_up(o, 16);
+    L.slab_start = o; o += sizeof(uidx_t) * (size_t)V; o = align_up(o, 16);
+    L.slab_len = o; o += sizeof(uidx_t) * (size_t)V; o = align_up(o, 16);
+    L.slab_next = o; o += sizeof(uidx_t) * (size_t)V; o = align_up(o, 16);
+    L.chain_tail = o; o += sizeof(uidx_t) * (size_t)V; o = align_up(o, 16);
     L.vmask = o; o += (size_t)V; o = align_up(o, 16);
-    L.ve = o; o += sizeof(uint16_t) * (size_t)ve_cap; o = align_up(o, 16);
-    L.eposa = o; o += sizeof(uint16_t) * (size_t)n; o = align_up(o, 16);
-    L.eposb = o; o += sizeof(uint16_t) * (size_t)n; o = align_up(o, 16);
+    L.ve = o; o += sizeof(uidx_t) * (size_t)ve_cap; o = align_up(o, 16);
+    L.eposa = o; o += sizeof(uidx_t) * (size_t)n; o = align_up(o, 16);
+    L.eposb = o; o += sizeof(uidx_t) * (size_t)n; o = align_up(o, 16);
     L.ulog_cap = 2 * n + 16;                     // every union's source dies within the same attempt: <= 2 per dead edge
-    L.ulog = o; o += sizeof(uint32_t) * (size_t)L.ulog_cap; o = align_up(o, 16);
+    L.ulog = o; o += sizeof(pair_t) * (size_t)L.ulog_cap; o = align_up(o, 16);
     L.cnt32 = o; o += sizeof(int) * 2 * (size_t)n; o = align_up(o, 16);           // out-degree, row length / cursor
     int np2 = 1;
     while (np2 < n) np2 <<= 1;
     L.npow2 = np2;
     // the sort keys (uint64[npow2]) are dead before the group evaluation needs occ (int32[n]) + out0 / out1 (u16[n] each)
-    L.keys = o; o += sizeof(unsigned long long) * (size_t)np2; o = align_up(o, 16);
+    {
+        const size_t ksz = sizeof(unsigned long long) * (size_t)np2, esz = (sizeof(int) + 2 * sizeof(uidx_t)) * (size_t)n;
+        L.keys = o; o += ksz > esz ? ksz : esz; o = align_up(o, 16);
+    }
     L.scan = o; o += sizeof(int) * 48; o = align_up(o, 16);
     L.total = o;
     return L;
 }
 
 // exclusive block scan of one int per thread; returns the prefix and (to all threads) the block total
+template <int NT>
 __device__ __forceinline__ int block_scan_excl(int v, int* scratch, int& total) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     int incl = v;
@@ -86,7 +118,7 @@ __device__ __forceinline__ int block_scan_excl(int v, int* scratch, int& total) 
     if (lane == 31) scratch[wid] = incl;
     __syncthreads();
     if (wid == 0) {
-        int w = (lane < POOL_THREADS / 32) ? scratch[lane] : 0;
+        int w = (lane < NT / 32) ? scratch[lane] : 0;
         int wi = w;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -103,19 +135,18 @@ __device__ __forceinline__ int block_scan_excl(int v, int* scratch, int& total) 
     return res;
 }
 
-constexpr unsigned NIL16 = 0xFFFFu;
 
 // The sequential collapse runs on thread 0.  Walks over vertex -> edge lists (the one-ring test, and the rare search for
 // the first occurrence of id 0) are handed to a helper warp (warp 1) through a small shared-memory ring: it walks a list 32
 // entries at a time and the collapse thread waits for the answer.
+template <class P>
 struct WarpCtx {
-    uint16_t *ve, *slab_start, *slab_len;
-    idx_t *slab_next, *chain_tail, *rep;
-    uint32_t *evp, *stamp;
+    typename P::uidx_t *ve, *slab_start, *slab_len, *slab_next, *chain_tail, *rep;
+    typename P::pair_t* evp;
+    uint32_t* stamp;
 };
 
 enum { WOP_EXIT = 0, WOP_ONE_RING = 1, WOP_REMOVE_SCAN = 2 };
-constexpr unsigned VE_TOMB = 0xFFFFu;          // removed list entry
 constexpr int WQ_CAP = 32;
 
 struct WorkQueue {
@@ -126,20 +157,22 @@ struct WorkQueue {
     int res_seq;              // sequence number (1-based) that `res` belongs to
 };
 
-__device__ __forceinline__ int uf_find(idx_t* rep, int v) {
+template <class U>
+__device__ __forceinline__ int uf_find(U* rep, int v) {
     int p = rep[v];
     while (p != v) {
         const int gp = rep[p];
-        rep[v] = (idx_t)gp;                             // path halving; concurrent lanes only ever write ancestors
+        rep[v] = (U)gp;                                 // path halving; concurrent lanes only ever write ancestors
         v = gp;
         p = rep[v];
     }
     return v;
 }
-__device__ __forceinline__ void edge_ends(const uint32_t* evp, idx_t* rep, int e, int& v0, int& v1) {
-    const uint32_t w = evp[e];
-    const int a = (int)(w & 0xFFFFu), b = (int)(w >> 16);
-    const int ra = rep[a], rb = rep[b];                 // both loads in flight before either branch
+template <class P>
+__device__ __forceinline__ void edge_ends(const typename P::pair_t* evp, typename P::uidx_t* rep, int e, int& v0, int& v1) {
+    const typename P::pair_t w = evp[e];
+    const int a = pr_lo<P>(w), b = pr_hi<P>(w);
+    const int ra = (int)rep[a], rb = (int)rep[b];                 // both loads in flight before either branch
     v0 = (ra == a) ? a : uf_find(rep, a);
     v1 = (rb == b) ? b : uf_find(rep, b);
 }
@@ -147,20 +180,21 @@ __device__ __forceinline__ void edge_ends(const uint32_t* evp, idx_t* rep, int e
 // __is_one_ring_valid (mesh_pool.py:95-100); the lists may hold stale / dead edge ids.  stamp[w] = tagA marks w as an
 // endpoint seen from v0; the lane that flips it to tagB counts it once.  The first slab of both lists (the whole list
 // unless a vertex was merged within this level) is fetched and resolved together, so the two dependent load chains overlap.
-__device__ __forceinline__ int wop_one_ring(const WarpCtx& w, int lane, int v0, int v1, uint32_t tagA, long long* hp) {
+template <class P>
+__device__ __forceinline__ int wop_one_ring(const WarpCtx<P>& w, int lane, int v0, int v1, uint32_t tagA, long long* hp) {
     const uint32_t tagB = tagA | 1u;
 #ifdef MCNN_POOL_PROF
     const long long t0_ = clock64();
 #endif
     const int start0 = w.slab_start[v0], len0 = w.slab_len[v0];
     const int start1 = w.slab_start[v1], len1 = w.slab_len[v1];
-    const unsigned next0 = (unsigned short)w.slab_next[v0], next1 = (unsigned short)w.slab_next[v1];
-    const unsigned x0 = (lane < len0) ? (unsigned)w.ve[start0 + lane] : VE_TOMB;
-    const unsigned x1 = (lane < len1) ? (unsigned)w.ve[start1 + lane] : VE_TOMB;
+    const unsigned next0 = (unsigned)w.slab_next[v0], next1 = (unsigned)w.slab_next[v1];
+    const unsigned x0 = (lane < len0) ? (unsigned)w.ve[start0 + lane] : P::NIL;
+    const unsigned x1 = (lane < len1) ? (unsigned)w.ve[start1 + lane] : P::NIL;
     int a0 = 0, b0 = 0, a1 = 0, b1 = 0;
-    if (x0 != VE_TOMB) edge_ends(w.evp, w.rep, (int)x0, a0, b0);
-    if (x1 != VE_TOMB) edge_ends(w.evp, w.rep, (int)x1, a1, b1);
-    if (x0 != VE_TOMB) { w.stamp[a0] = tagA; w.stamp[b0] = tagA; }
+    if (x0 != P::NIL) edge_ends<P>(w.evp, w.rep, (int)x0, a0, b0);
+    if (x1 != P::NIL) edge_ends<P>(w.evp, w.rep, (int)x1, a1, b1);
+    if (x0 != P::NIL) { w.stamp[a0] = tagA; w.stamp[b0] = tagA; }
 #ifdef MCNN_POOL_PROF
     const long long t1_ = clock64();
 #endif
@@ -171,14 +205,14 @@ __device__ __forceinline__ int wop_one_ring(const WarpCtx& w, int lane, int v0, 
         while (true) {
             for (int i = first + lane; i < len; i += 32) {
                 const unsigned x = w.ve[start + i];
-                if (x == VE_TOMB) continue;
+                if (x == P::NIL) continue;
                 int a, b;
-                edge_ends(w.evp, w.rep, (int)x, a, b);
+                edge_ends<P>(w.evp, w.rep, (int)x, a, b);
                 w.stamp[a] = tagA;
                 w.stamp[b] = tagA;
             }
-            s = (s == (unsigned)v0) ? next0 : (unsigned)(unsigned short)w.slab_next[s];
-            if (s == NIL16) break;
+            s = (s == (unsigned)v0) ? next0 : (unsigned)(unsigned)w.slab_next[s];
+            if (s == P::NIL) break;
             start = w.slab_start[s]; len = w.slab_len[s]; first = 0;
         }
     }
@@ -187,7 +221,7 @@ __device__ __forceinline__ int wop_one_ring(const WarpCtx& w, int lane, int v0, 
     const long long t2_ = clock64();
 #endif
     bool ha = false, hb = false;
-    if (x1 != VE_TOMB) {
+    if (x1 != P::NIL) {
         if (a1 != v0 && a1 != v1) ha = atomicCAS(&w.stamp[a1], tagA, tagB) == tagA;
         if (b1 != v0 && b1 != v1) hb = atomicCAS(&w.stamp[b1], tagA, tagB) == tagA;
     }
@@ -202,18 +236,18 @@ __device__ __forceinline__ int wop_one_ring(const WarpCtx& w, int lane, int v0, 
         while (true) {
             for (int base = first; base < len; base += 32) {
                 const int i = base + lane;
-                const unsigned x = (i < len) ? (unsigned)w.ve[start + i] : VE_TOMB;
+                const unsigned x = (i < len) ? (unsigned)w.ve[start + i] : P::NIL;
                 ha = false; hb = false;
-                if (x != VE_TOMB) {
+                if (x != P::NIL) {
                     int a, b;
-                    edge_ends(w.evp, w.rep, (int)x, a, b);
+                    edge_ends<P>(w.evp, w.rep, (int)x, a, b);
                     if (a != v0 && a != v1) ha = atomicCAS(&w.stamp[a], tagA, tagB) == tagA;
                     if (b != v0 && b != v1) hb = atomicCAS(&w.stamp[b], tagA, tagB) == tagA;
                 }
                 shared += __popc(__ballot_sync(0xffffffffu, ha)) + __popc(__ballot_sync(0xffffffffu, hb));
             }
-            s = (s == (unsigned)v1) ? next1 : (unsigned)(unsigned short)w.slab_next[s];
-            if (s == NIL16) break;
+            s = (s == (unsigned)v1) ? next1 : (unsigned)(unsigned)w.slab_next[s];
+            if (s == P::NIL) break;
             start = w.slab_start[s]; len = w.slab_len[s]; first = 0;
         }
     }
@@ -221,15 +255,16 @@ __device__ __forceinline__ int wop_one_ring(const WarpCtx& w, int lane, int v0, 
 }
 
 // list.remove(x) on ve[v] (mesh.py:48) by search: the first occurrence in list order becomes a tombstone
-__device__ __forceinline__ bool wop_list_remove(const WarpCtx& w, int lane, int v, int x) {
-    for (unsigned s = (unsigned)v; s != NIL16; s = (unsigned short)w.slab_next[s]) {
+template <class P>
+__device__ __forceinline__ bool wop_list_remove(const WarpCtx<P>& w, int lane, int v, int x) {
+    for (unsigned s = (unsigned)v; s != P::NIL; s = (unsigned)w.slab_next[s]) {
         const int start = w.slab_start[s], len = w.slab_len[s];
         for (int base = 0; base < len; base += 32) {
             const int i = base + lane;
             const bool hit = (i < len) && ((int)w.ve[start + i] == x);
             const unsigned m = __ballot_sync(0xffffffffu, hit);
             if (m != 0u) {
-                if (lane == __ffs(m) - 1) w.ve[start + i] = (uint16_t)VE_TOMB;
+                if (lane == __ffs(m) - 1) w.ve[start + i] = (typename P::uidx_t)P::NIL;
                 __syncwarp();
                 return true;
             }
@@ -239,7 +274,8 @@ __device__ __forceinline__ bool wop_list_remove(const WarpCtx& w, int lane, int 
 }
 
 // Service loop of the helper warp: executes the posted operations in order until WOP_EXIT.
-__device__ void helper_warp_loop(const WarpCtx& w, WorkQueue* q, int lane, long long* hprof) {
+template <class P>
+__device__ void helper_warp_loop(const WarpCtx<P>& w, WorkQueue* q, int lane, long long* hprof) {
     volatile int* vhead = &q->head;
     int seq = 0;                                             // operations finished so far
     while (true) {
@@ -256,10 +292,10 @@ __device__ void helper_warp_loop(const WarpCtx& w, WorkQueue* q, int lane, long 
 #endif
         int r;
         if (rq.x == WOP_ONE_RING) {
-            r = wop_one_ring(w, lane, rq.y, rq.z, (uint32_t)rq.w, hprof ? hprof + 3 : nullptr);
+            r = wop_one_ring<P>(w, lane, rq.y, rq.z, (uint32_t)rq.w, hprof ? hprof + 3 : nullptr);
         } else {                                             // WOP_REMOVE_SCAN: x leaves ve[a], then ve[b] (mesh.py:42-48)
-            r = wop_list_remove(w, lane, rq.z, rq.y) ? 1 : 0;
-            if (r) r = wop_list_remove(w, lane, rq.w, rq.y) ? 1 : 0;
+            r = wop_list_remove<P>(w, lane, rq.z, rq.y) ? 1 : 0;
+            if (r) r = wop_list_remove<P>(w, lane, rq.w, rq.y) ? 1 : 0;
         }
         if (lane == 0) {
             *(volatile int*)&q->res = r;
@@ -275,12 +311,16 @@ __device__ void helper_warp_loop(const WarpCtx& w, WorkQueue* q, int lane, long 
 }
 
 // The collapse state as seen by lane 0 of warp 0 (the only thread that runs the reference's control flow).
+template <class P>
 struct Collapse {
+    typedef typename P::idx_t idx_t;
+    typedef typename P::uidx_t uidx_t;
+    typedef typename P::pair_t pair_t;
     WorkQueue* q;             // list walks go to the helper warp
     int posted;
-    idx_t *gemm, *rep, *slab_next, *chain_tail;
-    uint16_t *ve, *eposa, *eposb;
-    uint32_t *evp, *ulog;
+    idx_t* gemm;
+    uidx_t *rep, *slab_next, *chain_tail, *ve, *eposa, *eposb;
+    pair_t *evp, *ulog;
     int8_t* sides;
     uint8_t* mask;
     double* vs;               // shared copy or nullptr
@@ -297,7 +337,7 @@ struct Collapse {
 #else
 #define PROF_T(i, stmt) { stmt; }
 #endif
-    __device__ __forceinline__ void ends(int e, int& v0, int& v1) { edge_ends(evp, rep, e, v0, v1); }
+    __device__ __forceinline__ void ends(int e, int& v0, int& v1) { edge_ends<P>(evp, rep, e, v0, v1); }
 
     __device__ __forceinline__ void post(int op, int a0, int a1, int a2) {
         while (posted - *(volatile int*)&q->done >= WQ_CAP) {}
@@ -317,20 +357,30 @@ struct Collapse {
     __device__ __forceinline__ void group_union(int s, int t) {
         if (log_unions != nullptr && nunions < union_cap) { log_unions[2 * nunions] = s; log_unions[2 * nunions + 1] = t; }
         if (s == t) status = MCNN_ST_DEGENERATE;
-        if (nunions < ulog_cap) ulog[nunions] = (uint32_t)s | ((uint32_t)t << 16);
+        if (nunions < ulog_cap) ulog[nunions] = pr_pack<P>(s, t);
         else status = MCNN_ST_GROUP_OVERFLOW;
         ++nunions;
     }
 
     // MeshPool.has_boundaries (mesh_pool.py:87-92)
     __device__ bool has_boundaries(int e) const {
-        const unsigned long long row = *reinterpret_cast<const unsigned long long*>(gemm + 4 * e);
-        if ((row & 0x8000800080008000ULL) != 0ULL) return true;
-        const unsigned long long r0 = *reinterpret_cast<const unsigned long long*>(gemm + 4 * (int)(row & 0xFFFF));
-        const unsigned long long r1 = *reinterpret_cast<const unsigned long long*>(gemm + 4 * (int)((row >> 16) & 0xFFFF));
-        const unsigned long long r2 = *reinterpret_cast<const unsigned long long*>(gemm + 4 * (int)((row >> 32) & 0xFFFF));
-        const unsigned long long r3 = *reinterpret_cast<const unsigned long long*>(gemm + 4 * (int)((row >> 48) & 0xFFFF));
-        return ((r0 | r1 | r2 | r3) & 0x8000800080008000ULL) != 0ULL;
+        if (!P::WIDE) {
+            const unsigned long long row = *reinterpret_cast<const unsigned long long*>(gemm + 4 * e);
+            if ((row & 0x8000800080008000ULL) != 0ULL) return true;
+            const unsigned long long r0 = *reinterpret_cast<const unsigned long long*>(gemm + 4 * (int)(row & 0xFFFF));
+            const unsigned long long r1 = *reinterpret_cast<const unsigned long long*>(gemm + 4 * (int)((row >> 16) & 0xFFFF));
+            const unsigned long long r2 = *reinterpret_cast<const unsigned long long*>(gemm + 4 * (int)((row >> 32) & 0xFFFF));
+            const unsigned long long r3 = *reinterpret_cast<const unsigned long long*>(gemm + 4 * (int)((row >> 48) & 0xFFFF));
+            return ((r0 | r1 | r2 | r3) & 0x8000800080008000ULL) != 0ULL;
+        } else {
+            const int4 row = *reinterpret_cast<const int4*>(gemm + 4 * e);
+            if ((row.x | row.y | row.z | row.w) < 0) return true;
+            const int4 r0 = *reinterpret_cast<const int4*>(gemm + 4 * row.x);
+            const int4 r1 = *reinterpret_cast<const int4*>(gemm + 4 * row.y);
+            const int4 r2 = *reinterpret_cast<const int4*>(gemm + 4 * row.z);
+            const int4 r3 = *reinterpret_cast<const int4*>(gemm + 4 * row.w);
+            return ((r0.x | r0.y | r0.z | r0.w | r1.x | r1.y | r1.z | r1.w | r2.x | r2.y | r2.z | r2.w | r3.x | r3.y | r3.z | r3.w) < 0);
+        }
     }
 
     struct Face { int ka, kb, sa, sb, osa, osb, oka0, oka1, okb0, okb1; };
@@ -443,9 +493,9 @@ struct Collapse {
     // Mesh.remove_edge (mesh.py:42-48): both list entries of x become tombstones
     __device__ void remove_edge(int x) {
         const unsigned ia = eposa[x], ib = eposb[x];
-        if (x != 0 && ia != NIL16 && ib != NIL16 && ve[ia] == x && ve[ib] == x) {
-            ve[ia] = (uint16_t)VE_TOMB;
-            ve[ib] = (uint16_t)VE_TOMB;
+        if (x != 0 && ia != P::NIL && ib != P::NIL && (int)ve[ia] == x && (int)ve[ib] == x) {
+            ve[ia] = (uidx_t)P::NIL;
+            ve[ib] = (uidx_t)P::NIL;
             return;
         }
         int a, b;
@@ -479,9 +529,9 @@ struct Collapse {
         }
         vmask[v1] = 0;
         // ve[v0].extend(ve[v1]) : v1's chain moves behind v0's (ve[v1] is unreachable once every row holding v1 reads v0)
-        slab_next[(unsigned short)chain_tail[v0]] = (idx_t)v1;
+        slab_next[(unsigned)chain_tail[v0]] = (uidx_t)v1;
         chain_tail[v0] = chain_tail[v1];
-        rep[v1] = (idx_t)v0;          // edges[edges == v1] = v0 over every row
+        rep[v1] = (uidx_t)v0;         // edges[edges == v1] = v0 over every row
     }
 
     // __pool_edge (mesh_pool.py:58-72)
@@ -505,32 +555,38 @@ struct Collapse {
     }
 };
 
-__global__ void __launch_bounds__(POOL_THREADS, 1) pool_collapse_kernel(const mcnn_pool_args a) {
-    extern __shared__ __align__(16) unsigned char smem[];
+template <class P>
+__global__ void __launch_bounds__(P::THREADS, 1) pool_collapse_kernel(const mcnn_pool_args a) {
+    typedef typename P::idx_t idx_t;
+    typedef typename P::uidx_t uidx_t;
+    typedef typename P::pair_t pair_t;
+    constexpr int POOL_THREADS = P::THREADS;
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    unsigned char* smem = P::WIDE ? reinterpret_cast<unsigned char*>(a.workspace) + (size_t)blockIdx.x * a.workspace_stride : dyn_smem;
     const int b = blockIdx.x;
     const int tid = threadIdx.x;
     const int E_in = a.E_in, T = a.T, V = a.V;
     const int n = a.ec_in[b];                      // rows of the incoming level
     const bool with_vs = a.vs != nullptr;
-    const PoolLayout L = pool_layout(E_in, V, a.ve_cap, with_vs);
+    const PoolLayout L = pool_layout<P>(E_in, V, a.ve_cap, with_vs);
 
     double* vs_s = with_vs ? reinterpret_cast<double*>(smem + L.vs) : nullptr;
     idx_t* gemm = reinterpret_cast<idx_t*>(smem + L.gemm);
-    uint32_t* evp = reinterpret_cast<uint32_t*>(smem + L.evp);
+    pair_t* evp = reinterpret_cast<pair_t*>(smem + L.evp);
     int8_t* sides = reinterpret_cast<int8_t*>(smem + L.sides);
     uint8_t* mask = smem + L.mask;
-    idx_t* order = reinterpret_cast<idx_t*>(smem + L.order);
-    idx_t* rep = reinterpret_cast<idx_t*>(smem + L.rep);
+    uidx_t* order = reinterpret_cast<uidx_t*>(smem + L.order);
+    uidx_t* rep = reinterpret_cast<uidx_t*>(smem + L.rep);
     uint32_t* stamp = reinterpret_cast<uint32_t*>(smem + L.stamp);
-    uint16_t* slab_start = reinterpret_cast<uint16_t*>(smem + L.slab_start);
-    uint16_t* slab_len = reinterpret_cast<uint16_t*>(smem + L.slab_len);
-    idx_t* slab_next = reinterpret_cast<idx_t*>(smem + L.slab_next);
-    idx_t* chain_tail = reinterpret_cast<idx_t*>(smem + L.chain_tail);
+    uidx_t* slab_start = reinterpret_cast<uidx_t*>(smem + L.slab_start);
+    uidx_t* slab_len = reinterpret_cast<uidx_t*>(smem + L.slab_len);
+    uidx_t* slab_next = reinterpret_cast<uidx_t*>(smem + L.slab_next);
+    uidx_t* chain_tail = reinterpret_cast<uidx_t*>(smem + L.chain_tail);
     uint8_t* vmask_s = smem + L.vmask;
-    uint16_t* ve = reinterpret_cast<uint16_t*>(smem + L.ve);
-    uint16_t* eposa = reinterpret_cast<uint16_t*>(smem + L.eposa);
-    uint16_t* eposb = reinterpret_cast<uint16_t*>(smem + L.eposb);
-    uint32_t* ulog = reinterpret_cast<uint32_t*>(smem + L.ulog);
+    uidx_t* ve = reinterpret_cast<uidx_t*>(smem + L.ve);
+    uidx_t* eposa = reinterpret_cast<uidx_t*>(smem + L.eposa);
+    uidx_t* eposb = reinterpret_cast<uidx_t*>(smem + L.eposb);
+    pair_t* ulog = reinterpret_cast<pair_t*>(smem + L.ulog);
     unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem + L.keys);
     int* scan = reinterpret_cast<int*>(smem + L.scan);
 
@@ -551,24 +607,24 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) pool_collapse_kernel(const mc
         sides[i] = g_sides[i];
     }
     for (int i = tid; i < n; i += POOL_THREADS) {
-        evp[i] = (uint32_t)(g_edges[2 * i] & 0xFFFF) | ((uint32_t)(g_edges[2 * i + 1] & 0xFFFF) << 16);
+        evp[i] = pr_pack<P>(g_edges[2 * i], g_edges[2 * i + 1]);
         mask[i] = 1;
-        eposa[i] = (uint16_t)NIL16;
-        eposb[i] = (uint16_t)NIL16;
+        eposa[i] = (uidx_t)P::NIL;
+        eposb[i] = (uidx_t)P::NIL;
     }
     for (int v = tid; v < V; v += POOL_THREADS) {
-        rep[v] = (idx_t)v;
+        rep[v] = (uidx_t)v;
         stamp[v] = 0u;
         vmask_s[v] = g_vmask[v];
         const int beg = g_ve_ptr[v], end = g_ve_ptr[v + 1];
-        slab_start[v] = (uint16_t)beg;
-        slab_len[v] = (uint16_t)(end - beg);
-        slab_next[v] = (idx_t)NIL16;
-        chain_tail[v] = (idx_t)v;
+        slab_start[v] = (uidx_t)beg;
+        slab_len[v] = (uidx_t)(end - beg);
+        slab_next[v] = (uidx_t)P::NIL;
+        chain_tail[v] = (uidx_t)v;
     }
     {
         const int nve = min(g_ve_ptr[V], a.ve_cap);
-        for (int i = tid; i < nve; i += POOL_THREADS) ve[i] = (uint16_t)g_ve_idx[i];
+        for (int i = tid; i < nve; i += POOL_THREADS) ve[i] = (uidx_t)g_ve_idx[i];
     }
     if (with_vs)
         for (int i = tid; i < 3 * V; i += POOL_THREADS) vs_s[i] = g_vs[i];
@@ -594,16 +650,16 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) pool_collapse_kernel(const mc
             __syncthreads();
         }
     }
-    for (int i = tid; i < n; i += POOL_THREADS) order[i] = (idx_t)(keys[i] & 0xffffffffULL);
+    for (int i = tid; i < n; i += POOL_THREADS) order[i] = (uidx_t)(keys[i] & 0xffffffffULL);
     // where the two list entries of every edge sit (the entry in the slab of its first / second endpoint)
     for (int v = tid; v < V; v += POOL_THREADS) {
         const int start = slab_start[v], len = slab_len[v];
         for (int i = start; i < start + len; ++i) {
             const int x = ve[i];
             if (x >= n) continue;
-            const uint32_t w = evp[x];
-            if ((int)(w & 0xFFFFu) == v) eposa[x] = (uint16_t)i;
-            else if ((int)(w >> 16) == v) eposb[x] = (uint16_t)i;
+            const pair_t w = evp[x];
+            if (pr_lo<P>(w) == v) eposa[x] = (uidx_t)i;
+            else if (pr_hi<P>(w) == v) eposb[x] = (uidx_t)i;
         }
     }
     __shared__ int s_status, s_nunions, s_cursor, s_flag, s_ndead;
@@ -615,7 +671,7 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) pool_collapse_kernel(const mc
     if (tid == 0) { s_queue.head = 0; s_queue.done = 0; s_queue.res = 0; s_queue.res_seq = 0; }
     __syncthreads();
     if (tid == 0) {
-        Collapse c;
+        Collapse<P> c;
         c.q = &s_queue; c.posted = 0;
         c.gemm = gemm; c.rep = rep; c.slab_next = slab_next; c.chain_tail = chain_tail; c.ve = ve; c.eposa = eposa; c.eposb = eposb;
         c.evp = evp; c.ulog = ulog;
@@ -650,10 +706,10 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) pool_collapse_kernel(const mc
 #endif
         }
     } else if (tid >= 32 && tid < 64) {
-        WarpCtx w;
+        WarpCtx<P> w;
         w.ve = ve; w.slab_start = slab_start; w.slab_len = slab_len; w.slab_next = slab_next; w.chain_tail = chain_tail;
         w.rep = rep; w.evp = evp; w.stamp = stamp;
-        helper_warp_loop(w, &s_queue, tid - 32, clk ? clk + 13 : nullptr);
+        helper_warp_loop<P>(w, &s_queue, tid - 32, clk ? clk + 13 : nullptr);
     }
     __syncthreads();
     int status = s_status;
@@ -661,31 +717,31 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) pool_collapse_kernel(const mc
     // ---- phase E: Mesh.clean (mesh.py:50-71) + group export ---------------------------------------------------
     // group evaluation scratch: occ / out-adjacency live where the sort keys were
     int* occ = reinterpret_cast<int*>(smem + L.keys);                       // int32[n]
-    uint16_t* out0 = reinterpret_cast<uint16_t*>(occ + n);                  // u16[n]
-    uint16_t* out1 = out0 + n;                                               // u16[n]
+    uidx_t* out0 = reinterpret_cast<uidx_t*>(occ + n);                      // [n]
+    uidx_t* out1 = out0 + n;                                                 // [n]
     int* outdeg = reinterpret_cast<int*>(smem + L.cnt32);                   // int32[n]  (later: column lengths)
     int* rowlen = outdeg + n;                                                // int32[n]  (row lengths, then fill cursors)
     for (int i = tid; i < n; i += POOL_THREADS) { occ[i] = 1; outdeg[i] = 0; rowlen[i] = 0; }
     // E1: survivor ranks; dead -> 0
-    idx_t* newid = order;
+    uidx_t* newid = order;
     int carry = 0, total = 0;
     for (int base = 0; base < n; base += POOL_THREADS) {
         const int i = base + tid;
         const int m = (i < n) ? mask[i] : 0;
         int tot;
-        const int pre = block_scan_excl(m, scan, tot);
-        if (i < n) newid[i] = (idx_t)(m ? carry + pre : 0);
+        const int pre = block_scan_excl<POOL_THREADS>(m, scan, tot);
+        if (i < n) newid[i] = (uidx_t)(m ? carry + pre : 0);
         carry += tot;
     }
     total = carry;
     __syncthreads();
     // out-adjacency of the pour DAG: every source has at most two targets
     for (int k = tid; k < U; k += POOL_THREADS) {
-        const uint32_t w = ulog[k];
-        const int s = (int)(w & 0xFFFFu);
+        const pair_t w = ulog[k];
+        const int s = pr_lo<P>(w);
         const int slot = atomicAdd(&outdeg[s], 1);
-        if (slot == 0) out0[s] = (uint16_t)(w >> 16);
-        else if (slot == 1) out1[s] = (uint16_t)(w >> 16);
+        if (slot == 0) out0[s] = (uidx_t)pr_hi<P>(w);
+        else if (slot == 1) out1[s] = (uidx_t)pr_hi<P>(w);
         else s_flag = MCNN_ST_GROUP_OVERFLOW;
     }
     if (clk) { __syncthreads(); if (tid == 0) clk[19] = clock64(); }
@@ -703,10 +759,10 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) pool_collapse_kernel(const mc
             o_gemm[4 * r + j] = g < 0 ? -1 : (int)newid[g];
             o_sides[4 * r + j] = sides[4 * i + j];
         }
-        const uint32_t w = evp[i];
-        int v0 = (int)(w & 0xFFFFu), v1 = (int)(w >> 16);
-        while (rep[v0] != v0) v0 = rep[v0];
-        while (rep[v1] != v1) v1 = rep[v1];
+        const pair_t w = evp[i];
+        int v0 = pr_lo<P>(w), v1 = pr_hi<P>(w);
+        while ((int)rep[v0] != v0) v0 = (int)rep[v0];
+        while ((int)rep[v1] != v1) v1 = (int)rep[v1];
         g_edges[2 * r] = v0;
         g_edges[2 * r + 1] = v1;
     }
@@ -722,23 +778,23 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) pool_collapse_kernel(const mc
     for (int base = 0; base < V; base += POOL_THREADS) {
         const int v = base + tid;
         int len = 0;
-        const bool root = (v < V) && (rep[v] == v);
+        const bool root = (v < V) && ((int)rep[v] == v);
         if (root)
-            for (unsigned s = (unsigned)v; s != NIL16; s = (unsigned short)slab_next[s]) {
+            for (unsigned s = (unsigned)v; s != P::NIL; s = (unsigned)slab_next[s]) {
                 const int start = slab_start[s], sl = slab_len[s];
-                for (int i = 0; i < sl; ++i) len += (ve[start + i] != VE_TOMB);
+                for (int i = 0; i < sl; ++i) len += (ve[start + i] != P::NIL);
             }
         int tot;
-        const int pre = block_scan_excl(len, scan, tot);
+        const int pre = block_scan_excl<POOL_THREADS>(len, scan, tot);
         if (v < V) {
             int pos = carry + pre;
             g_ve_ptr[v] = pos;
             if (root)
-                for (unsigned s = (unsigned)v; s != NIL16; s = (unsigned short)slab_next[s]) {
+                for (unsigned s = (unsigned)v; s != P::NIL; s = (unsigned)slab_next[s]) {
                     const int start = slab_start[s], sl = slab_len[s];
                     for (int i = 0; i < sl; ++i) {
                         const unsigned x = ve[start + i];
-                        if (x != VE_TOMB) g_ve_idx[pos++] = newid[x];
+                        if (x != P::NIL) g_ve_idx[pos++] = newid[x];
                     }
                 }
         }
@@ -750,9 +806,9 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) pool_collapse_kernel(const mc
     // E4: MeshUnion.  (a) occurrences = number of paths starting at each edge:  occ[s] = 1 + sum over the pours s -> t of
     // occ[t].  A target is alive when it is poured into, so the pours form a DAG; sweeping all edges in parallel until
     // nothing changes reaches its unique fixed point after (depth + 1) rounds.
-    uint16_t* cpool = reinterpret_cast<uint16_t*>(smem + L.gemm);           // u16[3n] column members, allocated by cursor
-    uint16_t* coff = cpool + 3 * n;                                          // u16[n]
-    uint16_t* rpool = reinterpret_cast<uint16_t*>(smem + L.evp);            // u16[<= 4n]: rows at their final CSR offsets
+    uidx_t* cpool = reinterpret_cast<uidx_t*>(smem + L.gemm);               // [3n] column members, allocated by cursor
+    uidx_t* coff = cpool + 3 * n;                                            // [n]
+    uidx_t* rpool = reinterpret_cast<uidx_t*>(smem + L.evp);                // [<= 3n]: rows at their final CSR offsets
     int* collen = reinterpret_cast<int*>(smem + L.ve);                      // int32[n]; the ve slabs were exported in E3
     const int pool_cap = min(a.nnz_cap, 3 * n);
     for (int round = 0; round <= n; ++round) {
@@ -769,7 +825,7 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) pool_collapse_kernel(const mc
     if (clk) { __syncthreads(); if (tid == 0) clk[22] = clock64(); }
     // (b) the CSC column of every old edge: a survivor sits in its own row; a dead edge is walked forward through the DAG
     // to the surviving rows that contain it.  Dead edges are compacted first so that every thread gets at most a few.
-    uint16_t* deadlist = reinterpret_cast<uint16_t*>(smem + L.ulog);        // u16[n]; the log is consumed
+    uidx_t* deadlist = reinterpret_cast<uidx_t*>(smem + L.ulog);            // [n]; the log is consumed
     for (int j = tid; j < n; j += POOL_THREADS) {
         if (mask[j]) {
             const int nr = newid[j];
@@ -777,22 +833,22 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) pool_collapse_kernel(const mc
             if (nr < T) rn = 1;
             const int off = atomicAdd(&s_cursor, rn);
             collen[j] = rn;
-            coff[j] = (uint16_t)min(off, 0xFFFF);
-            if (rn && off + rn <= pool_cap) { cpool[off] = (uint16_t)nr; atomicAdd(&rowlen[nr], 1); }
+            coff[j] = (uidx_t)min((unsigned)off, P::NIL);
+            if (rn && off + rn <= pool_cap) { cpool[off] = (uidx_t)nr; atomicAdd(&rowlen[nr], 1); }
         } else {
-            deadlist[atomicAdd(&s_ndead, 1)] = (uint16_t)j;
+            deadlist[atomicAdd(&s_ndead, 1)] = (uidx_t)j;
         }
     }
     __syncthreads();
     {
-        uint16_t q[POOL_BFS_CAP], r[POOL_BFS_CAP];
+        uidx_t q[POOL_BFS_CAP], r[POOL_BFS_CAP];
         const int ndead = s_ndead;
         for (int di = tid; di < ndead; di += POOL_THREADS) {
             const int j = deadlist[di];
             int rn = 0;
             {
                 int qn = 1;
-                q[0] = (uint16_t)j;
+                q[0] = (uidx_t)j;
                 bool over = false;
                 for (int h = 0; h < qn; ++h) {
                     const int x = q[h];
@@ -804,17 +860,17 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) pool_collapse_kernel(const mc
                             if (nr >= T) continue;
                             int k = 0;
                             while (k < rn && r[k] != nr) ++k;
-                            if (k == rn) { if (rn < POOL_BFS_CAP) r[rn++] = (uint16_t)nr; else over = true; }
+                            if (k == rn) { if (rn < POOL_BFS_CAP) r[rn++] = (uidx_t)nr; else over = true; }
                         } else {
                             int k = 0;
                             while (k < qn && q[k] != t) ++k;
-                            if (k == qn) { if (qn < POOL_BFS_CAP) q[qn++] = (uint16_t)t; else over = true; }
+                            if (k == qn) { if (qn < POOL_BFS_CAP) q[qn++] = (uidx_t)t; else over = true; }
                         }
                     }
                 }
                 if (over) s_flag = MCNN_ST_GROUP_OVERFLOW;
                 for (int p = 1; p < rn; ++p) {                       // ascending pooled id
-                    const uint16_t v = r[p];
+                    const uidx_t v = r[p];
                     int k = p;
                     while (k > 0 && r[k - 1] > v) { r[k] = r[k - 1]; --k; }
                     r[k] = v;
@@ -822,7 +878,7 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) pool_collapse_kernel(const mc
             }
             const int off = atomicAdd(&s_cursor, rn);
             collen[j] = rn;
-            coff[j] = (uint16_t)min(off, 0xFFFF);
+            coff[j] = (uidx_t)min((unsigned)off, P::NIL);
             if (off + rn <= pool_cap)
                 for (int k = 0; k < rn; ++k) { cpool[off + k] = r[k]; atomicAdd(&rowlen[r[k]], 1); }
         }
@@ -845,7 +901,7 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) pool_collapse_kernel(const mc
         const int j = base + tid;
         const int cnt = (j < n) ? collen[j] : 0;
         int tot;
-        const int pre = block_scan_excl(cnt, scan, tot);
+        const int pre = block_scan_excl<POOL_THREADS>(cnt, scan, tot);
         if (j < n) {
             o_colptr[j] = carry + pre;
             if (nnz_ok) {
@@ -863,7 +919,7 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) pool_collapse_kernel(const mc
         const int r = base + tid;
         const int len = (r < total) ? rowlen[r] : 0;
         int tot;
-        const int pre = block_scan_excl(len, scan, tot);
+        const int pre = block_scan_excl<POOL_THREADS>(len, scan, tot);
         if (r < total) {
             o_rowptr[r] = carry + pre;
             occ[r] = carry + pre;                       // occ is exported: reuse as row start ...
@@ -879,7 +935,7 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) pool_collapse_kernel(const mc
             const int cnt = ((j + 1 < n) ? collen[j + 1] : nnz) - collen[j];
             for (int k = 0; k < cnt; ++k) {
                 const int pos = atomicAdd(&rowlen[cpool[off + k]], 1);
-                rpool[pos] = (uint16_t)j;
+                rpool[pos] = (uidx_t)j;
             }
         }
         __syncthreads();
@@ -1018,7 +1074,11 @@ static int launch_segment(const float* in, float* out, const int32_t* ptr, const
 using namespace mcnn;
 
 extern "C" size_t mcnn_pool_smem_bytes(int E_in, int V, int ve_cap, int with_vs) {
-    return pool_layout(E_in, V, ve_cap, with_vs != 0).total + 64;
+    return pool_layout<Narrow>(E_in, V, ve_cap, with_vs != 0).total + 64;
+}
+
+extern "C" size_t mcnn_pool_workspace_bytes(int E_in, int V, int ve_cap, int with_vs) {
+    return align_up(pool_layout<Wide>(E_in, V, ve_cap, with_vs != 0).total + 64, 256);
 }
 
 extern "C" size_t mcnn_pool_smem_limit(void) { return 227 * 1024; }
@@ -1035,17 +1095,23 @@ extern "C" int mcnn_pool_collapse(const mcnn_pool_args* a, void* stream) {
         !a->norms || !a->edges || !a->ve_ptr || !a->ve_idx || !a->v_mask || !a->gemm_out || !a->sides_out ||
         !a->ec_out || !a->grp_rowptr || !a->grp_cols || !a->grp_colptr || !a->grp_rows || !a->occ || !a->status)
         return MCNN_E_BADARG;
-    if (a->E_in > 10900 || a->V > 32767 || a->ve_cap > 65535) return MCNN_E_TOO_LARGE;      // 16-bit ids in shared memory
     if (a->ve_cap < 2 * a->E_in) return MCNN_E_BADARG;                                        // the column lengths reuse the ve slabs
-    const size_t smem = pool_layout(a->E_in, a->V, a->ve_cap, a->vs != nullptr).total;
-    if (smem > mcnn_pool_smem_limit()) return MCNN_E_TOO_LARGE;
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(pool_collapse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) { g_last_error = e; return MCNN_E_CUDA; }
-        configured = smem;
+    const size_t smem = pool_layout<Narrow>(a->E_in, a->V, a->ve_cap, a->vs != nullptr).total;
+    const bool narrow_ok = a->E_in <= 10900 && a->V <= 32767 && a->ve_cap <= 65535 && smem <= mcnn_pool_smem_limit();   // 16-bit ids on chip
+    if (narrow_ok && !(a->workspace != nullptr && a->force_workspace)) {
+        static size_t configured = 0;
+        if (smem > configured) {
+            cudaError_t e = cudaFuncSetAttribute(pool_collapse_kernel<Narrow>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) { g_last_error = e; return MCNN_E_CUDA; }
+            configured = smem;
+        }
+        pool_collapse_kernel<Narrow><<<a->B, Narrow::THREADS, smem, (cudaStream_t)stream>>>(*a);
+        return after_launch();
     }
-    pool_collapse_kernel<<<a->B, POOL_THREADS, smem, (cudaStream_t)stream>>>(*a);
+    // large meshes: the same algorithm with 32-bit ids on a global-memory workspace (one slice per mesh)
+    if (a->workspace == nullptr) return MCNN_E_TOO_LARGE;
+    if ((size_t)a->workspace_stride < mcnn_pool_workspace_bytes(a->E_in, a->V, a->ve_cap, a->vs != nullptr)) return MCNN_E_BADARG;
+    pool_collapse_kernel<Wide><<<a->B, Wide::THREADS, 0, (cudaStream_t)stream>>>(*a);
     return after_launch();
 }
 

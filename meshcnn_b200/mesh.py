@@ -13,6 +13,8 @@ B200-first design: the topology of the whole batch lives in HBM as flat arrays (
 blob); MeshPool rewrites it on the device and the host attributes become lazy mirrors that are downloaded only
 when host code actually reads them (``Mesh.gemm_edges`` etc. are properties).
 """
+import os
+
 import numpy as np
 import torch
 
@@ -146,6 +148,8 @@ class MeshBatch:
         self._pristine = None
         self.keep_logs = False
         self.keep_clocks = False
+        self.force_wide = os.environ.get('MESHCNN_B200_POOL_WIDE', '0') == '1'    # tests: large-mesh variant on small meshes
+        self._pool_ws = None
 
     def pack(self, meshes, hs=None):
         """Pack the topology of `meshes` into the pinned staging buffer (one blob); returns it.  No device work."""
@@ -258,9 +262,13 @@ class MeshBatch:
         lv = self.levels[self.cur]
         B, E_in, dev = self.B, lv.E, self.device
         need = L.mcnn_pool_smem_bytes(E_in, self.V, self.ve_cap, 1 if self.with_vs else 0)
-        if need > L.mcnn_pool_smem_limit():
-            raise PoolError('mesh level with %d edges / %d vertices needs %d bytes of collapse state; the on-chip '
-                            'limit is %d' % (E_in, self.V, need, L.mcnn_pool_smem_limit()))
+        # meshes whose collapse state does not fit on chip run the same kernel on a global-memory workspace (32-bit ids)
+        wide = self.force_wide or need > L.mcnn_pool_smem_limit() or E_in > 10900 or self.V > 32767 or self.ve_cap > 65535
+        ws_stride = 0
+        if wide:
+            ws_stride = L.mcnn_pool_workspace_bytes(E_in, self.V, self.ve_cap, 1 if self.with_vs else 0)
+            if self._pool_ws is None or self._pool_ws.numel() < B * ws_stride:
+                self._pool_ws = torch.empty(B * ws_stride, dtype=torch.uint8, device=dev)
         nnz_cap = 3 * E_in
         ints = torch.empty(B * (T * 4 + 1 + (T + 1) + (E_in + 1) + 2 * nnz_cap + 1), dtype=torch.int32, device=dev)
         o = 0
@@ -296,6 +304,8 @@ class MeshBatch:
         a.gemm_out, a.sides_out, a.ec_out = gemm_out.data_ptr(), sides_out.data_ptr(), ec_out.data_ptr()
         a.grp_rowptr, a.grp_cols, a.grp_colptr, a.grp_rows = rowptr.data_ptr(), cols.data_ptr(), colptr.data_ptr(), rows.data_ptr()
         a.occ, a.status = occ.data_ptr(), status.data_ptr()
+        if wide:
+            a.workspace, a.workspace_stride, a.force_workspace = self._pool_ws.data_ptr(), ws_stride, 1
         if self.keep_logs:
             cap = E_in
             lg = {'npops': torch.zeros(B, dtype=torch.int32, device=dev),

@@ -31,7 +31,7 @@ def test_header_symbols_all_bound_and_exported():
 
 def test_pool_args_struct_matches_header_size():
     # 8 int32 + 4 ptr + (ptr, 2 int32) + 4 ptr + 3 ptr + 6 ptr + 6 ptr on LP64
-    assert ctypes.sizeof(_lib.PoolArgs) == 8 * 4 + 4 * 8 + 8 + 8 + 4 * 8 + 3 * 8 + 6 * 8 + 7 * 8
+    assert ctypes.sizeof(_lib.PoolArgs) == 8 * 4 + 4 * 8 + 8 + 8 + 4 * 8 + 3 * 8 + 6 * 8 + 7 * 8 + 3 * 8
 
 
 def test_smem_budget_queries():
