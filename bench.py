@@ -33,6 +33,10 @@ CONFIGS = {
     'humanseg': dict(arch='meshunet', ncf=[32, 64, 128, 256], pool_res=[1800, 1350, 600], E=2280, B=12, nclasses=8,
                      resblocks=3, lr=1e-3, mesh=('torus', dict(m=20, n=38)), mesh2=('torus', dict(m=20, n=38))),
     # configs[3]; scripts/coseg_seg/train.sh
+    # configs[4]: MedMeshCNN-scale meshes (the reference cannot run them: its MeshUnion is a dense n x n matrix = 115 GB);
+    # torus(238 x 238) = 169 932 edges padded to 170 000, one mesh per GPU, suggested deep pool chain
+    'large': dict(arch='meshunet', ncf=[32, 64, 128, 256], pool_res=[128000, 96000, 48000], E=170000, B=1, nclasses=8,
+                  resblocks=3, lr=1e-3, mesh=('torus', dict(m=238, n=238)), mesh2=('torus', dict(m=238, n=238)), dense=False),
     'coseg': dict(arch='meshunet', ncf=[32, 64, 128, 256], pool_res=[1800, 1350, 600], E=2280, B=32, nclasses=4,
                   resblocks=3, lr=1e-3, mesh=('torus', dict(m=20, n=38)), mesh2=('torus', dict(m=20, n=38))),
 }
@@ -81,10 +85,10 @@ def build_net(cfg, impl):
         from meshcnn_b200.networks import init_weights
         if cfg['arch'] == 'mconvnet':
             net = ON.OMeshConvNet(functools.partial(torch.nn.GroupNorm, cfg['groups']), 5, cfg['ncf'], cfg['nclasses'],
-                                  cfg['E'], cfg['pool_res'], cfg['fc_n'], cfg['resblocks'], dense=True)
+                                  cfg['E'], cfg['pool_res'], cfg['fc_n'], cfg['resblocks'], dense=cfg.get('dense', True))
         else:
             net = ON.OMeshEncoderDecoder([cfg['E']] + cfg['pool_res'], [5] + cfg['ncf'], cfg['ncf'][::-1] + [cfg['nclasses']],
-                                         blocks=cfg['resblocks'], dense=True)
+                                         blocks=cfg['resblocks'], dense=cfg.get('dense', True))
         init_weights(net, 'normal', 0.02)
     return net
 
