@@ -22,6 +22,7 @@ namespace mcnn {
 // debug knobs for bottleneck attribution (tools/tc_knobs.py): bit 0 = producers skip global loads, bit 1 = MMA warp skips
 // the tcgen05.mma issue, bit 2 = producers skip the st.shared.  0 in normal operation.
 __device__ int g_tc_debug = 0;
+static int g_tc_force_ntile = 0;          // host side: 0 = heuristic
 
 constexpr int TC_M = 128;
 constexpr int TC_PRODUCER_WARPS = 8;
@@ -703,7 +704,9 @@ __global__ void colsum_part_kernel(const float* __restrict__ dout, float* __rest
 
 static int bw_splits(int M, int Cin, int Cout, int* rows_per_split) {
     const int tiles = ceil_div(Cout, 128) * (Cin / 32);
-    int S = ceil_div(296, tiles);
+    // one CTA per SM (222 KB of shared memory each): fill exactly one wave of the 148 SMs -- a 149th CTA would cost a
+    // whole second round
+    int S = 148 / tiles;
     const int maxS = max(1, M / 256);
     if (S > maxS) S = maxS;
     if (S < 1) S = 1;
@@ -730,9 +733,11 @@ extern "C" int mcnn_meshconv_fwd_tc(const float* x, const int32_t* gemm, const i
     int rc = after_launch();
     if (rc) return rc;
     const int mtiles = ceil_div(B * E, TC_M);
+    int nt = (Cout % 256 == 0) ? 256 : ((Cout % 128 == 0) ? 128 : 64);
     (void)mtiles;
-    if (Cout % 256 == 0) return launch_fwd_tc<256>(x, gemm, ec, wt_ws, bias, out, B, E, Cin, Cout, st);
-    if (Cout % 128 == 0) return launch_fwd_tc<128>(x, gemm, ec, wt_ws, bias, out, B, E, Cin, Cout, st);
+    if (g_tc_force_ntile && Cout % g_tc_force_ntile == 0) nt = g_tc_force_ntile;
+    if (nt == 256) return launch_fwd_tc<256>(x, gemm, ec, wt_ws, bias, out, B, E, Cin, Cout, st);
+    if (nt == 128) return launch_fwd_tc<128>(x, gemm, ec, wt_ws, bias, out, B, E, Cin, Cout, st);
     return launch_fwd_tc<64>(x, gemm, ec, wt_ws, bias, out, B, E, Cin, Cout, st);
 }
 
@@ -799,6 +804,11 @@ extern "C" int mcnn_meshconv_bwd_weight_tc(const float* dout, const float* x, co
     return rc;
 }
 
+
+extern "C" int mcnn_debug_set_tc_ntile(int ntile) {
+    g_tc_force_ntile = (ntile == 64 || ntile == 128 || ntile == 256) ? ntile : 0;
+    return MCNN_OK;
+}
 
 extern "C" int mcnn_debug_set_tc(int flags) {
     cudaError_t e = cudaMemcpyToSymbol(g_tc_debug, &flags, sizeof(int));

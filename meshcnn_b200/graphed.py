@@ -53,6 +53,8 @@ class GraphedTrainStep:
             self.batch.snapshot()
         self.h2d_bytes = self.blob_host.numel() + self.x_host.numel() * 4 + self.y_host.numel() * self.y_host.element_size()
         self.loss = None
+        self.loss_host = torch.zeros((), dtype=torch.float32).pin_memory()   # the step's result, copied out by the graph itself
+        self.done = torch.cuda.Event()
         self.graph = None
         self._capture(warmup)
 
@@ -74,6 +76,7 @@ class GraphedTrainStep:
         loss.backward()
         self.reducer.allreduce()
         self.opt.step_state()
+        self.loss_host.copy_(loss.detach(), non_blocking=True)
         return loss
 
     def _capture(self, warmup):
@@ -101,11 +104,43 @@ class GraphedTrainStep:
         """Replay the captured step; returns the (device) loss tensor of the graph's static output."""
         self.opt.sync_lr()
         self.graph.replay()
+        self.done.record()
         self.batch.version += 1                     # host mirrors of the meshes refresh lazily from the new state
         return self.loss
+
+    def result(self):
+        """Loss of the most recent run() as a Python float; waits for THAT replay only (later work keeps running)."""
+        self.done.synchronize()
+        return float(self.loss_host)
 
     def __call__(self, meshes, x, y):
         if self.source != 'host':
             raise RuntimeError("a source='device' step replays its resident batch: call run()")
         self.stage(meshes, x, y)
         return self.run()
+
+
+class PipelinedTrainStep:
+    """Two GraphedTrainSteps over the same network / optimiser with their own staging buffers: while the GPU replays step k
+    from slot A, the host packs the meshes of step k+1 into slot B.  ``submit`` returns the slot; ``slot.result()`` is the
+    loss of that step (one event wait, no device-wide synchronisation)."""
+
+    def __init__(self, net, criterion, reducer, optimizer, meshes, x, y, E, **kw):
+        self.slots = [GraphedTrainStep(net, criterion, reducer, optimizer, meshes, x, y, E, source='host', **kw)]
+        self.slots.append(GraphedTrainStep(net, criterion, reducer, optimizer, self._detached(meshes), x, y, E, source='host', **kw))
+        self.k = 0
+        self.h2d_bytes = self.slots[0].h2d_bytes
+
+    @staticmethod
+    def _detached(meshes):
+        for m in meshes:
+            m._batch = None
+        return meshes
+
+    def submit(self, meshes, x, y):
+        slot = self.slots[self.k & 1]
+        self.k += 1
+        slot.done.synchronize()                     # the replay that last read this slot's staging buffers has finished
+        slot.stage(meshes, x, y)
+        slot.run()
+        return slot
