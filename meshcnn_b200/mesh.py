@@ -306,6 +306,10 @@ class MeshBatch:
         a.occ, a.status = occ.data_ptr(), status.data_ptr()
         if wide:
             a.workspace, a.workspace_stride, a.force_workspace = self._pool_ws.data_ptr(), ws_stride, 1
+        exporting = [i for i, m in enumerate(self.meshes) if m.export_folder]
+        if exporting and not self.keep_logs:
+            rec.edge_mask = torch.zeros(B, E_in, dtype=torch.int32, device=dev)
+            a.edge_mask_out = rec.edge_mask.data_ptr()
         if self.keep_logs:
             cap = E_in
             lg = {'npops': torch.zeros(B, dtype=torch.int32, device=dev),
@@ -335,6 +339,15 @@ class MeshBatch:
         self.version += 1
         for m in self.meshes:
             m.pool_count += 1
+        for i in exporting:                              # Mesh.clean ends with export() (mesh.py:71): test / visualisation
+            m = self.meshes[i]                           # runs only -- this synchronises and downloads the level
+            if m.history_data is not None and 'edges_mask' in m.history_data:
+                alive = m.history_data['edges_mask'][-1]
+                keep = rec.edge_mask[i, :int(alive.sum())].cpu().numpy().astype(bool)
+                idx = np.nonzero(alive)[0]
+                alive[idx[~keep]] = False
+                m.history_data['edges_mask'].append(alive.copy())
+            m.export()
         return rec
 
     def unroll(self):
@@ -409,6 +422,7 @@ class Mesh:
         self._batch, self._bi, self._seen = None, -1, -1
         if hold_history:
             self.init_history()
+        self.export()                                    # mesh.py:21 (a no-op without an export folder)
 
     # ---- device link -------------------------------------------------------------------------------------
     def _attach(self, batch, i):
@@ -452,10 +466,84 @@ class Mesh:
 
     def init_history(self):                          # mesh.py:151-162 (the unpool-relevant part lives on the device)
         self.history_data = {'groups': [], 'gemm_edges': [self._h['gemm_edges'].copy()], 'occurrences': [],
-                             'edges_count': [self._h['edges_count']]}
+                             'edges_count': [self._h['edges_count']],
+                             # survivors of every pool as a mask over the ORIGINAL edge ids (export_segments)
+                             'edges_mask': [np.ones(self._h['edges_count'], dtype=bool)]}
 
+    # ---- OBJ export (mesh.py:74-124).  Host-side: the mirrored arrays are downloaded on demand. ----------
     def export(self, file=None, vcolor=None):
-        raise NotImplementedError('OBJ export (mesh.py:74-98) is outside the hot path; see DESIGN.md "out of scope"')
+        """Write the current mesh as `v` / `f` / `e` records.  With no file name: `<export_folder>/<name>_<pool_count><ext>`,
+        or nothing at all if the mesh has no export folder (mesh.py:74-80)."""
+        if file is None:
+            if not self.export_folder:
+                return
+            stem, ext = os.path.splitext(self.filename)
+            file = '%s/%s_%d%s' % (self.export_folder, stem, self.pool_count, ext)
+        v_mask = np.asarray(self.v_mask, dtype=bool)
+        vs = np.asarray(self.vs)[v_mask]
+        n = int(self.edges_count)
+        edges = np.asarray(self.edges)[:n]
+        sides = np.asarray(self.sides)[:n]
+        left = np.array(np.asarray(self.gemm_edges)[:n], dtype=np.int64)       # consumed while the faces are walked
+        renum = np.zeros(len(v_mask), dtype=np.int64)
+        renum[v_mask] = np.arange(int(v_mask.sum()))
+        faces = []
+        for e0 in range(n):
+            for start in (0, 2):
+                if left[e0, start] == -1:
+                    continue
+                ring, key, side = [], e0, start
+                for _ in range(3):                                               # walk the three edges of the face
+                    nxt = int(left[key, side])
+                    nside = int(sides[key, side])
+                    nside += 1 - 2 * (nside % 2)
+                    left[key, side] = -1
+                    left[key, side + 1 - 2 * (side % 2)] = -1
+                    key, side = nxt, nside
+                    ring.append(key)
+                face = []
+                for i in range(3):
+                    common = set(edges[ring[i]].tolist()) & set(edges[ring[(i + 1) % 3]].tolist())
+                    face.append(int(renum[next(iter(common))]))
+                faces.append(face)
+        rows = []
+        for vi, v in enumerate(vs):
+            col = ' %f %f %f' % (vcolor[vi, 0], vcolor[vi, 1], vcolor[vi, 2]) if vcolor is not None else ''
+            rows.append('v %f %f %f%s\n' % (v[0], v[1], v[2], col))
+        for f in faces[:-1]:
+            rows.append('f %d %d %d\n' % (f[0] + 1, f[1] + 1, f[2] + 1))
+        rows.append('f %d %d %d' % (faces[-1][0] + 1, faces[-1][1] + 1, faces[-1][2] + 1))
+        for a, b in edges:
+            rows.append('\ne %d %d' % (renum[a] + 1, renum[b] + 1))
+        with open(file, 'w+') as fh:
+            fh.write(''.join(rows))
+
+    def export_segments(self, segments):
+        """Append the segment id of every edge to the `e` records of the files written by export(), one file per pool
+        level; deeper levels keep the labels of the edges that survived (mesh.py:100-124)."""
+        if not self.export_folder:
+            return
+        segments = np.asarray(segments)
+        cur = segments
+        masks = self.history_data.get('edges_mask', []) if self.history_data else []
+        stem, ext = os.path.splitext(self.filename)
+        for level in range(self.pool_count + 1):
+            path = '%s/%s_%d%s' % (self.export_folder, stem, level, ext)
+            out, k = [], 0
+            with open(path) as fh:
+                for line in fh:
+                    if line[0] == 'e':
+                        out.append('%s %d' % (line.strip(), cur[k]))
+                        if k < len(cur):
+                            k += 1
+                            out.append('\n')
+                    else:
+                        out.append(line)
+            with open(path, 'w') as fh:
+                fh.write(''.join(out))
+            if level < len(masks):
+                m = np.asarray(masks[level], dtype=bool)
+                cur = segments[:len(m)][m]
 
 
 def _mirror(name):
