@@ -33,7 +33,19 @@ __device__ __forceinline__ void slab_colsums(const NormShape s, float* __restric
     const int r0 = slab * s.rows_per_slab, r1 = min(s.rows_per_block, r0 + s.rows_per_slab);
     float u[4] = {0.f, 0.f, 0.f, 0.f}, v[4] = {0.f, 0.f, 0.f, 0.f};
     if (ty < rpp) {
-        for (int r = r0 + ty; r < r1; r += rpp) {
+        int r = r0 + ty;
+        for (; r + 3 * rpp < r1; r += 4 * rpp) {          // four independent rows in flight
+            float4 a[4], b[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                fn(((size_t)blk * s.rows_per_block + r + k * rpp) * s.C + (tx << 2), tx << 2, a[k], b[k]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                u[0] += a[k].x; u[1] += a[k].y; u[2] += a[k].z; u[3] += a[k].w;
+                v[0] += b[k].x; v[1] += b[k].y; v[2] += b[k].z; v[3] += b[k].w;
+            }
+        }
+        for (; r < r1; r += rpp) {
             const size_t off = ((size_t)blk * s.rows_per_block + r) * s.C + (tx << 2);
             float4 a, b;
             fn(off, tx << 2, a, b);
@@ -103,36 +115,63 @@ __global__ void norm_finalize_kernel(const float* __restrict__ part, float* __re
     }
 }
 
+// y = post(gamma * (pre(x [+ a]) - mean) * rstd + beta [+ r]).  Same (block, row slab) decomposition as the statistics:
+// a thread owns one float4 of columns, so mean / rstd / gamma / beta are loaded once and folded into scale / shift; the
+// row loop keeps four rows in flight.
 __global__ void __launch_bounds__(NT) norm_apply_kernel(const float* __restrict__ x, const float* __restrict__ a,
                                                         const float* __restrict__ r, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, const float* __restrict__ mean,
                                                         const float* __restrict__ rstd, float* __restrict__ y, int pre_relu,
-                                                        int post_relu, NormShape s, long long total4) {
-    const long long i = (long long)blockIdx.x * NT + threadIdx.x;
-    if (i >= total4) return;
+                                                        int post_relu, NormShape s) {
     const int cq = s.C >> 2;
-    const long long row = i / cq;
-    const int c = (int)(i - row * cq) << 2;
-    const int blk = (int)(row / s.rows_per_block);
-    const size_t off = (size_t)row * s.C + c;
-    float4 z = ld4(x + off);
-    if (a != nullptr) { const float4 t = ld4(a + off); z.x += t.x; z.y += t.y; z.z += t.z; z.w += t.w; }
-    float zz[4] = {z.x, z.y, z.z, z.w};
-    float rr[4] = {0.f, 0.f, 0.f, 0.f};
-    if (r != nullptr) { const float4 t = ld4(r + off); rr[0] = t.x; rr[1] = t.y; rr[2] = t.z; rr[3] = t.w; }
+    const int rpp = NT / cq;
+    const int tx = threadIdx.x % cq, ty = threadIdx.x / cq;
+    if (ty >= rpp) return;
+    const int blk = blockIdx.x, slab = blockIdx.y;
+    const int r0 = slab * s.rows_per_slab, r1 = min(s.rows_per_block, r0 + s.rows_per_slab);
+    const int c = tx << 2;
     const int cpg = s.C / s.G;
-    float out[4];
+    float sc[4], sh[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        float v = pre_relu ? fmaxf(zz[j], 0.f) : zz[j];
         const int g = (c + j) / cpg;
         const float m = __ldg(mean + blk * s.G + g), rs = __ldg(rstd + blk * s.G + g);
-        v = (v - m) * rs;
-        if (gamma != nullptr) v = v * __ldg(gamma + c + j) + __ldg(beta + c + j);
-        v += rr[j];
-        out[j] = post_relu ? fmaxf(v, 0.f) : v;
+        const float gm = gamma != nullptr ? __ldg(gamma + c + j) : 1.f;
+        const float bt = gamma != nullptr ? __ldg(beta + c + j) : 0.f;
+        sc[j] = rs * gm;
+        sh[j] = bt - m * rs * gm;
     }
-    *reinterpret_cast<float4*>(y + off) = make_float4(out[0], out[1], out[2], out[3]);
+    const size_t base = (size_t)blk * s.rows_per_block * s.C + c;
+    auto one = [&](const float4 z4, const float4 a4, const float4 r4) {
+        float z[4] = {z4.x + a4.x, z4.y + a4.y, z4.z + a4.z, z4.w + a4.w};
+        const float rr[4] = {r4.x, r4.y, r4.z, r4.w};
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float v = pre_relu ? fmaxf(z[j], 0.f) : z[j];
+            const float w = fmaf(v, sc[j], sh[j]) + rr[j];
+            o[j] = post_relu ? fmaxf(w, 0.f) : w;
+        }
+        return make_float4(o[0], o[1], o[2], o[3]);
+    };
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    int row = r0 + ty;
+    for (; row + 3 * rpp < r1; row += 4 * rpp) {
+        float4 z[4], av[4], rv[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const size_t off = base + (size_t)(row + k * rpp) * s.C;
+            z[k] = ld4(x + off);
+            av[k] = a != nullptr ? ld4(a + off) : zero;
+            rv[k] = r != nullptr ? ld4(r + off) : zero;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) *reinterpret_cast<float4*>(y + base + (size_t)(row + k * rpp) * s.C) = one(z[k], av[k], rv[k]);
+    }
+    for (; row < r1; row += rpp) {
+        const size_t off = base + (size_t)row * s.C;
+        *reinterpret_cast<float4*>(y + off) = one(ld4(x + off), a != nullptr ? ld4(a + off) : zero, r != nullptr ? ld4(r + off) : zero);
+    }
 }
 
 // backward stage 1: per-slab column sums of (dyh, dyh * xhat), dyh = dy * [y > 0 if post_relu]
@@ -202,47 +241,69 @@ __global__ void norm_bwd_finalize_kernel(const float* __restrict__ part, const f
     }
 }
 
-// backward stage 3: dz = rstd * (gamma*dyh - s1 - xhat*s2); dx = da = dz * [z_pre > 0 if pre_relu]; dr = dyh
+// backward stage 3: dz = rstd * (gamma*dyh - s1 - xhat*s2); dx = da = dz * [z_pre > 0 if pre_relu]; dr = dyh.
+// Slab form as above: per-column constants hoisted (xhat = z*rs - m*rs), two rows in flight.
 __global__ void __launch_bounds__(NT) norm_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ y,
                                                             const float* __restrict__ x, const float* __restrict__ a,
                                                             const float* __restrict__ gamma, const float* __restrict__ mean,
                                                             const float* __restrict__ rstd, const float* __restrict__ s1,
                                                             const float* __restrict__ s2, float* __restrict__ dx,
-                                                            float* __restrict__ dr, int pre_relu, int post_relu, NormShape s,
-                                                            long long total4) {
-    const long long i = (long long)blockIdx.x * NT + threadIdx.x;
-    if (i >= total4) return;
+                                                            float* __restrict__ dr, int pre_relu, int post_relu, NormShape s) {
     const int cq = s.C >> 2;
-    const long long row = i / cq;
-    const int c = (int)(i - row * cq) << 2;
-    const int blk = (int)(row / s.rows_per_block);
-    const size_t off = (size_t)row * s.C + c;
-    float4 d4 = ld4(dy + off);
-    float d[4] = {d4.x, d4.y, d4.z, d4.w};
-    if (post_relu) {
-        const float4 yy = ld4(y + off);
-        const float yv[4] = {yy.x, yy.y, yy.z, yy.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) d[j] = yv[j] > 0.f ? d[j] : 0.f;
-    }
-    if (dr != nullptr) *reinterpret_cast<float4*>(dr + off) = make_float4(d[0], d[1], d[2], d[3]);
-    float4 z4 = ld4(x + off);
-    if (a != nullptr) { const float4 t = ld4(a + off); z4.x += t.x; z4.y += t.y; z4.z += t.z; z4.w += t.w; }
-    const float zr[4] = {z4.x, z4.y, z4.z, z4.w};
+    const int rpp = NT / cq;
+    const int tx = threadIdx.x % cq, ty = threadIdx.x / cq;
+    if (ty >= rpp) return;
+    const int blk = blockIdx.x, slab = blockIdx.y;
+    const int r0 = slab * s.rows_per_slab, r1 = min(s.rows_per_block, r0 + s.rows_per_slab);
+    const int c = tx << 2;
     const int cpg = s.C / s.G;
-    float out[4];
+    float rs[4], mrs[4], gm[4], k1[4], k2[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const int g = (c + j) / cpg;
-        const float m = __ldg(mean + blk * s.G + g), rs = __ldg(rstd + blk * s.G + g);
-        const float z = pre_relu ? fmaxf(zr[j], 0.f) : zr[j];
-        const float xh = (z - m) * rs;
-        const float gm = gamma != nullptr ? __ldg(gamma + c + j) : 1.f;
-        float dz = rs * (gm * d[j] - __ldg(s1 + blk * s.G + g) - xh * __ldg(s2 + blk * s.G + g));
-        if (pre_relu && !(zr[j] > 0.f)) dz = 0.f;
-        out[j] = dz;
+        rs[j] = __ldg(rstd + blk * s.G + g);
+        mrs[j] = __ldg(mean + blk * s.G + g) * rs[j];
+        gm[j] = gamma != nullptr ? __ldg(gamma + c + j) : 1.f;
+        k1[j] = __ldg(s1 + blk * s.G + g);
+        k2[j] = __ldg(s2 + blk * s.G + g);
     }
-    *reinterpret_cast<float4*>(dx + off) = make_float4(out[0], out[1], out[2], out[3]);
+    const size_t base = (size_t)blk * s.rows_per_block * s.C + c;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto one = [&](size_t off, const float4 d4, const float4 y4, const float4 z4, const float4 a4) {
+        float d[4] = {d4.x, d4.y, d4.z, d4.w};
+        const float yv[4] = {y4.x, y4.y, y4.z, y4.w};
+        const float zr[4] = {z4.x + a4.x, z4.y + a4.y, z4.z + a4.z, z4.w + a4.w};
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (post_relu) d[j] = yv[j] > 0.f ? d[j] : 0.f;
+            const float z = pre_relu ? fmaxf(zr[j], 0.f) : zr[j];
+            const float xh = z * rs[j] - mrs[j];
+            float dz = rs[j] * (gm[j] * d[j] - k1[j] - xh * k2[j]);
+            if (pre_relu && !(zr[j] > 0.f)) dz = 0.f;
+            o[j] = dz;
+        }
+        if (dr != nullptr) *reinterpret_cast<float4*>(dr + off) = make_float4(d[0], d[1], d[2], d[3]);
+        *reinterpret_cast<float4*>(dx + off) = make_float4(o[0], o[1], o[2], o[3]);
+    };
+    int row = r0 + ty;
+    for (; row + rpp < r1; row += 2 * rpp) {
+        float4 d[2], yy[2], z[2], av[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const size_t off = base + (size_t)(row + k * rpp) * s.C;
+            d[k] = ld4(dy + off);
+            yy[k] = post_relu ? ld4(y + off) : zero;
+            z[k] = ld4(x + off);
+            av[k] = a != nullptr ? ld4(a + off) : zero;
+        }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) one(base + (size_t)(row + k * rpp) * s.C, d[k], yy[k], z[k], av[k]);
+    }
+    for (; row < r1; row += rpp) {
+        const size_t off = base + (size_t)row * s.C;
+        one(off, ld4(dy + off), post_relu ? ld4(y + off) : zero, ld4(x + off), a != nullptr ? ld4(a + off) : zero);
+    }
 }
 
 // ---- flat Adam over contiguous parameter / gradient / moment buffers (torch.optim.Adam semantics, no amsgrad) ----------
@@ -329,8 +390,7 @@ extern "C" int mcnn_norm_fwd(const float* x, const float* a, const float* r, con
         norm_finalize_kernel<<<ceil_div(nblocks * G * 32, 256), 256, 0, st>>>(part, mean, rstd, running_mean, running_var, momentum, eps, s);
         if ((rc = after_launch())) return rc;
     }
-    const long long total4 = (long long)nblocks * rows_per_block * (C / 4);
-    norm_apply_kernel<<<(unsigned)((total4 + NT - 1) / NT), NT, 0, st>>>(x, a, r, gamma, beta, mean, rstd, y, pre_relu, post_relu, s, total4);
+    norm_apply_kernel<<<dim3(nblocks, s.slabs), NT, 0, st>>>(x, a, r, gamma, beta, mean, rstd, y, pre_relu, post_relu, s);
     return after_launch();
 }
 
@@ -349,9 +409,7 @@ extern "C" int mcnn_norm_bwd(const float* dy, const float* y, const float* x, co
     const int nfin = nblocks * G + C;
     norm_bwd_finalize_kernel<<<ceil_div(nfin * 32, 256), 256, 0, st>>>(part, gamma, s1, s2, dgamma, dbeta, s);
     if ((rc = after_launch())) return rc;
-    const long long total4 = (long long)nblocks * rows_per_block * (C / 4);
-    norm_bwd_apply_kernel<<<(unsigned)((total4 + NT - 1) / NT), NT, 0, st>>>(dy, y, x, a, gamma, mean, rstd, s1, s2, dx, dr, pre_relu,
-                                                                             post_relu, s, total4);
+    norm_bwd_apply_kernel<<<dim3(nblocks, s.slabs), NT, 0, st>>>(dy, y, x, a, gamma, mean, rstd, s1, s2, dx, dr, pre_relu, post_relu, s);
     return after_launch();
 }
 
