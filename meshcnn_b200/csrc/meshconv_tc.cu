@@ -148,7 +148,7 @@ meshconv_fwd_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ 
                 const int c = cb * 32 + (((blk - 1) & 1) << 4) + ((pt & 3) << 2);
 #pragma unroll
                 for (int it = 0; it < 2; ++it) {
-                    const int sa = srcA[it][pr], sb = srcB[it][pr];
+                    const int sa = pr ? srcA[it][1] : srcA[it][0], sb = pr ? srcB[it][1] : srcB[it][0];   // selects, not a dynamic index (local memory)
                     R.a[2 * it] = sa >= 0 ? __ldg(reinterpret_cast<const float4*>(x + (size_t)sa * Cin + c)) : zero4;
                     R.a[2 * it + 1] = sb >= 0 ? __ldg(reinterpret_cast<const float4*>(x + (size_t)sb * Cin + c)) : zero4;
                 }
