@@ -86,6 +86,8 @@ int mcnn_meshconv_fwd_tc(const float* x, const int32_t* gemm, const int32_t* ec,
 int mcnn_debug_set_tc(int flags);
 /* diagnostics only: force the N tile (64 / 128 / 256) of the tensor-core forward kernel; 0 = built-in choice */
 int mcnn_debug_set_tc_ntile(int ntile);
+/* the CTA-pair (tcgen05 cta_group::2) forward kernel for Cout % 256 == 0: on / off */
+int mcnn_debug_set_tc_pair(int on);
 
 /* dx of the above (autograd of mesh_conv.py:47-69: conv2d dgrad, abs/add backward, index_select scatter).
  *   dout [B][E][Cout]   dx [B][E][Cin]  -- must be ZERO on entry (the kernel accumulates with red.global) */

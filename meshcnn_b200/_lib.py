@@ -43,6 +43,7 @@ SIGNATURES = {
     'mcnn_meshconv_bwd_weight': (_c_int, [_c_vp] * 6 + [_c_int] * 4 + [_c_vp]),
     'mcnn_debug_set_tc': (_c_int, [_c_int]),
     'mcnn_debug_set_tc_ntile': (_c_int, [_c_int]),
+    'mcnn_debug_set_tc_pair': (_c_int, [_c_int]),
     'mcnn_meshconv_bwd_data_tc': (_c_int, [_c_vp] * 7 + [_c_int] * 4 + [_c_vp]),
     'mcnn_meshconv_bwd_weight_tc_ws': (_c_sz, [_c_int] * 4),
     'mcnn_meshconv_bwd_weight_tc': (_c_int, [_c_vp] * 7 + [_c_int] * 4 + [_c_vp]),
@@ -62,6 +63,9 @@ SIGNATURES = {
     'mcnn_unpool_bwd': (_c_int, [_c_vp] * 6 + [_c_int] * 6 + [_c_vp]),
 }
 
+# CTA-pair (tcgen05 cta_group::2) forward kernel for Cout % 256 == 0; MESHCNN_B200_TC_PAIR=0/1 overrides
+TC_PAIR_DEFAULT = int(os.environ.get('MESHCNN_B200_TC_PAIR', '0'))
+
 _ERRORS = {1: 'MCNN_E_BADARG', 2: 'MCNN_E_TOO_LARGE', 3: 'MCNN_E_CUDA'}
 _lib = None
 
@@ -79,6 +83,7 @@ def lib():
             fn = getattr(l, name)
             fn.restype = res
             fn.argtypes = args
+        l.mcnn_debug_set_tc_pair(TC_PAIR_DEFAULT)
         _lib = l
     return _lib
 

@@ -23,10 +23,17 @@ namespace mcnn {
 // the tcgen05.mma issue, bit 2 = producers skip the st.shared.  0 in normal operation.
 __device__ int g_tc_debug = 0;
 static int g_tc_force_ntile = 0;          // host side: 0 = heuristic
+static int g_tc_pair = 0;                 // host side: use the CTA-pair (cta_group::2) forward kernel for N = 256
 
 constexpr int TC_M = 128;
 constexpr int TC_PRODUCER_WARPS = 8;
 constexpr int TC_THREADS = (TC_PRODUCER_WARPS + 1) * 32;
+
+// Row / chunk of item i (0 .. 511) of a "pair" K block (two 16-channel halves per row: 4 + 4 chunks, written by two
+// separate stores).  The shared-memory pipeline serves a 16-byte-per-lane store in quarter-warps of 8 lanes; with the
+// 128-byte swizzle the 4 chunks of row r land in chunk slots {0..3} ^ (r & 7), so a quarter-warp is conflict-free iff its
+// two rows differ in bit 2: rows (r, r + 4) instead of (r, r + 1).
+__device__ __forceinline__ int pair_item_row(int i) { return ((i >> 5) << 3) + (((i >> 2) & 1) << 2) + ((i >> 3) & 3); }
 
 // weight [Cout][Cin][5] -> the B operand exactly as the tensor core wants it in shared memory, split into TF32 head and
 // remainder:  img[hi|lo][kb][Cout rows x 128 bytes, canonical K-major SWIZZLE_128B atoms], K in the permuted order above.
@@ -125,7 +132,7 @@ meshconv_fwd_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ 
         for (int it = 0; it < 4; ++it) src0[it] = nb[(pt + it * 256) >> 3][0];
 #pragma unroll
         for (int it = 0; it < 2; ++it) {
-            const int r = (pt + it * 256) >> 2;
+            const int r = pair_item_row(pt + it * 256);
             srcA[it][0] = nb[r][1]; srcB[it][0] = nb[r][3];     // pair (f1, f3)
             srcA[it][1] = nb[r][2]; srcB[it][1] = nb[r][4];     // pair (f2, f4)
         }
@@ -183,25 +190,25 @@ meshconv_fwd_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ 
                     const int item = pt + it * 256;
                     const uint32_t off = tc::sw128_off(item >> 3, item & 7);
                     tc::split4(R.a[it], hi, lo);
-                    *reinterpret_cast<float4*>(a_hi + off) = hi;
-                    *reinterpret_cast<float4*>(a_lo + off) = lo;
+                    tc::sts128(tc::smem_u32(a_hi) + off, hi);
+                    tc::sts128(tc::smem_u32(a_lo) + off, lo);
                 }
             } else {
 #pragma unroll
                 for (int it = 0; it < 2; ++it) {
                     const int item = pt + it * 256;
-                    const int r = item >> 2, q = item & 3;
+                    const int r = pair_item_row(item), q = item & 3;
                     const float4 fa = R.a[2 * it], fb = R.a[2 * it + 1];
                     const float4 sum = make_float4(fa.x + fb.x, fa.y + fb.y, fa.z + fb.z, fa.w + fb.w);
                     const float4 dif = make_float4(fabsf(fa.x - fb.x), fabsf(fa.y - fb.y), fabsf(fa.z - fb.z), fabsf(fa.w - fb.w));
                     tc::split4(sum, hi, lo);
                     uint32_t off = tc::sw128_off(r, q);
-                    *reinterpret_cast<float4*>(a_hi + off) = hi;
-                    *reinterpret_cast<float4*>(a_lo + off) = lo;
+                    tc::sts128(tc::smem_u32(a_hi) + off, hi);
+                    tc::sts128(tc::smem_u32(a_lo) + off, lo);
                     tc::split4(dif, hi, lo);
                     off = tc::sw128_off(r, q + 4);
-                    *reinterpret_cast<float4*>(a_hi + off) = hi;
-                    *reinterpret_cast<float4*>(a_lo + off) = lo;
+                    tc::sts128(tc::smem_u32(a_hi) + off, hi);
+                    tc::sts128(tc::smem_u32(a_lo) + off, lo);
                 }
             }
             tc::fence_proxy_async_smem();                                  // every writer fences its own stores ...
@@ -209,19 +216,23 @@ meshconv_fwd_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ 
             if (lane == 0) tc::mbar_arrive(full_bar + s);                  // ... then one arrival per warp
         };
         {                                                        // prefetch distance 2 (three register sets)
+            // three register sets, prefetch distance 3.  The gathers of block kb + 3 are issued right AFTER block kb has been
+            // handed over: fence.proxy.async waits for the thread's outstanding loads, so a load issued just before a
+            // store_block would put the whole L2 latency on the critical path of every K block.
             Regs R0, R1, R2;
             load_block(0, R0);
             if (num_kb > 1) load_block(1, R1);
+            if (num_kb > 2) load_block(2, R2);
             for (int kb = 0; kb < num_kb; kb += 3) {
-                if (kb + 2 < num_kb) load_block(kb + 2, R2);
                 store_block(kb, R0);
+                if (kb + 3 < num_kb) load_block(kb + 3, R0);
                 if (kb + 1 < num_kb) {
-                    if (kb + 3 < num_kb) load_block(kb + 3, R0);
                     store_block(kb + 1, R1);
+                    if (kb + 4 < num_kb) load_block(kb + 4, R1);
                 }
                 if (kb + 2 < num_kb) {
-                    if (kb + 4 < num_kb) load_block(kb + 4, R1);
                     store_block(kb + 2, R2);
+                    if (kb + 5 < num_kb) load_block(kb + 5, R2);
                 }
             }
         }
@@ -284,6 +295,255 @@ meshconv_fwd_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ 
         tc::tc_fence_after();
         tc::tmem_dealloc<N_TILE>(tmem_base);
     }
+}
+
+// =============================================================================================================
+// Forward on a CTA PAIR (tcgen05 cta_group::2): two CTAs of one cluster compute 256 edges x 256 output channels.  Each CTA
+// gathers / builds the A operand of its own 128 edges and fetches only HALF of the weight tile (128 of the 256 rows of B);
+// the pair's tensor cores share both halves.  Per SM this halves the B traffic from L2 and the B reads from shared memory
+// -- the two things that bound the single-CTA kernel at N = 256 -- and the smaller stage (64 KB) buys a third pipeline stage.
+// Hand-over: the producers of BOTH CTAs arrive on the LEADER's full barrier (remote arrive through the cluster window); the
+// leader's elected thread issues the MMAs for the pair and its commit multicasts the stage-free signal to both CTAs.
+// =============================================================================================================
+struct Tc2Smem {
+    static constexpr int A_BYTES = TC_M * 128;            // 128 rows x 32 fp32
+    static constexpr int B_BYTES = 128 * 128;              // this CTA's half of the 256-row B tile
+    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;     // 65536
+    static constexpr int STAGES = 3;
+    static constexpr int NB_OFF = STAGES * STAGE_BYTES;
+    static constexpr int BAR_OFF = NB_OFF + TC_M * 5 * 4;
+    static constexpr int TOTAL = BAR_OFF + 16 * 8 + 16 + 1024;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+meshconv_fwd_tc2_kernel(const float* __restrict__ x, const int32_t* __restrict__ gemm, const int32_t* __restrict__ ec,
+                        const float* __restrict__ wt, const float* __restrict__ bias, float* __restrict__ out,
+                        int B, int E, int Cin, int Cout) {
+    using S = Tc2Smem;
+    constexpr int N_TILE = 256;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    int (*nb)[5] = reinterpret_cast<int (*)[5]>(smem + S::NB_OFF);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);      // used in the leader: 16 warp arrivals + its own B bytes
+    uint64_t* empty_bar = full_bar + S::STAGES;                                // in each CTA: one multicast commit
+    uint64_t* bfull_bar = empty_bar + S::STAGES;                               // peer only: its half of B has landed
+    uint64_t* accum_bar = bfull_bar + S::STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = tc::cluster_ctarank();
+    const int M = B * E;
+    const int m0 = blockIdx.x * TC_M, n0 = blockIdx.y * N_TILE;
+    const int K = 5 * Cin;
+    const int num_kb = K >> 5;
+
+    for (int i = tid; i < TC_M * 5; i += TC_THREADS) {
+        const int r = i / 5, k = i - r * 5;
+        const int m = m0 + r;
+        int idx = -1;
+        if (m < M) {
+            const int b = m / E, e = m - b * E;
+            if (e >= __ldg(ec + b)) idx = b * E;                                  // padded slot -> edge 0
+            else if (k == 0) idx = m;
+            else { const int g = __ldg(gemm + (size_t)m * 4 + (k - 1)); idx = g < 0 ? -1 : b * E + g; }
+        }
+        nb[r][k] = idx;
+    }
+    if (warp == TC_PRODUCER_WARPS) {
+        if (lane == 0) {
+            for (int s = 0; s < S::STAGES; ++s) {
+                tc::mbar_init(full_bar + s, 2 * TC_PRODUCER_WARPS);
+                tc::mbar_init(empty_bar + s, 1);
+                tc::mbar_init(bfull_bar + s, 1);
+            }
+            tc::mbar_init(accum_bar, 1);
+            tc::fence_barrier_init();
+        }
+        __syncwarp();
+        tc::tmem_alloc_pair<N_TILE>(tmem_slot);
+    }
+    tc::tc_fence_before();
+    tc::cluster_sync_all();                                  // both CTAs: barriers initialised, TMEM allocated
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < TC_PRODUCER_WARPS) {
+        const int pt = tid;
+        int src0[4], srcA[2][2], srcB[2][2];
+#pragma unroll
+        for (int it = 0; it < 4; ++it) src0[it] = nb[(pt + it * 256) >> 3][0];
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+            const int r = pair_item_row(pt + it * 256);
+            srcA[it][0] = nb[r][1]; srcB[it][0] = nb[r][3];
+            srcA[it][1] = nb[r][2]; srcB[it][1] = nb[r][4];
+        }
+        struct Regs { float4 a[4]; };
+        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        auto load_block = [&](int kb, Regs& R) {
+            const int cb = kb / 5, blk = kb - cb * 5;
+            if (blk == 0) {
+                const int c = cb * 32 + ((pt & 7) << 2);
+#pragma unroll
+                for (int it = 0; it < 4; ++it)
+                    R.a[it] = src0[it] >= 0 ? __ldg(reinterpret_cast<const float4*>(x + (size_t)src0[it] * Cin + c)) : zero4;
+            } else {
+                const int pr = (blk <= 2) ? 0 : 1;
+                const int c = cb * 32 + (((blk - 1) & 1) << 4) + ((pt & 3) << 2);
+#pragma unroll
+                for (int it = 0; it < 2; ++it) {
+                    const int sa = pr ? srcA[it][1] : srcA[it][0], sb = pr ? srcB[it][1] : srcB[it][0];
+                    R.a[2 * it] = sa >= 0 ? __ldg(reinterpret_cast<const float4*>(x + (size_t)sa * Cin + c)) : zero4;
+                    R.a[2 * it + 1] = sb >= 0 ? __ldg(reinterpret_cast<const float4*>(x + (size_t)sb * Cin + c)) : zero4;
+                }
+            }
+        };
+        auto store_block = [&](int kb, const Regs& R) {
+            const int s = kb % S::STAGES;
+            const uint32_t ph = (kb / S::STAGES) & 1;
+            if (lane == 0) tc::mbar_wait_cluster(empty_bar + s, ph ^ 1);
+            __syncwarp();
+            unsigned char* a_hi = smem + s * S::STAGE_BYTES;
+            unsigned char* a_lo = a_hi + S::A_BYTES;
+            unsigned char* b_hi = a_lo + S::A_BYTES;
+            unsigned char* b_lo = b_hi + S::B_BYTES;
+            const int blk = kb % 5;
+            float4 hi, lo;
+            if (tid == 0) {                                               // this CTA's 128 rows of the B tile
+                const float* src = wt + ((size_t)kb * Cout + n0 + rank * 128) * 32;
+                uint64_t* bbar = rank == 0 ? full_bar + s : bfull_bar + s;
+                if (rank == 0) tc::mbar_expect_tx(bbar, 2 * S::B_BYTES);
+                else tc::mbar_arrive_expect_tx(bbar, 2 * S::B_BYTES);
+                tc::bulk_g2s(b_hi, src, S::B_BYTES, bbar);
+                tc::bulk_g2s(b_lo, src + (size_t)Cout * K, S::B_BYTES, bbar);
+            }
+            if (blk == 0) {
+#pragma unroll
+                for (int it = 0; it < 4; ++it) {
+                    const int item = pt + it * 256;
+                    const uint32_t off = tc::sw128_off(item >> 3, item & 7);
+                    tc::split4(R.a[it], hi, lo);
+                    tc::sts128(tc::smem_u32(a_hi) + off, hi);
+                    tc::sts128(tc::smem_u32(a_lo) + off, lo);
+                }
+            } else {
+#pragma unroll
+                for (int it = 0; it < 2; ++it) {
+                    const int item = pt + it * 256;
+                    const int r = pair_item_row(item), q = item & 3;
+                    const float4 fa = R.a[2 * it], fb = R.a[2 * it + 1];
+                    const float4 sum = make_float4(fa.x + fb.x, fa.y + fb.y, fa.z + fb.z, fa.w + fb.w);
+                    const float4 dif = make_float4(fabsf(fa.x - fb.x), fabsf(fa.y - fb.y), fabsf(fa.z - fb.z), fabsf(fa.w - fb.w));
+                    tc::split4(sum, hi, lo);
+                    uint32_t off = tc::sw128_off(r, q);
+                    tc::sts128(tc::smem_u32(a_hi) + off, hi);
+                    tc::sts128(tc::smem_u32(a_lo) + off, lo);
+                    tc::split4(dif, hi, lo);
+                    off = tc::sw128_off(r, q + 4);
+                    tc::sts128(tc::smem_u32(a_hi) + off, hi);
+                    tc::sts128(tc::smem_u32(a_lo) + off, lo);
+                }
+            }
+            tc::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                if (rank != 0 && warp == 0) tc::mbar_wait(bfull_bar + s, ph);   // the peer vouches for its half of B as well
+                tc::mbar_arrive_leader(full_bar + s);
+            }
+        };
+        {
+            // three register sets, prefetch distance 3.  The gathers of block kb + 3 are issued right AFTER block kb has been
+            // handed over: fence.proxy.async waits for the thread's outstanding loads, so a load issued just before a
+            // store_block would put the whole L2 latency on the critical path of every K block.
+            Regs R0, R1, R2;
+            load_block(0, R0);
+            if (num_kb > 1) load_block(1, R1);
+            if (num_kb > 2) load_block(2, R2);
+            for (int kb = 0; kb < num_kb; kb += 3) {
+                store_block(kb, R0);
+                if (kb + 3 < num_kb) load_block(kb + 3, R0);
+                if (kb + 1 < num_kb) {
+                    store_block(kb + 1, R1);
+                    if (kb + 4 < num_kb) load_block(kb + 4, R1);
+                }
+                if (kb + 2 < num_kb) {
+                    store_block(kb + 2, R2);
+                    if (kb + 5 < num_kb) load_block(kb + 5, R2);
+                }
+            }
+        }
+        // ---- epilogue: this CTA's 128 rows of the accumulator ----
+        tc::mbar_wait_cluster(accum_bar, 0);
+        tc::tc_fence_after();
+        const int lane_grp = warp & 3;
+        const int r = lane_grp * 32 + lane;
+        const int m = m0 + r;
+        constexpr int COLS_PER_WARP = N_TILE / 2;
+        const int col0 = (warp >> 2) * COLS_PER_WARP;
+#pragma unroll 1
+        for (int cc = 0; cc < COLS_PER_WARP; cc += 32) {
+            float v[32];
+            tc::tmem_ld32(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(col0 + cc), v);
+            if (m < M) {
+                const int n = n0 + col0 + cc;
+                float* o = out + (size_t)m * Cout + n;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (bias != nullptr) bv = __ldg(reinterpret_cast<const float4*>(bias + n + j));
+                    *reinterpret_cast<float4*>(o + j) = make_float4(v[j] + bv.x, v[j + 1] + bv.y, v[j + 2] + bv.z, v[j + 3] + bv.w);
+                }
+            }
+        }
+        tc::tc_fence_before();
+    } else if (rank == 0) {
+        // ======================================== MMA issuer (leader CTA only) ========================================
+        constexpr uint32_t idesc = tc::make_idesc_tf32_pair(N_TILE);
+        for (int kb = 0; kb < num_kb; ++kb) {
+            const int s = kb % S::STAGES;
+            const uint32_t ph = (kb / S::STAGES) & 1;
+            tc::mbar_wait_cluster(full_bar + s, ph);
+            tc::tc_fence_after();
+            if (tc::elect_one()) {
+                const uint32_t a_hi = tc::smem_u32(smem + s * S::STAGE_BYTES);
+                const uint32_t a_lo = a_hi + S::A_BYTES;
+                const uint32_t b_hi = a_lo + S::A_BYTES;
+                const uint32_t b_lo = b_hi + S::B_BYTES;
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    const uint64_t dah = tc::make_desc_sw128(a_hi + kk * 32), dal = tc::make_desc_sw128(a_lo + kk * 32);
+                    const uint64_t dbh = tc::make_desc_sw128(b_hi + kk * 32), dbl = tc::make_desc_sw128(b_lo + kk * 32);
+                    tc::mma_tf32_pair(tmem_base, dah, dbh, idesc, (kb | kk) != 0);
+                    tc::mma_tf32_pair(tmem_base, dah, dbl, idesc, 1);
+                    tc::mma_tf32_pair(tmem_base, dal, dbh, idesc, 1);
+                }
+                tc::mma_commit_pair(empty_bar + s);
+                if (kb == num_kb - 1) tc::mma_commit_pair(accum_bar);
+            }
+            __syncwarp();
+        }
+        tc::tc_fence_before();
+    }
+    tc::cluster_sync_all();                                  // both epilogues done before the pair's TMEM goes away
+    if (warp == TC_PRODUCER_WARPS) {
+        tc::tc_fence_after();
+        tc::tmem_dealloc_pair<N_TILE>(tmem_base);
+    }
+}
+
+static int launch_fwd_tc2(const float* x, const int32_t* gemm, const int32_t* ec, const float* wt, const float* bias,
+                          float* out, int B, int E, int Cin, int Cout, cudaStream_t st) {
+    using S = Tc2Smem;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(meshconv_fwd_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+        if (e != cudaSuccess) { g_last_error = e; return MCNN_E_CUDA; }
+        configured = true;
+    }
+    const int mtiles = ceil_div(B * E, TC_M);
+    dim3 grid(2 * ceil_div(mtiles, 2), Cout / 256);          // whole CTA pairs; a surplus CTA works on rows >= M (all zero)
+    meshconv_fwd_tc2_kernel<<<grid, TC_THREADS, S::TOTAL, st>>>(x, gemm, ec, wt, bias, out, B, E, Cin, Cout);
+    return after_launch();
 }
 
 template <int N_TILE>
@@ -400,8 +660,8 @@ meshconv_bwd_data_tc_kernel(const float* __restrict__ dout, const float* __restr
                 float4 hi, lo;
                 tc::split4(v, hi, lo);
                 const uint32_t off = tc::sw128_off(r, q);
-                *reinterpret_cast<float4*>(a_hi + off) = hi;
-                *reinterpret_cast<float4*>(a_lo + off) = lo;
+                tc::sts128(tc::smem_u32(a_hi) + off, hi);
+                tc::sts128(tc::smem_u32(a_lo) + off, lo);
             }
             if (tid == 0) {                                               // B tile: two bulk copies of the pre-built image
                 tc::mbar_expect_tx(full_bar + s, 2 * S::B_BYTES);
@@ -561,8 +821,8 @@ meshconv_bwd_weight_tc_kernel(const float* __restrict__ dout, const float* __res
                 float4 hi, lo;
                 tc::split4(v, hi, lo);
                 const uint32_t off = tc::sw128_mn_off(k, q, S::LBO);
-                *reinterpret_cast<float4*>(a_hi + off) = hi;
-                *reinterpret_cast<float4*>(a_lo + off) = lo;
+                tc::sts128(tc::smem_u32(a_hi) + off, hi);
+                tc::sts128(tc::smem_u32(a_lo) + off, lo);
             }
             // B: G rows for 32 edges x 8 channel chunks (one item per thread)
             {
@@ -598,8 +858,8 @@ meshconv_bwd_weight_tc_kernel(const float* __restrict__ dout, const float* __res
                     float4 hi, lo;
                     tc::split4(gk[k5], hi, lo);
                     const uint32_t off = tc::sw128_mn_off(k, k5 * 8 + q, S::LBO);
-                    *reinterpret_cast<float4*>(b_hi + off) = hi;
-                    *reinterpret_cast<float4*>(b_lo + off) = lo;
+                    tc::sts128(tc::smem_u32(b_hi) + off, hi);
+                    tc::sts128(tc::smem_u32(b_lo) + off, lo);
                 }
             }
             tc::fence_proxy_async_smem();                                  // every writer fences its own stores ...
@@ -736,6 +996,7 @@ extern "C" int mcnn_meshconv_fwd_tc(const float* x, const int32_t* gemm, const i
     int nt = (Cout % 256 == 0) ? 256 : ((Cout % 128 == 0) ? 128 : 64);
     (void)mtiles;
     if (g_tc_force_ntile && Cout % g_tc_force_ntile == 0) nt = g_tc_force_ntile;
+    if (nt == 256 && g_tc_pair) return launch_fwd_tc2(x, gemm, ec, wt_ws, bias, out, B, E, Cin, Cout, st);
     if (nt == 256) return launch_fwd_tc<256>(x, gemm, ec, wt_ws, bias, out, B, E, Cin, Cout, st);
     if (nt == 128) return launch_fwd_tc<128>(x, gemm, ec, wt_ws, bias, out, B, E, Cin, Cout, st);
     return launch_fwd_tc<64>(x, gemm, ec, wt_ws, bias, out, B, E, Cin, Cout, st);
@@ -804,6 +1065,11 @@ extern "C" int mcnn_meshconv_bwd_weight_tc(const float* dout, const float* x, co
     return rc;
 }
 
+
+extern "C" int mcnn_debug_set_tc_pair(int on) {
+    g_tc_pair = on ? 1 : 0;
+    return MCNN_OK;
+}
 
 extern "C" int mcnn_debug_set_tc_ntile(int ntile) {
     g_tc_force_ntile = (ntile == 64 || ntile == 128 || ntile == 256) ? ntile : 0;

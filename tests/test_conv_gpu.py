@@ -129,3 +129,27 @@ def test_conv_tensor_core_path_matches_ffma_path(cin, cout):
     g_ff = [xg2.grad, conv.conv.weight.grad, conv.conv.bias.grad]
     for a, b in zip(g_tc, g_ff):
         assert close(a.cpu().numpy(), b.cpu().numpy(), 3e-5)
+
+
+@pytest.mark.parametrize('cin,cout,B', [(128, 256, 24), (256, 256, 23), (256, 512, 5)])
+def test_conv_cta_pair_kernel_matches_single_cta_kernel(cin, cout, B):
+    """The cta_group::2 forward kernel (two CTAs share the weight tile) against the single-CTA tcgen05 kernel: both run the
+    same 3xTF32 products in the same K order, so the results must agree to rounding of the accumulation order (bit-exact
+    in practice); odd tile counts exercise the surplus CTA of the last pair."""
+    from meshcnn_b200 import _lib, synth
+    from meshcnn_b200.mesh_conv import MeshConv
+    from tests.gpu_util import DEV, product_mesh
+    meshes = [product_mesh(*synth.make('ico' if s % 3 else 'torus', s, **(dict(nu=5) if s % 3 else dict(m=10, n=25)))) for s in range(B)]
+    torch.manual_seed(cin + cout + B)
+    conv = MeshConv(cin, cout, bias=True).to(DEV)
+    x = torch.randn(B, cin, 750, device=DEV)
+    L = _lib.lib()
+    try:
+        L.mcnn_debug_set_tc_pair(0)
+        y1 = conv(x, meshes).clone()
+        L.mcnn_debug_set_tc_pair(1)
+        y2 = conv(x, meshes).clone()
+        torch.cuda.synchronize()
+    finally:
+        L.mcnn_debug_set_tc_pair(_lib.TC_PAIR_DEFAULT)
+    assert close(y2.detach().cpu().numpy(), y1.detach().cpu().numpy(), 1e-6)
