@@ -20,7 +20,7 @@
 namespace mcnn {
 
 // debug knobs for bottleneck attribution (tools/tc_knobs.py): bit 0 = producers skip global loads, bit 1 = MMA warp skips
-// the tcgen05.mma issue, bit 2 = producers skip the st.shared.  0 in normal operation.
+// the tcgen05.mma issue, bit 2 = producers skip the st.shared, bit 3 = no bulk copies of the weight tile.  0 in normal operation.
 __device__ int g_tc_debug = 0;
 static int g_tc_force_ntile = 0;          // host side: 0 = heuristic
 static int g_tc_pair = 0;                 // host side: use the CTA-pair (cta_group::2) forward kernel for N = 256
@@ -172,7 +172,7 @@ meshconv_fwd_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ 
             unsigned char* b_lo = b_hi + S::B_BYTES;
             const int blk = kb % 5;
             float4 hi, lo;
-            if (tid == 0) {                                               // the B tile of this K block: two bulk copies (TMA engine)
+            if (tid == 0 && !(dbg & 8)) {                                 // the B tile of this K block: two bulk copies (TMA engine)
                 tc::mbar_expect_tx(full_bar + s, 2 * S::B_BYTES);
                 const float* src = wt + ((size_t)kb * Cout + n0) * 32;
                 tc::bulk_g2s(b_hi, src, S::B_BYTES, full_bar + s);
