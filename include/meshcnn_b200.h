@@ -88,6 +88,8 @@ int mcnn_debug_set_tc(int flags);
 int mcnn_debug_set_tc_ntile(int ntile);
 /* the CTA-pair (tcgen05 cta_group::2) forward kernel for Cout % 256 == 0: on / off */
 int mcnn_debug_set_tc_pair(int on);
+/* diagnostics only (-DMCNN_TC_PROF builds): copy the 16 cycle counters of CTA 0 of the forward kernel to host memory */
+int mcnn_debug_tc_prof(long long* out16_host, int reset);
 
 /* dx of the above (autograd of mesh_conv.py:47-69: conv2d dgrad, abs/add backward, index_select scatter).
  *   dout [B][E][Cout]   dx [B][E][Cin]  -- must be ZERO on entry (the kernel accumulates with red.global) */

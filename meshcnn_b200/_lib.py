@@ -44,6 +44,7 @@ SIGNATURES = {
     'mcnn_debug_set_tc': (_c_int, [_c_int]),
     'mcnn_debug_set_tc_ntile': (_c_int, [_c_int]),
     'mcnn_debug_set_tc_pair': (_c_int, [_c_int]),
+    'mcnn_debug_tc_prof': (_c_int, [_c_vp, _c_int]),
     'mcnn_meshconv_bwd_data_tc': (_c_int, [_c_vp] * 7 + [_c_int] * 4 + [_c_vp]),
     'mcnn_meshconv_bwd_weight_tc_ws': (_c_sz, [_c_int] * 4),
     'mcnn_meshconv_bwd_weight_tc': (_c_int, [_c_vp] * 7 + [_c_int] * 4 + [_c_vp]),

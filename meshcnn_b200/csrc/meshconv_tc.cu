@@ -22,6 +22,7 @@ namespace mcnn {
 // debug knobs for bottleneck attribution (tools/tc_knobs.py): bit 0 = producers skip global loads, bit 1 = MMA warp skips
 // the tcgen05.mma issue, bit 2 = producers skip the st.shared, bit 3 = no bulk copies of the weight tile.  0 in normal operation.
 __device__ int g_tc_debug = 0;
+__device__ long long g_tc_prof[16];        // -DMCNN_TC_PROF: cycle counters of CTA 0 (tools/tc_prof.py)
 static int g_tc_force_ntile = 0;          // host side: 0 = heuristic
 static int g_tc_pair = 0;                 // host side: use the CTA-pair (cta_group::2) forward kernel for N = 256
 
@@ -164,8 +165,15 @@ meshconv_fwd_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ 
         auto store_block = [&](int kb, const Regs& R) {
             const int s = kb % S::STAGES;
             const uint32_t ph = (kb / S::STAGES) & 1;
+#ifdef MCNN_TC_PROF
+            const long long tp0 = clock64();
+#endif
             if (lane == 0) tc::mbar_wait(empty_bar + s, ph ^ 1);      // one poller per warp
             __syncwarp();
+#ifdef MCNN_TC_PROF
+            const long long tp1 = clock64();
+            if (blockIdx.x == 0 && tid == 0) { g_tc_prof[0] += tp1 - tp0; g_tc_prof[6] += 1; }
+#endif
             unsigned char* a_hi = smem + s * S::STAGE_BYTES;
             unsigned char* a_lo = a_hi + S::A_BYTES;
             unsigned char* b_hi = a_lo + S::A_BYTES;
@@ -211,9 +219,15 @@ meshconv_fwd_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ 
                     tc::sts128(tc::smem_u32(a_lo) + off, lo);
                 }
             }
+#ifdef MCNN_TC_PROF
+            const long long tp2 = clock64();
+#endif
             tc::fence_proxy_async_smem();                                  // every writer fences its own stores ...
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(full_bar + s);                  // ... then one arrival per warp
+#ifdef MCNN_TC_PROF
+            if (blockIdx.x == 0 && tid == 0) { const long long tp3 = clock64(); g_tc_prof[1] += tp2 - tp1; g_tc_prof[2] += tp3 - tp2; }
+#endif
         };
         {                                                        // prefetch distance 2 (three register sets)
             // three register sets, prefetch distance 3.  The gathers of block kb + 3 are issued right AFTER block kb has been
@@ -237,8 +251,14 @@ meshconv_fwd_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ 
             }
         }
         // ======================================== epilogue ==========================================================
+#ifdef MCNN_TC_PROF
+        const long long te0 = clock64();
+#endif
         tc::mbar_wait(accum_bar, 0);
         tc::tc_fence_after();
+#ifdef MCNN_TC_PROF
+        if (blockIdx.x == 0 && tid == 0) g_tc_prof[4] += clock64() - te0;
+#endif
         const int lane_grp = warp & 3;                           // TMEM lanes 32*lane_grp .. +31
         const int r = lane_grp * 32 + lane;
         const int m = m0 + r;
@@ -268,8 +288,14 @@ meshconv_fwd_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ 
         for (int kb = 0; kb < num_kb; ++kb) {
             const int s = kb % S::STAGES;
             const uint32_t ph = (kb / S::STAGES) & 1;
+#ifdef MCNN_TC_PROF
+            const long long tm0 = clock64();
+#endif
             tc::mbar_wait(full_bar + s, ph);
             tc::tc_fence_after();
+#ifdef MCNN_TC_PROF
+            if (blockIdx.x == 0 && lane == 0) g_tc_prof[3] += clock64() - tm0;
+#endif
             if (tc::elect_one()) {
                 const uint32_t a_hi = tc::smem_u32(smem + s * S::STAGE_BYTES);
                 const uint32_t a_lo = a_hi + S::A_BYTES;
@@ -1065,6 +1091,15 @@ extern "C" int mcnn_meshconv_bwd_weight_tc(const float* dout, const float* x, co
     return rc;
 }
 
+
+extern "C" int mcnn_debug_tc_prof(long long* out16, int reset) {
+    cudaError_t e = cudaMemcpyFromSymbol(out16, g_tc_prof, sizeof(long long) * 16);
+    if (e == cudaSuccess && reset) {
+        long long z[16] = {0};
+        e = cudaMemcpyToSymbol(g_tc_prof, z, sizeof(z));
+    }
+    return e == cudaSuccess ? MCNN_OK : MCNN_E_CUDA;
+}
 
 extern "C" int mcnn_debug_set_tc_pair(int on) {
     g_tc_pair = on ? 1 : 0;
