@@ -24,6 +24,7 @@ namespace mcnn {
 __device__ int g_tc_debug = 0;
 __device__ long long g_tc_prof[16];        // -DMCNN_TC_PROF: cycle counters of CTA 0 (tools/tc_prof.py)
 static int g_tc_force_ntile = 0;          // host side: 0 = heuristic
+static int g_tc_pw16 = 0;                 // host side: 16 producer warps in the forward kernel (N >= 128)
 static int g_tc_pair = 0;                 // host side: use the CTA-pair (cta_group::2) forward kernel for N = 256
 
 constexpr int TC_M = 128;
@@ -74,12 +75,17 @@ struct TcSmem {
     static constexpr int TOTAL = BAR_OFF + 16 * 8 + 16 + 1024;   // + barriers + tmem slot + alignment slack
 };
 
-template <int N_TILE>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+template <int N_TILE, int PW>
+__global__ void __launch_bounds__((PW + 1) * 32, 1)
 meshconv_fwd_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ gemm, const int32_t* __restrict__ ec,
                        const float* __restrict__ wt, const float* __restrict__ bias, float* __restrict__ out,
                        int B, int E, int Cin, int Cout) {
     using S = TcSmem<N_TILE>;
+    constexpr int NTHREADS = (PW + 1) * 32;      // PW producer / epilogue warps + the MMA warp
+    constexpr int PT = PW * 32;                  // producer threads
+    constexpr int IT0 = (TC_M * 8) / PT;         // 16-byte items per thread in a G0 block (128 rows x 8 chunks)
+    constexpr int ITP = (TC_M * 4) / PT;         // items per thread in a pair block (128 rows x 4 chunks, two gathers each)
+    static_assert(IT0 == 2 * ITP && ITP >= 1, "producer mapping");
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     int (*nb)[5] = reinterpret_cast<int (*)[5]>(smem + S::NB_OFF);
@@ -96,7 +102,7 @@ meshconv_fwd_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ 
     const int dbg = g_tc_debug;
 
     // ---- setup ------------------------------------------------------------------------------------------------
-    for (int i = tid; i < TC_M * 5; i += TC_THREADS) {
+    for (int i = tid; i < TC_M * 5; i += NTHREADS) {
         const int r = i / 5, k = i - r * 5;
         const int m = m0 + r;
         int idx = -1;
@@ -108,9 +114,9 @@ meshconv_fwd_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ 
         }
         nb[r][k] = idx;
     }
-    if (warp == TC_PRODUCER_WARPS) {
+    if (warp == PW) {
         if (lane == 0) {
-            for (int s = 0; s < S::STAGES; ++s) { tc::mbar_init(full_bar + s, TC_PRODUCER_WARPS); tc::mbar_init(empty_bar + s, 1); }
+            for (int s = 0; s < S::STAGES; ++s) { tc::mbar_init(full_bar + s, PW); tc::mbar_init(empty_bar + s, 1); }
             tc::mbar_init(accum_bar, 1);
             tc::fence_barrier_init();
         }
@@ -122,40 +128,40 @@ meshconv_fwd_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ 
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp < TC_PRODUCER_WARPS) {
+    if (warp < PW) {
         // ======================================== producers ========================================================
         // Each thread owns the same tile rows for every K block, so its gather row ids live in registers and the global
         // loads of K block kb+2 are issued before the shared-memory stores of block kb (register prefetch, distance 2):
         // the L2 latency of the gathers is hidden behind two blocks of split / st.shared / MMA work.
         const int pt = tid;                                     // 0..255
-        int src0[4], srcA[2][2], srcB[2][2];                    // blk 0: 4 items (row, chunk); pair blocks: 2 items x 2 rows
+        int src0[IT0], srcA[ITP][2], srcB[ITP][2];                    // blk 0: 4 items (row, chunk); pair blocks: 2 items x 2 rows
 #pragma unroll
-        for (int it = 0; it < 4; ++it) src0[it] = nb[(pt + it * 256) >> 3][0];
+        for (int it = 0; it < IT0; ++it) src0[it] = nb[(pt + it * PT) >> 3][0];
 #pragma unroll
-        for (int it = 0; it < 2; ++it) {
-            const int r = pair_item_row(pt + it * 256);
+        for (int it = 0; it < ITP; ++it) {
+            const int r = pair_item_row(pt + it * PT);
             srcA[it][0] = nb[r][1]; srcB[it][0] = nb[r][3];     // pair (f1, f3)
             srcA[it][1] = nb[r][2]; srcB[it][1] = nb[r][4];     // pair (f2, f4)
         }
-        struct Regs { float4 a[4]; };
+        struct Regs { float4 a[IT0]; };
         const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
         auto load_block = [&](int kb, Regs& R) {
             const int cb = kb / 5, blk = kb - cb * 5;
             if (dbg & 1) {
 #pragma unroll
-                for (int it = 0; it < 4; ++it) R.a[it] = zero4;
+                for (int it = 0; it < IT0; ++it) R.a[it] = zero4;
                 return;
             }
             if (blk == 0) {
                 const int c = cb * 32 + ((pt & 7) << 2);
 #pragma unroll
-                for (int it = 0; it < 4; ++it)
+                for (int it = 0; it < IT0; ++it)
                     R.a[it] = src0[it] >= 0 ? __ldg(reinterpret_cast<const float4*>(x + (size_t)src0[it] * Cin + c)) : zero4;
             } else {
                 const int pr = (blk <= 2) ? 0 : 1;
                 const int c = cb * 32 + (((blk - 1) & 1) << 4) + ((pt & 3) << 2);
 #pragma unroll
-                for (int it = 0; it < 2; ++it) {
+                for (int it = 0; it < ITP; ++it) {
                     const int sa = pr ? srcA[it][1] : srcA[it][0], sb = pr ? srcB[it][1] : srcB[it][0];   // selects, not a dynamic index (local memory)
                     R.a[2 * it] = sa >= 0 ? __ldg(reinterpret_cast<const float4*>(x + (size_t)sa * Cin + c)) : zero4;
                     R.a[2 * it + 1] = sb >= 0 ? __ldg(reinterpret_cast<const float4*>(x + (size_t)sb * Cin + c)) : zero4;
@@ -194,8 +200,8 @@ meshconv_fwd_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ 
             }
             if (blk == 0) {
 #pragma unroll
-                for (int it = 0; it < 4; ++it) {
-                    const int item = pt + it * 256;
+                for (int it = 0; it < IT0; ++it) {
+                    const int item = pt + it * PT;
                     const uint32_t off = tc::sw128_off(item >> 3, item & 7);
                     tc::split4(R.a[it], hi, lo);
                     tc::sts128(tc::smem_u32(a_hi) + off, hi);
@@ -203,8 +209,8 @@ meshconv_fwd_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ 
                 }
             } else {
 #pragma unroll
-                for (int it = 0; it < 2; ++it) {
-                    const int item = pt + it * 256;
+                for (int it = 0; it < ITP; ++it) {
+                    const int item = pt + it * PT;
                     const int r = pair_item_row(item), q = item & 3;
                     const float4 fa = R.a[2 * it], fb = R.a[2 * it + 1];
                     const float4 sum = make_float4(fa.x + fb.x, fa.y + fb.y, fa.z + fb.z, fa.w + fb.w);
@@ -262,7 +268,8 @@ meshconv_fwd_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ 
         const int lane_grp = warp & 3;                           // TMEM lanes 32*lane_grp .. +31
         const int r = lane_grp * 32 + lane;
         const int m = m0 + r;
-        constexpr int COLS_PER_WARP = N_TILE / 2;                // warps w and w+4 share a lane group
+        constexpr int COLS_PER_WARP = N_TILE / (PW / 4);         // the PW / 4 warps of a lane group split the columns
+        static_assert(COLS_PER_WARP % 32 == 0, "epilogue reads 32 columns at a time");
         const int col0 = (warp >> 2) * COLS_PER_WARP;
 #pragma unroll 1
         for (int cc = 0; cc < COLS_PER_WARP; cc += 32) {
@@ -317,7 +324,7 @@ meshconv_fwd_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ 
         tc::tc_fence_before();
     }
     __syncthreads();
-    if (warp == TC_PRODUCER_WARPS) {
+    if (warp == PW) {
         tc::tc_fence_after();
         tc::tmem_dealloc<N_TILE>(tmem_base);
     }
@@ -572,18 +579,18 @@ static int launch_fwd_tc2(const float* x, const int32_t* gemm, const int32_t* ec
     return after_launch();
 }
 
-template <int N_TILE>
+template <int N_TILE, int PW>
 static int launch_fwd_tc(const float* x, const int32_t* gemm, const int32_t* ec, const float* wt, const float* bias,
                          float* out, int B, int E, int Cin, int Cout, cudaStream_t st) {
     using S = TcSmem<N_TILE>;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(meshconv_fwd_tc_kernel<N_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+        cudaError_t e = cudaFuncSetAttribute(meshconv_fwd_tc_kernel<N_TILE, PW>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
         if (e != cudaSuccess) { g_last_error = e; return MCNN_E_CUDA; }
         configured = true;
     }
     dim3 grid(ceil_div(B * E, TC_M), ceil_div(Cout, N_TILE));
-    meshconv_fwd_tc_kernel<N_TILE><<<grid, TC_THREADS, S::TOTAL, st>>>(x, gemm, ec, wt, bias, out, B, E, Cin, Cout);
+    meshconv_fwd_tc_kernel<N_TILE, PW><<<grid, (PW + 1) * 32, S::TOTAL, st>>>(x, gemm, ec, wt, bias, out, B, E, Cin, Cout);
     return after_launch();
 }
 
@@ -1023,9 +1030,13 @@ extern "C" int mcnn_meshconv_fwd_tc(const float* x, const int32_t* gemm, const i
     (void)mtiles;
     if (g_tc_force_ntile && Cout % g_tc_force_ntile == 0) nt = g_tc_force_ntile;
     if (nt == 256 && g_tc_pair) return launch_fwd_tc2(x, gemm, ec, wt_ws, bias, out, B, E, Cin, Cout, st);
-    if (nt == 256) return launch_fwd_tc<256>(x, gemm, ec, wt_ws, bias, out, B, E, Cin, Cout, st);
-    if (nt == 128) return launch_fwd_tc<128>(x, gemm, ec, wt_ws, bias, out, B, E, Cin, Cout, st);
-    return launch_fwd_tc<64>(x, gemm, ec, wt_ws, bias, out, B, E, Cin, Cout, st);
+    if (g_tc_pw16) {                                          // 16 producer warps (the kernel is bound by operand production)
+        if (nt == 256) return launch_fwd_tc<256, 16>(x, gemm, ec, wt_ws, bias, out, B, E, Cin, Cout, st);
+        if (nt == 128) return launch_fwd_tc<128, 16>(x, gemm, ec, wt_ws, bias, out, B, E, Cin, Cout, st);
+    }
+    if (nt == 256) return launch_fwd_tc<256, 8>(x, gemm, ec, wt_ws, bias, out, B, E, Cin, Cout, st);
+    if (nt == 128) return launch_fwd_tc<128, 8>(x, gemm, ec, wt_ws, bias, out, B, E, Cin, Cout, st);
+    return launch_fwd_tc<64, 8>(x, gemm, ec, wt_ws, bias, out, B, E, Cin, Cout, st);
 }
 
 
@@ -1102,7 +1113,8 @@ extern "C" int mcnn_debug_tc_prof(long long* out16, int reset) {
 }
 
 extern "C" int mcnn_debug_set_tc_pair(int on) {
-    g_tc_pair = on ? 1 : 0;
+    g_tc_pw16 = (on & 2) ? 1 : 0;
+    g_tc_pair = (on & 1) ? 1 : 0;
     return MCNN_OK;
 }
 

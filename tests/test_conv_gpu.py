@@ -131,8 +131,9 @@ def test_conv_tensor_core_path_matches_ffma_path(cin, cout):
         assert close(a.cpu().numpy(), b.cpu().numpy(), 3e-5)
 
 
-@pytest.mark.parametrize('cin,cout,B', [(128, 256, 24), (256, 256, 23), (256, 512, 5)])
-def test_conv_cta_pair_kernel_matches_single_cta_kernel(cin, cout, B):
+@pytest.mark.parametrize('mode', [1, 2], ids=['cta_pair', 'producers16'])
+@pytest.mark.parametrize('cin,cout,B', [(128, 256, 24), (256, 256, 23), (256, 512, 5), (128, 128, 7)])
+def test_conv_cta_pair_kernel_matches_single_cta_kernel(cin, cout, B, mode):
     """The cta_group::2 forward kernel (two CTAs share the weight tile) against the single-CTA tcgen05 kernel: both run the
     same 3xTF32 products in the same K order, so the results must agree to rounding of the accumulation order (bit-exact
     in practice); odd tile counts exercise the surplus CTA of the last pair."""
@@ -147,7 +148,7 @@ def test_conv_cta_pair_kernel_matches_single_cta_kernel(cin, cout, B):
     try:
         L.mcnn_debug_set_tc_pair(0)
         y1 = conv(x, meshes).clone()
-        L.mcnn_debug_set_tc_pair(1)
+        L.mcnn_debug_set_tc_pair(mode)           # 1: cta_group::2 kernel, 2: 16 producer warps
         y2 = conv(x, meshes).clone()
         torch.cuda.synchronize()
     finally:

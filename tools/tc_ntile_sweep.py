@@ -42,10 +42,13 @@ for E, cin, cout in shapes:
         res.append(timeit(lambda: _lib.check(L.mcnn_meshconv_fwd_tc(x.data_ptr(), g.data_ptr(), ec.data_ptr(), w.data_ptr(), None, out.data_ptr(), wt.data_ptr(), B, E, cin, cout, st()), 'fwd')))
     L.mcnn_debug_set_tc_ntile(0)
     pair = float('nan')
+    L.mcnn_debug_set_tc_pair(2)
+    pw16 = timeit(lambda: _lib.check(L.mcnn_meshconv_fwd_tc(x.data_ptr(), g.data_ptr(), ec.data_ptr(), w.data_ptr(), None, out.data_ptr(), wt.data_ptr(), B, E, cin, cout, st()), 'fwd'))
+    L.mcnn_debug_set_tc_pair(0)
     if cout % 256 == 0:
         L.mcnn_debug_set_tc_pair(1)
         pair = timeit(lambda: _lib.check(L.mcnn_meshconv_fwd_tc(x.data_ptr(), g.data_ptr(), ec.data_ptr(), w.data_ptr(), None, out.data_ptr(), wt.data_ptr(), B, E, cin, cout, st()), 'fwd'))
         L.mcnn_debug_set_tc_pair(0)
     bd = timeit(lambda: _lib.check(L.mcnn_meshconv_bwd_data_tc(dout.data_ptr(), x.data_ptr(), g.data_ptr(), ec.data_ptr(), w.data_ptr(), dx.data_ptr(), wt.data_ptr(), B, E, cin, cout, st()), 'bd'))
     bw = timeit(lambda: _lib.check(L.mcnn_meshconv_bwd_weight_tc(dout.data_ptr(), x.data_ptr(), g.data_ptr(), ec.data_ptr(), dw.data_ptr(), None, ws.data_ptr(), B, E, cin, cout, st()), 'bw'))
-    print('E=%d %d->%d  fwd us: N64 %.1f | N128 %.1f | N256 %.1f | pair %.1f   bwd_data %.1f  bwd_weight %.1f   (m-tiles %d)' % (E, cin, cout, *res, pair, bd, bw, (B * E + 127) // 128))
+    print('E=%d %d->%d  fwd us: N64 %.1f | N128 %.1f | N256 %.1f | pair %.1f | 16 producer warps %.1f   bwd_data %.1f  bwd_weight %.1f   (m-tiles %d)' % (E, cin, cout, *res, pair, pw16, bd, bw, (B * E + 127) // 128))
