@@ -5,6 +5,8 @@ is new code, not a port.
 The gradients of all parameters are views into one flat fp32 buffer, so zeroing them is one memset, the allreduce is
 one NCCL call over NVLink / NVSwitch on a 5-9 MB bucket (latency-bound: one bucket, not many), and no gather / scatter
 copies are needed.  Works with the gloo backend on CPU tensors as well (tests/test_ddp_cpu.py)."""
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -39,7 +41,7 @@ class FlatGradReducer:
         self.flat.zero_()
 
     def allreduce(self):
-        if self.world == 1:
+        if self.world == 1 or os.environ.get('MESHCNN_B200_SKIP_ALLREDUCE') == '1':     # the latter: scaling diagnostics only
             return
         if self.scale != 1.0:
             self.flat.mul_(self.scale)
