@@ -645,6 +645,7 @@ meshconv_bwd_data_tc_kernel(const float* __restrict__ dout, const float* __restr
     const int M = B * E;
     const int m0 = blockIdx.x * TC_M, cb = blockIdx.y;
     const int num_kb = Cout >> 5;
+    const int dbg = g_tc_debug;            // diagnostics: bit 4 = no scatter, bit 5 = no sign loads (results wrong)
 
     for (int i = tid; i < TC_M * 5; i += TC_THREADS) {
         const int r = i / 5, k = i - r * 5;
@@ -716,7 +717,7 @@ meshconv_bwd_data_tc_kernel(const float* __restrict__ dout, const float* __restr
         float g[5][16];
 #pragma unroll
         for (int k5 = 0; k5 < 5; ++k5) tc::tmem_ld16(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(k5 * 32 + cl0), g[k5]);
-        if (m < M) {
+        if (m < M && !(dbg & 16)) {
             const int b = m / E, e = m - b * E;
             const int c0 = cb * 32 + cl0;
             if (e >= __ldg(ec + b)) {
@@ -730,10 +731,10 @@ meshconv_bwd_data_tc_kernel(const float* __restrict__ dout, const float* __restr
                 const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                 for (int j = 0; j < 16; j += 4) {
-                    const float4 f1 = n1 >= 0 ? __ldg(reinterpret_cast<const float4*>(x + (size_t)n1 * Cin + c0 + j)) : z;
-                    const float4 f2 = n2 >= 0 ? __ldg(reinterpret_cast<const float4*>(x + (size_t)n2 * Cin + c0 + j)) : z;
-                    const float4 f3 = n3 >= 0 ? __ldg(reinterpret_cast<const float4*>(x + (size_t)n3 * Cin + c0 + j)) : z;
-                    const float4 f4 = n4 >= 0 ? __ldg(reinterpret_cast<const float4*>(x + (size_t)n4 * Cin + c0 + j)) : z;
+                    const float4 f1 = (n1 >= 0 && !(dbg & 32)) ? __ldg(reinterpret_cast<const float4*>(x + (size_t)n1 * Cin + c0 + j)) : z;
+                    const float4 f2 = (n2 >= 0 && !(dbg & 32)) ? __ldg(reinterpret_cast<const float4*>(x + (size_t)n2 * Cin + c0 + j)) : z;
+                    const float4 f3 = (n3 >= 0 && !(dbg & 32)) ? __ldg(reinterpret_cast<const float4*>(x + (size_t)n3 * Cin + c0 + j)) : z;
+                    const float4 f4 = (n4 >= 0 && !(dbg & 32)) ? __ldg(reinterpret_cast<const float4*>(x + (size_t)n4 * Cin + c0 + j)) : z;
                     const float s13[4] = {sgn(f1.x - f3.x), sgn(f1.y - f3.y), sgn(f1.z - f3.z), sgn(f1.w - f3.w)};
                     const float s24[4] = {sgn(f2.x - f4.x), sgn(f2.y - f4.y), sgn(f2.z - f4.z), sgn(f2.w - f4.w)};
                     tc::red_add_v4(dx + (size_t)m * Cin + c0 + j, g[0][j], g[0][j + 1], g[0][j + 2], g[0][j + 3]);
