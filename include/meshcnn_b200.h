@@ -81,6 +81,11 @@ int mcnn_meshconv_fwd(const float* x, const int32_t* gemm, const int32_t* ec, co
 int mcnn_meshconv_tc_supported(int Cin, int Cout);
 int mcnn_meshconv_fwd_tc(const float* x, const int32_t* gemm, const int32_t* ec, const float* weight,
                          const float* bias, float* out, float* wt_ws, int B, int E, int Cin, int Cout, void* stream);
+/* the same, additionally writing signs[2][B*E][Cin] (int8: sign(f1 - f3), then sign(f2 - f4), the derivative of the two abs
+ * terms of mesh_conv.py:67-68) for mcnn_meshconv_bwd_data_tc_signs; signs may be NULL */
+int mcnn_meshconv_fwd_tc_signs(const float* x, const int32_t* gemm, const int32_t* ec, const float* weight,
+                               const float* bias, float* out, float* wt_ws, int8_t* signs, int B, int E, int Cin, int Cout,
+                               void* stream);
 
 /* diagnostics only: bottleneck-attribution knobs of the tensor-core forward kernel (0 = normal operation) */
 int mcnn_debug_set_tc(int flags);
@@ -106,6 +111,11 @@ int mcnn_meshconv_bwd_weight(const float* dout, const float* x, const int32_t* g
  *   bwd_weight_tc: Cin % 32 == 0 and Cout % 4 == 0; dweight / dbias are OVERWRITTEN (slab partials are written to
  *                  `ws` and reduced by a second kernel: deterministic, no atomics); ws holds
  *                  mcnn_meshconv_bwd_weight_tc_ws(B, E, Cin, Cout) floats */
+/* mcnn_meshconv_bwd_data_tc with the signs kept by the forward kernel instead of re-reading four neighbour rows of x per edge
+ * (x may then be NULL) */
+int mcnn_meshconv_bwd_data_tc_signs(const float* dout, const float* x, const int8_t* signs, const int32_t* gemm,
+                                    const int32_t* ec, const float* weight, float* dx, float* wtb_ws, int B, int E, int Cin,
+                                    int Cout, void* stream);
 int mcnn_meshconv_bwd_data_tc(const float* dout, const float* x, const int32_t* gemm, const int32_t* ec,
                               const float* weight, float* dx, float* wtb_ws, int B, int E, int Cin, int Cout,
                               void* stream);

@@ -39,6 +39,8 @@ SIGNATURES = {
     'mcnn_meshconv_fwd': (_c_int, [_c_vp] * 7 + [_c_int] * 4 + [_c_vp]),
     'mcnn_meshconv_tc_supported': (_c_int, [_c_int, _c_int]),
     'mcnn_meshconv_fwd_tc': (_c_int, [_c_vp] * 7 + [_c_int] * 4 + [_c_vp]),
+    'mcnn_meshconv_fwd_tc_signs': (_c_int, [_c_vp] * 8 + [_c_int] * 4 + [_c_vp]),
+    'mcnn_meshconv_bwd_data_tc_signs': (_c_int, [_c_vp] * 8 + [_c_int] * 4 + [_c_vp]),
     'mcnn_meshconv_bwd_data': (_c_int, [_c_vp] * 6 + [_c_int] * 4 + [_c_vp]),
     'mcnn_meshconv_bwd_weight': (_c_int, [_c_vp] * 6 + [_c_int] * 4 + [_c_vp]),
     'mcnn_debug_set_tc': (_c_int, [_c_int]),

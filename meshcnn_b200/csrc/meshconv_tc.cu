@@ -79,7 +79,7 @@ template <int N_TILE, int PW>
 __global__ void __launch_bounds__((PW + 1) * 32, 1)
 meshconv_fwd_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ gemm, const int32_t* __restrict__ ec,
                        const float* __restrict__ wt, const float* __restrict__ bias, float* __restrict__ out,
-                       int B, int E, int Cin, int Cout) {
+                       int8_t* __restrict__ signs, int B, int E, int Cin, int Cout) {
     using S = TcSmem<N_TILE>;
     constexpr int NTHREADS = (PW + 1) * 32;      // PW producer / epilogue warps + the MMA warp
     constexpr int PT = PW * 32;                  // producer threads
@@ -214,7 +214,14 @@ meshconv_fwd_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ 
                     const int r = pair_item_row(item), q = item & 3;
                     const float4 fa = R.a[2 * it], fb = R.a[2 * it + 1];
                     const float4 sum = make_float4(fa.x + fb.x, fa.y + fb.y, fa.z + fb.z, fa.w + fb.w);
-                    const float4 dif = make_float4(fabsf(fa.x - fb.x), fabsf(fa.y - fb.y), fabsf(fa.z - fb.z), fabsf(fa.w - fb.w));
+                    const float4 dd = make_float4(fa.x - fb.x, fa.y - fb.y, fa.z - fb.z, fa.w - fb.w);
+                    const float4 dif = make_float4(fabsf(dd.x), fabsf(dd.y), fabsf(dd.z), fabsf(dd.w));
+                    if (signs != nullptr && blockIdx.y == 0 && m0 + r < M) {
+                        // sign(f1 - f3) / sign(f2 - f4) of this edge, kept for the data-gradient kernel (abs backward)
+                        const int cb_ = kb / 5, c_ = cb_ * 32 + (((blk - 1) & 1) << 4) + (q << 2);
+                        const size_t so = ((size_t)(blk <= 2 ? 0 : 1) * M + (m0 + r)) * Cin + c_;
+                        *reinterpret_cast<char4*>(signs + so) = make_char4((signed char)sgn(dd.x), (signed char)sgn(dd.y), (signed char)sgn(dd.z), (signed char)sgn(dd.w));
+                    }
                     tc::split4(sum, hi, lo);
                     uint32_t off = tc::sw128_off(r, q);
                     tc::sts128(tc::smem_u32(a_hi) + off, hi);
@@ -351,7 +358,7 @@ struct Tc2Smem {
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 meshconv_fwd_tc2_kernel(const float* __restrict__ x, const int32_t* __restrict__ gemm, const int32_t* __restrict__ ec,
                         const float* __restrict__ wt, const float* __restrict__ bias, float* __restrict__ out,
-                        int B, int E, int Cin, int Cout) {
+                        int8_t* __restrict__ signs, int B, int E, int Cin, int Cout) {
     using S = Tc2Smem;
     constexpr int N_TILE = 256;
     extern __shared__ unsigned char smem_raw[];
@@ -466,7 +473,14 @@ meshconv_fwd_tc2_kernel(const float* __restrict__ x, const int32_t* __restrict__
                     const int r = pair_item_row(item), q = item & 3;
                     const float4 fa = R.a[2 * it], fb = R.a[2 * it + 1];
                     const float4 sum = make_float4(fa.x + fb.x, fa.y + fb.y, fa.z + fb.z, fa.w + fb.w);
-                    const float4 dif = make_float4(fabsf(fa.x - fb.x), fabsf(fa.y - fb.y), fabsf(fa.z - fb.z), fabsf(fa.w - fb.w));
+                    const float4 dd = make_float4(fa.x - fb.x, fa.y - fb.y, fa.z - fb.z, fa.w - fb.w);
+                    const float4 dif = make_float4(fabsf(dd.x), fabsf(dd.y), fabsf(dd.z), fabsf(dd.w));
+                    if (signs != nullptr && blockIdx.y == 0 && m0 + r < M) {
+                        // sign(f1 - f3) / sign(f2 - f4) of this edge, kept for the data-gradient kernel (abs backward)
+                        const int cb_ = kb / 5, c_ = cb_ * 32 + (((blk - 1) & 1) << 4) + (q << 2);
+                        const size_t so = ((size_t)(blk <= 2 ? 0 : 1) * M + (m0 + r)) * Cin + c_;
+                        *reinterpret_cast<char4*>(signs + so) = make_char4((signed char)sgn(dd.x), (signed char)sgn(dd.y), (signed char)sgn(dd.z), (signed char)sgn(dd.w));
+                    }
                     tc::split4(sum, hi, lo);
                     uint32_t off = tc::sw128_off(r, q);
                     tc::sts128(tc::smem_u32(a_hi) + off, hi);
@@ -565,7 +579,7 @@ meshconv_fwd_tc2_kernel(const float* __restrict__ x, const int32_t* __restrict__
 }
 
 static int launch_fwd_tc2(const float* x, const int32_t* gemm, const int32_t* ec, const float* wt, const float* bias,
-                          float* out, int B, int E, int Cin, int Cout, cudaStream_t st) {
+                          float* out, int8_t* signs, int B, int E, int Cin, int Cout, cudaStream_t st) {
     using S = Tc2Smem;
     static bool configured = false;
     if (!configured) {
@@ -575,13 +589,13 @@ static int launch_fwd_tc2(const float* x, const int32_t* gemm, const int32_t* ec
     }
     const int mtiles = ceil_div(B * E, TC_M);
     dim3 grid(2 * ceil_div(mtiles, 2), Cout / 256);          // whole CTA pairs; a surplus CTA works on rows >= M (all zero)
-    meshconv_fwd_tc2_kernel<<<grid, TC_THREADS, S::TOTAL, st>>>(x, gemm, ec, wt, bias, out, B, E, Cin, Cout);
+    meshconv_fwd_tc2_kernel<<<grid, TC_THREADS, S::TOTAL, st>>>(x, gemm, ec, wt, bias, out, signs, B, E, Cin, Cout);
     return after_launch();
 }
 
 template <int N_TILE, int PW>
 static int launch_fwd_tc(const float* x, const int32_t* gemm, const int32_t* ec, const float* wt, const float* bias,
-                         float* out, int B, int E, int Cin, int Cout, cudaStream_t st) {
+                         float* out, int8_t* signs, int B, int E, int Cin, int Cout, cudaStream_t st) {
     using S = TcSmem<N_TILE>;
     static bool configured = false;
     if (!configured) {
@@ -590,7 +604,7 @@ static int launch_fwd_tc(const float* x, const int32_t* gemm, const int32_t* ec,
         configured = true;
     }
     dim3 grid(ceil_div(B * E, TC_M), ceil_div(Cout, N_TILE));
-    meshconv_fwd_tc_kernel<N_TILE, PW><<<grid, (PW + 1) * 32, S::TOTAL, st>>>(x, gemm, ec, wt, bias, out, B, E, Cin, Cout);
+    meshconv_fwd_tc_kernel<N_TILE, PW><<<grid, (PW + 1) * 32, S::TOTAL, st>>>(x, gemm, ec, wt, bias, out, signs, B, E, Cin, Cout);
     return after_launch();
 }
 
@@ -631,7 +645,7 @@ __global__ void weight_tc_bwd_layout_kernel(const float* __restrict__ w, float* 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 meshconv_bwd_data_tc_kernel(const float* __restrict__ dout, const float* __restrict__ x, const int32_t* __restrict__ gemm,
                             const int32_t* __restrict__ ec, const float* __restrict__ wtb, float* __restrict__ dx,
-                            int B, int E, int Cin, int Cout) {
+                            const int8_t* __restrict__ signs, int B, int E, int Cin, int Cout) {
     using S = BdSmem;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -731,12 +745,20 @@ meshconv_bwd_data_tc_kernel(const float* __restrict__ dout, const float* __restr
                 const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                 for (int j = 0; j < 16; j += 4) {
-                    const float4 f1 = (n1 >= 0 && !(dbg & 32)) ? __ldg(reinterpret_cast<const float4*>(x + (size_t)n1 * Cin + c0 + j)) : z;
-                    const float4 f2 = (n2 >= 0 && !(dbg & 32)) ? __ldg(reinterpret_cast<const float4*>(x + (size_t)n2 * Cin + c0 + j)) : z;
-                    const float4 f3 = (n3 >= 0 && !(dbg & 32)) ? __ldg(reinterpret_cast<const float4*>(x + (size_t)n3 * Cin + c0 + j)) : z;
-                    const float4 f4 = (n4 >= 0 && !(dbg & 32)) ? __ldg(reinterpret_cast<const float4*>(x + (size_t)n4 * Cin + c0 + j)) : z;
-                    const float s13[4] = {sgn(f1.x - f3.x), sgn(f1.y - f3.y), sgn(f1.z - f3.z), sgn(f1.w - f3.w)};
-                    const float s24[4] = {sgn(f2.x - f4.x), sgn(f2.y - f4.y), sgn(f2.z - f4.z), sgn(f2.w - f4.w)};
+                    float s13[4], s24[4];
+                    if (signs != nullptr) {                                 // kept by the forward kernel: 2 x 4 bytes instead of 4 x 16
+                        const char4 a13 = *reinterpret_cast<const char4*>(signs + (size_t)m * Cin + c0 + j);
+                        const char4 a24 = *reinterpret_cast<const char4*>(signs + ((size_t)M + m) * Cin + c0 + j);
+                        s13[0] = (float)a13.x; s13[1] = (float)a13.y; s13[2] = (float)a13.z; s13[3] = (float)a13.w;
+                        s24[0] = (float)a24.x; s24[1] = (float)a24.y; s24[2] = (float)a24.z; s24[3] = (float)a24.w;
+                    } else {
+                        const float4 f1 = (n1 >= 0 && !(dbg & 32)) ? __ldg(reinterpret_cast<const float4*>(x + (size_t)n1 * Cin + c0 + j)) : z;
+                        const float4 f2 = (n2 >= 0 && !(dbg & 32)) ? __ldg(reinterpret_cast<const float4*>(x + (size_t)n2 * Cin + c0 + j)) : z;
+                        const float4 f3 = (n3 >= 0 && !(dbg & 32)) ? __ldg(reinterpret_cast<const float4*>(x + (size_t)n3 * Cin + c0 + j)) : z;
+                        const float4 f4 = (n4 >= 0 && !(dbg & 32)) ? __ldg(reinterpret_cast<const float4*>(x + (size_t)n4 * Cin + c0 + j)) : z;
+                        s13[0] = sgn(f1.x - f3.x); s13[1] = sgn(f1.y - f3.y); s13[2] = sgn(f1.z - f3.z); s13[3] = sgn(f1.w - f3.w);
+                        s24[0] = sgn(f2.x - f4.x); s24[1] = sgn(f2.y - f4.y); s24[2] = sgn(f2.z - f4.z); s24[3] = sgn(f2.w - f4.w);
+                    }
                     tc::red_add_v4(dx + (size_t)m * Cin + c0 + j, g[0][j], g[0][j + 1], g[0][j + 2], g[0][j + 3]);
                     if (n1 >= 0) tc::red_add_v4(dx + (size_t)n1 * Cin + c0 + j, g[1][j] + s13[0] * g[3][j], g[1][j + 1] + s13[1] * g[3][j + 1],
                                                 g[1][j + 2] + s13[2] * g[3][j + 2], g[1][j + 3] + s13[3] * g[3][j + 3]);
@@ -1019,6 +1041,12 @@ extern "C" int mcnn_meshconv_tc_supported(int Cin, int Cout) { return (Cin > 0 &
 extern "C" int mcnn_meshconv_fwd_tc(const float* x, const int32_t* gemm, const int32_t* ec, const float* weight,
                                     const float* bias, float* out, float* wt_ws, int B, int E, int Cin, int Cout,
                                     void* stream) {
+    return mcnn_meshconv_fwd_tc_signs(x, gemm, ec, weight, bias, out, wt_ws, nullptr, B, E, Cin, Cout, stream);
+}
+
+extern "C" int mcnn_meshconv_fwd_tc_signs(const float* x, const int32_t* gemm, const int32_t* ec, const float* weight,
+                                          const float* bias, float* out, float* wt_ws, int8_t* signs, int B, int E, int Cin,
+                                          int Cout, void* stream) {
     if (!x || !gemm || !ec || !weight || !out || !wt_ws || B <= 0 || E <= 0) return MCNN_E_BADARG;
     if (!mcnn_meshconv_tc_supported(Cin, Cout)) return MCNN_E_BADARG;
     cudaStream_t st = (cudaStream_t)stream;
@@ -1030,21 +1058,27 @@ extern "C" int mcnn_meshconv_fwd_tc(const float* x, const int32_t* gemm, const i
     int nt = (Cout % 256 == 0) ? 256 : ((Cout % 128 == 0) ? 128 : 64);
     (void)mtiles;
     if (g_tc_force_ntile && Cout % g_tc_force_ntile == 0) nt = g_tc_force_ntile;
-    if (nt == 256 && g_tc_pair) return launch_fwd_tc2(x, gemm, ec, wt_ws, bias, out, B, E, Cin, Cout, st);
+    if (nt == 256 && g_tc_pair) return launch_fwd_tc2(x, gemm, ec, wt_ws, bias, out, signs, B, E, Cin, Cout, st);
     if (g_tc_pw16) {                                          // 16 producer warps (the kernel is bound by operand production)
-        if (nt == 256) return launch_fwd_tc<256, 16>(x, gemm, ec, wt_ws, bias, out, B, E, Cin, Cout, st);
-        if (nt == 128) return launch_fwd_tc<128, 16>(x, gemm, ec, wt_ws, bias, out, B, E, Cin, Cout, st);
+        if (nt == 256) return launch_fwd_tc<256, 16>(x, gemm, ec, wt_ws, bias, out, signs, B, E, Cin, Cout, st);
+        if (nt == 128) return launch_fwd_tc<128, 16>(x, gemm, ec, wt_ws, bias, out, signs, B, E, Cin, Cout, st);
     }
-    if (nt == 256) return launch_fwd_tc<256, 8>(x, gemm, ec, wt_ws, bias, out, B, E, Cin, Cout, st);
-    if (nt == 128) return launch_fwd_tc<128, 8>(x, gemm, ec, wt_ws, bias, out, B, E, Cin, Cout, st);
-    return launch_fwd_tc<64, 8>(x, gemm, ec, wt_ws, bias, out, B, E, Cin, Cout, st);
+    if (nt == 256) return launch_fwd_tc<256, 8>(x, gemm, ec, wt_ws, bias, out, signs, B, E, Cin, Cout, st);
+    if (nt == 128) return launch_fwd_tc<128, 8>(x, gemm, ec, wt_ws, bias, out, signs, B, E, Cin, Cout, st);
+    return launch_fwd_tc<64, 8>(x, gemm, ec, wt_ws, bias, out, signs, B, E, Cin, Cout, st);
 }
 
 
 extern "C" int mcnn_meshconv_bwd_data_tc(const float* dout, const float* x, const int32_t* gemm, const int32_t* ec,
                                          const float* weight, float* dx, float* wtb_ws, int B, int E, int Cin, int Cout,
                                          void* stream) {
-    if (!dout || !x || !gemm || !ec || !weight || !dx || !wtb_ws || B <= 0 || E <= 0) return MCNN_E_BADARG;
+    return mcnn_meshconv_bwd_data_tc_signs(dout, x, nullptr, gemm, ec, weight, dx, wtb_ws, B, E, Cin, Cout, stream);
+}
+
+extern "C" int mcnn_meshconv_bwd_data_tc_signs(const float* dout, const float* x, const int8_t* signs, const int32_t* gemm,
+                                               const int32_t* ec, const float* weight, float* dx, float* wtb_ws, int B, int E,
+                                               int Cin, int Cout, void* stream) {
+    if (!dout || (!x && !signs) || !gemm || !ec || !weight || !dx || !wtb_ws || B <= 0 || E <= 0) return MCNN_E_BADARG;
     if (!(Cin > 0 && Cin % 32 == 0 && Cout > 0 && Cout % 32 == 0)) return MCNN_E_BADARG;
     cudaStream_t st = (cudaStream_t)stream;
     const int total = Cout * 5 * Cin;
@@ -1058,7 +1092,7 @@ extern "C" int mcnn_meshconv_bwd_data_tc(const float* dout, const float* x, cons
         configured = true;
     }
     dim3 grid(ceil_div(B * E, TC_M), Cin / 32);
-    meshconv_bwd_data_tc_kernel<<<grid, TC_THREADS, BdSmem::TOTAL, st>>>(dout, x, gemm, ec, wtb_ws, dx, B, E, Cin, Cout);
+    meshconv_bwd_data_tc_kernel<<<grid, TC_THREADS, BdSmem::TOTAL, st>>>(dout, x, gemm, ec, wtb_ws, dx, signs, B, E, Cin, Cout);
     return after_launch();
 }
 

@@ -30,12 +30,21 @@ class MeshConvFn(torch.autograd.Function):
         out = torch.empty(B, E, Cout, dtype=torch.float32, device=x.device)
         L = _lib.lib()
         use_tc = USE_TC and L.mcnn_meshconv_tc_supported(Cin, Cout)
-        fwd = L.mcnn_meshconv_fwd_tc if use_tc else L.mcnn_meshconv_fwd
+        # the tensor-core forward also keeps sign(f1 - f3), sign(f2 - f4) for the data-gradient kernel when x needs a gradient
+        signs = None
+        if use_tc and ctx.needs_input_grad[0] and Cout % 32 == 0:
+            signs = torch.empty(2, B * E, Cin, dtype=torch.int8, device=x.device)
         with profiler.span('meshconv_fwd_tc' if use_tc else 'meshconv_fwd', B=B, E=E, Cin=Cin, Cout=Cout):
-            _lib.check(fwd(x.data_ptr(), level.gemm.data_ptr(), level.ec.data_ptr(), w.data_ptr(),
-                                           _lib.ptr(bias), out.data_ptr(), wt_ws.data_ptr(), B, E, Cin, Cout,
-                                           _lib.current_stream()), 'mcnn_meshconv_fwd')
+            if use_tc:
+                _lib.check(L.mcnn_meshconv_fwd_tc_signs(x.data_ptr(), level.gemm.data_ptr(), level.ec.data_ptr(), w.data_ptr(),
+                                                        _lib.ptr(bias), out.data_ptr(), wt_ws.data_ptr(), _lib.ptr(signs), B, E, Cin, Cout,
+                                                        _lib.current_stream()), 'mcnn_meshconv_fwd_tc')
+            else:
+                _lib.check(L.mcnn_meshconv_fwd(x.data_ptr(), level.gemm.data_ptr(), level.ec.data_ptr(), w.data_ptr(),
+                                               _lib.ptr(bias), out.data_ptr(), wt_ws.data_ptr(), B, E, Cin, Cout,
+                                               _lib.current_stream()), 'mcnn_meshconv_fwd')
         ctx.save_for_backward(x, w)
+        ctx.signs = signs
         ctx.level = level
         ctx.has_bias = bias is not None
         return out
@@ -56,9 +65,9 @@ class MeshConvFn(torch.autograd.Function):
             if tc_ok and Cout % 32 == 0:
                 wtb = torch.empty(2 * 5 * Cin, Cout, dtype=torch.float32, device=x.device)
                 with profiler.span('meshconv_bwd_data_tc', B=B, E=E, Cin=Cin, Cout=Cout):
-                    _lib.check(L.mcnn_meshconv_bwd_data_tc(dout.data_ptr(), x.data_ptr(), level.gemm.data_ptr(), level.ec.data_ptr(),
-                                                           w.data_ptr(), dx.data_ptr(), wtb.data_ptr(), B, E, Cin, Cout, st),
-                               'mcnn_meshconv_bwd_data_tc')
+                    _lib.check(L.mcnn_meshconv_bwd_data_tc_signs(dout.data_ptr(), x.data_ptr(), _lib.ptr(ctx.signs), level.gemm.data_ptr(),
+                                                                 level.ec.data_ptr(), w.data_ptr(), dx.data_ptr(), wtb.data_ptr(), B, E, Cin,
+                                                                 Cout, st), 'mcnn_meshconv_bwd_data_tc')
             else:
                 with profiler.span('meshconv_bwd_data', B=B, E=E, Cin=Cin, Cout=Cout):
                     _lib.check(L.mcnn_meshconv_bwd_data(dout.data_ptr(), x.data_ptr(), level.gemm.data_ptr(), level.ec.data_ptr(),
