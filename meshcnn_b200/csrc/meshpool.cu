@@ -21,7 +21,7 @@
 //                            un-clamped occurrences of m = number of paths starting at m.  Both are
 //                            evaluated after the collapse by all threads.
 //
-// Phases: load -> bitonic sort of (norm bits, id) keys -> lane 0 of warp 0 runs the sequential collapse (order and
+// Phases: load -> stable radix sort of the norm bits (ties stay in id order) -> lane 0 of warp 0 runs the sequential collapse (order and
 // side effects identical to the reference, failed attempts included) and calls in the other 31 lanes for every list
 // walk -> all threads run Mesh.clean (compaction, re-indexing with dead -> 0) and emit the groups as CSR + CSC +
 // un-clamped occurrences.
@@ -92,14 +92,10 @@ __host__ __device__ inline PoolLayout pool_layout(int n, int V, int ve_cap, bool
     L.ulog_cap = 2 * n + 16;                     // every union's source dies within the same attempt: <= 2 per dead edge
     L.ulog = o; o += sizeof(pair_t) * (size_t)L.ulog_cap; o = align_up(o, 16);
     L.cnt32 = o; o += sizeof(int) * 2 * (size_t)n; o = align_up(o, 16);           // out-degree, row length / cursor
-    int np2 = 1;
-    while (np2 < n) np2 <<= 1;
-    L.npow2 = np2;
-    // the sort keys (uint64[npow2]) are dead before the group evaluation needs occ (int32[n]) + out0 / out1 (u16[n] each)
-    {
-        const size_t ksz = sizeof(unsigned long long) * (size_t)np2, esz = (sizeof(int) + 2 * sizeof(uidx_t)) * (size_t)n;
-        L.keys = o; o += ksz > esz ? ksz : esz; o = align_up(o, 16);
-    }
+    L.npow2 = 0;
+    // the radix-sort ping-pong buffers (2 x (u32 key + id)[n]) are dead before the group evaluation needs occ (int32[n]) +
+    // out0 / out1 (id[n] each), which live in the same place
+    L.keys = o; o += (2 * sizeof(uint32_t) + 2 * sizeof(uidx_t)) * (size_t)n; o = align_up(o, 16);
     L.scan = o; o += sizeof(int) * 48; o = align_up(o, 16);
     L.total = o;
     return L;
@@ -587,7 +583,6 @@ __global__ void __launch_bounds__(P::THREADS, 1) pool_collapse_kernel(const mcnn
     uidx_t* eposa = reinterpret_cast<uidx_t*>(smem + L.eposa);
     uidx_t* eposb = reinterpret_cast<uidx_t*>(smem + L.eposb);
     pair_t* ulog = reinterpret_cast<pair_t*>(smem + L.ulog);
-    unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem + L.keys);
     int* scan = reinterpret_cast<int*>(smem + L.scan);
 
     const int32_t* g_gemm = a.gemm_in + (size_t)b * E_in * 4;
@@ -630,27 +625,63 @@ __global__ void __launch_bounds__(P::THREADS, 1) pool_collapse_kernel(const mcnn
         for (int i = tid; i < 3 * V; i += POOL_THREADS) vs_s[i] = g_vs[i];
     if (clk && tid == 0) clk[1] = clock64();
     // ---- phase B: sort (norm bits, id) ascending == heapify + heappop order (mesh_pool.py:184-192, F2) ----
-    const int np2 = L.npow2;
-    for (int i = tid; i < np2; i += POOL_THREADS) {
-        unsigned long long k = ~0ULL;
-        if (i < n) k = ((unsigned long long)__float_as_uint(g_norms[i]) << 32) | (unsigned)i;
-        keys[i] = k;
-    }
-    __syncthreads();
-    for (int k = 2; k <= np2; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = tid; i < np2; i += POOL_THREADS) {
-                const int ixj = i ^ j;
-                if (ixj > i) {
-                    const unsigned long long x = keys[i], y = keys[ixj];
-                    const bool up = (i & k) == 0;
-                    if ((x > y) == up) { keys[i] = y; keys[ixj] = x; }
-                }
+    // Squared norms are non-negative floats: their bit patterns order like unsigned integers.  Stable LSD radix sort, four
+    // 8-bit passes, starting from id order, so that equal norms stay in ascending id order (the heap's tie-break).  Every
+    // warp owns a contiguous chunk of the current sequence; `match.any` ranks equal digits inside a group of 32.
+    {
+        constexpr int NW = POOL_THREADS / 32;
+        __shared__ int s_hist[NW][256];
+        uint32_t* kA = reinterpret_cast<uint32_t*>(smem + L.keys);
+        uint32_t* kB = kA + n;
+        uidx_t* iA = reinterpret_cast<uidx_t*>(kB + n);
+        uidx_t* iB = iA + n;
+        for (int i = tid; i < n; i += POOL_THREADS) { kA[i] = __float_as_uint(g_norms[i]); iA[i] = (uidx_t)i; }
+        const int wid = tid >> 5, lane = tid & 31;
+        const int chunk = ((n + NW - 1) / NW + 31) & ~31;
+        const int cbeg = min(n, wid * chunk), cend = min(n, cbeg + chunk);
+        const unsigned lt = (1u << lane) - 1u;
+        for (int pass = 0; pass < 4; ++pass) {
+            const int shift = pass * 8;
+            for (int i = tid; i < NW * 256; i += POOL_THREADS) (&s_hist[0][0])[i] = 0;
+            __syncthreads();
+            for (int base = cbeg; base < cend; base += 32) {             // count
+                const int i = base + lane;
+                const bool ok = i < cend;
+                const unsigned d = ok ? ((kA[i] >> shift) & 255u) : 256u;
+                const unsigned grp = __match_any_sync(0xffffffffu, d);
+                if (ok && (grp & lt) == 0u) s_hist[wid][d] += __popc(grp);
             }
             __syncthreads();
+            // exclusive scan in (digit, warp) order: one thread per digit walks the NW counters, block scan over digit totals
+            {
+                int tot = 0;
+                if (tid < 256)
+                    for (int w = 0; w < NW; ++w) { const int c = s_hist[w][tid]; s_hist[w][tid] = tot; tot += c; }
+                int all;
+                const int pre = block_scan_excl<POOL_THREADS>(tid < 256 ? tot : 0, scan, all);
+                if (tid < 256)
+                    for (int w = 0; w < NW; ++w) s_hist[w][tid] += pre;
+            }
+            __syncthreads();
+            for (int base = cbeg; base < cend; base += 32) {             // scatter, in order
+                const int i = base + lane;
+                const bool ok = i < cend;
+                const uint32_t key = ok ? kA[i] : 0u;
+                const unsigned d = ok ? ((key >> shift) & 255u) : 256u;
+                const unsigned grp = __match_any_sync(0xffffffffu, d);
+                int pos = 0;
+                if (ok) pos = s_hist[wid][d] + __popc(grp & lt);
+                __syncwarp();
+                if (ok && (grp & lt) == 0u) s_hist[wid][d] += __popc(grp);
+                __syncwarp();
+                if (ok) { kB[pos] = key; iB[pos] = iA[i]; }
+            }
+            __syncthreads();
+            uint32_t* tk = kA; kA = kB; kB = tk;
+            uidx_t* ti = iA; iA = iB; iB = ti;
         }
+        for (int i = tid; i < n; i += POOL_THREADS) order[i] = iA[i];
     }
-    for (int i = tid; i < n; i += POOL_THREADS) order[i] = (uidx_t)(keys[i] & 0xffffffffULL);
     // where the two list entries of every edge sit (the entry in the slab of its first / second endpoint)
     for (int v = tid; v < V; v += POOL_THREADS) {
         const int start = slab_start[v], len = slab_len[v];
@@ -1081,7 +1112,7 @@ extern "C" size_t mcnn_pool_workspace_bytes(int E_in, int V, int ve_cap, int wit
     return align_up(pool_layout<Wide>(E_in, V, ve_cap, with_vs != 0).total + 64, 256);
 }
 
-extern "C" size_t mcnn_pool_smem_limit(void) { return 227 * 1024; }
+extern "C" size_t mcnn_pool_smem_limit(void) { return 227 * 1024 - 9 * 1024; }   /* dynamic part: the kernel also has ~8.6 KB of static shared memory */
 
 extern "C" int mcnn_pool_norms(const float* x, float* norms, int B, int E, int C, void* stream) {
     if (!x || !norms || B <= 0 || E <= 0 || C <= 0) return MCNN_E_BADARG;

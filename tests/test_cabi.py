@@ -39,7 +39,7 @@ def test_smem_budget_queries():
         pytest.skip('library not built yet')
     L = _lib.lib()
     lim = L.mcnn_pool_smem_limit()
-    assert lim == 227 * 1024
+    assert 200 * 1024 <= lim <= 227 * 1024                              # 227 KB per CTA minus the kernel's static shared memory
     assert L.mcnn_pool_smem_bytes(750, 252, 1500, 0) < 64 * 1024
     assert L.mcnn_pool_smem_bytes(2280, 760, 4560, 1) < lim            # human-seg / COSEG resolution fits on chip
     assert L.mcnn_pool_smem_bytes(170000, 57000, 340000, 0) > lim      # config 5 does not
