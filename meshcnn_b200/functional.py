@@ -9,6 +9,17 @@ from . import profiler
 
 # tensor-core (tcgen05, 3xTF32) path for the layers that are real dense GEMMs; MESHCNN_B200_TC=0 forces the FFMA path
 USE_TC = os.environ.get('MESHCNN_B200_TC', '1') != '0'
+# run the weight-gradient kernel of a MeshConv on a side stream, concurrently with its data-gradient kernel (both only
+# read dout / x): fills the tail waves of either kernel.  MESHCNN_B200_BWD_OVERLAP=0 keeps them on one stream.
+BWD_OVERLAP = os.environ.get('MESHCNN_B200_BWD_OVERLAP', '1') != '0'
+_SIDE = {}
+
+
+def _side_stream(device):
+    s = _SIDE.get(device)
+    if s is None:
+        s = _SIDE[device] = torch.cuda.Stream(device=device)
+    return s
 
 
 def _chk_cuda(*ts):
@@ -60,6 +71,27 @@ class MeshConvFn(torch.autograd.Function):
         st = _lib.current_stream()
         dx = dw = db = None
         tc_ok = USE_TC and Cin % 32 == 0
+        want_w = ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2])
+        fork = BWD_OVERLAP and not profiler.enabled and ctx.needs_input_grad[0] and want_w
+        if fork:
+            # every buffer is allocated on the main stream; the side stream only runs the dW kernels between two events
+            use_tc_w = tc_ok and Cout % 4 == 0
+            dw = torch.empty_like(w) if use_tc_w else torch.zeros_like(w)
+            db = None
+            if ctx.has_bias:
+                db = torch.empty(Cout, dtype=torch.float32, device=x.device) if use_tc_w else torch.zeros(Cout, dtype=torch.float32, device=x.device)
+            ws = torch.empty(L.mcnn_meshconv_bwd_weight_tc_ws(B, E, Cin, Cout), dtype=torch.float32, device=x.device) if use_tc_w else None
+            main, side = torch.cuda.current_stream(), _side_stream(x.device)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                if use_tc_w:
+                    _lib.check(L.mcnn_meshconv_bwd_weight_tc(dout.data_ptr(), x.data_ptr(), level.gemm.data_ptr(), level.ec.data_ptr(),
+                                                             dw.data_ptr(), _lib.ptr(db), ws.data_ptr(), B, E, Cin, Cout,
+                                                             side.cuda_stream), 'mcnn_meshconv_bwd_weight_tc')
+                else:
+                    _lib.check(L.mcnn_meshconv_bwd_weight(dout.data_ptr(), x.data_ptr(), level.gemm.data_ptr(), level.ec.data_ptr(),
+                                                          dw.data_ptr(), _lib.ptr(db), B, E, Cin, Cout, side.cuda_stream),
+                               'mcnn_meshconv_bwd_weight')
         if ctx.needs_input_grad[0]:
             dx = torch.zeros_like(x)
             if tc_ok and Cout % 32 == 0:
@@ -72,7 +104,9 @@ class MeshConvFn(torch.autograd.Function):
                 with profiler.span('meshconv_bwd_data', B=B, E=E, Cin=Cin, Cout=Cout):
                     _lib.check(L.mcnn_meshconv_bwd_data(dout.data_ptr(), x.data_ptr(), level.gemm.data_ptr(), level.ec.data_ptr(),
                                                         w.data_ptr(), dx.data_ptr(), B, E, Cin, Cout, st), 'mcnn_meshconv_bwd_data')
-        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+        if fork:
+            main.wait_stream(side)
+        elif want_w:
             if tc_ok and Cout % 4 == 0:
                 dw = torch.empty_like(w)
                 db = torch.empty(Cout, dtype=torch.float32, device=x.device) if ctx.has_bias else None
