@@ -79,6 +79,9 @@ int mcnn_meshconv_fwd(const float* x, const int32_t* gemm, const int32_t* ec, co
  *   wt_ws  2*5*Cin*Cout floats of scratch: a first small kernel writes the weight there as the ready-to-use B operand
  *          (TF32 head + remainder, K-major SWIZZLE_128B atoms), which every CTA then fetches with bulk copies */
 int mcnn_meshconv_tc_supported(int Cin, int Cout);
+/* The two weight images (each 2*5*Cin*Cout floats) used by mcnn_meshconv_fwd_tc* / mcnn_meshconv_bwd_data_tc*, built ahead of
+ * time (e.g. on a side stream at the start of a step); those calls then take weight = NULL and the image as wt_ws / wtb_ws. */
+int mcnn_meshconv_tc_weight_images(const float* weight, float* fwd_img, float* bwd_img, int Cin, int Cout, void* stream);
 int mcnn_meshconv_fwd_tc(const float* x, const int32_t* gemm, const int32_t* ec, const float* weight,
                          const float* bias, float* out, float* wt_ws, int B, int E, int Cin, int Cout, void* stream);
 /* the same, additionally writing signs[2][B*E][Cin] (int8: sign(f1 - f3), then sign(f2 - f4), the derivative of the two abs

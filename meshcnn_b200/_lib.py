@@ -38,6 +38,7 @@ SIGNATURES = {
     'mcnn_last_cuda_error': (ctypes.c_char_p, []),
     'mcnn_meshconv_fwd': (_c_int, [_c_vp] * 7 + [_c_int] * 4 + [_c_vp]),
     'mcnn_meshconv_tc_supported': (_c_int, [_c_int, _c_int]),
+    'mcnn_meshconv_tc_weight_images': (_c_int, [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_vp]),
     'mcnn_meshconv_fwd_tc': (_c_int, [_c_vp] * 7 + [_c_int] * 4 + [_c_vp]),
     'mcnn_meshconv_fwd_tc_signs': (_c_int, [_c_vp] * 8 + [_c_int] * 4 + [_c_vp]),
     'mcnn_meshconv_bwd_data_tc_signs': (_c_int, [_c_vp] * 8 + [_c_int] * 4 + [_c_vp]),

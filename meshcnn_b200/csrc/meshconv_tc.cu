@@ -1038,6 +1038,22 @@ using namespace mcnn;
 
 extern "C" int mcnn_meshconv_tc_supported(int Cin, int Cout) { return (Cin > 0 && Cin % 32 == 0 && Cout > 0 && Cout % 64 == 0) ? 1 : 0; }
 
+extern "C" int mcnn_meshconv_tc_weight_images(const float* weight, float* fwd_img, float* bwd_img, int Cin, int Cout, void* stream) {
+    if (!weight || (!fwd_img && !bwd_img) || !(Cin > 0 && Cin % 32 == 0 && Cout > 0 && Cout % 32 == 0)) return MCNN_E_BADARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int total = Cout * 5 * Cin;
+    int rc = MCNN_OK;
+    if (fwd_img != nullptr) {
+        weight_tc_layout_kernel<<<ceil_div(total, 256), 256, 0, st>>>(weight, fwd_img, Cin, Cout);
+        if ((rc = after_launch())) return rc;
+    }
+    if (bwd_img != nullptr) {
+        weight_tc_bwd_layout_kernel<<<ceil_div(total, 256), 256, 0, st>>>(weight, bwd_img, Cin, Cout);
+        rc = after_launch();
+    }
+    return rc;
+}
+
 extern "C" int mcnn_meshconv_fwd_tc(const float* x, const int32_t* gemm, const int32_t* ec, const float* weight,
                                     const float* bias, float* out, float* wt_ws, int B, int E, int Cin, int Cout,
                                     void* stream) {
@@ -1047,13 +1063,15 @@ extern "C" int mcnn_meshconv_fwd_tc(const float* x, const int32_t* gemm, const i
 extern "C" int mcnn_meshconv_fwd_tc_signs(const float* x, const int32_t* gemm, const int32_t* ec, const float* weight,
                                           const float* bias, float* out, float* wt_ws, int8_t* signs, int B, int E, int Cin,
                                           int Cout, void* stream) {
-    if (!x || !gemm || !ec || !weight || !out || !wt_ws || B <= 0 || E <= 0) return MCNN_E_BADARG;
+    if (!x || !gemm || !ec || !out || !wt_ws || B <= 0 || E <= 0) return MCNN_E_BADARG;
     if (!mcnn_meshconv_tc_supported(Cin, Cout)) return MCNN_E_BADARG;
     cudaStream_t st = (cudaStream_t)stream;
     const int total = Cout * 5 * Cin;
-    weight_tc_layout_kernel<<<ceil_div(total, 256), 256, 0, st>>>(weight, wt_ws, Cin, Cout);
-    int rc = after_launch();
-    if (rc) return rc;
+    int rc = MCNN_OK;
+    if (weight != nullptr) {                                 // NULL: wt_ws already holds the image (mcnn_meshconv_tc_weight_images)
+        weight_tc_layout_kernel<<<ceil_div(total, 256), 256, 0, st>>>(weight, wt_ws, Cin, Cout);
+        if ((rc = after_launch())) return rc;
+    }
     const int mtiles = ceil_div(B * E, TC_M);
     int nt = (Cout % 256 == 0) ? 256 : ((Cout % 128 == 0) ? 128 : 64);
     (void)mtiles;
@@ -1078,13 +1096,15 @@ extern "C" int mcnn_meshconv_bwd_data_tc(const float* dout, const float* x, cons
 extern "C" int mcnn_meshconv_bwd_data_tc_signs(const float* dout, const float* x, const int8_t* signs, const int32_t* gemm,
                                                const int32_t* ec, const float* weight, float* dx, float* wtb_ws, int B, int E,
                                                int Cin, int Cout, void* stream) {
-    if (!dout || (!x && !signs) || !gemm || !ec || !weight || !dx || !wtb_ws || B <= 0 || E <= 0) return MCNN_E_BADARG;
+    if (!dout || (!x && !signs) || !gemm || !ec || !dx || !wtb_ws || B <= 0 || E <= 0) return MCNN_E_BADARG;
     if (!(Cin > 0 && Cin % 32 == 0 && Cout > 0 && Cout % 32 == 0)) return MCNN_E_BADARG;
     cudaStream_t st = (cudaStream_t)stream;
     const int total = Cout * 5 * Cin;
-    weight_tc_bwd_layout_kernel<<<ceil_div(total, 256), 256, 0, st>>>(weight, wtb_ws, Cin, Cout);
-    int rc = after_launch();
-    if (rc) return rc;
+    int rc = MCNN_OK;
+    if (weight != nullptr) {                                 // NULL: wtb_ws already holds the image
+        weight_tc_bwd_layout_kernel<<<ceil_div(total, 256), 256, 0, st>>>(weight, wtb_ws, Cin, Cout);
+        if ((rc = after_launch())) return rc;
+    }
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(meshconv_bwd_data_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BdSmem::TOTAL);

@@ -13,6 +13,32 @@ USE_TC = os.environ.get('MESHCNN_B200_TC', '1') != '0'
 # read dout / x): fills the tail waves of either kernel.  MESHCNN_B200_BWD_OVERLAP=0 keeps them on one stream.
 BWD_OVERLAP = os.environ.get('MESHCNN_B200_BWD_OVERLAP', '1') != '0'
 _SIDE = {}
+STEP_TOKEN = -1          # >= 0 while a step prepared with begin_step() is being enqueued
+_NEXT_TOKEN = 0
+
+
+def begin_step(net):
+    """Start of a training step: build the tensor-core weight images of every MeshConv on the side stream, off the critical
+    path (they depend on the weights only).  Returns the step token; call end_step() after backward."""
+    global STEP_TOKEN, _NEXT_TOKEN
+    from .mesh_conv import MeshConv
+    _NEXT_TOKEN += 1
+    STEP_TOKEN = _NEXT_TOKEN
+    dev = next(net.parameters()).device
+    main, side = torch.cuda.current_stream(), _side_stream(dev)
+    side.wait_stream(main)
+    for m in net.modules():
+        if isinstance(m, MeshConv):
+            m.prepare_images(STEP_TOKEN, side)
+    return STEP_TOKEN
+
+
+def end_step():
+    """End of the step started by begin_step(): join the side stream, images are no longer valid."""
+    global STEP_TOKEN, _NEXT_TOKEN
+    for s in _SIDE.values():
+        torch.cuda.current_stream().wait_stream(s)
+    STEP_TOKEN = -1
 
 
 def _side_stream(device):
@@ -32,7 +58,7 @@ class MeshConvFn(torch.autograd.Function):
     """Fused MeshConv (mesh_conv.py:20-26) with the backward of SURVEY.md Appendix A."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, level, wt_ws):
+    def forward(ctx, x, weight, bias, level, wt_ws, img=None):
         _chk_cuda(x, weight, bias)
         B, E, Cin = x.shape
         Cout = weight.shape[0]
@@ -46,7 +72,12 @@ class MeshConvFn(torch.autograd.Function):
         if use_tc and ctx.needs_input_grad[0] and Cout % 32 == 0:
             signs = torch.empty(2, B * E, Cin, dtype=torch.int8, device=x.device)
         with profiler.span('meshconv_fwd_tc' if use_tc else 'meshconv_fwd', B=B, E=E, Cin=Cin, Cout=Cout):
-            if use_tc:
+            if use_tc and img is not None:                   # weight image prepared ahead of time on the side stream
+                torch.cuda.current_stream().wait_event(img[2])
+                _lib.check(L.mcnn_meshconv_fwd_tc_signs(x.data_ptr(), level.gemm.data_ptr(), level.ec.data_ptr(), None,
+                                                        _lib.ptr(bias), out.data_ptr(), img[0].data_ptr(), _lib.ptr(signs), B, E, Cin, Cout,
+                                                        _lib.current_stream()), 'mcnn_meshconv_fwd_tc')
+            elif use_tc:
                 _lib.check(L.mcnn_meshconv_fwd_tc_signs(x.data_ptr(), level.gemm.data_ptr(), level.ec.data_ptr(), w.data_ptr(),
                                                         _lib.ptr(bias), out.data_ptr(), wt_ws.data_ptr(), _lib.ptr(signs), B, E, Cin, Cout,
                                                         _lib.current_stream()), 'mcnn_meshconv_fwd_tc')
@@ -56,6 +87,7 @@ class MeshConvFn(torch.autograd.Function):
                                                _lib.current_stream()), 'mcnn_meshconv_fwd')
         ctx.save_for_backward(x, w)
         ctx.signs = signs
+        ctx.img = img if use_tc else None
         ctx.level = level
         ctx.has_bias = bias is not None
         return out
@@ -95,11 +127,12 @@ class MeshConvFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = torch.zeros_like(x)
             if tc_ok and Cout % 32 == 0:
-                wtb = torch.empty(2 * 5 * Cin, Cout, dtype=torch.float32, device=x.device)
+                pre = ctx.img is not None
+                wtb = ctx.img[1] if pre else torch.empty(2 * 5 * Cin, Cout, dtype=torch.float32, device=x.device)
                 with profiler.span('meshconv_bwd_data_tc', B=B, E=E, Cin=Cin, Cout=Cout):
                     _lib.check(L.mcnn_meshconv_bwd_data_tc_signs(dout.data_ptr(), x.data_ptr(), _lib.ptr(ctx.signs), level.gemm.data_ptr(),
-                                                                 level.ec.data_ptr(), w.data_ptr(), dx.data_ptr(), wtb.data_ptr(), B, E, Cin,
-                                                                 Cout, st), 'mcnn_meshconv_bwd_data_tc')
+                                                                 level.ec.data_ptr(), None if pre else w.data_ptr(), dx.data_ptr(),
+                                                                 wtb.data_ptr(), B, E, Cin, Cout, st), 'mcnn_meshconv_bwd_data_tc')
             else:
                 with profiler.span('meshconv_bwd_data', B=B, E=E, Cin=Cin, Cout=Cout):
                     _lib.check(L.mcnn_meshconv_bwd_data(dout.data_ptr(), x.data_ptr(), level.gemm.data_ptr(), level.ec.data_ptr(),
@@ -121,7 +154,7 @@ class MeshConvFn(torch.autograd.Function):
                 with profiler.span('meshconv_bwd_weight', B=B, E=E, Cin=Cin, Cout=Cout):
                     _lib.check(L.mcnn_meshconv_bwd_weight(dout.data_ptr(), x.data_ptr(), level.gemm.data_ptr(), level.ec.data_ptr(),
                                                           dw.data_ptr(), _lib.ptr(db), B, E, Cin, Cout, st), 'mcnn_meshconv_bwd_weight')
-        return dx, dw, db, None, None
+        return dx, dw, db, None, None, None
 
 
 def pool_norms(x):

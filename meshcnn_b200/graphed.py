@@ -18,6 +18,7 @@ once and replays it.  Per step the host packs the next batch of meshes into the 
 import numpy as np
 import torch
 
+from . import functional as Fn
 from .mesh import MeshBatch
 
 
@@ -71,9 +72,11 @@ class GraphedTrainStep:
             bt.reset()
         self.reducer.zero()
         self.x_dev.grad = None
+        Fn.begin_step(self.net)                     # weight images of every MeshConv, on the side stream
         out = self.net(self.x_dev, bt.meshes)
         loss = self.criterion(out, self.y_dev)
         loss.backward()
+        Fn.end_step()
         self.reducer.allreduce()
         self.opt.step_state()
         self.loss_host.copy_(loss.detach(), non_blocking=True)

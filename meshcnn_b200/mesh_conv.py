@@ -21,6 +21,7 @@ class MeshConv(nn.Module):
         self.conv = nn.Conv2d(in_channels=in_channels, out_channels=out_channels, kernel_size=(1, k), bias=bias)
         self.k = k
         self._wt_ws = None
+        self._img = None            # (fwd image, bwd image, event, step token) prepared ahead of time by prepare_images()
 
     def __call__(self, edge_f, mesh):
         return self.forward(edge_f, mesh)
@@ -28,9 +29,31 @@ class MeshConv(nn.Module):
     def forward(self, x, mesh):
         return as_bce1(self.forward_em(to_edge_major(x), MeshBatch.of(mesh, x.shape[2], x.device)))
 
+    def prepare_images(self, token, stream):
+        """Build the tensor-core weight images of this layer on `stream` (a side stream at the start of a step: the weight
+        does not depend on the activations).  forward / backward of step `token` then skip their own re-layout kernels."""
+        from . import _lib
+        from . import functional as Fn
+        w = self.conv.weight
+        cout, cin = w.shape[0], w.shape[1]
+        L = _lib.lib()
+        if not (Fn.USE_TC and w.is_cuda and L.mcnn_meshconv_tc_supported(cin, cout)):
+            return
+        if self._img is None or self._img[0].device != w.device:
+            n = 2 * 5 * cin * cout
+            self._img = [torch.empty(n, dtype=torch.float32, device=w.device), torch.empty(n, dtype=torch.float32, device=w.device),
+                         torch.cuda.Event(), -1]
+        with torch.cuda.stream(stream):
+            _lib.check(L.mcnn_meshconv_tc_weight_images(w.data_ptr(), self._img[0].data_ptr(), self._img[1].data_ptr(), cin, cout,
+                                                        stream.cuda_stream), 'mcnn_meshconv_tc_weight_images')
+            self._img[2].record(stream)
+        self._img[3] = token
+
     def forward_em(self, x_em, batch):
         """Edge-major entry used by meshcnn_b200.networks: [B, E, Cin] -> [B, E, Cout]."""
         w = self.conv.weight
         if self._wt_ws is None or self._wt_ws.device != x_em.device:
             self._wt_ws = torch.empty(2 * w.shape[1] * 5, w.shape[0], dtype=torch.float32, device=x_em.device)
-        return MeshConvFn.apply(x_em, w, self.conv.bias, batch.level(x_em.shape[1]), self._wt_ws)
+        from . import functional as Fn
+        img = self._img if (self._img is not None and self._img[3] == Fn.STEP_TOKEN and Fn.STEP_TOKEN >= 0) else None
+        return MeshConvFn.apply(x_em, w, self.conv.bias, batch.level(x_em.shape[1]), self._wt_ws, img)
