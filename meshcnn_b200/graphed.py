@@ -62,6 +62,7 @@ class GraphedTrainStep:
     # the work of one step, enqueued on the current stream
     def _enqueue(self):
         bt = self.batch
+        Fn.begin_step(self.net)                     # weight images of every MeshConv on the side stream, under the H2D copies
         if self.source == 'host':
             bt.blob.copy_(self.blob_host[:bt.nbytes], non_blocking=True)
             with torch.no_grad():
@@ -72,7 +73,6 @@ class GraphedTrainStep:
             bt.reset()
         self.reducer.zero()
         self.x_dev.grad = None
-        Fn.begin_step(self.net)                     # weight images of every MeshConv, on the side stream
         out = self.net(self.x_dev, bt.meshes)
         loss = self.criterion(out, self.y_dev)
         loss.backward()
