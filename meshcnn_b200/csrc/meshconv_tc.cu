@@ -856,71 +856,98 @@ meshconv_bwd_weight_tc_kernel(const float* __restrict__ dout, const float* __res
 
     if (warp < TC_PRODUCER_WARPS) {
         const int pt = tid;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        // Software pipeline: the gather is two dependent global loads (one-ring ids, then five rows), so the ids run three K
+        // blocks ahead and the rows / dout chunks two; every load is issued right after a hand-over (never just before the
+        // proxy fence of a store, which would wait for it).
+        struct Idx { int s0, s1, s2, s3, s4; };
+        struct Data { float4 a[4]; float4 f[5]; };
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int bk = pt >> 3, bq = pt & 7;                                // this thread's edge-in-block and channel chunk (B operand)
+        auto load_idx = [&](int kb) {
+            Idx I; I.s0 = I.s1 = I.s2 = I.s3 = I.s4 = -1;
+            const int m = mbeg + (kb << 5) + bk;
+            if (m < mend) {
+                const int b = m / E, e = m - b * E;
+                if (e >= __ldg(ec + b)) { I.s0 = I.s1 = I.s2 = I.s3 = I.s4 = b * E; }
+                else {
+                    const int4 g4 = __ldg(reinterpret_cast<const int4*>(gemm + (size_t)m * 4));
+                    I.s0 = m;
+                    I.s1 = g4.x < 0 ? -1 : b * E + g4.x; I.s2 = g4.y < 0 ? -1 : b * E + g4.y;
+                    I.s3 = g4.z < 0 ? -1 : b * E + g4.z; I.s4 = g4.w < 0 ? -1 : b * E + g4.w;
+                }
+            }
+            return I;
+        };
+        auto load_data = [&](int kb, const Idx& I) {
+            Data D;
+            const int mb = mbeg + (kb << 5);
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {                                // A: dout[m][o0 + 4q ..] for 32 edges x 32 chunks
+                const int item = pt + it * 256;
+                const int m = mb + (item >> 5), o = o0 + ((item & 31) << 2);
+                D.a[it] = (m < mend && o < Cout) ? __ldg(reinterpret_cast<const float4*>(dout + (size_t)m * Cout + o)) : z;
+            }
+            const int c = cb * 32 + (bq << 2);
+            D.f[0] = I.s0 >= 0 ? __ldg(reinterpret_cast<const float4*>(x + (size_t)I.s0 * Cin + c)) : z;
+            D.f[1] = I.s1 >= 0 ? __ldg(reinterpret_cast<const float4*>(x + (size_t)I.s1 * Cin + c)) : z;
+            D.f[2] = I.s2 >= 0 ? __ldg(reinterpret_cast<const float4*>(x + (size_t)I.s2 * Cin + c)) : z;
+            D.f[3] = I.s3 >= 0 ? __ldg(reinterpret_cast<const float4*>(x + (size_t)I.s3 * Cin + c)) : z;
+            D.f[4] = I.s4 >= 0 ? __ldg(reinterpret_cast<const float4*>(x + (size_t)I.s4 * Cin + c)) : z;
+            return D;
+        };
+        auto store_block = [&](int kb, const Data& D) {
             const int s = kb % S::STAGES;
             const uint32_t ph = (kb / S::STAGES) & 1;
             if (lane == 0) tc::mbar_wait(empty_bar + s, ph ^ 1);      // one poller per warp
             __syncwarp();
-            unsigned char* a_hi = smem + s * S::STAGE_BYTES;
-            unsigned char* a_lo = a_hi + S::A_BYTES;
-            unsigned char* b_hi = a_lo + S::A_BYTES;
-            unsigned char* b_lo = b_hi + S::B_BYTES;
-            const int mb = mbeg + (kb << 5);
-            // A: dout[m][o0 + 4q .. ] for 32 edges x 32 chunks
+            const uint32_t a_hi = tc::smem_u32(smem + s * S::STAGE_BYTES);
+            const uint32_t a_lo = a_hi + S::A_BYTES;
+            const uint32_t b_hi = a_lo + S::A_BYTES;
+            const uint32_t b_lo = b_hi + S::B_BYTES;
 #pragma unroll
-            for (int it = 0; it < (32 * 32) / 256; ++it) {
+            for (int it = 0; it < 4; ++it) {
                 const int item = pt + it * 256;
-                const int k = item >> 5, q = item & 31;
-                const int m = mb + k, o = o0 + (q << 2);
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (m < mend && o < Cout) v = __ldg(reinterpret_cast<const float4*>(dout + (size_t)m * Cout + o));
                 float4 hi, lo;
-                tc::split4(v, hi, lo);
-                const uint32_t off = tc::sw128_mn_off(k, q, S::LBO);
-                tc::sts128(tc::smem_u32(a_hi) + off, hi);
-                tc::sts128(tc::smem_u32(a_lo) + off, lo);
+                tc::split4(D.a[it], hi, lo);
+                const uint32_t off = tc::sw128_mn_off(item >> 5, item & 31, S::LBO);
+                tc::sts128(a_hi + off, hi);
+                tc::sts128(a_lo + off, lo);
             }
-            // B: G rows for 32 edges x 8 channel chunks (one item per thread)
-            {
-                const int k = pt >> 3, q = pt & 7;
-                const int m = mb + k;
-                const int c = cb * 32 + (q << 2);
-                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-                float4 f0 = z, f1 = z, f2 = z, f3 = z, f4 = z;
-                if (m < mend) {
-                    const int b = m / E, e = m - b * E;
-                    int s0, s1, s2, s3, s4;
-                    if (e >= __ldg(ec + b)) { s0 = s1 = s2 = s3 = s4 = b * E; }
-                    else {
-                        const int4 g4 = __ldg(reinterpret_cast<const int4*>(gemm + (size_t)m * 4));
-                        s0 = m;
-                        s1 = g4.x < 0 ? -1 : b * E + g4.x; s2 = g4.y < 0 ? -1 : b * E + g4.y;
-                        s3 = g4.z < 0 ? -1 : b * E + g4.z; s4 = g4.w < 0 ? -1 : b * E + g4.w;
-                    }
-                    f0 = __ldg(reinterpret_cast<const float4*>(x + (size_t)s0 * Cin + c));
-                    if (s1 >= 0) f1 = __ldg(reinterpret_cast<const float4*>(x + (size_t)s1 * Cin + c));
-                    if (s2 >= 0) f2 = __ldg(reinterpret_cast<const float4*>(x + (size_t)s2 * Cin + c));
-                    if (s3 >= 0) f3 = __ldg(reinterpret_cast<const float4*>(x + (size_t)s3 * Cin + c));
-                    if (s4 >= 0) f4 = __ldg(reinterpret_cast<const float4*>(x + (size_t)s4 * Cin + c));
-                }
-                float4 gk[5];
-                gk[0] = f0;
-                gk[1] = make_float4(f1.x + f3.x, f1.y + f3.y, f1.z + f3.z, f1.w + f3.w);
-                gk[2] = make_float4(f2.x + f4.x, f2.y + f4.y, f2.z + f4.z, f2.w + f4.w);
-                gk[3] = make_float4(fabsf(f1.x - f3.x), fabsf(f1.y - f3.y), fabsf(f1.z - f3.z), fabsf(f1.w - f3.w));
-                gk[4] = make_float4(fabsf(f2.x - f4.x), fabsf(f2.y - f4.y), fabsf(f2.z - f4.z), fabsf(f2.w - f4.w));
+            const float4 f0 = D.f[0], f1 = D.f[1], f2 = D.f[2], f3 = D.f[3], f4 = D.f[4];
+            float4 gk[5];
+            gk[0] = f0;
+            gk[1] = make_float4(f1.x + f3.x, f1.y + f3.y, f1.z + f3.z, f1.w + f3.w);
+            gk[2] = make_float4(f2.x + f4.x, f2.y + f4.y, f2.z + f4.z, f2.w + f4.w);
+            gk[3] = make_float4(fabsf(f1.x - f3.x), fabsf(f1.y - f3.y), fabsf(f1.z - f3.z), fabsf(f1.w - f3.w));
+            gk[4] = make_float4(fabsf(f2.x - f4.x), fabsf(f2.y - f4.y), fabsf(f2.z - f4.z), fabsf(f2.w - f4.w));
 #pragma unroll
-                for (int k5 = 0; k5 < 5; ++k5) {
-                    float4 hi, lo;
-                    tc::split4(gk[k5], hi, lo);
-                    const uint32_t off = tc::sw128_mn_off(k, k5 * 8 + q, S::LBO);
-                    tc::sts128(tc::smem_u32(b_hi) + off, hi);
-                    tc::sts128(tc::smem_u32(b_lo) + off, lo);
-                }
+            for (int k5 = 0; k5 < 5; ++k5) {
+                float4 hi, lo;
+                tc::split4(gk[k5], hi, lo);
+                const uint32_t off = tc::sw128_mn_off(bk, k5 * 8 + bq, S::LBO);
+                tc::sts128(b_hi + off, hi);
+                tc::sts128(b_lo + off, lo);
             }
             tc::fence_proxy_async_smem();                                  // every writer fences its own stores ...
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(full_bar + s);                  // ... then one arrival per warp
+        };
+        if (num_kb > 0) {
+            Data D0 = load_data(0, load_idx(0));
+            Data D1;
+            if (num_kb > 1) D1 = load_data(1, load_idx(1));
+            Idx In;
+            if (num_kb > 2) In = load_idx(2);
+            for (int kb = 0; kb < num_kb; kb += 2) {
+                store_block(kb, D0);
+                if (kb + 2 < num_kb) D0 = load_data(kb + 2, In);
+                if (kb + 3 < num_kb) In = load_idx(kb + 3);
+                if (kb + 1 < num_kb) {
+                    store_block(kb + 1, D1);
+                    if (kb + 3 < num_kb) D1 = load_data(kb + 3, In);
+                    if (kb + 4 < num_kb) In = load_idx(kb + 4);
+                }
+            }
         }
         // ---- epilogue: slab partial -> ws[split][o][c][k5] ---------------------------------------------------------
         const int lane_grp = warp & 3;
