@@ -86,7 +86,7 @@ __host__ __device__ inline PoolLayout pool_layout(int n, int V, int ve_cap, bool
     L.slab_next = o; o += sizeof(uidx_t) * (size_t)V; o = align_up(o, 16);
     L.chain_tail = o; o += sizeof(uidx_t) * (size_t)V; o = align_up(o, 16);
     L.vmask = o; o += (size_t)V; o = align_up(o, 16);
-    L.ve = o; o += sizeof(uidx_t) * (size_t)ve_cap; o = align_up(o, 16);
+    L.ve = o; o += sizeof(uidx_t) * ((size_t)ve_cap + 2 * (size_t)n); o = align_up(o, 16);   // + room for re-packed lists
     L.eposa = o; o += sizeof(uidx_t) * (size_t)n; o = align_up(o, 16);
     L.eposb = o; o += sizeof(uidx_t) * (size_t)n; o = align_up(o, 16);
     L.ulog_cap = 2 * n + 16;                     // every union's source dies within the same attempt: <= 2 per dead edge
@@ -137,9 +137,10 @@ __device__ __forceinline__ int block_scan_excl(int v, int* scratch, int& total) 
 // entries at a time and the collapse thread waits for the answer.
 template <class P>
 struct WarpCtx {
-    typename P::uidx_t *ve, *slab_start, *slab_len, *slab_next, *chain_tail, *rep;
+    typename P::uidx_t *ve, *slab_start, *slab_len, *slab_next, *chain_tail, *rep, *eposa, *eposb;
     typename P::pair_t* evp;
     uint32_t* stamp;
+    int bump, bump_end;        // free room behind the lists (entries), used by wop_repack
 };
 
 enum { WOP_EXIT = 0, WOP_ONE_RING = 1, WOP_REMOVE_SCAN = 2 };
@@ -171,6 +172,47 @@ __device__ __forceinline__ void edge_ends(const typename P::pair_t* evp, typenam
     const int ra = (int)rep[a], rb = (int)rep[b];                 // both loads in flight before either branch
     v0 = (ra == a) ? a : uf_find(rep, a);
     v1 = (rb == b) ? b : uf_find(rep, b);
+}
+
+// A list that has absorbed other lists (`extend`) is a chain of slabs; every later walk pays one dependent round trip per
+// slab.  While the collapse thread waits for a one-ring answer anyway, the helper warp re-packs such a chain into ONE slab in
+// the free room behind the lists: order preserved, tombstones dropped, the positions of the moved entries (epos) updated.
+template <class P>
+__device__ __forceinline__ void wop_repack(WarpCtx<P>& w, int lane, int v) {
+    if ((unsigned)w.slab_next[v] == P::NIL) return;
+    int need = 0;
+    for (unsigned s = (unsigned)v; s != P::NIL; s = (unsigned)w.slab_next[s]) need += (int)w.slab_len[s];
+    if (w.bump + need > w.bump_end) return;                                  // no room left: keep the chain
+    const unsigned lt = (1u << lane) - 1u;
+    const int out = w.bump;
+    int total = 0;
+    for (unsigned s = (unsigned)v; s != P::NIL; s = (unsigned)w.slab_next[s]) {
+        const int start = w.slab_start[s], len = w.slab_len[s];
+        for (int base = 0; base < len; base += 32) {
+            const int i = base + lane;
+            const unsigned x = (i < len) ? (unsigned)w.ve[start + i] : P::NIL;
+            const bool live = x != P::NIL;
+            const unsigned m = __ballot_sync(0xffffffffu, live);
+            if (live) {
+                const int dst = out + total + __popc(m & lt);
+                w.ve[dst] = (typename P::uidx_t)x;
+                if (x != 0u) {
+                    if ((int)w.eposa[x] == start + i) w.eposa[x] = (typename P::uidx_t)dst;
+                    else if ((int)w.eposb[x] == start + i) w.eposb[x] = (typename P::uidx_t)dst;
+                }
+            }
+            total += __popc(m);
+        }
+    }
+    __syncwarp();
+    if (lane == 0) {
+        w.slab_start[v] = (typename P::uidx_t)out;
+        w.slab_len[v] = (typename P::uidx_t)total;
+        w.slab_next[v] = (typename P::uidx_t)P::NIL;
+        w.chain_tail[v] = (typename P::uidx_t)v;
+    }
+    w.bump = out + total;
+    __syncwarp();
 }
 
 // __is_one_ring_valid (mesh_pool.py:95-100); the lists may hold stale / dead edge ids.  stamp[w] = tagA marks w as an
@@ -271,7 +313,7 @@ __device__ __forceinline__ bool wop_list_remove(const WarpCtx<P>& w, int lane, i
 
 // Service loop of the helper warp: executes the posted operations in order until WOP_EXIT.
 template <class P>
-__device__ void helper_warp_loop(const WarpCtx<P>& w, WorkQueue* q, int lane, long long* hprof) {
+__device__ void helper_warp_loop(WarpCtx<P>& w, WorkQueue* q, int lane, long long* hprof) {
     volatile int* vhead = &q->head;
     int seq = 0;                                             // operations finished so far
     while (true) {
@@ -288,6 +330,8 @@ __device__ void helper_warp_loop(const WarpCtx<P>& w, WorkQueue* q, int lane, lo
 #endif
         int r;
         if (rq.x == WOP_ONE_RING) {
+            wop_repack<P>(w, lane, rq.y);
+            wop_repack<P>(w, lane, rq.z);
             r = wop_one_ring<P>(w, lane, rq.y, rq.z, (uint32_t)rq.w, hprof ? hprof + 3 : nullptr);
         } else {                                             // WOP_REMOVE_SCAN: x leaves ve[a], then ve[b] (mesh.py:42-48)
             r = wop_list_remove<P>(w, lane, rq.z, rq.y) ? 1 : 0;
@@ -739,7 +783,8 @@ __global__ void __launch_bounds__(P::THREADS, 1) pool_collapse_kernel(const mcnn
     } else if (tid >= 32 && tid < 64) {
         WarpCtx<P> w;
         w.ve = ve; w.slab_start = slab_start; w.slab_len = slab_len; w.slab_next = slab_next; w.chain_tail = chain_tail;
-        w.rep = rep; w.evp = evp; w.stamp = stamp;
+        w.rep = rep; w.evp = evp; w.stamp = stamp; w.eposa = eposa; w.eposb = eposb;
+        w.bump = min(g_ve_ptr[V], a.ve_cap); w.bump_end = a.ve_cap + 2 * E_in;
         helper_warp_loop<P>(w, &s_queue, tid - 32, clk ? clk + 13 : nullptr);
     }
     __syncthreads();
