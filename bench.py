@@ -150,19 +150,26 @@ class ClockSampler:
         self._t = threading.Thread(target=self._run, daemon=True)
         self._t.start()
 
-    def _run(self):
+    def sample(self):
+        """One sample, callable from the main thread between timed steps (the background thread can be starved of the GIL
+        by a tight replay loop)."""
         if self._h is None:
-            return
+            return False
         nv = self._nv
+        try:
+            self.sm.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+            r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
+            for name, bit in self.REASONS.items():
+                if r & bit:
+                    self.reasons.add(name)
+        except Exception as e:                                       # noqa: BLE001
+            self.err = 'nvml: %s' % e
+            return False
+        return True
+
+    def _run(self):
         while not self._stop.is_set():
-            try:
-                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
-                r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
-                for name, bit in self.REASONS.items():
-                    if r & bit:
-                        self.reasons.add(name)
-            except Exception as e:                                   # noqa: BLE001
-                self.err = 'nvml: %s' % e
+            if not self.sample():
                 return
             time.sleep(0.002)
 
@@ -341,6 +348,8 @@ def main():
         step()
         b.record()
         evs.append((a, b))
+        if sampler is not None and (len(evs) & 3) == 0:
+            sampler.sample()                                            # GPU is busy with this step; the call is not timed
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
