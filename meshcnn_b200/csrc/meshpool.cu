@@ -219,19 +219,29 @@ __device__ __forceinline__ void wop_repack(WarpCtx<P>& w, int lane, int v) {
 // endpoint seen from v0; the lane that flips it to tagB counts it once.  The first slab of both lists (the whole list
 // unless a vertex was merged within this level) is fetched and resolved together, so the two dependent load chains overlap.
 template <class P>
-__device__ __forceinline__ int wop_one_ring(const WarpCtx<P>& w, int lane, int v0, int v1, uint32_t tagA, long long* hp) {
+__device__ __forceinline__ int wop_one_ring(WarpCtx<P>& w, int lane, int v0, int v1, uint32_t tagA, long long* hp) {
     const uint32_t tagB = tagA | 1u;
 #ifdef MCNN_POOL_PROF
     const long long t0_ = clock64();
 #endif
+    // both lists' descriptors in one round trip; a chained list is re-packed first (rare)
+    if ((unsigned)w.slab_next[v0] != P::NIL) wop_repack<P>(w, lane, v0);
+    if ((unsigned)w.slab_next[v1] != P::NIL) wop_repack<P>(w, lane, v1);
     const int start0 = w.slab_start[v0], len0 = w.slab_len[v0];
     const int start1 = w.slab_start[v1], len1 = w.slab_len[v1];
     const unsigned next0 = (unsigned)w.slab_next[v0], next1 = (unsigned)w.slab_next[v1];
     const unsigned x0 = (lane < len0) ? (unsigned)w.ve[start0 + lane] : P::NIL;
     const unsigned x1 = (lane < len1) ? (unsigned)w.ve[start1 + lane] : P::NIL;
-    int a0 = 0, b0 = 0, a1 = 0, b1 = 0;
-    if (x0 != P::NIL) edge_ends<P>(w.evp, w.rep, (int)x0, a0, b0);
-    if (x1 != P::NIL) edge_ends<P>(w.evp, w.rep, (int)x1, a1, b1);
+    // the two dependent chains (entry -> endpoints -> union-find roots) run side by side: unconditional loads with a safe index
+    const typename P::pair_t w0 = w.evp[x0 != P::NIL ? x0 : 0u], w1 = w.evp[x1 != P::NIL ? x1 : 0u];
+    int a0 = pr_lo<P>(w0), b0 = pr_hi<P>(w0), a1 = pr_lo<P>(w1), b1 = pr_hi<P>(w1);
+    {
+        const int ra0 = (int)w.rep[a0], rb0 = (int)w.rep[b0], ra1 = (int)w.rep[a1], rb1 = (int)w.rep[b1];
+        if (ra0 != a0) a0 = uf_find(w.rep, a0);
+        if (rb0 != b0) b0 = uf_find(w.rep, b0);
+        if (ra1 != a1) a1 = uf_find(w.rep, a1);
+        if (rb1 != b1) b1 = uf_find(w.rep, b1);
+    }
     if (x0 != P::NIL) { w.stamp[a0] = tagA; w.stamp[b0] = tagA; }
 #ifdef MCNN_POOL_PROF
     const long long t1_ = clock64();
@@ -330,8 +340,6 @@ __device__ void helper_warp_loop(WarpCtx<P>& w, WorkQueue* q, int lane, long lon
 #endif
         int r;
         if (rq.x == WOP_ONE_RING) {
-            wop_repack<P>(w, lane, rq.y);
-            wop_repack<P>(w, lane, rq.z);
             r = wop_one_ring<P>(w, lane, rq.y, rq.z, (uint32_t)rq.w, hprof ? hprof + 3 : nullptr);
         } else {                                             // WOP_REMOVE_SCAN: x leaves ve[a], then ve[b] (mesh.py:42-48)
             r = wop_list_remove<P>(w, lane, rq.z, rq.y) ? 1 : 0;
