@@ -553,8 +553,11 @@ struct Collapse {
     }
 
     // __pool_side (mesh_pool.py:102-113)
-    __device__ void pool_side(int e, int side) {
-        const Face f = face_info(e, side);
+    __device__ void pool_side(int e, int side) { pool_side(e, side, face_info(e, side)); }
+
+    // the same with the face record already fetched (the caller reads it while it waits for the one-ring answer)
+    __device__ void pool_side(int e, int side, const Face f) {
+        (void)side;
         const int base = f.sa - (f.sa & 1);
         redirect(f.ka, base, f.okb0, sides[4 * f.kb + f.osb]);
         redirect(f.ka, base + 1, f.okb1, sides[4 * f.kb + f.osb + 1]);     // read after the first rewiring, as the reference does
@@ -590,10 +593,12 @@ struct Collapse {
         PROF_T(2, one_ring_request(e));
         PROF_T(1, r = clean_side(e, 0));
         if (r) PROF_T(1, r = clean_side(e, 2) ? true : (side2 = true, false));
+        // nothing writes the one-ring tables between here and __pool_side(0): fetch its face record under the wait
+        const Face f0 = r ? face_info(e, 0) : Face();
         const bool ring_ok = wait_result() == 2;             // always collected: the ring has one result slot
         if (!r) return side2 ? MCNN_POP_REJ_SIDE2 : MCNN_POP_REJ_SIDE0;
         if (!ring_ok) return MCNN_POP_REJ_ONE_RING;
-        PROF_T(3, pool_side(e, 0));
+        PROF_T(3, pool_side(e, 0, f0));
         if (status) return MCNN_POP_COLLAPSED;
         PROF_T(3, pool_side(e, 2));
         if (status) return MCNN_POP_COLLAPSED;
