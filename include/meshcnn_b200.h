@@ -89,6 +89,17 @@ int mcnn_meshconv_fwd_tc(const float* x, const int32_t* gemm, const int32_t* ec,
 int mcnn_meshconv_fwd_tc_signs(const float* x, const int32_t* gemm, const int32_t* ec, const float* weight,
                                const float* bias, float* out, float* wt_ws, int8_t* signs, int B, int E, int Cin, int Cout,
                                void* stream);
+/* the same computation as mcnn_meshconv_fwd_tc_signs by a persistent kernel: the (128-edge tile, 32-wide K block) units
+ * are spread evenly over at most one CTA per SM ("stream-K"), so a tile count just above a multiple of the SM count does
+ * not pay for a nearly empty last wave.  A tile cut between CTAs is summed in a fixed order (deterministic; it differs from
+ * the one-CTA-per-tile kernel by fp32 rounding of that sum only).  sk_ws: mcnn_meshconv_fwd_tc_sk_ws() bytes of device memory,
+ * zeroed ONCE by the caller after allocation (the kernel leaves it reusable), not shared by concurrently running launches. */
+size_t mcnn_meshconv_fwd_tc_sk_ws(void);
+int mcnn_meshconv_fwd_tc_sk(const float* x, const int32_t* gemm, const int32_t* ec, const float* weight,
+                            const float* bias, float* out, float* wt_ws, int8_t* signs, void* sk_ws, int B, int E, int Cin,
+                            int Cout, void* stream);
+/* diagnostics only: force the grid size of mcnn_meshconv_fwd_tc_sk (0 = one CTA per SM) */
+int mcnn_debug_set_tc_sk_ctas(int n);
 
 /* diagnostics only: bottleneck-attribution knobs of the tensor-core forward kernel (0 = normal operation) */
 int mcnn_debug_set_tc(int flags);

@@ -338,6 +338,287 @@ meshconv_fwd_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ 
 }
 
 // =============================================================================================================
+// Forward, persistent "stream-K" form.  The plain kernel above launches one CTA per 128-edge tile, and the tile counts of
+// this workload sit just above a multiple of the SM count (150 / 225 / 300 / 375 tiles on 148 SMs): the last, nearly
+// empty wave costs as much as a full one.  Here the work is cut into (tile, K block) units, unit u = tile * num_kb + kb,
+// and CTA c of G <= #SMs resident CTAs takes the contiguous range [total*c/G, total*(c+1)/G): a tail of one tile, whole
+// tiles, a head of the next.  A CTA that starts in the middle of a tile stores its partial accumulator to its own slot
+// of a workspace and raises its flag; the CTA that holds the tile's K block 0 (the owner: it reaches that tile LAST, the
+// others reach it FIRST, so it practically never waits) adds the partials in ascending CTA order, the bias, and writes
+// the tile.  Deterministic: the split depends only on the shape and the grid.  The owner lowers each flag it consumed,
+// so the workspace needs zeroing once, at allocation; one workspace must not be shared by concurrent launches.
+// =============================================================================================================
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+constexpr int SK_FLAG_BYTES = 4096;
+constexpr int SK_MAX_CTAS = 256;                 // workspace: flags + one 128 x 256 fp32 partial per CTA
+
+template <int N_TILE>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+meshconv_fwd_tc_sk_kernel(const float* __restrict__ x, const int32_t* __restrict__ gemm, const int32_t* __restrict__ ec,
+                          const float* __restrict__ wt, const float* __restrict__ bias, float* __restrict__ out,
+                          int8_t* __restrict__ signs, float* part, int* flags, int B, int E, int Cin, int Cout) {
+    using S = TcSmem<N_TILE>;
+    constexpr int PW = TC_PRODUCER_WARPS, PT = PW * 32, IT0 = (TC_M * 8) / PT, ITP = (TC_M * 4) / PT;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    int (*nb)[5] = reinterpret_cast<int (*)[5]>(smem + S::NB_OFF);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
+    uint64_t* empty_bar = full_bar + S::STAGES;
+    uint64_t* accum_bar = empty_bar + S::STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int M = B * E;
+    const int K = 5 * Cin;
+    const int num_kb = K >> 5;
+    const int ntn = Cout / N_TILE;
+    const long long total = (long long)ceil_div(M, TC_M) * ntn * num_kb;
+    const int G = gridDim.x, cta = blockIdx.x;
+    const long long u_begin = total * cta / G, u_end = total * (cta + 1) / G;
+
+    if (warp == PW) {
+        if (lane == 0) {
+            for (int s = 0; s < S::STAGES; ++s) { tc::mbar_init(full_bar + s, PW); tc::mbar_init(empty_bar + s, 1); }
+            tc::mbar_init(accum_bar, 1);
+            tc::fence_barrier_init();
+        }
+        __syncwarp();
+        tc::tmem_alloc<N_TILE>(tmem_slot);
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < PW) {
+        const int pt = tid;
+        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        struct Regs { float4 a[IT0]; };
+        uint32_t g = 0;                                          // K blocks this CTA has pushed through the stage ring
+        int seg = 0;
+        for (long long u = u_begin; u < u_end; ++seg) {
+            const int tile = (int)(u / num_kb), ka = (int)(u - (long long)tile * num_kb);
+            const int ke = (int)min((long long)num_kb, ka + (u_end - u));
+            const int mt = tile / ntn, nt = tile - mt * ntn;
+            const int m0 = mt * TC_M, n0 = nt * N_TILE;
+            // ---- gather table of this tile (no thread can still be reading the previous one: every warp handed over its
+            // last K block before anyone got past that segment's accumulator barrier) ----
+            for (int i = tid; i < TC_M * 5; i += PT) {
+                const int r = i / 5, k = i - r * 5;
+                const int m = m0 + r;
+                int idx = -1;
+                if (m < M) {
+                    const int b = m / E, e = m - b * E;
+                    if (e >= __ldg(ec + b)) idx = b * E;
+                    else if (k == 0) idx = m;
+                    else { const int gg = __ldg(gemm + (size_t)m * 4 + (k - 1)); idx = gg < 0 ? -1 : b * E + gg; }
+                }
+                nb[r][k] = idx;
+            }
+            named_bar_sync(1, PT);
+            int src0[IT0], srcA[ITP][2], srcB[ITP][2];
+#pragma unroll
+            for (int it = 0; it < IT0; ++it) src0[it] = nb[(pt + it * PT) >> 3][0];
+#pragma unroll
+            for (int it = 0; it < ITP; ++it) {
+                const int r = pair_item_row(pt + it * PT);
+                srcA[it][0] = nb[r][1]; srcB[it][0] = nb[r][3];
+                srcA[it][1] = nb[r][2]; srcB[it][1] = nb[r][4];
+            }
+            auto load_block = [&](int kb, Regs& R) {
+                const int cb = kb / 5, blk = kb - cb * 5;
+                if (blk == 0) {
+                    const int c = cb * 32 + ((pt & 7) << 2);
+#pragma unroll
+                    for (int it = 0; it < IT0; ++it)
+                        R.a[it] = src0[it] >= 0 ? __ldg(reinterpret_cast<const float4*>(x + (size_t)src0[it] * Cin + c)) : zero4;
+                } else {
+                    const int pr = (blk <= 2) ? 0 : 1;
+                    const int c = cb * 32 + (((blk - 1) & 1) << 4) + ((pt & 3) << 2);
+#pragma unroll
+                    for (int it = 0; it < ITP; ++it) {
+                        const int sa = pr ? srcA[it][1] : srcA[it][0], sb = pr ? srcB[it][1] : srcB[it][0];
+                        R.a[2 * it] = sa >= 0 ? __ldg(reinterpret_cast<const float4*>(x + (size_t)sa * Cin + c)) : zero4;
+                        R.a[2 * it + 1] = sb >= 0 ? __ldg(reinterpret_cast<const float4*>(x + (size_t)sb * Cin + c)) : zero4;
+                    }
+                }
+            };
+            auto store_block = [&](int kb, const Regs& R) {
+                const int s = g % S::STAGES;
+                const uint32_t ph = (g / S::STAGES) & 1;
+                ++g;
+                if (lane == 0) tc::mbar_wait(empty_bar + s, ph ^ 1);
+                __syncwarp();
+                const uint32_t a_hi = tc::smem_u32(smem + s * S::STAGE_BYTES);
+                const uint32_t a_lo = a_hi + S::A_BYTES;
+                const int blk = kb % 5;
+                float4 hi, lo;
+                if (tid == 0) {
+                    unsigned char* b_hi = smem + s * S::STAGE_BYTES + 2 * S::A_BYTES;
+                    tc::mbar_expect_tx(full_bar + s, 2 * S::B_BYTES);
+                    const float* src = wt + ((size_t)kb * Cout + n0) * 32;
+                    tc::bulk_g2s(b_hi, src, S::B_BYTES, full_bar + s);
+                    tc::bulk_g2s(b_hi + S::B_BYTES, src + (size_t)Cout * K, S::B_BYTES, full_bar + s);
+                }
+                if (blk == 0) {
+#pragma unroll
+                    for (int it = 0; it < IT0; ++it) {
+                        const int item = pt + it * PT;
+                        const uint32_t off = tc::sw128_off(item >> 3, item & 7);
+                        tc::split4(R.a[it], hi, lo);
+                        tc::sts128(a_hi + off, hi);
+                        tc::sts128(a_lo + off, lo);
+                    }
+                } else {
+#pragma unroll
+                    for (int it = 0; it < ITP; ++it) {
+                        const int item = pt + it * PT;
+                        const int r = pair_item_row(item), q = item & 3;
+                        const float4 fa = R.a[2 * it], fb = R.a[2 * it + 1];
+                        const float4 sum = make_float4(fa.x + fb.x, fa.y + fb.y, fa.z + fb.z, fa.w + fb.w);
+                        const float4 dd = make_float4(fa.x - fb.x, fa.y - fb.y, fa.z - fb.z, fa.w - fb.w);
+                        const float4 dif = make_float4(fabsf(dd.x), fabsf(dd.y), fabsf(dd.z), fabsf(dd.w));
+                        if (signs != nullptr && nt == 0 && m0 + r < M) {
+                            const int c_ = (kb / 5) * 32 + (((blk - 1) & 1) << 4) + (q << 2);
+                            const size_t so = ((size_t)(blk <= 2 ? 0 : 1) * M + (m0 + r)) * Cin + c_;
+                            *reinterpret_cast<char4*>(signs + so) = make_char4((signed char)sgn(dd.x), (signed char)sgn(dd.y), (signed char)sgn(dd.z), (signed char)sgn(dd.w));
+                        }
+                        tc::split4(sum, hi, lo);
+                        uint32_t off = tc::sw128_off(r, q);
+                        tc::sts128(a_hi + off, hi);
+                        tc::sts128(a_lo + off, lo);
+                        tc::split4(dif, hi, lo);
+                        off = tc::sw128_off(r, q + 4);
+                        tc::sts128(a_hi + off, hi);
+                        tc::sts128(a_lo + off, lo);
+                    }
+                }
+                tc::fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(full_bar + s);
+            };
+            {
+                Regs R0, R1, R2;
+                load_block(ka, R0);
+                if (ka + 1 < ke) load_block(ka + 1, R1);
+                if (ka + 2 < ke) load_block(ka + 2, R2);
+                for (int kb = ka; kb < ke; kb += 3) {
+                    store_block(kb, R0);
+                    if (kb + 3 < ke) load_block(kb + 3, R0);
+                    if (kb + 1 < ke) {
+                        store_block(kb + 1, R1);
+                        if (kb + 4 < ke) load_block(kb + 4, R1);
+                    }
+                    if (kb + 2 < ke) {
+                        store_block(kb + 2, R2);
+                        if (kb + 5 < ke) load_block(kb + 5, R2);
+                    }
+                }
+            }
+            // ---- epilogue of the segment ----
+            const bool head = ka == 0, last = ke == num_kb;
+            int n_parts = 0;
+            if (head && !last) {
+                // owner of a tile that other CTAs finish: CTAs cta+1 .. whose range starts inside this tile
+                const long long tile_end = (long long)(tile + 1) * num_kb;
+                for (int c2 = cta + 1; c2 < G && total * c2 / G < tile_end; ++c2) ++n_parts;
+                if (tid == 0) {
+                    for (int j = 1; j <= n_parts; ++j) {
+                        volatile int* f = flags + cta + j;
+                        while (*f == 0) __nanosleep(64);
+                        *f = 0;
+                    }
+                    __threadfence();
+                }
+                named_bar_sync(2, PT);
+            }
+            tc::mbar_wait(accum_bar, seg & 1);
+            tc::tc_fence_after();
+            const int lane_grp = warp & 3;
+            const int r = lane_grp * 32 + lane;
+            const int m = m0 + r;
+            constexpr int COLS_PER_WARP = N_TILE / (PW / 4);
+            const int col0 = (warp >> 2) * COLS_PER_WARP;
+#pragma unroll 1
+            for (int cc = 0; cc < COLS_PER_WARP; cc += 32) {
+                float v[32];
+                tc::tmem_ld32(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(col0 + cc), v);
+                if (m < M) {
+                    if (!head) {
+                        float4* o = reinterpret_cast<float4*>(part + ((size_t)cta * TC_M + r) * N_TILE + col0 + cc);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) __stcg(o + j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+                    } else {
+                        for (int p = 1; p <= n_parts; ++p) {
+                            const float4* q4 = reinterpret_cast<const float4*>(part + ((size_t)(cta + p) * TC_M + r) * N_TILE + col0 + cc);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float4 t = __ldcg(q4 + j);
+                                v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+                            }
+                        }
+                        const int n = n0 + col0 + cc;
+                        float* o = out + (size_t)m * Cout + n;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            float4 bv = zero4;
+                            if (bias != nullptr) bv = __ldg(reinterpret_cast<const float4*>(bias + n + j));
+                            *reinterpret_cast<float4*>(o + j) = make_float4(v[j] + bv.x, v[j + 1] + bv.y, v[j + 2] + bv.z, v[j + 3] + bv.w);
+                        }
+                    }
+                }
+            }
+            tc::tc_fence_before();
+            if (!head) {                                         // publish the partial: every writer fences, then one flag store
+                __threadfence();
+                named_bar_sync(2, PT);
+                if (tid == 0) { volatile int* f = flags + cta; *f = 1; }
+            }
+            u += ke - ka;
+        }
+    } else {
+        // ======================================== MMA issuer ========================================================
+        constexpr uint32_t idesc = tc::make_idesc_tf32(N_TILE);
+        uint32_t g = 0;
+        for (long long u = u_begin; u < u_end;) {
+            const int tile = (int)(u / num_kb), ka = (int)(u - (long long)tile * num_kb);
+            const int ke = (int)min((long long)num_kb, ka + (u_end - u));
+            for (int kb = ka; kb < ke; ++kb, ++g) {
+                const int s = g % S::STAGES;
+                const uint32_t ph = (g / S::STAGES) & 1;
+                tc::mbar_wait(full_bar + s, ph);
+                tc::tc_fence_after();
+                if (tc::elect_one()) {
+                    const uint32_t a_hi = tc::smem_u32(smem + s * S::STAGE_BYTES);
+                    const uint32_t a_lo = a_hi + S::A_BYTES;
+                    const uint32_t b_hi = a_lo + S::A_BYTES;
+                    const uint32_t b_lo = b_hi + S::B_BYTES;
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const uint64_t dah = tc::make_desc_sw128(a_hi + kk * 32), dal = tc::make_desc_sw128(a_lo + kk * 32);
+                        const uint64_t dbh = tc::make_desc_sw128(b_hi + kk * 32), dbl = tc::make_desc_sw128(b_lo + kk * 32);
+                        tc::mma_tf32(tmem_base, dah, dbh, idesc, (kb != ka) || (kk != 0));
+                        tc::mma_tf32(tmem_base, dah, dbl, idesc, 1);
+                        tc::mma_tf32(tmem_base, dal, dbh, idesc, 1);
+                    }
+                    tc::mma_commit(empty_bar + s);
+                    if (kb == ke - 1) tc::mma_commit(accum_bar);
+                }
+                __syncwarp();
+            }
+            u += ke - ka;
+        }
+        tc::tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == PW) {
+        tc::tc_fence_after();
+        tc::tmem_dealloc<N_TILE>(tmem_base);
+    }
+}
+
+// =============================================================================================================
 // Forward on a CTA PAIR (tcgen05 cta_group::2): two CTAs of one cluster compute 256 edges x 256 output channels.  Each CTA
 // gathers / builds the A operand of its own 128 edges and fetches only HALF of the weight tile (128 of the 256 rows of B);
 // the pair's tensor cores share both halves.  Per SM this halves the B traffic from L2 and the B reads from shared memory
@@ -608,6 +889,36 @@ static int launch_fwd_tc(const float* x, const int32_t* gemm, const int32_t* ec,
     return after_launch();
 }
 
+
+static int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+
+static int g_tc_sk_ctas = 0;               // debug: force the stream-K grid size (0 = heuristic)
+
+template <int N_TILE>
+static int launch_fwd_tc_sk(const float* x, const int32_t* gemm, const int32_t* ec, const float* wt, const float* bias,
+                            float* out, int8_t* signs, void* sk_ws, int B, int E, int Cin, int Cout, cudaStream_t st) {
+    using S = TcSmem<N_TILE>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(meshconv_fwd_tc_sk_kernel<N_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+        if (e != cudaSuccess) { g_last_error = e; return MCNN_E_CUDA; }
+        configured = true;
+    }
+    const long long total = (long long)ceil_div(B * E, TC_M) * (Cout / N_TILE) * (5 * Cin / 32);
+    long long G = min((long long)min(sm_count(), SK_MAX_CTAS), max(1LL, total / 4));     // at least 4 K blocks per CTA
+    if (g_tc_sk_ctas > 0) G = min((long long)g_tc_sk_ctas, total);
+    int* flags = reinterpret_cast<int*>(sk_ws);
+    float* part = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(sk_ws) + SK_FLAG_BYTES);
+    meshconv_fwd_tc_sk_kernel<N_TILE><<<(int)G, TC_THREADS, S::TOTAL, st>>>(x, gemm, ec, wt, bias, out, signs, part, flags, B, E, Cin, Cout);
+    return after_launch();
+}
 
 // =============================================================================================================
 // backward, data:   dG[m][(k5, c)] = sum_o dout[m][o] * W[o][c][k5]   on tcgen05, then the abs/add backward and the
@@ -1112,6 +1423,30 @@ extern "C" int mcnn_meshconv_fwd_tc_signs(const float* x, const int32_t* gemm, c
     if (nt == 128) return launch_fwd_tc<128, 8>(x, gemm, ec, wt_ws, bias, out, signs, B, E, Cin, Cout, st);
     return launch_fwd_tc<64, 8>(x, gemm, ec, wt_ws, bias, out, signs, B, E, Cin, Cout, st);
 }
+
+
+/* bytes of the stream-K workspace (flags + one partial tile per CTA); the caller zeroes it ONCE after allocating it */
+extern "C" size_t mcnn_meshconv_fwd_tc_sk_ws(void) { return (size_t)SK_FLAG_BYTES + (size_t)SK_MAX_CTAS * TC_M * 256 * sizeof(float); }
+
+extern "C" int mcnn_meshconv_fwd_tc_sk(const float* x, const int32_t* gemm, const int32_t* ec, const float* weight,
+                                       const float* bias, float* out, float* wt_ws, int8_t* signs, void* sk_ws, int B, int E,
+                                       int Cin, int Cout, void* stream) {
+    if (!x || !gemm || !ec || !out || !wt_ws || !sk_ws || B <= 0 || E <= 0) return MCNN_E_BADARG;
+    if (!mcnn_meshconv_tc_supported(Cin, Cout)) return MCNN_E_BADARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = MCNN_OK;
+    if (weight != nullptr) {
+        weight_tc_layout_kernel<<<ceil_div(Cout * 5 * Cin, 256), 256, 0, st>>>(weight, wt_ws, Cin, Cout);
+        if ((rc = after_launch())) return rc;
+    }
+    int nt = (Cout % 256 == 0) ? 256 : ((Cout % 128 == 0) ? 128 : 64);
+    if (g_tc_force_ntile && Cout % g_tc_force_ntile == 0) nt = g_tc_force_ntile;
+    if (nt == 256) return launch_fwd_tc_sk<256>(x, gemm, ec, wt_ws, bias, out, signs, sk_ws, B, E, Cin, Cout, st);
+    if (nt == 128) return launch_fwd_tc_sk<128>(x, gemm, ec, wt_ws, bias, out, signs, sk_ws, B, E, Cin, Cout, st);
+    return launch_fwd_tc_sk<64>(x, gemm, ec, wt_ws, bias, out, signs, sk_ws, B, E, Cin, Cout, st);
+}
+
+extern "C" int mcnn_debug_set_tc_sk_ctas(int n) { g_tc_sk_ctas = n > 0 ? (n > SK_MAX_CTAS ? SK_MAX_CTAS : n) : 0; return MCNN_OK; }
 
 
 extern "C" int mcnn_meshconv_bwd_data_tc(const float* dout, const float* x, const int32_t* gemm, const int32_t* ec,

@@ -12,7 +12,11 @@ USE_TC = os.environ.get('MESHCNN_B200_TC', '1') != '0'
 # run the weight-gradient kernel of a MeshConv on a side stream, concurrently with its data-gradient kernel (both only
 # read dout / x): fills the tail waves of either kernel.  MESHCNN_B200_BWD_OVERLAP=0 keeps them on one stream.
 BWD_OVERLAP = os.environ.get('MESHCNN_B200_BWD_OVERLAP', '1') != '0'
+# persistent ("stream-K") forward kernel: (tile, K block) units spread evenly over the SMs; MESHCNN_B200_TC_SK=0 launches
+# one CTA per tile instead
+USE_SK = os.environ.get('MESHCNN_B200_TC_SK', '1') != '0'
 _SIDE = {}
+_SK_WS = {}
 STEP_TOKEN = -1          # >= 0 while a step prepared with begin_step() is being enqueued
 _NEXT_TOKEN = 0
 
@@ -48,6 +52,16 @@ def _side_stream(device):
     return s
 
 
+def _sk_workspace(device):
+    """Partial-tile slots + flags of the stream-K forward kernel, one per (device, stream): launches on one stream are
+    ordered, so they can share it.  Zeroed once here; the kernel leaves every flag lowered."""
+    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    ws = _SK_WS.get(key)
+    if ws is None:
+        ws = _SK_WS[key] = torch.zeros(int(_lib.lib().mcnn_meshconv_fwd_tc_sk_ws()), dtype=torch.uint8, device=device)
+    return ws
+
+
 def _chk_cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:
@@ -72,15 +86,21 @@ class MeshConvFn(torch.autograd.Function):
         if use_tc and ctx.needs_input_grad[0] and Cout % 32 == 0:
             signs = torch.empty(2, B * E, Cin, dtype=torch.int8, device=x.device)
         with profiler.span('meshconv_fwd_tc' if use_tc else 'meshconv_fwd', B=B, E=E, Cin=Cin, Cout=Cout):
-            if use_tc and img is not None:                   # weight image prepared ahead of time on the side stream
-                torch.cuda.current_stream().wait_event(img[2])
-                _lib.check(L.mcnn_meshconv_fwd_tc_signs(x.data_ptr(), level.gemm.data_ptr(), level.ec.data_ptr(), None,
-                                                        _lib.ptr(bias), out.data_ptr(), img[0].data_ptr(), _lib.ptr(signs), B, E, Cin, Cout,
-                                                        _lib.current_stream()), 'mcnn_meshconv_fwd_tc')
-            elif use_tc:
-                _lib.check(L.mcnn_meshconv_fwd_tc_signs(x.data_ptr(), level.gemm.data_ptr(), level.ec.data_ptr(), w.data_ptr(),
-                                                        _lib.ptr(bias), out.data_ptr(), wt_ws.data_ptr(), _lib.ptr(signs), B, E, Cin, Cout,
-                                                        _lib.current_stream()), 'mcnn_meshconv_fwd_tc')
+            if use_tc:
+                if img is not None:                          # weight image prepared ahead of time on the side stream
+                    torch.cuda.current_stream().wait_event(img[2])
+                    wptr, iptr = None, img[0].data_ptr()
+                else:
+                    wptr, iptr = w.data_ptr(), wt_ws.data_ptr()
+                if USE_SK:
+                    _lib.check(L.mcnn_meshconv_fwd_tc_sk(x.data_ptr(), level.gemm.data_ptr(), level.ec.data_ptr(), wptr,
+                                                         _lib.ptr(bias), out.data_ptr(), iptr, _lib.ptr(signs),
+                                                         _sk_workspace(x.device).data_ptr(), B, E, Cin, Cout,
+                                                         _lib.current_stream()), 'mcnn_meshconv_fwd_tc_sk')
+                else:
+                    _lib.check(L.mcnn_meshconv_fwd_tc_signs(x.data_ptr(), level.gemm.data_ptr(), level.ec.data_ptr(), wptr,
+                                                            _lib.ptr(bias), out.data_ptr(), iptr, _lib.ptr(signs), B, E, Cin, Cout,
+                                                            _lib.current_stream()), 'mcnn_meshconv_fwd_tc')
             else:
                 _lib.check(L.mcnn_meshconv_fwd(x.data_ptr(), level.gemm.data_ptr(), level.ec.data_ptr(), w.data_ptr(),
                                                _lib.ptr(bias), out.data_ptr(), wt_ws.data_ptr(), B, E, Cin, Cout,

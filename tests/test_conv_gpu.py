@@ -144,13 +144,61 @@ def test_conv_cta_pair_kernel_matches_single_cta_kernel(cin, cout, B, mode):
     torch.manual_seed(cin + cout + B)
     conv = MeshConv(cin, cout, bias=True).to(DEV)
     x = torch.randn(B, cin, 750, device=DEV)
+    from meshcnn_b200 import functional as Fn
     L = _lib.lib()
+    sk = Fn.USE_SK
     try:
+        Fn.USE_SK = False                        # both are one-CTA(-pair)-per-tile kernels
         L.mcnn_debug_set_tc_pair(0)
         y1 = conv(x, meshes).clone()
         L.mcnn_debug_set_tc_pair(mode)           # 1: cta_group::2 kernel, 2: 16 producer warps
         y2 = conv(x, meshes).clone()
         torch.cuda.synchronize()
     finally:
+        Fn.USE_SK = sk
         L.mcnn_debug_set_tc_pair(_lib.TC_PAIR_DEFAULT)
     assert close(y2.detach().cpu().numpy(), y1.detach().cpu().numpy(), 1e-6)
+
+
+@pytest.mark.parametrize('ctas', [0, 1, 7, 148, 251], ids=lambda c: 'ctas%d' % c)
+@pytest.mark.parametrize('cin,cout,B', [(64, 64, 24), (128, 256, 9), (256, 256, 23), (256, 512, 5), (32, 192, 3)])
+def test_conv_stream_k_kernel_matches_tile_kernel(cin, cout, B, ctas):
+    """The persistent stream-K forward kernel against the one-CTA-per-tile kernel, with the grid forced to 1 CTA (no tile is
+    cut), 7 (long ranges), 148 and 251 (more CTAs than tiles for the small cases: a tile is cut into 3+ partials).  Same
+    products; only the fp32 sum of the partials of a cut tile is associated differently.  The signs kept for the backward
+    must be identical, and a second launch on the same workspace must reproduce the first bit for bit (flags lowered)."""
+    from meshcnn_b200 import _lib, synth
+    from meshcnn_b200 import functional as Fn
+    from meshcnn_b200.mesh_conv import MeshConv
+    from tests.gpu_util import DEV, product_mesh
+    meshes = [product_mesh(*synth.make('ico' if s % 3 else 'torus', s, **(dict(nu=5) if s % 3 else dict(m=10, n=25)))) for s in range(B)]
+    torch.manual_seed(cin + cout + B)
+    conv = MeshConv(cin, cout, bias=True).to(DEV)
+    x = torch.randn(B, cin, 750, device=DEV)
+    dy = torch.randn(B, cout, 750, 1, device=DEV)
+    L = _lib.lib()
+    assert Fn.USE_SK and Fn.USE_TC
+
+    def run():
+        xg = x.clone().requires_grad_(True)
+        y = conv(xg, meshes)
+        y.backward(dy)
+        torch.cuda.synchronize()
+        return y.detach().clone(), xg.grad.clone()
+    try:
+        Fn.USE_SK = False
+        y1, g1 = run()
+        Fn.USE_SK = True
+        L.mcnn_debug_set_tc_sk_ctas(ctas)
+        y2, g2 = run()
+        y3, g3 = run()
+    finally:
+        Fn.USE_SK = True
+        L.mcnn_debug_set_tc_sk_ctas(0)
+    assert torch.equal(y2, y3)
+    # measured: both differ from the exact-fp32 FFMA kernel by <= 1.1e-5 of max|y| (fp32 accumulation in TMEM over K = 1280);
+    # summing a cut tile's partials moves the result by the same order
+    assert close(y2.cpu().numpy(), y1.cpu().numpy(), 2e-5)
+    assert close(g2.cpu().numpy(), g1.cpu().numpy(), 1e-5)          # same signs; the scatter atomics reorder sums
+    if ctas == 1:
+        assert torch.equal(y2, y1)
