@@ -100,6 +100,10 @@ int mcnn_meshconv_fwd_tc_sk(const float* x, const int32_t* gemm, const int32_t* 
                             int Cout, void* stream);
 /* diagnostics only: force the grid size of mcnn_meshconv_fwd_tc_sk (0 = one CTA per SM) */
 int mcnn_debug_set_tc_sk_ctas(int n);
+/* diagnostics only (library built with -DMCNN_TC_PROF): 64 clock64 stamps of one CTA of the last stream-K launch */
+int mcnn_debug_sk_prof(long long* out64, int cta);
+/* diagnostics only (-DMCNN_TC_PROF): %globaltimer ns at entry / exit of each of the first 256 CTAs of the last stream-K launch */
+int mcnn_debug_sk_cta_times(unsigned long long* out512);
 
 /* diagnostics only: bottleneck-attribution knobs of the tensor-core forward kernel (0 = normal operation) */
 int mcnn_debug_set_tc(int flags);

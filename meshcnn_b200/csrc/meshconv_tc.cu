@@ -23,6 +23,15 @@ namespace mcnn {
 // the tcgen05.mma issue, bit 2 = producers skip the st.shared, bit 3 = no bulk copies of the weight tile.  0 in normal operation.
 __device__ int g_tc_debug = 0;
 __device__ long long g_tc_prof[16];        // -DMCNN_TC_PROF: cycle counters of CTA 0 (tools/tc_prof.py)
+__device__ long long g_sk_prof[64];        // -DMCNN_TC_PROF: clock64 stamps of one CTA of the stream-K kernel (tools/sk_prof.py)
+__device__ int g_sk_prof_cta = 0;
+__device__ unsigned long long g_sk_cta_ns[256][2];   // -DMCNN_TC_PROF: %globaltimer at entry / exit of every CTA
+__device__ __forceinline__ unsigned long long globaltimer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#ifdef MCNN_TC_PROF
+#define SK_STAMP(cond, idx) do { if ((cond) && blockIdx.x == g_sk_prof_cta && (idx) < 64) g_sk_prof[(idx)] = clock64(); } while (0)
+#else
+#define SK_STAMP(cond, idx) do { } while (0)
+#endif
 static int g_tc_force_ntile = 0;          // host side: 0 = heuristic
 static int g_tc_pw16 = 0;                 // host side: 16 producer warps in the forward kernel (N >= 128)
 static int g_tc_pair = 0;                 // host side: use the CTA-pair (cta_group::2) forward kernel for N = 256
@@ -351,22 +360,117 @@ meshconv_fwd_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 constexpr int SK_FLAG_BYTES = 4096;
-constexpr int SK_MAX_CTAS = 256;                 // workspace: flags + one 128 x 256 fp32 partial per CTA
+constexpr int SK_MAX_CTAS = 192;                 // workspace: flags + two 128 x 256 fp32 partial slots per CTA
+constexpr int SK_EPI_WARPS = 4;                  // one per TMEM lane quarter
+constexpr int SK_THREADS = (TC_PRODUCER_WARPS + 1 + SK_EPI_WARPS) * 32;
 
 template <int N_TILE>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+struct SkSmem {
+    using T = TcSmem<N_TILE>;
+    static constexpr int NB_OFF = T::TILE_BYTES;                      // int nb[2][128][5]: gather table of this and the next tile
+    static constexpr int BAR_OFF = NB_OFF + 2 * TC_M * 5 * 4;
+    static constexpr int NBARS = 2 * T::STAGES + 8;                   // full / empty per stage, accumulator and table full / empty x 2
+    static constexpr int TOTAL = BAR_OFF + NBARS * 8 + 16 + 1024;
+    static constexpr int TMEM_COLS = 2 * N_TILE;                      // two accumulators: the epilogue of a segment overlaps the next one
+};
+
+// The segments of one CTA's unit range, in the order they are processed.  A tile that the range boundaries cut into pieces
+// is OWNED by the CTA holding its longest piece (the first such on ties): every CTA works through its non-owned pieces
+// first (each is published as a partial as soon as its accumulator is complete, without waiting for anybody), then its
+// whole tiles, and last the pieces it owns -- by then the partials it has to add were written long ago.
+struct SkSeg { int tile, ka, ke, kind, slot; };   // kind 0: whole tile, 1: partial (goes to `slot`), 2: owner of a cut tile
+
+struct SkPlan {
+    long long total, u0, u1;
+    int G, cta, nkb;
+    int n_early, n_whole, n_late, w0;
+    int e_tile[2], e_ka[2], e_ke[2], e_slot[2];
+    int l_tile[2], l_ka[2], l_ke[2];
+
+    __device__ __forceinline__ long long start_of(int c) const { return total * c / G; }
+    // first CTA whose range intersects `tile`, given one CTA that does
+    __device__ int first_cta_of(int tile, int hint) const {
+        const long long ts = (long long)tile * nkb;
+        int c = hint;
+        while (c > 0 && start_of(c) > ts) --c;
+        while (start_of(c + 1) <= ts) ++c;
+        return c;
+    }
+    __device__ int owner_of(int tile, int hint) const {
+        const long long ts = (long long)tile * nkb, te = ts + nkb;
+        int best = -1;
+        long long best_len = 0;
+        for (int c = first_cta_of(tile, hint); c < G; ++c) {
+            const long long a = max(start_of(c), ts), b = min(start_of(c + 1), te);
+            if (a >= te) break;
+            if (b - a > best_len) { best_len = b - a; best = c; }
+        }
+        return best;
+    }
+    __device__ void add_piece(int tile, int ka, int ke, int at_start) {
+        if (owner_of(tile, cta) == cta) { l_tile[n_late] = tile; l_ka[n_late] = ka; l_ke[n_late] = ke; ++n_late; }
+        else { e_tile[n_early] = tile; e_ka[n_early] = ka; e_ke[n_early] = ke; e_slot[n_early] = 2 * cta + (at_start ? 0 : 1); ++n_early; }
+    }
+    __device__ void build(long long total_, int G_, int cta_, int nkb_) {
+        total = total_; G = G_; cta = cta_; nkb = nkb_;
+        u0 = start_of(cta); u1 = start_of(cta + 1);
+        n_early = n_whole = n_late = 0; w0 = 0;
+        const int tf = (int)(u0 / nkb), tl = (int)((u1 - 1) / nkb);
+        const int ka = (int)(u0 - (long long)tf * nkb), ke = (int)(u1 - (long long)tl * nkb);       // first piece starts at ka, last ends at ke
+        if (tf == tl) {
+            if (ka == 0 && ke == nkb) { w0 = tf; n_whole = 1; }
+            else add_piece(tf, ka, ke, 1);
+            return;
+        }
+        int wa = tf, wb = tl;                                   // whole tiles wa .. wb
+        if (ka > 0) { add_piece(tf, ka, nkb, 1); wa = tf + 1; }
+        if (ke < nkb) { add_piece(tl, 0, ke, 0); wb = tl - 1; }
+        w0 = wa; n_whole = wb - wa + 1;
+    }
+    __device__ __forceinline__ int nseg() const { return n_early + n_whole + n_late; }
+    __device__ SkSeg seg(int i) const {
+        SkSeg r;
+        if (i < n_early) {
+            const int j = i;                                     // selects, not dynamic indexing (would go to local memory)
+            r.tile = j ? e_tile[1] : e_tile[0]; r.ka = j ? e_ka[1] : e_ka[0]; r.ke = j ? e_ke[1] : e_ke[0];
+            r.slot = j ? e_slot[1] : e_slot[0]; r.kind = 1;
+        } else if (i < n_early + n_whole) {
+            r.tile = w0 + (i - n_early); r.ka = 0; r.ke = nkb; r.kind = 0; r.slot = -1;
+        } else {
+            const int j = i - n_early - n_whole;
+            r.tile = j ? l_tile[1] : l_tile[0]; r.ka = j ? l_ka[1] : l_ka[0]; r.ke = j ? l_ke[1] : l_ke[0];
+            r.kind = 2; r.slot = -1;
+        }
+        return r;
+    }
+};
+
+// Warp roles: 0-7 producers (gather -> symmetric functions -> hi/lo split -> st.shared), 8 MMA issuer, 9-12 epilogue.
+// The epilogue warps also prepare the gather table of the NEXT segment's tile while the current one is produced, and the
+// accumulator is double-buffered in TMEM, so producers and tensor core run from one segment straight into the next.
+template <int N_TILE>
+__global__ void __launch_bounds__(SK_THREADS, 1)
 meshconv_fwd_tc_sk_kernel(const float* __restrict__ x, const int32_t* __restrict__ gemm, const int32_t* __restrict__ ec,
                           const float* __restrict__ wt, const float* __restrict__ bias, float* __restrict__ out,
                           int8_t* __restrict__ signs, float* part, int* flags, int B, int E, int Cin, int Cout) {
     using S = TcSmem<N_TILE>;
+    using SS = SkSmem<N_TILE>;
     constexpr int PW = TC_PRODUCER_WARPS, PT = PW * 32, IT0 = (TC_M * 8) / PT, ITP = (TC_M * 4) / PT;
+    constexpr int ET = SK_EPI_WARPS * 32;
+    SK_STAMP(threadIdx.x == 0, 61);
+#ifdef MCNN_TC_PROF
+    if (threadIdx.x == 0 && blockIdx.x < 256) g_sk_cta_ns[blockIdx.x][0] = globaltimer_ns();
+#endif
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    int (*nb)[5] = reinterpret_cast<int (*)[5]>(smem + S::NB_OFF);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
+    int (*nb)[TC_M][5] = reinterpret_cast<int (*)[TC_M][5]>(smem + SS::NB_OFF);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SS::BAR_OFF);
     uint64_t* empty_bar = full_bar + S::STAGES;
-    uint64_t* accum_bar = empty_bar + S::STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+    uint64_t* acc_full = empty_bar + S::STAGES;              // [2]
+    uint64_t* acc_empty = acc_full + 2;                      // [2]
+    uint64_t* nb_full = acc_empty + 2;                       // [2]
+    uint64_t* nb_empty = nb_full + 2;                        // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(nb_empty + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int M = B * E;
@@ -375,57 +479,134 @@ meshconv_fwd_tc_sk_kernel(const float* __restrict__ x, const int32_t* __restrict
     const int ntn = Cout / N_TILE;
     const long long total = (long long)ceil_div(M, TC_M) * ntn * num_kb;
     const int G = gridDim.x, cta = blockIdx.x;
-    const long long u_begin = total * cta / G, u_end = total * (cta + 1) / G;
+    SkPlan plan;
+    plan.build(total, G, cta, num_kb);
+    const int nseg = plan.nseg();
+    SK_STAMP(tid == 0, 62);
 
     if (warp == PW) {
         if (lane == 0) {
             for (int s = 0; s < S::STAGES; ++s) { tc::mbar_init(full_bar + s, PW); tc::mbar_init(empty_bar + s, 1); }
-            tc::mbar_init(accum_bar, 1);
+            for (int i = 0; i < 2; ++i) {
+                tc::mbar_init(acc_full + i, 1); tc::mbar_init(acc_empty + i, SK_EPI_WARPS);
+                tc::mbar_init(nb_full + i, SK_EPI_WARPS); tc::mbar_init(nb_empty + i, PW);
+            }
             tc::fence_barrier_init();
         }
         __syncwarp();
-        tc::tmem_alloc<N_TILE>(tmem_slot);
+        tc::tmem_alloc<SS::TMEM_COLS>(tmem_slot);
     }
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    SK_STAMP(tid == 0, 0);
+
+    // Epilogue of a whole tile or of the piece this CTA owns: accumulator (+ the other CTAs' pieces, ascending K order) + bias
+    // -> out.  The calling warp reads its TMEM lane quarter and the 32-column chunks chunk0, chunk0 + step, ...
+    auto finish_tile = [&](const SkSeg& sg, int seg, int chunk0, int step, bool all_warps) {
+        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int tile = sg.tile, buf = seg & 1;
+        const int mt = tile / ntn, nt = tile - mt * ntn;
+        const int m0 = mt * TC_M, n0 = nt * N_TILE;
+        const int lane_grp = warp & 3;                           // the TMEM lane quarter this warp may read
+        const int r = lane_grp * 32 + lane;
+        const int m = m0 + r;
+        const uint32_t acc = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(buf * N_TILE);
+        int c_first = 0, n_cov = 0;                              // CTAs c_first .. c_first + n_cov - 1 hold pieces of this tile
+        const long long ts = (long long)tile * num_kb, te = ts + num_kb;
+        if (sg.kind == 2) {
+            c_first = plan.first_cta_of(tile, cta);
+            while (c_first + n_cov < G && plan.start_of(c_first + n_cov) < te) ++n_cov;
+            if (tid == (PW + 1) * 32) {                          // first epilogue thread: wait for the pieces, lower their flags
+                for (int j = 0; j < n_cov; ++j) {
+                    const int c2 = c_first + j;
+                    if (c2 == cta) continue;
+                    volatile int* f = flags + 2 * c2 + (plan.start_of(c2) >= ts ? 0 : 1);
+                    while (*f == 0) __nanosleep(64);
+                    *f = 0;
+                }
+                __threadfence();
+            }
+            if (all_warps) named_bar_sync(3, PT + ET); else named_bar_sync(2, ET);
+            SK_STAMP(tid == (PW + 1) * 32, 22 + 4 * seg);
+        }
+        auto slot_base = [&](int j) -> const float4* {
+            const int c2 = c_first + j;
+            const int slot = 2 * c2 + (plan.start_of(c2) >= ts ? 0 : 1);
+            return reinterpret_cast<const float4*>(part) + (size_t)slot * (N_TILE / 4) * TC_M + r;
+        };
+        int j_first = -1;
+        for (int j = n_cov - 1; j >= 0; --j) if (c_first + j != cta) j_first = j;
+        const float4* p_first = (j_first >= 0 && m < M) ? slot_base(j_first) : nullptr;
+        float4 nxt[8];                                           // the first foreign piece is fetched one chunk ahead
+        if (p_first != nullptr && chunk0 * 32 < N_TILE) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) nxt[j] = __ldcg(p_first + (size_t)(chunk0 * 8 + j) * TC_M);
+        }
+        tc::mbar_wait(acc_full + buf, (seg >> 1) & 1);
+        tc::tc_fence_after();
+        SK_STAMP(tid == (PW + 1) * 32, 20 + 4 * seg);
+#pragma unroll 1
+        for (int cc = chunk0 * 32; cc < N_TILE; cc += 32 * step) {
+            float v[32];
+            tc::tmem_ld32(acc + (uint32_t)cc, v);
+            if (m < M) {
+                if (p_first != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { v[4 * j] += nxt[j].x; v[4 * j + 1] += nxt[j].y; v[4 * j + 2] += nxt[j].z; v[4 * j + 3] += nxt[j].w; }
+                    const int cn = cc + 32 * step;
+                    if (cn < N_TILE) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) nxt[j] = __ldcg(p_first + (size_t)((cn >> 2) + j) * TC_M);
+                    }
+                    for (int jj = j_first + 1; jj < n_cov; ++jj) {          // a tile cut into 3+ pieces (more CTAs than tiles)
+                        if (c_first + jj == cta) continue;
+                        const float4* q4 = slot_base(jj) + (size_t)(cc >> 2) * TC_M;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 t = __ldcg(q4 + (size_t)j * TC_M);
+                            v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+                        }
+                    }
+                }
+                const int n = n0 + cc;
+                float* o = out + (size_t)m * Cout + n;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    float4 bv = zero4;
+                    if (bias != nullptr) bv = __ldg(reinterpret_cast<const float4*>(bias + n + j));
+                    *reinterpret_cast<float4*>(o + j) = make_float4(v[j] + bv.x, v[j + 1] + bv.y, v[j + 2] + bv.z, v[j + 3] + bv.w);
+                }
+            }
+        }
+    };
 
     if (warp < PW) {
+        // ======================================== producers ========================================================
         const int pt = tid;
         const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
         struct Regs { float4 a[IT0]; };
         uint32_t g = 0;                                          // K blocks this CTA has pushed through the stage ring
-        int seg = 0;
-        for (long long u = u_begin; u < u_end; ++seg) {
-            const int tile = (int)(u / num_kb), ka = (int)(u - (long long)tile * num_kb);
-            const int ke = (int)min((long long)num_kb, ka + (u_end - u));
+        for (int seg = 0; seg < nseg; ++seg) {
+            const SkSeg sg = plan.seg(seg);
+            const int tile = sg.tile, ka = sg.ka, ke = sg.ke;
             const int mt = tile / ntn, nt = tile - mt * ntn;
             const int m0 = mt * TC_M, n0 = nt * N_TILE;
-            // ---- gather table of this tile (no thread can still be reading the previous one: every warp handed over its
-            // last K block before anyone got past that segment's accumulator barrier) ----
-            for (int i = tid; i < TC_M * 5; i += PT) {
-                const int r = i / 5, k = i - r * 5;
-                const int m = m0 + r;
-                int idx = -1;
-                if (m < M) {
-                    const int b = m / E, e = m - b * E;
-                    if (e >= __ldg(ec + b)) idx = b * E;
-                    else if (k == 0) idx = m;
-                    else { const int gg = __ldg(gemm + (size_t)m * 4 + (k - 1)); idx = gg < 0 ? -1 : b * E + gg; }
-                }
-                nb[r][k] = idx;
-            }
-            named_bar_sync(1, PT);
+            const int buf = seg & 1;
+            tc::mbar_wait(nb_full + buf, (seg >> 1) & 1);
+            SK_STAMP(tid == 0, 1 + 4 * seg);
             int src0[IT0], srcA[ITP][2], srcB[ITP][2];
 #pragma unroll
-            for (int it = 0; it < IT0; ++it) src0[it] = nb[(pt + it * PT) >> 3][0];
+            for (int it = 0; it < IT0; ++it) src0[it] = nb[buf][(pt + it * PT) >> 3][0];
 #pragma unroll
             for (int it = 0; it < ITP; ++it) {
                 const int r = pair_item_row(pt + it * PT);
-                srcA[it][0] = nb[r][1]; srcB[it][0] = nb[r][3];
-                srcA[it][1] = nb[r][2]; srcB[it][1] = nb[r][4];
+                srcA[it][0] = nb[buf][r][1]; srcB[it][0] = nb[buf][r][3];
+                srcA[it][1] = nb[buf][r][2]; srcB[it][1] = nb[buf][r][4];
             }
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(nb_empty + buf);
             auto load_block = [&](int kb, Regs& R) {
                 const int cb = kb / 5, blk = kb - cb * 5;
                 if (blk == 0) {
@@ -516,74 +697,27 @@ meshconv_fwd_tc_sk_kernel(const float* __restrict__ x, const int32_t* __restrict
                     }
                 }
             }
-            // ---- epilogue of the segment ----
-            const bool head = ka == 0, last = ke == num_kb;
-            int n_parts = 0;
-            if (head && !last) {
-                // owner of a tile that other CTAs finish: CTAs cta+1 .. whose range starts inside this tile
-                const long long tile_end = (long long)(tile + 1) * num_kb;
-                for (int c2 = cta + 1; c2 < G && total * c2 / G < tile_end; ++c2) ++n_parts;
-                if (tid == 0) {
-                    for (int j = 1; j <= n_parts; ++j) {
-                        volatile int* f = flags + cta + j;
-                        while (*f == 0) __nanosleep(64);
-                        *f = 0;
-                    }
-                    __threadfence();
-                }
-                named_bar_sync(2, PT);
-            }
-            tc::mbar_wait(accum_bar, seg & 1);
-            tc::tc_fence_after();
-            const int lane_grp = warp & 3;
-            const int r = lane_grp * 32 + lane;
-            const int m = m0 + r;
-            constexpr int COLS_PER_WARP = N_TILE / (PW / 4);
-            const int col0 = (warp >> 2) * COLS_PER_WARP;
-#pragma unroll 1
-            for (int cc = 0; cc < COLS_PER_WARP; cc += 32) {
-                float v[32];
-                tc::tmem_ld32(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(col0 + cc), v);
-                if (m < M) {
-                    if (!head) {
-                        float4* o = reinterpret_cast<float4*>(part + ((size_t)cta * TC_M + r) * N_TILE + col0 + cc);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) __stcg(o + j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
-                    } else {
-                        for (int p = 1; p <= n_parts; ++p) {
-                            const float4* q4 = reinterpret_cast<const float4*>(part + ((size_t)(cta + p) * TC_M + r) * N_TILE + col0 + cc);
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const float4 t = __ldcg(q4 + j);
-                                v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
-                            }
-                        }
-                        const int n = n0 + col0 + cc;
-                        float* o = out + (size_t)m * Cout + n;
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            float4 bv = zero4;
-                            if (bias != nullptr) bv = __ldg(reinterpret_cast<const float4*>(bias + n + j));
-                            *reinterpret_cast<float4*>(o + j) = make_float4(v[j] + bv.x, v[j + 1] + bv.y, v[j + 2] + bv.z, v[j + 3] + bv.w);
-                        }
-                    }
-                }
-            }
-            tc::tc_fence_before();
-            if (!head) {                                         // publish the partial: every writer fences, then one flag store
-                __threadfence();
-                named_bar_sync(2, PT);
-                if (tid == 0) { volatile int* f = flags + cta; *f = 1; }
-            }
-            u += ke - ka;
+            SK_STAMP(tid == 0, 2 + 4 * seg);
         }
-    } else {
+        // nothing left to produce: help the epilogue warps with the CTA's last tile (two more warps per TMEM lane quarter)
+        const SkSeg lastseg = plan.seg(nseg - 1);
+        if (lastseg.kind != 1) {
+            finish_tile(lastseg, nseg - 1, 1 + (warp >> 2), 3, true);
+            tc::tc_fence_before();
+        }
+    } else if (warp == PW) {
         // ======================================== MMA issuer ========================================================
         constexpr uint32_t idesc = tc::make_idesc_tf32(N_TILE);
         uint32_t g = 0;
-        for (long long u = u_begin; u < u_end;) {
-            const int tile = (int)(u / num_kb), ka = (int)(u - (long long)tile * num_kb);
-            const int ke = (int)min((long long)num_kb, ka + (u_end - u));
+        for (int seg = 0; seg < nseg; ++seg) {
+            const SkSeg sg = plan.seg(seg);
+            const int ka = sg.ka, ke = sg.ke;
+            const int buf = seg & 1;
+            const uint32_t acc = tmem_base + (uint32_t)(buf * N_TILE);
+            if (seg >= 2) {                                      // the epilogue of segment seg - 2 has drained this accumulator
+                tc::mbar_wait(acc_empty + buf, ((seg >> 1) - 1) & 1);
+                tc::tc_fence_after();
+            }
             for (int kb = ka; kb < ke; ++kb, ++g) {
                 const int s = g % S::STAGES;
                 const uint32_t ph = (g / S::STAGES) & 1;
@@ -598,23 +732,98 @@ meshconv_fwd_tc_sk_kernel(const float* __restrict__ x, const int32_t* __restrict
                     for (int kk = 0; kk < 4; ++kk) {
                         const uint64_t dah = tc::make_desc_sw128(a_hi + kk * 32), dal = tc::make_desc_sw128(a_lo + kk * 32);
                         const uint64_t dbh = tc::make_desc_sw128(b_hi + kk * 32), dbl = tc::make_desc_sw128(b_lo + kk * 32);
-                        tc::mma_tf32(tmem_base, dah, dbh, idesc, (kb != ka) || (kk != 0));
-                        tc::mma_tf32(tmem_base, dah, dbl, idesc, 1);
-                        tc::mma_tf32(tmem_base, dal, dbh, idesc, 1);
+                        tc::mma_tf32(acc, dah, dbh, idesc, (kb != ka) || (kk != 0));
+                        tc::mma_tf32(acc, dah, dbl, idesc, 1);
+                        tc::mma_tf32(acc, dal, dbh, idesc, 1);
                     }
                     tc::mma_commit(empty_bar + s);
-                    if (kb == ke - 1) tc::mma_commit(accum_bar);
+                    if (kb == ke - 1) tc::mma_commit(acc_full + buf);
                 }
                 __syncwarp();
             }
-            u += ke - ka;
+            SK_STAMP(lane == 0, 3 + 4 * seg);
         }
         tc::tc_fence_before();
+    } else {
+        // ======================================== epilogue + gather tables =========================================
+        const int et = tid - (PW + 1) * 32;                      // 0 .. 127
+        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        auto fill_table = [&](int tile_, int buf_) {
+            const int m0_ = (tile_ / ntn) * TC_M;
+            for (int i = et; i < TC_M * 5; i += ET) {
+                const int r = i / 5, k = i - r * 5;
+                const int m = m0_ + r;
+                int idx = -1;
+                if (m < M) {
+                    const int b = m / E, e = m - b * E;
+                    if (e >= __ldg(ec + b)) idx = b * E;                               // padded slot -> edge 0
+                    else if (k == 0) idx = m;
+                    else { const int gg = __ldg(gemm + (size_t)m * 4 + (k - 1)); idx = gg < 0 ? -1 : b * E + gg; }
+                }
+                nb[buf_][r][k] = idx;
+            }
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(nb_full + buf_);
+        };
+        fill_table(plan.seg(0).tile, 0);
+        for (int seg = 0; seg < nseg; ++seg) {
+            const SkSeg sg = plan.seg(seg);
+            const int tile = sg.tile;
+            const int mt = tile / ntn, nt = tile - mt * ntn;
+            const int m0 = mt * TC_M, n0 = nt * N_TILE;
+            const int buf = seg & 1;
+            SK_STAMP(et == 0, 23 + 4 * seg);
+            if (seg + 1 < nseg) {                                // gather table of the next segment's tile
+                if (seg >= 1) tc::mbar_wait(nb_empty + (buf ^ 1), ((seg - 1) >> 1) & 1);   // producers copied segment seg - 1's table out
+                fill_table(plan.seg(seg + 1).tile, buf ^ 1);
+            }
+            const int lane_grp = warp & 3;                       // the TMEM lane quarter this warp may read
+            const int r = lane_grp * 32 + lane;
+            const int m = m0 + r;
+            const uint32_t acc = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(buf * N_TILE);
+            if (sg.kind == 1) {
+                // ---- a piece of a tile another CTA owns: publish the raw accumulator ----
+                tc::mbar_wait(acc_full + buf, (seg >> 1) & 1);
+                tc::tc_fence_after();
+                SK_STAMP(et == 0, 20 + 4 * seg);
+#pragma unroll 1
+                for (int cc = 0; cc < N_TILE; cc += 32) {
+                    float v[32];
+                    tc::tmem_ld32(acc + (uint32_t)cc, v);
+                    if (m < M) {
+                        // slot layout [column / 4][row] of float4: the 32 lanes of a store (32 rows) touch 512 contiguous bytes
+                        float4* o = reinterpret_cast<float4*>(part) + ((size_t)sg.slot * (N_TILE / 4) + (cc >> 2)) * TC_M + r;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) __stcg(o + j * TC_M, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+                    }
+                }
+                tc::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(acc_empty + buf);
+                __threadfence();                                 // every writer fences, then one flag store
+                named_bar_sync(2, ET);
+                if (et == 0) { volatile int* f = flags + sg.slot; *f = 1; }
+                SK_STAMP(et == 0, 21 + 4 * seg);
+                continue;
+            }
+            // ---- whole tile, or the owned piece of a cut tile; the producer warps help with the CTA's last one ----
+            const bool all_warps = seg == nseg - 1;
+            finish_tile(sg, seg, 0, all_warps ? 3 : 1, all_warps);
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(acc_empty + buf);     // accumulator free for segment seg + 2
+            SK_STAMP(et == 0, 21 + 4 * seg);
+        }
     }
+    SK_STAMP(tid == 0, 60);
     __syncthreads();
     if (warp == PW) {
         tc::tc_fence_after();
-        tc::tmem_dealloc<N_TILE>(tmem_base);
+        tc::tmem_dealloc<SS::TMEM_COLS>(tmem_base);
+        SK_STAMP(lane == 0, 59);
+#ifdef MCNN_TC_PROF
+        if (lane == 0 && blockIdx.x < 256) g_sk_cta_ns[blockIdx.x][1] = globaltimer_ns();
+#endif
     }
 }
 
@@ -904,7 +1113,7 @@ static int g_tc_sk_ctas = 0;               // debug: force the stream-K grid siz
 template <int N_TILE>
 static int launch_fwd_tc_sk(const float* x, const int32_t* gemm, const int32_t* ec, const float* wt, const float* bias,
                             float* out, int8_t* signs, void* sk_ws, int B, int E, int Cin, int Cout, cudaStream_t st) {
-    using S = TcSmem<N_TILE>;
+    using S = SkSmem<N_TILE>;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(meshconv_fwd_tc_sk_kernel<N_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
@@ -916,7 +1125,7 @@ static int launch_fwd_tc_sk(const float* x, const int32_t* gemm, const int32_t* 
     if (g_tc_sk_ctas > 0) G = min((long long)g_tc_sk_ctas, total);
     int* flags = reinterpret_cast<int*>(sk_ws);
     float* part = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(sk_ws) + SK_FLAG_BYTES);
-    meshconv_fwd_tc_sk_kernel<N_TILE><<<(int)G, TC_THREADS, S::TOTAL, st>>>(x, gemm, ec, wt, bias, out, signs, part, flags, B, E, Cin, Cout);
+    meshconv_fwd_tc_sk_kernel<N_TILE><<<(int)G, SK_THREADS, S::TOTAL, st>>>(x, gemm, ec, wt, bias, out, signs, part, flags, B, E, Cin, Cout);
     return after_launch();
 }
 
@@ -1426,7 +1635,7 @@ extern "C" int mcnn_meshconv_fwd_tc_signs(const float* x, const int32_t* gemm, c
 
 
 /* bytes of the stream-K workspace (flags + one partial tile per CTA); the caller zeroes it ONCE after allocating it */
-extern "C" size_t mcnn_meshconv_fwd_tc_sk_ws(void) { return (size_t)SK_FLAG_BYTES + (size_t)SK_MAX_CTAS * TC_M * 256 * sizeof(float); }
+extern "C" size_t mcnn_meshconv_fwd_tc_sk_ws(void) { return (size_t)SK_FLAG_BYTES + (size_t)2 * SK_MAX_CTAS * TC_M * 256 * sizeof(float); }
 
 extern "C" int mcnn_meshconv_fwd_tc_sk(const float* x, const int32_t* gemm, const int32_t* ec, const float* weight,
                                        const float* bias, float* out, float* wt_ws, int8_t* signs, void* sk_ws, int B, int E,
@@ -1526,6 +1735,23 @@ extern "C" int mcnn_debug_tc_prof(long long* out16, int reset) {
         long long z[16] = {0};
         e = cudaMemcpyToSymbol(g_tc_prof, z, sizeof(z));
     }
+    return e == cudaSuccess ? MCNN_OK : MCNN_E_CUDA;
+}
+
+/* diagnostics (prof build): %globaltimer (ns) at entry and exit of every CTA of the last stream-K forward launch */
+extern "C" int mcnn_debug_sk_cta_times(unsigned long long* out512) {
+    cudaError_t e = cudaMemcpyFromSymbol(out512, g_sk_cta_ns, sizeof(unsigned long long) * 512);
+    return e == cudaSuccess ? MCNN_OK : MCNN_E_CUDA;
+}
+
+/* diagnostics (prof build): clock64 stamps of CTA `cta` of the last stream-K forward launch; selects the CTA for the next */
+extern "C" int mcnn_debug_sk_prof(long long* out64, int cta) {
+    cudaError_t e = cudaMemcpyFromSymbol(out64, g_sk_prof, sizeof(long long) * 64);
+    if (e == cudaSuccess) {
+        long long z[64] = {0};
+        e = cudaMemcpyToSymbol(g_sk_prof, z, sizeof(z));
+    }
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_sk_prof_cta, &cta, sizeof(int));
     return e == cudaSuccess ? MCNN_OK : MCNN_E_CUDA;
 }
 

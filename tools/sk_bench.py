@@ -31,7 +31,10 @@ def timeit(fn, k=20):
 bt = MeshBatch([Mesh(data=d) for d in datas], 750, dev)
 lvl = bt.level(750)
 ws = torch.zeros(int(L.mcnn_meshconv_fwd_tc_sk_ws()), dtype=torch.uint8, device=dev)
-for E, cin, cout in [(750, 64, 64), (600, 64, 128), (600, 128, 128), (450, 128, 256), (450, 256, 256), (300, 256, 256)]:
+SHAPES = [(750, 64, 64), (600, 64, 128), (600, 128, 128), (450, 128, 256), (450, 256, 256), (300, 256, 256)]
+if os.environ.get('SK_SHAPES'):
+    SHAPES = [tuple(int(v) for v in t.split(',')) for t in os.environ['SK_SHAPES'].split(';')]
+for E, cin, cout in SHAPES:
     # the topology of the 750-edge level serves every E (gather ids < E are what matters for timing): use the first E edges
     x = torch.randn(B, E, cin, device=dev)
     w = torch.randn(cout, cin, 5, device=dev) * 0.05
@@ -47,3 +50,9 @@ for E, cin, cout in [(750, 64, 64), (600, 64, 128), (600, 128, 128), (450, 128, 
     t1 = timeit(lambda: L.mcnn_meshconv_fwd_tc_sk(x.data_ptr(), gemm.data_ptr(), ec.data_ptr(), None, bias.data_ptr(), out.data_ptr(), img.data_ptr(), None, ws.data_ptr(), B, E, cin, cout, st))
     err = float((out - o0).abs().max() / o0.abs().max())
     print('E %d %d->%d: tiles %d  tile kernel %.1f us, stream-K %.1f us (%.2fx), rel diff %.1e' % (E, cin, cout, (B * E + 127) // 128 * max(1, cout // 256), t0, t1, t0 / t1, err), flush=True)
+    if len(sys.argv) > 1:
+        for gsz in [int(a) for a in sys.argv[1:]]:
+            L.mcnn_debug_set_tc_sk_ctas(gsz)
+            t = timeit(lambda: L.mcnn_meshconv_fwd_tc_sk(x.data_ptr(), gemm.data_ptr(), ec.data_ptr(), None, bias.data_ptr(), out.data_ptr(), img.data_ptr(), None, ws.data_ptr(), B, E, cin, cout, st))
+            print('      grid %d: %.1f us' % (gsz, t), flush=True)
+        L.mcnn_debug_set_tc_sk_ctas(0)

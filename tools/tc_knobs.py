@@ -25,7 +25,7 @@ for E, cin, cout in shapes:
     out = torch.empty(B, E, cout, device=dev)
     wt = torch.empty(2 * 5 * cin, cout, device=dev)
     res = []
-    for knob in (0, 1, 2, 4, 3, 7, 15):
+    for knob in (0, 1, 2, 4, 3, 7, 15, 8, 9):
         L.mcnn_debug_set_tc(knob)
         torch.cuda.synchronize()
         def run():
@@ -39,5 +39,5 @@ for E, cin, cout in shapes:
         res.append(a.elapsed_time(b) / 10 * 1e3)
     L.mcnn_debug_set_tc(0)
     flops = 2.0 * B * E * 5 * cin * cout
-    print('E=%d %d->%d  us: normal %.1f | noload %.1f | nomma %.1f | nosts %.1f | noload+nomma %.1f | all-off %.1f | all-off, no B copies %.1f   (%.1f TFLOP/s fp32-equivalent)'
+    print('E=%d %d->%d  us: normal %.1f | noload %.1f | nomma %.1f | nosts %.1f | noload+nomma %.1f | all-off %.1f | all-off, no B copies %.1f | only B copies off %.1f | B copies + gathers off %.1f  (%.1f TFLOP/s fp32-equivalent)'
           % (E, cin, cout, *res, flops / res[0] / 1e6))
