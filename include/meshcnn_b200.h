@@ -98,6 +98,9 @@ size_t mcnn_meshconv_fwd_tc_sk_ws(void);
 int mcnn_meshconv_fwd_tc_sk(const float* x, const int32_t* gemm, const int32_t* ec, const float* weight,
                             const float* bias, float* out, float* wt_ws, int8_t* signs, void* sk_ws, int B, int E, int Cin,
                             int Cout, void* stream);
+/* diagnostics only: 1 = mcnn_meshconv_bwd_data_tc_signs launches one CTA per (edge tile, channel block) instead of the
+ * persistent kernel (same arithmetic; the scatter order differs) */
+int mcnn_debug_set_tc_bd_tile(int on);
 /* diagnostics only: force the grid size of mcnn_meshconv_fwd_tc_sk (0 = one CTA per SM) */
 int mcnn_debug_set_tc_sk_ctas(int n);
 /* diagnostics only (library built with -DMCNN_TC_PROF): 64 clock64 stamps of one CTA of the last stream-K launch */

@@ -1109,6 +1109,7 @@ static int sm_count() {
 }
 
 static int g_tc_sk_ctas = 0;               // debug: force the stream-K grid size (0 = heuristic)
+static int g_tc_bd_tile = 0;               // debug: 1 = one CTA per item for the data gradient instead of the persistent kernel
 
 template <int N_TILE>
 static int launch_fwd_tc_sk(const float* x, const int32_t* gemm, const int32_t* ec, const float* wt, const float* bias,
@@ -1323,6 +1324,267 @@ meshconv_bwd_data_tc_kernel(const float* __restrict__ dout, const float* __restr
     if (warp == TC_PRODUCER_WARPS) {
         tc::tc_fence_after();
         tc::tmem_dealloc<256>(tmem_base);
+    }
+}
+
+// =============================================================================================================
+// backward, data, persistent form.  The kernel above spends its time in three places that use different parts of the SM
+// and the chip -- per-CTA set-up, a short main loop (2-8 K blocks on the tensor core), and a long epilogue (sign loads,
+// then 5 x 128 x 32 fp32 atomics through L2) -- strictly one after the other, 1200 times per launch.  Here <= one CTA per
+// SM stays resident and walks a contiguous range of (128-edge tile, 32-channel block) items with dedicated warps:
+//   warps 0-7  producers: dout rows of the item's K blocks -> hi/lo split -> st.shared (register prefetch, distance 2)
+//   warp  8    MMA issuer; the accumulator (160 TMEM columns) is double-buffered
+//   warps 9-16 epilogue: tcgen05.ld -> abs/add backward with the kept signs -> red.global.add.v4 scatter
+// so the scatter of item i runs under the main loop of item i + 1, and set-up is paid once per CTA.
+// =============================================================================================================
+constexpr int BDP_PRODUCER_WARPS = 8;
+constexpr int BDP_EPI_WARPS = 8;
+constexpr int BDP_THREADS = (BDP_PRODUCER_WARPS + 1 + BDP_EPI_WARPS) * 32;
+
+__global__ void __launch_bounds__(BDP_THREADS, 1)
+meshconv_bwd_data_tc_p_kernel(const float* __restrict__ dout, const int32_t* __restrict__ gemm, const int32_t* __restrict__ ec,
+                              const float* __restrict__ wtb, float* __restrict__ dx, const int8_t* __restrict__ signs,
+                              int B, int E, int Cin, int Cout) {
+    using S = BdSmem;
+    constexpr int PW = BDP_PRODUCER_WARPS, PT = PW * 32, ET = BDP_EPI_WARPS * 32;
+    constexpr int IT = (TC_M * 8) / PT;                          // 16-byte items per producer thread and K block
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    int (*nb)[5] = reinterpret_cast<int (*)[5]>(smem + S::NB_OFF);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
+    uint64_t* empty_bar = full_bar + S::STAGES;
+    uint64_t* acc_full = empty_bar + S::STAGES;              // [2]
+    uint64_t* acc_empty = acc_full + 2;                      // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int M = B * E;
+    const int num_kb = Cout >> 5, ncb = Cin >> 5;
+    const long long n_items_all = (long long)ceil_div(M, TC_M) * ncb;
+    const int G = gridDim.x, cta = blockIdx.x;
+    const int item0 = (int)(n_items_all * cta / G), item1 = (int)(n_items_all * (cta + 1) / G);
+    const int dbg = g_tc_debug;            // diagnostics (results wrong): 1 no dout loads, 2 no MMA, 4 no st.shared, 16 no scatter, 32 no sign loads
+
+    if (warp == PW) {
+        if (lane == 0) {
+            for (int s = 0; s < S::STAGES; ++s) { tc::mbar_init(full_bar + s, PW); tc::mbar_init(empty_bar + s, 1); }
+            for (int i = 0; i < 2; ++i) { tc::mbar_init(acc_full + i, 1); tc::mbar_init(acc_empty + i, BDP_EPI_WARPS); }
+            tc::fence_barrier_init();
+        }
+        __syncwarp();
+        tc::tmem_alloc<512>(tmem_slot);
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+#ifdef MCNN_TC_PROF
+#define BDP_ACC(cond, idx, expr) do { const long long t0_ = clock64(); expr; if ((cond) && blockIdx.x == g_sk_prof_cta) g_sk_prof[(idx)] += clock64() - t0_; } while (0)
+#else
+#define BDP_ACC(cond, idx, expr) do { expr; } while (0)
+#endif
+    const long long t_begin = clock64();
+    if (warp < PW) {
+        // ======================================== producers ========================================================
+        const int pt = tid;
+        const int n_q = (item1 - item0) * num_kb;                // (item, K block) steps of this CTA
+        struct Regs { float4 a[IT]; };
+        // (item, K block) of the step being loaded / stored are carried along instead of divided out of q: an integer
+        // division by a run-time value is a ~100-cycle dependent chain, and a producer warp has its scheduler to itself
+        struct Cursor {
+            int m0, cb, kb;
+            __device__ __forceinline__ void next(int num_kb, int ncb) {
+                if (++kb == num_kb) { kb = 0; if (++cb == ncb) { cb = 0; m0 += TC_M; } }
+            }
+        };
+        Cursor lc, sc;                                           // load cursor (two steps ahead), store cursor
+        lc.m0 = sc.m0 = (item0 / ncb) * TC_M; lc.cb = sc.cb = item0 % ncb; lc.kb = sc.kb = 0;
+        uint32_t stage = 0, phase = 0;
+        auto load_step = [&](Regs& R) {
+#pragma unroll
+            for (int it = 0; it < IT; ++it) {
+                const int e = pt + it * PT;
+                const int m = lc.m0 + (e >> 3);
+                R.a[it] = (m < M && !(dbg & 1)) ? __ldg(reinterpret_cast<const float4*>(dout + (size_t)m * Cout + (lc.kb << 5) + ((e & 7) << 2))) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            lc.next(num_kb, ncb);
+        };
+        auto store_step = [&](const Regs& R) {
+            const uint32_t s = stage, ph = phase;
+            if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
+            BDP_ACC(tid == 0, 1, if (lane == 0) tc::mbar_wait(empty_bar + s, ph ^ 1); __syncwarp());
+            const uint32_t a_hi = tc::smem_u32(smem + s * S::STAGE_BYTES), a_lo = a_hi + S::A_BYTES;
+            if (tid == 0 && !(dbg & 8)) {                                 // B tile: two bulk copies of the pre-built image
+                unsigned char* b_hi = smem + s * S::STAGE_BYTES + 2 * S::A_BYTES;
+                tc::mbar_expect_tx(full_bar + s, 2 * S::B_BYTES);
+                const float* src = wtb + ((size_t)sc.cb * num_kb + sc.kb) * (BD_N * 32);
+                tc::bulk_g2s(b_hi, src, S::B_BYTES, full_bar + s);
+                tc::bulk_g2s(b_hi + S::B_BYTES, src + (size_t)5 * Cin * Cout, S::B_BYTES, full_bar + s);
+            }
+            sc.next(num_kb, ncb);
+#pragma unroll
+            for (int it = 0; it < ((dbg & 4) ? 0 : IT); ++it) {
+                const int e = pt + it * PT;
+                float4 hi, lo;
+                tc::split4(R.a[it], hi, lo);
+                const uint32_t off = tc::sw128_off(e >> 3, e & 7);
+                tc::sts128(a_hi + off, hi);
+                tc::sts128(a_lo + off, lo);
+            }
+            BDP_ACC(tid == 0, 2, if (!(dbg & 64)) tc::fence_proxy_async_smem(); __syncwarp(); if (lane == 0) tc::mbar_arrive(full_bar + s));
+        };
+        Regs R0, R1;
+        if (n_q > 0) load_step(R0);
+        if (n_q > 1) load_step(R1);
+        for (int q = 0; q < n_q; q += 2) {
+            store_step(R0);
+            if (q + 2 < n_q) load_step(R0);
+            if (q + 1 < n_q) {
+                store_step(R1);
+                if (q + 3 < n_q) load_step(R1);
+            }
+        }
+#ifdef MCNN_TC_PROF
+        if (tid == 0 && blockIdx.x == g_sk_prof_cta) { g_sk_prof[0] += clock64() - t_begin; g_sk_prof[3] += n_q; }
+#endif
+    } else if (warp == PW) {
+        // ======================================== MMA issuer ========================================================
+        constexpr uint32_t idesc = tc::make_idesc_tf32(BD_N);
+        uint32_t stage = 0, phase = 0;
+        for (int item = item0; item < item1; ++item) {
+            const int i = item - item0, buf = i & 1;
+            const uint32_t acc = tmem_base + (uint32_t)(buf * 256);
+            if (i >= 2) {
+                BDP_ACC(lane == 0, 5, tc::mbar_wait(acc_empty + buf, ((i >> 1) - 1) & 1));
+                tc::tc_fence_after();
+            }
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const uint32_t s = stage, ph = phase;
+                if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
+                BDP_ACC(lane == 0, 6, tc::mbar_wait(full_bar + s, ph));
+                tc::tc_fence_after();
+                if (tc::elect_one()) {
+#ifdef MCNN_TC_PROF
+                    const long long tm0 = clock64();
+#endif
+                    const uint32_t a_hi = tc::smem_u32(smem + s * S::STAGE_BYTES);
+                    const uint32_t a_lo = a_hi + S::A_BYTES;
+                    const uint32_t b_hi = a_lo + S::A_BYTES;
+                    const uint32_t b_lo = b_hi + S::B_BYTES;
+#pragma unroll
+                    for (int kk = 0; kk < ((dbg & 2) ? 0 : 4); ++kk) {
+                        const uint64_t dah = tc::make_desc_sw128(a_hi + kk * 32), dal = tc::make_desc_sw128(a_lo + kk * 32);
+                        const uint64_t dbh = tc::make_desc_sw128(b_hi + kk * 32), dbl = tc::make_desc_sw128(b_lo + kk * 32);
+                        tc::mma_tf32(acc, dah, dbh, idesc, (kb | kk) != 0);
+                        tc::mma_tf32(acc, dah, dbl, idesc, 1);
+                        tc::mma_tf32(acc, dal, dbh, idesc, 1);
+                    }
+#ifdef MCNN_TC_PROF
+                    const long long tc0 = clock64();
+#endif
+                    tc::mma_commit(empty_bar + s);
+                    if (kb == num_kb - 1) tc::mma_commit(acc_full + buf);
+#ifdef MCNN_TC_PROF
+                    if (blockIdx.x == g_sk_prof_cta) { g_sk_prof[9] += clock64() - tc0; g_sk_prof[10] += tc0 - tm0; }
+#endif
+                }
+                __syncwarp();
+            }
+        }
+#ifdef MCNN_TC_PROF
+        if (lane == 0 && blockIdx.x == g_sk_prof_cta) g_sk_prof[4] += clock64() - t_begin;
+#endif
+        tc::tc_fence_before();
+    } else {
+        // ======================================== epilogue: abs/add backward + scatter =========
+        const int et = tid - (PW + 1) * 32;                      // 0 .. 255
+        const int lane_grp = warp & 3;                           // the TMEM lane quarter this warp may read
+        const int r = lane_grp * 32 + lane;
+        const int cl0 = ((warp - (PW + 1)) >> 2) * 16;           // the two warps of a lane quarter split the 32 channels
+        int cur_mt = -1;
+        int n1 = -1, n2 = -1, n3 = -1, n4 = -1;
+        bool padded = false;
+        int mt = item0 / ncb, cb = item0 % ncb;
+        for (int item = item0; item < item1; ++item, cb = (cb + 1 == ncb) ? 0 : cb + 1, mt += (cb == 0)) {
+            const int i = item - item0, buf = i & 1;
+            const int m0 = mt * TC_M, m = m0 + r;
+            if (mt != cur_mt) {                                  // scatter targets of this thread's edge (once per edge tile)
+                cur_mt = mt;
+                n1 = n2 = n3 = n4 = -1; padded = false;
+                if (m < M) {
+                    const int b = m / E, e = m - b * E;
+                    if (e >= __ldg(ec + b)) padded = true;
+                    else {
+                        const int4 gq = __ldg(reinterpret_cast<const int4*>(gemm) + m);
+                        n1 = gq.x < 0 ? -1 : b * E + gq.x; n2 = gq.y < 0 ? -1 : b * E + gq.y;
+                        n3 = gq.z < 0 ? -1 : b * E + gq.z; n4 = gq.w < 0 ? -1 : b * E + gq.w;
+                    }
+                }
+            }
+            const int c0 = cb * 32 + cl0;
+            // the signs do not depend on the accumulator: fetch them while the tensor core still works on this item
+            uint4 sg13 = make_uint4(0, 0, 0, 0), sg24 = make_uint4(0, 0, 0, 0);
+            if (m < M && !padded && !(dbg & 32)) {
+                sg13 = __ldg(reinterpret_cast<const uint4*>(signs + (size_t)m * Cin + c0));
+                sg24 = __ldg(reinterpret_cast<const uint4*>(signs + ((size_t)M + m) * Cin + c0));
+            }
+            BDP_ACC(et == 0, 8, tc::mbar_wait(acc_full + buf, (i >> 1) & 1));
+            tc::tc_fence_after();
+            const uint32_t acc = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(buf * 256 + cl0);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                float g[5][8];
+#pragma unroll
+                for (int k5 = 0; k5 < 5; ++k5) tc::tmem_ld8_nowait(acc + (uint32_t)(k5 * 32 + half * 8), g[k5]);
+                tc::tmem_wait_ld();
+                if (half == 1) {                                 // accumulator drained: the tensor core may start item i + 2
+                    tc::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive(acc_empty + buf);
+                }
+                if (m >= M || (dbg & 16)) continue;
+                float* d0 = dx + c0 + half * 8;
+                if (padded) {
+                    float* d = d0 + (size_t)((m / E) * E) * Cin;
+#pragma unroll
+                    for (int j = 0; j < 8; j += 4)
+                        tc::red_add_v4(d + j, g[0][j] + 2.f * (g[1][j] + g[2][j]), g[0][j + 1] + 2.f * (g[1][j + 1] + g[2][j + 1]),
+                                       g[0][j + 2] + 2.f * (g[1][j + 2] + g[2][j + 2]), g[0][j + 3] + 2.f * (g[1][j + 3] + g[2][j + 3]));
+                    continue;
+                }
+                const uint32_t w13[2] = {half ? sg13.z : sg13.x, half ? sg13.w : sg13.y};
+                const uint32_t w24[2] = {half ? sg24.z : sg24.x, half ? sg24.w : sg24.y};
+#pragma unroll
+                for (int j = 0; j < 8; j += 4) {
+                    float s13[4], s24[4];
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        s13[t] = (float)(int)(signed char)((w13[j >> 2] >> (8 * t)) & 0xff);
+                        s24[t] = (float)(int)(signed char)((w24[j >> 2] >> (8 * t)) & 0xff);
+                    }
+                    tc::red_add_v4(d0 + (size_t)m * Cin + j, g[0][j], g[0][j + 1], g[0][j + 2], g[0][j + 3]);
+                    if (n1 >= 0) tc::red_add_v4(d0 + (size_t)n1 * Cin + j, g[1][j] + s13[0] * g[3][j], g[1][j + 1] + s13[1] * g[3][j + 1],
+                                                g[1][j + 2] + s13[2] * g[3][j + 2], g[1][j + 3] + s13[3] * g[3][j + 3]);
+                    if (n3 >= 0) tc::red_add_v4(d0 + (size_t)n3 * Cin + j, g[1][j] - s13[0] * g[3][j], g[1][j + 1] - s13[1] * g[3][j + 1],
+                                                g[1][j + 2] - s13[2] * g[3][j + 2], g[1][j + 3] - s13[3] * g[3][j + 3]);
+                    if (n2 >= 0) tc::red_add_v4(d0 + (size_t)n2 * Cin + j, g[2][j] + s24[0] * g[4][j], g[2][j + 1] + s24[1] * g[4][j + 1],
+                                                g[2][j + 2] + s24[2] * g[4][j + 2], g[2][j + 3] + s24[3] * g[4][j + 3]);
+                    if (n4 >= 0) tc::red_add_v4(d0 + (size_t)n4 * Cin + j, g[2][j] - s24[0] * g[4][j], g[2][j + 1] - s24[1] * g[4][j + 1],
+                                                g[2][j + 2] - s24[2] * g[4][j + 2], g[2][j + 3] - s24[3] * g[4][j + 3]);
+                }
+            }
+        }
+#ifdef MCNN_TC_PROF
+        if (et == 0 && blockIdx.x == g_sk_prof_cta) g_sk_prof[7] += clock64() - t_begin;
+#endif
+        (void)et; (void)nb;
+        tc::tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == PW) {
+        tc::tc_fence_after();
+        tc::tmem_dealloc<512>(tmem_base);
     }
 }
 
@@ -1655,6 +1917,8 @@ extern "C" int mcnn_meshconv_fwd_tc_sk(const float* x, const int32_t* gemm, cons
     return launch_fwd_tc_sk<64>(x, gemm, ec, wt_ws, bias, out, signs, sk_ws, B, E, Cin, Cout, st);
 }
 
+extern "C" int mcnn_debug_set_tc_bd_tile(int on) { g_tc_bd_tile = on ? 1 : 0; return MCNN_OK; }
+
 extern "C" int mcnn_debug_set_tc_sk_ctas(int n) { g_tc_sk_ctas = n > 0 ? (n > SK_MAX_CTAS ? SK_MAX_CTAS : n) : 0; return MCNN_OK; }
 
 
@@ -1681,6 +1945,18 @@ extern "C" int mcnn_meshconv_bwd_data_tc_signs(const float* dout, const float* x
         cudaError_t e = cudaFuncSetAttribute(meshconv_bwd_data_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BdSmem::TOTAL);
         if (e != cudaSuccess) { g_last_error = e; return MCNN_E_CUDA; }
         configured = true;
+    }
+    if (signs != nullptr && !g_tc_bd_tile) {                 // persistent kernel (needs the signs kept by the forward)
+        static bool configured_p = false;
+        if (!configured_p) {
+            cudaError_t e = cudaFuncSetAttribute(meshconv_bwd_data_tc_p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BdSmem::TOTAL);
+            if (e != cudaSuccess) { g_last_error = e; return MCNN_E_CUDA; }
+            configured_p = true;
+        }
+        const long long items = (long long)ceil_div(B * E, TC_M) * (Cin / 32);
+        const int G = (int)min((long long)sm_count(), items);
+        meshconv_bwd_data_tc_p_kernel<<<G, BDP_THREADS, BdSmem::TOTAL, st>>>(dout, gemm, ec, wtb_ws, dx, signs, B, E, Cin, Cout);
+        return after_launch();
     }
     dim3 grid(ceil_div(B * E, TC_M), Cin / 32);
     meshconv_bwd_data_tc_kernel<<<grid, TC_THREADS, BdSmem::TOTAL, st>>>(dout, x, gemm, ec, wtb_ws, dx, signs, B, E, Cin, Cout);

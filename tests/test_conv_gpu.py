@@ -202,3 +202,32 @@ def test_conv_stream_k_kernel_matches_tile_kernel(cin, cout, B, ctas):
     assert close(g2.cpu().numpy(), g1.cpu().numpy(), 1e-5)          # same signs; the scatter atomics reorder sums
     if ctas == 1:
         assert torch.equal(y2, y1)
+
+
+@pytest.mark.parametrize('cin,cout,B', [(64, 64, 24), (128, 256, 9), (256, 256, 23), (256, 64, 5), (32, 192, 3), (256, 256, 1)])
+def test_conv_persistent_data_gradient_matches_tile_kernel(cin, cout, B):
+    """The persistent data-gradient kernel (dedicated producer / MMA / scatter warps walking a range of items) against the
+    one-CTA-per-item kernel: identical products and signs, only the order of the scatter atomics differs."""
+    from meshcnn_b200 import _lib, synth
+    from meshcnn_b200.mesh_conv import MeshConv
+    from tests.gpu_util import DEV, product_mesh
+    meshes = [product_mesh(*synth.make('ico' if s % 3 else 'torus', s, **(dict(nu=5) if s % 3 else dict(m=10, n=25)))) for s in range(B)]
+    torch.manual_seed(cin + cout + B)
+    conv = MeshConv(cin, cout, bias=True).to(DEV)
+    x = torch.randn(B, cin, 750, device=DEV)
+    dy = torch.randn(B, cout, 750, 1, device=DEV)
+    L = _lib.lib()
+
+    def run():
+        xg = x.clone().requires_grad_(True)
+        conv(xg, meshes).backward(dy)
+        torch.cuda.synchronize()
+        return xg.grad.clone()
+    try:
+        L.mcnn_debug_set_tc_bd_tile(1)
+        g1 = run()
+        L.mcnn_debug_set_tc_bd_tile(0)
+        g2 = run()
+    finally:
+        L.mcnn_debug_set_tc_bd_tile(0)
+    assert close(g2.cpu().numpy(), g1.cpu().numpy(), 2e-6)
