@@ -1136,6 +1136,12 @@ static int launch_fwd_tc_sk(const float* x, const int32_t* gemm, const int32_t* 
 //   A = dout rows (K-major as they lie in memory), B = weight re-laid as wtb[(cb*160 + k5*32 + cl)][o] (K-major).
 // =============================================================================================================
 constexpr int BD_N = 160;
+// Accumulator column (within a tap's block of 32) of input channel cl (within the CTA's block of 32).  Permuted so that
+// the mma-fragment TMEM load (tcgen05.ld .16x256b.x2 at column 0 or 16 of the block) hands thread t of a warp the four
+// CONSECUTIVE channels 16*h + 4*(t%4) .. +3 of an edge row: the four threads of a quad then scatter 64 contiguous bytes of
+// one dx row with one red.v4 each, and a warp instruction touches 8 rows instead of 32 (the scatter is bound by the
+// number of distinct lines per instruction, one L1 wavefront each).
+__host__ __device__ constexpr int bd_col(int cl) { return 8 * (2 * (cl >> 4) + ((cl >> 1) & 1)) + 2 * ((cl & 15) >> 2) + (cl & 1); }
 
 struct BdSmem {
     static constexpr int A_BYTES = TC_M * 128;
@@ -1148,7 +1154,7 @@ struct BdSmem {
 };
 
 // weight [Cout][Cin][5] -> B operand image of the data-gradient GEMM, TF32 head / remainder:
-//   img[hi|lo][cb][kb][160 rows x 128 bytes swizzled],  row n = k5*32 + cl (c = cb*32 + cl),  K = output channels
+//   img[hi|lo][cb][kb][160 rows x 128 bytes swizzled],  row n = k5*32 + bd_col(cl) (c = cb*32 + cl),  K = output channels
 __global__ void weight_tc_bwd_layout_kernel(const float* __restrict__ w, float* __restrict__ img, int Cin, int Cout) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= 5 * Cin * Cout) return;
@@ -1158,7 +1164,8 @@ __global__ void weight_tc_bwd_layout_kernel(const float* __restrict__ w, float* 
     const int kb = o >> 5, p = o & 31;
     float hi, lo;
     tc::split_tf32(w[((size_t)o * Cin + c) * 5 + k5], hi, lo);
-    const size_t off = ((size_t)cb * (Cout >> 5) + kb) * (BD_N * 32) + (tc::sw128_off(n, p >> 2) >> 2) + (p & 3);
+    const int nrow = k5 * 32 + bd_col(n & 31);                 // B row = accumulator column of (tap, channel)
+    const size_t off = ((size_t)cb * (Cout >> 5) + kb) * (BD_N * 32) + (tc::sw128_off(nrow, p >> 2) >> 2) + (p & 3);
     img[off] = hi;
     img[(size_t)5 * Cin * Cout + off] = lo;
 }
@@ -1249,7 +1256,7 @@ meshconv_bwd_data_tc_kernel(const float* __restrict__ dout, const float* __restr
         const int r = lane_grp * 32 + lane;
         const int m = m0 + r;
         const int cl0 = (warp >> 2) * 16;                     // the two warps of a lane group split the 32 channels
-        float g[5][16];
+        float g[5][16];                                        // g[k5][bd_col(co)] = tap k5, channel c0 + co (columns are permuted)
 #pragma unroll
         for (int k5 = 0; k5 < 5; ++k5) tc::tmem_ld16(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(k5 * 32 + cl0), g[k5]);
         if (m < M && !(dbg & 16)) {
@@ -1259,8 +1266,8 @@ meshconv_bwd_data_tc_kernel(const float* __restrict__ dout, const float* __restr
                 float* d = dx + (size_t)(b * E) * Cin + c0;
 #pragma unroll
                 for (int j = 0; j < 16; j += 4)
-                    tc::red_add_v4(d + j, g[0][j] + 2.f * (g[1][j] + g[2][j]), g[0][j + 1] + 2.f * (g[1][j + 1] + g[2][j + 1]),
-                                   g[0][j + 2] + 2.f * (g[1][j + 2] + g[2][j + 2]), g[0][j + 3] + 2.f * (g[1][j + 3] + g[2][j + 3]));
+                    tc::red_add_v4(d + j, g[0][bd_col(j)] + 2.f * (g[1][bd_col(j)] + g[2][bd_col(j)]), g[0][bd_col(j + 1)] + 2.f * (g[1][bd_col(j + 1)] + g[2][bd_col(j + 1)]),
+                                   g[0][bd_col(j + 2)] + 2.f * (g[1][bd_col(j + 2)] + g[2][bd_col(j + 2)]), g[0][bd_col(j + 3)] + 2.f * (g[1][bd_col(j + 3)] + g[2][bd_col(j + 3)]));
             } else {
                 const int n1 = nb[r][1], n2 = nb[r][2], n3 = nb[r][3], n4 = nb[r][4];
                 const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1280,15 +1287,15 @@ meshconv_bwd_data_tc_kernel(const float* __restrict__ dout, const float* __restr
                         s13[0] = sgn(f1.x - f3.x); s13[1] = sgn(f1.y - f3.y); s13[2] = sgn(f1.z - f3.z); s13[3] = sgn(f1.w - f3.w);
                         s24[0] = sgn(f2.x - f4.x); s24[1] = sgn(f2.y - f4.y); s24[2] = sgn(f2.z - f4.z); s24[3] = sgn(f2.w - f4.w);
                     }
-                    tc::red_add_v4(dx + (size_t)m * Cin + c0 + j, g[0][j], g[0][j + 1], g[0][j + 2], g[0][j + 3]);
-                    if (n1 >= 0) tc::red_add_v4(dx + (size_t)n1 * Cin + c0 + j, g[1][j] + s13[0] * g[3][j], g[1][j + 1] + s13[1] * g[3][j + 1],
-                                                g[1][j + 2] + s13[2] * g[3][j + 2], g[1][j + 3] + s13[3] * g[3][j + 3]);
-                    if (n3 >= 0) tc::red_add_v4(dx + (size_t)n3 * Cin + c0 + j, g[1][j] - s13[0] * g[3][j], g[1][j + 1] - s13[1] * g[3][j + 1],
-                                                g[1][j + 2] - s13[2] * g[3][j + 2], g[1][j + 3] - s13[3] * g[3][j + 3]);
-                    if (n2 >= 0) tc::red_add_v4(dx + (size_t)n2 * Cin + c0 + j, g[2][j] + s24[0] * g[4][j], g[2][j + 1] + s24[1] * g[4][j + 1],
-                                                g[2][j + 2] + s24[2] * g[4][j + 2], g[2][j + 3] + s24[3] * g[4][j + 3]);
-                    if (n4 >= 0) tc::red_add_v4(dx + (size_t)n4 * Cin + c0 + j, g[2][j] - s24[0] * g[4][j], g[2][j + 1] - s24[1] * g[4][j + 1],
-                                                g[2][j + 2] - s24[2] * g[4][j + 2], g[2][j + 3] - s24[3] * g[4][j + 3]);
+                    tc::red_add_v4(dx + (size_t)m * Cin + c0 + j, g[0][bd_col(j)], g[0][bd_col(j + 1)], g[0][bd_col(j + 2)], g[0][bd_col(j + 3)]);
+                    if (n1 >= 0) tc::red_add_v4(dx + (size_t)n1 * Cin + c0 + j, g[1][bd_col(j)] + s13[0] * g[3][bd_col(j)], g[1][bd_col(j + 1)] + s13[1] * g[3][bd_col(j + 1)],
+                                                g[1][bd_col(j + 2)] + s13[2] * g[3][bd_col(j + 2)], g[1][bd_col(j + 3)] + s13[3] * g[3][bd_col(j + 3)]);
+                    if (n3 >= 0) tc::red_add_v4(dx + (size_t)n3 * Cin + c0 + j, g[1][bd_col(j)] - s13[0] * g[3][bd_col(j)], g[1][bd_col(j + 1)] - s13[1] * g[3][bd_col(j + 1)],
+                                                g[1][bd_col(j + 2)] - s13[2] * g[3][bd_col(j + 2)], g[1][bd_col(j + 3)] - s13[3] * g[3][bd_col(j + 3)]);
+                    if (n2 >= 0) tc::red_add_v4(dx + (size_t)n2 * Cin + c0 + j, g[2][bd_col(j)] + s24[0] * g[4][bd_col(j)], g[2][bd_col(j + 1)] + s24[1] * g[4][bd_col(j + 1)],
+                                                g[2][bd_col(j + 2)] + s24[2] * g[4][bd_col(j + 2)], g[2][bd_col(j + 3)] + s24[3] * g[4][bd_col(j + 3)]);
+                    if (n4 >= 0) tc::red_add_v4(dx + (size_t)n4 * Cin + c0 + j, g[2][bd_col(j)] - s24[0] * g[4][bd_col(j)], g[2][bd_col(j + 1)] - s24[1] * g[4][bd_col(j + 1)],
+                                                g[2][bd_col(j + 2)] - s24[2] * g[4][bd_col(j + 2)], g[2][bd_col(j + 3)] - s24[3] * g[4][bd_col(j + 3)]);
                 }
             }
         }
@@ -1498,87 +1505,97 @@ meshconv_bwd_data_tc_p_kernel(const float* __restrict__ dout, const int32_t* __r
         tc::tc_fence_before();
     } else {
         // ======================================== epilogue: abs/add backward + scatter =========
-        const int et = tid - (PW + 1) * 32;                      // 0 .. 255
-        const int lane_grp = warp & 3;                           // the TMEM lane quarter this warp may read
-        const int r = lane_grp * 32 + lane;
-        const int cl0 = ((warp - (PW + 1)) >> 2) * 16;           // the two warps of a lane quarter split the 32 channels
-        int cur_mt = -1;
-        int n1 = -1, n2 = -1, n3 = -1, n4 = -1;
-        bool padded = false;
+        // Warp (lane quarter lq, channel half hb) reads its accumulator lanes in two passes of 16 with the mma-fragment
+        // load: thread t holds rows rsub = t/4 and rsub + 8 of the pass, channels c0 .. c0+3 with c0 = 16 hb + 4 (t%4).
+        const int lq = warp & 3, hb = (warp - (PW + 1)) >> 2;
+        const int rsub = lane >> 2, q4 = lane & 3;
         int mt = item0 / ncb, cb = item0 % ncb;
+        int cur_mt = -1;
+        int tgt[4][5];                                           // per row (pass, +0 / +8): dx row of self, n1, n2, n3, n4 (-1: none)
+        bool pad[4];
         for (int item = item0; item < item1; ++item, cb = (cb + 1 == ncb) ? 0 : cb + 1, mt += (cb == 0)) {
             const int i = item - item0, buf = i & 1;
-            const int m0 = mt * TC_M, m = m0 + r;
-            if (mt != cur_mt) {                                  // scatter targets of this thread's edge (once per edge tile)
+            const int m0 = mt * TC_M;
+            if (mt != cur_mt) {                                  // scatter targets of this thread's four edges (once per edge tile)
                 cur_mt = mt;
-                n1 = n2 = n3 = n4 = -1; padded = false;
-                if (m < M) {
-                    const int b = m / E, e = m - b * E;
-                    if (e >= __ldg(ec + b)) padded = true;
-                    else {
-                        const int4 gq = __ldg(reinterpret_cast<const int4*>(gemm) + m);
-                        n1 = gq.x < 0 ? -1 : b * E + gq.x; n2 = gq.y < 0 ? -1 : b * E + gq.y;
-                        n3 = gq.z < 0 ? -1 : b * E + gq.z; n4 = gq.w < 0 ? -1 : b * E + gq.w;
+#pragma unroll
+                for (int rr = 0; rr < 4; ++rr) {
+                    const int m = m0 + lq * 32 + (rr >> 1) * 16 + rsub + (rr & 1) * 8;
+                    tgt[rr][0] = tgt[rr][1] = tgt[rr][2] = tgt[rr][3] = tgt[rr][4] = -1; pad[rr] = false;
+                    if (m < M) {
+                        const int b = m / E, e = m - b * E;
+                        if (e >= __ldg(ec + b)) { pad[rr] = true; tgt[rr][0] = b * E; }
+                        else {
+                            const int4 gq = __ldg(reinterpret_cast<const int4*>(gemm) + m);
+                            tgt[rr][0] = m;
+                            tgt[rr][1] = gq.x < 0 ? -1 : b * E + gq.x; tgt[rr][2] = gq.y < 0 ? -1 : b * E + gq.y;
+                            tgt[rr][3] = gq.z < 0 ? -1 : b * E + gq.z; tgt[rr][4] = gq.w < 0 ? -1 : b * E + gq.w;
+                        }
                     }
                 }
             }
-            const int c0 = cb * 32 + cl0;
+            const int c0 = cb * 32 + hb * 16 + 4 * q4;
             // the signs do not depend on the accumulator: fetch them while the tensor core still works on this item
-            uint4 sg13 = make_uint4(0, 0, 0, 0), sg24 = make_uint4(0, 0, 0, 0);
-            if (m < M && !padded && !(dbg & 32)) {
-                sg13 = __ldg(reinterpret_cast<const uint4*>(signs + (size_t)m * Cin + c0));
-                sg24 = __ldg(reinterpret_cast<const uint4*>(signs + ((size_t)M + m) * Cin + c0));
+            uint32_t sg13[4], sg24[4];
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+                sg13[rr] = sg24[rr] = 0;
+                if (tgt[rr][0] >= 0 && !pad[rr] && !(dbg & 32)) {
+                    sg13[rr] = __ldg(reinterpret_cast<const uint32_t*>(signs + (size_t)tgt[rr][0] * Cin + c0));
+                    sg24[rr] = __ldg(reinterpret_cast<const uint32_t*>(signs + ((size_t)M + tgt[rr][0]) * Cin + c0));
+                }
             }
-            BDP_ACC(et == 0, 8, tc::mbar_wait(acc_full + buf, (i >> 1) & 1));
+            BDP_ACC(lane == 0 && warp == PW + 1, 8, tc::mbar_wait(acc_full + buf, (i >> 1) & 1));
             tc::tc_fence_after();
-            const uint32_t acc = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(buf * 256 + cl0);
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
+            for (int pass = 0; pass < 2; ++pass) {
                 float g[5][8];
+                const uint32_t acc = tmem_base + ((uint32_t)(lq * 32 + pass * 16) << 16) + (uint32_t)(buf * 256 + hb * 16);
 #pragma unroll
-                for (int k5 = 0; k5 < 5; ++k5) tc::tmem_ld8_nowait(acc + (uint32_t)(k5 * 32 + half * 8), g[k5]);
+                for (int k5 = 0; k5 < 5; ++k5) tc::tmem_ld_16x256b_x2_nowait(acc + (uint32_t)(k5 * 32), g[k5]);
                 tc::tmem_wait_ld();
-                if (half == 1) {                                 // accumulator drained: the tensor core may start item i + 2
+                if (pass == 1) {                                 // accumulator drained: the tensor core may start item i + 2
                     tc::tc_fence_before();
                     __syncwarp();
                     if (lane == 0) tc::mbar_arrive(acc_empty + buf);
                 }
-                if (m >= M || (dbg & 16)) continue;
-                float* d0 = dx + c0 + half * 8;
-                if (padded) {
-                    float* d = d0 + (size_t)((m / E) * E) * Cin;
+                if (dbg & 16) continue;
 #pragma unroll
-                    for (int j = 0; j < 8; j += 4)
-                        tc::red_add_v4(d + j, g[0][j] + 2.f * (g[1][j] + g[2][j]), g[0][j + 1] + 2.f * (g[1][j + 1] + g[2][j + 1]),
-                                       g[0][j + 2] + 2.f * (g[1][j + 2] + g[2][j + 2]), g[0][j + 3] + 2.f * (g[1][j + 3] + g[2][j + 3]));
-                    continue;
-                }
-                const uint32_t w13[2] = {half ? sg13.z : sg13.x, half ? sg13.w : sg13.y};
-                const uint32_t w24[2] = {half ? sg24.z : sg24.x, half ? sg24.w : sg24.y};
+                for (int j2 = 0; j2 < 2; ++j2) {
+                    const int rr = pass * 2 + j2;
+                    if (tgt[rr][0] < 0) continue;
+                    // channels c0 .. c0+3 of this row: registers (0, 1, 4, 5) for the row at +0, (2, 3, 6, 7) for the row at +8
+                    float v[5][4];
 #pragma unroll
-                for (int j = 0; j < 8; j += 4) {
+                    for (int k5 = 0; k5 < 5; ++k5) { v[k5][0] = g[k5][2 * j2]; v[k5][1] = g[k5][2 * j2 + 1]; v[k5][2] = g[k5][4 + 2 * j2]; v[k5][3] = g[k5][5 + 2 * j2]; }
+                    float* d0 = dx + c0;
+                    if (pad[rr]) {
+                        tc::red_add_v4(d0 + (size_t)tgt[rr][0] * Cin, v[0][0] + 2.f * (v[1][0] + v[2][0]), v[0][1] + 2.f * (v[1][1] + v[2][1]),
+                                       v[0][2] + 2.f * (v[1][2] + v[2][2]), v[0][3] + 2.f * (v[1][3] + v[2][3]));
+                        continue;
+                    }
                     float s13[4], s24[4];
 #pragma unroll
                     for (int t = 0; t < 4; ++t) {
-                        s13[t] = (float)(int)(signed char)((w13[j >> 2] >> (8 * t)) & 0xff);
-                        s24[t] = (float)(int)(signed char)((w24[j >> 2] >> (8 * t)) & 0xff);
+                        s13[t] = (float)(int)(signed char)((sg13[rr] >> (8 * t)) & 0xff);
+                        s24[t] = (float)(int)(signed char)((sg24[rr] >> (8 * t)) & 0xff);
                     }
-                    tc::red_add_v4(d0 + (size_t)m * Cin + j, g[0][j], g[0][j + 1], g[0][j + 2], g[0][j + 3]);
-                    if (n1 >= 0) tc::red_add_v4(d0 + (size_t)n1 * Cin + j, g[1][j] + s13[0] * g[3][j], g[1][j + 1] + s13[1] * g[3][j + 1],
-                                                g[1][j + 2] + s13[2] * g[3][j + 2], g[1][j + 3] + s13[3] * g[3][j + 3]);
-                    if (n3 >= 0) tc::red_add_v4(d0 + (size_t)n3 * Cin + j, g[1][j] - s13[0] * g[3][j], g[1][j + 1] - s13[1] * g[3][j + 1],
-                                                g[1][j + 2] - s13[2] * g[3][j + 2], g[1][j + 3] - s13[3] * g[3][j + 3]);
-                    if (n2 >= 0) tc::red_add_v4(d0 + (size_t)n2 * Cin + j, g[2][j] + s24[0] * g[4][j], g[2][j + 1] + s24[1] * g[4][j + 1],
-                                                g[2][j + 2] + s24[2] * g[4][j + 2], g[2][j + 3] + s24[3] * g[4][j + 3]);
-                    if (n4 >= 0) tc::red_add_v4(d0 + (size_t)n4 * Cin + j, g[2][j] - s24[0] * g[4][j], g[2][j + 1] - s24[1] * g[4][j + 1],
-                                                g[2][j + 2] - s24[2] * g[4][j + 2], g[2][j + 3] - s24[3] * g[4][j + 3]);
+                    tc::red_add_v4(d0 + (size_t)tgt[rr][0] * Cin, v[0][0], v[0][1], v[0][2], v[0][3]);
+                    if (tgt[rr][1] >= 0) tc::red_add_v4(d0 + (size_t)tgt[rr][1] * Cin, v[1][0] + s13[0] * v[3][0], v[1][1] + s13[1] * v[3][1],
+                                                        v[1][2] + s13[2] * v[3][2], v[1][3] + s13[3] * v[3][3]);
+                    if (tgt[rr][3] >= 0) tc::red_add_v4(d0 + (size_t)tgt[rr][3] * Cin, v[1][0] - s13[0] * v[3][0], v[1][1] - s13[1] * v[3][1],
+                                                        v[1][2] - s13[2] * v[3][2], v[1][3] - s13[3] * v[3][3]);
+                    if (tgt[rr][2] >= 0) tc::red_add_v4(d0 + (size_t)tgt[rr][2] * Cin, v[2][0] + s24[0] * v[4][0], v[2][1] + s24[1] * v[4][1],
+                                                        v[2][2] + s24[2] * v[4][2], v[2][3] + s24[3] * v[4][3]);
+                    if (tgt[rr][4] >= 0) tc::red_add_v4(d0 + (size_t)tgt[rr][4] * Cin, v[2][0] - s24[0] * v[4][0], v[2][1] - s24[1] * v[4][1],
+                                                        v[2][2] - s24[2] * v[4][2], v[2][3] - s24[3] * v[4][3]);
                 }
             }
         }
 #ifdef MCNN_TC_PROF
-        if (et == 0 && blockIdx.x == g_sk_prof_cta) g_sk_prof[7] += clock64() - t_begin;
+        if (lane == 0 && warp == PW + 1 && blockIdx.x == g_sk_prof_cta) g_sk_prof[7] += clock64() - t_begin;
 #endif
-        (void)et; (void)nb;
+        (void)nb;
         tc::tc_fence_before();
     }
     __syncthreads();
