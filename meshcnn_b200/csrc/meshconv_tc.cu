@@ -1638,6 +1638,7 @@ meshconv_bwd_weight_tc_kernel(const float* __restrict__ dout, const float* __res
     const int split = blockIdx.x, o0 = blockIdx.y * 128, cb = blockIdx.z;
     const int mbeg = split * rows_per_split, mend = min(M, mbeg + rows_per_split);
     const int num_kb = (mend > mbeg) ? (mend - mbeg + 31) >> 5 : 0;
+    const int dbg = g_tc_debug;            // diagnostics (results wrong): 1 no global loads, 2 no MMA, 4 no st.shared
 
     if (warp == TC_PRODUCER_WARPS) {
         if (lane == 0) {
@@ -1662,11 +1663,16 @@ meshconv_bwd_weight_tc_kernel(const float* __restrict__ dout, const float* __res
         struct Data { float4 a[4]; float4 f[5]; };
         const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
         const int bk = pt >> 3, bq = pt & 7;                                // this thread's edge-in-block and channel chunk (B operand)
+        // load_idx is called for kb = 0, 1, 2, ... in order: the (mesh, edge) of this thread's row is carried along instead
+        // of divided out of m every K block (an integer division by a run-time E is a ~100-cycle dependent chain)
+        int nb_b = (mbeg + bk) / E, nb_e = (mbeg + bk) - nb_b * E;
         auto load_idx = [&](int kb) {
             Idx I; I.s0 = I.s1 = I.s2 = I.s3 = I.s4 = -1;
             const int m = mbeg + (kb << 5) + bk;
+            const int b = nb_b, e = nb_e;
+            nb_e += 32;
+            while (nb_e >= E) { nb_e -= E; ++nb_b; }
             if (m < mend) {
-                const int b = m / E, e = m - b * E;
                 if (e >= __ldg(ec + b)) { I.s0 = I.s1 = I.s2 = I.s3 = I.s4 = b * E; }
                 else {
                     const int4 g4 = __ldg(reinterpret_cast<const int4*>(gemm + (size_t)m * 4));
@@ -1679,6 +1685,13 @@ meshconv_bwd_weight_tc_kernel(const float* __restrict__ dout, const float* __res
         };
         auto load_data = [&](int kb, const Idx& I) {
             Data D;
+            if (dbg & 1) {
+#pragma unroll
+                for (int it = 0; it < 4; ++it) D.a[it] = z;
+#pragma unroll
+                for (int it = 0; it < 5; ++it) D.f[it] = z;
+                return D;
+            }
             const int mb = mbeg + (kb << 5);
 #pragma unroll
             for (int it = 0; it < 4; ++it) {                                // A: dout[m][o0 + 4q ..] for 32 edges x 32 chunks
@@ -1703,6 +1716,12 @@ meshconv_bwd_weight_tc_kernel(const float* __restrict__ dout, const float* __res
             const uint32_t a_lo = a_hi + S::A_BYTES;
             const uint32_t b_hi = a_lo + S::A_BYTES;
             const uint32_t b_lo = b_hi + S::B_BYTES;
+            if (dbg & 4) {
+                tc::fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(full_bar + s);
+                return;
+            }
 #pragma unroll
             for (int it = 0; it < 4; ++it) {
                 const int item = pt + it * 256;
@@ -1793,7 +1812,7 @@ meshconv_bwd_weight_tc_kernel(const float* __restrict__ dout, const float* __res
                 const uint32_t b_hi = a_lo + S::A_BYTES;
                 const uint32_t b_lo = b_hi + S::B_BYTES;
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {                 // one 8-edge K group per MMA: +1024 bytes
+                for (int kk = 0; kk < ((dbg & 2) ? 0 : 4); ++kk) {                 // one 8-edge K group per MMA: +1024 bytes
                     const uint64_t dah = tc::make_desc_sw128_mn(a_hi + kk * 1024, S::LBO), dal = tc::make_desc_sw128_mn(a_lo + kk * 1024, S::LBO);
                     const uint64_t dbh = tc::make_desc_sw128_mn(b_hi + kk * 1024, S::LBO), dbl = tc::make_desc_sw128_mn(b_lo + kk * 1024, S::LBO);
                     tc::mma_tf32(tmem_base, dah, dbh, idesc, (kb | kk) != 0);
