@@ -507,7 +507,14 @@ def main():
         base = name[:-3] if name.endswith('_tc') else name
         nbytes = algorithmic_bytes(base, m)
         avg_ms = tot / cnt
-        common = {'kernel': name, 'shape': m, 'avg_launch_ms': avg_ms, 'algorithmic_bytes': nbytes, 'traffic': None,
+        traffic, traffic_src = None, None                    # DRAM bytes per launch of this kernel from the committed ncu capture
+        tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
+        if os.path.exists(tpath):
+            ent = json.load(open(tpath)).get('%s|%s' % (name, ','.join('%s=%s' % kv for kv in sorted(m.items()))))
+            if ent:
+                traffic, traffic_src = ent['dram_bytes'], 'profiles/r01_v9_ncu_top_kernels.md row %d (ncu --set full, one launch)' % ent['row']
+        common = {'kernel': name, 'shape': m, 'avg_launch_ms': avg_ms, 'algorithmic_bytes': nbytes, 'traffic': traffic,
+                  'traffic_source': traffic_src,
                   'dominant_by_time': dominant,
                   'share_of_step': {k: v / eager_ms for k, v in sorted(by_kernel.items())},
                   'timing': 'CUDA events around each C-ABI call in %d eagerly launched steps (%.3f ms/step) run right after '
