@@ -249,6 +249,9 @@ int mcnn_unpool_bwd(const float* dout, const int32_t* grp_rowptr, const int32_t*
  * s1 / s2: [nblocks][G] scratch.
  * ------------------------------------------------------------------------------------------------------ */
 size_t mcnn_norm_ws(int nblocks, int rows_per_block, int C, int G);
+/* diagnostics only: 0 = always the three-kernel form (statistics, finalize, apply); 1 (default) = per-mesh statistics
+ * (GroupNorm, InstanceNorm2d) use the fused one-launch form when the mesh's slab fits in shared memory */
+int mcnn_debug_set_norm_fused(int on);
 int mcnn_norm_fwd(const float* x, const float* a, const float* r, const float* gamma, const float* beta, float* y,
                   float* mean, float* rstd, float* part, float* running_mean, float* running_var, float momentum,
                   float eps, int nblocks, int rows_per_block, int C, int G, int pre_relu, int post_relu, int stats_given,

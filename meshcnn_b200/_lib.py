@@ -66,6 +66,7 @@ SIGNATURES = {
     'mcnn_segmean_bwd': (_c_int, [_c_vp] * 6 + [_c_int] * 5 + [_c_vp]),
     'mcnn_unpool_fwd': (_c_int, [_c_vp] * 6 + [_c_int] * 6 + [_c_vp]),
     'mcnn_norm_ws': (_c_sz, [_c_int] * 4),
+    'mcnn_debug_set_norm_fused': (_c_int, [_c_int]),
     'mcnn_norm_fwd': (_c_int, [_c_vp] * 11 + [ctypes.c_float, ctypes.c_float] + [_c_int] * 7 + [_c_vp]),
     'mcnn_norm_bwd': (_c_int, [_c_vp] * 14 + [_c_int] * 6 + [_c_vp]),
     'mcnn_adam_flat': (_c_int, [_c_vp] * 4 + [ctypes.c_longlong] + [ctypes.c_float] * 5 + [_c_int, _c_vp]),
@@ -94,6 +95,8 @@ def lib():
             fn.restype = res
             fn.argtypes = args
         l.mcnn_debug_set_tc_pair(TC_PAIR_DEFAULT)
+        if os.environ.get('MESHCNN_B200_NORM_FUSED') == '0':     # A/B switch: statistics / finalize / apply kernels everywhere
+            l.mcnn_debug_set_norm_fused(0)
         _lib = l
     return _lib
 

@@ -306,6 +306,269 @@ __global__ void __launch_bounds__(NT) norm_bwd_apply_kernel(const float* __restr
     }
 }
 
+// ---- fused per-mesh forms (GroupNorm / InstanceNorm2d: statistics never cross a mesh) ------------------------------------
+// One CTA = one block of rows (a mesh) x CW consecutive channels (whole groups).  The pre-activation z = pre(x [+ a]) of the
+// CTA's slab is kept in shared memory, so each activation is read ONCE: partial sums -> block reduction -> group statistics
+// (fp64) -> normalise from shared memory.  One launch instead of three per direction (+ the small dgamma / dbeta reduction
+// in the backward), and no statistics round trip through global memory between dependent launches -- at the sizes of this
+// workload the three-kernel form is bound by exactly those dependent launches, not by HBM.
+struct FusedShape { int nblocks, rows, C, G, CW; };
+
+__device__ __forceinline__ void fused_reduce_columns(float* red, float* tot, const float (&u)[4], const float (&v)[4], int tx, int ty,
+                                                     int rl, int CW) {
+    // red[ty][2][CW] -> tot[2][CW]
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        red[(ty * 2 + 0) * CW + (tx << 2) + j] = u[j];
+        red[(ty * 2 + 1) * CW + (tx << 2) + j] = v[j];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * CW; i += NT) {
+        const int which = i / CW, c = i - which * CW;
+        float acc = 0.f;
+        for (int y = 0; y < rl; ++y) acc += red[(y * 2 + which) * CW + c];
+        tot[i] = acc;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(NT) norm_fused_fwd_kernel(const float* __restrict__ x, const float* __restrict__ a,
+                                                            const float* __restrict__ r, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, float* __restrict__ y,
+                                                            float* __restrict__ mean, float* __restrict__ rstd, float eps,
+                                                            int pre_relu, int post_relu, FusedShape s) {
+    extern __shared__ float sm[];
+    const int CW = s.CW, cq = CW >> 2, rl = NT / cq;
+    float* zs = sm;                                   // [rows][CW]
+    float* red = zs + (size_t)s.rows * CW;            // [rl][2][CW]
+    float* tot = red + rl * 2 * CW;                   // [2][CW]
+    float* stat = tot + 2 * CW;                       // [2][CW / cpg]: mean, rstd of the CTA's groups
+    const int tx = threadIdx.x % cq, ty = threadIdx.x / cq;
+    const int blk = blockIdx.x, c0 = blockIdx.y * CW;
+    const int cpg = s.C / s.G;
+    const size_t base = (size_t)blk * s.rows * s.C + c0 + (tx << 2);
+    float u[4] = {0.f, 0.f, 0.f, 0.f}, v[4] = {0.f, 0.f, 0.f, 0.f};
+    auto take = [&](int row, float4 z, const float4 t) {
+        z.x += t.x; z.y += t.y; z.z += t.z; z.w += t.w;
+        if (pre_relu) { z.x = fmaxf(z.x, 0.f); z.y = fmaxf(z.y, 0.f); z.z = fmaxf(z.z, 0.f); z.w = fmaxf(z.w, 0.f); }
+        *reinterpret_cast<float4*>(zs + (size_t)row * CW + (tx << 2)) = z;
+        u[0] += z.x; u[1] += z.y; u[2] += z.z; u[3] += z.w;
+        v[0] += z.x * z.x; v[1] += z.y * z.y; v[2] += z.z * z.z; v[3] += z.w * z.w;
+    };
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    int row = ty;
+    for (; row + 3 * rl < s.rows; row += 4 * rl) {            // four independent rows in flight
+        float4 z[4], t[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const size_t off = base + (size_t)(row + k * rl) * s.C;
+            z[k] = ld4(x + off);
+            t[k] = a != nullptr ? ld4(a + off) : zero;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) take(row + k * rl, z[k], t[k]);
+    }
+    for (; row < s.rows; row += rl) {
+        const size_t off = base + (size_t)row * s.C;
+        take(row, ld4(x + off), a != nullptr ? ld4(a + off) : zero);
+    }
+    fused_reduce_columns(red, tot, u, v, tx, ty, rl, CW);
+    const int ngrp = CW / cpg;
+    if (threadIdx.x < ngrp) {
+        const int g = threadIdx.x;
+        double su = 0.0, sv = 0.0;
+        for (int j = 0; j < cpg; ++j) { su += (double)tot[g * cpg + j]; sv += (double)tot[CW + g * cpg + j]; }
+        const double n = (double)s.rows * cpg;
+        const double m = su / n;
+        double var = sv / n - m * m;
+        if (var < 0.0) var = 0.0;
+        const float mf = (float)m, rf = (float)(1.0 / sqrt(var + (double)eps));
+        stat[g] = mf; stat[ngrp + g] = rf;
+        mean[blk * s.G + c0 / cpg + g] = mf;
+        rstd[blk * s.G + c0 / cpg + g] = rf;
+    }
+    __syncthreads();
+    float sc[4], sh[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int cl = (tx << 2) + j, g = cl / cpg;
+        const float m = stat[g], rs = stat[ngrp + g];
+        const float gm = gamma != nullptr ? __ldg(gamma + c0 + cl) : 1.f;
+        const float bt = gamma != nullptr ? __ldg(beta + c0 + cl) : 0.f;
+        sc[j] = rs * gm;
+        sh[j] = bt - m * rs * gm;
+    }
+    auto put = [&](int row_, const float4 r4) {
+        const float4 z = *reinterpret_cast<const float4*>(zs + (size_t)row_ * CW + (tx << 2));
+        float o[4] = {fmaf(z.x, sc[0], sh[0]) + r4.x, fmaf(z.y, sc[1], sh[1]) + r4.y, fmaf(z.z, sc[2], sh[2]) + r4.z, fmaf(z.w, sc[3], sh[3]) + r4.w};
+        if (post_relu) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[j] = fmaxf(o[j], 0.f);
+        }
+        *reinterpret_cast<float4*>(y + base + (size_t)row_ * s.C) = make_float4(o[0], o[1], o[2], o[3]);
+    };
+    row = ty;
+    if (r != nullptr) {
+        for (; row + 3 * rl < s.rows; row += 4 * rl) {
+            float4 rv[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) rv[k] = ld4(r + base + (size_t)(row + k * rl) * s.C);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) put(row + k * rl, rv[k]);
+        }
+        for (; row < s.rows; row += rl) put(row, ld4(r + base + (size_t)row * s.C));
+    } else {
+        for (; row < s.rows; row += rl) put(row, zero);
+    }
+}
+
+// backward: pass 1 keeps the raw z = x [+ a] of the slab in shared memory and accumulates A_c = sum dyh, B_c = sum dyh * xhat;
+// the per-mesh column sums go to part[blk][2][C] (dgamma / dbeta are reduced over the meshes by norm_bwd_finalize_kernel);
+// pass 2 re-reads dy (and y) from L2 and writes dx (and dr).
+__global__ void __launch_bounds__(NT) norm_fused_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y,
+                                                            const float* __restrict__ x, const float* __restrict__ a,
+                                                            const float* __restrict__ gamma, const float* __restrict__ mean,
+                                                            const float* __restrict__ rstd, float* __restrict__ dx,
+                                                            float* __restrict__ dr, float* __restrict__ part, int pre_relu,
+                                                            int post_relu, FusedShape s) {
+    extern __shared__ float sm[];
+    const int CW = s.CW, cq = CW >> 2, rl = NT / cq;
+    float* zs = sm;
+    float* red = zs + (size_t)s.rows * CW;
+    float* tot = red + rl * 2 * CW;
+    float* stat = tot + 2 * CW;                       // [2][ngrp]: s1, s2
+    const int tx = threadIdx.x % cq, ty = threadIdx.x / cq;
+    const int blk = blockIdx.x, c0 = blockIdx.y * CW;
+    const int cpg = s.C / s.G;
+    const int ngrp = CW / cpg;
+    const size_t base = (size_t)blk * s.rows * s.C + c0 + (tx << 2);
+    float rs[4], mrs[4], gm[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int cl = (tx << 2) + j, g = (c0 + cl) / cpg;
+        rs[j] = __ldg(rstd + blk * s.G + g);
+        mrs[j] = __ldg(mean + blk * s.G + g) * rs[j];
+        gm[j] = gamma != nullptr ? __ldg(gamma + c0 + cl) : 1.f;
+    }
+    float u[4] = {0.f, 0.f, 0.f, 0.f}, v[4] = {0.f, 0.f, 0.f, 0.f};
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto take = [&](int row_, const float4 d4, const float4 y4, float4 z, const float4 t) {
+        z.x += t.x; z.y += t.y; z.z += t.z; z.w += t.w;
+        *reinterpret_cast<float4*>(zs + (size_t)row_ * CW + (tx << 2)) = z;          // raw: pass 2 needs the sign for pre_relu
+        float d[4] = {d4.x, d4.y, d4.z, d4.w};
+        const float yv[4] = {y4.x, y4.y, y4.z, y4.w};
+        const float zr[4] = {z.x, z.y, z.z, z.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (post_relu) d[j] = yv[j] > 0.f ? d[j] : 0.f;
+            const float zc = pre_relu ? fmaxf(zr[j], 0.f) : zr[j];
+            const float xh = zc * rs[j] - mrs[j];
+            u[j] += d[j];
+            v[j] += d[j] * xh;
+        }
+    };
+    int row = ty;
+    for (; row + rl < s.rows; row += 2 * rl) {
+        float4 d[2], yy[2], z[2], t[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const size_t off = base + (size_t)(row + k * rl) * s.C;
+            d[k] = ld4(dy + off);
+            yy[k] = post_relu ? ld4(y + off) : zero;
+            z[k] = ld4(x + off);
+            t[k] = a != nullptr ? ld4(a + off) : zero;
+        }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) take(row + k * rl, d[k], yy[k], z[k], t[k]);
+    }
+    for (; row < s.rows; row += rl) {
+        const size_t off = base + (size_t)row * s.C;
+        take(row, ld4(dy + off), post_relu ? ld4(y + off) : zero, ld4(x + off), a != nullptr ? ld4(a + off) : zero);
+    }
+    fused_reduce_columns(red, tot, u, v, tx, ty, rl, CW);
+    for (int i = threadIdx.x; i < 2 * CW; i += NT) {           // per-mesh column sums for dbeta (A) / dgamma (B)
+        const int which = i / CW, c = i - which * CW;
+        part[((size_t)blk * 2 + which) * s.C + c0 + c] = tot[i];
+    }
+    if (threadIdx.x < ngrp) {
+        const int g = threadIdx.x;
+        double a1 = 0.0, a2 = 0.0;
+        for (int j = 0; j < cpg; ++j) {
+            const double gmj = gamma != nullptr ? (double)__ldg(gamma + c0 + g * cpg + j) : 1.0;
+            a1 += gmj * (double)tot[g * cpg + j];
+            a2 += gmj * (double)tot[CW + g * cpg + j];
+        }
+        const double n = (double)s.rows * cpg;
+        stat[g] = (float)(a1 / n);
+        stat[ngrp + g] = (float)(a2 / n);
+    }
+    __syncthreads();
+    float k1[4], k2[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int g = ((tx << 2) + j) / cpg;
+        k1[j] = stat[g];
+        k2[j] = stat[ngrp + g];
+    }
+    auto put = [&](int row_, const float4 d4, const float4 y4) {
+        const size_t off = base + (size_t)row_ * s.C;
+        const float4 z4 = *reinterpret_cast<const float4*>(zs + (size_t)row_ * CW + (tx << 2));
+        float d[4] = {d4.x, d4.y, d4.z, d4.w};
+        const float yv[4] = {y4.x, y4.y, y4.z, y4.w};
+        const float zr[4] = {z4.x, z4.y, z4.z, z4.w};
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (post_relu) d[j] = yv[j] > 0.f ? d[j] : 0.f;
+            const float z = pre_relu ? fmaxf(zr[j], 0.f) : zr[j];
+            const float xh = z * rs[j] - mrs[j];
+            float dz = rs[j] * (gm[j] * d[j] - k1[j] - xh * k2[j]);
+            if (pre_relu && !(zr[j] > 0.f)) dz = 0.f;
+            o[j] = dz;
+        }
+        if (dr != nullptr) *reinterpret_cast<float4*>(dr + off) = make_float4(d[0], d[1], d[2], d[3]);
+        *reinterpret_cast<float4*>(dx + off) = make_float4(o[0], o[1], o[2], o[3]);
+    };
+    row = ty;
+    for (; row + 3 * rl < s.rows; row += 4 * rl) {
+        float4 d[4], yy[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const size_t off = base + (size_t)(row + k * rl) * s.C;
+            d[k] = ld4(dy + off);
+            yy[k] = post_relu ? ld4(y + off) : zero;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) put(row + k * rl, d[k], yy[k]);
+    }
+    for (; row < s.rows; row += rl) {
+        const size_t off = base + (size_t)row * s.C;
+        put(row, ld4(dy + off), post_relu ? ld4(y + off) : zero);
+    }
+}
+
+static int g_norm_fused = 1;                 // debug: 0 = always the three-kernel form
+
+// channel width of the fused form for a shape, 0 if it does not apply (statistics crossing meshes, odd group sizes, or a
+// slab that does not fit in shared memory)
+static int fused_cw(int nblocks, int rows, int C, int G, size_t* smem_bytes) {
+    if (!g_norm_fused || nblocks < 8) return 0;
+    const int cpg = C / G;
+    if (cpg & (cpg - 1)) return 0;
+    int cw = 32;
+    if (cw < cpg) cw = cpg;
+    if (cw > C) cw = C;
+    if ((cw & (cw - 1)) || C % cw || cw < 4 || cw > 256) return 0;
+    // measured: worth it only while two CTAs fit on an SM and a row segment is at least 64 bytes (humanseg's 2280-row slabs
+    // were 4 % slower per step in the one-launch form: one 256-thread CTA per SM cannot keep enough loads in flight)
+    for (; cw >= 16 && cw >= cpg; cw >>= 1) {
+        const int rl = NT / (cw >> 2);
+        const size_t b = ((size_t)rows * cw + (size_t)rl * 2 * cw + 2 * cw + 2 * (cw / cpg)) * sizeof(float);
+        if (b <= 100 * 1024) { *smem_bytes = b; return cw; }
+    }
+    return 0;
+}
+
 // ---- flat Adam over contiguous parameter / gradient / moment buffers (torch.optim.Adam semantics, no amsgrad) ----------
 __global__ void adam_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                                  long long n, float lr, float beta1, float beta2, float eps, float weight_decay, float bc1, float bc2_sqrt) {
@@ -384,6 +647,19 @@ extern "C" int mcnn_norm_fwd(const float* x, const float* a, const float* r, con
     const NormShape s = make_shape(nblocks, rows_per_block, C, G);
     const size_t smem = (size_t)(NT / (C / 4)) * 2 * C * sizeof(float);
     int rc;
+    size_t fsm = 0;
+    const int cw = (!stats_given && running_mean == nullptr) ? fused_cw(nblocks, rows_per_block, C, G, &fsm) : 0;
+    if (cw) {
+        static size_t configured = 0;
+        if (fsm > configured) {
+            cudaError_t e = cudaFuncSetAttribute(norm_fused_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            if (e != cudaSuccess) { g_last_error = e; return MCNN_E_CUDA; }
+            configured = 200 * 1024;
+        }
+        FusedShape f; f.nblocks = nblocks; f.rows = rows_per_block; f.C = C; f.G = G; f.CW = cw;
+        norm_fused_fwd_kernel<<<dim3(nblocks, C / cw), NT, fsm, st>>>(x, a, r, gamma, beta, y, mean, rstd, eps, pre_relu, post_relu, f);
+        return after_launch();
+    }
     if (!stats_given) {
         norm_stats_kernel<<<dim3(nblocks, s.slabs), NT, smem, st>>>(x, a, pre_relu, part, s);
         if ((rc = after_launch())) return rc;
@@ -404,6 +680,26 @@ extern "C" int mcnn_norm_bwd(const float* dy, const float* y, const float* x, co
     const NormShape s = make_shape(nblocks, rows_per_block, C, G);
     const size_t smem = (size_t)(NT / (C / 4)) * 2 * C * sizeof(float);
     int rc;
+    size_t fsm = 0;
+    const int cw = fused_cw(nblocks, rows_per_block, C, G, &fsm);
+    if (cw) {
+        static size_t configured = 0;
+        if (fsm > configured) {
+            cudaError_t e = cudaFuncSetAttribute(norm_fused_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            if (e != cudaSuccess) { g_last_error = e; return MCNN_E_CUDA; }
+            configured = 200 * 1024;
+        }
+        FusedShape f; f.nblocks = nblocks; f.rows = rows_per_block; f.C = C; f.G = G; f.CW = cw;
+        norm_fused_bwd_kernel<<<dim3(nblocks, C / cw), NT, fsm, st>>>(dy, y, x, a, gamma, mean, rstd, dx, dr, part, pre_relu, post_relu, f);
+        if ((rc = after_launch())) return rc;
+        if (dgamma != nullptr) {                               // dgamma / dbeta: the per-mesh column sums reduced over the meshes
+            NormShape s1s = s; s1s.slabs = 1; s1s.rows_per_slab = rows_per_block;
+            const int nfin1 = nblocks * G + C;
+            norm_bwd_finalize_kernel<<<ceil_div(nfin1 * 32, 256), 256, 0, st>>>(part, gamma, s1, s2, dgamma, dbeta, s1s);
+            rc = after_launch();
+        }
+        return rc;
+    }
     norm_bwd_stats_kernel<<<dim3(nblocks, s.slabs), NT, smem, st>>>(dy, y, x, a, mean, rstd, pre_relu, post_relu, part, s);
     if ((rc = after_launch())) return rc;
     const int nfin = nblocks * G + C;
@@ -412,6 +708,8 @@ extern "C" int mcnn_norm_bwd(const float* dy, const float* y, const float* x, co
     norm_bwd_apply_kernel<<<dim3(nblocks, s.slabs), NT, 0, st>>>(dy, y, x, a, gamma, mean, rstd, s1, s2, dx, dr, pre_relu, post_relu, s);
     return after_launch();
 }
+
+extern "C" int mcnn_debug_set_norm_fused(int on) { g_norm_fused = on ? 1 : 0; return MCNN_OK; }
 
 extern "C" int mcnn_adam_flat_state(float* p, const float* g, float* m, float* v, long long n, float* state, void* stream) {
     if (!p || !g || !m || !v || !state || n <= 0) return MCNN_E_BADARG;

@@ -28,10 +28,12 @@ def _ref(norm, x, a, r, pre_relu, post_relu):
 
 @pytest.mark.parametrize('kind,C', [('batch', 64), ('group', 128), ('instance', 32), ('group', 256), ('instance', 8), ('batch', 256)])
 @pytest.mark.parametrize('variant', ['plain', 'pre', 'post'])
-def test_fused_norm_matches_torch(kind, C, variant):
+@pytest.mark.parametrize('B,E', [(6, 750), (16, 300), (9, 1400)], ids=['three_kernels', 'one_launch', 'one_launch_narrow'])
+def test_fused_norm_matches_torch(kind, C, variant, B, E):
+    """B = 6: statistics / finalize / apply kernels; B >= 8 with per-mesh statistics (group, instance): the one-launch form
+    that keeps the mesh's slab in shared memory (1400 rows: 16-channel chunks)."""
     from meshcnn_b200.functional import fused_norm
     torch.manual_seed(C + len(variant))
-    B, E = 6, 750
     mk = {'batch': lambda: nn.BatchNorm2d(C), 'group': lambda: nn.GroupNorm(16 if C >= 16 else 4, C),
           'instance': lambda: nn.InstanceNorm2d(C)}[kind]
     n1, n2 = mk().to(DEV).train(), mk().to(DEV).train()
@@ -95,3 +97,34 @@ def test_flat_adam_matches_torch_adam():
         opt2.step()
     for p1, p2 in zip(net1.parameters(), net2.parameters()):
         assert close(p1.detach().cpu().numpy(), p2.detach().cpu().numpy(), 1e-5, 1e-7)
+
+
+@pytest.mark.parametrize('kind,C,E', [('group', 64, 750), ('group', 256, 300), ('instance', 128, 600), ('group', 32, 1400)])
+def test_one_launch_norm_matches_three_kernel_form(kind, C, E):
+    """Same statistics, same formulas: the two forms must agree to fp32 rounding of the partial sums."""
+    from meshcnn_b200 import _lib
+    from meshcnn_b200.functional import fused_norm
+    torch.manual_seed(C + E)
+    B = 12
+    norm = (nn.GroupNorm(16, C) if kind == 'group' else nn.InstanceNorm2d(C)).to(DEV).train()
+    if kind == 'group':
+        with torch.no_grad():
+            norm.weight.uniform_(0.5, 1.5); norm.bias.uniform_(-0.3, 0.3)
+    x = torch.randn(B, E, C, device=DEV) * 1.3 - 0.2
+    aux = torch.randn(B, E, C, device=DEV)
+    dy = torch.randn(B, E, C, device=DEV)
+    L = _lib.lib()
+    res = []
+    try:
+        for on in (0, 1):
+            L.mcnn_debug_set_norm_fused(on)
+            xs, ax = x.clone().requires_grad_(True), aux.clone().requires_grad_(True)
+            norm.zero_grad()
+            y = fused_norm(xs, norm, pre_add=ax, pre_relu=True, post_relu=True)
+            y.backward(dy)
+            torch.cuda.synchronize()
+            res.append([y.detach().clone(), xs.grad.clone(), ax.grad.clone()] + ([norm.weight.grad.clone(), norm.bias.grad.clone()] if kind == 'group' else []))
+    finally:
+        L.mcnn_debug_set_norm_fused(1)
+    for p3, p1 in zip(*res):
+        assert close(p1.cpu().numpy(), p3.cpu().numpy(), 2e-6, 1e-7)
