@@ -280,12 +280,12 @@ meshconv_bwd_data_kernel(const float* __restrict__ dout, const float* __restrict
 // ---------------------------------------------------------------------------------------------------------
 // backward, weight:  dW[o][c][k] = sum_m dout[m][o] * G_k[m][c]   (all E slots, padded ones included)
 // ---------------------------------------------------------------------------------------------------------
-constexpr int MSPLIT = 1024;    // rows reduced by one CTA before the atomic flush
+constexpr int MSPLIT_MAX = 1024;    // most rows reduced by one CTA before the atomic flush
 
 __global__ void __launch_bounds__(NTHREADS)
 meshconv_bwd_weight_kernel(const float* __restrict__ dout, const float* __restrict__ x, const int32_t* __restrict__ gemm,
                            const int32_t* __restrict__ ec, float* __restrict__ dw, float* __restrict__ dbias,
-                           int B, int E, int Cin, int Cout) {
+                           int B, int E, int Cin, int Cout, int msplit) {
     __shared__ int nb[TM][5];
     __shared__ __align__(16) float As[TM * (TN + 4)];     // dout tile [mm][oo]
     __shared__ float Gs[TM * (KK + 1)];                   // G tile    [mm][cl*5+k]
@@ -299,7 +299,7 @@ meshconv_bwd_weight_kernel(const float* __restrict__ dout, const float* __restri
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int k = 0; k < 5; ++k) acc[i][k] = 0.f;
-    const int mbeg = blockIdx.x * MSPLIT, mend = min(M, mbeg + MSPLIT);
+    const int mbeg = blockIdx.x * msplit, mend = min(M, mbeg + msplit);
     for (int m0 = mbeg; m0 < mend; m0 += TM) {
         resolve_rows(nb, m0, mend, E, gemm, ec);           // rows >= mend resolve to -1 -> zero G
         for (int i = threadIdx.x; i < TM * (TN / 4); i += NTHREADS) {
@@ -381,7 +381,12 @@ extern "C" int mcnn_meshconv_bwd_data(const float* dout, const float* x, const i
 extern "C" int mcnn_meshconv_bwd_weight(const float* dout, const float* x, const int32_t* gemm, const int32_t* ec,
                                         float* dweight, float* dbias, int B, int E, int Cin, int Cout, void* stream) {
     if (!dout || !x || !gemm || !ec || !dweight || B <= 0 || E <= 0 || Cin <= 0 || Cout <= 0) return MCNN_E_BADARG;
-    dim3 grid(ceil_div(B * E, MSPLIT), ceil_div(Cout, TN), ceil_div(Cin, CK));
-    meshconv_bwd_weight_kernel<<<grid, NTHREADS, 0, (cudaStream_t)stream>>>(dout, x, gemm, ec, dweight, dbias, B, E, Cin, Cout);
+    // rows per CTA: about two CTAs per SM in total (a narrow layer has a single (Cout, Cin) tile: 1024-row slabs left
+    // two thirds of the SMs idle), at least one 64-row tile, at most 1024 rows
+    const int tiles = ceil_div(Cout, TN) * ceil_div(Cin, CK);
+    int msplit = ceil_div(ceil_div(B * E, max(1, 296 / tiles)), TM) * TM;
+    msplit = min(MSPLIT_MAX, max(TM, msplit));
+    dim3 grid(ceil_div(B * E, msplit), ceil_div(Cout, TN), ceil_div(Cin, CK));
+    meshconv_bwd_weight_kernel<<<grid, NTHREADS, 0, (cudaStream_t)stream>>>(dout, x, gemm, ec, dweight, dbias, B, E, Cin, Cout, msplit);
     return after_launch();
 }

@@ -1052,26 +1052,33 @@ __global__ void __launch_bounds__(P::THREADS, 1) pool_collapse_kernel(const mcnn
 // ---------------------------------------------------------------------------------------------------------
 // feature kernels
 // ---------------------------------------------------------------------------------------------------------
+// squared feature norm of every edge row (the collapse priority, mesh_pool.py:197).  Eight lanes per row: a row is read as
+// contiguous 128-byte pieces; the eight partial sums are combined in a fixed butterfly order (deterministic).
 __global__ void pool_norms_kernel(const float* __restrict__ x, float* __restrict__ norms, int M, int C) {
-    const int m = blockIdx.x * blockDim.x + threadIdx.x;
-    if (m >= M) return;
-    const float* p = x + (size_t)m * C;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int m = (int)(t >> 3), l = (int)(t & 7);
     float s = 0.f;
-    if ((C & 3) == 0) {
-        for (int c = 0; c < C; c += 4) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(p + c));
-            s = __fadd_rn(s, __fmul_rn(v.x, v.x));
-            s = __fadd_rn(s, __fmul_rn(v.y, v.y));
-            s = __fadd_rn(s, __fmul_rn(v.z, v.z));
-            s = __fadd_rn(s, __fmul_rn(v.w, v.w));
-        }
-    } else {
-        for (int c = 0; c < C; ++c) {
-            const float v = __ldg(p + c);
-            s = __fadd_rn(s, __fmul_rn(v, v));
+    if (m < M) {
+        const float* p = x + (size_t)m * C;
+        if ((C & 3) == 0) {
+            for (int c = l << 2; c < C; c += 32) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(p + c));
+                s = __fadd_rn(s, __fmul_rn(v.x, v.x));
+                s = __fadd_rn(s, __fmul_rn(v.y, v.y));
+                s = __fadd_rn(s, __fmul_rn(v.z, v.z));
+                s = __fadd_rn(s, __fmul_rn(v.w, v.w));
+            }
+        } else {
+            for (int c = l; c < C; c += 8) {
+                const float v = __ldg(p + c);
+                s = __fadd_rn(s, __fmul_rn(v, v));
+            }
         }
     }
-    norms[m] = s;
+    s = __fadd_rn(s, __shfl_xor_sync(0xffffffffu, s, 4));
+    s = __fadd_rn(s, __shfl_xor_sync(0xffffffffu, s, 2));
+    s = __fadd_rn(s, __shfl_xor_sync(0xffffffffu, s, 1));
+    if (m < M && l == 0) norms[m] = s;
 }
 
 // one thread per (row, channel quad); used for the four segment kernels below
@@ -1110,12 +1117,13 @@ __global__ void segment_kernel(const float* __restrict__ in, float* __restrict__
                                const int32_t* __restrict__ idx, const int32_t* __restrict__ aux_ptr,
                                const float* __restrict__ occ, const int32_t* __restrict__ valid, int B, int R_out,
                                int R_in, int ptr_stride, int aux_stride, int occ_stride, int C, int nnz_cap) {
+    // grid (row blocks, meshes); a CTA covers 256 / cq rows, one thread per (row, channel quad).  32-bit index arithmetic
+    // only (the flat 64-bit thread id of the first version cost three 64-bit divisions per thread).
     const int cq = (C + 3) >> 2;
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (long long)B * R_out * cq) return;
-    const int q = (int)(t % cq);
-    const long long br = t / cq;
-    const int r = (int)(br % R_out), b = (int)(br / R_out);
+    const int rpc = blockDim.x / cq;                             // rows per CTA
+    const int lr = threadIdx.x / cq, q = threadIdx.x - lr * cq;
+    const int b = blockIdx.y, r = blockIdx.x * rpc + lr;
+    if (lr >= rpc || r >= R_out) return;
     const int c = q * 4;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (r < __ldg(valid + b) && r < ptr_stride - 1) {
@@ -1123,16 +1131,27 @@ __global__ void segment_kernel(const float* __restrict__ in, float* __restrict__
         const int beg = __ldg(pp + r), end = __ldg(pp + r + 1);
         const int32_t* ii = idx + (size_t)b * nnz_cap;
         const float* src = in + (size_t)b * R_in * C;
-        for (int p = beg; p < end; ++p) {
-            const int j = __ldg(ii + p);
-            float w = 1.f;
+        auto weight_of = [&](int j) -> float {
             if (MODE == 1) {
                 const int32_t* ap = aux_ptr + (size_t)b * aux_stride;
-                w = 1.f / (float)(__ldg(ap + j + 1) - __ldg(ap + j));
-            } else if (MODE == 3) {
-                w = 1.f / __ldg(occ + (size_t)b * occ_stride + j);
+                return 1.f / (float)(__ldg(ap + j + 1) - __ldg(ap + j));
             }
-            acc_row<VEC>(acc, src + (size_t)j * C, C, c, w);
+            if (MODE == 3) return 1.f / __ldg(occ + (size_t)b * occ_stride + j);
+            return 1.f;
+        };
+        int p = beg;
+        for (; p + 1 < end; p += 2) {                           // two independent rows in flight (segments are short: 1-3 entries)
+            const int j0 = __ldg(ii + p), j1 = __ldg(ii + p + 1);
+            const float w0 = weight_of(j0), w1 = weight_of(j1);
+            float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+            acc_row<VEC>(a0, src + (size_t)j0 * C, C, c, w0);
+            acc_row<VEC>(a1, src + (size_t)j1 * C, C, c, w1);
+            acc.x += a0.x; acc.y += a0.y; acc.z += a0.z; acc.w += a0.w;      // same order as the one-at-a-time loop
+            acc.x += a1.x; acc.y += a1.y; acc.z += a1.z; acc.w += a1.w;
+        }
+        if (p < end) {
+            const int j = __ldg(ii + p);
+            acc_row<VEC>(acc, src + (size_t)j * C, C, c, weight_of(j));
         }
         float s = 1.f;
         if (MODE == 0) s = 1.f / (float)(end - beg);
@@ -1146,15 +1165,17 @@ template <int MODE>
 static int launch_segment(const float* in, float* out, const int32_t* ptr, const int32_t* idx, const int32_t* aux_ptr,
                           const float* occ, const int32_t* valid, int B, int R_out, int R_in, int ptr_stride,
                           int aux_stride, int occ_stride, int C, int nnz_cap, cudaStream_t st) {
-    const long long total = (long long)B * R_out * ((C + 3) / 4);
-    const int threads = 256;
-    const unsigned blocks = (unsigned)((total + threads - 1) / threads);
+    const int cq = (C + 3) / 4;
+    const int threads = cq <= 256 ? 256 : ((cq + 31) / 32) * 32;
+    if (threads > 1024) return MCNN_E_BADARG;
+    const int rpc = threads / cq;
+    dim3 grid((unsigned)ceil_div(R_out, rpc), (unsigned)B);
     if ((C & 3) == 0)
-        segment_kernel<MODE, true><<<blocks, threads, 0, st>>>(in, out, ptr, idx, aux_ptr, occ, valid, B, R_out, R_in,
-                                                                ptr_stride, aux_stride, occ_stride, C, nnz_cap);
+        segment_kernel<MODE, true><<<grid, threads, 0, st>>>(in, out, ptr, idx, aux_ptr, occ, valid, B, R_out, R_in,
+                                                             ptr_stride, aux_stride, occ_stride, C, nnz_cap);
     else
-        segment_kernel<MODE, false><<<blocks, threads, 0, st>>>(in, out, ptr, idx, aux_ptr, occ, valid, B, R_out, R_in,
-                                                                 ptr_stride, aux_stride, occ_stride, C, nnz_cap);
+        segment_kernel<MODE, false><<<grid, threads, 0, st>>>(in, out, ptr, idx, aux_ptr, occ, valid, B, R_out, R_in,
+                                                              ptr_stride, aux_stride, occ_stride, C, nnz_cap);
     return after_launch();
 }
 
@@ -1175,7 +1196,7 @@ extern "C" size_t mcnn_pool_smem_limit(void) { return 227 * 1024 - 9 * 1024; }  
 extern "C" int mcnn_pool_norms(const float* x, float* norms, int B, int E, int C, void* stream) {
     if (!x || !norms || B <= 0 || E <= 0 || C <= 0) return MCNN_E_BADARG;
     const int M = B * E;
-    pool_norms_kernel<<<ceil_div(M, 128), 128, 0, (cudaStream_t)stream>>>(x, norms, M, C);
+    pool_norms_kernel<<<ceil_div(M, 32), 256, 0, (cudaStream_t)stream>>>(x, norms, M, C);
     return after_launch();
 }
 
