@@ -15,6 +15,10 @@ BWD_OVERLAP = os.environ.get('MESHCNN_B200_BWD_OVERLAP', '1') != '0'
 # persistent ("stream-K") forward kernel: (tile, K block) units spread evenly over the SMs; MESHCNN_B200_TC_SK=0 launches
 # one CTA per tile instead
 USE_SK = os.environ.get('MESHCNN_B200_TC_SK', '1') != '0'
+# inside a step opened with begin_step() (gradients zeroed by the caller, every parameter used once per step) the weight /
+# bias / gamma / beta gradient kernels write straight into p.grad (the flat gradient bucket) and autograd gets None for them:
+# no AccumulateGrad add kernel per parameter (32 tiny launches per step of the cubes net).  MESHCNN_B200_DIRECT_GRADS=0 disables.
+DIRECT_GRADS = os.environ.get('MESHCNN_B200_DIRECT_GRADS', '1') != '0'
 _SIDE = {}
 _SK_WS = {}
 STEP_TOKEN = -1          # >= 0 while a step prepared with begin_step() is being enqueued
@@ -62,6 +66,22 @@ def _sk_workspace(device):
     return ws
 
 
+def _direct_grad(*params):
+    """The .grad buffers of `params` if the kernels may write into them directly (see DIRECT_GRADS), else None."""
+    if not (DIRECT_GRADS and STEP_TOKEN >= 0):
+        return None
+    out = []
+    for p in params:
+        if p is None:
+            out.append(None)
+            continue
+        g = getattr(p, 'grad', None)
+        if not isinstance(p, torch.nn.Parameter) or g is None or not g.is_contiguous() or g.dtype != torch.float32 or g.shape != p.shape:
+            return None
+        out.append(g)
+    return out
+
+
 def _chk_cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:
@@ -106,6 +126,7 @@ class MeshConvFn(torch.autograd.Function):
                                                _lib.ptr(bias), out.data_ptr(), wt_ws.data_ptr(), B, E, Cin, Cout,
                                                _lib.current_stream()), 'mcnn_meshconv_fwd')
         ctx.save_for_backward(x, w)
+        ctx.params = (weight, bias)
         ctx.signs = signs
         ctx.img = img if use_tc else None
         ctx.level = level
@@ -125,13 +146,17 @@ class MeshConvFn(torch.autograd.Function):
         tc_ok = USE_TC and Cin % 32 == 0
         want_w = ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2])
         fork = BWD_OVERLAP and not profiler.enabled and ctx.needs_input_grad[0] and want_w
+        direct = _direct_grad(*ctx.params) if (want_w and ctx.needs_input_grad[1] and (not ctx.has_bias or ctx.needs_input_grad[2])) else None
         if fork:
             # every buffer is allocated on the main stream; the side stream only runs the dW kernels between two events
             use_tc_w = tc_ok and Cout % 4 == 0
-            dw = torch.empty_like(w) if use_tc_w else torch.zeros_like(w)
-            db = None
-            if ctx.has_bias:
-                db = torch.empty(Cout, dtype=torch.float32, device=x.device) if use_tc_w else torch.zeros(Cout, dtype=torch.float32, device=x.device)
+            if direct is not None:                           # zeroed by the step; the kernels overwrite (tc) or add into zero (FFMA)
+                dw, db = direct
+            else:
+                dw = torch.empty_like(w) if use_tc_w else torch.zeros_like(w)
+                db = None
+                if ctx.has_bias:
+                    db = torch.empty(Cout, dtype=torch.float32, device=x.device) if use_tc_w else torch.zeros(Cout, dtype=torch.float32, device=x.device)
             ws = torch.empty(L.mcnn_meshconv_bwd_weight_tc_ws(B, E, Cin, Cout), dtype=torch.float32, device=x.device) if use_tc_w else None
             main, side = torch.cuda.current_stream(), _side_stream(x.device)
             side.wait_stream(main)
@@ -161,19 +186,27 @@ class MeshConvFn(torch.autograd.Function):
             main.wait_stream(side)
         elif want_w:
             if tc_ok and Cout % 4 == 0:
-                dw = torch.empty_like(w)
-                db = torch.empty(Cout, dtype=torch.float32, device=x.device) if ctx.has_bias else None
+                if direct is not None:
+                    dw, db = direct
+                else:
+                    dw = torch.empty_like(w)
+                    db = torch.empty(Cout, dtype=torch.float32, device=x.device) if ctx.has_bias else None
                 ws = torch.empty(L.mcnn_meshconv_bwd_weight_tc_ws(B, E, Cin, Cout), dtype=torch.float32, device=x.device)
                 with profiler.span('meshconv_bwd_weight_tc', B=B, E=E, Cin=Cin, Cout=Cout):
                     _lib.check(L.mcnn_meshconv_bwd_weight_tc(dout.data_ptr(), x.data_ptr(), level.gemm.data_ptr(), level.ec.data_ptr(),
                                                              dw.data_ptr(), _lib.ptr(db), ws.data_ptr(), B, E, Cin, Cout, st),
                                'mcnn_meshconv_bwd_weight_tc')
             else:
-                dw = torch.zeros_like(w)
-                db = torch.zeros(Cout, dtype=torch.float32, device=x.device) if ctx.has_bias else None
+                if direct is not None:
+                    dw, db = direct
+                else:
+                    dw = torch.zeros_like(w)
+                    db = torch.zeros(Cout, dtype=torch.float32, device=x.device) if ctx.has_bias else None
                 with profiler.span('meshconv_bwd_weight', B=B, E=E, Cin=Cin, Cout=Cout):
                     _lib.check(L.mcnn_meshconv_bwd_weight(dout.data_ptr(), x.data_ptr(), level.gemm.data_ptr(), level.ec.data_ptr(),
                                                           dw.data_ptr(), _lib.ptr(db), B, E, Cin, Cout, st), 'mcnn_meshconv_bwd_weight')
+        if direct is not None:
+            dw = db = None                                   # already in weight.grad / bias.grad
         return dx, dw, db, None, None, None
 
 
@@ -269,6 +302,7 @@ class FusedNormFn(torch.autograd.Function):
                                        int(cfg['pre_relu']), int(cfg['post_relu']), int(stats_given), _lib.current_stream()),
                        'mcnn_norm_fwd')
         ctx.save_for_backward(x, a, gamma, mean, rstd, y)
+        ctx.params = (gamma, beta)
         ctx.cfg = (nblocks, rows, C, G, int(cfg['pre_relu']), int(cfg['post_relu']), stats_given, r is not None)
         return y
 
@@ -283,8 +317,12 @@ class FusedNormFn(torch.autograd.Function):
         dev = dy.device
         dx = torch.empty_like(x)
         dr = torch.empty_like(x) if has_r else None
-        dgamma = torch.empty_like(gamma) if gamma is not None else None
-        dbeta = torch.empty_like(gamma) if gamma is not None else None
+        direct = _direct_grad(*ctx.params) if (gamma is not None and ctx.needs_input_grad[3] and ctx.needs_input_grad[4]) else None
+        if direct is not None:
+            dgamma, dbeta = direct
+        else:
+            dgamma = torch.empty_like(gamma) if gamma is not None else None
+            dbeta = torch.empty_like(gamma) if gamma is not None else None
         part = torch.empty(max(1, L.mcnn_norm_ws(nblocks, rows, C, G)), dtype=torch.float32, device=dev)
         s12 = torch.empty(2, nblocks * G, dtype=torch.float32, device=dev)
         with profiler.span('norm_bwd', nblocks=nblocks, rows=rows, C=C, G=G):
@@ -292,6 +330,8 @@ class FusedNormFn(torch.autograd.Function):
                                        rstd.data_ptr(), dx.data_ptr(), _lib.ptr(dr), _lib.ptr(dgamma), _lib.ptr(dbeta),
                                        part.data_ptr(), s12[0].data_ptr(), s12[1].data_ptr(), nblocks, rows, C, G, pre_relu,
                                        post_relu, _lib.current_stream()), 'mcnn_norm_bwd')
+        if direct is not None:
+            dgamma = dbeta = None                            # already in gamma.grad / beta.grad
         return dx, (dx if a is not None else None), dr, dgamma, dbeta, None
 
 
