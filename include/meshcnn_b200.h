@@ -101,6 +101,9 @@ int mcnn_meshconv_fwd_tc_sk(const float* x, const int32_t* gemm, const int32_t* 
 /* diagnostics only: 1 = mcnn_meshconv_bwd_data_tc_signs launches one CTA per (edge tile, channel block) instead of the
  * persistent kernel (same arithmetic; the scatter order differs) */
 int mcnn_debug_set_tc_bd_tile(int on);
+/* diagnostics only: output-channel tiles of 128 per CTA in mcnn_meshconv_bwd_weight_tc (1 or 2; 0 = built-in choice: 2 when
+ * Cout % 256 == 0).  mcnn_meshconv_bwd_weight_tc_ws() follows the setting. */
+int mcnn_debug_set_tc_bw_ot(int ot);
 /* diagnostics only: force the grid size of mcnn_meshconv_fwd_tc_sk (0 = one CTA per SM) */
 int mcnn_debug_set_tc_sk_ctas(int n);
 /* diagnostics only (library built with -DMCNN_TC_PROF): 64 clock64 stamps of one CTA of the last stream-K launch */

@@ -45,6 +45,7 @@ SIGNATURES = {
     'mcnn_meshconv_fwd_tc_sk': (_c_int, [_c_vp] * 9 + [_c_int] * 4 + [_c_vp]),
     'mcnn_debug_set_tc_sk_ctas': (_c_int, [_c_int]),
     'mcnn_debug_set_tc_bd_tile': (_c_int, [_c_int]),
+    'mcnn_debug_set_tc_bw_ot': (_c_int, [_c_int]),
     'mcnn_debug_sk_prof': (_c_int, [_c_vp, _c_int]),
     'mcnn_debug_sk_cta_times': (_c_int, [_c_vp]),
     'mcnn_meshconv_bwd_data_tc_signs': (_c_int, [_c_vp] * 8 + [_c_int] * 4 + [_c_vp]),

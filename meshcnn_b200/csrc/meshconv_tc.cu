@@ -1611,21 +1611,27 @@ meshconv_bwd_data_tc_p_kernel(const float* __restrict__ dout, const int32_t* __r
 // MN-major exactly as they are produced: A[k=edge][o] = dout rows, B[k=edge][(k5, cl)] = G rows.  Slab partials go
 // to a workspace and are reduced by a second kernel (deterministic, no atomics).
 // =============================================================================================================
+// OT = output-channel tiles of 128 per CTA.  With two, the gathered operand (five row loads, symmetric functions, five
+// splits and ten 16-byte stores per thread and K block -- the expensive one: this kernel is bound by operand PRODUCTION)
+// is built once for 256 output channels instead of once per 128.
+template <int OT>
 struct BwSmem {
-    static constexpr int A_BYTES = 32 * 128 * 4;            // 32 edges x 128 o
+    static constexpr int A_BYTES = 32 * 128 * 4;            // 32 edges x 128 o, per output tile
     static constexpr int B_BYTES = 32 * BD_N * 4;            // 32 edges x 160 cols
-    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;     // 73728
-    static constexpr int STAGES = 3;
+    static constexpr int STAGE_BYTES = OT * 2 * A_BYTES + 2 * B_BYTES;     // 73728 / 106496
+    static constexpr int STAGES = OT == 1 ? 3 : 2;
     static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
     static constexpr int TOTAL = BAR_OFF + 16 * 8 + 16 + 1024;
     static constexpr uint32_t LBO = 4096;                    // 4 K-groups of 1024 bytes per M/N atom
+    static constexpr int TMEM_COLS = OT == 1 ? 256 : 512;    // accumulator t at column 256 t
 };
 
+template <int OT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 meshconv_bwd_weight_tc_kernel(const float* __restrict__ dout, const float* __restrict__ x, const int32_t* __restrict__ gemm,
                               const int32_t* __restrict__ ec, float* __restrict__ ws, int B, int E, int Cin, int Cout,
                               int rows_per_split) {
-    using S = BwSmem;
+    using S = BwSmem<OT>;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
@@ -1635,7 +1641,7 @@ meshconv_bwd_weight_tc_kernel(const float* __restrict__ dout, const float* __res
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int M = B * E;
-    const int split = blockIdx.x, o0 = blockIdx.y * 128, cb = blockIdx.z;
+    const int split = blockIdx.x, o0 = blockIdx.y * (128 * OT), cb = blockIdx.z;
     const int mbeg = split * rows_per_split, mend = min(M, mbeg + rows_per_split);
     const int num_kb = (mend > mbeg) ? (mend - mbeg + 31) >> 5 : 0;
     const int dbg = g_tc_debug;            // diagnostics (results wrong): 1 no global loads, 2 no MMA, 4 no st.shared
@@ -1647,7 +1653,7 @@ meshconv_bwd_weight_tc_kernel(const float* __restrict__ dout, const float* __res
             tc::fence_barrier_init();
         }
         __syncwarp();
-        tc::tmem_alloc<256>(tmem_slot);
+        tc::tmem_alloc<S::TMEM_COLS>(tmem_slot);
     }
     tc::tc_fence_before();
     __syncthreads();
@@ -1660,7 +1666,7 @@ meshconv_bwd_weight_tc_kernel(const float* __restrict__ dout, const float* __res
         // blocks ahead and the rows / dout chunks two; every load is issued right after a hand-over (never just before the
         // proxy fence of a store, which would wait for it).
         struct Idx { int s0, s1, s2, s3, s4; };
-        struct Data { float4 a[4]; float4 f[5]; };
+        struct Data { float4 a[4 * OT]; float4 f[5]; };
         const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
         const int bk = pt >> 3, bq = pt & 7;                                // this thread's edge-in-block and channel chunk (B operand)
         // load_idx is called for kb = 0, 1, 2, ... in order: the (mesh, edge) of this thread's row is carried along instead
@@ -1687,16 +1693,16 @@ meshconv_bwd_weight_tc_kernel(const float* __restrict__ dout, const float* __res
             Data D;
             if (dbg & 1) {
 #pragma unroll
-                for (int it = 0; it < 4; ++it) D.a[it] = z;
+                for (int it = 0; it < 4 * OT; ++it) D.a[it] = z;
 #pragma unroll
                 for (int it = 0; it < 5; ++it) D.f[it] = z;
                 return D;
             }
             const int mb = mbeg + (kb << 5);
 #pragma unroll
-            for (int it = 0; it < 4; ++it) {                                // A: dout[m][o0 + 4q ..] for 32 edges x 32 chunks
+            for (int it = 0; it < 4 * OT; ++it) {                           // A: dout[m][o0 + 4q ..] for 32 edges x 32 OT chunks
                 const int item = pt + it * 256;
-                const int m = mb + (item >> 5), o = o0 + ((item & 31) << 2);
+                const int m = mb + item / (32 * OT), o = o0 + ((item % (32 * OT)) << 2);
                 D.a[it] = (m < mend && o < Cout) ? __ldg(reinterpret_cast<const float4*>(dout + (size_t)m * Cout + o)) : z;
             }
             const int c = cb * 32 + (bq << 2);
@@ -1712,9 +1718,8 @@ meshconv_bwd_weight_tc_kernel(const float* __restrict__ dout, const float* __res
             const uint32_t ph = (kb / S::STAGES) & 1;
             if (lane == 0) tc::mbar_wait(empty_bar + s, ph ^ 1);      // one poller per warp
             __syncwarp();
-            const uint32_t a_hi = tc::smem_u32(smem + s * S::STAGE_BYTES);
-            const uint32_t a_lo = a_hi + S::A_BYTES;
-            const uint32_t b_hi = a_lo + S::A_BYTES;
+            const uint32_t a_hi = tc::smem_u32(smem + s * S::STAGE_BYTES);     // per output tile t: hi at + 2 t A_BYTES, lo behind it
+            const uint32_t b_hi = a_hi + OT * 2 * S::A_BYTES;
             const uint32_t b_lo = b_hi + S::B_BYTES;
             if (dbg & 4) {
                 tc::fence_proxy_async_smem();
@@ -1723,13 +1728,14 @@ meshconv_bwd_weight_tc_kernel(const float* __restrict__ dout, const float* __res
                 return;
             }
 #pragma unroll
-            for (int it = 0; it < 4; ++it) {
+            for (int it = 0; it < 4 * OT; ++it) {
                 const int item = pt + it * 256;
                 float4 hi, lo;
                 tc::split4(D.a[it], hi, lo);
-                const uint32_t off = tc::sw128_mn_off(item >> 5, item & 31, S::LBO);
+                const int ch = item % (32 * OT);
+                const uint32_t off = (uint32_t)((ch >> 5) * 2 * S::A_BYTES) + tc::sw128_mn_off(item / (32 * OT), ch & 31, S::LBO);
                 tc::sts128(a_hi + off, hi);
-                tc::sts128(a_lo + off, lo);
+                tc::sts128(a_hi + S::A_BYTES + off, lo);
             }
             const float4 f0 = D.f[0], f1 = D.f[1], f2 = D.f[2], f3 = D.f[3], f4 = D.f[4];
             float4 gk[5];
@@ -1769,33 +1775,38 @@ meshconv_bwd_weight_tc_kernel(const float* __restrict__ dout, const float* __res
         }
         // ---- epilogue: slab partial -> ws[split][o][c][k5] ---------------------------------------------------------
         const int lane_grp = warp & 3;
-        const int o = o0 + lane_grp * 32 + lane;
         const int cl0 = (warp >> 2) * 16;
-        float g[5][16];
         if (num_kb > 0) {
             tc::mbar_wait(accum_bar, 0);
             tc::tc_fence_after();
-#pragma unroll
-            for (int k5 = 0; k5 < 5; ++k5) tc::tmem_ld16(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(k5 * 32 + cl0), g[k5]);
-        } else {
-#pragma unroll
-            for (int k5 = 0; k5 < 5; ++k5)
-#pragma unroll
-                for (int j = 0; j < 16; ++j) g[k5][j] = 0.f;
         }
-        if (o < Cout) {
-            float* dst = ws + (((size_t)split * Cout + o) * Cin + cb * 32 + cl0) * 5;      // 80 contiguous floats
+#pragma unroll 1
+        for (int t = 0; t < OT; ++t) {
+            const int o = o0 + t * 128 + lane_grp * 32 + lane;
+            float g[5][16];
+            if (num_kb > 0) {
 #pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-                // (c, k5) interleave: 4 channels x 5 taps = 20 floats = 5 float4
-                float t[20];
+                for (int k5 = 0; k5 < 5; ++k5) tc::tmem_ld16(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(t * 256 + k5 * 32 + cl0), g[k5]);
+            } else {
 #pragma unroll
-                for (int jj = 0; jj < 4; ++jj)
+                for (int k5 = 0; k5 < 5; ++k5)
 #pragma unroll
-                    for (int k5 = 0; k5 < 5; ++k5) t[jj * 5 + k5] = g[k5][j + jj];
+                    for (int j = 0; j < 16; ++j) g[k5][j] = 0.f;
+            }
+            if (o < Cout) {
+                float* dst = ws + (((size_t)split * Cout + o) * Cin + cb * 32 + cl0) * 5;      // 80 contiguous floats
 #pragma unroll
-                for (int v = 0; v < 5; ++v)
-                    *reinterpret_cast<float4*>(dst + j * 5 + v * 4) = make_float4(t[v * 4], t[v * 4 + 1], t[v * 4 + 2], t[v * 4 + 3]);
+                for (int j = 0; j < 16; j += 4) {
+                    // (c, k5) interleave: 4 channels x 5 taps = 20 floats = 5 float4
+                    float tt[20];
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+                        for (int k5 = 0; k5 < 5; ++k5) tt[jj * 5 + k5] = g[k5][j + jj];
+#pragma unroll
+                    for (int v = 0; v < 5; ++v)
+                        *reinterpret_cast<float4*>(dst + j * 5 + v * 4) = make_float4(tt[v * 4], tt[v * 4 + 1], tt[v * 4 + 2], tt[v * 4 + 3]);
+                }
             }
         }
         tc::tc_fence_before();
@@ -1807,17 +1818,20 @@ meshconv_bwd_weight_tc_kernel(const float* __restrict__ dout, const float* __res
             tc::mbar_wait(full_bar + s, ph);
             tc::tc_fence_after();
             if (tc::elect_one()) {
-                const uint32_t a_hi = tc::smem_u32(smem + s * S::STAGE_BYTES);
-                const uint32_t a_lo = a_hi + S::A_BYTES;
-                const uint32_t b_hi = a_lo + S::A_BYTES;
+                const uint32_t a0 = tc::smem_u32(smem + s * S::STAGE_BYTES);
+                const uint32_t b_hi = a0 + OT * 2 * S::A_BYTES;
                 const uint32_t b_lo = b_hi + S::B_BYTES;
 #pragma unroll
                 for (int kk = 0; kk < ((dbg & 2) ? 0 : 4); ++kk) {                 // one 8-edge K group per MMA: +1024 bytes
-                    const uint64_t dah = tc::make_desc_sw128_mn(a_hi + kk * 1024, S::LBO), dal = tc::make_desc_sw128_mn(a_lo + kk * 1024, S::LBO);
                     const uint64_t dbh = tc::make_desc_sw128_mn(b_hi + kk * 1024, S::LBO), dbl = tc::make_desc_sw128_mn(b_lo + kk * 1024, S::LBO);
-                    tc::mma_tf32(tmem_base, dah, dbh, idesc, (kb | kk) != 0);
-                    tc::mma_tf32(tmem_base, dah, dbl, idesc, 1);
-                    tc::mma_tf32(tmem_base, dal, dbh, idesc, 1);
+#pragma unroll
+                    for (int t = 0; t < OT; ++t) {
+                        const uint32_t a_hi = a0 + t * 2 * S::A_BYTES, a_lo = a_hi + S::A_BYTES;
+                        const uint64_t dah = tc::make_desc_sw128_mn(a_hi + kk * 1024, S::LBO), dal = tc::make_desc_sw128_mn(a_lo + kk * 1024, S::LBO);
+                        tc::mma_tf32(tmem_base + (uint32_t)(t * 256), dah, dbh, idesc, (kb | kk) != 0);
+                        tc::mma_tf32(tmem_base + (uint32_t)(t * 256), dah, dbl, idesc, 1);
+                        tc::mma_tf32(tmem_base + (uint32_t)(t * 256), dal, dbh, idesc, 1);
+                    }
                 }
                 tc::mma_commit(empty_bar + s);
                 if (kb == num_kb - 1) tc::mma_commit(accum_bar);
@@ -1829,7 +1843,7 @@ meshconv_bwd_weight_tc_kernel(const float* __restrict__ dout, const float* __res
     __syncthreads();
     if (warp == TC_PRODUCER_WARPS) {
         tc::tc_fence_after();
-        tc::tmem_dealloc<256>(tmem_base);
+        tc::tmem_dealloc<S::TMEM_COLS>(tmem_base);
     }
 }
 
@@ -1863,8 +1877,14 @@ __global__ void colsum_part_kernel(const float* __restrict__ dout, float* __rest
     }
 }
 
+static int g_tc_bw_ot = 0;                 // debug: force the output tiles per CTA of the weight gradient (0 = heuristic)
+static int bw_ot(int Cout) {
+    if (g_tc_bw_ot == 1 || g_tc_bw_ot == 2) return g_tc_bw_ot;
+    return Cout % 256 == 0 ? 2 : 1;
+}
+
 static int bw_splits(int M, int Cin, int Cout, int* rows_per_split) {
-    const int tiles = ceil_div(Cout, 128) * (Cin / 32);
+    const int tiles = ceil_div(Cout, 128 * bw_ot(Cout)) * (Cin / 32);
     // one CTA per SM (222 KB of shared memory each): fill exactly one wave of the 148 SMs -- a 149th CTA would cost a
     // whole second round
     int S = 148 / tiles;
@@ -1953,6 +1973,8 @@ extern "C" int mcnn_meshconv_fwd_tc_sk(const float* x, const int32_t* gemm, cons
     return launch_fwd_tc_sk<64>(x, gemm, ec, wt_ws, bias, out, signs, sk_ws, B, E, Cin, Cout, st);
 }
 
+extern "C" int mcnn_debug_set_tc_bw_ot(int ot) { g_tc_bw_ot = (ot == 1 || ot == 2) ? ot : 0; return MCNN_OK; }
+
 extern "C" int mcnn_debug_set_tc_bd_tile(int on) { g_tc_bd_tile = on ? 1 : 0; return MCNN_OK; }
 
 extern "C" int mcnn_debug_set_tc_sk_ctas(int n) { g_tc_sk_ctas = n > 0 ? (n > SK_MAX_CTAS ? SK_MAX_CTAS : n) : 0; return MCNN_OK; }
@@ -2012,17 +2034,28 @@ extern "C" int mcnn_meshconv_bwd_weight_tc(const float* dout, const float* x, co
     if (!dout || !x || !gemm || !ec || !dweight || !ws || B <= 0 || E <= 0) return MCNN_E_BADARG;
     if (!(Cin > 0 && Cin % 32 == 0 && Cout > 0 && Cout % 4 == 0)) return MCNN_E_BADARG;
     cudaStream_t st = (cudaStream_t)stream;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(meshconv_bwd_weight_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BwSmem::TOTAL);
-        if (e != cudaSuccess) { g_last_error = e; return MCNN_E_CUDA; }
-        configured = true;
-    }
     const int M = B * E;
     int rows;
     const int S = bw_splits(M, Cin, Cout, &rows);
-    dim3 grid(S, ceil_div(Cout, 128), Cin / 32);
-    meshconv_bwd_weight_tc_kernel<<<grid, TC_THREADS, BwSmem::TOTAL, st>>>(dout, x, gemm, ec, ws, B, E, Cin, Cout, rows);
+    if (bw_ot(Cout) == 2) {
+        static bool configured2 = false;
+        if (!configured2) {
+            cudaError_t e = cudaFuncSetAttribute(meshconv_bwd_weight_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwSmem<2>::TOTAL);
+            if (e != cudaSuccess) { g_last_error = e; return MCNN_E_CUDA; }
+            configured2 = true;
+        }
+        dim3 grid(S, ceil_div(Cout, 256), Cin / 32);
+        meshconv_bwd_weight_tc_kernel<2><<<grid, TC_THREADS, BwSmem<2>::TOTAL, st>>>(dout, x, gemm, ec, ws, B, E, Cin, Cout, rows);
+    } else {
+        static bool configured = false;
+        if (!configured) {
+            cudaError_t e = cudaFuncSetAttribute(meshconv_bwd_weight_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwSmem<1>::TOTAL);
+            if (e != cudaSuccess) { g_last_error = e; return MCNN_E_CUDA; }
+            configured = true;
+        }
+        dim3 grid(S, ceil_div(Cout, 128), Cin / 32);
+        meshconv_bwd_weight_tc_kernel<1><<<grid, TC_THREADS, BwSmem<1>::TOTAL, st>>>(dout, x, gemm, ec, ws, B, E, Cin, Cout, rows);
+    }
     int rc = after_launch();
     if (rc) return rc;
     const int n = Cout * Cin * 5;

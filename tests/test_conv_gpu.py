@@ -231,3 +231,32 @@ def test_conv_persistent_data_gradient_matches_tile_kernel(cin, cout, B):
     finally:
         L.mcnn_debug_set_tc_bd_tile(0)
     assert close(g2.cpu().numpy(), g1.cpu().numpy(), 2e-6)
+
+
+@pytest.mark.parametrize('cin,cout,B', [(128, 256, 9), (256, 256, 23), (64, 512, 5), (32, 256, 1)])
+def test_conv_weight_gradient_two_output_tiles_per_cta(cin, cout, B):
+    """Weight-gradient kernel with two 128-channel output tiles per CTA (gathered operand built once for 256 output
+    channels) against one tile per CTA: same products, the row range is split over a different number of CTAs, so the
+    results agree to fp32 rounding of the split sums."""
+    from meshcnn_b200 import _lib, synth
+    from meshcnn_b200.mesh_conv import MeshConv
+    from tests.gpu_util import DEV, product_mesh
+    meshes = [product_mesh(*synth.make('ico' if s % 3 else 'torus', s, **(dict(nu=5) if s % 3 else dict(m=10, n=25)))) for s in range(B)]
+    torch.manual_seed(cin + cout + B)
+    conv = MeshConv(cin, cout, bias=True).to(DEV)
+    x = torch.randn(B, cin, 750, device=DEV)
+    dy = torch.randn(B, cout, 750, 1, device=DEV)
+    L = _lib.lib()
+    res = []
+    try:
+        for ot in (1, 2):
+            L.mcnn_debug_set_tc_bw_ot(ot)
+            conv.zero_grad()
+            conv(x, meshes).backward(dy)
+            torch.cuda.synchronize()
+            res.append((conv.conv.weight.grad.clone(), conv.conv.bias.grad.clone()))
+    finally:
+        L.mcnn_debug_set_tc_bw_ot(0)
+    for a, b in zip(res[1], res[0]):
+        err = float((a - b).abs().max() / b.abs().max())
+        assert err <= 1e-5, err

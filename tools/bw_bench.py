@@ -37,6 +37,13 @@ for E, cin, cout in [(750, 64, 64), (600, 64, 128), (600, 128, 128), (450, 128, 
     st = torch.cuda.current_stream().cuda_stream
     call = lambda: L.mcnn_meshconv_bwd_weight_tc(dout.data_ptr(), x.data_ptr(), gemm.data_ptr(), ec.data_ptr(), dw.data_ptr(), db.data_ptr(), ws.data_ptr(), B, E, cin, cout, st)
     res = []
+    if cout % 256 == 0:
+        for ot in (1, 2):
+            L.mcnn_debug_set_tc_bw_ot(ot)
+            ws = torch.empty(int(L.mcnn_meshconv_bwd_weight_tc_ws(B, E, cin, cout)), device=dev)
+            res.append('tiles/CTA %d: %.1f' % (ot, timeit(call)))
+        L.mcnn_debug_set_tc_bw_ot(0)
+        ws = torch.empty(int(L.mcnn_meshconv_bwd_weight_tc_ws(B, E, cin, cout)), device=dev)
     for knob in ((0, 1, 4, 5, 2, 7) if len(sys.argv) > 1 else (0,)):
         L.mcnn_debug_set_tc(knob)
         res.append('%d: %.1f' % (knob, timeit(call)))
