@@ -94,6 +94,7 @@ __global__ void norm_finalize_kernel(const float* __restrict__ part, float* __re
     const int cpg = s.C / s.G;
     double su = 0.0, sv = 0.0;
     const int items = s.slabs * cpg;
+#pragma unroll 4
     for (int it = lane; it < items; it += 32) {
         const int sl = it / cpg, c = g * cpg + (it - sl * cpg);
         su += (double)part[(((size_t)blk * s.slabs + sl) * 2 + 0) * s.C + c];
@@ -214,6 +215,7 @@ __global__ void norm_bwd_finalize_kernel(const float* __restrict__ part, const f
         const int blk = w / s.G, g = w - blk * s.G;
         double a1 = 0.0, a2 = 0.0;
         const int items = s.slabs * cpg;
+#pragma unroll 4
         for (int it = lane; it < items; it += 32) {
             const int sl = it / cpg, c = g * cpg + (it - sl * cpg);
             const double gm = gamma != nullptr ? (double)gamma[c] : 1.0;
@@ -231,6 +233,7 @@ __global__ void norm_bwd_finalize_kernel(const float* __restrict__ part, const f
         const int c = w - ngroups;
         double A = 0.0, Bc = 0.0;
         const int items = s.nblocks * s.slabs;
+#pragma unroll 4
         for (int it = lane; it < items; it += 32) {
             A += (double)part[((size_t)it * 2 + 0) * s.C + c];
             Bc += (double)part[((size_t)it * 2 + 1) * s.C + c];
@@ -614,7 +617,8 @@ __global__ void adam_flat_state_kernel(float* __restrict__ p, const float* __res
 static NormShape make_shape(int nblocks, int rows_per_block, int C, int G) {
     NormShape s;
     s.nblocks = nblocks; s.rows_per_block = rows_per_block; s.C = C; s.G = G;
-    int slabs = ceil_div(592, nblocks);                      // ~4 CTAs per SM in flight
+    int slabs = ceil_div(nblocks == 1 ? 296 : 592, nblocks); // 2-4 CTAs per SM in flight; fewer slabs for BatchNorm: the finalize
+                                                             // kernels walk them with one warp per channel (latency bound)
     const int max_slabs = max(1, rows_per_block / 64);
     if (slabs > max_slabs) slabs = max_slabs;
     if (slabs > 512) slabs = 512;
