@@ -59,7 +59,10 @@ def _side_stream(device):
 def _sk_workspace(device):
     """Partial-tile slots + flags of the stream-K forward kernel, one per (device, stream): launches on one stream are
     ordered, so they can share it.  Zeroed once here; the kernel leaves every flag lowered."""
-    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    # inside a step opened with begin_step() (the graphed train step: warm-up, capture and replays are ordered among
+    # themselves) one workspace per device, allocated during the warm-up -- an allocation during capture would put its 50 MB
+    # zero-fill into the graph and replay it every step
+    key = (device, 'step') if STEP_TOKEN >= 0 else (device, torch.cuda.current_stream(device).cuda_stream)
     ws = _SK_WS.get(key)
     if ws is None:
         ws = _SK_WS[key] = torch.zeros(int(_lib.lib().mcnn_meshconv_fwd_tc_sk_ws()), dtype=torch.uint8, device=device)
