@@ -1141,6 +1141,11 @@ constexpr int BD_N = 160;
 // CONSECUTIVE channels 16*h + 4*(t%4) .. +3 of an edge row: the four threads of a quad then scatter 64 contiguous bytes of
 // one dx row with one red.v4 each, and a warp instruction touches 8 rows instead of 32 (the scatter is bound by the
 // number of distinct lines per instruction, one L1 wavefront each).
+// K position (within a 32-wide K block = 32 output channels) of output channel p of the block.  Permuted so that the
+// producers of the persistent kernel can write the A operand (dout rows) straight into TENSOR MEMORY in the mma-fragment
+// layout (tcgen05.st .16x256b: thread t holds columns 8i + 2(t%4) + {0,1}) from 32 CONTIGUOUS bytes of a row per thread:
+// memory channel 8q + j  <->  K column 8(j/2) + 2q + (j%2).  A and B use the same order, so the product is unchanged.
+__host__ __device__ constexpr int bd_kperm(int p) { return 8 * ((p & 7) >> 1) + 2 * (p >> 3) + (p & 1); }
 __host__ __device__ constexpr int bd_col(int cl) { return 8 * (2 * (cl >> 4) + ((cl >> 1) & 1)) + 2 * ((cl & 15) >> 2) + (cl & 1); }
 
 struct BdSmem {
@@ -1165,7 +1170,8 @@ __global__ void weight_tc_bwd_layout_kernel(const float* __restrict__ w, float* 
     float hi, lo;
     tc::split_tf32(w[((size_t)o * Cin + c) * 5 + k5], hi, lo);
     const int nrow = k5 * 32 + bd_col(n & 31);                 // B row = accumulator column of (tap, channel)
-    const size_t off = ((size_t)cb * (Cout >> 5) + kb) * (BD_N * 32) + (tc::sw128_off(nrow, p >> 2) >> 2) + (p & 3);
+    const int pk = bd_kperm(p);                                 // K position of this output channel inside its block
+    const size_t off = ((size_t)cb * (Cout >> 5) + kb) * (BD_N * 32) + (tc::sw128_off(nrow, pk >> 2) >> 2) + (pk & 3);
     img[off] = hi;
     img[(size_t)5 * Cin * Cout + off] = lo;
 }
@@ -1235,9 +1241,14 @@ meshconv_bwd_data_tc_kernel(const float* __restrict__ dout, const float* __restr
                 if (m < M) v = __ldg(reinterpret_cast<const float4*>(dout + (size_t)m * Cout + (kb << 5) + (q << 2)));
                 float4 hi, lo;
                 tc::split4(v, hi, lo);
-                const uint32_t off = tc::sw128_off(r, q);
-                tc::sts128(tc::smem_u32(a_hi) + off, hi);
-                tc::sts128(tc::smem_u32(a_lo) + off, lo);
+                // permuted K order (bd_kperm): the chunk's channels 4q .. 4q+3 are K columns c1, c1+1 and c1+8, c1+9
+                const int c1 = 16 * (q & 1) + 2 * (q >> 1);
+                const uint32_t o1 = tc::sw128_off(r, c1 >> 2) + (uint32_t)((c1 & 3) << 2);
+                const uint32_t o2 = tc::sw128_off(r, (c1 + 8) >> 2) + (uint32_t)((c1 & 3) << 2);
+                tc::sts64(tc::smem_u32(a_hi) + o1, hi.x, hi.y);
+                tc::sts64(tc::smem_u32(a_hi) + o2, hi.z, hi.w);
+                tc::sts64(tc::smem_u32(a_lo) + o1, lo.x, lo.y);
+                tc::sts64(tc::smem_u32(a_lo) + o2, lo.z, lo.w);
             }
             if (tid == 0) {                                               // B tile: two bulk copies of the pre-built image
                 tc::mbar_expect_tx(full_bar + s, 2 * S::B_BYTES);
@@ -1348,16 +1359,27 @@ constexpr int BDP_PRODUCER_WARPS = 8;
 constexpr int BDP_EPI_WARPS = 8;
 constexpr int BDP_THREADS = (BDP_PRODUCER_WARPS + 1 + BDP_EPI_WARPS) * 32;
 
+// Shared memory holds only the B (weight) tiles: the A operand lives in tensor memory.  TMEM columns (512 allocated):
+//   accumulators  [0,160) and [256,416);   A stage s: hi / lo = 32 columns each at  s0: 160 / 192,  s1: 416 / 448,  s2: 224 / 480
+struct BdpSmem {
+    static constexpr int B_BYTES = BD_N * 128;
+    static constexpr int STAGE_BYTES = 2 * B_BYTES;                   // 40960
+    static constexpr int STAGES = 3;                                  // = A stages that fit in TMEM next to two accumulators
+    static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+    static constexpr int TOTAL = BAR_OFF + 16 * 8 + 16 + 1024;
+};
+__device__ __forceinline__ uint32_t bdp_a_hi_col(uint32_t s) { return s == 0 ? 160u : (s == 1 ? 416u : 224u); }
+__device__ __forceinline__ uint32_t bdp_a_lo_col(uint32_t s) { return s == 0 ? 192u : (s == 1 ? 448u : 480u); }
+
 __global__ void __launch_bounds__(BDP_THREADS, 1)
 meshconv_bwd_data_tc_p_kernel(const float* __restrict__ dout, const int32_t* __restrict__ gemm, const int32_t* __restrict__ ec,
                               const float* __restrict__ wtb, float* __restrict__ dx, const int8_t* __restrict__ signs,
                               int B, int E, int Cin, int Cout) {
-    using S = BdSmem;
+    using S = BdpSmem;
     constexpr int PW = BDP_PRODUCER_WARPS, PT = PW * 32, ET = BDP_EPI_WARPS * 32;
-    constexpr int IT = (TC_M * 8) / PT;                          // 16-byte items per producer thread and K block
+    static_assert(PW == 8, "two producer warps per TMEM lane quarter");
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    int (*nb)[5] = reinterpret_cast<int (*)[5]>(smem + S::NB_OFF);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
     uint64_t* empty_bar = full_bar + S::STAGES;
     uint64_t* acc_full = empty_bar + S::STAGES;              // [2]
@@ -1370,7 +1392,7 @@ meshconv_bwd_data_tc_p_kernel(const float* __restrict__ dout, const int32_t* __r
     const long long n_items_all = (long long)ceil_div(M, TC_M) * ncb;
     const int G = gridDim.x, cta = blockIdx.x;
     const int item0 = (int)(n_items_all * cta / G), item1 = (int)(n_items_all * (cta + 1) / G);
-    const int dbg = g_tc_debug;            // diagnostics (results wrong): 1 no dout loads, 2 no MMA, 4 no st.shared, 16 no scatter, 32 no sign loads
+    const int dbg = g_tc_debug;            // diagnostics (results wrong): 1 no dout loads, 2 no MMA, 4 no TMEM stores, 8 no B copies, 16 no scatter, 32 no sign loads
 
     if (warp == PW) {
         if (lane == 0) {
@@ -1394,9 +1416,14 @@ meshconv_bwd_data_tc_p_kernel(const float* __restrict__ dout, const int32_t* __r
     const long long t_begin = clock64();
     if (warp < PW) {
         // ======================================== producers ========================================================
-        const int pt = tid;
+        // Warp w owns 16 accumulator rows: TMEM lanes 32 (w % 4) + 16 (w / 4) + [0, 16).  Thread t holds rows t/4 and t/4 + 8
+        // of them and, per K block, the 8 consecutive output channels 8 (t%4) .. +7 of each row (two 16-byte loads per row;
+        // a quad reads one 128-byte line) -- exactly the registers tcgen05.st .16x256b.x4 wants under the bd_kperm K order.
         const int n_q = (item1 - item0) * num_kb;                // (item, K block) steps of this CTA
-        struct Regs { float4 a[IT]; };
+        const int rowA = (warp & 3) * 32 + (warp >> 2) * 16 + (lane >> 2);       // and rowA + 8
+        const int q8 = (lane & 3) << 3;
+        const uint32_t lane_field = (uint32_t)((warp & 3) * 32 + (warp >> 2) * 16) << 16;
+        struct Regs { float4 a[4]; };                            // rowA: channels 0-3, 4-7; rowA + 8: channels 0-3, 4-7
         // (item, K block) of the step being loaded / stored are carried along instead of divided out of q: an integer
         // division by a run-time value is a ~100-cycle dependent chain, and a producer warp has its scheduler to itself
         struct Cursor {
@@ -1408,12 +1435,15 @@ meshconv_bwd_data_tc_p_kernel(const float* __restrict__ dout, const int32_t* __r
         Cursor lc, sc;                                           // load cursor (two steps ahead), store cursor
         lc.m0 = sc.m0 = (item0 / ncb) * TC_M; lc.cb = sc.cb = item0 % ncb; lc.kb = sc.kb = 0;
         uint32_t stage = 0, phase = 0;
+        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
         auto load_step = [&](Regs& R) {
 #pragma unroll
-            for (int it = 0; it < IT; ++it) {
-                const int e = pt + it * PT;
-                const int m = lc.m0 + (e >> 3);
-                R.a[it] = (m < M && !(dbg & 1)) ? __ldg(reinterpret_cast<const float4*>(dout + (size_t)m * Cout + (lc.kb << 5) + ((e & 7) << 2))) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int h = 0; h < 2; ++h) {
+                const int m = lc.m0 + rowA + 8 * h;
+                const float* p = dout + (size_t)m * Cout + (lc.kb << 5) + q8;
+                const bool ok = m < M && !(dbg & 1);
+                R.a[2 * h] = ok ? __ldg(reinterpret_cast<const float4*>(p)) : zero4;
+                R.a[2 * h + 1] = ok ? __ldg(reinterpret_cast<const float4*>(p + 4)) : zero4;
             }
             lc.next(num_kb, ncb);
         };
@@ -1421,25 +1451,32 @@ meshconv_bwd_data_tc_p_kernel(const float* __restrict__ dout, const int32_t* __r
             const uint32_t s = stage, ph = phase;
             if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
             BDP_ACC(tid == 0, 1, if (lane == 0) tc::mbar_wait(empty_bar + s, ph ^ 1); __syncwarp());
-            const uint32_t a_hi = tc::smem_u32(smem + s * S::STAGE_BYTES), a_lo = a_hi + S::A_BYTES;
+            tc::tc_fence_after();
             if (tid == 0 && !(dbg & 8)) {                                 // B tile: two bulk copies of the pre-built image
-                unsigned char* b_hi = smem + s * S::STAGE_BYTES + 2 * S::A_BYTES;
+                unsigned char* b_hi = smem + s * S::STAGE_BYTES;
                 tc::mbar_expect_tx(full_bar + s, 2 * S::B_BYTES);
                 const float* src = wtb + ((size_t)sc.cb * num_kb + sc.kb) * (BD_N * 32);
                 tc::bulk_g2s(b_hi, src, S::B_BYTES, full_bar + s);
                 tc::bulk_g2s(b_hi + S::B_BYTES, src + (size_t)5 * Cin * Cout, S::B_BYTES, full_bar + s);
             }
             sc.next(num_kb, ncb);
+            if (!(dbg & 4)) {
+                // fragment registers: v[4i + {0,1}] = rowA channels 2i, 2i+1;  v[4i + {2,3}] = rowA + 8, the same channels
+                const float fa[8] = {R.a[0].x, R.a[0].y, R.a[0].z, R.a[0].w, R.a[1].x, R.a[1].y, R.a[1].z, R.a[1].w};
+                const float fb[8] = {R.a[2].x, R.a[2].y, R.a[2].z, R.a[2].w, R.a[3].x, R.a[3].y, R.a[3].z, R.a[3].w};
+                float hi[16], lo[16];
 #pragma unroll
-            for (int it = 0; it < ((dbg & 4) ? 0 : IT); ++it) {
-                const int e = pt + it * PT;
-                float4 hi, lo;
-                tc::split4(R.a[it], hi, lo);
-                const uint32_t off = tc::sw128_off(e >> 3, e & 7);
-                tc::sts128(a_hi + off, hi);
-                tc::sts128(a_lo + off, lo);
+                for (int i = 0; i < 4; ++i) {
+                    tc::split_tf32(fa[2 * i], hi[4 * i], lo[4 * i]);
+                    tc::split_tf32(fa[2 * i + 1], hi[4 * i + 1], lo[4 * i + 1]);
+                    tc::split_tf32(fb[2 * i], hi[4 * i + 2], lo[4 * i + 2]);
+                    tc::split_tf32(fb[2 * i + 1], hi[4 * i + 3], lo[4 * i + 3]);
+                }
+                tc::tmem_st_16x256b_x4(tmem_base + lane_field + bdp_a_hi_col(s), hi);
+                tc::tmem_st_16x256b_x4(tmem_base + lane_field + bdp_a_lo_col(s), lo);
+                tc::tmem_wait_st();
             }
-            BDP_ACC(tid == 0, 2, if (!(dbg & 64)) tc::fence_proxy_async_smem(); __syncwarp(); if (lane == 0) tc::mbar_arrive(full_bar + s));
+            BDP_ACC(tid == 0, 2, tc::tc_fence_before(); __syncwarp(); if (lane == 0) tc::mbar_arrive(full_bar + s));
         };
         Regs R0, R1;
         if (n_q > 0) load_step(R0);
@@ -1472,29 +1509,18 @@ meshconv_bwd_data_tc_p_kernel(const float* __restrict__ dout, const int32_t* __r
                 BDP_ACC(lane == 0, 6, tc::mbar_wait(full_bar + s, ph));
                 tc::tc_fence_after();
                 if (tc::elect_one()) {
-#ifdef MCNN_TC_PROF
-                    const long long tm0 = clock64();
-#endif
-                    const uint32_t a_hi = tc::smem_u32(smem + s * S::STAGE_BYTES);
-                    const uint32_t a_lo = a_hi + S::A_BYTES;
-                    const uint32_t b_hi = a_lo + S::A_BYTES;
+                    const uint32_t a_hi = tmem_base + bdp_a_hi_col(s), a_lo = tmem_base + bdp_a_lo_col(s);
+                    const uint32_t b_hi = tc::smem_u32(smem + s * S::STAGE_BYTES);
                     const uint32_t b_lo = b_hi + S::B_BYTES;
 #pragma unroll
                     for (int kk = 0; kk < ((dbg & 2) ? 0 : 4); ++kk) {
-                        const uint64_t dah = tc::make_desc_sw128(a_hi + kk * 32), dal = tc::make_desc_sw128(a_lo + kk * 32);
                         const uint64_t dbh = tc::make_desc_sw128(b_hi + kk * 32), dbl = tc::make_desc_sw128(b_lo + kk * 32);
-                        tc::mma_tf32(acc, dah, dbh, idesc, (kb | kk) != 0);
-                        tc::mma_tf32(acc, dah, dbl, idesc, 1);
-                        tc::mma_tf32(acc, dal, dbh, idesc, 1);
+                        tc::mma_tf32_ts(acc, a_hi + 8 * kk, dbh, idesc, (kb | kk) != 0);
+                        tc::mma_tf32_ts(acc, a_hi + 8 * kk, dbl, idesc, 1);
+                        tc::mma_tf32_ts(acc, a_lo + 8 * kk, dbh, idesc, 1);
                     }
-#ifdef MCNN_TC_PROF
-                    const long long tc0 = clock64();
-#endif
                     tc::mma_commit(empty_bar + s);
                     if (kb == num_kb - 1) tc::mma_commit(acc_full + buf);
-#ifdef MCNN_TC_PROF
-                    if (blockIdx.x == g_sk_prof_cta) { g_sk_prof[9] += clock64() - tc0; g_sk_prof[10] += tc0 - tm0; }
-#endif
                 }
                 __syncwarp();
             }
@@ -1595,7 +1621,7 @@ meshconv_bwd_data_tc_p_kernel(const float* __restrict__ dout, const int32_t* __r
 #ifdef MCNN_TC_PROF
         if (lane == 0 && warp == PW + 1 && blockIdx.x == g_sk_prof_cta) g_sk_prof[7] += clock64() - t_begin;
 #endif
-        (void)nb;
+        (void)ET;
         tc::tc_fence_before();
     }
     __syncthreads();
@@ -2007,13 +2033,13 @@ extern "C" int mcnn_meshconv_bwd_data_tc_signs(const float* dout, const float* x
     if (signs != nullptr && !g_tc_bd_tile) {                 // persistent kernel (needs the signs kept by the forward)
         static bool configured_p = false;
         if (!configured_p) {
-            cudaError_t e = cudaFuncSetAttribute(meshconv_bwd_data_tc_p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BdSmem::TOTAL);
+            cudaError_t e = cudaFuncSetAttribute(meshconv_bwd_data_tc_p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BdpSmem::TOTAL);
             if (e != cudaSuccess) { g_last_error = e; return MCNN_E_CUDA; }
             configured_p = true;
         }
         const long long items = (long long)ceil_div(B * E, TC_M) * (Cin / 32);
         const int G = (int)min((long long)sm_count(), items);
-        meshconv_bwd_data_tc_p_kernel<<<G, BDP_THREADS, BdSmem::TOTAL, st>>>(dout, gemm, ec, wtb_ws, dx, signs, B, E, Cin, Cout);
+        meshconv_bwd_data_tc_p_kernel<<<G, BDP_THREADS, BdpSmem::TOTAL, st>>>(dout, gemm, ec, wtb_ws, dx, signs, B, E, Cin, Cout);
         return after_launch();
     }
     dim3 grid(ceil_div(B * E, TC_M), Cin / 32);
