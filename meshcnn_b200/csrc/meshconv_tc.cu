@@ -46,6 +46,16 @@ constexpr int TC_THREADS = (TC_PRODUCER_WARPS + 1) * 32;
 // two rows differ in bit 2: rows (r, r + 4) instead of (r, r + 1).
 __device__ __forceinline__ int pair_item_row(int i) { return ((i >> 5) << 3) + (((i >> 2) & 1) << 2) + ((i >> 3) & 3); }
 
+// Position inside a 32-wide K block of its p-th logical entry (blk 0: input channel p of the block; pair blocks: p < 16 ->
+// first tap, channel p; p >= 16 -> second tap, channel p - 16).  Permuted so that the producers of the persistent kernel
+// can write the A operand straight into TENSOR MEMORY in the mma-fragment layout (tcgen05.st .16x256b: thread t holds K
+// columns 8i + 2(t%4) + {0,1}): in a G0 block thread t owns channels 8(t%4) .. +7, in a pair block channels 4(t%4) .. +3 of
+// both taps -- each a contiguous piece of a gathered row.  A and B use the same order, so the product is unchanged.
+__host__ __device__ constexpr int fw_kpos(int blk, int p) {
+    return blk == 0 ? (8 * ((p & 7) >> 1) + 2 * (p >> 3) + (p & 1))
+                    : ((p & 16) + 8 * (((p & 15) & 3) >> 1) + 2 * ((p & 15) >> 2) + (p & 1));
+}
+
 // weight [Cout][Cin][5] -> the B operand exactly as the tensor core wants it in shared memory, split into TF32 head and
 // remainder:  img[hi|lo][kb][Cout rows x 128 bytes, canonical K-major SWIZZLE_128B atoms], K in the permuted order above.
 // The rows n0 .. n0+N_TILE of one K block are N_TILE*128 contiguous bytes, so a CTA fetches its B tile with one bulk copy
@@ -66,9 +76,20 @@ __global__ void weight_tc_layout_kernel(const float* __restrict__ w, float* __re
     }
     float hi, lo;
     tc::split_tf32(w[((size_t)o * Cin + c) * 5 + k5], hi, lo);
-    const size_t off = (size_t)kb * Cout * 32 + (tc::sw128_off(o, p >> 2) >> 2) + (p & 3);
+    const int pk = fw_kpos(blk, p);
+    const size_t off = (size_t)kb * Cout * 32 + (tc::sw128_off(o, pk >> 2) >> 2) + (pk & 3);
     img[off] = hi;
     img[(size_t)Cout * K + off] = lo;
+}
+
+// four consecutive logical K entries (a float4 of channels) under fw_kpos: K columns c1, c1+1 and c1+8, c1+9 of row r
+__device__ __forceinline__ void sts_kperm(uint32_t a_hi, uint32_t a_lo, int r, int c1, const float4& hi, const float4& lo) {
+    const uint32_t o1 = tc::sw128_off(r, c1 >> 2) + (uint32_t)((c1 & 3) << 2);
+    const uint32_t o2 = tc::sw128_off(r, (c1 + 8) >> 2) + (uint32_t)((c1 & 3) << 2);
+    tc::sts64(a_hi + o1, hi.x, hi.y);
+    tc::sts64(a_hi + o2, hi.z, hi.w);
+    tc::sts64(a_lo + o1, lo.x, lo.y);
+    tc::sts64(a_lo + o2, lo.z, lo.w);
 }
 
 template <int N_TILE>
@@ -211,10 +232,8 @@ meshconv_fwd_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ 
 #pragma unroll
                 for (int it = 0; it < IT0; ++it) {
                     const int item = pt + it * PT;
-                    const uint32_t off = tc::sw128_off(item >> 3, item & 7);
                     tc::split4(R.a[it], hi, lo);
-                    tc::sts128(tc::smem_u32(a_hi) + off, hi);
-                    tc::sts128(tc::smem_u32(a_lo) + off, lo);
+                    sts_kperm(tc::smem_u32(a_hi), tc::smem_u32(a_lo), item >> 3, 16 * (item & 1) + 2 * ((item & 7) >> 1), hi, lo);
                 }
             } else {
 #pragma unroll
@@ -232,13 +251,9 @@ meshconv_fwd_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ 
                         *reinterpret_cast<char4*>(signs + so) = make_char4((signed char)sgn(dd.x), (signed char)sgn(dd.y), (signed char)sgn(dd.z), (signed char)sgn(dd.w));
                     }
                     tc::split4(sum, hi, lo);
-                    uint32_t off = tc::sw128_off(r, q);
-                    tc::sts128(tc::smem_u32(a_hi) + off, hi);
-                    tc::sts128(tc::smem_u32(a_lo) + off, lo);
+                    sts_kperm(tc::smem_u32(a_hi), tc::smem_u32(a_lo), r, 2 * q, hi, lo);
                     tc::split4(dif, hi, lo);
-                    off = tc::sw128_off(r, q + 4);
-                    tc::sts128(tc::smem_u32(a_hi) + off, hi);
-                    tc::sts128(tc::smem_u32(a_lo) + off, lo);
+                    sts_kperm(tc::smem_u32(a_hi), tc::smem_u32(a_lo), r, 16 + 2 * q, hi, lo);
                 }
             }
 #ifdef MCNN_TC_PROF
@@ -364,14 +379,21 @@ constexpr int SK_MAX_CTAS = 192;                 // workspace: flags + two 128 x
 constexpr int SK_EPI_WARPS = 4;                  // one per TMEM lane quarter
 constexpr int SK_THREADS = (TC_PRODUCER_WARPS + 1 + SK_EPI_WARPS) * 32;
 
+// Shared memory holds only the B (weight) tiles; the A operand is written to tensor memory by the producers.  TMEM (512
+// columns): accumulator b at column b * N_TILE (two for N <= 128, one for N = 256), A stage s at 256 + 64 s (hi) / + 32 (lo).
 template <int N_TILE>
 struct SkSmem {
-    using T = TcSmem<N_TILE>;
-    static constexpr int NB_OFF = T::TILE_BYTES;                      // int nb[2][128][5]: gather table of this and the next tile
+    static constexpr int B_BYTES = N_TILE * 128;
+    static constexpr int STAGE_BYTES = 2 * B_BYTES;
+    static constexpr int STAGES = 3;                                  // = A stages in TMEM
+    static constexpr int TILE_BYTES = STAGES * STAGE_BYTES;
+    static constexpr int NB_OFF = TILE_BYTES;                         // int nb[2][128][5]: gather table of this and the next tile
     static constexpr int BAR_OFF = NB_OFF + 2 * TC_M * 5 * 4;
-    static constexpr int NBARS = 2 * T::STAGES + 8;                   // full / empty per stage, accumulator and table full / empty x 2
+    static constexpr int NBARS = 2 * STAGES + 8;                      // full / empty per stage, accumulator and table full / empty x 2
     static constexpr int TOTAL = BAR_OFF + NBARS * 8 + 16 + 1024;
-    static constexpr int TMEM_COLS = 2 * N_TILE;                      // two accumulators: the epilogue of a segment overlaps the next one
+    static constexpr int NACC = N_TILE <= 128 ? 2 : 1;                // accumulators: with two, the epilogue of a segment overlaps the next one
+    static constexpr int TMEM_COLS = 512;
+    static constexpr uint32_t A_COL0 = 256;
 };
 
 // The segments of one CTA's unit range, in the order they are processed.  A tile that the range boundaries cut into pieces
@@ -453,9 +475,11 @@ __global__ void __launch_bounds__(SK_THREADS, 1)
 meshconv_fwd_tc_sk_kernel(const float* __restrict__ x, const int32_t* __restrict__ gemm, const int32_t* __restrict__ ec,
                           const float* __restrict__ wt, const float* __restrict__ bias, float* __restrict__ out,
                           int8_t* __restrict__ signs, float* part, int* flags, int B, int E, int Cin, int Cout) {
-    using S = TcSmem<N_TILE>;
+    using S = SkSmem<N_TILE>;
     using SS = SkSmem<N_TILE>;
-    constexpr int PW = TC_PRODUCER_WARPS, PT = PW * 32, IT0 = (TC_M * 8) / PT, ITP = (TC_M * 4) / PT;
+    constexpr int PW = TC_PRODUCER_WARPS, PT = PW * 32;
+    constexpr int NACC = SS::NACC;
+    static_assert(PW == 8, "two producer warps per TMEM lane quarter");
     constexpr int ET = SK_EPI_WARPS * 32;
     SK_STAMP(threadIdx.x == 0, 61);
 #ifdef MCNN_TC_PROF
@@ -506,7 +530,7 @@ meshconv_fwd_tc_sk_kernel(const float* __restrict__ x, const int32_t* __restrict
     // -> out.  The calling warp reads its TMEM lane quarter and the 32-column chunks chunk0, chunk0 + step, ...
     auto finish_tile = [&](const SkSeg& sg, int seg, int chunk0, int step, bool all_warps) {
         const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        const int tile = sg.tile, buf = seg & 1;
+        const int tile = sg.tile, buf = seg % NACC;
         const int mt = tile / ntn, nt = tile - mt * ntn;
         const int m0 = mt * TC_M, n0 = nt * N_TILE;
         const int lane_grp = warp & 3;                           // the TMEM lane quarter this warp may read
@@ -544,7 +568,7 @@ meshconv_fwd_tc_sk_kernel(const float* __restrict__ x, const int32_t* __restrict
 #pragma unroll
             for (int j = 0; j < 8; ++j) nxt[j] = __ldcg(p_first + (size_t)(chunk0 * 8 + j) * TC_M);
         }
-        tc::mbar_wait(acc_full + buf, (seg >> 1) & 1);
+        tc::mbar_wait(acc_full + buf, (seg / NACC) & 1);
         tc::tc_fence_after();
         SK_STAMP(tid == (PW + 1) * 32, 20 + 4 * seg);
 #pragma unroll 1
@@ -584,98 +608,103 @@ meshconv_fwd_tc_sk_kernel(const float* __restrict__ x, const int32_t* __restrict
 
     if (warp < PW) {
         // ======================================== producers ========================================================
-        const int pt = tid;
+        // Warp w owns 16 rows of the tile: TMEM lanes 32 (w % 4) + 16 (w / 4) + [0, 16); thread t holds rows t/4 and t/4 + 8 of
+        // them.  Per K block it gathers, for each of its two rows, 32 contiguous bytes (G0 block: channels 8 (t%4) .. +7) or
+        // 16 + 16 (pair block: channels 4 (t%4) .. +3 of both gathered rows), forms the symmetric functions, splits and writes
+        // the values into tensor memory with tcgen05.st .16x256b.x4 -- the registers are already in that layout (fw_kpos).
+        const int rowA = (warp & 3) * 32 + (warp >> 2) * 16 + (lane >> 2);       // and rowA + 8
+        const int q4 = lane & 3;
+        const uint32_t lane_field = (uint32_t)((warp & 3) * 32 + (warp >> 2) * 16) << 16;
         const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        struct Regs { float4 a[IT0]; };
+        struct Regs { float4 a[4]; };            // G0: rowA ch 0-3, 4-7, rowB ch 0-3, 4-7;  pair: rowA first, second row; rowB first, second
         uint32_t g = 0;                                          // K blocks this CTA has pushed through the stage ring
         for (int seg = 0; seg < nseg; ++seg) {
             const SkSeg sg = plan.seg(seg);
             const int tile = sg.tile, ka = sg.ka, ke = sg.ke;
             const int mt = tile / ntn, nt = tile - mt * ntn;
             const int m0 = mt * TC_M, n0 = nt * N_TILE;
-            const int buf = seg & 1;
-            tc::mbar_wait(nb_full + buf, (seg >> 1) & 1);
+            const int nbuf = seg & 1;
+            tc::mbar_wait(nb_full + nbuf, (seg >> 1) & 1);
             SK_STAMP(tid == 0, 1 + 4 * seg);
-            int src0[IT0], srcA[ITP][2], srcB[ITP][2];
+            int src[2][5];                                       // gather rows of rowA / rowA + 8: self, then the four neighbours
 #pragma unroll
-            for (int it = 0; it < IT0; ++it) src0[it] = nb[buf][(pt + it * PT) >> 3][0];
+            for (int h = 0; h < 2; ++h)
 #pragma unroll
-            for (int it = 0; it < ITP; ++it) {
-                const int r = pair_item_row(pt + it * PT);
-                srcA[it][0] = nb[buf][r][1]; srcB[it][0] = nb[buf][r][3];
-                srcA[it][1] = nb[buf][r][2]; srcB[it][1] = nb[buf][r][4];
-            }
+                for (int kq = 0; kq < 5; ++kq) src[h][kq] = nb[nbuf][rowA + 8 * h][kq];
             __syncwarp();
-            if (lane == 0) tc::mbar_arrive(nb_empty + buf);
+            if (lane == 0) tc::mbar_arrive(nb_empty + nbuf);
             auto load_block = [&](int kb, Regs& R) {
                 const int cb = kb / 5, blk = kb - cb * 5;
                 if (blk == 0) {
-                    const int c = cb * 32 + ((pt & 7) << 2);
+                    const int c = cb * 32 + (q4 << 3);
 #pragma unroll
-                    for (int it = 0; it < IT0; ++it)
-                        R.a[it] = src0[it] >= 0 ? __ldg(reinterpret_cast<const float4*>(x + (size_t)src0[it] * Cin + c)) : zero4;
+                    for (int h = 0; h < 2; ++h) {
+                        const float* p = x + (size_t)src[h][0] * Cin + c;
+                        R.a[2 * h] = src[h][0] >= 0 ? __ldg(reinterpret_cast<const float4*>(p)) : zero4;
+                        R.a[2 * h + 1] = src[h][0] >= 0 ? __ldg(reinterpret_cast<const float4*>(p + 4)) : zero4;
+                    }
                 } else {
                     const int pr = (blk <= 2) ? 0 : 1;
-                    const int c = cb * 32 + (((blk - 1) & 1) << 4) + ((pt & 3) << 2);
+                    const int c = cb * 32 + (((blk - 1) & 1) << 4) + (q4 << 2);
 #pragma unroll
-                    for (int it = 0; it < ITP; ++it) {
-                        const int sa = pr ? srcA[it][1] : srcA[it][0], sb = pr ? srcB[it][1] : srcB[it][0];
-                        R.a[2 * it] = sa >= 0 ? __ldg(reinterpret_cast<const float4*>(x + (size_t)sa * Cin + c)) : zero4;
-                        R.a[2 * it + 1] = sb >= 0 ? __ldg(reinterpret_cast<const float4*>(x + (size_t)sb * Cin + c)) : zero4;
+                    for (int h = 0; h < 2; ++h) {
+                        const int sa = pr ? src[h][2] : src[h][1], sb = pr ? src[h][4] : src[h][3];     // selects, not a dynamic index
+                        R.a[2 * h] = sa >= 0 ? __ldg(reinterpret_cast<const float4*>(x + (size_t)sa * Cin + c)) : zero4;
+                        R.a[2 * h + 1] = sb >= 0 ? __ldg(reinterpret_cast<const float4*>(x + (size_t)sb * Cin + c)) : zero4;
                     }
                 }
             };
             auto store_block = [&](int kb, const Regs& R) {
-                const int s = g % S::STAGES;
+                const uint32_t s = g % S::STAGES;
                 const uint32_t ph = (g / S::STAGES) & 1;
                 ++g;
                 if (lane == 0) tc::mbar_wait(empty_bar + s, ph ^ 1);
                 __syncwarp();
-                const uint32_t a_hi = tc::smem_u32(smem + s * S::STAGE_BYTES);
-                const uint32_t a_lo = a_hi + S::A_BYTES;
+                tc::tc_fence_after();
                 const int blk = kb % 5;
-                float4 hi, lo;
                 if (tid == 0) {
-                    unsigned char* b_hi = smem + s * S::STAGE_BYTES + 2 * S::A_BYTES;
+                    unsigned char* b_hi = smem + s * S::STAGE_BYTES;
                     tc::mbar_expect_tx(full_bar + s, 2 * S::B_BYTES);
-                    const float* src = wt + ((size_t)kb * Cout + n0) * 32;
-                    tc::bulk_g2s(b_hi, src, S::B_BYTES, full_bar + s);
-                    tc::bulk_g2s(b_hi + S::B_BYTES, src + (size_t)Cout * K, S::B_BYTES, full_bar + s);
+                    const float* srcw = wt + ((size_t)kb * Cout + n0) * 32;
+                    tc::bulk_g2s(b_hi, srcw, S::B_BYTES, full_bar + s);
+                    tc::bulk_g2s(b_hi + S::B_BYTES, srcw + (size_t)Cout * K, S::B_BYTES, full_bar + s);
                 }
+                float va[8], vb[8];                              // the 8 K entries of rowA / rowA + 8 owned by this thread
                 if (blk == 0) {
-#pragma unroll
-                    for (int it = 0; it < IT0; ++it) {
-                        const int item = pt + it * PT;
-                        const uint32_t off = tc::sw128_off(item >> 3, item & 7);
-                        tc::split4(R.a[it], hi, lo);
-                        tc::sts128(a_hi + off, hi);
-                        tc::sts128(a_lo + off, lo);
-                    }
+                    va[0] = R.a[0].x; va[1] = R.a[0].y; va[2] = R.a[0].z; va[3] = R.a[0].w;
+                    va[4] = R.a[1].x; va[5] = R.a[1].y; va[6] = R.a[1].z; va[7] = R.a[1].w;
+                    vb[0] = R.a[2].x; vb[1] = R.a[2].y; vb[2] = R.a[2].z; vb[3] = R.a[2].w;
+                    vb[4] = R.a[3].x; vb[5] = R.a[3].y; vb[6] = R.a[3].z; vb[7] = R.a[3].w;
                 } else {
 #pragma unroll
-                    for (int it = 0; it < ITP; ++it) {
-                        const int item = pt + it * PT;
-                        const int r = pair_item_row(item), q = item & 3;
-                        const float4 fa = R.a[2 * it], fb = R.a[2 * it + 1];
-                        const float4 sum = make_float4(fa.x + fb.x, fa.y + fb.y, fa.z + fb.z, fa.w + fb.w);
-                        const float4 dd = make_float4(fa.x - fb.x, fa.y - fb.y, fa.z - fb.z, fa.w - fb.w);
-                        const float4 dif = make_float4(fabsf(dd.x), fabsf(dd.y), fabsf(dd.z), fabsf(dd.w));
-                        if (signs != nullptr && nt == 0 && m0 + r < M) {
-                            const int c_ = (kb / 5) * 32 + (((blk - 1) & 1) << 4) + (q << 2);
-                            const size_t so = ((size_t)(blk <= 2 ? 0 : 1) * M + (m0 + r)) * Cin + c_;
-                            *reinterpret_cast<char4*>(signs + so) = make_char4((signed char)sgn(dd.x), (signed char)sgn(dd.y), (signed char)sgn(dd.z), (signed char)sgn(dd.w));
+                    for (int h = 0; h < 2; ++h) {
+                        const float4 fa = R.a[2 * h], fb = R.a[2 * h + 1];
+                        const float dd[4] = {fa.x - fb.x, fa.y - fb.y, fa.z - fb.z, fa.w - fb.w};
+                        float* v = h ? vb : va;
+                        v[0] = fa.x + fb.x; v[1] = fa.y + fb.y; v[2] = fa.z + fb.z; v[3] = fa.w + fb.w;
+                        v[4] = fabsf(dd[0]); v[5] = fabsf(dd[1]); v[6] = fabsf(dd[2]); v[7] = fabsf(dd[3]);
+                        const int m = m0 + rowA + 8 * h;
+                        if (signs != nullptr && nt == 0 && m < M) {
+                            // sign(f1 - f3) / sign(f2 - f4) of this edge, kept for the data-gradient kernel (abs backward)
+                            const int c_ = (kb / 5) * 32 + (((blk - 1) & 1) << 4) + (q4 << 2);
+                            const size_t so = ((size_t)(blk <= 2 ? 0 : 1) * M + m) * Cin + c_;
+                            *reinterpret_cast<char4*>(signs + so) = make_char4((signed char)sgn(dd[0]), (signed char)sgn(dd[1]), (signed char)sgn(dd[2]), (signed char)sgn(dd[3]));
                         }
-                        tc::split4(sum, hi, lo);
-                        uint32_t off = tc::sw128_off(r, q);
-                        tc::sts128(a_hi + off, hi);
-                        tc::sts128(a_lo + off, lo);
-                        tc::split4(dif, hi, lo);
-                        off = tc::sw128_off(r, q + 4);
-                        tc::sts128(a_hi + off, hi);
-                        tc::sts128(a_lo + off, lo);
                     }
                 }
-                tc::fence_proxy_async_smem();
+                float hi[16], lo[16];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    tc::split_tf32(va[2 * i], hi[4 * i], lo[4 * i]);
+                    tc::split_tf32(va[2 * i + 1], hi[4 * i + 1], lo[4 * i + 1]);
+                    tc::split_tf32(vb[2 * i], hi[4 * i + 2], lo[4 * i + 2]);
+                    tc::split_tf32(vb[2 * i + 1], hi[4 * i + 3], lo[4 * i + 3]);
+                }
+                const uint32_t acol = tmem_base + lane_field + SS::A_COL0 + 64u * s;
+                tc::tmem_st_16x256b_x4(acol, hi);
+                tc::tmem_st_16x256b_x4(acol + 32u, lo);
+                tc::tmem_wait_st();
+                tc::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(full_bar + s);
             };
@@ -712,29 +741,27 @@ meshconv_fwd_tc_sk_kernel(const float* __restrict__ x, const int32_t* __restrict
         for (int seg = 0; seg < nseg; ++seg) {
             const SkSeg sg = plan.seg(seg);
             const int ka = sg.ka, ke = sg.ke;
-            const int buf = seg & 1;
+            const int buf = seg % NACC;
             const uint32_t acc = tmem_base + (uint32_t)(buf * N_TILE);
-            if (seg >= 2) {                                      // the epilogue of segment seg - 2 has drained this accumulator
-                tc::mbar_wait(acc_empty + buf, ((seg >> 1) - 1) & 1);
+            if (seg >= NACC) {                                   // the epilogue of segment seg - NACC has drained this accumulator
+                tc::mbar_wait(acc_empty + buf, ((seg / NACC) - 1) & 1);
                 tc::tc_fence_after();
             }
             for (int kb = ka; kb < ke; ++kb, ++g) {
-                const int s = g % S::STAGES;
+                const uint32_t s = g % S::STAGES;
                 const uint32_t ph = (g / S::STAGES) & 1;
                 tc::mbar_wait(full_bar + s, ph);
                 tc::tc_fence_after();
                 if (tc::elect_one()) {
-                    const uint32_t a_hi = tc::smem_u32(smem + s * S::STAGE_BYTES);
-                    const uint32_t a_lo = a_hi + S::A_BYTES;
-                    const uint32_t b_hi = a_lo + S::A_BYTES;
+                    const uint32_t a_hi = tmem_base + SS::A_COL0 + 64u * s, a_lo = a_hi + 32u;
+                    const uint32_t b_hi = tc::smem_u32(smem + s * S::STAGE_BYTES);
                     const uint32_t b_lo = b_hi + S::B_BYTES;
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk) {
-                        const uint64_t dah = tc::make_desc_sw128(a_hi + kk * 32), dal = tc::make_desc_sw128(a_lo + kk * 32);
                         const uint64_t dbh = tc::make_desc_sw128(b_hi + kk * 32), dbl = tc::make_desc_sw128(b_lo + kk * 32);
-                        tc::mma_tf32(acc, dah, dbh, idesc, (kb != ka) || (kk != 0));
-                        tc::mma_tf32(acc, dah, dbl, idesc, 1);
-                        tc::mma_tf32(acc, dal, dbh, idesc, 1);
+                        tc::mma_tf32_ts(acc, a_hi + 8 * kk, dbh, idesc, (kb != ka) || (kk != 0));
+                        tc::mma_tf32_ts(acc, a_hi + 8 * kk, dbl, idesc, 1);
+                        tc::mma_tf32_ts(acc, a_lo + 8 * kk, dbh, idesc, 1);
                     }
                     tc::mma_commit(empty_bar + s);
                     if (kb == ke - 1) tc::mma_commit(acc_full + buf);
@@ -771,11 +798,11 @@ meshconv_fwd_tc_sk_kernel(const float* __restrict__ x, const int32_t* __restrict
             const int tile = sg.tile;
             const int mt = tile / ntn, nt = tile - mt * ntn;
             const int m0 = mt * TC_M, n0 = nt * N_TILE;
-            const int buf = seg & 1;
+            const int nbuf = seg & 1, buf = seg % NACC;
             SK_STAMP(et == 0, 23 + 4 * seg);
             if (seg + 1 < nseg) {                                // gather table of the next segment's tile
-                if (seg >= 1) tc::mbar_wait(nb_empty + (buf ^ 1), ((seg - 1) >> 1) & 1);   // producers copied segment seg - 1's table out
-                fill_table(plan.seg(seg + 1).tile, buf ^ 1);
+                if (seg >= 1) tc::mbar_wait(nb_empty + (nbuf ^ 1), ((seg - 1) >> 1) & 1);   // producers copied segment seg - 1's table out
+                fill_table(plan.seg(seg + 1).tile, nbuf ^ 1);
             }
             const int lane_grp = warp & 3;                       // the TMEM lane quarter this warp may read
             const int r = lane_grp * 32 + lane;
@@ -783,7 +810,7 @@ meshconv_fwd_tc_sk_kernel(const float* __restrict__ x, const int32_t* __restrict
             const uint32_t acc = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(buf * N_TILE);
             if (sg.kind == 1) {
                 // ---- a piece of a tile another CTA owns: publish the raw accumulator ----
-                tc::mbar_wait(acc_full + buf, (seg >> 1) & 1);
+                tc::mbar_wait(acc_full + buf, (seg / NACC) & 1);
                 tc::tc_fence_after();
                 SK_STAMP(et == 0, 20 + 4 * seg);
 #pragma unroll 1
@@ -951,10 +978,8 @@ meshconv_fwd_tc2_kernel(const float* __restrict__ x, const int32_t* __restrict__
 #pragma unroll
                 for (int it = 0; it < 4; ++it) {
                     const int item = pt + it * 256;
-                    const uint32_t off = tc::sw128_off(item >> 3, item & 7);
                     tc::split4(R.a[it], hi, lo);
-                    tc::sts128(tc::smem_u32(a_hi) + off, hi);
-                    tc::sts128(tc::smem_u32(a_lo) + off, lo);
+                    sts_kperm(tc::smem_u32(a_hi), tc::smem_u32(a_lo), item >> 3, 16 * (item & 1) + 2 * ((item & 7) >> 1), hi, lo);
                 }
             } else {
 #pragma unroll
@@ -972,13 +997,9 @@ meshconv_fwd_tc2_kernel(const float* __restrict__ x, const int32_t* __restrict__
                         *reinterpret_cast<char4*>(signs + so) = make_char4((signed char)sgn(dd.x), (signed char)sgn(dd.y), (signed char)sgn(dd.z), (signed char)sgn(dd.w));
                     }
                     tc::split4(sum, hi, lo);
-                    uint32_t off = tc::sw128_off(r, q);
-                    tc::sts128(tc::smem_u32(a_hi) + off, hi);
-                    tc::sts128(tc::smem_u32(a_lo) + off, lo);
+                    sts_kperm(tc::smem_u32(a_hi), tc::smem_u32(a_lo), r, 2 * q, hi, lo);
                     tc::split4(dif, hi, lo);
-                    off = tc::sw128_off(r, q + 4);
-                    tc::sts128(tc::smem_u32(a_hi) + off, hi);
-                    tc::sts128(tc::smem_u32(a_lo) + off, lo);
+                    sts_kperm(tc::smem_u32(a_hi), tc::smem_u32(a_lo), r, 16 + 2 * q, hi, lo);
                 }
             }
             tc::fence_proxy_async_smem();

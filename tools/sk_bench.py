@@ -11,6 +11,8 @@ from meshcnn_b200 import mesh_prepare
 
 dev = torch.device('cuda:0')
 L = _lib.lib()
+if os.environ.get('SK_NTILE'):
+    L.mcnn_debug_set_tc_ntile(int(os.environ['SK_NTILE']))
 B = 64
 datas = [mesh_prepare.from_arrays(*synth.make('ico' if s % 3 else 'torus', s, **(dict(nu=5) if s % 3 else dict(m=10, n=25)))) for s in range(B)]
 
