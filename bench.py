@@ -512,7 +512,7 @@ def main():
         if os.path.exists(tpath):
             ent = json.load(open(tpath)).get('%s|%s' % (name, ','.join('%s=%s' % kv for kv in sorted(m.items()))))
             if ent:
-                traffic, traffic_src = ent['dram_bytes'], 'profiles/r01_v10_ncu_top_kernels.md row %d (ncu --set full, one launch)' % ent['row']
+                traffic, traffic_src = ent['dram_bytes'], 'profiles/r01_v11_ncu_top_kernels.md row %d (ncu --set full, one launch)' % ent['row']
         common = {'kernel': name, 'shape': m, 'avg_launch_ms': avg_ms, 'algorithmic_bytes': nbytes, 'traffic': traffic,
                   'traffic_source': traffic_src,
                   'dominant_by_time': dominant,

@@ -47,7 +47,7 @@ for E, cin, cout in [(750, 64, 64), (600, 64, 128), (600, 128, 128), (450, 128, 
     print('E %d %d->%d: items %d  tile kernel %.1f us, persistent %.1f us (%.2fx), rel diff %.1e' % (E, cin, cout, (B * E + 127) // 128 * (cin // 32), t0, t1, t0 / t1, err), flush=True)
     if len(sys.argv) > 1:
         res = []
-        for knob in (0, 16, 18, 17, 20, 24, 21, 23, 31):
+        for knob in (0, 16, 2, 4, 1, 8, 20, 22, 31):
             L.mcnn_debug_set_tc(knob)
             res.append('%d: %.1f' % (knob, timeit(call)))
         L.mcnn_debug_set_tc(0)
