@@ -1417,7 +1417,7 @@ meshconv_bwd_data_tc_p_kernel(const float* __restrict__ dout, const int32_t* __r
 
     if (warp == PW) {
         if (lane == 0) {
-            for (int s = 0; s < S::STAGES; ++s) { tc::mbar_init(full_bar + s, PW); tc::mbar_init(empty_bar + s, 1); }
+            for (int s = 0; s < S::STAGES; ++s) { tc::mbar_init(full_bar + s, PW / 2); tc::mbar_init(empty_bar + s, 1); }
             for (int i = 0; i < 2; ++i) { tc::mbar_init(acc_full + i, 1); tc::mbar_init(acc_empty + i, BDP_EPI_WARPS); }
             tc::fence_barrier_init();
         }
@@ -1437,14 +1437,18 @@ meshconv_bwd_data_tc_p_kernel(const float* __restrict__ dout, const int32_t* __r
     const long long t_begin = clock64();
     if (warp < PW) {
         // ======================================== producers ========================================================
-        // Warp w owns 16 accumulator rows: TMEM lanes 32 (w % 4) + 16 (w / 4) + [0, 16).  Thread t holds rows t/4 and t/4 + 8
-        // of them and, per K block, the 8 consecutive output channels 8 (t%4) .. +7 of each row (two 16-byte loads per row;
-        // a quad reads one 128-byte line) -- exactly the registers tcgen05.st .16x256b.x4 wants under the bd_kperm K order.
+        // Two groups of four warps take alternate (item, K block) steps, so the serial chain of a step (wait for the stage,
+        // split, tcgen05.st, wait::st, hand-over) may last two step periods; the gathers of a group's next step fly while
+        // the other group works.  Inside a group warp w owns the TMEM lane quarter w % 4 (32 accumulator rows, as two 16-lane
+        // halves); thread t holds rows t/4 and t/4 + 8 of each half and, per K block, the 8 consecutive output channels
+        // 8 (t%4) .. +7 of each row (two 16-byte loads per row; a quad reads one 128-byte line) -- exactly the registers
+        // tcgen05.st .16x256b.x4 wants under the bd_kperm K order.
         const int n_q = (item1 - item0) * num_kb;                // (item, K block) steps of this CTA
-        const int rowA = (warp & 3) * 32 + (warp >> 2) * 16 + (lane >> 2);       // and rowA + 8
+        const int grp = warp >> 2;
+        const int row0 = (warp & 3) * 32 + (lane >> 2);          // rows row0 + {0, 8, 16, 24}
         const int q8 = (lane & 3) << 3;
-        const uint32_t lane_field = (uint32_t)((warp & 3) * 32 + (warp >> 2) * 16) << 16;
-        struct Regs { float4 a[4]; };                            // rowA: channels 0-3, 4-7; rowA + 8: channels 0-3, 4-7
+        const uint32_t lane_field = (uint32_t)((warp & 3) * 32) << 16;
+        struct Regs { float4 a[8]; };                            // row k (0..3): channels 0-3 in a[2k], 4-7 in a[2k+1]
         // (item, K block) of the step being loaded / stored are carried along instead of divided out of q: an integer
         // division by a run-time value is a ~100-cycle dependent chain, and a producer warp has its scheduler to itself
         struct Cursor {
@@ -1453,62 +1457,65 @@ meshconv_bwd_data_tc_p_kernel(const float* __restrict__ dout, const int32_t* __r
                 if (++kb == num_kb) { kb = 0; if (++cb == ncb) { cb = 0; m0 += TC_M; } }
             }
         };
-        Cursor lc, sc;                                           // load cursor (two steps ahead), store cursor
-        lc.m0 = sc.m0 = (item0 / ncb) * TC_M; lc.cb = sc.cb = item0 % ncb; lc.kb = sc.kb = 0;
-        uint32_t stage = 0, phase = 0;
+        Cursor lc;                                               // this group's next step to load; the store cursor follows it
+        lc.m0 = (item0 / ncb) * TC_M; lc.cb = item0 % ncb; lc.kb = 0;
+        if (grp) lc.next(num_kb, ncb);
+        Cursor sc = lc;
+        uint32_t stage = (uint32_t)grp, phase = 0;
         const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
         auto load_step = [&](Regs& R) {
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int m = lc.m0 + rowA + 8 * h;
+            for (int k = 0; k < 4; ++k) {
+                const int m = lc.m0 + row0 + 8 * k;
                 const float* p = dout + (size_t)m * Cout + (lc.kb << 5) + q8;
                 const bool ok = m < M && !(dbg & 1);
-                R.a[2 * h] = ok ? __ldg(reinterpret_cast<const float4*>(p)) : zero4;
-                R.a[2 * h + 1] = ok ? __ldg(reinterpret_cast<const float4*>(p + 4)) : zero4;
+                R.a[2 * k] = ok ? __ldg(reinterpret_cast<const float4*>(p)) : zero4;
+                R.a[2 * k + 1] = ok ? __ldg(reinterpret_cast<const float4*>(p + 4)) : zero4;
             }
-            lc.next(num_kb, ncb);
+            lc.next(num_kb, ncb); lc.next(num_kb, ncb);
         };
         auto store_step = [&](const Regs& R) {
             const uint32_t s = stage, ph = phase;
-            if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
+            stage += 2;
+            if (stage >= (uint32_t)S::STAGES) { stage -= S::STAGES; phase ^= 1; }
             BDP_ACC(tid == 0, 1, if (lane == 0) tc::mbar_wait(empty_bar + s, ph ^ 1); __syncwarp());
             tc::tc_fence_after();
-            if (tid == 0 && !(dbg & 8)) {                                 // B tile: two bulk copies of the pre-built image
+            if ((tid & 127) == 0 && !(dbg & 8)) {                         // B tile: two bulk copies of the pre-built image
                 unsigned char* b_hi = smem + s * S::STAGE_BYTES;
                 tc::mbar_expect_tx(full_bar + s, 2 * S::B_BYTES);
                 const float* src = wtb + ((size_t)sc.cb * num_kb + sc.kb) * (BD_N * 32);
                 tc::bulk_g2s(b_hi, src, S::B_BYTES, full_bar + s);
                 tc::bulk_g2s(b_hi + S::B_BYTES, src + (size_t)5 * Cin * Cout, S::B_BYTES, full_bar + s);
             }
-            sc.next(num_kb, ncb);
+            sc.next(num_kb, ncb); sc.next(num_kb, ncb);
             if (!(dbg & 4)) {
-                // fragment registers: v[4i + {0,1}] = rowA channels 2i, 2i+1;  v[4i + {2,3}] = rowA + 8, the same channels
-                const float fa[8] = {R.a[0].x, R.a[0].y, R.a[0].z, R.a[0].w, R.a[1].x, R.a[1].y, R.a[1].z, R.a[1].w};
-                const float fb[8] = {R.a[2].x, R.a[2].y, R.a[2].z, R.a[2].w, R.a[3].x, R.a[3].y, R.a[3].z, R.a[3].w};
-                float hi[16], lo[16];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    tc::split_tf32(fa[2 * i], hi[4 * i], lo[4 * i]);
-                    tc::split_tf32(fa[2 * i + 1], hi[4 * i + 1], lo[4 * i + 1]);
-                    tc::split_tf32(fb[2 * i], hi[4 * i + 2], lo[4 * i + 2]);
-                    tc::split_tf32(fb[2 * i + 1], hi[4 * i + 3], lo[4 * i + 3]);
+                for (int h = 0; h < 2; ++h) {
+                    // fragment registers: v[4i + {0,1}] = row (2h) channels 2i, 2i+1;  v[4i + {2,3}] = row (2h + 1), the same channels
+                    const float4 a0 = R.a[4 * h], a1 = R.a[4 * h + 1], b0 = R.a[4 * h + 2], b1 = R.a[4 * h + 3];
+                    const float fa[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                    const float fb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                    float hi[16], lo[16];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        tc::split_tf32(fa[2 * i], hi[4 * i], lo[4 * i]);
+                        tc::split_tf32(fa[2 * i + 1], hi[4 * i + 1], lo[4 * i + 1]);
+                        tc::split_tf32(fb[2 * i], hi[4 * i + 2], lo[4 * i + 2]);
+                        tc::split_tf32(fb[2 * i + 1], hi[4 * i + 3], lo[4 * i + 3]);
+                    }
+                    const uint32_t lf = lane_field + ((uint32_t)(16 * h) << 16);
+                    tc::tmem_st_16x256b_x4(tmem_base + lf + bdp_a_hi_col(s), hi);
+                    tc::tmem_st_16x256b_x4(tmem_base + lf + bdp_a_lo_col(s), lo);
                 }
-                tc::tmem_st_16x256b_x4(tmem_base + lane_field + bdp_a_hi_col(s), hi);
-                tc::tmem_st_16x256b_x4(tmem_base + lane_field + bdp_a_lo_col(s), lo);
                 tc::tmem_wait_st();
             }
             BDP_ACC(tid == 0, 2, tc::tc_fence_before(); __syncwarp(); if (lane == 0) tc::mbar_arrive(full_bar + s));
         };
-        Regs R0, R1;
-        if (n_q > 0) load_step(R0);
-        if (n_q > 1) load_step(R1);
-        for (int q = 0; q < n_q; q += 2) {
-            store_step(R0);
-            if (q + 2 < n_q) load_step(R0);
-            if (q + 1 < n_q) {
-                store_step(R1);
-                if (q + 3 < n_q) load_step(R1);
-            }
+        Regs R;
+        if (grp < n_q) load_step(R);
+        for (int q = grp; q < n_q; q += 2) {
+            store_step(R);
+            if (q + 2 < n_q) load_step(R);
         }
 #ifdef MCNN_TC_PROF
         if (tid == 0 && blockIdx.x == g_sk_prof_cta) { g_sk_prof[0] += clock64() - t_begin; g_sk_prof[3] += n_q; }
