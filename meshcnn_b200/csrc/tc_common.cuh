@@ -154,16 +154,6 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// 8 columns, no wait: issue several, then tmem_wait_ld() once
-__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, float (&v)[8]) {
-    uint32_t r[8];
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                 : "r"(taddr)
-                 : "memory");
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
-}
 // 16 TMEM lanes x 16 columns in the mma-fragment pattern (.16x256b.x2), no wait.  Thread t of the warp receives, for lane
 // base L and column base C of taddr:   v[0], v[1] = lane L + t/4,     columns C + 2(t%4) + {0, 1}
 //                                      v[2], v[3] = lane L + t/4 + 8, the same columns
