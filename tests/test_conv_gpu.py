@@ -260,3 +260,35 @@ def test_conv_weight_gradient_two_output_tiles_per_cta(cin, cout, B):
     for a, b in zip(res[1], res[0]):
         err = float((a - b).abs().max() / b.abs().max())
         assert err <= 1e-5, err
+
+
+@pytest.mark.parametrize('cin,cout,B', [(256, 256, 26), (256, 256, 39), (128, 128, 52), (64, 64, 64)])
+def test_conv_stream_k_at_bench_tile_counts(cin, cout, B):
+    """Tile counts just above a multiple of the SM count, as in the bench configuration (153 / 229 / 305 / 375 tiles of
+    128 edges on 148 SMs): every CTA holds cut pieces, most own one.  Forward and the gradients that use its signs against
+    the one-CTA-per-tile kernel."""
+    from meshcnn_b200 import synth
+    from meshcnn_b200 import functional as Fn
+    from meshcnn_b200.mesh_conv import MeshConv
+    from tests.gpu_util import DEV, product_mesh
+    meshes = [product_mesh(*synth.make('ico' if s % 3 else 'torus', s, **(dict(nu=5) if s % 3 else dict(m=10, n=25)))) for s in range(B)]
+    torch.manual_seed(cin + cout + B)
+    conv = MeshConv(cin, cout, bias=True).to(DEV)
+    x = torch.randn(B, cin, 750, device=DEV)
+    dy = torch.randn(B, cout, 750, 1, device=DEV)
+
+    def run():
+        xg = x.clone().requires_grad_(True)
+        y = conv(xg, meshes)
+        y.backward(dy)
+        torch.cuda.synchronize()
+        return y.detach().clone(), xg.grad.clone()
+    try:
+        Fn.USE_SK = False
+        y1, g1 = run()
+        Fn.USE_SK = True
+        y2, g2 = run()
+    finally:
+        Fn.USE_SK = True
+    assert close(y2.cpu().numpy(), y1.cpu().numpy(), 2e-5)
+    assert close(g2.cpu().numpy(), g1.cpu().numpy(), 1e-5)
