@@ -536,7 +536,7 @@ def main():
             roofline = dict(common, bound='hbm', achieved=ach, peak=peak, unit='GB/s', frac=ach / peak, peak_source=peak_src)
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:                  # rank 0 at N = 1 only (bounded sample, ~2 s)
         sample_B = min(B, 16 if E <= 750 else 6)
         v, threads, sec = cpu_port_meshes_per_s(cfg, sample_B, 2, 1)
         cpu = {'value': v, 'unit': 'meshes/s', 'cores': threads, 'kind': 'port',
