@@ -26,6 +26,7 @@ class _TracedRun(O._PoolRun):
 
     def begin(self, e):
         self.R, self.W = {('mask', e)}, set()
+        self.rewired = False                                     # __get_invalids found a valence-3 vertex and rewired (mesh_pool.py:115-138)
 
     def has_boundaries(self, e):
         g = self.m.gemm_edges
@@ -43,6 +44,12 @@ class _TracedRun(O._PoolRun):
     def redirect(self, a, sa, b, sb):
         self.W.update({('g', int(a)), ('g', int(b))})
         super().redirect(a, sa, b, sb)
+
+    def get_invalids(self, e, side):
+        inv = super().get_invalids(e, side)
+        if inv:
+            self.rewired = True
+        return inv
 
     def union(self, s, t):
         self.R.add(('grp', int(s)))
@@ -136,7 +143,7 @@ def _traced_pool(mesh, norms, target, radius=4):
             far = max([ball.get(v, radius + 1) for v in live] + [0])  # radius + 1: further away than the ball
         log['pops'].append(e)
         log['outcomes'].append(out)
-        acc.append((out, frozenset(run.R), frozenset(run.W), ball, far))
+        acc.append((out, frozenset(run.R), frozenset(run.W), ball, far, run.rewired))
     mesh.clean(run.mask, groups)
     return log, acc
 
@@ -144,7 +151,7 @@ def _traced_pool(mesh, norms, target, radius=4):
 def _levels(acc):
     """Earliest level of every pop under read/write dependencies (row granularity)."""
     lw, lr, lev = {}, {}, []
-    for out, R, W, _, _ in acc:
+    for out, R, W, _, _, _ in acc:
         l = 0
         for k in R | W:
             l = max(l, lw.get(k, -1) + 1)
@@ -162,7 +169,7 @@ def _levels_by_ball(acc, r):
     """Earliest level of every pop when two pops are ordered whenever their radius-r vertex balls intersect -- a rule a kernel
     can evaluate BEFORE running a candidate (stamp the ball, look for foreign stamps)."""
     last, lev = {}, []
-    for out, _, _, ball, _ in acc:
+    for out, _, _, ball, _, _ in acc:
         if out == O.SKIP_MASKED:
             lev.append(0)
             continue
@@ -177,7 +184,7 @@ def _levels_by_ball(acc, r):
 def _rule_misses(acc, r):
     """Pairs of pops with a true row conflict whose radius-r balls do NOT intersect (the rule would run them concurrently)."""
     touch = {}
-    for j, (out, R, W, ball, _) in enumerate(acc):
+    for j, (out, R, W, ball, _, _) in enumerate(acc):
         if out == O.SKIP_MASKED:
             continue
         for k in R | W:
@@ -220,7 +227,7 @@ def _study(seeds, chain):
             for r in (2, 3):
                 lb = _levels_by_ball(acc, r)
                 ball[r] = (int(lb.max()) + 1, int(sum(-(-int(work[lb == l].sum()) // 4) for l in range(int(lb.max()) + 1))), _rule_misses(acc, r))
-            rows.append((s, ec, T, len(acc), n, depth, sched, far, ball))
+            rows.append((s, ec, T, len(acc), n, depth, sched, far, ball, sum(1 for a in acc if a[5])))
     return rows
 
 
@@ -233,6 +240,8 @@ def test_collapse_sequence_has_exploitable_parallelism():
         sp = {P: np.mean([r[4] / max(1, r[6][P]) for r in sel]) for P in (2, 4, 8)}
         print('  -> %3d edges: %5.1f examined candidates per mesh, longest dependency chain %5.1f (%.1fx), '
               'level schedule with 2 / 4 / 8 workers: %.2fx / %.2fx / %.2fx' % (T, n, d, n / d, sp[2], sp[4], sp[8]))
+    print('  candidates whose __get_invalids rewires (they cannot be inspected read-only and would run alone): %d of %d'
+          % (sum(r[9] for r in rows), sum(r[4] for r in rows)))
     far = max(r[7] for r in rows)
     print('  every LIVE vertex whose rows a pop touches lies within %d hops of the candidate edge' % far)
     for rr in (2, 3):
