@@ -200,6 +200,17 @@ def algorithmic_bytes(name, m):
         return m['B'] * m['E'] * (4 * m['Cout'] + 4 * m['Cin'] + 16) + 20 * m['Cin'] * m['Cout']
     if name == 'pool_collapse':
         return 28 * m['B'] * (m['E_in'] + m['T'])
+    if name == 'pool_norms':
+        return 4 * m['B'] * m['E'] * (m['C'] + 1)
+    if name in ('segmean_fwd', 'segmean_bwd'):                 # rows in + rows out + CSR (~1.07 nnz per input edge)
+        return 4 * m['B'] * m['C'] * (m['E_in'] + m['T']) + 4 * m['B'] * (2 * m['E_in'] + m['T'])
+    if name in ('unpool_fwd', 'unpool_bwd'):
+        return 4 * m['B'] * m['C'] * (m['E_lo'] + m['E_hi']) + 4 * m['B'] * (3 * m['E_hi'])
+    if name in ('norm_fwd', 'norm_bwd'):                       # x (+ y/dy) in, y/dx out
+        n = m['nblocks'] * m['rows'] * m['C'] * 4
+        return 2 * n if name == 'norm_fwd' else 4 * n
+    if name == 'adam_flat':
+        return 28 * m['n']
     return 0
 
 
@@ -212,21 +223,39 @@ def peaks():
 
 
 # -----------------------------------------------------------------------------------------------------------------
+def reference_cpu(cfg, B, steps, warmup, budget_s=None):
+    """The reference's own CPU implementation of the path, timed on this box's host cores: the UNMODIFIED reference
+    (oracle/reference_arm.py: networks.define_classifier + Adam, fresh Mesh objects per step) on all B meshes of the workload
+    -> kind "reference".  Only the 170 k-edge config, which the reference cannot run (dense n x n MeshUnion = 115 GB, SURVEY
+    F15), falls back to the sparse oracle port -> kind "port"."""
+    threads = os.cpu_count() or 1
+    if cfg.get('dense', True):
+        from oracle import reference_arm
+        r = reference_arm.run(cfg, B, steps, warmup, budget_s=budget_s, threads=threads)
+        split = {'fwd_s': r['fwd_s'], 'bwd_s': r['bwd_s'], 'opt_s': r['opt_s'], 'meshpool_s': r['pool_s'],
+                 'meshpool_ms_per_mesh_per_level': 1e3 * r['pool_s'] / (B * len(cfg['pool_res'])),
+                 'meshpool_share_of_step': r['pool_s'] / r['s_per_step']}
+        sample = ('%d timed steps (+%d warm-up) of ALL %d meshes of the batch; unmodified reference (models/networks.py define_classifier, '
+                  'torch.optim.Adam, fresh Mesh objects per step built outside the timed region), %d torch threads; the collapse '
+                  'loop is single-threaded Python as in the reference; %.2f s/step' % (r['steps'], warmup, B, threads, r['s_per_step']))
+        return r['meshes_per_s'], threads, r['s_per_step'], 'reference', sample, split, r['steps']
+    v, threads, sec = cpu_port_meshes_per_s(cfg, B, steps, warmup, budget_s=budget_s)
+    sample = ('timed steps of %d meshes; sparse oracle port (the reference cannot allocate its dense MeshUnion at this size); '
+              '%.2f s/step' % (B, sec))
+    return v, threads, sec, 'port', sample, None, steps
+
+
 def run_reference(args, cfg, rank, world):
-    """--impl reference: the reference's CPU algorithm (oracle port; the reference itself is Python and is not on
-    the GPU box) on a bounded sample of the same workload.  Rank 0 only."""
+    """--impl reference: rank 0 only; same workload, metric and unit as our arm, every step over the whole batch."""
     if rank != 0:
         return None
-    sample_B = min(cfg['B'], 16 if cfg['E'] <= 750 else 6)
-    v, threads, sec = cpu_port_meshes_per_s(cfg, sample_B, max(1, args.steps), max(0, args.warmup))
+    v, threads, sec, kind, sample, split, n = reference_cpu(cfg, cfg['B'], max(1, args.steps), max(0, args.warmup))
     line = {'impl': 'reference', 'metric': 'train meshes/sec (fwd+bwd+pool)', 'value': v, 'unit': 'meshes/s', 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': workload_name(args.config, cfg), 'sample': '%d meshes per step' % sample_B},
-            'cpu_baseline': {'value': v, 'unit': 'meshes/s', 'cores': threads, 'kind': 'port',
-                             'sample': '%d steps of %d meshes (of %d per batch); oracle port with the reference\'s dense MeshUnion '
-                                       'and op sequence, %d torch threads; the collapse loop is single-threaded Python as in the '
-                                       'reference' % (args.steps, sample_B, cfg['B'], threads)},
+            'config': {'workload': workload_name(args.config, cfg), 'global_batch': cfg['B'],
+                       'sample': 'all %d meshes of the batch every step' % cfg['B']},
+            'cpu_baseline': {'value': v, 'unit': 'meshes/s', 'cores': threads, 'kind': kind, 'sample': sample, 'split': split},
             'e2e': {'value': v, 'unit': 'meshes/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
     return line
@@ -249,14 +278,26 @@ def _claim_stdout():
     return os.fdopen(keep, 'w')
 
 
-def _finish(out, line):
-    """Print the result and leave without running destructors: tearing an NCCL communicator down while CUDA graphs that
-    captured its collectives are still alive can block forever."""
+def _finish(out, line, cleanup=None):
+    """Print the result, release the CUDA graphs and the NCCL communicator in that order, and leave through the normal
+    interpreter exit (atexit hooks run, so the driver can record which .so files this process mapped).  Graphs that captured
+    a collective must be destroyed BEFORE their communicator; a watchdog ends the process if teardown still blocks."""
     if line is not None:
         out.write(json.dumps(line) + '\n')
         out.flush()
     sys.stderr.flush()
-    os._exit(0)
+    import threading
+
+    def _bail():
+        sys.stderr.write('bench.py: teardown did not finish within 90 s; forcing exit\n')
+        sys.stderr.flush()
+        os._exit(0)
+    wd = threading.Timer(90.0, _bail)
+    wd.daemon = True
+    wd.start()
+    if cleanup is not None:
+        cleanup()
+    sys.exit(0)
 
 
 def main():
@@ -409,6 +450,7 @@ def main():
 
     # ---- end-to-end arm: host buffers in, loss out, every step ------------------------------------------------------
     e2e = None
+    ge_holder = [None]
     if not args.no_e2e:
         k_e2e = args.steps
         n_fresh = min(k_e2e + 2, 12)
@@ -437,6 +479,7 @@ def main():
         else:
             from meshcnn_b200.graphed import PipelinedTrainStep
             ge = PipelinedTrainStep(net, crit, reducer, opt, fresh[0], x, labels, E)
+            ge_holder[0] = ge
             x_np, y_np = torch.from_numpy(x), torch.from_numpy(labels)
             pending = [None]
 
@@ -478,10 +521,22 @@ def main():
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    if rank != 0:
-        _finish(out, None)
 
-    # ---- roofline of the dominant kernel (live CUDA-event timings collected inside the timed steps) ----------------
+    def cleanup():
+        """CUDA graphs first (they hold the captured NCCL kernels), then the communicator."""
+        import gc
+        for g in [gs] + (list(ge_holder[0].slots) if ge_holder[0] is not None else []):
+            if g is not None:
+                g.graph = None
+        gc.collect()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.destroy_process_group()
+
+    if rank != 0:
+        _finish(out, None, cleanup)
+
+    # ---- roofline: the dominant kernel by time, whichever it is, + one entry per kernel family ------------------------
     agg = {}
     for name, meta, ms in recs:
         key = (name, tuple(sorted(meta.items())))
@@ -490,66 +545,67 @@ def main():
     by_kernel = {}
     for (name, meta), (tot, cnt) in agg.items():
         by_kernel[name] = by_kernel.get(name, 0.0) + tot
-    peak, peak_src = peaks()
-    roofline, pool_info = None, None
-    if agg:
-        dominant = max(by_kernel, key=by_kernel.get)
-        # The collapse kernel is a sequential algorithm (one edge after another, per mesh): it has no bandwidth or tensor
-        # roofline ("report us/collapse and x vs CPU").  It gets its own object; `roofline` describes the
-        # dominant THROUGHPUT kernel.
-        pools = [(k, v) for k, v in agg.items() if k[0] == 'pool_collapse']
-        if pools:
-            (name, meta), (tot, cnt) = max(pools, key=lambda kv: kv[1][0])
-            m = dict(meta)
-            us = 1e3 * tot / cnt
-            ncol = max(1, (m['E_in'] - m['T']) // 3)
-            pool_info = {'kernel': 'pool_collapse', 'bound': 'latency (sequential edge collapse, one CTA per mesh)', 'shape': m,
-                         'avg_launch_us': us, 'collapses_per_mesh': ncol, 'us_per_collapse': us / ncol,
-                         'us_per_mesh_per_level': us / m['B'], 'share_of_step': by_kernel['pool_collapse'] / eager_ms,
-                         'algorithmic_bytes': algorithmic_bytes('pool_collapse', m),
-                         'hbm_GBps': algorithmic_bytes('pool_collapse', m) / (us * 1e-6) / 1e9}
-        cands = {k: v for k, v in by_kernel.items() if k != 'pool_collapse'}
-        top_name = max(cands, key=cands.get) if cands else dominant
-        (name, meta), (tot, cnt) = max(((k, v) for k, v in agg.items() if k[0] == top_name), key=lambda kv: kv[1][0])
+    hbm_peak, hbm_src = peaks()
+    mp = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    tf32_peak = json.load(open(mp))['bf16_tflops_sustained'] / 2.0 if os.path.exists(mp) else 1125.0
+    tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
+    traffic_db = json.load(open(tpath)) if os.path.exists(tpath) else {}
+    timing_note = ('EAGER attribution pass: CUDA events around each C-ABI call in %d steps launched kernel by kernel (%.3f ms/step) '
+                   'right after the timed region -- events cannot bracket nodes of the replayed graph (%.3f ms/step); shares of '
+                   'the graph step are in profiles/ (ncu launch list)' % (k_prof, eager_ms / k_prof, total_ms / args.steps))
+
+    def family_entry(fam):
+        """Roofline of the heaviest launch shape of one kernel family."""
+        (name, meta), (tot, cnt) = max(((k, v) for k, v in agg.items() if k[0] == fam), key=lambda kv: kv[1][0])
         m = dict(meta)
+        avg_ms = tot / cnt
         base = name[:-3] if name.endswith('_tc') else name
         nbytes = algorithmic_bytes(base, m)
-        avg_ms = tot / cnt
-        traffic, traffic_src = None, None                    # DRAM bytes per launch of this kernel from the committed ncu capture
-        tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
-        if os.path.exists(tpath):
-            ent = json.load(open(tpath)).get('%s|%s' % (name, ','.join('%s=%s' % kv for kv in sorted(m.items()))))
-            if ent:
-                traffic, traffic_src = ent['dram_bytes'], 'profiles/r01_v11_ncu_top_kernels.md row %d (ncu --set full, one launch)' % ent['row']
-        common = {'kernel': name, 'shape': m, 'avg_launch_ms': avg_ms, 'algorithmic_bytes': nbytes, 'traffic': traffic,
-                  'traffic_source': traffic_src,
-                  'dominant_by_time': dominant,
-                  'share_of_step': {k: v / eager_ms for k, v in sorted(by_kernel.items())},
-                  'timing': 'CUDA events around each C-ABI call in %d eagerly launched steps (%.3f ms/step) run right after '
-                            'the timed region' % (k_prof, eager_ms / k_prof)}
+        ent = traffic_db.get('%s|%s' % (name, ','.join('%s=%s' % kv for kv in sorted(m.items()))))
+        e = {'kernel': name, 'shape': m, 'avg_launch_ms': avg_ms, 'launches_per_step': sum(c for k, (t, c) in agg.items() if k[0] == fam) / k_prof,
+             'share_of_eager_step': by_kernel[fam] / eager_ms, 'algorithmic_bytes': nbytes,
+             'traffic': ent['dram_bytes'] if ent else None,
+             'traffic_source': ('%s row %d (ncu --set full, one launch)' % (ent.get('file', 'profiles/r01_v11_ncu_top_kernels.md'), ent['row'])) if ent else None}
         if name.endswith('_tc'):
-            # tensor-core MeshConv: algorithmic flops of the contraction (fp32 result); the kernel issues 3 TF32 MMAs per
-            # algorithmic MMA (3xTF32 split), so the tensor pipe is busy for 3x the achieved figure.  Peak = TF32 dense rate,
-            # half the measured bf16 rate.
-            flops = (2.0 if 'fwd' in name else 2.0) * m['B'] * m['E'] * 5 * m['Cin'] * m['Cout']
+            # tensor-core MeshConv: algorithmic flops of the contraction (fp32 result); 3 TF32 MMAs are issued per algorithmic
+            # MMA (3xTF32 split), so the tensor pipe is busy for 3x the achieved figure.  Peak = TF32 dense = bf16 sustained / 2.
+            flops = 2.0 * m['B'] * m['E'] * 5 * m['Cin'] * m['Cout']
             ach = flops / (avg_ms * 1e-3) / 1e12
-            pk = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['bf16_tflops_sustained'] / 2.0 \
-                if os.path.exists(os.path.join(ROOT, 'MEASURED_PEAKS.json')) else 1125.0
-            roofline = dict(common, bound='tensor', achieved=ach, peak=pk, unit='TFLOP/s', frac=ach / pk,
-                            algorithmic_flops=flops, mma_passes=3, tensor_pipe_frac=3.0 * ach / pk,
-                            hbm_GBps=nbytes / (avg_ms * 1e-3) / 1e9,
-                            peak_source='TF32 dense = measured bf16 sustained (MEASURED_PEAKS.json) / 2')
+            e.update(bound='tensor', achieved=ach, peak=tf32_peak, unit='TFLOP/s', frac=ach / tf32_peak, algorithmic_flops=flops,
+                     mma_passes=3, tensor_pipe_frac=3.0 * ach / tf32_peak, hbm_GBps=nbytes / (avg_ms * 1e-3) / 1e9,
+                     peak_source='TF32 dense = measured bf16 sustained (MEASURED_PEAKS.json) / 2')
         else:
             ach = nbytes / (avg_ms * 1e-3) / 1e9
-            roofline = dict(common, bound='hbm', achieved=ach, peak=peak, unit='GB/s', frac=ach / peak, peak_source=peak_src)
+            e.update(bound='hbm', achieved=ach, peak=hbm_peak, unit='GB/s', frac=ach / hbm_peak, peak_source=hbm_src)
+        if name == 'pool_collapse':
+            ncol = max(1, (m['E_in'] - m['T']) // 3)
+            e.update(limiter='latency: a dependent chain of edge collapses per mesh (one CTA per mesh); the HBM fraction is reported '
+                             'for completeness, us/collapse is the figure of merit (SURVEY 8d)',
+                     collapses_per_mesh=ncol, us_per_collapse=1e3 * avg_ms / ncol, us_per_mesh_per_level=1e3 * avg_ms / m['B'])
+        return e
+
+    roofline, pool_info = None, None
+    if agg:
+        fams = sorted(by_kernel, key=by_kernel.get, reverse=True)
+        entries = {f: e for f, e in ((f, family_entry(f)) for f in fams) if e['algorithmic_bytes'] > 0}
+        dominant = fams[0]
+        top = entries.get(dominant) or next(iter(entries.values()))
+        roofline = dict(top, dominant_by_time=dominant, timing=timing_note,
+                        share_of_step={k: v / eager_ms for k, v in sorted(by_kernel.items())},
+                        kernels=[entries[f] for f in fams if f in entries and entries[f] is not top])
+        pool_info = entries.get('pool_collapse')
 
     cpu = None
-    if not args.no_cpu_baseline and world == 1:                  # rank 0 at N = 1 only (bounded sample, ~2 s)
-        sample_B = min(B, 16 if E <= 750 else 6)
-        v, threads, sec = cpu_port_meshes_per_s(cfg, sample_B, 2, 1, budget_s=12.0)
-        cpu = {'value': v, 'unit': 'meshes/s', 'cores': threads, 'kind': 'port',
-               'sample': 'about 12 s of CPU work: timed steps (+1 warm-up) of %d meshes of the same workload; oracle port with the '
-                         'reference\'s dense MeshUnion and op sequence; %.2f s/step' % (sample_B, sec)}
+    if not args.no_cpu_baseline and world == 1:                  # rank 0 at N = 1 only; a bounded sample (~15 s of CPU work)
+        v, threads, sec, kind, sample, split, n = reference_cpu(cfg, B, 2, 1, budget_s=12.0)
+        cpu = {'value': v, 'unit': 'meshes/s', 'cores': threads, 'kind': kind, 'sample': sample, 'split': split}
+        if split is not None and pool_info is not None:
+            # MeshPool alone (SURVEY 8d asks for >= 50x at one GPU): the reference's MeshPool.forward wall time per step
+            # against the sum of our pool kernels (norms + collapse + segment mean) per step
+            ours_ms = sum(by_kernel.get(k, 0.0) for k in ('pool_collapse', 'pool_norms', 'segmean_fwd')) / k_prof
+            cpu['meshpool_speedup'] = {'reference_ms_per_step': 1e3 * split['meshpool_s'], 'ours_ms_per_step': ours_ms,
+                                       'ratio': 1e3 * split['meshpool_s'] / max(ours_ms, 1e-9),
+                                       'note': 'reference: wall time inside MeshPool.forward (host); ours: CUDA-event time of the pool kernels in the eager attribution pass'}
 
     line = {'metric': 'train meshes/sec (fwd+bwd+pool)', 'value': value, 'unit': 'meshes/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': total_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
@@ -559,7 +615,7 @@ def main():
                        'l2': 'flushed between timed steps (256 MiB write, untimed); per-step CUDA events, max over ranks',
                        'optimizer': 'Adam (in the timed region)', 'launch': mode},
             'roofline': roofline, 'pool_collapse': pool_info, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks}
-    _finish(out, line)
+    _finish(out, line, cleanup)
 
 
 if __name__ == '__main__':

@@ -217,7 +217,8 @@ def pool_norms(x):
     """fp32 squared feature norms [B, E] (mesh_pool.py:186); not differentiable by construction."""
     B, E, C = x.shape
     norms = torch.empty(B, E, dtype=torch.float32, device=x.device)
-    _lib.check(_lib.lib().mcnn_pool_norms(x.data_ptr(), norms.data_ptr(), B, E, C, _lib.current_stream()), 'mcnn_pool_norms')
+    with profiler.span('pool_norms', B=B, E=E, C=C):
+        _lib.check(_lib.lib().mcnn_pool_norms(x.data_ptr(), norms.data_ptr(), B, E, C, _lib.current_stream()), 'mcnn_pool_norms')
     return norms
 
 
@@ -230,9 +231,10 @@ class SegMeanFn(torch.autograd.Function):
         x = x.contiguous()
         B, E_in, C = x.shape
         out = torch.empty(B, rec.T, C, dtype=torch.float32, device=x.device)
-        _lib.check(_lib.lib().mcnn_segmean_fwd(x.data_ptr(), rec.rowptr.data_ptr(), rec.cols.data_ptr(), ec_out.data_ptr(),
-                                               out.data_ptr(), B, E_in, rec.T, C, rec.nnz_cap, _lib.current_stream()),
-                   'mcnn_segmean_fwd')
+        with profiler.span('segmean_fwd', B=B, E_in=E_in, T=rec.T, C=C):
+            _lib.check(_lib.lib().mcnn_segmean_fwd(x.data_ptr(), rec.rowptr.data_ptr(), rec.cols.data_ptr(), ec_out.data_ptr(),
+                                                   out.data_ptr(), B, E_in, rec.T, C, rec.nnz_cap, _lib.current_stream()),
+                       'mcnn_segmean_fwd')
         ctx.rec, ctx.ec_in, ctx.shape = rec, ec_in, (B, E_in, C)
         return out
 
@@ -242,9 +244,10 @@ class SegMeanFn(torch.autograd.Function):
         B, E_in, C = ctx.shape
         dout = dout.contiguous()
         dx = torch.empty(B, E_in, C, dtype=torch.float32, device=dout.device)
-        _lib.check(_lib.lib().mcnn_segmean_bwd(dout.data_ptr(), rec.rowptr.data_ptr(), rec.colptr.data_ptr(),
-                                               rec.rows.data_ptr(), ctx.ec_in.data_ptr(), dx.data_ptr(), B, E_in, rec.T, C,
-                                               rec.nnz_cap, _lib.current_stream()), 'mcnn_segmean_bwd')
+        with profiler.span('segmean_bwd', B=B, E_in=E_in, T=rec.T, C=C):
+            _lib.check(_lib.lib().mcnn_segmean_bwd(dout.data_ptr(), rec.rowptr.data_ptr(), rec.colptr.data_ptr(),
+                                                   rec.rows.data_ptr(), ctx.ec_in.data_ptr(), dx.data_ptr(), B, E_in, rec.T, C,
+                                                   rec.nnz_cap, _lib.current_stream()), 'mcnn_segmean_bwd')
         return dx, None, None, None
 
 
@@ -257,9 +260,10 @@ class UnpoolFn(torch.autograd.Function):
         f = f.contiguous()
         B, E_lo, C = f.shape
         out = torch.empty(B, E_hi, C, dtype=torch.float32, device=f.device)
-        _lib.check(_lib.lib().mcnn_unpool_fwd(f.data_ptr(), rec.colptr.data_ptr(), rec.rows.data_ptr(), rec.occ.data_ptr(),
-                                              ec_hi.data_ptr(), out.data_ptr(), B, E_lo, E_hi, rec.E_in, C, rec.nnz_cap,
-                                              _lib.current_stream()), 'mcnn_unpool_fwd')
+        with profiler.span('unpool_fwd', B=B, E_lo=E_lo, E_hi=E_hi, C=C):
+            _lib.check(_lib.lib().mcnn_unpool_fwd(f.data_ptr(), rec.colptr.data_ptr(), rec.rows.data_ptr(), rec.occ.data_ptr(),
+                                                  ec_hi.data_ptr(), out.data_ptr(), B, E_lo, E_hi, rec.E_in, C, rec.nnz_cap,
+                                                  _lib.current_stream()), 'mcnn_unpool_fwd')
         ctx.rec, ctx.ec_lo, ctx.shape, ctx.E_hi = rec, ec_lo, (B, E_lo, C), E_hi
         return out
 
@@ -269,9 +273,10 @@ class UnpoolFn(torch.autograd.Function):
         B, E_lo, C = ctx.shape
         dout = dout.contiguous()
         df = torch.empty(B, E_lo, C, dtype=torch.float32, device=dout.device)
-        _lib.check(_lib.lib().mcnn_unpool_bwd(dout.data_ptr(), rec.rowptr.data_ptr(), rec.cols.data_ptr(), rec.occ.data_ptr(),
-                                              ctx.ec_lo.data_ptr(), df.data_ptr(), B, E_lo, ctx.E_hi, rec.E_in, C,
-                                              rec.nnz_cap, _lib.current_stream()), 'mcnn_unpool_bwd')
+        with profiler.span('unpool_bwd', B=B, E_lo=E_lo, E_hi=ctx.E_hi, C=C):
+            _lib.check(_lib.lib().mcnn_unpool_bwd(dout.data_ptr(), rec.rowptr.data_ptr(), rec.cols.data_ptr(), rec.occ.data_ptr(),
+                                                  ctx.ec_lo.data_ptr(), df.data_ptr(), B, E_lo, ctx.E_hi, rec.E_in, C,
+                                                  rec.nnz_cap, _lib.current_stream()), 'mcnn_unpool_bwd')
         return df, None, None, None, None
 
 
