@@ -9,7 +9,9 @@
  * Conventions
  *   - every pointer is a DEVICE pointer unless its name ends in _host; sizes are element counts
  *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises
- *   - no allocation, no global mutable state; safe to call from any host thread and under CUDA-graph capture
+ *   - no allocation, no global mutable state (the per-device cache of configured kernel attributes aside); safe to call
+ *     from any host thread and under CUDA-graph capture.  The process-global diagnostics switches (mcnn_debug_*) are NOT
+ *     part of this ABI: they are declared in meshcnn_b200_debug.h
  *   - return value: 0 = launched, otherwise a MCNN_E_* code (argument errors are detected on the host;
  *     data-dependent errors of the collapse kernel are written to its per-mesh `status` array)
  *
@@ -98,27 +100,7 @@ size_t mcnn_meshconv_fwd_tc_sk_ws(void);
 int mcnn_meshconv_fwd_tc_sk(const float* x, const int32_t* gemm, const int32_t* ec, const float* weight,
                             const float* bias, float* out, float* wt_ws, int8_t* signs, void* sk_ws, int B, int E, int Cin,
                             int Cout, void* stream);
-/* diagnostics only: 1 = mcnn_meshconv_bwd_data_tc_signs launches one CTA per (edge tile, channel block) instead of the
- * persistent kernel (same arithmetic; the scatter order differs) */
-int mcnn_debug_set_tc_bd_tile(int on);
-/* diagnostics only: output-channel tiles of 128 per CTA in mcnn_meshconv_bwd_weight_tc (1 or 2; 0 = built-in choice: 2 when
- * Cout % 256 == 0).  mcnn_meshconv_bwd_weight_tc_ws() follows the setting. */
-int mcnn_debug_set_tc_bw_ot(int ot);
-/* diagnostics only: force the grid size of mcnn_meshconv_fwd_tc_sk (0 = one CTA per SM) */
-int mcnn_debug_set_tc_sk_ctas(int n);
-/* diagnostics only (library built with -DMCNN_TC_PROF): 64 clock64 stamps of one CTA of the last stream-K launch */
-int mcnn_debug_sk_prof(long long* out64, int cta);
-/* diagnostics only (-DMCNN_TC_PROF): %globaltimer ns at entry / exit of each of the first 256 CTAs of the last stream-K launch */
-int mcnn_debug_sk_cta_times(unsigned long long* out512);
 
-/* diagnostics only: bottleneck-attribution knobs of the tensor-core forward kernel (0 = normal operation) */
-int mcnn_debug_set_tc(int flags);
-/* diagnostics only: force the N tile (64 / 128 / 256) of the tensor-core forward kernel; 0 = built-in choice */
-int mcnn_debug_set_tc_ntile(int ntile);
-/* the CTA-pair (tcgen05 cta_group::2) forward kernel for Cout % 256 == 0: on / off */
-int mcnn_debug_set_tc_pair(int on);
-/* diagnostics only (-DMCNN_TC_PROF builds): copy the 16 cycle counters of CTA 0 of the forward kernel to host memory */
-int mcnn_debug_tc_prof(long long* out16_host, int reset);
 
 /* dx of the above (autograd of mesh_conv.py:47-69: conv2d dgrad, abs/add backward, index_select scatter).
  *   dout [B][E][Cout]   dx [B][E][Cin]  -- must be ZERO on entry (the kernel accumulates with red.global) */
@@ -252,9 +234,6 @@ int mcnn_unpool_bwd(const float* dout, const int32_t* grp_rowptr, const int32_t*
  * s1 / s2: [nblocks][G] scratch.
  * ------------------------------------------------------------------------------------------------------ */
 size_t mcnn_norm_ws(int nblocks, int rows_per_block, int C, int G);
-/* diagnostics only: 0 = always the three-kernel form (statistics, finalize, apply); 1 (default) = per-mesh statistics
- * (GroupNorm, InstanceNorm2d) use the fused one-launch form when the mesh's slab fits in shared memory */
-int mcnn_debug_set_norm_fused(int on);
 int mcnn_norm_fwd(const float* x, const float* a, const float* r, const float* gamma, const float* beta, float* y,
                   float* mean, float* rstd, float* part, float* running_mean, float* running_var, float momentum,
                   float eps, int nblocks, int rows_per_block, int C, int G, int pre_relu, int post_relu, int stats_given,

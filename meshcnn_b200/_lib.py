@@ -43,18 +43,9 @@ SIGNATURES = {
     'mcnn_meshconv_fwd_tc_signs': (_c_int, [_c_vp] * 8 + [_c_int] * 4 + [_c_vp]),
     'mcnn_meshconv_fwd_tc_sk_ws': (_c_sz, []),
     'mcnn_meshconv_fwd_tc_sk': (_c_int, [_c_vp] * 9 + [_c_int] * 4 + [_c_vp]),
-    'mcnn_debug_set_tc_sk_ctas': (_c_int, [_c_int]),
-    'mcnn_debug_set_tc_bd_tile': (_c_int, [_c_int]),
-    'mcnn_debug_set_tc_bw_ot': (_c_int, [_c_int]),
-    'mcnn_debug_sk_prof': (_c_int, [_c_vp, _c_int]),
-    'mcnn_debug_sk_cta_times': (_c_int, [_c_vp]),
     'mcnn_meshconv_bwd_data_tc_signs': (_c_int, [_c_vp] * 8 + [_c_int] * 4 + [_c_vp]),
     'mcnn_meshconv_bwd_data': (_c_int, [_c_vp] * 6 + [_c_int] * 4 + [_c_vp]),
     'mcnn_meshconv_bwd_weight': (_c_int, [_c_vp] * 6 + [_c_int] * 4 + [_c_vp]),
-    'mcnn_debug_set_tc': (_c_int, [_c_int]),
-    'mcnn_debug_set_tc_ntile': (_c_int, [_c_int]),
-    'mcnn_debug_set_tc_pair': (_c_int, [_c_int]),
-    'mcnn_debug_tc_prof': (_c_int, [_c_vp, _c_int]),
     'mcnn_meshconv_bwd_data_tc': (_c_int, [_c_vp] * 7 + [_c_int] * 4 + [_c_vp]),
     'mcnn_meshconv_bwd_weight_tc_ws': (_c_sz, [_c_int] * 4),
     'mcnn_meshconv_bwd_weight_tc': (_c_int, [_c_vp] * 7 + [_c_int] * 4 + [_c_vp]),
@@ -67,12 +58,25 @@ SIGNATURES = {
     'mcnn_segmean_bwd': (_c_int, [_c_vp] * 6 + [_c_int] * 5 + [_c_vp]),
     'mcnn_unpool_fwd': (_c_int, [_c_vp] * 6 + [_c_int] * 6 + [_c_vp]),
     'mcnn_norm_ws': (_c_sz, [_c_int] * 4),
-    'mcnn_debug_set_norm_fused': (_c_int, [_c_int]),
     'mcnn_norm_fwd': (_c_int, [_c_vp] * 11 + [ctypes.c_float, ctypes.c_float] + [_c_int] * 7 + [_c_vp]),
     'mcnn_norm_bwd': (_c_int, [_c_vp] * 14 + [_c_int] * 6 + [_c_vp]),
     'mcnn_adam_flat': (_c_int, [_c_vp] * 4 + [ctypes.c_longlong] + [ctypes.c_float] * 5 + [_c_int, _c_vp]),
     'mcnn_adam_flat_state': (_c_int, [_c_vp] * 4 + [ctypes.c_longlong, _c_vp, _c_vp]),
     'mcnn_unpool_bwd': (_c_int, [_c_vp] * 6 + [_c_int] * 6 + [_c_vp]),
+}
+
+# diagnostics switches / profiling read-outs (include/meshcnn_b200_debug.h): process-global, not part of the production ABI
+DEBUG_SIGNATURES = {
+    'mcnn_debug_set_tc_sk_ctas': (_c_int, [_c_int]),
+    'mcnn_debug_set_tc_bd_tile': (_c_int, [_c_int]),
+    'mcnn_debug_set_tc_bw_ot': (_c_int, [_c_int]),
+    'mcnn_debug_sk_prof': (_c_int, [_c_vp, _c_int]),
+    'mcnn_debug_sk_cta_times': (_c_int, [_c_vp]),
+    'mcnn_debug_set_tc': (_c_int, [_c_int]),
+    'mcnn_debug_set_tc_ntile': (_c_int, [_c_int]),
+    'mcnn_debug_set_tc_pair': (_c_int, [_c_int]),
+    'mcnn_debug_tc_prof': (_c_int, [_c_vp, _c_int]),
+    'mcnn_debug_set_norm_fused': (_c_int, [_c_int]),
 }
 
 # CTA-pair (tcgen05 cta_group::2) forward kernel for Cout % 256 == 0; MESHCNN_B200_TC_PAIR=0/1 overrides
@@ -91,7 +95,7 @@ def lib():
                 'meshcnn_b200: %s is missing. Build it with `python -c "import __graft_entry__ as g; g.build()"` '
                 'or `make -C meshcnn_b200/csrc`. There is no CPU fallback.' % LIB_PATH)
         l = ctypes.CDLL(LIB_PATH)
-        for name, (res, args) in SIGNATURES.items():
+        for name, (res, args) in list(SIGNATURES.items()) + list(DEBUG_SIGNATURES.items()):
             fn = getattr(l, name)
             fn.restype = res
             fn.argtypes = args

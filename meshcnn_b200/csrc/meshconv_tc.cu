@@ -1092,12 +1092,8 @@ meshconv_fwd_tc2_kernel(const float* __restrict__ x, const int32_t* __restrict__
 static int launch_fwd_tc2(const float* x, const int32_t* gemm, const int32_t* ec, const float* wt, const float* bias,
                           float* out, int8_t* signs, int B, int E, int Cin, int Cout, cudaStream_t st) {
     using S = Tc2Smem;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(meshconv_fwd_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
-        if (e != cudaSuccess) { g_last_error = e; return MCNN_E_CUDA; }
-        configured = true;
-    }
+    static DynSmemGuard configured;
+    if (int grc = configured.ensure(meshconv_fwd_tc2_kernel, S::TOTAL)) return grc;
     const int mtiles = ceil_div(B * E, TC_M);
     dim3 grid(2 * ceil_div(mtiles, 2), Cout / 256);          // whole CTA pairs; a surplus CTA works on rows >= M (all zero)
     meshconv_fwd_tc2_kernel<<<grid, TC_THREADS, S::TOTAL, st>>>(x, gemm, ec, wt, bias, out, signs, B, E, Cin, Cout);
@@ -1108,26 +1104,13 @@ template <int N_TILE, int PW>
 static int launch_fwd_tc(const float* x, const int32_t* gemm, const int32_t* ec, const float* wt, const float* bias,
                          float* out, int8_t* signs, int B, int E, int Cin, int Cout, cudaStream_t st) {
     using S = TcSmem<N_TILE>;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(meshconv_fwd_tc_kernel<N_TILE, PW>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
-        if (e != cudaSuccess) { g_last_error = e; return MCNN_E_CUDA; }
-        configured = true;
-    }
+    static DynSmemGuard configured;
+    if (int grc = configured.ensure(meshconv_fwd_tc_kernel<N_TILE, PW>, S::TOTAL)) return grc;
     dim3 grid(ceil_div(B * E, TC_M), ceil_div(Cout, N_TILE));
     meshconv_fwd_tc_kernel<N_TILE, PW><<<grid, (PW + 1) * 32, S::TOTAL, st>>>(x, gemm, ec, wt, bias, out, signs, B, E, Cin, Cout);
     return after_launch();
 }
 
-
-static int sm_count() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-    }
-    return n;
-}
 
 static int g_tc_sk_ctas = 0;               // debug: force the stream-K grid size (0 = heuristic)
 static int g_tc_bd_tile = 0;               // debug: 1 = one CTA per item for the data gradient instead of the persistent kernel
@@ -1136,12 +1119,8 @@ template <int N_TILE>
 static int launch_fwd_tc_sk(const float* x, const int32_t* gemm, const int32_t* ec, const float* wt, const float* bias,
                             float* out, int8_t* signs, void* sk_ws, int B, int E, int Cin, int Cout, cudaStream_t st) {
     using S = SkSmem<N_TILE>;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(meshconv_fwd_tc_sk_kernel<N_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
-        if (e != cudaSuccess) { g_last_error = e; return MCNN_E_CUDA; }
-        configured = true;
-    }
+    static DynSmemGuard configured;
+    if (int grc = configured.ensure(meshconv_fwd_tc_sk_kernel<N_TILE>, S::TOTAL)) return grc;
     const long long total = (long long)ceil_div(B * E, TC_M) * (Cout / N_TILE) * (5 * Cin / 32);
     long long G = min((long long)min(sm_count(), SK_MAX_CTAS), max(1LL, total / 4));     // at least 4 K blocks per CTA
     if (g_tc_sk_ctas > 0) G = min((long long)g_tc_sk_ctas, total);
@@ -2052,19 +2031,11 @@ extern "C" int mcnn_meshconv_bwd_data_tc_signs(const float* dout, const float* x
         weight_tc_bwd_layout_kernel<<<ceil_div(total, 256), 256, 0, st>>>(weight, wtb_ws, Cin, Cout);
         if ((rc = after_launch())) return rc;
     }
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(meshconv_bwd_data_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BdSmem::TOTAL);
-        if (e != cudaSuccess) { g_last_error = e; return MCNN_E_CUDA; }
-        configured = true;
-    }
+    static DynSmemGuard configured;
+    if (int grc = configured.ensure(meshconv_bwd_data_tc_kernel, BdSmem::TOTAL)) return grc;
     if (signs != nullptr && !g_tc_bd_tile) {                 // persistent kernel (needs the signs kept by the forward)
-        static bool configured_p = false;
-        if (!configured_p) {
-            cudaError_t e = cudaFuncSetAttribute(meshconv_bwd_data_tc_p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BdpSmem::TOTAL);
-            if (e != cudaSuccess) { g_last_error = e; return MCNN_E_CUDA; }
-            configured_p = true;
-        }
+        static DynSmemGuard configured_p;
+        if (int grc = configured_p.ensure(meshconv_bwd_data_tc_p_kernel, BdpSmem::TOTAL)) return grc;
         const long long items = (long long)ceil_div(B * E, TC_M) * (Cin / 32);
         const int G = (int)min((long long)sm_count(), items);
         meshconv_bwd_data_tc_p_kernel<<<G, BDP_THREADS, BdpSmem::TOTAL, st>>>(dout, gemm, ec, wtb_ws, dx, signs, B, E, Cin, Cout);
@@ -2092,21 +2063,13 @@ extern "C" int mcnn_meshconv_bwd_weight_tc(const float* dout, const float* x, co
     int rows;
     const int S = bw_splits(M, Cin, Cout, &rows);
     if (bw_ot(Cout) == 2) {
-        static bool configured2 = false;
-        if (!configured2) {
-            cudaError_t e = cudaFuncSetAttribute(meshconv_bwd_weight_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwSmem<2>::TOTAL);
-            if (e != cudaSuccess) { g_last_error = e; return MCNN_E_CUDA; }
-            configured2 = true;
-        }
+        static DynSmemGuard configured2;
+        if (int grc = configured2.ensure(meshconv_bwd_weight_tc_kernel<2>, BwSmem<2>::TOTAL)) return grc;
         dim3 grid(S, ceil_div(Cout, 256), Cin / 32);
         meshconv_bwd_weight_tc_kernel<2><<<grid, TC_THREADS, BwSmem<2>::TOTAL, st>>>(dout, x, gemm, ec, ws, B, E, Cin, Cout, rows);
     } else {
-        static bool configured = false;
-        if (!configured) {
-            cudaError_t e = cudaFuncSetAttribute(meshconv_bwd_weight_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwSmem<1>::TOTAL);
-            if (e != cudaSuccess) { g_last_error = e; return MCNN_E_CUDA; }
-            configured = true;
-        }
+        static DynSmemGuard configured;
+        if (int grc = configured.ensure(meshconv_bwd_weight_tc_kernel<1>, BwSmem<1>::TOTAL)) return grc;
         dim3 grid(S, ceil_div(Cout, 128), Cin / 32);
         meshconv_bwd_weight_tc_kernel<1><<<grid, TC_THREADS, BwSmem<1>::TOTAL, st>>>(dout, x, gemm, ec, ws, B, E, Cin, Cout, rows);
     }

@@ -1209,12 +1209,8 @@ extern "C" int mcnn_pool_collapse(const mcnn_pool_args* a, void* stream) {
     const size_t smem = pool_layout<Narrow>(a->E_in, a->V, a->ve_cap, a->vs != nullptr).total;
     const bool narrow_ok = a->E_in <= 10900 && a->V <= 32767 && a->ve_cap <= 65535 && smem <= mcnn_pool_smem_limit();   // 16-bit ids on chip
     if (narrow_ok && !(a->workspace != nullptr && a->force_workspace)) {
-        static size_t configured = 0;
-        if (smem > configured) {
-            cudaError_t e = cudaFuncSetAttribute(pool_collapse_kernel<Narrow>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) { g_last_error = e; return MCNN_E_CUDA; }
-            configured = smem;
-        }
+        static DynSmemGuard configured;
+        if (int grc = configured.ensure(pool_collapse_kernel<Narrow>, smem)) return grc;
         pool_collapse_kernel<Narrow><<<a->B, Narrow::THREADS, smem, (cudaStream_t)stream>>>(*a);
         return after_launch();
     }

@@ -654,12 +654,8 @@ extern "C" int mcnn_norm_fwd(const float* x, const float* a, const float* r, con
     size_t fsm = 0;
     const int cw = (!stats_given && running_mean == nullptr) ? fused_cw(nblocks, rows_per_block, C, G, &fsm) : 0;
     if (cw) {
-        static size_t configured = 0;
-        if (fsm > configured) {
-            cudaError_t e = cudaFuncSetAttribute(norm_fused_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            if (e != cudaSuccess) { g_last_error = e; return MCNN_E_CUDA; }
-            configured = 200 * 1024;
-        }
+        static DynSmemGuard configured;
+        if (int grc = configured.ensure(norm_fused_fwd_kernel, 200 * 1024)) return grc;
         FusedShape f; f.nblocks = nblocks; f.rows = rows_per_block; f.C = C; f.G = G; f.CW = cw;
         norm_fused_fwd_kernel<<<dim3(nblocks, C / cw), NT, fsm, st>>>(x, a, r, gamma, beta, y, mean, rstd, eps, pre_relu, post_relu, f);
         return after_launch();
@@ -687,12 +683,8 @@ extern "C" int mcnn_norm_bwd(const float* dy, const float* y, const float* x, co
     size_t fsm = 0;
     const int cw = fused_cw(nblocks, rows_per_block, C, G, &fsm);
     if (cw) {
-        static size_t configured = 0;
-        if (fsm > configured) {
-            cudaError_t e = cudaFuncSetAttribute(norm_fused_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            if (e != cudaSuccess) { g_last_error = e; return MCNN_E_CUDA; }
-            configured = 200 * 1024;
-        }
+        static DynSmemGuard configured;
+        if (int grc = configured.ensure(norm_fused_bwd_kernel, 200 * 1024)) return grc;
         FusedShape f; f.nblocks = nblocks; f.rows = rows_per_block; f.C = C; f.G = G; f.CW = cw;
         norm_fused_bwd_kernel<<<dim3(nblocks, C / cw), NT, fsm, st>>>(dy, y, x, a, gamma, mean, rstd, dx, dr, part, pre_relu, post_relu, f);
         if ((rc = after_launch())) return rc;

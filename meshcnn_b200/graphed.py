@@ -63,26 +63,33 @@ class GraphedTrainStep:
     def _enqueue(self):
         bt = self.batch
         Fn.begin_step(self.net)                     # weight images of every MeshConv on the side stream, under the H2D copies
-        if self.source == 'host':
-            bt.blob.copy_(self.blob_host[:bt.nbytes], non_blocking=True)
-            with torch.no_grad():
-                self.x_dev.copy_(self.x_host, non_blocking=True)
-                self.y_dev.copy_(self.y_host, non_blocking=True)
-            bt.rewind()
-        else:
-            bt.reset()
-        self.reducer.zero()
-        self.x_dev.grad = None
-        out = self.net(self.x_dev, bt.meshes)
-        loss = self.criterion(out, self.y_dev)
-        loss.backward()
-        Fn.end_step()
+        try:
+            if self.source == 'host':
+                bt.blob.copy_(self.blob_host[:bt.nbytes], non_blocking=True)
+                with torch.no_grad():
+                    self.x_dev.copy_(self.x_host, non_blocking=True)
+                    self.y_dev.copy_(self.y_host, non_blocking=True)
+                bt.rewind()
+            else:
+                bt.reset()
+            self.reducer.zero()
+            self.x_dev.grad = None
+            out = self.net(self.x_dev, bt.meshes)
+            loss = self.criterion(out, self.y_dev)
+            loss.backward()
+        finally:
+            Fn.end_step()                           # also on an exception: a dangling step token would make later backward
+                                                    # passes write straight into p.grad
         self.reducer.allreduce()
         self.opt.step_state()
         self.loss_host.copy_(loss.detach(), non_blocking=True)
         return loss
 
     def _capture(self, warmup):
+        """Warm-up (allocator, lazy kernel configuration, NCCL) on a side stream, then capture.  The warm-up steps are real
+        steps on the first batch; their effect on the training state -- parameters, Adam moments and step counter,
+        BatchNorm running statistics -- is undone afterwards, so building a GraphedTrainStep does not train."""
+        saved = self._training_state()
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream()
         side.wait_stream(cur)
@@ -96,9 +103,38 @@ class GraphedTrainStep:
         with torch.cuda.graph(self.graph):
             self.loss = self._enqueue()
         self.warmup_steps = max(1, warmup)
+        self._restore_training_state(saved)
+        torch.cuda.synchronize()
+
+    def _training_state(self):
+        opt = self.opt
+        st = {'buffers': [b.detach().clone() for b in self.net.buffers()], 'step_count': getattr(opt, 'step_count', None)}
+        for k in ('flat_p', 'exp_avg', 'exp_avg_sq', 'state'):
+            t = getattr(opt, k, None)
+            st[k] = None if t is None else t.detach().clone()
+        if st['flat_p'] is None:                     # not a FlatAdam: keep the parameters themselves
+            st['params'] = [p.detach().clone() for p in self.net.parameters()]
+        return st
+
+    def _restore_training_state(self, st):
+        with torch.no_grad():
+            for b, v in zip(self.net.buffers(), st['buffers']):
+                b.copy_(v)
+            for k in ('flat_p', 'exp_avg', 'exp_avg_sq', 'state'):
+                if st[k] is not None:
+                    getattr(self.opt, k).copy_(st[k])
+            if st.get('params') is not None:
+                for p, v in zip(self.net.parameters(), st['params']):
+                    p.copy_(v)
+        if st['step_count'] is not None:
+            self.opt.step_count = st['step_count']
 
     def stage(self, meshes, x, y):
-        """Host side of a step: pack the next batch into the pinned staging buffers (no device work)."""
+        """Host side of a step: pack the next batch into the pinned staging buffers (no device work).  Waits for the previous
+        replay of THIS graph first: its host->device copy nodes read these buffers (PipelinedTrainStep alternates two graphs
+        so that this wait is normally over before it starts), and looks at the collapse status that replay left behind."""
+        self.done.synchronize()
+        self.batch.check_captured_status()
         self.batch.pack(meshes)
         self.x_host.copy_(torch.as_tensor(x) if not torch.is_tensor(x) else x)
         self.y_host.copy_(torch.as_tensor(y) if not torch.is_tensor(y) else y)
@@ -114,6 +150,7 @@ class GraphedTrainStep:
     def result(self):
         """Loss of the most recent run() as a Python float; waits for THAT replay only (later work keeps running)."""
         self.done.synchronize()
+        self.batch.check_captured_status()
         return float(self.loss_host)
 
     def __call__(self, meshes, x, y):
@@ -143,7 +180,6 @@ class PipelinedTrainStep:
     def submit(self, meshes, x, y):
         slot = self.slots[self.k & 1]
         self.k += 1
-        slot.done.synchronize()                     # the replay that last read this slot's staging buffers has finished
-        slot.stage(meshes, x, y)
+        slot.stage(meshes, x, y)                    # waits for the replay that last read this slot's staging buffers
         slot.run()
         return slot

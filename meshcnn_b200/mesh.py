@@ -63,6 +63,43 @@ def _staging_buffer(nbytes, device):
     return slot[0], slot
 
 
+# Collapse-kernel failures (the exceptions the reference raises inside MeshPool) must reach a plain training loop that never
+# reads a mirrored Mesh attribute, without a device synchronisation per step: every pool() call copies its per-mesh status
+# words into pinned host memory asynchronously; the words are looked at as soon as the copy has completed -- at the next
+# MeshBatch construction / load / pool call, i.e. at the latest in the following step -- and raise there.
+_STATUS_LEVELS = 16
+_STATUS_FREE = {}        # B -> recycled pinned [_STATUS_LEVELS, B] int32 buffers
+_STATUS_PENDING = []     # [event, pinned buffer, number of levels written, filenames]
+
+
+def _raise_status(words, names):
+    for lvl in range(words.shape[0]):
+        bad = np.nonzero(words[lvl])[0]
+        if len(bad):
+            b = int(bad[0])
+            exc, msg = _STATUS_EXC.get(int(words[lvl, b]), (PoolError, 'status %d' % int(words[lvl, b])))
+            raise exc('MeshPool (pool call %d of the forward), mesh %d of the batch (%s): %s' % (lvl, b, names[b], msg))
+
+
+def poll_pool_status(block=False):
+    """Look at the status words of finished pool calls (all of them with block=True); raises what the reference would have
+    raised inside MeshPool.forward for the first failed mesh."""
+    i = 0
+    while i < len(_STATUS_PENDING):
+        ent = _STATUS_PENDING[i]
+        ev, buf, n, names = ent
+        if block:
+            ev.synchronize()
+        if not ev.query():
+            i += 1
+            continue
+        _STATUS_PENDING.pop(i)
+        words = buf[:n].numpy().copy()
+        ent[2] = 0
+        _STATUS_FREE.setdefault(buf.shape[1], []).append(buf)
+        _raise_status(words, names)
+
+
 class Level:
     """One resolution of the batch: one-ring tables + live edge counts, all on the device."""
     __slots__ = ('E', 'gemm', 'sides', 'ec', 'padded')
@@ -106,6 +143,8 @@ class MeshBatch:
         (so that the host->device copy can itself be a node of a captured graph)."""
         meshes = list(meshes)
         self.device = torch.device(device)
+        if _STATUS_PENDING:
+            poll_pool_status()                                   # failures of earlier steps surface here, one step late at most
         B = len(meshes)
         hs = [m._host_state() for m in meshes]
         V = max(max(len(h['vs']) for h in hs), int(V_cap))
@@ -150,6 +189,7 @@ class MeshBatch:
         self.keep_clocks = False
         self.force_wide = os.environ.get('MESHCNN_B200_POOL_WIDE', '0') == '1'    # tests: large-mesh variant on small meshes
         self._pool_ws = None
+        self._status_ent = None    # entry of _STATUS_PENDING (eager) or [None, pinned buffer, n, names] (captured step)
 
     def pack(self, meshes, hs=None):
         """Pack the topology of `meshes` into the pinned staging buffer (one blob); returns it.  No device work."""
@@ -219,7 +259,10 @@ class MeshBatch:
 
     def rewind(self):
         """Host-side bookkeeping back to level 0 (no device work)."""
+        if _STATUS_PENDING and not torch.cuda.is_current_stream_capturing():
+            poll_pool_status()
         self.levels = [self.level0]
+        self.level0.padded.clear()                               # tables widened for another batch / another replay are stale
         self.cur = 0
         self.stack, self.records = [], []
         self.version += 1
@@ -307,8 +350,8 @@ class MeshBatch:
         if wide:
             a.workspace, a.workspace_stride, a.force_workspace = self._pool_ws.data_ptr(), ws_stride, 1
         exporting = [i for i, m in enumerate(self.meshes) if m.export_folder]
-        if exporting and not self.keep_logs:
-            rec.edge_mask = torch.zeros(B, E_in, dtype=torch.int32, device=dev)
+        if (exporting or any(m.history_data is not None for m in self.meshes)) and not self.keep_logs:
+            rec.edge_mask = torch.empty(B, E_in, dtype=torch.int32, device=dev)      # the kernel writes every entry
             a.edge_mask_out = rec.edge_mask.data_ptr()
         if self.keep_logs:
             cap = E_in
@@ -329,6 +372,7 @@ class MeshBatch:
             a.dbg_clocks = rec.clocks.data_ptr()
         with profiler.span('pool_collapse', B=B, E_in=E_in, T=T):
             _lib.check(L.mcnn_pool_collapse(a, _lib.current_stream()), 'mcnn_pool_collapse')
+        self._publish_status(status)
         new = Level(T, gemm_out, sides_out, ec_out)
         rec.level_in = self.cur
         self.levels = self.levels[:self.cur + 1] + [new]
@@ -350,6 +394,37 @@ class MeshBatch:
             m.export()
         return rec
 
+    def _publish_status(self, status):
+        """Asynchronous copy of one pool call's status words into pinned memory (see poll_pool_status)."""
+        if self.device.type != 'cuda':
+            return
+        k = len(self.records)
+        if k >= _STATUS_LEVELS:
+            return
+        capturing = torch.cuda.is_current_stream_capturing()
+        ent = self._status_ent
+        if capturing:
+            # the copy becomes a node of the graph: a buffer of its own, never recycled, read by check_captured_status()
+            if ent is None or ent[0] is not None:
+                ent = self._status_ent = [None, torch.zeros(_STATUS_LEVELS, self.B, dtype=torch.int32).pin_memory(), 0, None]
+        elif ent is None or ent[0] is None or not any(ent is e for e in _STATUS_PENDING):
+            free = _STATUS_FREE.get(self.B)
+            buf = free.pop() if free else torch.zeros(_STATUS_LEVELS, self.B, dtype=torch.int32).pin_memory()
+            ent = self._status_ent = [torch.cuda.Event(), buf, 0, None]
+            _STATUS_PENDING.append(ent)
+        ent[1][k].copy_(status, non_blocking=True)
+        ent[2] = max(ent[2], k + 1)
+        ent[3] = [m.filename for m in self.meshes]
+        if not capturing:
+            ent[0].record()
+
+    def check_captured_status(self):
+        """For a step replayed from a CUDA graph: the status words of the LAST COMPLETED replay sit in pinned memory (the
+        copies are graph nodes); the caller guarantees that replay has finished (GraphedTrainStep waits on its event)."""
+        ent = self._status_ent
+        if ent is not None and ent[2]:
+            _raise_status(ent[1][:ent[2]].numpy().copy(), ent[3])
+
     def unroll(self):
         """Mesh.get_groups / get_occurrences / unroll_gemm (mesh.py:176-198): pop one level."""
         if not self.stack:
@@ -361,6 +436,10 @@ class MeshBatch:
 
     def check(self):
         """Synchronise and raise the exception the reference would have raised inside MeshPool (deferred)."""
+        ent = self._status_ent
+        if ent is not None:                                  # this is the full check: nothing left for the deferred one
+            _STATUS_PENDING[:] = [e for e in _STATUS_PENDING if e is not ent]
+            self._status_ent = None
         for rec in self.records:
             st = rec.status.cpu().numpy()
             bad = np.nonzero(st)[0]
@@ -407,7 +486,7 @@ class Mesh:
         if data is None:
             if file is None:
                 raise ValueError('Mesh needs an .obj file or prepared data')
-            data = mesh_prepare.from_obj(file)
+            data = mesh_prepare.fill(file, opt)              # mesh.py:16 fill_mesh: npz cache + augmentation per `opt`
         self._h = {'vs': np.array(data.vs, dtype=np.float64), 'v_mask': np.array(data.v_mask, dtype=bool),
                    'edges': np.array(data.edges, dtype=np.int32), 'gemm_edges': np.array(data.gemm_edges, dtype=np.int64),
                    'sides': np.array(data.sides, dtype=np.int64), 'edges_count': int(data.edges_count)}
@@ -420,6 +499,7 @@ class Mesh:
         self.export_folder = export_folder
         self.history_data = None
         self._batch, self._bi, self._seen = None, -1, -1
+        self._hist_seen = 0
         if hold_history:
             self.init_history()
         self.export()                                    # mesh.py:21 (a no-op without an export folder)
@@ -427,35 +507,56 @@ class Mesh:
     # ---- device link -------------------------------------------------------------------------------------
     def _attach(self, batch, i):
         self._batch, self._bi, self._seen = batch, i, batch.version
+        self._hist_seen = 0
 
     def _sync(self):
         bt = self._batch
         if bt is not None and self._seen != bt.version:
             self._h.update(bt.download(self._bi))
+            self._h.pop('ve_lists', None)
             self._seen = bt.version
 
     def _host_state(self):
         self._sync()
+        lists = self._h.get('ve_lists')
+        if lists is not None:                            # host code may have edited the lists in place
+            self._h['ve_flat'], self._h['ve_off'] = _flatten_ve(lists)
         return self._h
 
     def __getstate__(self):
-        self._sync()
+        self._host_state()
+        self._pull_history()
         d = dict(self.__dict__)
         d['_batch'], d['_bi'], d['_seen'] = None, -1, -1
+        d['_hist_seen'] = 0
         return d
+
+    def _own(self):
+        """Host code is about to mutate this mesh (the methods of mesh.py:26-71): fetch the current device state, mirror the
+        history the device holds, and detach -- from here on the host copy is the truth (a later forward re-uploads it)."""
+        if self._batch is None:
+            return
+        self._host_state()
+        self._pull_history()
+        self._batch = None
 
     # ---- reference API -------------------------------------------------------------------------------------
     @property
     def ve(self):
-        """vertex -> incident edge ids as a list of lists (mesh_prepare.py:142-143); stored flat (CSR) internally so
-        that a batch can be packed for upload without touching Python lists."""
+        """vertex -> incident edge ids as a list of lists (mesh_prepare.py:142-143).  Stored flat (CSR) so that a batch can
+        be packed for upload without touching Python lists; the list form is made on first read and then kept, so in-place
+        edits (``mesh.ve[v].remove(e)``) stick like on the reference's attribute."""
         self._sync()
-        flat, off = self._h['ve_flat'], self._h['ve_off']
-        return [flat[off[v]:off[v + 1]].tolist() for v in range(len(off) - 1)]
+        lists = self._h.get('ve_lists')
+        if lists is None:
+            flat, off = self._h['ve_flat'], self._h['ve_off']
+            lists = self._h['ve_lists'] = [flat[off[v]:off[v + 1]].tolist() for v in range(len(off) - 1)]
+        return lists
 
     @ve.setter
     def ve(self, lists):
         self._sync()
+        self._h['ve_lists'] = [list(l) for l in lists]
         self._h['ve_flat'], self._h['ve_off'] = _flatten_ve(lists)
 
     def extract_features(self):                      # mesh.py:23-24
@@ -464,11 +565,136 @@ class Mesh:
     def get_edge_areas(self):                        # mesh.py:200-201
         return self.edge_areas
 
-    def init_history(self):                          # mesh.py:151-162 (the unpool-relevant part lives on the device)
+    # ---- host-side mutation (mesh.py:26-71).  MeshPool does all of this on the device; these are the reference's methods
+    # for host code that edits a mesh itself.  They work on the host mirror and detach the mesh from its device batch. ----
+    def merge_vertices(self, edge_id):               # mesh.py:26-37
+        self._own()
+        self.remove_edge(edge_id)
+        h = self._h
+        v0, v1 = int(h['edges'][edge_id][0]), int(h['edges'][edge_id][1])
+        h['vs'][v0] += h['vs'][v1]
+        h['vs'][v0] /= 2
+        h['v_mask'][v1] = False
+        hit = h['edges'] == v1                       # ALL rows, dead and stale ones included
+        self.ve[v0].extend(self.ve[v1])
+        h['edges'][hit] = v0
+
+    def remove_vertex(self, v):                      # mesh.py:39-40
+        self._own()
+        self._h['v_mask'][v] = False
+
+    def remove_edge(self, edge_id):                  # mesh.py:42-48 (list.remove: first occurrence, ValueError if absent)
+        self._own()
+        for v in self._h['edges'][edge_id]:
+            self.ve[int(v)].remove(edge_id)
+
+    def clean(self, edges_mask, groups):             # mesh.py:50-71
+        self._own()
+        h = self._h
+        keep = np.asarray(edges_mask).astype(bool)
+        h['gemm_edges'] = h['gemm_edges'][:len(keep)][keep]
+        h['edges'] = h['edges'][:len(keep)][keep]
+        h['sides'] = h['sides'][:len(keep)][keep]
+        renum = np.zeros(len(keep) + 1, dtype=np.int32)          # dead -> 0; the extra last slot serves id -1
+        renum[-1] = -1
+        renum[:-1][keep] = np.arange(int(keep.sum()))
+        h['gemm_edges'][:, :] = renum[h['gemm_edges']]
+        self.ve = [[int(renum[e]) for e in l] for l in self.ve]
+        self.__clean_history(groups, torch.from_numpy(keep.copy()))
+        self.pool_count += 1
+        self.export()
+
+    # ---- history (mesh.py:151-198) ---------------------------------------------------------------------------
+    def init_history(self):                          # mesh.py:151-162
+        n = self._h['edges_count']
         self.history_data = {'groups': [], 'gemm_edges': [self._h['gemm_edges'].copy()], 'occurrences': [],
-                             'edges_count': [self._h['edges_count']],
-                             # survivors of every pool as a mask over the ORIGINAL edge ids (export_segments)
-                             'edges_mask': [np.ones(self._h['edges_count'], dtype=bool)]}
+                             'old2current': np.arange(n, dtype=np.int32), 'current2old': np.arange(n, dtype=np.int32),
+                             # survivors as a mask over the ORIGINAL edge ids; one entry per exported level (export_segments)
+                             'edges_mask': [np.ones(n, dtype=bool)],
+                             'edges_count': [n]}
+        self._hist_seen = 0                          # pool records of the device batch already mirrored into the lists
+        if self.export_folder:
+            from .mesh_union import MeshUnion
+            self.history_data['collapses'] = MeshUnion(n)
+
+    def union_groups(self, source, target):          # mesh.py:164-167
+        if self.export_folder and self.history_data:
+            c2o = self.history_data['current2old']
+            self.history_data['collapses'].union(c2o[source], c2o[target])
+
+    def remove_group(self, index):                   # mesh.py:169-174
+        if self.history_data is not None:
+            hd = self.history_data
+            old = hd['current2old'][index]
+            hd['edges_mask'][-1][old] = 0
+            hd['old2current'][old] = -1
+            if self.export_folder:
+                hd['collapses'].remove_group(old)
+
+    def get_groups(self):                            # mesh.py:176-177
+        self._pull_history()
+        return self.history_data['groups'].pop()
+
+    def get_occurrences(self):                       # mesh.py:179-180
+        self._pull_history()
+        return self.history_data['occurrences'].pop()
+
+    def __clean_history(self, groups, pool_mask):    # mesh.py:182-192
+        if self.history_data is not None:
+            hd = self.history_data
+            n = self._h['edges_count']
+            alive = hd['old2current'] != -1
+            hd['old2current'][alive] = np.arange(n, dtype=np.int32)
+            hd['current2old'][0:n] = np.nonzero(alive)[0]
+            if self.export_folder != '':
+                hd['edges_mask'].append(hd['edges_mask'][-1].copy())
+            hd['occurrences'].append(groups.get_occurrences())
+            hd['groups'].append(groups.get_groups(pool_mask))
+            hd['gemm_edges'].append(self._h['gemm_edges'].copy())
+            hd['edges_count'].append(n)
+
+    def unroll_gemm(self):                           # mesh.py:194-198
+        self._own()
+        hd = self.history_data
+        hd['gemm_edges'].pop()
+        self._h['gemm_edges'] = hd['gemm_edges'][-1]
+        hd['edges_count'].pop()
+        self._h['edges_count'] = hd['edges_count'][-1]
+
+    def _pull_history(self):
+        """Mirror what the device batch recorded for this mesh (one PoolRecord per MeshPool call) into the reference's
+        history lists: dense clamped groups [ec_new, ec_old], un-clamped occurrences, pooled gemm_edges, edge counts, and the
+        old2current / current2old maps.  Lazy: only host code that asks pays for the downloads."""
+        bt = self._batch
+        if bt is None or self.history_data is None:
+            return
+        hd, i = self.history_data, self._bi
+        seen = getattr(self, '_hist_seen', 0)
+        if seen >= len(bt.records):
+            return
+        bt.check()
+        for rec in bt.records[seen:]:
+            n_old = int(bt.levels[rec.level_in].ec[i].item())
+            out = bt.levels[rec.level_out]
+            n_new = int(out.ec[i].item())
+            ptr = rec.rowptr[i, :n_new + 1].cpu().numpy()
+            cols = rec.cols[i, :int(ptr[-1])].cpu().numpy()
+            g = torch.zeros(n_new, n_old)
+            g[np.repeat(np.arange(n_new), np.diff(ptr)), cols] = 1.0
+            hd['groups'].append(g)
+            hd['occurrences'].append(rec.occ[i, :n_old].cpu())
+            hd['gemm_edges'].append(out.gemm[i, :n_new].cpu().numpy().astype(np.int64))
+            hd['edges_count'].append(n_new)
+            if rec.edge_mask is not None and 'old2current' in hd:
+                keep = rec.edge_mask[i, :n_old].cpu().numpy().astype(bool)
+                dead_old = hd['current2old'][:n_old][~keep]
+                hd['old2current'][dead_old] = -1
+                if not self.export_folder:                       # exporting meshes: MeshBatch.pool keeps the per-level masks
+                    hd['edges_mask'][-1][dead_old] = False
+                alive = hd['old2current'] != -1
+                hd['old2current'][alive] = np.arange(n_new, dtype=np.int32)
+                hd['current2old'][0:n_new] = np.nonzero(alive)[0]
+        self._hist_seen = len(bt.records)
 
     # ---- OBJ export (mesh.py:74-124; SURVEY 8f N3).  Host-side: the mirrored arrays are downloaded on demand. ----------
     def export(self, file=None, vcolor=None):

@@ -186,21 +186,188 @@ def extract_features(vs, edges, gemm):
     return np.concatenate([dihedral, ang, rat], 0), lengths
 
 
-def from_arrays(vs, faces, filename='synthetic'):
-    """Full preparation of one mesh from vertex / face arrays (no augmentation)."""
+def dihedral_angles(vs, edges, gemm):
+    """The first feature channel alone (mesh_prepare.py:325-330); slide_vertices ranks vertices by it."""
+    ep = edge_points(edges, gemm)
+
+    def normals(s):
+        n = np.cross(vs[ep[:, s + 2]] - vs[ep[:, s]], vs[ep[:, 1 - s]] - vs[ep[:, s]])
+        return n / _div_eps(np.linalg.norm(n, axis=1), 0.1)[:, None]
+    return np.pi - np.arccos(np.sum(normals(0) * normals(1), axis=1).clip(-1, 1))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# data augmentation (mesh_prepare.py:175-294).  Every random draw is made with the same numpy call, in the same order,
+# on the same generator (the global np.random unless `rng` is given) as the reference makes it, so that for an equal
+# generator state the augmented mesh is bit-identical (tests/test_mesh_prepare.py pins this against reference-made goldens).
+# ---------------------------------------------------------------------------------------------------------------
+def scale_vertices(vs, rng=np.random, mean=1.0, var=0.1):
+    """Anisotropic scaling: one normal draw per coordinate axis (mesh_prepare.py:204-206).  In place."""
+    for axis in range(vs.shape[1]):
+        vs[:, axis] = vs[:, axis] * rng.normal(mean, var)
+
+
+def _edge_table(faces):
+    """Edges in first-seen order over (face, corner): rows [v_lo, v_hi, first face, second face or -1] and the
+    {(v_lo, v_hi): edge id} index (mesh_prepare.py:275-291)."""
+    index, rows = {}, []
+    for fi in range(len(faces)):
+        f = faces[fi]
+        for c in range(3):
+            a, b = int(f[c]), int(f[(c + 1) % 3])
+            key = (a, b) if a < b else (b, a)
+            k = index.get(key)
+            if k is None:
+                index[key] = len(rows)
+                rows.append([key[0], key[1], fi, -1])
+            elif rows[k][2] == -1:
+                rows[k][2] = fi
+            else:
+                rows[k][3] = fi
+    return np.array(rows, dtype=np.int64).reshape(-1, 4), index
+
+
+def flip_edges(vs, faces, prct, rng=np.random):
+    """Random flips of flat interior edges, at most int(prct * #edges) of them (mesh_prepare.py:225-262).  `faces` is
+    edited in place and returned.  The dihedral angles are those of the input mesh (not refreshed between flips) and an edge
+    without a second face reads the LAST face of the array, both as in the reference."""
+    table, index = _edge_table(faces)
+    n_edges = len(table)
+    unit = []
+    for col in (2, 3):
+        f = faces[table[:, col]]
+        n = np.cross(vs[f[:, 2]] - vs[f[:, 1]], vs[f[:, 1]] - vs[f[:, 0]])
+        unit.append(n / _div_eps(np.linalg.norm(n, axis=1), 0)[:, None])
+    dihedral = np.pi - np.arccos(np.sum(unit[0] * unit[1], axis=1).clip(-1, 1))
+    order = rng.permutation(n_edges)
+    target = int(prct * n_edges)
+    done = 0
+    for k in order:
+        if done == target:
+            break
+        if not dihedral[k] > 2.7:
+            continue
+        v0, v1, fa, fb = (int(t) for t in table[k])
+        if fb == -1:
+            continue
+        opp = tuple(sorted(set(faces[fa].tolist()) ^ set(faces[fb].tolist())))
+        if opp in index:
+            continue
+        cand = np.array([[v1, opp[0], opp[1]], [v0, opp[0], opp[1]]])
+        if not (face_areas_of(vs, cand) > 0).all():
+            continue
+        del index[(v0, v1)]
+        table[k, 0], table[k, 1] = opp[0], opp[1]
+        index[opp] = k
+        for fid, tri in ((fa, cand[0]), (fb, cand[1])):           # swap the corner that is not part of the new triangle
+            face = faces[fid]
+            tri_l, face_l = tri.tolist(), face.tolist()
+            fresh = list(set(tri_l) - set(face_l))[0]
+            for c in range(3):
+                if face_l[c] not in tri_l:
+                    face[c] = fresh
+                    break
+        for me, other in ((fa, fb), (fb, fa)):                     # the outer edges that changed face
+            face = faces[me]
+            for c in range(3):
+                a, b = int(face[c]), int(face[(c + 1) % 3])
+                key = (a, b) if a < b else (b, a)
+                if key != opp:
+                    row = table[index[key]]
+                    for col in (2, 3):
+                        if row[col] == other:
+                            row[col] = me
+        done += 1
+    return faces
+
+
+def slide_vertices(vs, edges, gemm, ve, prct, rng=np.random):
+    """Slide up to int(prct * #vertices) vertices whose incident edges are all flat (dihedral > 2.65) 20-50 % of the way
+    along a random incident edge (mesh_prepare.py:186-202).  In place; returns the fraction of vertices moved."""
+    dihedral = dihedral_angles(vs, edges, gemm)
+    order = rng.permutation(len(ve))
+    target = int(prct * len(order))
+    moved = 0
+    for vi in order:
+        if moved >= target:
+            break
+        inc = ve[vi]
+        if min(dihedral[inc]) > 2.65:
+            e = edges[rng.choice(inc)]
+            other = e[1] if vi == e[0] else e[0]
+            vs[vi] = vs[vi] + rng.uniform(0.2, 0.5) * (vs[other] - vs[vi])
+            moved += 1
+    return moved / len(ve)
+
+
+def from_arrays(vs, faces, filename='synthetic', opt=None, rng=np.random):
+    """Full preparation of one mesh from vertex / face arrays (mesh_prepare.from_scratch, :39-63).  `opt` (the reference's
+    option namespace) switches the augmentations on: `num_aug > 1` and `scale_verts` / `flip_edges` / `slide_verts`."""
     vs = np.array(vs, dtype=np.float64)
     faces = np.asarray(faces, dtype=np.int64)
     faces, areas = drop_non_manifold(vs, faces)
+    augment = opt is not None and getattr(opt, 'num_aug', 1) > 1
+    if augment:                                                     # mesh_prepare.py:175-180
+        if getattr(opt, 'scale_verts', False):
+            scale_vertices(vs, rng)
+        if getattr(opt, 'flip_edges', 0):
+            faces = flip_edges(vs, faces, opt.flip_edges, rng)
     d = MeshData()
     d.vs = vs
     d.v_mask = np.ones(len(vs), dtype=bool)
     d.filename = filename
     d.edges, d.gemm_edges, d.sides, d.ve, d.edge_areas = build_topology(vs, faces, areas)
     d.edges_count = int(len(d.edges))
+    if augment and getattr(opt, 'slide_verts', 0):                  # mesh_prepare.py:183-185
+        slide_vertices(vs, d.edges, d.gemm_edges, d.ve, opt.slide_verts, rng)
     d.features, d.edge_lengths = extract_features(vs, d.edges, d.gemm_edges)
     return d
 
 
-def from_obj(path):
+def from_obj(path, opt=None):
     vs, faces = read_obj(path)
-    return from_arrays(vs, faces, filename=ntpath.split(path)[1])
+    return from_arrays(vs, faces, filename=ntpath.split(path)[1], opt=opt)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the .npz cache (mesh_prepare.py:6-37): <dir>/cache/<name>_<k>.npz with k = np.random.randint(0, num_aug), same keys as
+# the reference's files.  `ve` is ragged; the reference leaves the conversion to np.savez_compressed, which modern numpy
+# refuses (SURVEY F1) -- it is stored as the 1-D object array of lists that older numpy produced, so files interchange.
+# ---------------------------------------------------------------------------------------------------------------
+CACHE_KEYS = ('gemm_edges', 'vs', 'edges', 'edges_count', 've', 'v_mask', 'filename', 'sides', 'edge_lengths', 'edge_areas', 'features')
+
+
+def cache_path(file, num_aug, rng=np.random):
+    import os
+    stem = os.path.splitext(file)[0]
+    folder = os.path.join(os.path.dirname(stem), 'cache')
+    name = '%s_%03d.npz' % (os.path.basename(stem), rng.randint(0, num_aug))
+    if not os.path.isdir(folder):
+        os.makedirs(folder, exist_ok=True)
+    return os.path.join(folder, name)
+
+
+def fill(file, opt):
+    """fill_mesh (mesh_prepare.py:6-27): the cached preparation of `file` for a random augmentation slot, built and stored
+    on a miss.  opt=None means "no augmentation, no cache" (a convenience the reference does not have)."""
+    import os
+    if opt is None:
+        return from_obj(file)
+    path = cache_path(file, opt.num_aug)
+    if os.path.exists(path):
+        z = np.load(path, encoding='latin1', allow_pickle=True)
+        d = MeshData()
+        for k in CACHE_KEYS:
+            setattr(d, k, z[k])
+        d.edges_count = int(d.edges_count)
+        d.filename = str(d.filename)
+        d.ve = [list(map(int, l)) for l in d.ve]
+        return d
+    d = from_obj(file, opt)
+    ve = np.empty(len(d.ve), dtype=object)
+    for i, l in enumerate(d.ve):
+        ve[i] = list(l)
+    np.savez_compressed(path, gemm_edges=d.gemm_edges, vs=d.vs, edges=d.edges, edges_count=d.edges_count, ve=ve, v_mask=d.v_mask,
+                        filename=d.filename, sides=d.sides, edge_lengths=d.edge_lengths, edge_areas=d.edge_areas,
+                        features=d.features)
+    return d

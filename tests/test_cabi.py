@@ -11,8 +11,8 @@ from meshcnn_b200 import _lib
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _declared():
-    src = open(os.path.join(ROOT, 'include', 'meshcnn_b200.h')).read()
+def _declared(header='meshcnn_b200.h'):
+    src = open(os.path.join(ROOT, 'include', header)).read()
     src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
     return sorted(set(re.findall(r'\b(mcnn_[a-z0-9_]+)\s*\(', src)))
 
@@ -27,6 +27,18 @@ def test_header_symbols_all_bound_and_exported():
     for n in names:
         assert hasattr(so, n), n
     assert _lib.lib().mcnn_version() >= 100
+
+
+def test_debug_switches_live_in_their_own_header():
+    """The process-global diagnostics knobs are not part of the production ABI: separate header, separate ctypes table."""
+    prod, dbg = _declared(), _declared('meshcnn_b200_debug.h')
+    assert not [n for n in prod if n.startswith('mcnn_debug_')]
+    assert dbg and all(n.startswith('mcnn_debug_') for n in dbg)
+    assert sorted(_lib.DEBUG_SIGNATURES) == dbg
+    if os.path.exists(_lib.LIB_PATH):
+        so = ctypes.CDLL(_lib.LIB_PATH)
+        for n in dbg:
+            assert hasattr(so, n), n
 
 
 def test_pool_args_struct_matches_header_size():

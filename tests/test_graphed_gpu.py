@@ -82,6 +82,42 @@ def test_graph_replay_matches_eager(arch):
             np.testing.assert_array_equal(a.gemm_edges, b.gemm_edges)
 
 
+def test_back_to_back_steps_do_not_race_on_the_staging_buffers():
+    """Steps issued without reading the loss in between: every replay must still see ITS batch (stage() waits for the
+    previous replay's host->device copies before it rewrites the pinned buffers).  Building the step must not train:
+    the warm-up's parameter / Adam / BatchNorm updates are undone."""
+    from meshcnn_b200 import ddp
+    from meshcnn_b200.graphed import GraphedTrainStep
+    from meshcnn_b200.mesh import Mesh
+    from meshcnn_b200.optim import FlatAdam
+    dev = torch.device('cuda:0')
+    net0, batches, E = _setup('mconvnet')
+    crit = torch.nn.CrossEntropyLoss()
+    losses = []
+    for mode in ('back_to_back', 'synchronous'):
+        net = copy.deepcopy(net0).to(dev).train()
+        red = ddp.FlatGradReducer(net)
+        opt = FlatAdam(red, lr=2e-4)
+        before = opt.flat_p.clone()
+        bn_before = [b.clone() for b in net.buffers()]
+        datas, x, y = batches[0]
+        step = GraphedTrainStep(net, crit, red, opt, [Mesh(data=d) for d in datas], x, y, E)
+        torch.testing.assert_close(opt.flat_p, before, rtol=0, atol=0)           # construction did not train
+        assert float(opt.state[5]) == 0.0 and opt.step_count == 0 and float(opt.exp_avg.abs().max()) == 0.0
+        for b, v in zip(net.buffers(), bn_before):
+            torch.testing.assert_close(b, v, rtol=0, atol=0)
+        got = []
+        for rep in range(4):
+            for datas, x, y in batches:
+                got.append(step([Mesh(data=d) for d in datas], x, y).clone())
+                if mode == 'synchronous':
+                    torch.cuda.synchronize()
+        torch.cuda.synchronize()
+        losses.append(torch.stack(got).cpu())
+    torch.testing.assert_close(losses[0], losses[1], rtol=2e-3, atol=1e-5)
+    assert float((losses[0][:3] - losses[0][3:6]).abs().max()) > 0              # the three batches do differ / training moves
+
+
 def test_adam_state_kernel_matches_host_driven_kernel():
     """mcnn_adam_flat_state (hyper-parameters + step counter in device memory) == mcnn_adam_flat, step by step."""
     from meshcnn_b200 import ddp
