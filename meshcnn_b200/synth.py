@@ -120,3 +120,49 @@ def make(kind, seed, **kw):
         vs, faces = open_grid(kw.get('m', 10), kw.get('n', 12))
         return perturb(vs, seed, kw.get('a', 0.01)), faces
     raise ValueError(kind)
+
+
+def write_classification_dataset(root, classes=2, n_train=4, n_test=2, nu=3, seed=0):
+    """A tiny dataset in the layout the reference's ClassificationData expects (data/classification_data.py:47-60):
+    root/<class>/{train,test}/*.obj.  Class k is an icosphere stretched along axis k."""
+    import os
+    s = seed
+    for k in range(classes):
+        for split, n in (('train', n_train), ('test', n_test)):
+            d = os.path.join(root, 'class%d' % k, split)
+            os.makedirs(d, exist_ok=True)
+            for i in range(n):
+                vs, faces = make('ico', s, nu=nu)
+                vs = vs.copy()
+                vs[:, k % 3] *= 1.8
+                write_obj(os.path.join(d, 'm%d_%d.obj' % (k, i)), vs, faces)
+                s += 1
+    return root
+
+
+def write_segmentation_dataset(root, n_train=4, n_test=2, nu=3, nclasses=3, seed=0):
+    """Segmentation layout (data/segmentation_data.py:15-21): root/{train,test}/*.obj, root/seg/<name>.eseg (one label per
+    edge, 1-based), root/sseg/<name>.seseg (soft labels [E, nclasses]), root/classes.txt."""
+    import os
+    from . import mesh_prepare
+    os.makedirs(os.path.join(root, 'seg'), exist_ok=True)
+    os.makedirs(os.path.join(root, 'sseg'), exist_ok=True)
+    s = seed
+    for split, n in (('train', n_train), ('test', n_test)):
+        d = os.path.join(root, split)
+        os.makedirs(d, exist_ok=True)
+        for i in range(n):
+            vs, faces = make('ico', s, nu=nu)
+            name = '%s_%d' % (split, i)
+            write_obj(os.path.join(d, name + '.obj'), vs, faces)
+            m = mesh_prepare.from_obj(os.path.join(d, name + '.obj'))
+            mid = vs[m.edges].mean(1)
+            lab = np.minimum((np.clip((mid[:, 2] + 1.0) / 2.0, 0, 0.999) * nclasses).astype(np.int64), nclasses - 1)
+            np.savetxt(os.path.join(root, 'seg', name + '.eseg'), lab + 1, fmt='%d')
+            soft = np.zeros((len(lab), nclasses))
+            soft[np.arange(len(lab)), lab] = 1
+            np.savetxt(os.path.join(root, 'sseg', name + '.seseg'), soft, fmt='%f')
+            s += 1
+    with open(os.path.join(root, 'classes.txt'), 'w') as f:
+        f.write('\n'.join(str(i + 1) for i in range(nclasses)) + '\n')
+    return root

@@ -1,0 +1,90 @@
+"""Two ranks, two GPUs, NCCL: the all-reduced flat gradient of the sharded batch must equal the gradient one process computes
+over the whole batch.  Uneven shards (3 meshes = 2 + 1) exercise the mesh-count weighting.  Skipped on a box
+with fewer than two GPUs (run with `gpurun --gpus 2`)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _net_and_data():
+    from meshcnn_b200 import mesh_prepare, synth
+    from meshcnn_b200 import networks as N
+    torch.manual_seed(0)
+    E, B = 270, 3
+    net = N.MeshEncoderDecoder([E, 200, 150], [5, 16, 32, 64], [64, 32, 16, 4], blocks=1, transfer_data=True)   # InstanceNorm:
+    N.init_weights(net, 'normal', 0.02)                                        # no statistics across meshes, shards are exact
+    datas = [mesh_prepare.from_arrays(*synth.make('ico', s, nu=3)) for s in range(B)]
+    x = np.stack([d.features for d in datas], 0)
+    x = ((x - x.mean(axis=(0, 2), keepdims=True)) / x.std(axis=(0, 2), keepdims=True)).astype(np.float32)
+    y = np.random.RandomState(0).randint(0, 4, size=(B, E)).astype(np.int64)
+    return net, datas, x, y, E, B
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    from meshcnn_b200 import ddp
+    from meshcnn_b200.mesh import Mesh
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dev = torch.device('cuda', rank)
+    torch.cuda.set_device(dev)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
+    net, datas, x, y, E, B = _net_and_data()
+    net = net.to(dev).train()
+    ddp.broadcast_parameters(net)
+    lo, hi = ddp.shard_range(B, rank, world)
+    red = ddp.FlatGradReducer(net, local_items=hi - lo, global_items=B)
+    crit = torch.nn.CrossEntropyLoss(ignore_index=-1)
+    red.zero()
+    out = net(torch.from_numpy(x[lo:hi]).to(dev), [Mesh(data=d, hold_history=True) for d in datas[lo:hi]])
+    crit(out, torch.from_numpy(y[lo:hi]).to(dev)).backward()
+    assert red.check_views()
+    red.allreduce()
+    torch.cuda.synchronize()
+    q.put((rank, lo, hi, red.flat.cpu().numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs')
+def test_nccl_allreduced_gradient_equals_single_process_gradient():
+    import torch.multiprocessing as mp
+    from meshcnn_b200 import ddp
+    from meshcnn_b200.mesh import Mesh
+    world = 2
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = sorted((q.get(timeout=600) for _ in range(world)), key=lambda r: r[0])
+    for p in ps:
+        p.join(120)
+        assert p.exitcode == 0
+    assert [(r[1], r[2]) for r in res] == [(0, 2), (2, 3)]
+    # single-process truth on GPU 0: the whole batch, CE mean over all (equally many) edges
+    net, datas, x, y, E, B = _net_and_data()
+    dev = torch.device('cuda', 0)
+    net = net.to(dev).train()
+    red = ddp.FlatGradReducer(net)
+    red.zero()
+    out = net(torch.from_numpy(x).to(dev), [Mesh(data=d, hold_history=True) for d in datas])
+    torch.nn.CrossEntropyLoss(ignore_index=-1)(out, torch.from_numpy(y).to(dev)).backward()
+    truth = red.flat.cpu().numpy()
+    scale = float(np.abs(truth).max())
+    np.testing.assert_array_equal(res[0][3], res[1][3])                        # every rank holds the same reduced gradient
+    assert float(np.abs(res[0][3] - truth).max()) <= 1e-4 * scale, float(np.abs(res[0][3] - truth).max()) / scale
