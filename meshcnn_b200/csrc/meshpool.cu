@@ -21,10 +21,14 @@
 //                            un-clamped occurrences of m = number of paths starting at m.  Both are
 //                            evaluated after the collapse by all threads.
 //
-// Phases: load -> stable radix sort of the norm bits (ties stay in id order) -> lane 0 of warp 0 runs the sequential collapse (order and
-// side effects identical to the reference, failed attempts included) and calls in the other 31 lanes for every list
-// walk -> all threads run Mesh.clean (compaction, re-indexing with dead -> 0) and emit the groups as CSR + CSC +
-// un-clamped occurrences.
+// Phases: load -> stable radix sort of the norm bits (ties stay in id order) -> the collapse, in ROUNDS over a window of the next
+// pending candidates (one per warp): every warp inspects its candidate read-only on the committed state and reserves the
+// rows a collapse would write; the longest prefix of the window whose members touch nothing an earlier member writes is
+// committed in parallel -- each of them read exactly what it would have read in the strict one-at-a-time order, so pops,
+// outcomes, topology, lists and the union log are those of the reference, bit for bit.  A candidate that has to rewire
+// around a valence-3 vertex (__get_invalids finds a shared edge; a few per cent) runs alone through the sequential code
+// path, failed attempts and their persistent side effects included -> all threads run Mesh.clean (compaction, re-indexing
+// with dead -> 0) and emit the groups as CSR + CSC + un-clamped occurrences.
 #include "common.cuh"
 
 namespace mcnn {
@@ -56,11 +60,12 @@ template <class P> __device__ __forceinline__ typename P::pair_t pr_pack(int a, 
 template <class P> __device__ __forceinline__ int pr_lo(typename P::pair_t w) { return (int)(typename P::uidx_t)w; }
 template <class P> __device__ __forceinline__ int pr_hi(typename P::pair_t w) { return (int)(typename P::uidx_t)(w >> P::SHIFT); }
 
+constexpr int POOL_RSET_CAP = 256;       // vertex ids one inspection may read through the two vertex lists (2 per entry); more -> runs alone
 constexpr int POOL_BFS_CAP = 96;         // members of one MeshUnion row / column walked per thread (implementation limit)
 
 struct PoolLayout {
-    size_t vs, gemm, evp, sides, mask, order, rep, stamp, slab_start, slab_len, slab_next, chain_tail, vmask, ve, eposa, eposb, ulog, cnt32,
-        keys, scan, total;
+    size_t vs, gemm, evp, sides, mask, order, rep, own_e, own_v, wstamp, rset, slab_start, slab_len, slab_next, chain_tail, vmask, ve, eposa,
+        eposb, ulog, cnt32, keys, scan, total;
     int npow2, ulog_cap;
 };
 
@@ -80,7 +85,10 @@ __host__ __device__ inline PoolLayout pool_layout(int n, int V, int ve_cap, bool
     L.mask = o; o += (size_t)n; o = align_up(o, 16);
     L.order = o; o += sizeof(uidx_t) * (size_t)n; o = align_up(o, 16);
     L.rep = o; o += sizeof(uidx_t) * (size_t)V; o = align_up(o, 16);
-    L.stamp = o; o += sizeof(uint32_t) * (size_t)V; o = align_up(o, 16);
+    L.own_e = o; o += sizeof(uint32_t) * (size_t)n; o = align_up(o, 16);          // write reservations of the current round (edge rows)
+    L.own_v = o; o += sizeof(uint32_t) * (size_t)V; o = align_up(o, 16);          //   ... (vertex rows: list, union-find root, v_mask)
+    L.wstamp = o; o += sizeof(uint16_t) * (size_t)V * (P::THREADS / 32); o = align_up(o, 16);   // one-ring stamps, one array per warp
+    L.rset = o; o += sizeof(uidx_t) * (size_t)POOL_RSET_CAP * (P::THREADS / 32); o = align_up(o, 16);   // vertices an inspection read
     L.slab_start = o; o += sizeof(uidx_t) * (size_t)V; o = align_up(o, 16);
     L.slab_len = o; o += sizeof(uidx_t) * (size_t)V; o = align_up(o, 16);
     L.slab_next = o; o += sizeof(uidx_t) * (size_t)V; o = align_up(o, 16);
@@ -132,26 +140,19 @@ __device__ __forceinline__ int block_scan_excl(int v, int* scratch, int& total) 
 }
 
 
-// The sequential collapse runs on thread 0.  Walks over vertex -> edge lists (the one-ring test, and the rare search for
-// the first occurrence of id 0) are handed to a helper warp (warp 1) through a small shared-memory ring: it walks a list 32
-// entries at a time and the collapse thread waits for the answer.
+// Per-mesh collapse state (shared memory for Narrow, the L2-resident workspace for Wide).
 template <class P>
-struct WarpCtx {
-    typename P::uidx_t *ve, *slab_start, *slab_len, *slab_next, *chain_tail, *rep, *eposa, *eposb;
-    typename P::pair_t* evp;
-    uint32_t* stamp;
-    int bump, bump_end;        // free room behind the lists (entries), used by wop_repack
-};
-
-enum { WOP_EXIT = 0, WOP_ONE_RING = 1, WOP_REMOVE_SCAN = 2 };
-constexpr int WQ_CAP = 32;
-
-struct WorkQueue {
-    int ent[WQ_CAP][4];       // op, a0, a1, a2
-    int head;                 // entries posted   (written by the collapse thread)
-    int done;                 // entries finished (written by the helper warp)
-    int res;                  // result of the most recent operation
-    int res_seq;              // sequence number (1-based) that `res` belongs to
+struct PoolState {
+    typename P::idx_t* gemm;
+    int8_t* sides;
+    uint8_t* mask;
+    typename P::pair_t *evp, *ulog;
+    typename P::uidx_t *rep, *slab_start, *slab_len, *slab_next, *chain_tail, *ve, *eposa, *eposb;
+    uint8_t* vmask;
+    double* vs;               // or nullptr
+    uint32_t *own_e, *own_v;  // write reservations: (round << 5) | (31 - window position)
+    int* bump;                // free room behind the lists (entries), used by warp_repack
+    int bump_end;
 };
 
 template <class U>
@@ -159,7 +160,7 @@ __device__ __forceinline__ int uf_find(U* rep, int v) {
     int p = rep[v];
     while (p != v) {
         const int gp = rep[p];
-        rep[v] = (U)gp;                                 // path halving; concurrent lanes only ever write ancestors
+        rep[v] = (U)gp;                                 // path halving; concurrent readers only ever write ancestors
         v = gp;
         p = rep[v];
     }
@@ -174,17 +175,22 @@ __device__ __forceinline__ void edge_ends(const typename P::pair_t* evp, typenam
     v1 = (rb == b) ? b : uf_find(rep, b);
 }
 
-// A list that has absorbed other lists (`extend`) is a chain of slabs; every later walk pays one dependent round trip per
-// slab.  While the collapse thread waits for a one-ring answer anyway, the helper warp re-packs such a chain into ONE slab in
-// the free room behind the lists: order preserved, tombstones dropped, the positions of the moved entries (epos) updated.
+// A list that has absorbed another one (`extend`) is a chain of slabs; every later walk pays one dependent round trip per
+// slab.  The warp that commits a merge re-packs the chain into ONE slab in the free room behind the lists: order preserved,
+// tombstones dropped, the positions of the moved entries (epos) updated.  The caller owns vertex v (nobody else reads it).
 template <class P>
-__device__ __forceinline__ void wop_repack(WarpCtx<P>& w, int lane, int v) {
+__device__ __forceinline__ void warp_repack(const PoolState<P>& w, int lane, int v) {
     if ((unsigned)w.slab_next[v] == P::NIL) return;
     int need = 0;
     for (unsigned s = (unsigned)v; s != P::NIL; s = (unsigned)w.slab_next[s]) need += (int)w.slab_len[s];
-    if (w.bump + need > w.bump_end) return;                                  // no room left: keep the chain
+    int out = -1;
+    if (lane == 0) {
+        out = atomicAdd(w.bump, need);
+        if (out + need > w.bump_end) { atomicSub(w.bump, need); out = -1; }     // no room left: keep the chain
+    }
+    out = __shfl_sync(0xffffffffu, out, 0);
+    if (out < 0) return;
     const unsigned lt = (1u << lane) - 1u;
-    const int out = w.bump;
     int total = 0;
     for (unsigned s = (unsigned)v; s != P::NIL; s = (unsigned)w.slab_next[s]) {
         const int start = w.slab_start[s], len = w.slab_len[s];
@@ -211,201 +217,102 @@ __device__ __forceinline__ void wop_repack(WarpCtx<P>& w, int lane, int v) {
         w.slab_next[v] = (typename P::uidx_t)P::NIL;
         w.chain_tail[v] = (typename P::uidx_t)v;
     }
-    w.bump = out + total;
     __syncwarp();
 }
 
-// __is_one_ring_valid (mesh_pool.py:95-100); the lists may hold stale / dead edge ids.  stamp[w] = tagA marks w as an
-// endpoint seen from v0; the lane that flips it to tagB counts it once.  The first slab of both lists (the whole list
-// unless a vertex was merged within this level) is fetched and resolved together, so the two dependent load chains overlap.
+// __is_one_ring_valid (mesh_pool.py:95-100), by one warp, read-only on the mesh state: the number of distinct vertices other
+// than v0 / v1 that occur as an endpoint of an entry of BOTH lists (the lists may hold stale / dead edge ids).
+// stamp: this warp's own array (tag = endpoint seen from v0; tag | 1 = already counted), so warps do not disturb each other.
+// Every endpoint read is recorded in rset (the vertices this inspection depends on) unless rset is NULL; returns -1 if they
+// do not fit.
 template <class P>
-__device__ __forceinline__ int wop_one_ring(WarpCtx<P>& w, int lane, int v0, int v1, uint32_t tagA, long long* hp) {
-    const uint32_t tagB = tagA | 1u;
-#ifdef MCNN_POOL_PROF
-    const long long t0_ = clock64();
-#endif
-    // both lists' descriptors in one round trip; a chained list is re-packed first (rare)
-    if ((unsigned)w.slab_next[v0] != P::NIL) wop_repack<P>(w, lane, v0);
-    if ((unsigned)w.slab_next[v1] != P::NIL) wop_repack<P>(w, lane, v1);
-    const int start0 = w.slab_start[v0], len0 = w.slab_len[v0];
-    const int start1 = w.slab_start[v1], len1 = w.slab_len[v1];
-    const unsigned next0 = (unsigned)w.slab_next[v0], next1 = (unsigned)w.slab_next[v1];
-    const unsigned x0 = (lane < len0) ? (unsigned)w.ve[start0 + lane] : P::NIL;
-    const unsigned x1 = (lane < len1) ? (unsigned)w.ve[start1 + lane] : P::NIL;
-    // the two dependent chains (entry -> endpoints -> union-find roots) run side by side: unconditional loads with a safe index
-    const typename P::pair_t w0 = w.evp[x0 != P::NIL ? x0 : 0u], w1 = w.evp[x1 != P::NIL ? x1 : 0u];
-    int a0 = pr_lo<P>(w0), b0 = pr_hi<P>(w0), a1 = pr_lo<P>(w1), b1 = pr_hi<P>(w1);
-    {
-        const int ra0 = (int)w.rep[a0], rb0 = (int)w.rep[b0], ra1 = (int)w.rep[a1], rb1 = (int)w.rep[b1];
-        if (ra0 != a0) a0 = uf_find(w.rep, a0);
-        if (rb0 != b0) b0 = uf_find(w.rep, b0);
-        if (ra1 != a1) a1 = uf_find(w.rep, a1);
-        if (rb1 != b1) b1 = uf_find(w.rep, b1);
-    }
-    if (x0 != P::NIL) { w.stamp[a0] = tagA; w.stamp[b0] = tagA; }
-#ifdef MCNN_POOL_PROF
-    const long long t1_ = clock64();
-#endif
-    // the rest of the first list: entries 32.. of the first slab, then the slabs linked behind it
-    {
-        unsigned s = (unsigned)v0;
-        int start = start0, len = len0, first = 32;
-        while (true) {
-            for (int i = first + lane; i < len; i += 32) {
-                const unsigned x = w.ve[start + i];
-                if (x == P::NIL) continue;
-                int a, b;
+__device__ __forceinline__ int warp_one_ring(const PoolState<P>& w, uint16_t* stamp, unsigned tagA, int lane, int v0, int v1,
+                                             typename P::uidx_t* rset, int& nrset) {
+    typedef typename P::uidx_t uidx_t;
+    const uint16_t tA = (uint16_t)tagA, tB = (uint16_t)(tagA | 1u);
+    const unsigned lt = (1u << lane) - 1u;
+    int step = 0;
+    bool over = false;
+    for (unsigned s = (unsigned)v0; s != P::NIL; s = (unsigned)w.slab_next[s]) {
+        const int start = w.slab_start[s], len = w.slab_len[s];
+        for (int base = 0; base < len; base += 32, ++step) {
+            const int i = base + lane;
+            const unsigned x = (i < len) ? (unsigned)w.ve[start + i] : P::NIL;
+            int a = (int)P::NIL, b = (int)P::NIL;
+            if (x != P::NIL) {
                 edge_ends<P>(w.evp, w.rep, (int)x, a, b);
-                w.stamp[a] = tagA;
-                w.stamp[b] = tagA;
+                stamp[a] = tA;
+                stamp[b] = tA;
             }
-            s = (s == (unsigned)v0) ? next0 : (unsigned)(unsigned)w.slab_next[s];
-            if (s == P::NIL) break;
-            start = w.slab_start[s]; len = w.slab_len[s]; first = 0;
+            if (rset != nullptr) {
+                if (step * 64 + 64 <= POOL_RSET_CAP) { rset[step * 64 + 2 * lane] = (uidx_t)a; rset[step * 64 + 2 * lane + 1] = (uidx_t)b; }
+                else over = true;
+            }
         }
     }
     __syncwarp();
-#ifdef MCNN_POOL_PROF
-    const long long t2_ = clock64();
-#endif
-    bool ha = false, hb = false;
-    if (x1 != P::NIL) {
-        if (a1 != v0 && a1 != v1) ha = atomicCAS(&w.stamp[a1], tagA, tagB) == tagA;
-        if (b1 != v0 && b1 != v1) hb = atomicCAS(&w.stamp[b1], tagA, tagB) == tagA;
-    }
-    int shared = __popc(__ballot_sync(0xffffffffu, ha)) + __popc(__ballot_sync(0xffffffffu, hb));
-#ifdef MCNN_POOL_PROF
-    const long long t3_ = clock64();
-    if (lane == 0 && hp) { hp[0] += t1_ - t0_; hp[1] += t2_ - t1_; hp[2] += t3_ - t2_; }
-#endif
-    {
-        unsigned s = (unsigned)v1;
-        int start = start1, len = len1, first = 32;
-        while (true) {
-            for (int base = first; base < len; base += 32) {
-                const int i = base + lane;
-                const unsigned x = (i < len) ? (unsigned)w.ve[start + i] : P::NIL;
-                ha = false; hb = false;
-                if (x != P::NIL) {
-                    int a, b;
-                    edge_ends<P>(w.evp, w.rep, (int)x, a, b);
-                    if (a != v0 && a != v1) ha = atomicCAS(&w.stamp[a], tagA, tagB) == tagA;
-                    if (b != v0 && b != v1) hb = atomicCAS(&w.stamp[b], tagA, tagB) == tagA;
-                }
-                shared += __popc(__ballot_sync(0xffffffffu, ha)) + __popc(__ballot_sync(0xffffffffu, hb));
+    int shared = 0;
+    for (unsigned s = (unsigned)v1; s != P::NIL; s = (unsigned)w.slab_next[s]) {
+        const int start = w.slab_start[s], len = w.slab_len[s];
+        for (int base = 0; base < len; base += 32, ++step) {
+            const int i = base + lane;
+            const unsigned x = (i < len) ? (unsigned)w.ve[start + i] : P::NIL;
+            int a = (int)P::NIL, b = (int)P::NIL;
+            if (x != P::NIL) edge_ends<P>(w.evp, w.rep, (int)x, a, b);
+            if (rset != nullptr) {
+                if (step * 64 + 64 <= POOL_RSET_CAP) { rset[step * 64 + 2 * lane] = (uidx_t)a; rset[step * 64 + 2 * lane + 1] = (uidx_t)b; }
+                else over = true;
             }
-            s = (s == (unsigned)v1) ? next1 : (unsigned)(unsigned)w.slab_next[s];
-            if (s == P::NIL) break;
-            start = w.slab_start[s]; len = w.slab_len[s]; first = 0;
+#pragma unroll
+            for (int which = 0; which < 2; ++which) {                      // first endpoints, then second endpoints
+                const int c = which ? b : a;
+                const bool hit = (x != P::NIL) && c != v0 && c != v1 && stamp[c] == tA;
+                const unsigned peers = __match_any_sync(0xffffffffu, hit ? c : -1 - lane);
+                const bool lead = hit && (peers & lt) == 0u;               // one lane per distinct vertex counts it ...
+                shared += __popc(__ballot_sync(0xffffffffu, lead));
+                if (lead) stamp[c] = tB;                                   // ... once
+                __syncwarp();
+            }
         }
     }
-    return shared;
+    nrset = min(step * 64, POOL_RSET_CAP);
+    return over ? -1 : shared;
 }
 
-// list.remove(x) on ve[v] (mesh.py:48) by search: the first occurrence in list order becomes a tombstone
+// list.remove(x) on ve[v] (mesh.py:48) by search (one thread): the first occurrence in list order becomes a tombstone.
+// Only needed for id 0 -- which the previous level's re-indexing gives to every stale entry -- and for inconsistent input.
 template <class P>
-__device__ __forceinline__ bool wop_list_remove(const WarpCtx<P>& w, int lane, int v, int x) {
+__device__ bool list_remove_scan(const PoolState<P>& w, int v, int x) {
     for (unsigned s = (unsigned)v; s != P::NIL; s = (unsigned)w.slab_next[s]) {
         const int start = w.slab_start[s], len = w.slab_len[s];
-        for (int base = 0; base < len; base += 32) {
-            const int i = base + lane;
-            const bool hit = (i < len) && ((int)w.ve[start + i] == x);
-            const unsigned m = __ballot_sync(0xffffffffu, hit);
-            if (m != 0u) {
-                if (lane == __ffs(m) - 1) w.ve[start + i] = (typename P::uidx_t)P::NIL;
-                __syncwarp();
-                return true;
-            }
-        }
+        for (int i = 0; i < len; ++i)
+            if ((int)w.ve[start + i] == x) { w.ve[start + i] = (typename P::uidx_t)P::NIL; return true; }
     }
     return false;
 }
 
-// Service loop of the helper warp: executes the posted operations in order until WOP_EXIT.
-template <class P>
-__device__ void helper_warp_loop(WarpCtx<P>& w, WorkQueue* q, int lane, long long* hprof) {
-    volatile int* vhead = &q->head;
-    int seq = 0;                                             // operations finished so far
-    while (true) {
-        while (*vhead == seq) {}                             // all lanes poll the same word: no divergence
-        __syncwarp();
-        __threadfence_block();
-        volatile int* ep = q->ent[seq % WQ_CAP];
-        int4 rq;
-        rq.x = ep[0]; rq.y = ep[1]; rq.z = ep[2]; rq.w = ep[3];
-        ++seq;
-        if (rq.x == WOP_EXIT) break;
-#ifdef MCNN_POOL_PROF
-        const long long th_ = clock64();
-#endif
-        int r;
-        if (rq.x == WOP_ONE_RING) {
-            r = wop_one_ring<P>(w, lane, rq.y, rq.z, (uint32_t)rq.w, hprof ? hprof + 3 : nullptr);
-        } else {                                             // WOP_REMOVE_SCAN: x leaves ve[a], then ve[b] (mesh.py:42-48)
-            r = wop_list_remove<P>(w, lane, rq.z, rq.y) ? 1 : 0;
-            if (r) r = wop_list_remove<P>(w, lane, rq.w, rq.y) ? 1 : 0;
-        }
-        if (lane == 0) {
-            *(volatile int*)&q->res = r;
-            __threadfence_block();
-            *(volatile int*)&q->res_seq = seq;
-        }
-        __syncwarp();
-        if (lane == 0) { __threadfence_block(); *(volatile int*)&q->done = seq; }
-#ifdef MCNN_POOL_PROF
-        if (lane == 0 && hprof) hprof[rq.x - 1] += clock64() - th_;
-#endif
-    }
-}
-
-// The collapse state as seen by lane 0 of warp 0 (the only thread that runs the reference's control flow).
+// The reference's control flow for ONE candidate, run by one thread on state nobody else touches meanwhile.
 template <class P>
 struct Collapse {
     typedef typename P::idx_t idx_t;
     typedef typename P::uidx_t uidx_t;
     typedef typename P::pair_t pair_t;
-    WorkQueue* q;             // list walks go to the helper warp
-    int posted;
+    PoolState<P> st;
     idx_t* gemm;
-    uidx_t *rep, *slab_next, *chain_tail, *ve, *eposa, *eposb;
-    pair_t *evp, *ulog;
     int8_t* sides;
     uint8_t* mask;
-    double* vs;               // shared copy or nullptr
-    uint8_t* vmask;           // shared copy of v_mask
     int32_t* log_unions;      // global or nullptr
     int union_cap;
-    int nunions, ulog_cap;
+    int nunions, ulog_cap;    // nunions: where this candidate's unions go in the log (strict order)
     int ec, T, status;
-    unsigned stamp_id;
 
-#ifdef MCNN_POOL_PROF
-    long long prof[7] = {0, 0, 0, 0, 0, 0, 0};
-#define PROF_T(i, stmt) { const long long t_ = clock64(); stmt; prof[i] += clock64() - t_; }
-#else
-#define PROF_T(i, stmt) { stmt; }
-#endif
-    __device__ __forceinline__ void ends(int e, int& v0, int& v1) { edge_ends<P>(evp, rep, e, v0, v1); }
-
-    __device__ __forceinline__ void post(int op, int a0, int a1, int a2) {
-        while (posted - *(volatile int*)&q->done >= WQ_CAP) {}
-#ifdef MCNN_POOL_PROF
-        const long long tp_ = clock64();
-#endif
-        volatile int* ep = q->ent[posted % WQ_CAP];
-        ep[0] = op; ep[1] = a0; ep[2] = a1; ep[3] = a2;
-        __threadfence_block();
-        *(volatile int*)&q->head = ++posted;
-#ifdef MCNN_POOL_PROF
-        prof[5] += clock64() - tp_;
-#endif
-    }
+    __device__ __forceinline__ void ends(int e, int& v0, int& v1) { edge_ends<P>(st.evp, st.rep, e, v0, v1); }
 
     // MeshUnion.union (mesh_union.py:11-12) is only logged here; the rows are evaluated after the collapse
     __device__ __forceinline__ void group_union(int s, int t) {
         if (log_unions != nullptr && nunions < union_cap) { log_unions[2 * nunions] = s; log_unions[2 * nunions + 1] = t; }
         if (s == t) status = MCNN_ST_DEGENERATE;
-        if (nunions < ulog_cap) ulog[nunions] = pr_pack<P>(s, t);
+        if (nunions < ulog_cap) st.ulog[nunions] = pr_pack<P>(s, t);
         else status = MCNN_ST_GROUP_OVERFLOW;
         ++nunions;
     }
@@ -497,7 +404,7 @@ struct Collapse {
         if ((a0 == b0 || a0 == b1) && (a0 == c0 || a0 == c1)) { ++count; v = a0; }
         if (a1 != a0 && (a1 == b0 || a1 == b1) && (a1 == c0 || a1 == c1)) { ++count; v = a1; }
         if (count != 1) { status = MCNN_ST_VERTEX_ASSERT; return; }
-        vmask[v] = 0;
+        st.vmask[v] = 0;
     }
 
     // __clean_side (mesh_pool.py:74-85)
@@ -516,48 +423,22 @@ struct Collapse {
         return status == 0;
     }
 
-    __device__ __forceinline__ int wait_result() {
-#ifdef MCNN_POOL_PROF
-        const long long tw_ = clock64();
-#endif
-        while (*(volatile int*)&q->res_seq != posted) {}
-        __threadfence_block();
-#ifdef MCNN_POOL_PROF
-        prof[6] += clock64() - tw_;
-#endif
-        return *(volatile int*)&q->res;
-    }
-
-    // __is_one_ring_valid (mesh_pool.py:95-100), walked by the helper warp.  The answer depends on the vertex lists, the
-    // endpoints and the union-find only -- none of which __clean_side touches -- so it is requested before the side
-    // cleaning and collected after it.
-    __device__ void one_ring_request(int e) {
-        int v0, v1;
-        ends(e, v0, v1);
-        ++stamp_id;
-        post(WOP_ONE_RING, v0, v1, (int)(stamp_id << 1));
-    }
-
     // Mesh.remove_edge (mesh.py:42-48): both list entries of x become tombstones
     __device__ void remove_edge(int x) {
-        const unsigned ia = eposa[x], ib = eposb[x];
-        if (x != 0 && ia != P::NIL && ib != P::NIL && (int)ve[ia] == x && (int)ve[ib] == x) {
-            ve[ia] = (uidx_t)P::NIL;
-            ve[ib] = (uidx_t)P::NIL;
+        const unsigned ia = st.eposa[x], ib = st.eposb[x];
+        if (x != 0 && ia != P::NIL && ib != P::NIL && (int)st.ve[ia] == x && (int)st.ve[ib] == x) {
+            st.ve[ia] = (uidx_t)P::NIL;
+            st.ve[ib] = (uidx_t)P::NIL;
             return;
         }
         int a, b;
         ends(x, a, b);
-        post(WOP_REMOVE_SCAN, x, a, b);
-        if (wait_result() != 1) status = MCNN_ST_VE_REMOVE;
+        if (!list_remove_scan<P>(st, a, x) || !list_remove_scan<P>(st, b, x)) status = MCNN_ST_VE_REMOVE;
     }
 
     // __pool_side (mesh_pool.py:102-113)
-    __device__ void pool_side(int e, int side) { pool_side(e, side, face_info(e, side)); }
-
-    // the same with the face record already fetched (the caller reads it while it waits for the one-ring answer)
-    __device__ void pool_side(int e, int side, const Face f) {
-        (void)side;
+    __device__ void pool_side(int e, int side) {
+        const Face f = face_info(e, side);
         const int base = f.sa - (f.sa & 1);
         redirect(f.ka, base, f.okb0, sides[4 * f.kb + f.osb]);
         redirect(f.ka, base + 1, f.okb1, sides[4 * f.kb + f.osb + 1]);     // read after the first rewiring, as the reference does
@@ -568,44 +449,59 @@ struct Collapse {
         ec -= 1;
     }
 
-    // Mesh.merge_vertices (mesh.py:26-37)
-    __device__ void merge_vertices(int e) {
+    // Mesh.merge_vertices (mesh.py:26-37); returns the surviving vertex (its list is now a chain) or -1
+    __device__ int merge_vertices(int e) {
         remove_edge(e);
         int v0, v1;
         ends(e, v0, v1);
-        if (v0 == v1) { status = MCNN_ST_DEGENERATE; return; }
-        if (vs != nullptr) {
+        if (v0 == v1) { status = MCNN_ST_DEGENERATE; return -1; }
+        if (st.vs != nullptr) {
 #pragma unroll
-            for (int k = 0; k < 3; ++k) vs[3 * v0 + k] = (vs[3 * v0 + k] + vs[3 * v1 + k]) / 2;
+            for (int k = 0; k < 3; ++k) st.vs[3 * v0 + k] = (st.vs[3 * v0 + k] + st.vs[3 * v1 + k]) / 2;
         }
-        vmask[v1] = 0;
+        st.vmask[v1] = 0;
         // ve[v0].extend(ve[v1]) : v1's chain moves behind v0's (ve[v1] is unreachable once every row holding v1 reads v0)
-        slab_next[(unsigned)chain_tail[v0]] = (uidx_t)v1;
-        chain_tail[v0] = chain_tail[v1];
-        rep[v1] = (uidx_t)v0;         // edges[edges == v1] = v0 over every row
+        st.slab_next[(unsigned)st.chain_tail[v0]] = (uidx_t)v1;
+        st.chain_tail[v0] = st.chain_tail[v1];
+        st.rep[v1] = (uidx_t)v0;         // edges[edges == v1] = v0 over every row
+        return v0;
     }
 
-    // __pool_edge (mesh_pool.py:58-72)
-    __device__ int pool_edge(int e) {
-        bool r, side2 = false;
-        PROF_T(0, r = has_boundaries(e));
-        if (r) return MCNN_POP_REJ_BOUNDARY;
-        PROF_T(2, one_ring_request(e));
-        PROF_T(1, r = clean_side(e, 0));
-        if (r) PROF_T(1, r = clean_side(e, 2) ? true : (side2 = true, false));
-        // nothing writes the one-ring tables between here and __pool_side(0): fetch its face record under the wait
-        const Face f0 = r ? face_info(e, 0) : Face();
-        const bool ring_ok = wait_result() == 2;             // always collected: the ring has one result slot
-        if (!r) return side2 ? MCNN_POP_REJ_SIDE2 : MCNN_POP_REJ_SIDE0;
-        if (!ring_ok) return MCNN_POP_REJ_ONE_RING;
-        PROF_T(3, pool_side(e, 0, f0));
+    // the tail of __pool_edge (mesh_pool.py:67-71) for a candidate that passed every test
+    __device__ int collapse(int e, int& merged) {
+        merged = -1;
+        pool_side(e, 0);
         if (status) return MCNN_POP_COLLAPSED;
-        PROF_T(3, pool_side(e, 2));
+        pool_side(e, 2);
         if (status) return MCNN_POP_COLLAPSED;
-        PROF_T(4, merge_vertices(e); mask[e] = 0);
+        merged = merge_vertices(e);
+        mask[e] = 0;
         ec -= 1;
         return MCNN_POP_COLLAPSED;
     }
+
+    // __pool_edge (mesh_pool.py:58-72), complete: used for the candidates that run alone.  ring_shared: the one-ring count,
+    // taken beforehand -- it depends on the vertex lists, the endpoints and the union-find only, none of which
+    // __clean_side touches.
+    __device__ int pool_edge(int e, int ring_shared, int& merged) {
+        merged = -1;
+        if (has_boundaries(e)) return MCNN_POP_REJ_BOUNDARY;
+        if (!clean_side(e, 0)) return MCNN_POP_REJ_SIDE0;
+        if (!clean_side(e, 2)) return MCNN_POP_REJ_SIDE2;
+        if (ring_shared != 2) return MCNN_POP_REJ_ONE_RING;
+        return collapse(e, merged);
+    }
+};
+
+// verdicts of the read-only inspection of a candidate
+enum { INSP_REJ_BOUNDARY = 1, INSP_REJ_ONE_RING = 2, INSP_COLLAPSE = 3, INSP_ALONE = 4 };
+constexpr int POOL_MAX_WARPS = 32;
+
+struct RoundCtl {                       // shared by the warps of the CTA
+    int verdict[POOL_MAX_WARPS];        // INSP_* of the window members, 0 = no member
+    int ok[POOL_MAX_WARPS];             // 1 = touches nothing an earlier member writes
+    int pos[POOL_MAX_WARPS];            // position of the member in the sorted order (its pop index)
+    int ec, nunions, status, bump;
 };
 
 template <class P>
@@ -630,7 +526,10 @@ __global__ void __launch_bounds__(P::THREADS, 1) pool_collapse_kernel(const mcnn
     uint8_t* mask = smem + L.mask;
     uidx_t* order = reinterpret_cast<uidx_t*>(smem + L.order);
     uidx_t* rep = reinterpret_cast<uidx_t*>(smem + L.rep);
-    uint32_t* stamp = reinterpret_cast<uint32_t*>(smem + L.stamp);
+    uint32_t* own_e = reinterpret_cast<uint32_t*>(smem + L.own_e);
+    uint32_t* own_v = reinterpret_cast<uint32_t*>(smem + L.own_v);
+    uint16_t* wstamp = reinterpret_cast<uint16_t*>(smem + L.wstamp);
+    uidx_t* rset_all = reinterpret_cast<uidx_t*>(smem + L.rset);
     uidx_t* slab_start = reinterpret_cast<uidx_t*>(smem + L.slab_start);
     uidx_t* slab_len = reinterpret_cast<uidx_t*>(smem + L.slab_len);
     uidx_t* slab_next = reinterpret_cast<uidx_t*>(smem + L.slab_next);
@@ -661,12 +560,13 @@ __global__ void __launch_bounds__(P::THREADS, 1) pool_collapse_kernel(const mcnn
     for (int i = tid; i < n; i += POOL_THREADS) {
         evp[i] = pr_pack<P>(g_edges[2 * i], g_edges[2 * i + 1]);
         mask[i] = 1;
+        own_e[i] = 0u;
         eposa[i] = (uidx_t)P::NIL;
         eposb[i] = (uidx_t)P::NIL;
     }
     for (int v = tid; v < V; v += POOL_THREADS) {
         rep[v] = (uidx_t)v;
-        stamp[v] = 0u;
+        own_v[v] = 0u;
         vmask_s[v] = g_vmask[v];
         const int beg = g_ve_ptr[v], end = g_ve_ptr[v + 1];
         slab_start[v] = (uidx_t)beg;
@@ -680,6 +580,7 @@ __global__ void __launch_bounds__(P::THREADS, 1) pool_collapse_kernel(const mcnn
     }
     if (with_vs)
         for (int i = tid; i < 3 * V; i += POOL_THREADS) vs_s[i] = g_vs[i];
+    for (int i = tid; i < V * (POOL_THREADS / 32); i += POOL_THREADS) wstamp[i] = 0;
     if (clk && tid == 0) clk[1] = clock64();
     // ---- phase B: sort (norm bits, id) ascending == heapify + heappop order (mesh_pool.py:184-192, F2) ----
     // Squared norms are non-negative floats: their bit patterns order like unsigned integers.  Stable LSD radix sort, four
@@ -754,51 +655,243 @@ __global__ void __launch_bounds__(P::THREADS, 1) pool_collapse_kernel(const mcnn
     if (tid == 0) { s_cursor = 0; s_flag = 0; s_ndead = 0; }
     __syncthreads();
     if (clk && tid == 0) clk[2] = clock64();
-    // ---- phase D: the sequential collapse (mesh_pool.py:41-53) on thread 0; warp 1 serves the list operations ----------
-    __shared__ WorkQueue s_queue;
-    if (tid == 0) { s_queue.head = 0; s_queue.done = 0; s_queue.res = 0; s_queue.res_seq = 0; }
+    // ---- phase D: the collapse (mesh_pool.py:41-53) in rounds; see the header comment ------------------------------------
+    __shared__ RoundCtl ctl;
+    constexpr int NWARPS = POOL_THREADS / 32;
+    const int wid = tid >> 5, lane = tid & 31;
+    PoolState<P> S;
+    S.gemm = gemm; S.sides = sides; S.mask = mask; S.evp = evp; S.ulog = ulog; S.rep = rep; S.slab_start = slab_start;
+    S.slab_len = slab_len; S.slab_next = slab_next; S.chain_tail = chain_tail; S.ve = ve; S.eposa = eposa; S.eposb = eposb;
+    S.vmask = vmask_s; S.vs = vs_s; S.own_e = own_e; S.own_v = own_v; S.bump = &ctl.bump; S.bump_end = a.ve_cap + 2 * E_in;
+    if (tid == 0) { ctl.ec = n; ctl.nunions = 0; ctl.status = 0; ctl.bump = min(g_ve_ptr[V], a.ve_cap); }
     __syncthreads();
-    if (tid == 0) {
-        Collapse<P> c;
-        c.q = &s_queue; c.posted = 0;
-        c.gemm = gemm; c.rep = rep; c.slab_next = slab_next; c.chain_tail = chain_tail; c.ve = ve; c.eposa = eposa; c.eposb = eposb;
-        c.evp = evp; c.ulog = ulog;
-        c.sides = sides; c.mask = mask; c.vs = vs_s; c.vmask = vmask_s;
-        c.log_unions = a.log_unions ? a.log_unions + (size_t)b * a.log_cap * 8 * 2 : nullptr;
-        c.union_cap = a.log_cap * 8; c.nunions = 0; c.ulog_cap = L.ulog_cap;
-        c.ec = n; c.T = T; c.status = 0; c.stamp_id = 0;
+    {
+        uint16_t* my_stamp = wstamp + (size_t)wid * V;
+        uidx_t* my_rset = rset_all + (size_t)wid * POOL_RSET_CAP;
         int32_t* lp = a.log_pops ? a.log_pops + (size_t)b * a.log_cap : nullptr;
         int8_t* lo = a.log_outcome ? a.log_outcome + (size_t)b * a.log_cap : nullptr;
-        int p = 0;
-        while (c.ec > T) {
-            if (p == n) { c.status = MCNN_ST_QUEUE_EMPTY; break; }
-            const int e = order[p];
-            const int outcome = mask[e] ? c.pool_edge(e) : MCNN_POP_SKIP_MASKED;
-            if (lp && p < a.log_cap) lp[p] = e;
-            if (lo && p < a.log_cap) lo[p] = (int8_t)outcome;
-            ++p;
-            if (c.status) break;
+        int32_t* lu = a.log_unions ? a.log_unions + (size_t)b * a.log_cap * 8 * 2 : nullptr;
+        unsigned ring_tag = 0;                                   // per warp; tags are (k << 1), k = 1 .. 32766
+        unsigned round = 0;
+        int ec = n, cursor = 0, nunions = 0, cstatus = 0;
+        auto next_ring_tag = [&]() {
+            ring_tag += 2;
+            if (ring_tag >= 65534u) {                             // tags wrapped: clear this warp's stamps
+                for (int i = lane; i < V; i += 32) my_stamp[i] = 0;
+                ring_tag = 2;
+                __syncwarp();
+            }
+            return ring_tag;
+        };
+        while (ec > T && cstatus == 0) {
+            ++round;
+            // -- select: the next NWARPS unmasked entries of the sorted order, the w-th one for warp w.  Every warp scans the
+            //    same entries and gets the same window, so no hand-over is needed. ----------------------------------------------
+            int my_e = -1, my_pos = -1, found = 0;
+            for (int p0 = cursor; p0 < n && found < NWARPS; p0 += 32) {
+                const int p = p0 + lane;
+                const int e = (p < n) ? (int)order[p] : 0;
+                const bool alive = (p < n) && mask[e] != 0;
+                const unsigned m = __ballot_sync(0xffffffffu, alive);
+                const int cnt = __popc(m);
+                const int want = wid - found;                     // which set bit of this chunk is this warp's (uniform)
+                if (my_e < 0 && want >= 0 && want < cnt) {
+                    const int src = (int)__fns(m, 0, want + 1);
+                    my_e = __shfl_sync(0xffffffffu, e, src);
+                    my_pos = p0 + src;
+                }
+                found += cnt;
+            }
+            if (found == 0) {                                     // the queue ran dry before the target was reached
+                for (int p = cursor + tid; p < n && p < a.log_cap; p += POOL_THREADS) {
+                    if (lp) lp[p] = order[p];
+                    if (lo) lo[p] = MCNN_POP_SKIP_MASKED;
+                }
+                cursor = n;
+                cstatus = MCNN_ST_QUEUE_EMPTY;
+                break;
+            }
+            // -- inspect (read-only on the mesh state) + reserve the rows a collapse would write ----------------------------------
+            const unsigned my_tag = (round << 5) | (unsigned)(31 - wid);
+            int verdict = 0;
+            int re[5], nre = 0;                                   // edge rows read
+            int we[9], wv[6];                                     // rows a collapse reads again and writes: edge rows, vertex rows
+            int nrset = 0, v0 = -1, v1 = -1;
+            if (my_e >= 0) {
+                const int e = my_e;
+                int row[4], nb[4][4];
+                bool boundary = false;                            // MeshPool.has_boundaries (mesh_pool.py:87-92)
+                re[nre++] = e;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { row[k] = gemm[4 * e + k]; boundary |= row[k] < 0; }
+                if (!boundary) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        re[nre++] = row[k];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) { nb[k][j] = gemm[4 * row[k] + j]; boundary |= nb[k][j] < 0; }
+                    }
+                }
+                if (boundary) {
+                    verdict = INSP_REJ_BOUNDARY;
+                } else {
+                    bool alone = false;
+                    int okb[2][2];
+#pragma unroll
+                    for (int sd = 0; sd < 2; ++sd) {             // __get_invalids' test (mesh_pool.py:115-121) without its side effects
+                        const int side = 2 * sd;
+                        const int sa = sides[4 * e + side], sb = sides[4 * e + side + 1];
+                        const int osa = (sa - (sa & 1) + 2) & 3, osb = (sb - (sb & 1) + 2) & 3;
+                        int oka0 = 0, oka1 = 0, okb0 = 0, okb1 = 0;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {            // (register arrays: compile-time indices only)
+                            if (j == osa) oka0 = nb[side][j];
+                            if (j == osa + 1) oka1 = nb[side][j];
+                            if (j == osb) okb0 = nb[side + 1][j];
+                            if (j == osb + 1) okb1 = nb[side + 1][j];
+                        }
+                        alone |= (oka0 == okb0) | (oka0 == okb1) | (oka1 == okb0) | (oka1 == okb1);
+                        okb[sd][0] = okb0; okb[sd][1] = okb1;
+                    }
+                    edge_ends<P>(evp, rep, e, v0, v1);
+                    alone |= v0 == v1;
+                    int ring = 0;
+                    if (!alone) {
+                        ring = warp_one_ring<P>(S, my_stamp, next_ring_tag(), lane, v0, v1, my_rset, nrset);
+                        alone = ring < 0;                         // lists too long for the read-set buffer
+                    }
+                    if (alone) {
+                        verdict = INSP_ALONE;
+                    } else if (ring != 2) {
+                        verdict = INSP_REJ_ONE_RING;
+                    } else {
+                        verdict = INSP_COLLAPSE;
+                        we[0] = e;
+                        we[1] = row[0]; we[2] = row[1]; we[3] = okb[0][0]; we[4] = okb[0][1];
+                        we[5] = row[2]; we[6] = row[3]; we[7] = okb[1][0]; we[8] = okb[1][1];
+                        wv[0] = v0; wv[1] = v1;
+                        edge_ends<P>(evp, rep, row[1], wv[2], wv[3]);     // remove_edge(key_b) edits the lists of key_b's endpoints
+                        edge_ends<P>(evp, rep, row[3], wv[4], wv[5]);
+                        if (lane < 9) {
+                            int x = we[0];
+#pragma unroll
+                            for (int k = 1; k < 9; ++k) if (lane == k) x = we[k];
+                            atomicMax(&own_e[x], my_tag);
+                        } else if (lane < 15) {
+                            int x = wv[0];
+#pragma unroll
+                            for (int k = 1; k < 6; ++k) if (lane == 9 + k) x = wv[k];
+                            atomicMax(&own_v[x], my_tag);
+                        }
+                    }
+                }
+            }
+            if (lane == 0) { ctl.verdict[wid] = verdict; ctl.pos[wid] = my_pos; }
+            __syncthreads();
+            // -- check: does anything this candidate read, or will write, belong to an earlier member of the window? --------------
+            {
+                bool clash = false;
+                auto earlier = [&](unsigned t) { return (t >> 5) == round && (31u - (t & 31u)) < (unsigned)wid; };
+                if (verdict != 0 && verdict != INSP_ALONE) {
+                    if (lane < nre) {
+                        int x = re[0];
+#pragma unroll
+                        for (int k = 1; k < 5; ++k) if (lane == k) x = re[k];
+                        clash |= earlier(own_e[x]);
+                    }
+                    if (verdict == INSP_COLLAPSE) {
+                        if (lane >= 5 && lane < 14) {
+                            int x = we[0];
+#pragma unroll
+                            for (int k = 1; k < 9; ++k) if (lane == 5 + k) x = we[k];
+                            clash |= earlier(own_e[x]);
+                        } else if (lane >= 14 && lane < 20) {
+                            int x = wv[0];
+#pragma unroll
+                            for (int k = 1; k < 6; ++k) if (lane == 14 + k) x = wv[k];
+                            clash |= earlier(own_v[x]);
+                        }
+                    }
+                    if (verdict != INSP_REJ_BOUNDARY) {
+                        if (lane == 30) clash |= earlier(own_v[v0]);
+                        if (lane == 31) clash |= earlier(own_v[v1]);
+                        for (int i = lane; i < nrset; i += 32) {
+                            const unsigned x = my_rset[i];
+                            if (x != P::NIL) clash |= earlier(own_v[x]);
+                        }
+                    }
+                }
+                const bool any = __any_sync(0xffffffffu, clash);
+                if (lane == 0) ctl.ok[wid] = any ? 0 : 1;
+            }
+            __syncthreads();
+            // -- the prefix that commits (every thread derives it from the shared verdicts) -------------------------------------
+            int k = 0, ec_run = ec, ncol = 0, my_uoff = nunions;
+            bool alone_round = false;
+            for (int j = 0; j < NWARPS; ++j) {
+                const int vj = ctl.verdict[j];
+                if (vj == 0 || ec_run <= T) break;               // window exhausted / the level is complete (mesh_pool.py:49)
+                if (!ctl.ok[j]) break;
+                if (vj == INSP_ALONE) { if (j == 0) { k = 1; alone_round = true; } break; }
+                if (j == wid) my_uoff = nunions + 4 * ncol;
+                k = j + 1;
+                if (vj == INSP_COLLAPSE) { ec_run -= 3; ++ncol; }
+            }
+            const int new_cursor = ctl.pos[k - 1] + 1;            // the pops move just behind the last committed member
+            // -- commit ------------------------------------------------------------------------------------------------------------
+            if (wid < k) {
+                int outcome = -1, merged = -1;
+                if (alone_round) {                               // (warp 0) the reference's sequential code path, by one thread
+                    int a0, a1, ring = 0, dummy = 0;
+                    edge_ends<P>(evp, rep, my_e, a0, a1);
+                    if (a0 != a1) ring = warp_one_ring<P>(S, my_stamp, next_ring_tag(), lane, a0, a1, (uidx_t*)nullptr, dummy);
+                    if (lane == 0) {
+                        Collapse<P> c;
+                        c.st = S; c.gemm = gemm; c.sides = sides; c.mask = mask; c.log_unions = lu; c.union_cap = a.log_cap * 8;
+                        c.nunions = nunions; c.ulog_cap = L.ulog_cap; c.ec = ec; c.T = T; c.status = 0;
+                        outcome = c.pool_edge(my_e, ring, merged);
+                        ctl.ec = c.ec; ctl.nunions = c.nunions;
+                        if (c.status) ctl.status = c.status;
+                    }
+                } else if (verdict == INSP_COLLAPSE) {
+                    if (lane == 0) {
+                        Collapse<P> c;
+                        c.st = S; c.gemm = gemm; c.sides = sides; c.mask = mask; c.log_unions = lu; c.union_cap = a.log_cap * 8;
+                        c.nunions = my_uoff; c.ulog_cap = L.ulog_cap; c.ec = ec; c.T = T; c.status = 0;
+                        outcome = c.collapse(my_e, merged);
+                        if (c.status) atomicMax(&ctl.status, c.status);
+                    }
+                } else {
+                    outcome = (verdict == INSP_REJ_BOUNDARY) ? MCNN_POP_REJ_BOUNDARY : MCNN_POP_REJ_ONE_RING;
+                }
+                merged = __shfl_sync(0xffffffffu, merged, 0);
+                if (merged >= 0) warp_repack<P>(S, lane, merged);
+                if (lane == 0) {
+                    if (lp && my_pos < a.log_cap) lp[my_pos] = my_e;
+                    if (lo && my_pos < a.log_cap) lo[my_pos] = (int8_t)outcome;
+                }
+            } else if ((lp || lo) && wid == NWARPS - 1) {
+                // the entries between the members were masked when the round began (and stay masked): skipped pops
+                for (int p = cursor + lane; p < new_cursor && p < a.log_cap; p += 32) {
+                    bool member = false;
+                    for (int j = 0; j < k; ++j) member |= ctl.pos[j] == p;
+                    if (!member) { if (lp) lp[p] = order[p]; if (lo) lo[p] = MCNN_POP_SKIP_MASKED; }
+                }
+            }
+            if (!alone_round && tid == 0) { ctl.ec = ec_run; ctl.nunions = nunions + 4 * ncol; }
+            __syncthreads();
+            cursor = new_cursor;
+            ec = ctl.ec;
+            nunions = ctl.nunions;
+            cstatus = ctl.status;
         }
-        c.post(WOP_EXIT, 0, 0, 0);
-        if (a.log_npops) a.log_npops[b] = p;
-        if (a.log_nunions) a.log_nunions[b] = c.nunions;
-        s_status = c.status;
-        s_nunions = min(c.nunions, c.ulog_cap);
-        if (clk) {
-            clk[3] = clock64();
-            clk[7] = p;
-#ifdef MCNN_POOL_PROF
-            for (int i = 0; i < 5; ++i) clk[8 + i] = c.prof[i];
-            clk[5] = c.prof[5];
-            clk[6] = c.prof[6];
-#endif
+        if (tid == 0) {
+            if (a.log_npops) a.log_npops[b] = cursor;
+            if (a.log_nunions) a.log_nunions[b] = nunions;
+            s_status = cstatus;
+            s_nunions = min(nunions, L.ulog_cap);
+            if (clk) { clk[3] = clock64(); clk[7] = cursor; clk[8] = round; }
         }
-    } else if (tid >= 32 && tid < 64) {
-        WarpCtx<P> w;
-        w.ve = ve; w.slab_start = slab_start; w.slab_len = slab_len; w.slab_next = slab_next; w.chain_tail = chain_tail;
-        w.rep = rep; w.evp = evp; w.stamp = stamp; w.eposa = eposa; w.eposb = eposb;
-        w.bump = min(g_ve_ptr[V], a.ve_cap); w.bump_end = a.ve_cap + 2 * E_in;
-        helper_warp_loop<P>(w, &s_queue, tid - 32, clk ? clk + 13 : nullptr);
     }
     __syncthreads();
     int status = s_status;

@@ -272,28 +272,70 @@ class UpConv(nn.Module):
 
 
 class MeshEncoder(nn.Module):
+    """Down-convolution stack, optionally followed by the fully-connected head of networks.py:304-323 (`fcs` layer widths,
+    `global_pool` 'max' / 'avg' over the last pooled resolution or none = flatten [C x E])."""
+
     def __init__(self, pools, convs, fcs=None, blocks=0, global_pool=None):
         super(MeshEncoder, self).__init__()
-        if fcs is not None or global_pool is not None:
-            raise NotImplementedError('the fully-connected encoder head is not used by any shipped configuration')
         self.fcs = None
+        self.global_pool = None
         self.convs = nn.ModuleList([DownConv(convs[i], convs[i + 1], blocks=blocks,
                                              pool=pools[i + 1] if i + 1 < len(pools) else 0)
                                     for i in range(len(convs) - 1)])
+        if fcs is not None:
+            last_length = convs[-1]
+            if global_pool is not None:
+                if global_pool == 'max':
+                    self.global_pool = nn.MaxPool1d(pools[-1])
+                elif global_pool == 'avg':
+                    self.global_pool = nn.AvgPool1d(pools[-1])
+                else:
+                    assert False, 'global_pool %s is not defined' % global_pool
+            else:
+                last_length *= pools[-1]
+            fcs = list(fcs)
+            if fcs[0] == last_length:
+                fcs = fcs[1:]
+            layers, norms = [], []
+            for length in fcs:
+                layers.append(nn.Linear(last_length, length))
+                norms.append(nn.InstanceNorm1d(length))
+                last_length = length
+            self.fcs = nn.ModuleList(layers)
+            self.fcs_bn = nn.ModuleList(norms)
         _xavier_reset(self)
 
+    def _head(self, fe):
+        """fe: logical [B, C, E] (a view of the edge-major tensor)."""
+        if self.global_pool is not None:
+            fe = self.global_pool(fe)
+        fe = fe.contiguous().view(fe.size()[0], -1)
+        for i in range(len(self.fcs)):
+            fe = self.fcs[i](fe)
+            if self.fcs_bn:
+                fe = self.fcs_bn[i](fe.unsqueeze(1)).squeeze(1)
+            if i < len(self.fcs) - 1:
+                fe = F.relu(fe)
+        return fe
+
     def forward_em(self, fe, batch):
+        """-> (edge-major [B, E, C] features, or the [B, fcs[-1]] code when the head is present; encoder skips)."""
         outs = []
         for conv in self.convs:
             fe, before = conv.forward_em(fe, batch)
             outs.append(before)
+        if self.fcs is not None:
+            fe = self._head(as_bce(fe))
         return fe, outs
 
     def forward(self, x):
         fe, meshes = x
         batch = MeshBatch.of(meshes, fe.shape[2], fe.device)
         fe, outs = self.forward_em(to_edge_major(fe), batch)
-        return as_bce(fe), [None if o is None else as_bce(o) for o in outs]
+        return (fe if self.fcs is not None else as_bce(fe)), [None if o is None else as_bce(o) for o in outs]
+
+    def __call__(self, x):
+        return self.forward(x)
 
 
 class MeshDecoder(nn.Module):

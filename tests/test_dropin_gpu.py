@@ -52,6 +52,19 @@ for arch, ncf, ncls in (('mconvnet', [16, 32], 4), ('meshunet', [16, 32, 64], 4)
     assert close(g1, g2, 1e-3), arch
     for k in p1:
         assert close(p1[k], p2[k], 1e-3, 2e-6), (arch, k)
+# the fully-connected encoder head (networks.py:304-346): reference class vs ours, same weights
+for gp in (None, 'avg', 'max'):
+    torch.manual_seed(3)
+    enc_t = nets.MeshEncoder([E, 200, 150], [5, 8, 16], fcs=[64, 10], blocks=1, global_pool=gp).cuda()
+    enc_m = N.MeshEncoder([E, 200, 150], [5, 8, 16], fcs=[64, 10], blocks=1, global_pool=gp).cuda()
+    enc_m.load_state_dict(enc_t.state_dict())
+    outs = []
+    for enc in (enc_t, enc_m):
+        meshes = [Mesh(data=d, hold_history=True) for d in datas]
+        code, skips = enc((torch.from_numpy(x).cuda(), meshes))
+        outs.append(code.detach().cpu())
+        assert code.shape == (B, 10) and len(skips) == 2
+    assert float((outs[0] - outs[1]).abs().max()) <= 1e-4 * float(outs[0].abs().max()) + 1e-6, gp
 print('DROPIN-GPU-OK')
 '''
 

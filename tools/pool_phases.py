@@ -35,12 +35,9 @@ for rec in batch.records:
     for i, nm in enumerate(names):
         print('    %-14s mean %7.1f  max %7.1f us' % (nm, d[:, i].mean(), d[:, i].max()))
     print('    pops mean %.1f max %d; removed edges %d' % (clk[:, 7].mean(), clk[:, 7].max(), rec.E_in - rec.T))
-    if clk[:, 8:13].sum() > 0:
-        for i, nm in enumerate(['has_boundaries', 'clean_side x2', 'one_ring_valid', 'pool_side x2', 'merge+kill']):
-            print('    . %-14s mean %7.1f us' % (nm, clk[:, 8 + i].mean() / 1.965e3))
-        print('    . post() %.1f us, one-ring wait %.1f us; helper busy: one_ring %.1f remove_edge %.1f concat %.1f us' % tuple(
-            clk[:, i].mean() / 1.965e3 for i in (5, 6, 13, 14, 15)))
-        e = [clk[:, 3]] + [clk[:, i] for i in (19, 20, 21, 22, 23)] + [clk[:, 4]]
-        print('    . export: E1+adjacency %.1f | E2 %.1f | E3 %.1f | occ %.1f | BFS columns %.1f | CSC/CSR write %.1f us (mean);  max %s' % (
-            tuple(((e[i + 1] - e[i]) / 1.965e3).mean() for i in range(6)) + (' '.join('%.0f' % ((e[i + 1] - e[i]) / 1.965e3).max() for i in range(6)),)))
-        print('    . one_ring inside: fetch+resolve+stamp %.1f, syncwarp %.1f, cas+ballot %.1f us' % tuple(clk[:, i].mean() / 1.965e3 for i in (16, 17, 18)))
+    rounds = clk[:, 8]
+    print('    rounds mean %.1f max %d; pops per round %.2f; collapse phase per round %.2f us' % (
+        rounds.mean(), rounds.max(), clk[:, 7].sum() / max(rounds.sum(), 1), (d[:, 2] / np.maximum(rounds, 1)).mean()))
+    e = [clk[:, 3]] + [clk[:, i] for i in (19, 20, 21, 22, 23)] + [clk[:, 4]]
+    print('    . export: E1+adjacency %.1f | E2 %.1f | E3 %.1f | occ %.1f | BFS columns %.1f | CSC/CSR write %.1f us (mean);  max %s' % (
+        tuple(((e[i + 1] - e[i]) / 1.965e3).mean() for i in range(6)) + (' '.join('%.0f' % ((e[i + 1] - e[i]) / 1.965e3).max() for i in range(6)),)))
