@@ -312,6 +312,9 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='launch the step kernel by kernel instead of replaying a CUDA graph')
+    ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
+                    help='weak: the config batch PER GPU; strong: the config batch is the GLOBAL batch, sharded over the ranks '
+                         '(uneven shards are weighted by mesh count in the gradient all-reduce)')
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
     if args.batch:
@@ -334,11 +337,22 @@ def main():
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=dev)
     B, E = cfg['B'], cfg['E']
-    datas, x, labels = make_inputs(cfg, B, rank * B)
+    B_global = world * B
+    if args.scaling == 'strong':                                        # rank r owns a contiguous slice of the batch
+        B_global = cfg['B']
+        if B_global < world:
+            raise SystemExit('strong scaling needs at least one mesh per rank (batch %d, %d ranks)' % (B_global, world))
+        lo, hi = ddp.shard_range(B_global, rank, world)
+        datas, x, labels = make_inputs(cfg, B_global, 0)                # every rank builds the global batch, keeps its slice
+        datas, x, labels = datas[lo:hi], np.ascontiguousarray(x[lo:hi]), np.ascontiguousarray(labels[lo:hi])
+        B = hi - lo
+    else:
+        datas, x, labels = make_inputs(cfg, B, rank * B)
     net = build_net(cfg, 'ours').to(dev).train()
     if world > 1:
         ddp.broadcast_parameters(net)
-    reducer = ddp.FlatGradReducer(net)                                  # grads are views into one flat buffer
+    # grads are views into one flat buffer; uneven shards: each rank's mean gradient is weighted by its share of the batch
+    reducer = ddp.FlatGradReducer(net, local_items=B, global_items=B_global) if args.scaling == 'strong' else ddp.FlatGradReducer(net)
     from meshcnn_b200.optim import FlatAdam
     opt = FlatAdam(reducer, lr=cfg['lr'], betas=(0.9, 0.999))            # one kernel over the flat parameter buffer
     crit = loss_fn_for(cfg)
@@ -410,7 +424,7 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
-    value = world * B * args.steps / (total_ms / 1e3)
+    value = B_global * args.steps / (total_ms / 1e3)
 
     # ---- per-kernel CUDA-event timings: the same step launched kernel by kernel (events cannot bracket the nodes of a
     # replayed graph), L2 flushed between steps as above -------------------------------------------------------------
@@ -420,13 +434,23 @@ def main():
     px = torch.from_numpy(x).to(dev).requires_grad_(True)
     py = torch.from_numpy(labels).to(dev)
 
+    ar_events = []                                                   # per step: (start, before all-reduce, after all-reduce)
+
     def eager_step():
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)] if world > 1 else None
+        if ev:
+            ev[0].record()
         pbatch.reset()
         reducer.zero()
         px.grad = None
         loss = crit(net(px, pmeshes), py)
         loss.backward()
+        if ev:
+            ev[1].record()
         reducer.allreduce()
+        if ev:
+            ev[2].record()
+            ar_events.append(ev)
         opt.step()
 
     for _ in range(2):
@@ -447,6 +471,24 @@ def main():
     recs = profiler.collect()
     eager_ms = sum(a.elapsed_time(b) for a, b in pe)
     del pbatch, pmeshes
+    # where the multi-GPU step loses time: every rank's own compute time up to the all-reduce, and the time it then spends
+    # inside the all-reduce (= NCCL itself + waiting for the slowest rank); gathered from all ranks
+    attribution = None
+    if world > 1 and ar_events:
+        evs_ = ar_events[-k_prof:]
+        comp = sum(e[0].elapsed_time(e[1]) for e in evs_) / len(evs_)
+        wait = sum(e[1].elapsed_time(e[2]) for e in evs_) / len(evs_)
+        mine = torch.tensor([comp, wait], dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        comp_r = [float(t[0]) for t in allr]
+        wait_r = [float(t[1]) for t in allr]
+        attribution = {'compute_ms_per_rank': comp_r, 'allreduce_ms_per_rank': wait_r,
+                       'straggler_ms': max(comp_r) - sum(comp_r) / world,        # the step lasts as long as the slowest rank
+                       'nccl_alone_ms': min(wait_r),                            # the last rank to arrive waits for nobody
+                       'mean_wait_for_slowest_ms': sum(wait_r) / world - min(wait_r),
+                       'note': 'eager steps (kernel-by-kernel launch), CUDA events on each rank; the replayed graph has the same '
+                               'dependency structure: all-reduce after the last gradient kernel'}
 
     # ---- end-to-end arm: host buffers in, loss out, every step ------------------------------------------------------
     e2e = None
@@ -512,7 +554,7 @@ def main():
         t = torch.tensor([dt], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e = {'value': world * B * k_e2e / float(t.item()), 'unit': 'meshes/s', 'h2d_bytes_per_step': int(h2d_bytes()),
+        e2e = {'value': B_global * k_e2e / float(t.item()), 'unit': 'meshes/s', 'h2d_bytes_per_step': int(h2d_bytes()),
                'd2h_bytes_per_step': 4, 'timing': 'host wall clock between device synchronisations, max over ranks',
                'host_pack_ms_per_step': 1e3 * t_pack[0] / k_e2e,
                'api': 'meshcnn_b200.graphed.PipelinedTrainStep.submit(meshes, x, y) from host buffers, loss read back every step' if gs is not None else
@@ -608,13 +650,14 @@ def main():
                                        'note': 'reference: wall time inside MeshPool.forward (host); ours: CUDA-event time of the pool kernels in the eager attribution pass'}
 
     line = {'metric': 'train meshes/sec (fwd+bwd+pool)', 'value': value, 'unit': 'meshes/s', 'n_gpus': world, 'steps': args.steps,
-            'warmup': args.warmup, 'ms_per_step': total_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+            'warmup': args.warmup, 'ms_per_step': total_ms / args.steps, 'higher_is_better': True, 'scaling': args.scaling,
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': workload_name(args.config, cfg), 'global_batch': world * B,
+            'config': {'workload': workload_name(args.config, cfg) + (' [GLOBAL batch, sharded]' if args.scaling == 'strong' else ''),
+                       'global_batch': B_global,
                        'parallelism': 'dp%d (meshes sharded, one flat NCCL gradient allreduce)' % world,
                        'l2': 'flushed between timed steps (256 MiB write, untimed); per-step CUDA events, max over ranks',
                        'optimizer': 'Adam (in the timed region)', 'launch': mode},
-            'roofline': roofline, 'pool_collapse': pool_info, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks}
+            'roofline': roofline, 'pool_collapse': pool_info, 'cpu_baseline': cpu, 'e2e': e2e, 'multi_gpu_attribution': attribution, 'gpu_launches': int(launches), 'clocks': clocks}
     _finish(out, line, cleanup)
 
 

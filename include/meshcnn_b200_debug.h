@@ -20,6 +20,9 @@ int mcnn_debug_set_tc_bd_tile(int on);
 /* diagnostics only: output-channel tiles of 128 per CTA in mcnn_meshconv_bwd_weight_tc (1 or 2; 0 = built-in choice: 2 when
  * Cout % 256 == 0).  mcnn_meshconv_bwd_weight_tc_ws() follows the setting. */
 int mcnn_debug_set_tc_bw_ot(int ot);
+/* diagnostics only: 0 = mcnn_meshconv_bwd_weight_tc keeps both operands in shared memory (the first-generation kernel);
+ * 1 (default) = dout^T is held in tensor memory */
+int mcnn_debug_set_tc_bw_tmem_a(int on);
 
 /* diagnostics only: force the grid size of mcnn_meshconv_fwd_tc_sk (0 = one CTA per SM) */
 int mcnn_debug_set_tc_sk_ctas(int n);

@@ -1880,6 +1880,253 @@ meshconv_bwd_weight_tc_kernel(const float* __restrict__ dout, const float* __res
     }
 }
 
+// -------------------------------------------------------------------------------------------------------------
+// The same contraction with the A operand (dout, transposed: rows = output channels, K = edges) in TENSOR MEMORY.
+// The kernel above is bound by the shared-memory port: per 32-edge K block 256 threads write 106 KB of operands (A and B,
+// hi and lo) and the MMAs read 216 KB back.  dout^T is exactly what a TMEM A operand wants -- lane = output channel,
+// column = edge -- so each producer thread owns ONE output channel, reads its 32 values of the K block (a warp instruction
+// reads 32 consecutive channels of one edge: a coalesced 128-byte line), splits them and writes them into its own TMEM
+// lane with tcgen05.st.32x32b: no transpose, no shared memory, no proxy fence for A.  Shared memory holds only the
+// gathered G operand (40 KB per stage, four stages), built once per K block for all 128 * OT output channels.
+// TMEM (512 columns): accumulators [0,160) and [256,416); three A slots of 32 + 32 columns (hi, lo) in the gaps, the
+// column plan of the persistent data-gradient kernel.  A slot holds one (K block, output tile) unit; units go round the
+// three slots, so A production runs up to 1.5 K blocks ahead of the tensor core.
+// -------------------------------------------------------------------------------------------------------------
+template <int OT>
+struct BwaSmem {
+    static constexpr int B_BYTES = 32 * BD_N * 4;            // 32 edges x 160 cols
+    static constexpr int STAGE_BYTES = 2 * B_BYTES;          // hi + lo = 40960
+    static constexpr int STAGES = 4;
+    static constexpr int A_SLOTS = 3;
+    static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+    static constexpr int TOTAL = BAR_OFF + 32 * 8 + 16 + 1024;
+    static constexpr uint32_t LBO = 4096;
+};
+
+template <int OT>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+meshconv_bwd_weight_tca_kernel(const float* __restrict__ dout, const float* __restrict__ x, const int32_t* __restrict__ gemm,
+                               const int32_t* __restrict__ ec, float* __restrict__ ws, int B, int E, int Cin, int Cout,
+                               int rows_per_split) {
+    using S = BwaSmem<OT>;
+    constexpr int AV = 16 * OT;                              // dout values per thread and K block (OT == 1: half of the edges)
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full_b = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
+    uint64_t* empty_b = full_b + S::STAGES;
+    uint64_t* full_a = empty_b + S::STAGES;
+    uint64_t* empty_a = full_a + S::A_SLOTS;
+    uint64_t* accum_bar = empty_a + S::A_SLOTS;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int M = B * E;
+    const int split = blockIdx.x, o0 = blockIdx.y * (128 * OT), cb = blockIdx.z;
+    const int mbeg = split * rows_per_split, mend = min(M, mbeg + rows_per_split);
+    const int num_kb = (mend > mbeg) ? (mend - mbeg + 31) >> 5 : 0;
+
+    if (warp == TC_PRODUCER_WARPS) {
+        if (lane == 0) {
+            for (int s = 0; s < S::STAGES; ++s) { tc::mbar_init(full_b + s, TC_PRODUCER_WARPS); tc::mbar_init(empty_b + s, 1); }
+            for (int s = 0; s < S::A_SLOTS; ++s) { tc::mbar_init(full_a + s, OT == 2 ? 4 : 8); tc::mbar_init(empty_a + s, 1); }
+            tc::mbar_init(accum_bar, 1);
+            tc::fence_barrier_init();
+        }
+        __syncwarp();
+        tc::tmem_alloc<512>(tmem_slot);
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < TC_PRODUCER_WARPS) {
+        const int pt = tid;
+        struct Idx { int s0, s1, s2, s3, s4; };
+        struct Data { float av[AV]; float4 f[5]; };
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int bk = pt >> 3, bq = pt & 7;                                // this thread's edge-in-block and channel chunk (B operand)
+        // A operand: this thread's output channel and its share of the K block's edges
+        const int a_tile = OT == 2 ? (warp >> 2) : 0;                       // OT == 2: warps 0-3 feed tile 0, warps 4-7 tile 1
+        const int a_e0 = OT == 2 ? 0 : (warp >> 2) * 16;                    // OT == 1: the two warp groups split the 32 edges
+        const int a_o = o0 + a_tile * 128 + (warp & 3) * 32 + lane;
+        const uint32_t a_lane = (uint32_t)((warp & 3) * 32) << 16;
+        int nb_b = (mbeg + bk) / E, nb_e = (mbeg + bk) - nb_b * E;
+        auto load_idx = [&](int kb) {
+            Idx I; I.s0 = I.s1 = I.s2 = I.s3 = I.s4 = -1;
+            const int m = mbeg + (kb << 5) + bk;
+            const int b = nb_b, e = nb_e;
+            nb_e += 32;
+            while (nb_e >= E) { nb_e -= E; ++nb_b; }
+            if (m < mend) {
+                if (e >= __ldg(ec + b)) { I.s0 = I.s1 = I.s2 = I.s3 = I.s4 = b * E; }
+                else {
+                    const int4 g4 = __ldg(reinterpret_cast<const int4*>(gemm + (size_t)m * 4));
+                    I.s0 = m;
+                    I.s1 = g4.x < 0 ? -1 : b * E + g4.x; I.s2 = g4.y < 0 ? -1 : b * E + g4.y;
+                    I.s3 = g4.z < 0 ? -1 : b * E + g4.z; I.s4 = g4.w < 0 ? -1 : b * E + g4.w;
+                }
+            }
+            return I;
+        };
+        auto load_data = [&](int kb, const Idx& I) {
+            Data D;
+            const int mb = mbeg + (kb << 5) + a_e0;
+            const float* ap = dout + (size_t)mb * Cout + a_o;
+#pragma unroll
+            for (int j = 0; j < AV; ++j)
+                D.av[j] = (mb + j < mend && a_o < Cout) ? __ldg(ap + (size_t)j * Cout) : 0.f;
+            const int c = cb * 32 + (bq << 2);
+            D.f[0] = I.s0 >= 0 ? __ldg(reinterpret_cast<const float4*>(x + (size_t)I.s0 * Cin + c)) : z;
+            D.f[1] = I.s1 >= 0 ? __ldg(reinterpret_cast<const float4*>(x + (size_t)I.s1 * Cin + c)) : z;
+            D.f[2] = I.s2 >= 0 ? __ldg(reinterpret_cast<const float4*>(x + (size_t)I.s2 * Cin + c)) : z;
+            D.f[3] = I.s3 >= 0 ? __ldg(reinterpret_cast<const float4*>(x + (size_t)I.s3 * Cin + c)) : z;
+            D.f[4] = I.s4 >= 0 ? __ldg(reinterpret_cast<const float4*>(x + (size_t)I.s4 * Cin + c)) : z;
+            return D;
+        };
+        auto store_block = [&](int kb, const Data& D) {
+            // ---- B: the gathered operand into shared memory (all eight warps) ----
+            {
+                const int s = kb % S::STAGES;
+                const uint32_t ph = (kb / S::STAGES) & 1;
+                if (lane == 0) tc::mbar_wait(empty_b + s, ph ^ 1);        // one poller per warp
+                __syncwarp();
+                const uint32_t b_hi = tc::smem_u32(smem + s * S::STAGE_BYTES);
+                const uint32_t b_lo = b_hi + S::B_BYTES;
+                const float4 f0 = D.f[0], f1 = D.f[1], f2 = D.f[2], f3 = D.f[3], f4 = D.f[4];
+                float4 gk[5];
+                gk[0] = f0;
+                gk[1] = make_float4(f1.x + f3.x, f1.y + f3.y, f1.z + f3.z, f1.w + f3.w);
+                gk[2] = make_float4(f2.x + f4.x, f2.y + f4.y, f2.z + f4.z, f2.w + f4.w);
+                gk[3] = make_float4(fabsf(f1.x - f3.x), fabsf(f1.y - f3.y), fabsf(f1.z - f3.z), fabsf(f1.w - f3.w));
+                gk[4] = make_float4(fabsf(f2.x - f4.x), fabsf(f2.y - f4.y), fabsf(f2.z - f4.z), fabsf(f2.w - f4.w));
+#pragma unroll
+                for (int k5 = 0; k5 < 5; ++k5) {
+                    float4 hi, lo;
+                    tc::split4(gk[k5], hi, lo);
+                    const uint32_t off = tc::sw128_mn_off(bk, k5 * 8 + bq, S::LBO);
+                    tc::sts128(b_hi + off, hi);
+                    tc::sts128(b_lo + off, lo);
+                }
+                tc::fence_proxy_async_smem();                              // every writer fences its own stores ...
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(full_b + s);                // ... then one arrival per warp
+            }
+            // ---- A: this thread's output channel x its edges of the block, straight into its TMEM lane ----
+            {
+                const int u = kb * OT + a_tile;                            // (K block, output tile) unit -> A slot
+                const uint32_t slot = (uint32_t)(u % S::A_SLOTS), ph = (uint32_t)((u / S::A_SLOTS) & 1);
+                if (lane == 0) tc::mbar_wait(empty_a + slot, ph ^ 1);
+                __syncwarp();
+                tc::tc_fence_after();
+                const uint32_t c_hi = tmem_base + a_lane + bdp_a_hi_col(slot) + (uint32_t)a_e0;
+                const uint32_t c_lo = tmem_base + a_lane + bdp_a_lo_col(slot) + (uint32_t)a_e0;
+#pragma unroll
+                for (int h = 0; h < AV / 16; ++h) {
+                    float hi[16], lo[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) tc::split_tf32(D.av[16 * h + j], hi[j], lo[j]);
+                    tc::tmem_st_32x32b_x16(c_hi + 16 * h, hi);
+                    tc::tmem_st_32x32b_x16(c_lo + 16 * h, lo);
+                }
+                tc::tmem_wait_st();
+                tc::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(full_a + slot);
+            }
+        };
+        if (num_kb > 0) {
+            Data D0 = load_data(0, load_idx(0));
+            Data D1;
+            if (num_kb > 1) D1 = load_data(1, load_idx(1));
+            Idx In;
+            if (num_kb > 2) In = load_idx(2);
+            for (int kb = 0; kb < num_kb; kb += 2) {
+                store_block(kb, D0);
+                if (kb + 2 < num_kb) D0 = load_data(kb + 2, In);
+                if (kb + 3 < num_kb) In = load_idx(kb + 3);
+                if (kb + 1 < num_kb) {
+                    store_block(kb + 1, D1);
+                    if (kb + 3 < num_kb) D1 = load_data(kb + 3, In);
+                    if (kb + 4 < num_kb) In = load_idx(kb + 4);
+                }
+            }
+        }
+        // ---- epilogue: slab partial -> ws[split][o][c][k5] ---------------------------------------------------------
+        const int lane_grp = warp & 3;
+        const int cl0 = (warp >> 2) * 16;
+        if (num_kb > 0) {
+            tc::mbar_wait(accum_bar, 0);
+            tc::tc_fence_after();
+        }
+#pragma unroll 1
+        for (int t = 0; t < OT; ++t) {
+            const int o = o0 + t * 128 + lane_grp * 32 + lane;
+            float g[5][16];
+            if (num_kb > 0) {
+#pragma unroll
+                for (int k5 = 0; k5 < 5; ++k5) tc::tmem_ld16(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(t * 256 + k5 * 32 + cl0), g[k5]);
+            } else {
+#pragma unroll
+                for (int k5 = 0; k5 < 5; ++k5)
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) g[k5][j] = 0.f;
+            }
+            if (o < Cout) {
+                float* dst = ws + (((size_t)split * Cout + o) * Cin + cb * 32 + cl0) * 5;      // 80 contiguous floats
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                    float tt[20];                                        // (c, k5) interleave: 4 channels x 5 taps = 5 float4
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+                        for (int k5 = 0; k5 < 5; ++k5) tt[jj * 5 + k5] = g[k5][j + jj];
+#pragma unroll
+                    for (int v = 0; v < 5; ++v)
+                        *reinterpret_cast<float4*>(dst + j * 5 + v * 4) = make_float4(tt[v * 4], tt[v * 4 + 1], tt[v * 4 + 2], tt[v * 4 + 3]);
+                }
+            }
+        }
+        tc::tc_fence_before();
+    } else {
+        constexpr uint32_t idesc = tc::make_idesc_tf32_bmn(BD_N);
+        for (int kb = 0; kb < num_kb; ++kb) {
+            const int s = kb % S::STAGES;
+            tc::mbar_wait(full_b + s, (uint32_t)((kb / S::STAGES) & 1));
+            const uint32_t b_hi = tc::smem_u32(smem + s * S::STAGE_BYTES);
+            const uint32_t b_lo = b_hi + S::B_BYTES;
+#pragma unroll
+            for (int t = 0; t < OT; ++t) {
+                const int u = kb * OT + t;
+                const uint32_t slot = (uint32_t)(u % S::A_SLOTS);
+                tc::mbar_wait(full_a + slot, (uint32_t)((u / S::A_SLOTS) & 1));
+                tc::tc_fence_after();
+                if (tc::elect_one()) {
+                    const uint32_t a_hi = tmem_base + bdp_a_hi_col(slot), a_lo = tmem_base + bdp_a_lo_col(slot);
+                    const uint32_t acc = tmem_base + (uint32_t)(t * 256);
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {                     // one 8-edge K group per MMA: +1024 bytes in B, +8 columns in A
+                        const uint64_t dbh = tc::make_desc_sw128_mn(b_hi + kk * 1024, S::LBO), dbl = tc::make_desc_sw128_mn(b_lo + kk * 1024, S::LBO);
+                        tc::mma_tf32_ts(acc, a_hi + 8 * kk, dbh, idesc, (kb | kk) != 0);
+                        tc::mma_tf32_ts(acc, a_hi + 8 * kk, dbl, idesc, 1);
+                        tc::mma_tf32_ts(acc, a_lo + 8 * kk, dbh, idesc, 1);
+                    }
+                    tc::mma_commit(empty_a + slot);
+                    if (t == OT - 1) tc::mma_commit(empty_b + s);
+                    if (t == OT - 1 && kb == num_kb - 1) tc::mma_commit(accum_bar);
+                }
+                __syncwarp();
+            }
+        }
+        tc::tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == TC_PRODUCER_WARPS) {
+        tc::tc_fence_after();
+        tc::tmem_dealloc<512>(tmem_base);
+    }
+}
+
 // dW[i] = sum_s ws[s][i]
 __global__ void reduce_splits_kernel(const float* __restrict__ ws, float* __restrict__ dst, int n, int splits) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1911,6 +2158,7 @@ __global__ void colsum_part_kernel(const float* __restrict__ dout, float* __rest
 }
 
 static int g_tc_bw_ot = 0;                 // debug: force the output tiles per CTA of the weight gradient (0 = heuristic)
+static int g_tc_bw_tmem_a = 1;             // debug: 0 = the weight-gradient kernel with both operands in shared memory
 static int bw_ot(int Cout) {
     if (g_tc_bw_ot == 1 || g_tc_bw_ot == 2) return g_tc_bw_ot;
     return Cout % 256 == 0 ? 2 : 1;
@@ -2007,6 +2255,7 @@ extern "C" int mcnn_meshconv_fwd_tc_sk(const float* x, const int32_t* gemm, cons
 }
 
 extern "C" int mcnn_debug_set_tc_bw_ot(int ot) { g_tc_bw_ot = (ot == 1 || ot == 2) ? ot : 0; return MCNN_OK; }
+extern "C" int mcnn_debug_set_tc_bw_tmem_a(int on) { g_tc_bw_tmem_a = on ? 1 : 0; return MCNN_OK; }
 
 extern "C" int mcnn_debug_set_tc_bd_tile(int on) { g_tc_bd_tile = on ? 1 : 0; return MCNN_OK; }
 
@@ -2062,7 +2311,19 @@ extern "C" int mcnn_meshconv_bwd_weight_tc(const float* dout, const float* x, co
     const int M = B * E;
     int rows;
     const int S = bw_splits(M, Cin, Cout, &rows);
-    if (bw_ot(Cout) == 2) {
+    if (g_tc_bw_tmem_a) {                                   // A operand in tensor memory (default)
+        if (bw_ot(Cout) == 2) {
+            static DynSmemGuard cfg2;
+            if (int grc = cfg2.ensure(meshconv_bwd_weight_tca_kernel<2>, BwaSmem<2>::TOTAL)) return grc;
+            dim3 grid(S, ceil_div(Cout, 256), Cin / 32);
+            meshconv_bwd_weight_tca_kernel<2><<<grid, TC_THREADS, BwaSmem<2>::TOTAL, st>>>(dout, x, gemm, ec, ws, B, E, Cin, Cout, rows);
+        } else {
+            static DynSmemGuard cfg1;
+            if (int grc = cfg1.ensure(meshconv_bwd_weight_tca_kernel<1>, BwaSmem<1>::TOTAL)) return grc;
+            dim3 grid(S, ceil_div(Cout, 128), Cin / 32);
+            meshconv_bwd_weight_tca_kernel<1><<<grid, TC_THREADS, BwaSmem<1>::TOTAL, st>>>(dout, x, gemm, ec, ws, B, E, Cin, Cout, rows);
+        }
+    } else if (bw_ot(Cout) == 2) {
         static DynSmemGuard configured2;
         if (int grc = configured2.ensure(meshconv_bwd_weight_tc_kernel<2>, BwSmem<2>::TOTAL)) return grc;
         dim3 grid(S, ceil_div(Cout, 256), Cin / 32);

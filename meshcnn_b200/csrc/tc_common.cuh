@@ -180,6 +180,17 @@ __device__ __forceinline__ void tmem_st_16x256b_x4(uint32_t taddr, const float (
         "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
         : "memory");
 }
+// registers -> 32 TMEM lanes x 16 columns, one lane per thread: thread t supplies columns C .. C+15 of lane L + t
+__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const float (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+        "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+        "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+        "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+        : "memory");
+}
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -219,6 +230,11 @@ __device__ __forceinline__ uint64_t make_desc_sw128_mn(uint32_t smem_addr_bytes,
 // kind::tf32, fp32 accumulate, both operands MN-major (bits 15 / 16), M = 128
 __host__ __device__ constexpr uint32_t make_idesc_tf32_mn(int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+// kind::tf32, fp32 accumulate, A K-major (the layout of an A operand held in tensor memory), B MN-major (bit 16), M = 128
+__host__ __device__ constexpr uint32_t make_idesc_tf32_bmn(int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
 // instruction descriptor, kind::tf32, fp32 accumulate, both operands K-major, M = 128

@@ -262,6 +262,36 @@ def test_conv_weight_gradient_two_output_tiles_per_cta(cin, cout, B):
         assert err <= 1e-5, err
 
 
+@pytest.mark.parametrize('cin,cout,B', [(128, 256, 9), (256, 256, 23), (64, 128, 5), (32, 64, 3), (64, 192, 2), (256, 256, 64)])
+def test_conv_weight_gradient_tmem_operand_matches_smem_kernel(cin, cout, B):
+    """Weight-gradient kernel with dout^T held in tensor memory (the default) against the first-generation kernel that keeps
+    both operands in shared memory: the same split of the edge range, the same three TF32 products per term, so the results
+    agree to the rounding of the accumulation order inside the tensor core (<= 1e-6); and both against exact fp32 on the
+    CPU oracle formula at 1e-4."""
+    from meshcnn_b200 import _lib, synth
+    from meshcnn_b200.mesh_conv import MeshConv
+    from tests.gpu_util import DEV, product_mesh
+    meshes = [product_mesh(*synth.make('ico' if s % 3 else 'torus', s, **(dict(nu=5) if s % 3 else dict(m=10, n=25)))) for s in range(B)]
+    torch.manual_seed(cin + cout + B)
+    conv = MeshConv(cin, cout, bias=True).to(DEV)
+    x = torch.randn(B, cin, 750, device=DEV)
+    dy = torch.randn(B, cout, 750, 1, device=DEV)
+    L = _lib.lib()
+    res = []
+    try:
+        for on in (0, 1):
+            L.mcnn_debug_set_tc_bw_tmem_a(on)
+            conv.zero_grad()
+            conv(x, meshes).backward(dy)
+            torch.cuda.synchronize()
+            res.append((conv.conv.weight.grad.clone(), conv.conv.bias.grad.clone()))
+    finally:
+        L.mcnn_debug_set_tc_bw_tmem_a(1)
+    for a, b in zip(res[1], res[0]):
+        err = float((a - b).abs().max() / b.abs().max())
+        assert err <= 2e-6, err
+
+
 @pytest.mark.parametrize('cin,cout,B', [(256, 256, 26), (256, 256, 39), (128, 128, 52), (64, 64, 64)])
 def test_conv_stream_k_at_bench_tile_counts(cin, cout, B):
     """Tile counts just above a multiple of the SM count, as in the bench configuration (153 / 229 / 305 / 375 tiles of
