@@ -683,8 +683,10 @@ __global__ void __launch_bounds__(P::THREADS, 1) pool_collapse_kernel(const mcnn
             }
             return ring_tag;
         };
+        long long t_sel = 0, t_insp = 0, t_chk = 0, t_com = 0, n_alone = 0, n_commit = 0;
         while (ec > T && cstatus == 0) {
             ++round;
+            const long long c0_ = clk ? clock64() : 0;
             // -- select: the next NWARPS unmasked entries of the sorted order, the w-th one for warp w.  Every warp scans the
             //    same entries and gets the same window, so no hand-over is needed. ----------------------------------------------
             int my_e = -1, my_pos = -1, found = 0;
@@ -711,6 +713,7 @@ __global__ void __launch_bounds__(P::THREADS, 1) pool_collapse_kernel(const mcnn
                 cstatus = MCNN_ST_QUEUE_EMPTY;
                 break;
             }
+            const long long c1_ = clk ? clock64() : 0;
             // -- inspect (read-only on the mesh state) + reserve the rows a collapse would write ----------------------------------
             const unsigned my_tag = (round << 5) | (unsigned)(31 - wid);
             int verdict = 0;
@@ -788,6 +791,7 @@ __global__ void __launch_bounds__(P::THREADS, 1) pool_collapse_kernel(const mcnn
             }
             if (lane == 0) { ctl.verdict[wid] = verdict; ctl.pos[wid] = my_pos; }
             __syncthreads();
+            const long long c2_ = clk ? clock64() : 0;
             // -- check: does anything this candidate read, or will write, belong to an earlier member of the window? --------------
             {
                 bool clash = false;
@@ -825,6 +829,7 @@ __global__ void __launch_bounds__(P::THREADS, 1) pool_collapse_kernel(const mcnn
                 if (lane == 0) ctl.ok[wid] = any ? 0 : 1;
             }
             __syncthreads();
+            const long long c3_ = clk ? clock64() : 0;
             // -- the prefix that commits (every thread derives it from the shared verdicts) -------------------------------------
             int k = 0, ec_run = ec, ncol = 0, my_uoff = nunions;
             bool alone_round = false;
@@ -870,9 +875,10 @@ __global__ void __launch_bounds__(P::THREADS, 1) pool_collapse_kernel(const mcnn
                     if (lp && my_pos < a.log_cap) lp[my_pos] = my_e;
                     if (lo && my_pos < a.log_cap) lo[my_pos] = (int8_t)outcome;
                 }
-            } else if ((lp || lo) && wid == NWARPS - 1) {
+            }
+            if (lp || lo) {
                 // the entries between the members were masked when the round began (and stay masked): skipped pops
-                for (int p = cursor + lane; p < new_cursor && p < a.log_cap; p += 32) {
+                for (int p = cursor + tid; p < new_cursor && p < a.log_cap; p += POOL_THREADS) {
                     bool member = false;
                     for (int j = 0; j < k; ++j) member |= ctl.pos[j] == p;
                     if (!member) { if (lp) lp[p] = order[p]; if (lo) lo[p] = MCNN_POP_SKIP_MASKED; }
@@ -880,6 +886,7 @@ __global__ void __launch_bounds__(P::THREADS, 1) pool_collapse_kernel(const mcnn
             }
             if (!alone_round && tid == 0) { ctl.ec = ec_run; ctl.nunions = nunions + 4 * ncol; }
             __syncthreads();
+            if (clk) { const long long c4_ = clock64(); t_sel += c1_ - c0_; t_insp += c2_ - c1_; t_chk += c3_ - c2_; t_com += c4_ - c3_; n_alone += alone_round; n_commit += k; }
             cursor = new_cursor;
             ec = ctl.ec;
             nunions = ctl.nunions;
@@ -890,7 +897,7 @@ __global__ void __launch_bounds__(P::THREADS, 1) pool_collapse_kernel(const mcnn
             if (a.log_nunions) a.log_nunions[b] = nunions;
             s_status = cstatus;
             s_nunions = min(nunions, L.ulog_cap);
-            if (clk) { clk[3] = clock64(); clk[7] = cursor; clk[8] = round; }
+            if (clk) { clk[3] = clock64(); clk[7] = cursor; clk[8] = round; clk[9] = t_sel; clk[10] = t_insp; clk[11] = t_chk; clk[12] = t_com; clk[13] = n_alone; clk[14] = n_commit; }
         }
     }
     __syncthreads();

@@ -77,14 +77,30 @@ def test_reference_networks_on_cuda_layers_match_own_networks():
     assert 'DROPIN-GPU-OK' in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
 
 
+@pytest.fixture()
+def request_cleanup():
+    import shutil
+    paths = []
+    yield paths
+    for p in paths:
+        shutil.rmtree(p, ignore_errors=True)
+
+
 @pytest.mark.parametrize('mode', ['classification', 'segmentation'])
-def test_reference_train_and_test_scripts_run_unchanged(tmp_path, mode):
+def test_reference_train_and_test_scripts_run_unchanged(tmp_path, request_cleanup, mode):
     """python -m meshcnn_b200.dropin <reference>/train.py ... : one epoch with data augmentation on a tiny synthetic dataset,
     checkpoint written; then <reference>/test.py loads it and reports an accuracy."""
+    import shutil
+    import tempfile
     from meshcnn_b200 import synth
     ref = reference_arm.find_reference()
-    data = str(tmp_path / 'data')
-    ckpt = str(tmp_path / 'ckpt')
+    # the reference selects the files of a phase with `root.count(phase) == 1` (data/classification_data.py:56): the dataset
+    # path must not contain the words "train" / "test" itself, which pytest's tmp_path does
+    base = tempfile.mkdtemp(prefix='mcnn_ds_', dir='/tmp')
+    assert 'train' not in base and 'test' not in base
+    request_cleanup.append(base)
+    data = os.path.join(base, 'data')
+    ckpt = os.path.join(base, 'ckpt')
     if mode == 'classification':
         synth.write_classification_dataset(data, classes=2, n_train=4, n_test=2, nu=3)
         flags = ['--ncf', '16', '32', '--pool_res', '200', '150', '--norm', 'group', '--num_groups', '4', '--resblocks', '1',
@@ -103,6 +119,7 @@ def test_reference_train_and_test_scripts_run_unchanged(tmp_path, mode):
                        capture_output=True, text=True, timeout=1200, cwd=str(tmp_path), env=env)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert 'End of epoch 1 / 1' in r.stdout and 'TEST ACC' in r.stdout, r.stdout[-3000:]
+    assert '#training meshes = %d' % (8 if mode == 'classification' else 4) in r.stdout, r.stdout[-3000:]
     assert os.path.exists(os.path.join(ckpt, 'tiny', 'latest_net.pth'))
     sd = torch.load(os.path.join(ckpt, 'tiny', 'latest_net.pth'), map_location='cpu')
     assert any(k.endswith('conv.weight') and v.dim() == 4 and v.shape[-1] == 5 for k, v in sd.items())

@@ -37,6 +37,9 @@ for E, cin, cout in [(750, 64, 64), (600, 64, 128), (600, 128, 128), (450, 128, 
     st = torch.cuda.current_stream().cuda_stream
     call = lambda: L.mcnn_meshconv_bwd_weight_tc(dout.data_ptr(), x.data_ptr(), gemm.data_ptr(), ec.data_ptr(), dw.data_ptr(), db.data_ptr(), ws.data_ptr(), B, E, cin, cout, st)
     res = []
+    for on in (0, 1):                                   # first-generation kernel (both operands in shared memory) vs dout^T in TMEM
+        L.mcnn_debug_set_tc_bw_tmem_a(on)
+        res.append('%s: %.1f' % ('tmem-A' if on else 'smem-A', timeit(call)))
     if cout % 256 == 0:
         for ot in (1, 2):
             L.mcnn_debug_set_tc_bw_ot(ot)
