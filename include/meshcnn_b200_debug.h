@@ -49,6 +49,10 @@ int mcnn_debug_tc_prof(long long* out16_host, int reset);
  * (GroupNorm, InstanceNorm2d) use the fused one-launch form when the mesh's slab fits in shared memory */
 int mcnn_debug_set_norm_fused(int on);
 
+/* diagnostics only: which collapse kernel mcnn_pool_collapse launches for a mesh that fits on chip: 0 (default) = by the size
+ * of the incoming level (sequential up to 1000 edges, rounds above), 1 = always the round kernel, 2 = always the sequential one */
+int mcnn_debug_set_pool_mode(int mode);
+
 #ifdef __cplusplus
 }
 #endif

@@ -35,7 +35,7 @@ namespace mcnn {
 
 // Two instantiations of the same kernel:
 //   Narrow  16-bit ids, state in dynamic shared memory, 256 threads            (meshes up to a few thousand edges)
-//   Wide    32-bit ids, state in a per-mesh global-memory workspace (L2), 1024 threads  (no size limit: 170 k-edge meshes)
+//   Wide    32-bit ids, state in a per-mesh global-memory workspace (L2), 512 threads  (no size limit: 170 k-edge meshes)
 struct Narrow {
     typedef int16_t idx_t;
     typedef uint16_t uidx_t;
@@ -51,7 +51,7 @@ struct Wide {
     typedef unsigned long long pair_t;
     static constexpr unsigned NIL = 0xFFFFFFFFu;
     static constexpr int SHIFT = 32;
-    static constexpr int THREADS = 1024;
+    static constexpr int THREADS = 512;
     static constexpr bool WIDE = true;
 };
 template <class P> __device__ __forceinline__ typename P::pair_t pr_pack(int a, int b) {
@@ -94,7 +94,7 @@ __host__ __device__ inline PoolLayout pool_layout(int n, int V, int ve_cap, bool
     L.slab_next = o; o += sizeof(uidx_t) * (size_t)V; o = align_up(o, 16);
     L.chain_tail = o; o += sizeof(uidx_t) * (size_t)V; o = align_up(o, 16);
     L.vmask = o; o += (size_t)V; o = align_up(o, 16);
-    L.ve = o; o += sizeof(uidx_t) * ((size_t)ve_cap + 2 * (size_t)n); o = align_up(o, 16);   // + room for re-packed lists
+    L.ve = o; o += sizeof(uidx_t) * ((size_t)ve_cap + 3 * (size_t)n); o = align_up(o, 16);   // + room for re-packed lists
     L.eposa = o; o += sizeof(uidx_t) * (size_t)n; o = align_up(o, 16);
     L.eposb = o; o += sizeof(uidx_t) * (size_t)n; o = align_up(o, 16);
     L.ulog_cap = 2 * n + 16;                     // every union's source dies within the same attempt: <= 2 per dead edge
@@ -139,6 +139,23 @@ __device__ __forceinline__ int block_scan_excl(int v, int* scratch, int& total) 
     return res;
 }
 
+
+// One row of the one-ring table with a single load: 4 x int16 as one 64-bit word (Narrow) or 4 x int32 as an int4 (Wide).
+template <class P> struct Row4;
+template <> struct Row4<Narrow> {
+    typedef unsigned long long T;
+    static __device__ __forceinline__ T load(const int16_t* g, int e) { return *reinterpret_cast<const unsigned long long*>(g + 4 * e); }
+    static __device__ __forceinline__ bool neg(T r) { return (r & 0x8000800080008000ULL) != 0ULL; }       // any entry == -1
+    static __device__ __forceinline__ T join(T a, T b) { return a | b; }
+    static __device__ __forceinline__ int get(T r, int j) { return (int)((r >> (16 * j)) & 0xFFFFULL); }  // entry j (non-negative)
+};
+template <> struct Row4<Wide> {
+    typedef int4 T;
+    static __device__ __forceinline__ T load(const int32_t* g, int e) { return *reinterpret_cast<const int4*>(g + 4 * e); }
+    static __device__ __forceinline__ bool neg(T r) { return (r.x | r.y | r.z | r.w) < 0; }
+    static __device__ __forceinline__ T join(T a, T b) { return make_int4(a.x | b.x, a.y | b.y, a.z | b.z, a.w | b.w); }
+    static __device__ __forceinline__ int get(T r, int j) { return j == 0 ? r.x : (j == 1 ? r.y : (j == 2 ? r.z : r.w)); }
+};
 
 // Per-mesh collapse state (shared memory for Narrow, the L2-resident workspace for Wide).
 template <class P>
@@ -277,6 +294,96 @@ __device__ __forceinline__ int warp_one_ring(const PoolState<P>& w, uint16_t* st
     }
     nrset = min(step * 64, POOL_RSET_CAP);
     return over ? -1 : shared;
+}
+
+// The common case of the above: both lists are ONE slab of at most 32 entries (the committing warp re-packs a merged list,
+// so this holds until the spare room runs out).  The two lists are fetched and resolved side by side -- their dependent load
+// chains (descriptor -> entry -> endpoints -> union-find roots) overlap -- and the endpoints stay in registers: a0, b0 /
+// a1, b1 are the roots this lane read through entry `lane` of ve[v0] / ve[v1] (P::NIL: no entry), x0 / x1 the entries.
+// Returns the shared-vertex count, or -1 if the lists do not have that form (the caller takes the general walk).
+template <class P>
+__device__ __forceinline__ int warp_one_ring_fast(const PoolState<P>& w, uint16_t* stamp, unsigned tagA, int lane, int v0, int v1,
+                                                  int& a0, int& b0, int& a1, int& b1, int& start0, int& len0, int& start1, int& len1) {
+    const uint16_t tA = (uint16_t)tagA, tB = (uint16_t)(tagA | 1u);
+    const unsigned lt = (1u << lane) - 1u;
+    const unsigned next0 = (unsigned)w.slab_next[v0], next1 = (unsigned)w.slab_next[v1];
+    start0 = w.slab_start[v0]; len0 = w.slab_len[v0];
+    start1 = w.slab_start[v1]; len1 = w.slab_len[v1];
+    if (next0 != P::NIL || next1 != P::NIL || len0 > 32 || len1 > 32) return -1;
+    const unsigned x0 = (lane < len0) ? (unsigned)w.ve[start0 + lane] : P::NIL;
+    const unsigned x1 = (lane < len1) ? (unsigned)w.ve[start1 + lane] : P::NIL;
+    const typename P::pair_t w0 = w.evp[x0 != P::NIL ? x0 : 0u], w1 = w.evp[x1 != P::NIL ? x1 : 0u];   // unconditional, safe index
+    a0 = pr_lo<P>(w0); b0 = pr_hi<P>(w0); a1 = pr_lo<P>(w1); b1 = pr_hi<P>(w1);
+    {
+        const int ra0 = (int)w.rep[a0], rb0 = (int)w.rep[b0], ra1 = (int)w.rep[a1], rb1 = (int)w.rep[b1];
+        if (ra0 != a0) a0 = uf_find(w.rep, a0);
+        if (rb0 != b0) b0 = uf_find(w.rep, b0);
+        if (ra1 != a1) a1 = uf_find(w.rep, a1);
+        if (rb1 != b1) b1 = uf_find(w.rep, b1);
+    }
+    if (x0 != P::NIL) { stamp[a0] = tA; stamp[b0] = tA; } else { a0 = (int)P::NIL; b0 = (int)P::NIL; }
+    if (x1 == P::NIL) { a1 = (int)P::NIL; b1 = (int)P::NIL; }
+    __syncwarp();
+    // every lane tests its two endpoints; then each hitting (lane, endpoint) writes its own mark over the stamp and the one
+    // mark that survives per vertex counts it: distinct vertices are counted once without a warp-wide match
+    const bool hit_a = (x1 != P::NIL) && a1 != v0 && a1 != v1 && stamp[a1] == tA;
+    const bool hit_b = (x1 != P::NIL) && b1 != v0 && b1 != v1 && stamp[b1] == tA;
+    __syncwarp();
+    const uint16_t mark = (uint16_t)(tagA | 64u | (unsigned)(2 * lane));
+    if (hit_a) stamp[a1] = mark;
+    if (hit_b) stamp[b1] = (uint16_t)(mark | 1u);
+    __syncwarp();
+    const bool win_a = hit_a && stamp[a1] == mark, win_b = hit_b && stamp[b1] == (uint16_t)(mark | 1u);
+    (void)tB; (void)lt;
+    return __popc(__ballot_sync(0xffffffffu, win_a)) + __popc(__ballot_sync(0xffffffffu, win_b));
+}
+
+// The committing warp's re-pack of a list it has just merged, for two single-slab lists (see warp_one_ring_fast): the live
+// entries of the slab of v0, then those of v1, go to fresh room as one slab of v0.  Falls back to the general chain walk.
+template <class P>
+__device__ __forceinline__ void warp_repack_pair(const PoolState<P>& w, int lane, int v0, int start0, int len0, int start1, int len1,
+                                                 int& priv_bump, int priv_end) {
+    typedef typename P::uidx_t uidx_t;
+    const unsigned lt = (1u << lane) - 1u;
+    const unsigned x0 = (lane < len0) ? (unsigned)w.ve[start0 + lane] : P::NIL;
+    const unsigned x1 = (lane < len1) ? (unsigned)w.ve[start1 + lane] : P::NIL;
+    const unsigned m0 = __ballot_sync(0xffffffffu, x0 != P::NIL), m1 = __ballot_sync(0xffffffffu, x1 != P::NIL);
+    const int n0 = __popc(m0), need = n0 + __popc(m1);
+    int out = -1;
+    if (priv_bump + need <= priv_end) {                                          // this warp's own room: no atomics
+        out = priv_bump;
+        priv_bump += need;
+    } else {
+        if (lane == 0) {
+            out = atomicAdd(w.bump, need);
+            if (out + need > w.bump_end) { atomicSub(w.bump, need); out = -1; } // no room left: keep the chain
+        }
+        out = __shfl_sync(0xffffffffu, out, 0);
+        if (out < 0) return;
+    }
+    if (x0 != P::NIL) {
+        const int dst = out + __popc(m0 & lt);
+        w.ve[dst] = (uidx_t)x0;
+        if (x0 != 0u) {
+            if ((int)w.eposa[x0] == start0 + lane) w.eposa[x0] = (uidx_t)dst;
+            else if ((int)w.eposb[x0] == start0 + lane) w.eposb[x0] = (uidx_t)dst;
+        }
+    }
+    if (x1 != P::NIL) {
+        const int dst = out + n0 + __popc(m1 & lt);
+        w.ve[dst] = (uidx_t)x1;
+        if (x1 != 0u) {
+            if ((int)w.eposa[x1] == start1 + lane) w.eposa[x1] = (uidx_t)dst;
+            else if ((int)w.eposb[x1] == start1 + lane) w.eposb[x1] = (uidx_t)dst;
+        }
+    }
+    if (lane == 0) {
+        w.slab_start[v0] = (uidx_t)out;
+        w.slab_len[v0] = (uidx_t)need;
+        w.slab_next[v0] = (uidx_t)P::NIL;
+        w.chain_tail[v0] = (uidx_t)v0;
+    }
+    __syncwarp();
 }
 
 // list.remove(x) on ve[v] (mesh.py:48) by search (one thread): the first occurrence in list order becomes a tombstone.
@@ -501,6 +608,7 @@ struct RoundCtl {                       // shared by the warps of the CTA
     int verdict[POOL_MAX_WARPS];        // INSP_* of the window members, 0 = no member
     int ok[POOL_MAX_WARPS];             // 1 = touches nothing an earlier member writes
     int pos[POOL_MAX_WARPS];            // position of the member in the sorted order (its pop index)
+    unsigned bits[2][4];                // per round parity: members | COLLAPSE verdicts | ALONE verdicts | clash-free members
     int ec, nunions, status, bump;
 };
 
@@ -662,8 +770,9 @@ __global__ void __launch_bounds__(P::THREADS, 1) pool_collapse_kernel(const mcnn
     PoolState<P> S;
     S.gemm = gemm; S.sides = sides; S.mask = mask; S.evp = evp; S.ulog = ulog; S.rep = rep; S.slab_start = slab_start;
     S.slab_len = slab_len; S.slab_next = slab_next; S.chain_tail = chain_tail; S.ve = ve; S.eposa = eposa; S.eposb = eposb;
-    S.vmask = vmask_s; S.vs = vs_s; S.own_e = own_e; S.own_v = own_v; S.bump = &ctl.bump; S.bump_end = a.ve_cap + 2 * E_in;
+    S.vmask = vmask_s; S.vs = vs_s; S.own_e = own_e; S.own_v = own_v; S.bump = &ctl.bump; S.bump_end = a.ve_cap + E_in;
     if (tid == 0) { ctl.ec = n; ctl.nunions = 0; ctl.status = 0; ctl.bump = min(g_ve_ptr[V], a.ve_cap); }
+    if (tid < 8) (&ctl.bits[0][0])[tid] = 0u;
     __syncthreads();
     {
         uint16_t* my_stamp = wstamp + (size_t)wid * V;
@@ -671,19 +780,23 @@ __global__ void __launch_bounds__(P::THREADS, 1) pool_collapse_kernel(const mcnn
         int32_t* lp = a.log_pops ? a.log_pops + (size_t)b * a.log_cap : nullptr;
         int8_t* lo = a.log_outcome ? a.log_outcome + (size_t)b * a.log_cap : nullptr;
         int32_t* lu = a.log_unions ? a.log_unions + (size_t)b * a.log_cap * 8 * 2 : nullptr;
-        unsigned ring_tag = 0;                                   // per warp; tags are (k << 1), k = 1 .. 32766
+        const int priv_size = (2 * E_in) / NWARPS;               // this warp's own room for re-packed lists (see warp_repack_pair)
+        int priv_bump = a.ve_cap + E_in + wid * priv_size;
+        const int priv_end = priv_bump + priv_size;
+        unsigned ring_tag = 0;                                   // per warp; tags are (k << 7), k = 1 .. 510 (low bits: marks)
         unsigned round = 0;
         int ec = n, cursor = 0, nunions = 0, cstatus = 0;
         auto next_ring_tag = [&]() {
-            ring_tag += 2;
-            if (ring_tag >= 65534u) {                             // tags wrapped: clear this warp's stamps
+            ring_tag += 128;
+            if (ring_tag >= 65408u) {                             // tags wrapped: clear this warp's stamps
                 for (int i = lane; i < V; i += 32) my_stamp[i] = 0;
-                ring_tag = 2;
+                ring_tag = 128;
                 __syncwarp();
             }
             return ring_tag;
         };
-        long long t_sel = 0, t_insp = 0, t_chk = 0, t_com = 0, n_alone = 0, n_commit = 0;
+        long long t_sel = 0, t_insp = 0, t_chk = 0, t_com = 0, n_alone = 0, n_commit = 0, t_i1 = 0, t_i2 = 0, t_i3 = 0, t_c1 = 0, t_c2 = 0, t_c3 = 0;
+        long long s_i1 = 0, s_i2 = 0, s_i3 = 0, s_c1 = 0, s_c2 = 0, s_c3 = 0, n_ring = 0, n_ring_fast = 0, n_plain = 0, n_col = 0;
         while (ec > T && cstatus == 0) {
             ++round;
             const long long c0_ = clk ? clock64() : 0;
@@ -717,79 +830,94 @@ __global__ void __launch_bounds__(P::THREADS, 1) pool_collapse_kernel(const mcnn
             // -- inspect (read-only on the mesh state) + reserve the rows a collapse would write ----------------------------------
             const unsigned my_tag = (round << 5) | (unsigned)(31 - wid);
             int verdict = 0;
-            int re[5], nre = 0;                                   // edge rows read
-            int we[9], wv[6];                                     // rows a collapse reads again and writes: edge rows, vertex rows
-            int nrset = 0, v0 = -1, v1 = -1;
+            int nre = 0;                                          // edge rows read: e (+ its four neighbours)
+            int row[4] = {0, 0, 0, 0};
+            int we[4] = {0, 0, 0, 0};                             // besides e and row[]: key_b's far-face neighbours, both sides
+            int wv[4] = {0, 0, 0, 0};                             // besides v0, v1: the endpoints of both key_b
+            int nrset = 0, v0 = 0, v1 = 0;
+            int ra0 = (int)P::NIL, rb0 = (int)P::NIL, ra1 = (int)P::NIL, rb1 = (int)P::NIL;   // roots read through the lists (fast walk)
+            int ls0 = 0, ll0 = 0, ls1 = 0, ll1 = 0;               // the two list slabs (fast walk), for the re-pack at commit
+            bool fast_lists = false, plain = false;              // plain: the nine reserved edge rows are pairwise distinct
+            unsigned sd4 = 0, sdkb[2] = {0, 0};                   // sides rows of e and of both key_b
+            unsigned ep[6] = {0, 0, 0, 0, 0, 0};                  // list positions (eposa, eposb) of key_b (side 0), key_b (side 2), e
             if (my_e >= 0) {
+                typedef Row4<P> RW;
                 const int e = my_e;
-                int row[4], nb[4][4];
-                bool boundary = false;                            // MeshPool.has_boundaries (mesh_pool.py:87-92)
-                re[nre++] = e;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) { row[k] = gemm[4 * e + k]; boundary |= row[k] < 0; }
+                const typename RW::T R = RW::load(gemm, e);       // MeshPool.has_boundaries (mesh_pool.py:87-92)
+                bool boundary = RW::neg(R);
+                nre = 1;
+                typename RW::T N[4];
                 if (!boundary) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        re[nre++] = row[k];
+                    for (int k = 0; k < 4; ++k) row[k] = RW::get(R, k);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) { nb[k][j] = gemm[4 * row[k] + j]; boundary |= nb[k][j] < 0; }
-                    }
+                    for (int k = 0; k < 4; ++k) N[k] = RW::load(gemm, row[k]);
+                    boundary = RW::neg(RW::join(RW::join(N[0], N[1]), RW::join(N[2], N[3])));
+                    nre = 5;
                 }
                 if (boundary) {
                     verdict = INSP_REJ_BOUNDARY;
                 } else {
                     bool alone = false;
-                    int okb[2][2];
+                    sd4 = *reinterpret_cast<const unsigned*>(sides + 4 * e);
 #pragma unroll
                     for (int sd = 0; sd < 2; ++sd) {             // __get_invalids' test (mesh_pool.py:115-121) without its side effects
                         const int side = 2 * sd;
-                        const int sa = sides[4 * e + side], sb = sides[4 * e + side + 1];
-                        const int osa = (sa - (sa & 1) + 2) & 3, osb = (sb - (sb & 1) + 2) & 3;
-                        int oka0 = 0, oka1 = 0, okb0 = 0, okb1 = 0;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {            // (register arrays: compile-time indices only)
-                            if (j == osa) oka0 = nb[side][j];
-                            if (j == osa + 1) oka1 = nb[side][j];
-                            if (j == osb) okb0 = nb[side + 1][j];
-                            if (j == osb + 1) okb1 = nb[side + 1][j];
-                        }
+                        const int sa = (int)((sd4 >> (8 * side)) & 0xFFu), sb = (int)((sd4 >> (8 * side + 8)) & 0xFFu);
+                        const int osa = (sa & 2) ^ 2, osb = (sb & 2) ^ 2;       // == (s - s % 2 + 2) % 4
+                        const int oka0 = RW::get(N[side], osa), oka1 = RW::get(N[side], osa + 1);
+                        const int okb0 = RW::get(N[side + 1], osb), okb1 = RW::get(N[side + 1], osb + 1);
                         alone |= (oka0 == okb0) | (oka0 == okb1) | (oka1 == okb0) | (oka1 == okb1);
-                        okb[sd][0] = okb0; okb[sd][1] = okb1;
+                        we[2 * sd] = okb0; we[2 * sd + 1] = okb1;
                     }
                     edge_ends<P>(evp, rep, e, v0, v1);
                     alone |= v0 == v1;
+                    if (clk) s_i1 = clock64();
                     int ring = 0;
                     if (!alone) {
-                        ring = warp_one_ring<P>(S, my_stamp, next_ring_tag(), lane, v0, v1, my_rset, nrset);
-                        alone = ring < 0;                         // lists too long for the read-set buffer
+                        ring = warp_one_ring_fast<P>(S, my_stamp, next_ring_tag(), lane, v0, v1, ra0, rb0, ra1, rb1, ls0, ll0, ls1, ll1);
+                        fast_lists = ring >= 0;
+                        if (!fast_lists) {
+                            ra0 = rb0 = ra1 = rb1 = (int)P::NIL;
+                            ring = warp_one_ring<P>(S, my_stamp, next_ring_tag(), lane, v0, v1, my_rset, nrset);
+                            alone = ring < 0;                     // lists too long for the read-set buffer
+                        }
                     }
+                    if (clk) s_i2 = clock64();
                     if (alone) {
                         verdict = INSP_ALONE;
                     } else if (ring != 2) {
                         verdict = INSP_REJ_ONE_RING;
                     } else {
                         verdict = INSP_COLLAPSE;
-                        we[0] = e;
-                        we[1] = row[0]; we[2] = row[1]; we[3] = okb[0][0]; we[4] = okb[0][1];
-                        we[5] = row[2]; we[6] = row[3]; we[7] = okb[1][0]; we[8] = okb[1][1];
-                        wv[0] = v0; wv[1] = v1;
-                        edge_ends<P>(evp, rep, row[1], wv[2], wv[3]);     // remove_edge(key_b) edits the lists of key_b's endpoints
-                        edge_ends<P>(evp, rep, row[3], wv[4], wv[5]);
-                        if (lane < 9) {
-                            int x = we[0];
+                        edge_ends<P>(evp, rep, row[1], wv[0], wv[1]);     // remove_edge(key_b) edits the lists of key_b's endpoints
+                        edge_ends<P>(evp, rep, row[3], wv[2], wv[3]);
+                        // reserve: lanes 0..8 the edge rows {e, row[0..3], we[0..3]}, lanes 9..14 the vertex rows {v0, v1, wv[0..3]}
+                        int x = e;
 #pragma unroll
-                            for (int k = 1; k < 9; ++k) if (lane == k) x = we[k];
-                            atomicMax(&own_e[x], my_tag);
-                        } else if (lane < 15) {
-                            int x = wv[0];
-#pragma unroll
-                            for (int k = 1; k < 6; ++k) if (lane == 9 + k) x = wv[k];
-                            atomicMax(&own_v[x], my_tag);
-                        }
+                        for (int k = 0; k < 4; ++k) { if (lane == 1 + k) x = row[k]; if (lane == 5 + k) x = we[k]; if (lane == 11 + k) x = wv[k]; }
+                        if (lane == 9) x = v0;
+                        if (lane == 10) x = v1;
+                        unsigned prev = 0u;
+                        if (lane < 9) prev = atomicMax(&own_e[x], my_tag);
+                        else if (lane < 15) atomicMax(&own_v[x], my_tag);
+                        // two of this candidate's own edge rows coincide (tiny meshes, valence-3 endpoints): general commit path
+                        plain = !__any_sync(0xffffffffu, lane < 9 && prev == my_tag);
+                        sdkb[0] = *reinterpret_cast<const unsigned*>(sides + 4 * row[1]);
+                        sdkb[1] = *reinterpret_cast<const unsigned*>(sides + 4 * row[3]);
+                        ep[0] = eposa[row[1]]; ep[1] = eposb[row[1]]; ep[2] = eposa[row[3]]; ep[3] = eposb[row[3]];
+                        ep[4] = eposa[e]; ep[5] = eposb[e];
                     }
                 }
             }
-            if (lane == 0) { ctl.verdict[wid] = verdict; ctl.pos[wid] = my_pos; }
+            if (clk) s_i3 = clock64();
+            const int par = (int)(round & 1u);
+            if (lane == 0) {
+                ctl.pos[wid] = my_pos;
+                if (verdict != 0) atomicOr(&ctl.bits[par][0], 1u << wid);
+                if (verdict == INSP_COLLAPSE) atomicOr(&ctl.bits[par][1], 1u << wid);
+                if (verdict == INSP_ALONE) atomicOr(&ctl.bits[par][2], 1u << wid);
+            }
             __syncthreads();
             const long long c2_ = clk ? clock64() : 0;
             // -- check: does anything this candidate read, or will write, belong to an earlier member of the window? --------------
@@ -797,52 +925,55 @@ __global__ void __launch_bounds__(P::THREADS, 1) pool_collapse_kernel(const mcnn
                 bool clash = false;
                 auto earlier = [&](unsigned t) { return (t >> 5) == round && (31u - (t & 31u)) < (unsigned)wid; };
                 if (verdict != 0 && verdict != INSP_ALONE) {
-                    if (lane < nre) {
-                        int x = re[0];
+                    // lanes 0..8: edge rows (0..nre-1 read; 5..8 only written); lanes 9..14: vertex rows; every lane: its list roots
+                    int x = my_e;
 #pragma unroll
-                        for (int k = 1; k < 5; ++k) if (lane == k) x = re[k];
-                        clash |= earlier(own_e[x]);
-                    }
-                    if (verdict == INSP_COLLAPSE) {
-                        if (lane >= 5 && lane < 14) {
-                            int x = we[0];
-#pragma unroll
-                            for (int k = 1; k < 9; ++k) if (lane == 5 + k) x = we[k];
-                            clash |= earlier(own_e[x]);
-                        } else if (lane >= 14 && lane < 20) {
-                            int x = wv[0];
-#pragma unroll
-                            for (int k = 1; k < 6; ++k) if (lane == 14 + k) x = wv[k];
-                            clash |= earlier(own_v[x]);
-                        }
-                    }
-                    if (verdict != INSP_REJ_BOUNDARY) {
-                        if (lane == 30) clash |= earlier(own_v[v0]);
-                        if (lane == 31) clash |= earlier(own_v[v1]);
-                        for (int i = lane; i < nrset; i += 32) {
-                            const unsigned x = my_rset[i];
-                            if (x != P::NIL) clash |= earlier(own_v[x]);
+                    for (int k = 0; k < 4; ++k) { if (lane == 1 + k) x = row[k]; if (lane == 5 + k) x = we[k]; if (lane == 11 + k) x = wv[k]; }
+                    if (lane == 9) x = v0;
+                    if (lane == 10) x = v1;
+                    const bool col = verdict == INSP_COLLAPSE, ring_read = verdict != INSP_REJ_BOUNDARY;
+                    if (lane < 9) clash = (lane < nre || col) && earlier(own_e[x]);
+                    else if (lane < 15) clash = (col || (ring_read && lane < 11)) && earlier(own_v[x]);
+                    if (ring_read) {
+                        if (fast_lists) {
+                            const unsigned nil = P::NIL;
+                            const unsigned t0 = own_v[(unsigned)ra0 != nil ? ra0 : 0], t1 = own_v[(unsigned)rb0 != nil ? rb0 : 0];
+                            const unsigned t2 = own_v[(unsigned)ra1 != nil ? ra1 : 0], t3 = own_v[(unsigned)rb1 != nil ? rb1 : 0];
+                            clash |= ((unsigned)ra0 != nil && earlier(t0)) | ((unsigned)rb0 != nil && earlier(t1)) |
+                                     ((unsigned)ra1 != nil && earlier(t2)) | ((unsigned)rb1 != nil && earlier(t3));
+                        } else {
+                            for (int i = lane; i < nrset; i += 32) {
+                                const unsigned xx = my_rset[i];
+                                const unsigned t = own_v[xx != P::NIL ? xx : 0u];
+                                clash |= (xx != P::NIL) && earlier(t);
+                            }
                         }
                     }
                 }
                 const bool any = __any_sync(0xffffffffu, clash);
-                if (lane == 0) ctl.ok[wid] = any ? 0 : 1;
+                if (lane == 0 && !any) atomicOr(&ctl.bits[par][3], 1u << wid);
             }
             __syncthreads();
             const long long c3_ = clk ? clock64() : 0;
-            // -- the prefix that commits (every thread derives it from the shared verdicts) -------------------------------------
-            int k = 0, ec_run = ec, ncol = 0, my_uoff = nunions;
+            // -- the prefix that commits (every thread derives it from the shared verdict masks) ----------------------------------
+            const unsigned b_any = ctl.bits[par][0], b_col = ctl.bits[par][1], b_alone = ctl.bits[par][2], b_ok = ctl.bits[par][3];
+            if (tid < 4) ctl.bits[par ^ 1][tid] = 0u;             // the other parity's words are free since the previous barrier
+            int k, ncol;
             bool alone_round = false;
-            for (int j = 0; j < NWARPS; ++j) {
-                const int vj = ctl.verdict[j];
-                if (vj == 0 || ec_run <= T) break;               // window exhausted / the level is complete (mesh_pool.py:49)
-                if (!ctl.ok[j]) break;
-                if (vj == INSP_ALONE) { if (j == 0) { k = 1; alone_round = true; } break; }
-                if (j == wid) my_uoff = nunions + 4 * ncol;
-                k = j + 1;
-                if (vj == INSP_COLLAPSE) { ec_run -= 3; ++ncol; }
+            if (b_alone & 1u) {                                   // the head of the window has to rewire: it runs alone
+                k = 1; ncol = 0; alone_round = true;
+            } else {
+                const unsigned valid = b_any & b_ok & ~b_alone;   // members that may commit if every earlier one does
+                k = __ffs(~valid) - 1;                            // >= 1: the head has nothing before it to clash with
+                // mesh_pool.py:49: a member is popped only while edges_count > target; every earlier COLLAPSE removed three edges
+                const int budget = (ec - T - 1) / 3;              // most collapses that may precede a member
+                while (k > 1 && __popc(b_col & ((1u << (k - 1)) - 1u)) > budget) --k;
+                ncol = __popc(b_col & ((1u << k) - 1u));
             }
+            const int my_uoff = nunions + 4 * __popc(b_col & ((1u << wid) - 1u));
+            const int ec_run = ec - 3 * ncol;
             const int new_cursor = ctl.pos[k - 1] + 1;            // the pops move just behind the last committed member
+            if (clk) s_c1 = clock64();
             // -- commit ------------------------------------------------------------------------------------------------------------
             if (wid < k) {
                 int outcome = -1, merged = -1;
@@ -860,17 +991,77 @@ __global__ void __launch_bounds__(P::THREADS, 1) pool_collapse_kernel(const mcnn
                     }
                 } else if (verdict == INSP_COLLAPSE) {
                     if (lane == 0) {
-                        Collapse<P> c;
-                        c.st = S; c.gemm = gemm; c.sides = sides; c.mask = mask; c.log_unions = lu; c.union_cap = a.log_cap * 8;
-                        c.nunions = my_uoff; c.ulog_cap = L.ulog_cap; c.ec = ec; c.T = T; c.status = 0;
-                        outcome = c.collapse(my_e, merged);
-                        if (c.status) atomicMax(&ctl.status, c.status);
+                        if (plain && my_uoff + 4 <= L.ulog_cap) {
+                            // __pool_side x 2 + merge_vertices (mesh_pool.py:67-71, :102-113; mesh.py:26-37) for nine distinct rows,
+                            // on the values the inspection read -- nothing has written these rows since -- so this is stores only
+                            const int e = my_e;
+                            bool slow_remove = false;
+#pragma unroll
+                            for (int sd = 0; sd < 2; ++sd) {
+                                const int side = 2 * sd;
+                                const int ka = row[side], kb = row[side + 1], okb0 = we[side], okb1 = we[side + 1];
+                                const int sa = (int)((sd4 >> (8 * side)) & 0xFFu), sb = (int)((sd4 >> (8 * side + 8)) & 0xFFu);
+                                const int osb = (sb & 2) ^ 2, base = sa & 2;
+                                const int s0 = (int)((sdkb[sd] >> (8 * osb)) & 0xFFu), s1 = (int)((sdkb[sd] >> (8 * osb + 8)) & 0xFFu);
+                                gemm[4 * ka + base] = (idx_t)okb0;     gemm[4 * okb0 + s0] = (idx_t)ka;
+                                sides[4 * ka + base] = (int8_t)s0;     sides[4 * okb0 + s0] = (int8_t)base;
+                                gemm[4 * ka + base + 1] = (idx_t)okb1; gemm[4 * okb1 + s1] = (idx_t)ka;
+                                sides[4 * ka + base + 1] = (int8_t)s1; sides[4 * okb1 + s1] = (int8_t)(base + 1);
+                                ulog[my_uoff + side] = pr_pack<P>(kb, ka);          // union(key_b -> key_a), union(e -> key_a)
+                                ulog[my_uoff + side + 1] = pr_pack<P>(e, ka);
+                                if (lu != nullptr && my_uoff + side + 1 < a.log_cap * 8) {
+                                    lu[2 * (my_uoff + side)] = kb; lu[2 * (my_uoff + side) + 1] = ka;
+                                    lu[2 * (my_uoff + side + 1)] = e; lu[2 * (my_uoff + side + 1) + 1] = ka;
+                                }
+                                mask[kb] = 0;
+                                const unsigned ia = ep[2 * sd], ib = ep[2 * sd + 1];      // Mesh.remove_edge(key_b), mesh.py:42-48
+                                if (kb != 0 && ia != P::NIL && ib != P::NIL && (int)ve[ia] == kb && (int)ve[ib] == kb) {
+                                    ve[ia] = (uidx_t)P::NIL; ve[ib] = (uidx_t)P::NIL;
+                                } else {
+                                    slow_remove = true;
+                                    int ea, eb;
+                                    edge_ends<P>(evp, rep, kb, ea, eb);
+                                    if (!list_remove_scan<P>(S, ea, kb) || !list_remove_scan<P>(S, eb, kb)) atomicMax(&ctl.status, MCNN_ST_VE_REMOVE);
+                                }
+                            }
+                            {                                                 // Mesh.merge_vertices(e), mesh.py:26-37
+                                const unsigned ia = ep[4], ib = ep[5];
+                                if (e != 0 && ia != P::NIL && ib != P::NIL && (int)ve[ia] == e && (int)ve[ib] == e) {
+                                    ve[ia] = (uidx_t)P::NIL; ve[ib] = (uidx_t)P::NIL;
+                                } else {
+                                    slow_remove = true;
+                                    if (!list_remove_scan<P>(S, v0, e) || !list_remove_scan<P>(S, v1, e)) atomicMax(&ctl.status, MCNN_ST_VE_REMOVE);
+                                }
+                                if (vs_s != nullptr) {
+#pragma unroll
+                                    for (int q = 0; q < 3; ++q) vs_s[3 * v0 + q] = (vs_s[3 * v0 + q] + vs_s[3 * v1 + q]) / 2;
+                                }
+                                vmask_s[v1] = 0;
+                                slab_next[(unsigned)chain_tail[v0]] = (uidx_t)v1;
+                                chain_tail[v0] = chain_tail[v1];
+                                rep[v1] = (uidx_t)v0;
+                                mask[e] = 0;
+                            }
+                            (void)slow_remove;
+                            merged = v0;
+                            outcome = MCNN_POP_COLLAPSED;
+                        } else {
+                            Collapse<P> c;
+                            c.st = S; c.gemm = gemm; c.sides = sides; c.mask = mask; c.log_unions = lu; c.union_cap = a.log_cap * 8;
+                            c.nunions = my_uoff; c.ulog_cap = L.ulog_cap; c.ec = ec; c.T = T; c.status = 0;
+                            outcome = c.collapse(my_e, merged);
+                            if (c.status) atomicMax(&ctl.status, c.status);
+                        }
                     }
                 } else {
                     outcome = (verdict == INSP_REJ_BOUNDARY) ? MCNN_POP_REJ_BOUNDARY : MCNN_POP_REJ_ONE_RING;
                 }
                 merged = __shfl_sync(0xffffffffu, merged, 0);
-                if (merged >= 0) warp_repack<P>(S, lane, merged);
+                if (clk) s_c2 = clock64();
+                if (merged >= 0) {                               // keep the merged list one slab (see warp_one_ring_fast)
+                    if (!alone_round && fast_lists) warp_repack_pair<P>(S, lane, merged, ls0, ll0, ls1, ll1, priv_bump, priv_end);
+                    else warp_repack<P>(S, lane, merged);
+                }
                 if (lane == 0) {
                     if (lp && my_pos < a.log_cap) lp[my_pos] = my_e;
                     if (lo && my_pos < a.log_cap) lo[my_pos] = (int8_t)outcome;
@@ -885,8 +1076,12 @@ __global__ void __launch_bounds__(P::THREADS, 1) pool_collapse_kernel(const mcnn
                 }
             }
             if (!alone_round && tid == 0) { ctl.ec = ec_run; ctl.nunions = nunions + 4 * ncol; }
+            if (clk) s_c3 = clock64();
             __syncthreads();
-            if (clk) { const long long c4_ = clock64(); t_sel += c1_ - c0_; t_insp += c2_ - c1_; t_chk += c3_ - c2_; t_com += c4_ - c3_; n_alone += alone_round; n_commit += k; }
+            if (clk) { const long long c4_ = clock64(); t_sel += c1_ - c0_; t_insp += c2_ - c1_; t_chk += c3_ - c2_; t_com += c4_ - c3_; n_alone += alone_round; n_commit += k;
+                       if (verdict == INSP_COLLAPSE || verdict == INSP_REJ_ONE_RING) { t_i1 += s_i1 - c1_; t_i2 += s_i2 - s_i1; } t_i3 += s_i3 - c1_;
+                       t_c1 += s_c1 - c3_; t_c2 += s_c2 - s_c1; t_c3 += s_c3 - s_c2;
+                       if (verdict == INSP_COLLAPSE || verdict == INSP_REJ_ONE_RING) { ++n_ring; n_ring_fast += fast_lists; } if (verdict == INSP_COLLAPSE) { ++n_col; n_plain += plain; } }
             cursor = new_cursor;
             ec = ctl.ec;
             nunions = ctl.nunions;
@@ -897,7 +1092,9 @@ __global__ void __launch_bounds__(P::THREADS, 1) pool_collapse_kernel(const mcnn
             if (a.log_nunions) a.log_nunions[b] = nunions;
             s_status = cstatus;
             s_nunions = min(nunions, L.ulog_cap);
-            if (clk) { clk[3] = clock64(); clk[7] = cursor; clk[8] = round; clk[9] = t_sel; clk[10] = t_insp; clk[11] = t_chk; clk[12] = t_com; clk[13] = n_alone; clk[14] = n_commit; }
+            if (clk) { clk[3] = clock64(); clk[7] = cursor; clk[8] = round; clk[9] = t_sel; clk[10] = t_insp; clk[11] = t_chk; clk[12] = t_com; clk[13] = n_alone; clk[14] = n_commit; clk[15] = t_i1; clk[16] = t_i2; clk[17] = t_i3; clk[18] = t_c1; clk[5] = t_c2; clk[6] = t_c3; clk[19 - 19 + 9 + 0] = clk[9]; }
+            if (clk) { a.dbg_clocks[(size_t)b * 24 + 0] = clk[0]; }
+            if (clk) { clk[13] = n_alone * 1000000LL + n_ring * 1000LL + n_ring_fast; clk[14] = n_commit * 1000000LL + n_col * 1000LL + n_plain; }
         }
     }
     __syncthreads();
@@ -1281,7 +1478,17 @@ static int launch_segment(const float* in, float* out, const int32_t* ptr, const
 
 }  // namespace mcnn
 
+namespace mcnn {
+namespace seq { int launch(const mcnn_pool_args* a, size_t* smem_needed, cudaStream_t st, bool query_only); }   // meshpool_seq.cu
+// Below this many edges in the incoming level the sequential kernel is used: the window of the round kernel holds ~2
+// committable candidates on such a mesh, which only pays for the rounds' fixed cost (numbers in meshpool_seq.cu).
+constexpr int POOL_SEQ_MAX_EDGES = 1000;
+static int g_pool_mode = 0;                // debug: 0 = by size, 1 = always the round kernel, 2 = always the sequential kernel (on chip)
+}  // namespace mcnn
+
 using namespace mcnn;
+
+extern "C" int mcnn_debug_set_pool_mode(int mode) { g_pool_mode = (mode == 1 || mode == 2) ? mode : 0; return MCNN_OK; }
 
 extern "C" size_t mcnn_pool_smem_bytes(int E_in, int V, int ve_cap, int with_vs) {
     return pool_layout<Narrow>(E_in, V, ve_cap, with_vs != 0).total + 64;
@@ -1309,6 +1516,7 @@ extern "C" int mcnn_pool_collapse(const mcnn_pool_args* a, void* stream) {
     const size_t smem = pool_layout<Narrow>(a->E_in, a->V, a->ve_cap, a->vs != nullptr).total;
     const bool narrow_ok = a->E_in <= 10900 && a->V <= 32767 && a->ve_cap <= 65535 && smem <= mcnn_pool_smem_limit();   // 16-bit ids on chip
     if (narrow_ok && !(a->workspace != nullptr && a->force_workspace)) {
+        if (g_pool_mode == 2 || (g_pool_mode == 0 && a->E_in <= POOL_SEQ_MAX_EDGES)) return seq::launch(a, nullptr, (cudaStream_t)stream, false);
         static DynSmemGuard configured;
         if (int grc = configured.ensure(pool_collapse_kernel<Narrow>, smem)) return grc;
         pool_collapse_kernel<Narrow><<<a->B, Narrow::THREADS, smem, (cudaStream_t)stream>>>(*a);

@@ -1,0 +1,1045 @@
+// MeshPool collapse, SEQUENTIAL form: one CTA per mesh, thread 0 runs the reference's pop loop one candidate at a time and a
+// helper warp serves the vertex-list walks (the round-1 kernel).  Kept for SMALL meshes only: the round-based kernel in
+// meshpool.cu commits the conflict-free prefix of a window of candidates per round, and on a 750-edge mesh that prefix is
+// ~2 candidates (measured: 2.4 / 1.9 / 1.9 / 1.9 per round on the cubes pool chain) while a round costs ~2x a sequential
+// pop -- break-even.  From ~1000 edges up the window fills (3.9 per round at 2280 edges, ~15 at 170 k) and the round kernel
+// wins (1.5x at 2280 edges, 2.6x at 170 k).  mcnn_pool_collapse picks by the size of the incoming level.  Same results bit
+// for bit (tests/test_pool_gpu.py runs every golden chain through both).
+//
+// Everything below lives in namespace mcnn::seq; the data structures are described in meshpool.cu.
+#include "common.cuh"
+
+namespace mcnn {
+namespace seq {
+
+// Two instantiations of the same kernel:
+//   Narrow  16-bit ids, state in dynamic shared memory, 256 threads            (meshes up to a few thousand edges)
+//   Wide    32-bit ids, state in a per-mesh global-memory workspace (L2), 1024 threads  (no size limit: 170 k-edge meshes)
+struct Narrow {
+    typedef int16_t idx_t;
+    typedef uint16_t uidx_t;
+    typedef uint32_t pair_t;
+    static constexpr unsigned NIL = 0xFFFFu;
+    static constexpr int SHIFT = 16;
+    static constexpr int THREADS = 256;
+    static constexpr bool WIDE = false;
+};
+struct Wide {
+    typedef int32_t idx_t;
+    typedef uint32_t uidx_t;
+    typedef unsigned long long pair_t;
+    static constexpr unsigned NIL = 0xFFFFFFFFu;
+    static constexpr int SHIFT = 32;
+    static constexpr int THREADS = 1024;
+    static constexpr bool WIDE = true;
+};
+template <class P> __device__ __forceinline__ typename P::pair_t pr_pack(int a, int b) {
+    return (typename P::pair_t)(typename P::uidx_t)a | ((typename P::pair_t)(typename P::uidx_t)b << P::SHIFT);
+}
+template <class P> __device__ __forceinline__ int pr_lo(typename P::pair_t w) { return (int)(typename P::uidx_t)w; }
+template <class P> __device__ __forceinline__ int pr_hi(typename P::pair_t w) { return (int)(typename P::uidx_t)(w >> P::SHIFT); }
+
+constexpr int POOL_BFS_CAP = 96;         // members of one MeshUnion row / column walked per thread (implementation limit)
+
+struct PoolLayout {
+    size_t vs, gemm, evp, sides, mask, order, rep, stamp, slab_start, slab_len, slab_next, chain_tail, vmask, ve, eposa, eposb, ulog, cnt32,
+        keys, scan, total;
+    int npow2, ulog_cap;
+};
+
+__host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+template <class P>
+__host__ __device__ inline PoolLayout pool_layout(int n, int V, int ve_cap, bool with_vs) {
+    typedef typename P::idx_t idx_t;
+    typedef typename P::uidx_t uidx_t;
+    typedef typename P::pair_t pair_t;
+    PoolLayout L;
+    size_t o = 0;
+    L.vs = o; o += with_vs ? sizeof(double) * 3 * (size_t)V : 0; o = align_up(o, 16);
+    L.gemm = o; o += sizeof(idx_t) * 4 * (size_t)n; o = align_up(o, 16);          // later: column member pool (u16[3n]) + col_off
+    L.evp = o; o += sizeof(pair_t) * (size_t)n; o = align_up(o, 16);            // evp + sides, later: row member pool (u16[3n]) + ...
+    L.sides = o; o += 4 * (size_t)n; o = align_up(o, 16);
+    L.mask = o; o += (size_t)n; o = align_up(o, 16);
+    L.order = o; o += sizeof(uidx_t) * (size_t)n; o = align_up(o, 16);
+    L.rep = o; o += sizeof(uidx_t) * (size_t)V; o = align_up(o, 16);
+    L.stamp = o; o += sizeof(uint32_t) * (size_t)V; o = align_up(o, 16);
+    L.slab_start = o; o += sizeof(uidx_t) * (size_t)V; o = align_up(o, 16);
+    L.slab_len = o; o += sizeof(uidx_t) * (size_t)V; o = align_up(o, 16);
+    L.slab_next = o; o += sizeof(uidx_t) * (size_t)V; o = align_up(o, 16);
+    L.chain_tail = o; o += sizeof(uidx_t) * (size_t)V; o = align_up(o, 16);
+    L.vmask = o; o += (size_t)V; o = align_up(o, 16);
+    L.ve = o; o += sizeof(uidx_t) * ((size_t)ve_cap + 2 * (size_t)n); o = align_up(o, 16);   // + room for re-packed lists
+    L.eposa = o; o += sizeof(uidx_t) * (size_t)n; o = align_up(o, 16);
+    L.eposb = o; o += sizeof(uidx_t) * (size_t)n; o = align_up(o, 16);
+    L.ulog_cap = 2 * n + 16;                     // every union's source dies within the same attempt: <= 2 per dead edge
+    L.ulog = o; o += sizeof(pair_t) * (size_t)L.ulog_cap; o = align_up(o, 16);
+    L.cnt32 = o; o += sizeof(int) * 2 * (size_t)n; o = align_up(o, 16);           // out-degree, row length / cursor
+    L.npow2 = 0;
+    // the radix-sort ping-pong buffers (2 x (u32 key + id)[n]) are dead before the group evaluation needs occ (int32[n]) +
+    // out0 / out1 (id[n] each), which live in the same place
+    L.keys = o; o += (2 * sizeof(uint32_t) + 2 * sizeof(uidx_t)) * (size_t)n; o = align_up(o, 16);
+    L.scan = o; o += sizeof(int) * 48; o = align_up(o, 16);
+    L.total = o;
+    return L;
+}
+
+// exclusive block scan of one int per thread; returns the prefix and (to all threads) the block total
+template <int NT>
+__device__ __forceinline__ int block_scan_excl(int v, int* scratch, int& total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    if (lane == 31) scratch[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        int w = (lane < NT / 32) ? scratch[lane] : 0;
+        int wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, wi, d);
+            if (lane >= d) wi += t;
+        }
+        scratch[lane] = wi - w;                 // exclusive warp offsets
+        if (lane == 31) scratch[32] = wi;       // block total
+    }
+    __syncthreads();
+    int res = scratch[wid] + incl - v;
+    total = scratch[32];
+    __syncthreads();
+    return res;
+}
+
+
+// The sequential collapse runs on thread 0.  Walks over vertex -> edge lists (the one-ring test, and the rare search for
+// the first occurrence of id 0) are handed to a helper warp (warp 1) through a small shared-memory ring: it walks a list 32
+// entries at a time and the collapse thread waits for the answer.
+template <class P>
+struct WarpCtx {
+    typename P::uidx_t *ve, *slab_start, *slab_len, *slab_next, *chain_tail, *rep, *eposa, *eposb;
+    typename P::pair_t* evp;
+    uint32_t* stamp;
+    int bump, bump_end;        // free room behind the lists (entries), used by wop_repack
+};
+
+enum { WOP_EXIT = 0, WOP_ONE_RING = 1, WOP_REMOVE_SCAN = 2 };
+constexpr int WQ_CAP = 32;
+
+struct WorkQueue {
+    int ent[WQ_CAP][4];       // op, a0, a1, a2
+    int head;                 // entries posted   (written by the collapse thread)
+    int done;                 // entries finished (written by the helper warp)
+    int res;                  // result of the most recent operation
+    int res_seq;              // sequence number (1-based) that `res` belongs to
+};
+
+template <class U>
+__device__ __forceinline__ int uf_find(U* rep, int v) {
+    int p = rep[v];
+    while (p != v) {
+        const int gp = rep[p];
+        rep[v] = (U)gp;                                 // path halving; concurrent lanes only ever write ancestors
+        v = gp;
+        p = rep[v];
+    }
+    return v;
+}
+template <class P>
+__device__ __forceinline__ void edge_ends(const typename P::pair_t* evp, typename P::uidx_t* rep, int e, int& v0, int& v1) {
+    const typename P::pair_t w = evp[e];
+    const int a = pr_lo<P>(w), b = pr_hi<P>(w);
+    const int ra = (int)rep[a], rb = (int)rep[b];                 // both loads in flight before either branch
+    v0 = (ra == a) ? a : uf_find(rep, a);
+    v1 = (rb == b) ? b : uf_find(rep, b);
+}
+
+// A list that has absorbed other lists (`extend`) is a chain of slabs; every later walk pays one dependent round trip per
+// slab.  While the collapse thread waits for a one-ring answer anyway, the helper warp re-packs such a chain into ONE slab in
+// the free room behind the lists: order preserved, tombstones dropped, the positions of the moved entries (epos) updated.
+template <class P>
+__device__ __forceinline__ void wop_repack(WarpCtx<P>& w, int lane, int v) {
+    if ((unsigned)w.slab_next[v] == P::NIL) return;
+    int need = 0;
+    for (unsigned s = (unsigned)v; s != P::NIL; s = (unsigned)w.slab_next[s]) need += (int)w.slab_len[s];
+    if (w.bump + need > w.bump_end) return;                                  // no room left: keep the chain
+    const unsigned lt = (1u << lane) - 1u;
+    const int out = w.bump;
+    int total = 0;
+    for (unsigned s = (unsigned)v; s != P::NIL; s = (unsigned)w.slab_next[s]) {
+        const int start = w.slab_start[s], len = w.slab_len[s];
+        for (int base = 0; base < len; base += 32) {
+            const int i = base + lane;
+            const unsigned x = (i < len) ? (unsigned)w.ve[start + i] : P::NIL;
+            const bool live = x != P::NIL;
+            const unsigned m = __ballot_sync(0xffffffffu, live);
+            if (live) {
+                const int dst = out + total + __popc(m & lt);
+                w.ve[dst] = (typename P::uidx_t)x;
+                if (x != 0u) {
+                    if ((int)w.eposa[x] == start + i) w.eposa[x] = (typename P::uidx_t)dst;
+                    else if ((int)w.eposb[x] == start + i) w.eposb[x] = (typename P::uidx_t)dst;
+                }
+            }
+            total += __popc(m);
+        }
+    }
+    __syncwarp();
+    if (lane == 0) {
+        w.slab_start[v] = (typename P::uidx_t)out;
+        w.slab_len[v] = (typename P::uidx_t)total;
+        w.slab_next[v] = (typename P::uidx_t)P::NIL;
+        w.chain_tail[v] = (typename P::uidx_t)v;
+    }
+    w.bump = out + total;
+    __syncwarp();
+}
+
+// __is_one_ring_valid (mesh_pool.py:95-100); the lists may hold stale / dead edge ids.  stamp[w] = tagA marks w as an
+// endpoint seen from v0; the lane that flips it to tagB counts it once.  The first slab of both lists (the whole list
+// unless a vertex was merged within this level) is fetched and resolved together, so the two dependent load chains overlap.
+template <class P>
+__device__ __forceinline__ int wop_one_ring(WarpCtx<P>& w, int lane, int v0, int v1, uint32_t tagA, long long* hp) {
+    const uint32_t tagB = tagA | 1u;
+#ifdef MCNN_POOL_PROF
+    const long long t0_ = clock64();
+#endif
+    // both lists' descriptors in one round trip; a chained list is re-packed first (rare)
+    if ((unsigned)w.slab_next[v0] != P::NIL) wop_repack<P>(w, lane, v0);
+    if ((unsigned)w.slab_next[v1] != P::NIL) wop_repack<P>(w, lane, v1);
+    const int start0 = w.slab_start[v0], len0 = w.slab_len[v0];
+    const int start1 = w.slab_start[v1], len1 = w.slab_len[v1];
+    const unsigned next0 = (unsigned)w.slab_next[v0], next1 = (unsigned)w.slab_next[v1];
+    const unsigned x0 = (lane < len0) ? (unsigned)w.ve[start0 + lane] : P::NIL;
+    const unsigned x1 = (lane < len1) ? (unsigned)w.ve[start1 + lane] : P::NIL;
+    // the two dependent chains (entry -> endpoints -> union-find roots) run side by side: unconditional loads with a safe index
+    const typename P::pair_t w0 = w.evp[x0 != P::NIL ? x0 : 0u], w1 = w.evp[x1 != P::NIL ? x1 : 0u];
+    int a0 = pr_lo<P>(w0), b0 = pr_hi<P>(w0), a1 = pr_lo<P>(w1), b1 = pr_hi<P>(w1);
+    {
+        const int ra0 = (int)w.rep[a0], rb0 = (int)w.rep[b0], ra1 = (int)w.rep[a1], rb1 = (int)w.rep[b1];
+        if (ra0 != a0) a0 = uf_find(w.rep, a0);
+        if (rb0 != b0) b0 = uf_find(w.rep, b0);
+        if (ra1 != a1) a1 = uf_find(w.rep, a1);
+        if (rb1 != b1) b1 = uf_find(w.rep, b1);
+    }
+    if (x0 != P::NIL) { w.stamp[a0] = tagA; w.stamp[b0] = tagA; }
+#ifdef MCNN_POOL_PROF
+    const long long t1_ = clock64();
+#endif
+    // the rest of the first list: entries 32.. of the first slab, then the slabs linked behind it
+    {
+        unsigned s = (unsigned)v0;
+        int start = start0, len = len0, first = 32;
+        while (true) {
+            for (int i = first + lane; i < len; i += 32) {
+                const unsigned x = w.ve[start + i];
+                if (x == P::NIL) continue;
+                int a, b;
+                edge_ends<P>(w.evp, w.rep, (int)x, a, b);
+                w.stamp[a] = tagA;
+                w.stamp[b] = tagA;
+            }
+            s = (s == (unsigned)v0) ? next0 : (unsigned)(unsigned)w.slab_next[s];
+            if (s == P::NIL) break;
+            start = w.slab_start[s]; len = w.slab_len[s]; first = 0;
+        }
+    }
+    __syncwarp();
+#ifdef MCNN_POOL_PROF
+    const long long t2_ = clock64();
+#endif
+    bool ha = false, hb = false;
+    if (x1 != P::NIL) {
+        if (a1 != v0 && a1 != v1) ha = atomicCAS(&w.stamp[a1], tagA, tagB) == tagA;
+        if (b1 != v0 && b1 != v1) hb = atomicCAS(&w.stamp[b1], tagA, tagB) == tagA;
+    }
+    int shared = __popc(__ballot_sync(0xffffffffu, ha)) + __popc(__ballot_sync(0xffffffffu, hb));
+#ifdef MCNN_POOL_PROF
+    const long long t3_ = clock64();
+    if (lane == 0 && hp) { hp[0] += t1_ - t0_; hp[1] += t2_ - t1_; hp[2] += t3_ - t2_; }
+#endif
+    {
+        unsigned s = (unsigned)v1;
+        int start = start1, len = len1, first = 32;
+        while (true) {
+            for (int base = first; base < len; base += 32) {
+                const int i = base + lane;
+                const unsigned x = (i < len) ? (unsigned)w.ve[start + i] : P::NIL;
+                ha = false; hb = false;
+                if (x != P::NIL) {
+                    int a, b;
+                    edge_ends<P>(w.evp, w.rep, (int)x, a, b);
+                    if (a != v0 && a != v1) ha = atomicCAS(&w.stamp[a], tagA, tagB) == tagA;
+                    if (b != v0 && b != v1) hb = atomicCAS(&w.stamp[b], tagA, tagB) == tagA;
+                }
+                shared += __popc(__ballot_sync(0xffffffffu, ha)) + __popc(__ballot_sync(0xffffffffu, hb));
+            }
+            s = (s == (unsigned)v1) ? next1 : (unsigned)(unsigned)w.slab_next[s];
+            if (s == P::NIL) break;
+            start = w.slab_start[s]; len = w.slab_len[s]; first = 0;
+        }
+    }
+    return shared;
+}
+
+// list.remove(x) on ve[v] (mesh.py:48) by search: the first occurrence in list order becomes a tombstone
+template <class P>
+__device__ __forceinline__ bool wop_list_remove(const WarpCtx<P>& w, int lane, int v, int x) {
+    for (unsigned s = (unsigned)v; s != P::NIL; s = (unsigned)w.slab_next[s]) {
+        const int start = w.slab_start[s], len = w.slab_len[s];
+        for (int base = 0; base < len; base += 32) {
+            const int i = base + lane;
+            const bool hit = (i < len) && ((int)w.ve[start + i] == x);
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            if (m != 0u) {
+                if (lane == __ffs(m) - 1) w.ve[start + i] = (typename P::uidx_t)P::NIL;
+                __syncwarp();
+                return true;
+            }
+        }
+    }
+    return false;
+}
+
+// Service loop of the helper warp: executes the posted operations in order until WOP_EXIT.
+template <class P>
+__device__ void helper_warp_loop(WarpCtx<P>& w, WorkQueue* q, int lane, long long* hprof) {
+    volatile int* vhead = &q->head;
+    int seq = 0;                                             // operations finished so far
+    while (true) {
+        while (*vhead == seq) {}                             // all lanes poll the same word: no divergence
+        __syncwarp();
+        __threadfence_block();
+        volatile int* ep = q->ent[seq % WQ_CAP];
+        int4 rq;
+        rq.x = ep[0]; rq.y = ep[1]; rq.z = ep[2]; rq.w = ep[3];
+        ++seq;
+        if (rq.x == WOP_EXIT) break;
+#ifdef MCNN_POOL_PROF
+        const long long th_ = clock64();
+#endif
+        int r;
+        if (rq.x == WOP_ONE_RING) {
+            r = wop_one_ring<P>(w, lane, rq.y, rq.z, (uint32_t)rq.w, hprof ? hprof + 3 : nullptr);
+        } else {                                             // WOP_REMOVE_SCAN: x leaves ve[a], then ve[b] (mesh.py:42-48)
+            r = wop_list_remove<P>(w, lane, rq.z, rq.y) ? 1 : 0;
+            if (r) r = wop_list_remove<P>(w, lane, rq.w, rq.y) ? 1 : 0;
+        }
+        if (lane == 0) {
+            *(volatile int*)&q->res = r;
+            __threadfence_block();
+            *(volatile int*)&q->res_seq = seq;
+        }
+        __syncwarp();
+        if (lane == 0) { __threadfence_block(); *(volatile int*)&q->done = seq; }
+#ifdef MCNN_POOL_PROF
+        if (lane == 0 && hprof) hprof[rq.x - 1] += clock64() - th_;
+#endif
+    }
+}
+
+// The collapse state as seen by lane 0 of warp 0 (the only thread that runs the reference's control flow).
+template <class P>
+struct Collapse {
+    typedef typename P::idx_t idx_t;
+    typedef typename P::uidx_t uidx_t;
+    typedef typename P::pair_t pair_t;
+    WorkQueue* q;             // list walks go to the helper warp
+    int posted;
+    idx_t* gemm;
+    uidx_t *rep, *slab_next, *chain_tail, *ve, *eposa, *eposb;
+    pair_t *evp, *ulog;
+    int8_t* sides;
+    uint8_t* mask;
+    double* vs;               // shared copy or nullptr
+    uint8_t* vmask;           // shared copy of v_mask
+    int32_t* log_unions;      // global or nullptr
+    int union_cap;
+    int nunions, ulog_cap;
+    int ec, T, status;
+    unsigned stamp_id;
+
+#ifdef MCNN_POOL_PROF
+    long long prof[7] = {0, 0, 0, 0, 0, 0, 0};
+#define PROF_T(i, stmt) { const long long t_ = clock64(); stmt; prof[i] += clock64() - t_; }
+#else
+#define PROF_T(i, stmt) { stmt; }
+#endif
+    __device__ __forceinline__ void ends(int e, int& v0, int& v1) { edge_ends<P>(evp, rep, e, v0, v1); }
+
+    __device__ __forceinline__ void post(int op, int a0, int a1, int a2) {
+        while (posted - *(volatile int*)&q->done >= WQ_CAP) {}
+#ifdef MCNN_POOL_PROF
+        const long long tp_ = clock64();
+#endif
+        volatile int* ep = q->ent[posted % WQ_CAP];
+        ep[0] = op; ep[1] = a0; ep[2] = a1; ep[3] = a2;
+        __threadfence_block();
+        *(volatile int*)&q->head = ++posted;
+#ifdef MCNN_POOL_PROF
+        prof[5] += clock64() - tp_;
+#endif
+    }
+
+    // MeshUnion.union (mesh_union.py:11-12) is only logged here; the rows are evaluated after the collapse
+    __device__ __forceinline__ void group_union(int s, int t) {
+        if (log_unions != nullptr && nunions < union_cap) { log_unions[2 * nunions] = s; log_unions[2 * nunions + 1] = t; }
+        if (s == t) status = MCNN_ST_DEGENERATE;
+        if (nunions < ulog_cap) ulog[nunions] = pr_pack<P>(s, t);
+        else status = MCNN_ST_GROUP_OVERFLOW;
+        ++nunions;
+    }
+
+    // MeshPool.has_boundaries (mesh_pool.py:87-92)
+    __device__ bool has_boundaries(int e) const {
+        if (!P::WIDE) {
+            const unsigned long long row = *reinterpret_cast<const unsigned long long*>(gemm + 4 * e);
+            if ((row & 0x8000800080008000ULL) != 0ULL) return true;
+            const unsigned long long r0 = *reinterpret_cast<const unsigned long long*>(gemm + 4 * (int)(row & 0xFFFF));
+            const unsigned long long r1 = *reinterpret_cast<const unsigned long long*>(gemm + 4 * (int)((row >> 16) & 0xFFFF));
+            const unsigned long long r2 = *reinterpret_cast<const unsigned long long*>(gemm + 4 * (int)((row >> 32) & 0xFFFF));
+            const unsigned long long r3 = *reinterpret_cast<const unsigned long long*>(gemm + 4 * (int)((row >> 48) & 0xFFFF));
+            return ((r0 | r1 | r2 | r3) & 0x8000800080008000ULL) != 0ULL;
+        } else {
+            const int4 row = *reinterpret_cast<const int4*>(gemm + 4 * e);
+            if ((row.x | row.y | row.z | row.w) < 0) return true;
+            const int4 r0 = *reinterpret_cast<const int4*>(gemm + 4 * row.x);
+            const int4 r1 = *reinterpret_cast<const int4*>(gemm + 4 * row.y);
+            const int4 r2 = *reinterpret_cast<const int4*>(gemm + 4 * row.z);
+            const int4 r3 = *reinterpret_cast<const int4*>(gemm + 4 * row.w);
+            return ((r0.x | r0.y | r0.z | r0.w | r1.x | r1.y | r1.z | r1.w | r2.x | r2.y | r2.z | r2.w | r3.x | r3.y | r3.z | r3.w) < 0);
+        }
+    }
+
+    struct Face { int ka, kb, sa, sb, osa, osb, oka0, oka1, okb0, okb1; };
+
+    // __get_face_info (mesh_pool.py:160-170)
+    __device__ __forceinline__ Face face_info(int e, int side) const {
+        Face f;
+        f.ka = gemm[4 * e + side];
+        f.kb = gemm[4 * e + side + 1];
+        f.sa = sides[4 * e + side];
+        f.sb = sides[4 * e + side + 1];
+        f.osa = (f.sa - (f.sa & 1) + 2) & 3;
+        f.osb = (f.sb - (f.sb & 1) + 2) & 3;
+        f.oka0 = gemm[4 * f.ka + f.osa];
+        f.oka1 = gemm[4 * f.ka + f.osa + 1];
+        f.okb0 = gemm[4 * f.kb + f.osb];
+        f.okb1 = gemm[4 * f.kb + f.osb + 1];
+        return f;
+    }
+
+    // __redirect_edges (mesh_pool.py:140-145)
+    __device__ __forceinline__ void redirect(int a, int sa, int b, int sb) {
+        gemm[4 * a + sa] = (idx_t)b;
+        gemm[4 * b + sb] = (idx_t)a;
+        sides[4 * a + sa] = (int8_t)sb;
+        sides[4 * b + sb] = (int8_t)sa;
+    }
+
+    __device__ __forceinline__ static int other_side(int s) { return s + 1 - 2 * (s & 1); }
+
+    // __get_invalids (mesh_pool.py:115-138): returns 0 or 3 edges; rewires around a valence-3 vertex
+    __device__ int get_invalids(int e, int side, int& t0, int& t1, int& t2) {
+        const Face f = face_info(e, side);
+        int nsh = 0, mid = 0, ua = 0, ub = 0, usa = 0, usb = 0;
+        // shared items of (oka0, oka1) x (okb0, okb1), first match in the reference's iteration order
+        if (f.oka0 == f.okb0) { if (nsh == 0) { mid = f.oka0; ua = f.oka1; ub = f.okb1; usa = 1; usb = 1; } ++nsh; }
+        if (f.oka0 == f.okb1) { if (nsh == 0) { mid = f.oka0; ua = f.oka1; ub = f.okb0; usa = 1; usb = 0; } ++nsh; }
+        if (f.oka1 == f.okb0) { if (nsh == 0) { mid = f.oka1; ua = f.oka0; ub = f.okb1; usa = 0; usb = 1; } ++nsh; }
+        if (f.oka1 == f.okb1) { if (nsh == 0) { mid = f.oka1; ua = f.oka0; ub = f.okb0; usa = 0; usb = 0; } ++nsh; }
+        if (nsh == 0) return 0;
+        if (nsh != 1) { status = MCNN_ST_SHARED_ASSERT; return 0; }
+        usa = sides[4 * f.ka + f.osa + usa];
+        usb = sides[4 * f.kb + f.osb + usb];
+        redirect(e, side, ua, usa);
+        redirect(e, side + 1, ub, usb);
+        redirect(ua, other_side(usa), ub, other_side(usb));
+        group_union(f.ka, e);
+        group_union(f.kb, e);
+        group_union(f.ka, ua);
+        group_union(mid, ua);
+        group_union(f.kb, ub);
+        group_union(mid, ub);
+        t0 = f.ka; t1 = f.kb; t2 = mid;
+        return 3;
+    }
+
+    // __remove_triplete (mesh_pool.py:172-182): no remove_edge, the ve entries go stale
+    __device__ void remove_triplet(int t0, int t1, int t2) {
+        int a0, a1, b0, b1, c0, c1;
+        ends(t0, a0, a1);
+        ends(t1, b0, b1);
+        ends(t2, c0, c1);
+        mask[t0] = 0; mask[t1] = 0; mask[t2] = 0;
+        ec -= 3;
+        int count = 0, v = -1;
+        if ((a0 == b0 || a0 == b1) && (a0 == c0 || a0 == c1)) { ++count; v = a0; }
+        if (a1 != a0 && (a1 == b0 || a1 == b1) && (a1 == c0 || a1 == c1)) { ++count; v = a1; }
+        if (count != 1) { status = MCNN_ST_VERTEX_ASSERT; return; }
+        vmask[v] = 0;
+    }
+
+    // __clean_side (mesh_pool.py:74-85)
+    __device__ bool clean_side(int e, int side) {
+        if (ec <= T) return false;
+        int t0, t1, t2;
+        int n = get_invalids(e, side, t0, t1, t2);
+        while (n != 0 && ec > T) {
+            if (status) return false;
+            remove_triplet(t0, t1, t2);
+            if (status) return false;
+            if (ec <= T) return false;
+            if (has_boundaries(e)) return false;
+            n = get_invalids(e, side, t0, t1, t2);
+        }
+        return status == 0;
+    }
+
+    __device__ __forceinline__ int wait_result() {
+#ifdef MCNN_POOL_PROF
+        const long long tw_ = clock64();
+#endif
+        while (*(volatile int*)&q->res_seq != posted) {}
+        __threadfence_block();
+#ifdef MCNN_POOL_PROF
+        prof[6] += clock64() - tw_;
+#endif
+        return *(volatile int*)&q->res;
+    }
+
+    // __is_one_ring_valid (mesh_pool.py:95-100), walked by the helper warp.  The answer depends on the vertex lists, the
+    // endpoints and the union-find only -- none of which __clean_side touches -- so it is requested before the side
+    // cleaning and collected after it.
+    __device__ void one_ring_request(int e) {
+        int v0, v1;
+        ends(e, v0, v1);
+        ++stamp_id;
+        post(WOP_ONE_RING, v0, v1, (int)(stamp_id << 1));
+    }
+
+    // Mesh.remove_edge (mesh.py:42-48): both list entries of x become tombstones
+    __device__ void remove_edge(int x) {
+        const unsigned ia = eposa[x], ib = eposb[x];
+        if (x != 0 && ia != P::NIL && ib != P::NIL && (int)ve[ia] == x && (int)ve[ib] == x) {
+            ve[ia] = (uidx_t)P::NIL;
+            ve[ib] = (uidx_t)P::NIL;
+            return;
+        }
+        int a, b;
+        ends(x, a, b);
+        post(WOP_REMOVE_SCAN, x, a, b);
+        if (wait_result() != 1) status = MCNN_ST_VE_REMOVE;
+    }
+
+    // __pool_side (mesh_pool.py:102-113)
+    __device__ void pool_side(int e, int side) { pool_side(e, side, face_info(e, side)); }
+
+    // the same with the face record already fetched (the caller reads it while it waits for the one-ring answer)
+    __device__ void pool_side(int e, int side, const Face f) {
+        (void)side;
+        const int base = f.sa - (f.sa & 1);
+        redirect(f.ka, base, f.okb0, sides[4 * f.kb + f.osb]);
+        redirect(f.ka, base + 1, f.okb1, sides[4 * f.kb + f.osb + 1]);     // read after the first rewiring, as the reference does
+        group_union(f.kb, f.ka);
+        group_union(e, f.ka);
+        mask[f.kb] = 0;
+        remove_edge(f.kb);
+        ec -= 1;
+    }
+
+    // Mesh.merge_vertices (mesh.py:26-37)
+    __device__ void merge_vertices(int e) {
+        remove_edge(e);
+        int v0, v1;
+        ends(e, v0, v1);
+        if (v0 == v1) { status = MCNN_ST_DEGENERATE; return; }
+        if (vs != nullptr) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) vs[3 * v0 + k] = (vs[3 * v0 + k] + vs[3 * v1 + k]) / 2;
+        }
+        vmask[v1] = 0;
+        // ve[v0].extend(ve[v1]) : v1's chain moves behind v0's (ve[v1] is unreachable once every row holding v1 reads v0)
+        slab_next[(unsigned)chain_tail[v0]] = (uidx_t)v1;
+        chain_tail[v0] = chain_tail[v1];
+        rep[v1] = (uidx_t)v0;         // edges[edges == v1] = v0 over every row
+    }
+
+    // __pool_edge (mesh_pool.py:58-72)
+    __device__ int pool_edge(int e) {
+        bool r, side2 = false;
+        PROF_T(0, r = has_boundaries(e));
+        if (r) return MCNN_POP_REJ_BOUNDARY;
+        PROF_T(2, one_ring_request(e));
+        PROF_T(1, r = clean_side(e, 0));
+        if (r) PROF_T(1, r = clean_side(e, 2) ? true : (side2 = true, false));
+        // nothing writes the one-ring tables between here and __pool_side(0): fetch its face record under the wait
+        const Face f0 = r ? face_info(e, 0) : Face();
+        const bool ring_ok = wait_result() == 2;             // always collected: the ring has one result slot
+        if (!r) return side2 ? MCNN_POP_REJ_SIDE2 : MCNN_POP_REJ_SIDE0;
+        if (!ring_ok) return MCNN_POP_REJ_ONE_RING;
+        PROF_T(3, pool_side(e, 0, f0));
+        if (status) return MCNN_POP_COLLAPSED;
+        PROF_T(3, pool_side(e, 2));
+        if (status) return MCNN_POP_COLLAPSED;
+        PROF_T(4, merge_vertices(e); mask[e] = 0);
+        ec -= 1;
+        return MCNN_POP_COLLAPSED;
+    }
+};
+
+template <class P>
+__global__ void __launch_bounds__(P::THREADS, 1) pool_collapse_kernel(const mcnn_pool_args a) {
+    typedef typename P::idx_t idx_t;
+    typedef typename P::uidx_t uidx_t;
+    typedef typename P::pair_t pair_t;
+    constexpr int POOL_THREADS = P::THREADS;
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    unsigned char* smem = P::WIDE ? reinterpret_cast<unsigned char*>(a.workspace) + (size_t)blockIdx.x * a.workspace_stride : dyn_smem;
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int E_in = a.E_in, T = a.T, V = a.V;
+    const int n = a.ec_in[b];                      // rows of the incoming level
+    const bool with_vs = a.vs != nullptr;
+    const PoolLayout L = pool_layout<P>(E_in, V, a.ve_cap, with_vs);
+
+    double* vs_s = with_vs ? reinterpret_cast<double*>(smem + L.vs) : nullptr;
+    idx_t* gemm = reinterpret_cast<idx_t*>(smem + L.gemm);
+    pair_t* evp = reinterpret_cast<pair_t*>(smem + L.evp);
+    int8_t* sides = reinterpret_cast<int8_t*>(smem + L.sides);
+    uint8_t* mask = smem + L.mask;
+    uidx_t* order = reinterpret_cast<uidx_t*>(smem + L.order);
+    uidx_t* rep = reinterpret_cast<uidx_t*>(smem + L.rep);
+    uint32_t* stamp = reinterpret_cast<uint32_t*>(smem + L.stamp);
+    uidx_t* slab_start = reinterpret_cast<uidx_t*>(smem + L.slab_start);
+    uidx_t* slab_len = reinterpret_cast<uidx_t*>(smem + L.slab_len);
+    uidx_t* slab_next = reinterpret_cast<uidx_t*>(smem + L.slab_next);
+    uidx_t* chain_tail = reinterpret_cast<uidx_t*>(smem + L.chain_tail);
+    uint8_t* vmask_s = smem + L.vmask;
+    uidx_t* ve = reinterpret_cast<uidx_t*>(smem + L.ve);
+    uidx_t* eposa = reinterpret_cast<uidx_t*>(smem + L.eposa);
+    uidx_t* eposb = reinterpret_cast<uidx_t*>(smem + L.eposb);
+    pair_t* ulog = reinterpret_cast<pair_t*>(smem + L.ulog);
+    int* scan = reinterpret_cast<int*>(smem + L.scan);
+
+    const int32_t* g_gemm = a.gemm_in + (size_t)b * E_in * 4;
+    const int8_t* g_sides = a.sides_in + (size_t)b * E_in * 4;
+    int32_t* g_edges = a.edges + (size_t)b * a.edges_stride * 2;
+    int32_t* g_ve_ptr = a.ve_ptr + (size_t)b * (V + 1);
+    int32_t* g_ve_idx = a.ve_idx + (size_t)b * a.ve_cap;
+    uint8_t* g_vmask = a.v_mask + (size_t)b * V;
+    double* g_vs = with_vs ? a.vs + (size_t)b * V * 3 : nullptr;
+    const float* g_norms = a.norms + (size_t)b * E_in;
+
+    long long* clk = a.dbg_clocks ? a.dbg_clocks + (size_t)b * 24 : nullptr;
+    if (clk && tid == 0) clk[0] = clock64();
+    // ---- phase A: load -----------------------------------------------------------------------------------
+    for (int i = tid; i < 4 * n; i += POOL_THREADS) {
+        gemm[i] = (idx_t)g_gemm[i];
+        sides[i] = g_sides[i];
+    }
+    for (int i = tid; i < n; i += POOL_THREADS) {
+        evp[i] = pr_pack<P>(g_edges[2 * i], g_edges[2 * i + 1]);
+        mask[i] = 1;
+        eposa[i] = (uidx_t)P::NIL;
+        eposb[i] = (uidx_t)P::NIL;
+    }
+    for (int v = tid; v < V; v += POOL_THREADS) {
+        rep[v] = (uidx_t)v;
+        stamp[v] = 0u;
+        vmask_s[v] = g_vmask[v];
+        const int beg = g_ve_ptr[v], end = g_ve_ptr[v + 1];
+        slab_start[v] = (uidx_t)beg;
+        slab_len[v] = (uidx_t)(end - beg);
+        slab_next[v] = (uidx_t)P::NIL;
+        chain_tail[v] = (uidx_t)v;
+    }
+    {
+        const int nve = min(g_ve_ptr[V], a.ve_cap);
+        for (int i = tid; i < nve; i += POOL_THREADS) ve[i] = (uidx_t)g_ve_idx[i];
+    }
+    if (with_vs)
+        for (int i = tid; i < 3 * V; i += POOL_THREADS) vs_s[i] = g_vs[i];
+    if (clk && tid == 0) clk[1] = clock64();
+    // ---- phase B: sort (norm bits, id) ascending == heapify + heappop order (mesh_pool.py:184-192, F2) ----
+    // Squared norms are non-negative floats: their bit patterns order like unsigned integers.  Stable LSD radix sort, four
+    // 8-bit passes, starting from id order, so that equal norms stay in ascending id order (the heap's tie-break).  Every
+    // warp owns a contiguous chunk of the current sequence; `match.any` ranks equal digits inside a group of 32.
+    {
+        constexpr int NW = POOL_THREADS / 32;
+        __shared__ int s_hist[NW][256];
+        uint32_t* kA = reinterpret_cast<uint32_t*>(smem + L.keys);
+        uint32_t* kB = kA + n;
+        uidx_t* iA = reinterpret_cast<uidx_t*>(kB + n);
+        uidx_t* iB = iA + n;
+        for (int i = tid; i < n; i += POOL_THREADS) { kA[i] = __float_as_uint(g_norms[i]); iA[i] = (uidx_t)i; }
+        const int wid = tid >> 5, lane = tid & 31;
+        const int chunk = ((n + NW - 1) / NW + 31) & ~31;
+        const int cbeg = min(n, wid * chunk), cend = min(n, cbeg + chunk);
+        const unsigned lt = (1u << lane) - 1u;
+        for (int pass = 0; pass < 4; ++pass) {
+            const int shift = pass * 8;
+            for (int i = tid; i < NW * 256; i += POOL_THREADS) (&s_hist[0][0])[i] = 0;
+            __syncthreads();
+            for (int base = cbeg; base < cend; base += 32) {             // count
+                const int i = base + lane;
+                const bool ok = i < cend;
+                const unsigned d = ok ? ((kA[i] >> shift) & 255u) : 256u;
+                const unsigned grp = __match_any_sync(0xffffffffu, d);
+                if (ok && (grp & lt) == 0u) s_hist[wid][d] += __popc(grp);
+            }
+            __syncthreads();
+            // exclusive scan in (digit, warp) order: one thread per digit walks the NW counters, block scan over digit totals
+            {
+                int tot = 0;
+                if (tid < 256)
+                    for (int w = 0; w < NW; ++w) { const int c = s_hist[w][tid]; s_hist[w][tid] = tot; tot += c; }
+                int all;
+                const int pre = block_scan_excl<POOL_THREADS>(tid < 256 ? tot : 0, scan, all);
+                if (tid < 256)
+                    for (int w = 0; w < NW; ++w) s_hist[w][tid] += pre;
+            }
+            __syncthreads();
+            for (int base = cbeg; base < cend; base += 32) {             // scatter, in order
+                const int i = base + lane;
+                const bool ok = i < cend;
+                const uint32_t key = ok ? kA[i] : 0u;
+                const unsigned d = ok ? ((key >> shift) & 255u) : 256u;
+                const unsigned grp = __match_any_sync(0xffffffffu, d);
+                int pos = 0;
+                if (ok) pos = s_hist[wid][d] + __popc(grp & lt);
+                __syncwarp();
+                if (ok && (grp & lt) == 0u) s_hist[wid][d] += __popc(grp);
+                __syncwarp();
+                if (ok) { kB[pos] = key; iB[pos] = iA[i]; }
+            }
+            __syncthreads();
+            uint32_t* tk = kA; kA = kB; kB = tk;
+            uidx_t* ti = iA; iA = iB; iB = ti;
+        }
+        for (int i = tid; i < n; i += POOL_THREADS) order[i] = iA[i];
+    }
+    // where the two list entries of every edge sit (the entry in the slab of its first / second endpoint)
+    for (int v = tid; v < V; v += POOL_THREADS) {
+        const int start = slab_start[v], len = slab_len[v];
+        for (int i = start; i < start + len; ++i) {
+            const int x = ve[i];
+            if (x >= n) continue;
+            const pair_t w = evp[x];
+            if (pr_lo<P>(w) == v) eposa[x] = (uidx_t)i;
+            else if (pr_hi<P>(w) == v) eposb[x] = (uidx_t)i;
+        }
+    }
+    __shared__ int s_status, s_nunions, s_cursor, s_flag, s_ndead;
+    if (tid == 0) { s_cursor = 0; s_flag = 0; s_ndead = 0; }
+    __syncthreads();
+    if (clk && tid == 0) clk[2] = clock64();
+    // ---- phase D: the sequential collapse (mesh_pool.py:41-53) on thread 0; warp 1 serves the list operations ----------
+    __shared__ WorkQueue s_queue;
+    if (tid == 0) { s_queue.head = 0; s_queue.done = 0; s_queue.res = 0; s_queue.res_seq = 0; }
+    __syncthreads();
+    if (tid == 0) {
+        Collapse<P> c;
+        c.q = &s_queue; c.posted = 0;
+        c.gemm = gemm; c.rep = rep; c.slab_next = slab_next; c.chain_tail = chain_tail; c.ve = ve; c.eposa = eposa; c.eposb = eposb;
+        c.evp = evp; c.ulog = ulog;
+        c.sides = sides; c.mask = mask; c.vs = vs_s; c.vmask = vmask_s;
+        c.log_unions = a.log_unions ? a.log_unions + (size_t)b * a.log_cap * 8 * 2 : nullptr;
+        c.union_cap = a.log_cap * 8; c.nunions = 0; c.ulog_cap = L.ulog_cap;
+        c.ec = n; c.T = T; c.status = 0; c.stamp_id = 0;
+        int32_t* lp = a.log_pops ? a.log_pops + (size_t)b * a.log_cap : nullptr;
+        int8_t* lo = a.log_outcome ? a.log_outcome + (size_t)b * a.log_cap : nullptr;
+        int p = 0;
+        while (c.ec > T) {
+            if (p == n) { c.status = MCNN_ST_QUEUE_EMPTY; break; }
+            const int e = order[p];
+            const int outcome = mask[e] ? c.pool_edge(e) : MCNN_POP_SKIP_MASKED;
+            if (lp && p < a.log_cap) lp[p] = e;
+            if (lo && p < a.log_cap) lo[p] = (int8_t)outcome;
+            ++p;
+            if (c.status) break;
+        }
+        c.post(WOP_EXIT, 0, 0, 0);
+        if (a.log_npops) a.log_npops[b] = p;
+        if (a.log_nunions) a.log_nunions[b] = c.nunions;
+        s_status = c.status;
+        s_nunions = min(c.nunions, c.ulog_cap);
+        if (clk) {
+            clk[3] = clock64();
+            clk[7] = p;
+#ifdef MCNN_POOL_PROF
+            for (int i = 0; i < 5; ++i) clk[8 + i] = c.prof[i];
+            clk[5] = c.prof[5];
+            clk[6] = c.prof[6];
+#endif
+        }
+    } else if (tid >= 32 && tid < 64) {
+        WarpCtx<P> w;
+        w.ve = ve; w.slab_start = slab_start; w.slab_len = slab_len; w.slab_next = slab_next; w.chain_tail = chain_tail;
+        w.rep = rep; w.evp = evp; w.stamp = stamp; w.eposa = eposa; w.eposb = eposb;
+        w.bump = min(g_ve_ptr[V], a.ve_cap); w.bump_end = a.ve_cap + 2 * E_in;
+        helper_warp_loop<P>(w, &s_queue, tid - 32, clk ? clk + 13 : nullptr);
+    }
+    __syncthreads();
+    int status = s_status;
+    const int U = s_nunions;
+    // ---- phase E: Mesh.clean (mesh.py:50-71) + group export ---------------------------------------------------
+    // group evaluation scratch: occ / out-adjacency live where the sort keys were
+    int* occ = reinterpret_cast<int*>(smem + L.keys);                       // int32[n]
+    uidx_t* out0 = reinterpret_cast<uidx_t*>(occ + n);                      // [n]
+    uidx_t* out1 = out0 + n;                                                 // [n]
+    int* outdeg = reinterpret_cast<int*>(smem + L.cnt32);                   // int32[n]  (later: column lengths)
+    int* rowlen = outdeg + n;                                                // int32[n]  (row lengths, then fill cursors)
+    for (int i = tid; i < n; i += POOL_THREADS) { occ[i] = 1; outdeg[i] = 0; rowlen[i] = 0; }
+    // E1: survivor ranks; dead -> 0
+    uidx_t* newid = order;
+    int carry = 0, total = 0;
+    for (int base = 0; base < n; base += POOL_THREADS) {
+        const int i = base + tid;
+        const int m = (i < n) ? mask[i] : 0;
+        int tot;
+        const int pre = block_scan_excl<POOL_THREADS>(m, scan, tot);
+        if (i < n) newid[i] = (uidx_t)(m ? carry + pre : 0);
+        carry += tot;
+    }
+    total = carry;
+    __syncthreads();
+    // out-adjacency of the pour DAG: every source has at most two targets
+    for (int k = tid; k < U; k += POOL_THREADS) {
+        const pair_t w = ulog[k];
+        const int s = pr_lo<P>(w);
+        const int slot = atomicAdd(&outdeg[s], 1);
+        if (slot == 0) out0[s] = (uidx_t)pr_hi<P>(w);
+        else if (slot == 1) out1[s] = (uidx_t)pr_hi<P>(w);
+        else s_flag = MCNN_ST_GROUP_OVERFLOW;
+    }
+    if (clk) { __syncthreads(); if (tid == 0) clk[19] = clock64(); }
+    int32_t* o_gemm = a.gemm_out + (size_t)b * T * 4;
+    int8_t* o_sides = a.sides_out + (size_t)b * T * 4;
+    if (total > T) { status = status ? status : MCNN_ST_QUEUE_EMPTY; total = T; }   // only after an aborted collapse
+    // E2: compacted one-ring tables and edge endpoints
+    for (int i = tid; i < n; i += POOL_THREADS) {
+        if (!mask[i]) continue;
+        const int r = newid[i];
+        if (r >= T) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int g = gemm[4 * i + j];
+            o_gemm[4 * r + j] = g < 0 ? -1 : (int)newid[g];
+            o_sides[4 * r + j] = sides[4 * i + j];
+        }
+        const pair_t w = evp[i];
+        int v0 = pr_lo<P>(w), v1 = pr_hi<P>(w);
+        while ((int)rep[v0] != v0) v0 = (int)rep[v0];
+        while ((int)rep[v1] != v1) v1 = (int)rep[v1];
+        g_edges[2 * r] = v0;
+        g_edges[2 * r + 1] = v1;
+    }
+    for (int i = total * 4 + tid; i < T * 4; i += POOL_THREADS) { o_gemm[i] = 0; o_sides[i] = 0; }
+    if (a.edge_mask_out)
+        for (int i = tid; i < E_in; i += POOL_THREADS) a.edge_mask_out[(size_t)b * E_in + i] = (i < n) ? mask[i] : 0;
+    if (with_vs)
+        for (int i = tid; i < 3 * V; i += POOL_THREADS) g_vs[i] = vs_s[i];
+    for (int v = tid; v < V; v += POOL_THREADS) g_vmask[v] = vmask_s[v];
+    if (clk) { __syncthreads(); if (tid == 0) clk[20] = clock64(); }
+    // E3: ve chains -> CSR with re-indexed ids (the list of a merged-away vertex is dropped: nothing can reach it)
+    carry = 0;
+    for (int base = 0; base < V; base += POOL_THREADS) {
+        const int v = base + tid;
+        int len = 0;
+        const bool root = (v < V) && ((int)rep[v] == v);
+        if (root)
+            for (unsigned s = (unsigned)v; s != P::NIL; s = (unsigned)slab_next[s]) {
+                const int start = slab_start[s], sl = slab_len[s];
+                for (int i = 0; i < sl; ++i) len += (ve[start + i] != P::NIL);
+            }
+        int tot;
+        const int pre = block_scan_excl<POOL_THREADS>(len, scan, tot);
+        if (v < V) {
+            int pos = carry + pre;
+            g_ve_ptr[v] = pos;
+            if (root)
+                for (unsigned s = (unsigned)v; s != P::NIL; s = (unsigned)slab_next[s]) {
+                    const int start = slab_start[s], sl = slab_len[s];
+                    for (int i = 0; i < sl; ++i) {
+                        const unsigned x = ve[start + i];
+                        if (x != P::NIL) g_ve_idx[pos++] = newid[x];
+                    }
+                }
+        }
+        carry += tot;
+    }
+    if (tid == 0) g_ve_ptr[V] = carry;
+    __syncthreads();                       // gemm / sides / evp are dead from here on; out-adjacency complete
+    if (clk) { __syncthreads(); if (tid == 0) clk[21] = clock64(); }
+    // E4: MeshUnion.  (a) occurrences = number of paths starting at each edge:  occ[s] = 1 + sum over the pours s -> t of
+    // occ[t].  A target is alive when it is poured into, so the pours form a DAG; sweeping all edges in parallel until
+    // nothing changes reaches its unique fixed point after (depth + 1) rounds.
+    uidx_t* cpool = reinterpret_cast<uidx_t*>(smem + L.gemm);               // [3n] column members, allocated by cursor
+    uidx_t* coff = cpool + 3 * n;                                            // [n]
+    uidx_t* rpool = reinterpret_cast<uidx_t*>(smem + L.evp);                // [<= 3n]: rows at their final CSR offsets
+    int* collen = reinterpret_cast<int*>(smem + L.ve);                      // int32[n]; the ve slabs were exported in E3
+    const int pool_cap = min(a.nnz_cap, 3 * n);
+    for (int round = 0; round <= n; ++round) {
+        int changed = 0;
+        for (int j = tid; j < n; j += POOL_THREADS) {
+            const int d = outdeg[j];
+            if (d == 0) continue;
+            int v = 1 + occ[out0[j]];
+            if (d > 1) v += occ[out1[j]];
+            if (v != occ[j]) { occ[j] = v; changed = 1; }
+        }
+        if (!__syncthreads_or(changed)) break;
+    }
+    if (clk) { __syncthreads(); if (tid == 0) clk[22] = clock64(); }
+    // (b) the CSC column of every old edge: a survivor sits in its own row; a dead edge is walked forward through the DAG
+    // to the surviving rows that contain it.  Dead edges are compacted first so that every thread gets at most a few.
+    uidx_t* deadlist = reinterpret_cast<uidx_t*>(smem + L.ulog);            // [n]; the log is consumed
+    for (int j = tid; j < n; j += POOL_THREADS) {
+        if (mask[j]) {
+            const int nr = newid[j];
+            int rn = 0;
+            if (nr < T) rn = 1;
+            const int off = atomicAdd(&s_cursor, rn);
+            collen[j] = rn;
+            coff[j] = (uidx_t)min((unsigned)off, P::NIL);
+            if (rn && off + rn <= pool_cap) { cpool[off] = (uidx_t)nr; atomicAdd(&rowlen[nr], 1); }
+        } else {
+            deadlist[atomicAdd(&s_ndead, 1)] = (uidx_t)j;
+        }
+    }
+    __syncthreads();
+    {
+        uidx_t q[POOL_BFS_CAP], r[POOL_BFS_CAP];
+        const int ndead = s_ndead;
+        for (int di = tid; di < ndead; di += POOL_THREADS) {
+            const int j = deadlist[di];
+            int rn = 0;
+            {
+                int qn = 1;
+                q[0] = (uidx_t)j;
+                bool over = false;
+                for (int h = 0; h < qn; ++h) {
+                    const int x = q[h];
+                    const int d = min(outdeg[x], 2);
+                    for (int o = 0; o < d; ++o) {
+                        const int t = o ? out1[x] : out0[x];
+                        if (mask[t]) {
+                            const int nr = newid[t];
+                            if (nr >= T) continue;
+                            int k = 0;
+                            while (k < rn && r[k] != nr) ++k;
+                            if (k == rn) { if (rn < POOL_BFS_CAP) r[rn++] = (uidx_t)nr; else over = true; }
+                        } else {
+                            int k = 0;
+                            while (k < qn && q[k] != t) ++k;
+                            if (k == qn) { if (qn < POOL_BFS_CAP) q[qn++] = (uidx_t)t; else over = true; }
+                        }
+                    }
+                }
+                if (over) s_flag = MCNN_ST_GROUP_OVERFLOW;
+                for (int p = 1; p < rn; ++p) {                       // ascending pooled id
+                    const uidx_t v = r[p];
+                    int k = p;
+                    while (k > 0 && r[k - 1] > v) { r[k] = r[k - 1]; --k; }
+                    r[k] = v;
+                }
+            }
+            const int off = atomicAdd(&s_cursor, rn);
+            collen[j] = rn;
+            coff[j] = (uidx_t)min((unsigned)off, P::NIL);
+            if (off + rn <= pool_cap)
+                for (int k = 0; k < rn; ++k) { cpool[off + k] = r[k]; atomicAdd(&rowlen[r[k]], 1); }
+        }
+    }
+    __syncthreads();
+    if (status == 0 && s_flag) status = s_flag;
+    const int nnz = s_cursor;
+    const bool nnz_ok = nnz <= pool_cap;
+    if (!nnz_ok && status == 0) status = MCNN_ST_NNZ_OVERFLOW;
+    if (clk) { __syncthreads(); if (tid == 0) clk[23] = clock64(); }
+    float* o_occ = a.occ + (size_t)b * E_in;
+    for (int i = tid; i < E_in; i += POOL_THREADS) o_occ[i] = (i < n) ? (float)occ[i] : 1.f;
+    int32_t* o_rowptr = a.grp_rowptr + (size_t)b * (T + 1);
+    int32_t* o_cols = a.grp_cols + (size_t)b * a.nnz_cap;
+    int32_t* o_colptr = a.grp_colptr + (size_t)b * (E_in + 1);
+    int32_t* o_rows = a.grp_rows + (size_t)b * a.nnz_cap;
+    // CSC: column pointers + members (already ascending)
+    carry = 0;
+    for (int base = 0; base < n; base += POOL_THREADS) {
+        const int j = base + tid;
+        const int cnt = (j < n) ? collen[j] : 0;
+        int tot;
+        const int pre = block_scan_excl<POOL_THREADS>(cnt, scan, tot);
+        if (j < n) {
+            o_colptr[j] = carry + pre;
+            if (nnz_ok) {
+                const int off = coff[j];
+                for (int k = 0; k < cnt; ++k) o_rows[carry + pre + k] = cpool[off + k];
+            }
+            collen[j] = carry + pre;                    // keep the column start for the row fill below
+        }
+        carry += tot;
+    }
+    for (int i = n + tid; i <= E_in; i += POOL_THREADS) o_colptr[i] = nnz;
+    // CSR: row pointers over the surviving rows, fill through per-row cursors, sort each row, write out
+    carry = 0;
+    for (int base = 0; base < total; base += POOL_THREADS) {
+        const int r = base + tid;
+        const int len = (r < total) ? rowlen[r] : 0;
+        int tot;
+        const int pre = block_scan_excl<POOL_THREADS>(len, scan, tot);
+        if (r < total) {
+            o_rowptr[r] = carry + pre;
+            occ[r] = carry + pre;                       // occ is exported: reuse as row start ...
+            rowlen[r] = carry + pre;                    // ... and rowlen as the fill cursor
+        }
+        carry += tot;
+    }
+    for (int r = total + tid; r <= T; r += POOL_THREADS) o_rowptr[r] = nnz;
+    __syncthreads();
+    if (nnz_ok) {
+        for (int j = tid; j < n; j += POOL_THREADS) {
+            const int off = coff[j];
+            const int cnt = ((j + 1 < n) ? collen[j + 1] : nnz) - collen[j];
+            for (int k = 0; k < cnt; ++k) {
+                const int pos = atomicAdd(&rowlen[cpool[off + k]], 1);
+                rpool[pos] = (uidx_t)j;
+            }
+        }
+        __syncthreads();
+        // every (column j, row r) pair finds the rank of j inside row r and writes it to its sorted place
+        for (int j = tid; j < n; j += POOL_THREADS) {
+            const int off = coff[j];
+            const int cnt = ((j + 1 < n) ? collen[j + 1] : nnz) - collen[j];
+            for (int k = 0; k < cnt; ++k) {
+                const int r = cpool[off + k];
+                const int beg = occ[r], end = rowlen[r];
+                int rank = 0;
+                for (int p = beg; p < end; ++p) rank += (rpool[p] < j);
+                o_cols[beg + rank] = j;
+            }
+        }
+    }
+    if (clk) __syncthreads();
+    if (tid == 0) {
+        a.ec_out[b] = total;
+        a.status[b] = status;
+        if (clk) clk[4] = clock64();
+    }
+}
+int launch(const mcnn_pool_args* a, size_t* smem_needed, cudaStream_t st, bool query_only) {
+    const size_t smem = pool_layout<Narrow>(a->E_in, a->V, a->ve_cap, a->vs != nullptr).total;
+    if (smem_needed) *smem_needed = smem;
+    if (query_only) return MCNN_OK;
+    static DynSmemGuard configured;
+    if (int grc = configured.ensure(pool_collapse_kernel<Narrow>, smem)) return grc;
+    pool_collapse_kernel<Narrow><<<a->B, Narrow::THREADS, smem, st>>>(*a);
+    return after_launch();
+}
+
+}  // namespace seq
+}  // namespace mcnn

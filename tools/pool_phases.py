@@ -39,7 +39,11 @@ for rec in batch.records:
     print('    rounds mean %.1f max %d; pops per round %.2f; collapse phase per round %.2f us' % (
         rounds.mean(), rounds.max(), clk[:, 7].sum() / max(rounds.sum(), 1), (d[:, 2] / np.maximum(rounds, 1)).mean()))
     print('    per round (us): select %.2f | inspect + reserve %.2f | check %.2f | commit %.2f;  rounds that ran one candidate alone: %.1f of %.1f; committed per round %.2f' % (
-        tuple((clk[:, i] / np.maximum(rounds, 1)).mean() / 1.965e3 for i in (9, 10, 11, 12)) + (clk[:, 13].mean(), rounds.mean(), clk[:, 14].sum() / max(rounds.sum(), 1))))
+        tuple((clk[:, i] / np.maximum(rounds, 1)).mean() / 1.965e3 for i in (9, 10, 11, 12)) + ((clk[:, 13] // 1000000).mean(), rounds.mean(), (clk[:, 14] // 1000000).sum() / max(rounds.sum(), 1))))
+    print('      warp 0: one-ring walks %d, of them on single-slab lists %d; COLLAPSE verdicts %d, of them with nine distinct rows %d' % (
+        ((clk[:, 13] // 1000) % 1000).sum(), (clk[:, 13] % 1000).sum(), ((clk[:, 14] // 1000) % 1000).sum(), (clk[:, 14] % 1000).sum()))
+    print('      warp 0, per round (us): inspect = boundary/side tests %.2f + one-ring %.2f (when reached), own work in total %.2f, rest = wait at the barrier;  commit = prefix %.2f + collapse %.2f + re-pack/log %.2f, rest = wait' % tuple(
+        (clk[:, i] / np.maximum(rounds, 1)).mean() / 1.965e3 for i in (15, 16, 17, 18, 5, 6)))
     e = [clk[:, 3]] + [clk[:, i] for i in (19, 20, 21, 22, 23)] + [clk[:, 4]]
     print('    . export: E1+adjacency %.1f | E2 %.1f | E3 %.1f | occ %.1f | BFS columns %.1f | CSC/CSR write %.1f us (mean);  max %s' % (
         tuple(((e[i + 1] - e[i]) / 1.965e3).mean() for i in range(6)) + (' '.join('%.0f' % ((e[i + 1] - e[i]) / 1.965e3).max() for i in range(6)),)))
