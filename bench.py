@@ -434,23 +434,13 @@ def main():
     px = torch.from_numpy(x).to(dev).requires_grad_(True)
     py = torch.from_numpy(labels).to(dev)
 
-    ar_events = []                                                   # per step: (start, before all-reduce, after all-reduce)
-
     def eager_step():
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)] if world > 1 else None
-        if ev:
-            ev[0].record()
         pbatch.reset()
         reducer.zero()
         px.grad = None
         loss = crit(net(px, pmeshes), py)
         loss.backward()
-        if ev:
-            ev[1].record()
         reducer.allreduce()
-        if ev:
-            ev[2].record()
-            ar_events.append(ev)
         opt.step()
 
     for _ in range(2):
@@ -471,24 +461,47 @@ def main():
     recs = profiler.collect()
     eager_ms = sum(a.elapsed_time(b) for a, b in pe)
     del pbatch, pmeshes
-    # where the multi-GPU step loses time: every rank's own compute time up to the all-reduce, and the time it then spends
-    # inside the all-reduce (= NCCL itself + waiting for the slowest rank); gathered from all ranks
+    # where the multi-GPU step loses time, measured on the device: the same step captured once more WITHOUT the all-reduce
+    # node and replayed on every rank by itself (no collective: ranks do not wait for each other) gives each rank's own
+    # critical path; the timed region above gives the step with the collective.
     attribution = None
-    if world > 1 and ar_events:
-        evs_ = ar_events[-k_prof:]
-        comp = sum(e[0].elapsed_time(e[1]) for e in evs_) / len(evs_)
-        wait = sum(e[1].elapsed_time(e[2]) for e in evs_) / len(evs_)
-        mine = torch.tensor([comp, wait], dtype=torch.float64, device=dev)
+    if world > 1 and gs is not None:
+        reducer.enabled = False
+        saved_state = gs._training_state()                            # these replays update with un-reduced gradients: undone below
+        try:
+            gs0 = GraphedTrainStep(net, crit, reducer, opt, [Mesh(data=d, hold_history=hold) for d in datas], x, labels, E, source='device')
+            for _ in range(3):
+                gs0.run()
+            torch.cuda.synchronize()
+            ev0 = []
+            for _ in range(args.steps):
+                flush.fill_(1)
+                ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ea.record()
+                gs0.run()
+                eb.record()
+                ev0.append((ea, eb))
+            torch.cuda.synchronize()
+            own = sum(ea.elapsed_time(eb) for ea, eb in ev0) / len(ev0)
+            gs0.graph = None
+            del gs0
+        finally:
+            reducer.enabled = True
+            gs._restore_training_state(saved_state)
+            torch.cuda.synchronize()
+        mine = torch.tensor([own], dtype=torch.float64, device=dev)
         allr = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(allr, mine)
-        comp_r = [float(t[0]) for t in allr]
-        wait_r = [float(t[1]) for t in allr]
-        attribution = {'compute_ms_per_rank': comp_r, 'allreduce_ms_per_rank': wait_r,
-                       'straggler_ms': max(comp_r) - sum(comp_r) / world,        # the step lasts as long as the slowest rank
-                       'nccl_alone_ms': min(wait_r),                            # the last rank to arrive waits for nobody
-                       'mean_wait_for_slowest_ms': sum(wait_r) / world - min(wait_r),
-                       'note': 'eager steps (kernel-by-kernel launch), CUDA events on each rank; the replayed graph has the same '
-                               'dependency structure: all-reduce after the last gradient kernel'}
+        own_r = [float(t[0]) for t in allr]
+        step_ms = total_ms / args.steps
+        attribution = {'own_step_ms_per_rank': own_r, 'step_ms_with_allreduce': step_ms,
+                       'slowest_rank_ms': max(own_r), 'mean_rank_ms': sum(own_r) / world,
+                       'straggler_ms': max(own_r) - sum(own_r) / world,
+                       'allreduce_and_skew_ms': step_ms - max(own_r),
+                       'note': 'device time (CUDA events) of the step replayed as a graph: per rank without the all-reduce node '
+                               '(ranks run alone) vs the timed region with it.  straggler = slowest rank - mean rank (every '
+                               'rank has other meshes: its pool kernels last as long as its slowest mesh); the rest of the '
+                               'difference to the timed step is the NCCL kernel and the arrival skew it absorbs'}
 
     # ---- end-to-end arm: host buffers in, loss out, every step ------------------------------------------------------
     e2e = None

@@ -36,12 +36,13 @@ class FlatGradReducer:
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         # uneven shards (e.g. 12 meshes on 8 GPUs): weight each rank's mean gradient by its share of the batch
         self.scale = 1.0 / self.world if local_items is None else float(local_items) / float(global_items)
+        self.enabled = True       # False: allreduce() is a no-op (scaling diagnostics: the step's device time without the collective)
 
     def zero(self):
         self.flat.zero_()
 
     def allreduce(self):
-        if self.world == 1 or os.environ.get('MESHCNN_B200_SKIP_ALLREDUCE') == '1':     # the latter: scaling diagnostics only
+        if self.world == 1 or not self.enabled or os.environ.get('MESHCNN_B200_SKIP_ALLREDUCE') == '1':     # the latter two: scaling diagnostics only
             return
         if self.scale != 1.0:
             self.flat.mul_(self.scale)

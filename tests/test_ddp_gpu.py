@@ -76,15 +76,26 @@ def test_nccl_allreduced_gradient_equals_single_process_gradient():
         p.join(120)
         assert p.exitcode == 0
     assert [(r[1], r[2]) for r in res] == [(0, 2), (2, 3)]
-    # single-process truth on GPU 0: the whole batch, CE mean over all (equally many) edges
-    net, datas, x, y, E, B = _net_and_data()
-    dev = torch.device('cuda', 0)
-    net = net.to(dev).train()
-    red = ddp.FlatGradReducer(net)
-    red.zero()
-    out = net(torch.from_numpy(x).to(dev), [Mesh(data=d, hold_history=True) for d in datas])
-    torch.nn.CrossEntropyLoss(ignore_index=-1)(out, torch.from_numpy(y).to(dev)).backward()
-    truth = red.flat.cpu().numpy()
-    scale = float(np.abs(truth).max())
     np.testing.assert_array_equal(res[0][3], res[1][3])                        # every rank holds the same reduced gradient
-    assert float(np.abs(res[0][3] - truth).max()) <= 1e-4 * scale, float(np.abs(res[0][3] - truth).max()) / scale
+    # single-process truth on GPU 0 (a): the same shards, one after the other, combined with the mesh-count weights -- the
+    # same kernels on the same shapes as the ranks ran, so only the order of the atomic scatter-adds and the final fp32 sum
+    # differ: 2e-5;  (b) the whole batch in one forward / backward (CE mean over all, equally many, edges): other split sizes
+    # in the weight-gradient kernels and other summation orders throughout -- the fp32 gradient noise of a network
+    # (tests/test_networks_gpu.py): 2e-3
+    dev = torch.device('cuda', 0)
+
+    def grad_of(lo, hi):
+        net, datas, x, y, E, B = _net_and_data()
+        net = net.to(dev).train()
+        red = ddp.FlatGradReducer(net)
+        red.zero()
+        out = net(torch.from_numpy(x[lo:hi]).to(dev), [Mesh(data=d, hold_history=True) for d in datas[lo:hi]])
+        torch.nn.CrossEntropyLoss(ignore_index=-1)(out, torch.from_numpy(y[lo:hi]).to(dev)).backward()
+        return red.flat.double().cpu().numpy()
+
+    sharded = (2.0 / 3.0) * grad_of(0, 2) + (1.0 / 3.0) * grad_of(2, 3)
+    whole = grad_of(0, 3)
+    scale = float(np.abs(whole).max())
+    got = res[0][3].astype(np.float64)
+    assert float(np.abs(got - sharded).max()) <= 2e-5 * scale, float(np.abs(got - sharded).max()) / scale
+    assert float(np.abs(got - whole).max()) <= 2e-3 * scale, float(np.abs(got - whole).max()) / scale
