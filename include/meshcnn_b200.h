@@ -39,6 +39,15 @@ extern "C" {
 #define MCNN_E_TOO_LARGE 2       /* mesh does not fit the on-chip collapse state and no workspace was given */
 #define MCNN_E_CUDA 3            /* a CUDA runtime call failed (see mcnn_last_cuda_error)               */
 
+/* arithmetic of the tensor-core MeshConv kernels (the `_p` entry points).
+ *   MCNN_PREC_FP32  every product as three TF32 MMAs (a_hi b_hi + a_hi b_lo + a_lo b_hi): fp32 accuracy (~1e-6 relative) -- what the
+ *                   entry points without `_p` do, and the default of the Python layers
+ *   MCNN_PREC_TF32  one TF32 MMA per product (operands rounded to 10 mantissa bits, fp32 accumulate): ~5e-4 relative, inside
+ *                   the 2e-2 tolerance BASELINE.json states for reduced-precision activations; a third of the tensor work and
+ *                   half of the operand traffic.  Opt-in only. */
+#define MCNN_PREC_FP32 0
+#define MCNN_PREC_TF32 1
+
 /* per-mesh status words written by mcnn_pool_collapse (0 = fine).  The Python mirror turns them into the
  * exception the reference would raise (failure row). */
 #define MCNN_ST_OK 0
@@ -97,6 +106,16 @@ int mcnn_meshconv_fwd_tc_signs(const float* x, const int32_t* gemm, const int32_
  * the one-CTA-per-tile kernel by fp32 rounding of that sum only).  sk_ws: mcnn_meshconv_fwd_tc_sk_ws() bytes of device memory,
  * zeroed ONCE by the caller after allocation (the kernel leaves it reusable), not shared by concurrently running launches. */
 size_t mcnn_meshconv_fwd_tc_sk_ws(void);
+/* the same with the arithmetic selectable (MCNN_PREC_*); likewise for the two gradients below */
+int mcnn_meshconv_fwd_tc_sk_p(const float* x, const int32_t* gemm, const int32_t* ec, const float* weight,
+                              const float* bias, float* out, float* wt_ws, int8_t* signs, void* sk_ws, int B, int E, int Cin,
+                              int Cout, int precision, void* stream);
+int mcnn_meshconv_bwd_data_tc_signs_p(const float* dout, const float* x, const int8_t* signs, const int32_t* gemm,
+                                      const int32_t* ec, const float* weight, float* dx, float* wtb_ws, int B, int E,
+                                      int Cin, int Cout, int precision, void* stream);
+int mcnn_meshconv_bwd_weight_tc_p(const float* dout, const float* x, const int32_t* gemm, const int32_t* ec,
+                                  float* dweight, float* dbias, float* ws, int B, int E, int Cin, int Cout,
+                                  int precision, void* stream);
 int mcnn_meshconv_fwd_tc_sk(const float* x, const int32_t* gemm, const int32_t* ec, const float* weight,
                             const float* bias, float* out, float* wt_ws, int8_t* signs, void* sk_ws, int B, int E, int Cin,
                             int Cout, void* stream);

@@ -2,7 +2,7 @@
 MeshUnion, MeshUnpool -- behind the reference's own layer API.  See DESIGN.md."""
 from . import _lib  # noqa: F401
 
-__all__ = ['Mesh', 'MeshBatch', 'MeshConv', 'MeshPool', 'MeshUnpool', 'MeshUnion']
+__all__ = ['Mesh', 'MeshBatch', 'MeshConv', 'MeshPool', 'MeshUnpool', 'MeshUnion', 'set_precision']
 
 
 def __getattr__(name):
@@ -18,6 +18,9 @@ def __getattr__(name):
     if name == 'MeshUnpool':
         from .mesh_unpool import MeshUnpool
         return MeshUnpool
+    if name == 'set_precision':
+        from .functional import set_precision
+        return set_precision
     if name == 'MeshUnion':
         from .mesh_union import MeshUnion
         return MeshUnion

@@ -43,6 +43,9 @@ SIGNATURES = {
     'mcnn_meshconv_fwd_tc_signs': (_c_int, [_c_vp] * 8 + [_c_int] * 4 + [_c_vp]),
     'mcnn_meshconv_fwd_tc_sk_ws': (_c_sz, []),
     'mcnn_meshconv_fwd_tc_sk': (_c_int, [_c_vp] * 9 + [_c_int] * 4 + [_c_vp]),
+    'mcnn_meshconv_fwd_tc_sk_p': (_c_int, [_c_vp] * 9 + [_c_int] * 5 + [_c_vp]),
+    'mcnn_meshconv_bwd_data_tc_signs_p': (_c_int, [_c_vp] * 8 + [_c_int] * 5 + [_c_vp]),
+    'mcnn_meshconv_bwd_weight_tc_p': (_c_int, [_c_vp] * 7 + [_c_int] * 5 + [_c_vp]),
     'mcnn_meshconv_bwd_data_tc_signs': (_c_int, [_c_vp] * 8 + [_c_int] * 4 + [_c_vp]),
     'mcnn_meshconv_bwd_data': (_c_int, [_c_vp] * 6 + [_c_int] * 4 + [_c_vp]),
     'mcnn_meshconv_bwd_weight': (_c_int, [_c_vp] * 6 + [_c_int] * 4 + [_c_vp]),
@@ -83,6 +86,8 @@ DEBUG_SIGNATURES = {
 
 # CTA-pair (tcgen05 cta_group::2) forward kernel for Cout % 256 == 0; MESHCNN_B200_TC_PAIR=0/1 overrides
 TC_PAIR_DEFAULT = int(os.environ.get('MESHCNN_B200_TC_PAIR', '0'))
+
+PREC_FP32, PREC_TF32 = 0, 1                   # MCNN_PREC_* (include/meshcnn_b200.h)
 
 _ERRORS = {1: 'MCNN_E_BADARG', 2: 'MCNN_E_TOO_LARGE', 3: 'MCNN_E_CUDA'}
 _lib = None

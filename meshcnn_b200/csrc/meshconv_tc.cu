@@ -474,7 +474,7 @@ template <int N_TILE>
 __global__ void __launch_bounds__(SK_THREADS, 1)
 meshconv_fwd_tc_sk_kernel(const float* __restrict__ x, const int32_t* __restrict__ gemm, const int32_t* __restrict__ ec,
                           const float* __restrict__ wt, const float* __restrict__ bias, float* __restrict__ out,
-                          int8_t* __restrict__ signs, float* part, int* flags, int B, int E, int Cin, int Cout) {
+                          int8_t* __restrict__ signs, float* part, int* flags, int B, int E, int Cin, int Cout, int one_pass) {
     using S = SkSmem<N_TILE>;
     using SS = SkSmem<N_TILE>;
     constexpr int PW = TC_PRODUCER_WARPS, PT = PW * 32;
@@ -664,10 +664,10 @@ meshconv_fwd_tc_sk_kernel(const float* __restrict__ x, const int32_t* __restrict
                 const int blk = kb % 5;
                 if (tid == 0) {
                     unsigned char* b_hi = smem + s * S::STAGE_BYTES;
-                    tc::mbar_expect_tx(full_bar + s, 2 * S::B_BYTES);
+                    tc::mbar_expect_tx(full_bar + s, one_pass ? S::B_BYTES : 2 * S::B_BYTES);
                     const float* srcw = wt + ((size_t)kb * Cout + n0) * 32;
                     tc::bulk_g2s(b_hi, srcw, S::B_BYTES, full_bar + s);
-                    tc::bulk_g2s(b_hi + S::B_BYTES, srcw + (size_t)Cout * K, S::B_BYTES, full_bar + s);
+                    if (!one_pass) tc::bulk_g2s(b_hi + S::B_BYTES, srcw + (size_t)Cout * K, S::B_BYTES, full_bar + s);
                 }
                 float va[8], vb[8];                              // the 8 K entries of rowA / rowA + 8 owned by this thread
                 if (blk == 0) {
@@ -702,7 +702,7 @@ meshconv_fwd_tc_sk_kernel(const float* __restrict__ x, const int32_t* __restrict
                 }
                 const uint32_t acol = tmem_base + lane_field + SS::A_COL0 + 64u * s;
                 tc::tmem_st_16x256b_x4(acol, hi);
-                tc::tmem_st_16x256b_x4(acol + 32u, lo);
+                if (!one_pass) tc::tmem_st_16x256b_x4(acol + 32u, lo);
                 tc::tmem_wait_st();
                 tc::tc_fence_before();
                 __syncwarp();
@@ -760,8 +760,10 @@ meshconv_fwd_tc_sk_kernel(const float* __restrict__ x, const int32_t* __restrict
                     for (int kk = 0; kk < 4; ++kk) {
                         const uint64_t dbh = tc::make_desc_sw128(b_hi + kk * 32), dbl = tc::make_desc_sw128(b_lo + kk * 32);
                         tc::mma_tf32_ts(acc, a_hi + 8 * kk, dbh, idesc, (kb != ka) || (kk != 0));
-                        tc::mma_tf32_ts(acc, a_hi + 8 * kk, dbl, idesc, 1);
-                        tc::mma_tf32_ts(acc, a_lo + 8 * kk, dbh, idesc, 1);
+                        if (!one_pass) {
+                            tc::mma_tf32_ts(acc, a_hi + 8 * kk, dbl, idesc, 1);
+                            tc::mma_tf32_ts(acc, a_lo + 8 * kk, dbh, idesc, 1);
+                        }
                     }
                     tc::mma_commit(empty_bar + s);
                     if (kb == ke - 1) tc::mma_commit(acc_full + buf);
@@ -1117,7 +1119,7 @@ static int g_tc_bd_tile = 0;               // debug: 1 = one CTA per item for th
 
 template <int N_TILE>
 static int launch_fwd_tc_sk(const float* x, const int32_t* gemm, const int32_t* ec, const float* wt, const float* bias,
-                            float* out, int8_t* signs, void* sk_ws, int B, int E, int Cin, int Cout, cudaStream_t st) {
+                            float* out, int8_t* signs, void* sk_ws, int B, int E, int Cin, int Cout, int one_pass, cudaStream_t st) {
     using S = SkSmem<N_TILE>;
     static DynSmemGuard configured;
     if (int grc = configured.ensure(meshconv_fwd_tc_sk_kernel<N_TILE>, S::TOTAL)) return grc;
@@ -1126,7 +1128,7 @@ static int launch_fwd_tc_sk(const float* x, const int32_t* gemm, const int32_t* 
     if (g_tc_sk_ctas > 0) G = min((long long)g_tc_sk_ctas, total);
     int* flags = reinterpret_cast<int*>(sk_ws);
     float* part = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(sk_ws) + SK_FLAG_BYTES);
-    meshconv_fwd_tc_sk_kernel<N_TILE><<<(int)G, SK_THREADS, S::TOTAL, st>>>(x, gemm, ec, wt, bias, out, signs, part, flags, B, E, Cin, Cout);
+    meshconv_fwd_tc_sk_kernel<N_TILE><<<(int)G, SK_THREADS, S::TOTAL, st>>>(x, gemm, ec, wt, bias, out, signs, part, flags, B, E, Cin, Cout, one_pass);
     return after_launch();
 }
 
@@ -1374,7 +1376,7 @@ __device__ __forceinline__ uint32_t bdp_a_lo_col(uint32_t s) { return s == 0 ? 1
 __global__ void __launch_bounds__(BDP_THREADS, 1)
 meshconv_bwd_data_tc_p_kernel(const float* __restrict__ dout, const int32_t* __restrict__ gemm, const int32_t* __restrict__ ec,
                               const float* __restrict__ wtb, float* __restrict__ dx, const int8_t* __restrict__ signs,
-                              int B, int E, int Cin, int Cout) {
+                              int B, int E, int Cin, int Cout, int one_pass) {
     using S = BdpSmem;
     constexpr int PW = BDP_PRODUCER_WARPS, PT = PW * 32, ET = BDP_EPI_WARPS * 32;
     static_assert(PW == 8, "two producer warps per TMEM lane quarter");
@@ -1484,7 +1486,7 @@ meshconv_bwd_data_tc_p_kernel(const float* __restrict__ dout, const int32_t* __r
                     }
                     const uint32_t lf = lane_field + ((uint32_t)(16 * h) << 16);
                     tc::tmem_st_16x256b_x4(tmem_base + lf + bdp_a_hi_col(s), hi);
-                    tc::tmem_st_16x256b_x4(tmem_base + lf + bdp_a_lo_col(s), lo);
+                    if (!one_pass) tc::tmem_st_16x256b_x4(tmem_base + lf + bdp_a_lo_col(s), lo);
                 }
                 tc::tmem_wait_st();
             }
@@ -1523,8 +1525,10 @@ meshconv_bwd_data_tc_p_kernel(const float* __restrict__ dout, const int32_t* __r
                     for (int kk = 0; kk < ((dbg & 2) ? 0 : 4); ++kk) {
                         const uint64_t dbh = tc::make_desc_sw128(b_hi + kk * 32), dbl = tc::make_desc_sw128(b_lo + kk * 32);
                         tc::mma_tf32_ts(acc, a_hi + 8 * kk, dbh, idesc, (kb | kk) != 0);
-                        tc::mma_tf32_ts(acc, a_hi + 8 * kk, dbl, idesc, 1);
-                        tc::mma_tf32_ts(acc, a_lo + 8 * kk, dbh, idesc, 1);
+                        if (!one_pass) {
+                            tc::mma_tf32_ts(acc, a_hi + 8 * kk, dbl, idesc, 1);
+                            tc::mma_tf32_ts(acc, a_lo + 8 * kk, dbh, idesc, 1);
+                        }
                     }
                     tc::mma_commit(empty_bar + s);
                     if (kb == num_kb - 1) tc::mma_commit(acc_full + buf);
@@ -1907,7 +1911,7 @@ template <int OT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 meshconv_bwd_weight_tca_kernel(const float* __restrict__ dout, const float* __restrict__ x, const int32_t* __restrict__ gemm,
                                const int32_t* __restrict__ ec, float* __restrict__ ws, int B, int E, int Cin, int Cout,
-                               int rows_per_split) {
+                               int rows_per_split, int one_pass) {
     using S = BwaSmem<OT>;
     constexpr int AV = 16 * OT;                              // dout values per thread and K block (OT == 1: half of the edges)
     extern __shared__ unsigned char smem_raw[];
@@ -2006,7 +2010,7 @@ meshconv_bwd_weight_tca_kernel(const float* __restrict__ dout, const float* __re
                     tc::split4(gk[k5], hi, lo);
                     const uint32_t off = tc::sw128_mn_off(bk, k5 * 8 + bq, S::LBO);
                     tc::sts128(b_hi + off, hi);
-                    tc::sts128(b_lo + off, lo);
+                    if (!one_pass) tc::sts128(b_lo + off, lo);
                 }
                 tc::fence_proxy_async_smem();                              // every writer fences its own stores ...
                 __syncwarp();
@@ -2027,7 +2031,7 @@ meshconv_bwd_weight_tca_kernel(const float* __restrict__ dout, const float* __re
 #pragma unroll
                     for (int j = 0; j < 16; ++j) tc::split_tf32(D.av[16 * h + j], hi[j], lo[j]);
                     tc::tmem_st_32x32b_x16(c_hi + 16 * h, hi);
-                    tc::tmem_st_32x32b_x16(c_lo + 16 * h, lo);
+                    if (!one_pass) tc::tmem_st_32x32b_x16(c_lo + 16 * h, lo);
                 }
                 tc::tmem_wait_st();
                 tc::tc_fence_before();
@@ -2108,8 +2112,10 @@ meshconv_bwd_weight_tca_kernel(const float* __restrict__ dout, const float* __re
                     for (int kk = 0; kk < 4; ++kk) {                     // one 8-edge K group per MMA: +1024 bytes in B, +8 columns in A
                         const uint64_t dbh = tc::make_desc_sw128_mn(b_hi + kk * 1024, S::LBO), dbl = tc::make_desc_sw128_mn(b_lo + kk * 1024, S::LBO);
                         tc::mma_tf32_ts(acc, a_hi + 8 * kk, dbh, idesc, (kb | kk) != 0);
-                        tc::mma_tf32_ts(acc, a_hi + 8 * kk, dbl, idesc, 1);
-                        tc::mma_tf32_ts(acc, a_lo + 8 * kk, dbh, idesc, 1);
+                        if (!one_pass) {
+                            tc::mma_tf32_ts(acc, a_hi + 8 * kk, dbl, idesc, 1);
+                            tc::mma_tf32_ts(acc, a_lo + 8 * kk, dbh, idesc, 1);
+                        }
                     }
                     tc::mma_commit(empty_a + slot);
                     if (t == OT - 1) tc::mma_commit(empty_b + s);
@@ -2236,9 +2242,11 @@ extern "C" int mcnn_meshconv_fwd_tc_signs(const float* x, const int32_t* gemm, c
 /* bytes of the stream-K workspace (flags + one partial tile per CTA); the caller zeroes it ONCE after allocating it */
 extern "C" size_t mcnn_meshconv_fwd_tc_sk_ws(void) { return (size_t)SK_FLAG_BYTES + (size_t)2 * SK_MAX_CTAS * TC_M * 256 * sizeof(float); }
 
-extern "C" int mcnn_meshconv_fwd_tc_sk(const float* x, const int32_t* gemm, const int32_t* ec, const float* weight,
-                                       const float* bias, float* out, float* wt_ws, int8_t* signs, void* sk_ws, int B, int E,
-                                       int Cin, int Cout, void* stream) {
+extern "C" int mcnn_meshconv_fwd_tc_sk_p(const float* x, const int32_t* gemm, const int32_t* ec, const float* weight,
+                                         const float* bias, float* out, float* wt_ws, int8_t* signs, void* sk_ws, int B, int E,
+                                         int Cin, int Cout, int precision, void* stream) {
+    if (precision != MCNN_PREC_FP32 && precision != MCNN_PREC_TF32) return MCNN_E_BADARG;
+    const int one_pass = precision == MCNN_PREC_TF32;
     if (!x || !gemm || !ec || !out || !wt_ws || !sk_ws || B <= 0 || E <= 0) return MCNN_E_BADARG;
     if (!mcnn_meshconv_tc_supported(Cin, Cout)) return MCNN_E_BADARG;
     cudaStream_t st = (cudaStream_t)stream;
@@ -2249,9 +2257,15 @@ extern "C" int mcnn_meshconv_fwd_tc_sk(const float* x, const int32_t* gemm, cons
     }
     int nt = (Cout % 256 == 0) ? 256 : ((Cout % 128 == 0) ? 128 : 64);
     if (g_tc_force_ntile && Cout % g_tc_force_ntile == 0) nt = g_tc_force_ntile;
-    if (nt == 256) return launch_fwd_tc_sk<256>(x, gemm, ec, wt_ws, bias, out, signs, sk_ws, B, E, Cin, Cout, st);
-    if (nt == 128) return launch_fwd_tc_sk<128>(x, gemm, ec, wt_ws, bias, out, signs, sk_ws, B, E, Cin, Cout, st);
-    return launch_fwd_tc_sk<64>(x, gemm, ec, wt_ws, bias, out, signs, sk_ws, B, E, Cin, Cout, st);
+    if (nt == 256) return launch_fwd_tc_sk<256>(x, gemm, ec, wt_ws, bias, out, signs, sk_ws, B, E, Cin, Cout, one_pass, st);
+    if (nt == 128) return launch_fwd_tc_sk<128>(x, gemm, ec, wt_ws, bias, out, signs, sk_ws, B, E, Cin, Cout, one_pass, st);
+    return launch_fwd_tc_sk<64>(x, gemm, ec, wt_ws, bias, out, signs, sk_ws, B, E, Cin, Cout, one_pass, st);
+}
+
+extern "C" int mcnn_meshconv_fwd_tc_sk(const float* x, const int32_t* gemm, const int32_t* ec, const float* weight,
+                                       const float* bias, float* out, float* wt_ws, int8_t* signs, void* sk_ws, int B, int E,
+                                       int Cin, int Cout, void* stream) {
+    return mcnn_meshconv_fwd_tc_sk_p(x, gemm, ec, weight, bias, out, wt_ws, signs, sk_ws, B, E, Cin, Cout, MCNN_PREC_FP32, stream);
 }
 
 extern "C" int mcnn_debug_set_tc_bw_ot(int ot) { g_tc_bw_ot = (ot == 1 || ot == 2) ? ot : 0; return MCNN_OK; }
@@ -2268,9 +2282,20 @@ extern "C" int mcnn_meshconv_bwd_data_tc(const float* dout, const float* x, cons
     return mcnn_meshconv_bwd_data_tc_signs(dout, x, nullptr, gemm, ec, weight, dx, wtb_ws, B, E, Cin, Cout, stream);
 }
 
+extern "C" int mcnn_meshconv_bwd_data_tc_signs_p(const float* dout, const float* x, const int8_t* signs, const int32_t* gemm,
+                                                 const int32_t* ec, const float* weight, float* dx, float* wtb_ws, int B, int E,
+                                                 int Cin, int Cout, int precision, void* stream);
 extern "C" int mcnn_meshconv_bwd_data_tc_signs(const float* dout, const float* x, const int8_t* signs, const int32_t* gemm,
                                                const int32_t* ec, const float* weight, float* dx, float* wtb_ws, int B, int E,
                                                int Cin, int Cout, void* stream) {
+    return mcnn_meshconv_bwd_data_tc_signs_p(dout, x, signs, gemm, ec, weight, dx, wtb_ws, B, E, Cin, Cout, MCNN_PREC_FP32, stream);
+}
+extern "C" int mcnn_meshconv_bwd_data_tc_signs_p(const float* dout, const float* x, const int8_t* signs, const int32_t* gemm,
+                                                 const int32_t* ec, const float* weight, float* dx, float* wtb_ws, int B, int E,
+                                                 int Cin, int Cout, int precision, void* stream) {
+    if (precision != MCNN_PREC_FP32 && precision != MCNN_PREC_TF32) return MCNN_E_BADARG;
+    // single-pass TF32 exists in the persistent kernel only (it needs the signs the forward kept)
+    const int one_pass = (precision == MCNN_PREC_TF32 && signs != nullptr && !g_tc_bd_tile) ? 1 : 0;
     if (!dout || (!x && !signs) || !gemm || !ec || !dx || !wtb_ws || B <= 0 || E <= 0) return MCNN_E_BADARG;
     if (!(Cin > 0 && Cin % 32 == 0 && Cout > 0 && Cout % 32 == 0)) return MCNN_E_BADARG;
     cudaStream_t st = (cudaStream_t)stream;
@@ -2287,7 +2312,7 @@ extern "C" int mcnn_meshconv_bwd_data_tc_signs(const float* dout, const float* x
         if (int grc = configured_p.ensure(meshconv_bwd_data_tc_p_kernel, BdpSmem::TOTAL)) return grc;
         const long long items = (long long)ceil_div(B * E, TC_M) * (Cin / 32);
         const int G = (int)min((long long)sm_count(), items);
-        meshconv_bwd_data_tc_p_kernel<<<G, BDP_THREADS, BdpSmem::TOTAL, st>>>(dout, gemm, ec, wtb_ws, dx, signs, B, E, Cin, Cout);
+        meshconv_bwd_data_tc_p_kernel<<<G, BDP_THREADS, BdpSmem::TOTAL, st>>>(dout, gemm, ec, wtb_ws, dx, signs, B, E, Cin, Cout, one_pass);
         return after_launch();
     }
     dim3 grid(ceil_div(B * E, TC_M), Cin / 32);
@@ -2302,9 +2327,19 @@ extern "C" size_t mcnn_meshconv_bwd_weight_tc_ws(int B, int E, int Cin, int Cout
     return (size_t)S * Cout * Cin * 5 + (size_t)COLSUM_PARTS * Cout;
 }
 
+extern "C" int mcnn_meshconv_bwd_weight_tc_p(const float* dout, const float* x, const int32_t* gemm, const int32_t* ec,
+                                             float* dweight, float* dbias, float* ws, int B, int E, int Cin, int Cout,
+                                             int precision, void* stream);
 extern "C" int mcnn_meshconv_bwd_weight_tc(const float* dout, const float* x, const int32_t* gemm, const int32_t* ec,
                                            float* dweight, float* dbias, float* ws, int B, int E, int Cin, int Cout,
                                            void* stream) {
+    return mcnn_meshconv_bwd_weight_tc_p(dout, x, gemm, ec, dweight, dbias, ws, B, E, Cin, Cout, MCNN_PREC_FP32, stream);
+}
+extern "C" int mcnn_meshconv_bwd_weight_tc_p(const float* dout, const float* x, const int32_t* gemm, const int32_t* ec,
+                                             float* dweight, float* dbias, float* ws, int B, int E, int Cin, int Cout,
+                                             int precision, void* stream) {
+    if (precision != MCNN_PREC_FP32 && precision != MCNN_PREC_TF32) return MCNN_E_BADARG;
+    const int one_pass = (precision == MCNN_PREC_TF32 && g_tc_bw_tmem_a) ? 1 : 0;    // single-pass TF32: TMEM-operand kernel only
     if (!dout || !x || !gemm || !ec || !dweight || !ws || B <= 0 || E <= 0) return MCNN_E_BADARG;
     if (!(Cin > 0 && Cin % 32 == 0 && Cout > 0 && Cout % 4 == 0)) return MCNN_E_BADARG;
     cudaStream_t st = (cudaStream_t)stream;
@@ -2316,12 +2351,12 @@ extern "C" int mcnn_meshconv_bwd_weight_tc(const float* dout, const float* x, co
             static DynSmemGuard cfg2;
             if (int grc = cfg2.ensure(meshconv_bwd_weight_tca_kernel<2>, BwaSmem<2>::TOTAL)) return grc;
             dim3 grid(S, ceil_div(Cout, 256), Cin / 32);
-            meshconv_bwd_weight_tca_kernel<2><<<grid, TC_THREADS, BwaSmem<2>::TOTAL, st>>>(dout, x, gemm, ec, ws, B, E, Cin, Cout, rows);
+            meshconv_bwd_weight_tca_kernel<2><<<grid, TC_THREADS, BwaSmem<2>::TOTAL, st>>>(dout, x, gemm, ec, ws, B, E, Cin, Cout, rows, one_pass);
         } else {
             static DynSmemGuard cfg1;
             if (int grc = cfg1.ensure(meshconv_bwd_weight_tca_kernel<1>, BwaSmem<1>::TOTAL)) return grc;
             dim3 grid(S, ceil_div(Cout, 128), Cin / 32);
-            meshconv_bwd_weight_tca_kernel<1><<<grid, TC_THREADS, BwaSmem<1>::TOTAL, st>>>(dout, x, gemm, ec, ws, B, E, Cin, Cout, rows);
+            meshconv_bwd_weight_tca_kernel<1><<<grid, TC_THREADS, BwaSmem<1>::TOTAL, st>>>(dout, x, gemm, ec, ws, B, E, Cin, Cout, rows, one_pass);
         }
     } else if (bw_ot(Cout) == 2) {
         static DynSmemGuard configured2;

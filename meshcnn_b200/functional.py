@@ -19,6 +19,21 @@ USE_SK = os.environ.get('MESHCNN_B200_TC_SK', '1') != '0'
 # bias / gamma / beta gradient kernels write straight into p.grad (the flat gradient bucket) and autograd gets None for them:
 # no AccumulateGrad add kernel per parameter (32 tiny launches per step of the cubes net).  MESHCNN_B200_DIRECT_GRADS=0 disables.
 DIRECT_GRADS = os.environ.get('MESHCNN_B200_DIRECT_GRADS', '1') != '0'
+# Arithmetic of the tensor-core MeshConv kernels.  'fp32' (default): every product as three TF32 MMAs, fp32 accuracy (1e-6).
+# 'tf32': ONE TF32 MMA per product -- operands rounded to 10 mantissa bits, fp32 accumulation, ~5e-4 relative error, well inside
+# the 2e-2 that BASELINE.json allows a reduced-precision path; a third of the tensor work.  Opt-in: MESHCNN_B200_PRECISION=tf32
+# or set_precision('tf32'); never the default, and bench.py reports it beside the fp32 number, not instead of it.
+PRECISION = _lib.PREC_TF32 if os.environ.get('MESHCNN_B200_PRECISION', 'fp32').lower() == 'tf32' else _lib.PREC_FP32
+
+
+def set_precision(name):
+    """'fp32' (3xTF32, the default) or 'tf32' (single-pass TF32) for the tensor-core MeshConv kernels of layers called from now on."""
+    global PRECISION
+    if name not in ('fp32', 'tf32'):
+        raise ValueError("precision must be 'fp32' or 'tf32', got %r" % (name,))
+    PRECISION = _lib.PREC_TF32 if name == 'tf32' else _lib.PREC_FP32
+
+
 _SIDE = {}
 _SK_WS = {}
 STEP_TOKEN = -1          # >= 0 while a step prepared with begin_step() is being enqueued
@@ -116,10 +131,10 @@ class MeshConvFn(torch.autograd.Function):
                 else:
                     wptr, iptr = w.data_ptr(), wt_ws.data_ptr()
                 if USE_SK:
-                    _lib.check(L.mcnn_meshconv_fwd_tc_sk(x.data_ptr(), level.gemm.data_ptr(), level.ec.data_ptr(), wptr,
-                                                         _lib.ptr(bias), out.data_ptr(), iptr, _lib.ptr(signs),
-                                                         _sk_workspace(x.device).data_ptr(), B, E, Cin, Cout,
-                                                         _lib.current_stream()), 'mcnn_meshconv_fwd_tc_sk')
+                    _lib.check(L.mcnn_meshconv_fwd_tc_sk_p(x.data_ptr(), level.gemm.data_ptr(), level.ec.data_ptr(), wptr,
+                                                           _lib.ptr(bias), out.data_ptr(), iptr, _lib.ptr(signs),
+                                                           _sk_workspace(x.device).data_ptr(), B, E, Cin, Cout, PRECISION,
+                                                           _lib.current_stream()), 'mcnn_meshconv_fwd_tc_sk')
                 else:
                     _lib.check(L.mcnn_meshconv_fwd_tc_signs(x.data_ptr(), level.gemm.data_ptr(), level.ec.data_ptr(), wptr,
                                                             _lib.ptr(bias), out.data_ptr(), iptr, _lib.ptr(signs), B, E, Cin, Cout,
@@ -129,6 +144,7 @@ class MeshConvFn(torch.autograd.Function):
                                                _lib.ptr(bias), out.data_ptr(), wt_ws.data_ptr(), B, E, Cin, Cout,
                                                _lib.current_stream()), 'mcnn_meshconv_fwd')
         ctx.save_for_backward(x, w)
+        ctx.prec = PRECISION
         ctx.params = (weight, bias)
         ctx.signs = signs
         ctx.img = img if use_tc else None
@@ -165,9 +181,9 @@ class MeshConvFn(torch.autograd.Function):
             side.wait_stream(main)
             with torch.cuda.stream(side):
                 if use_tc_w:
-                    _lib.check(L.mcnn_meshconv_bwd_weight_tc(dout.data_ptr(), x.data_ptr(), level.gemm.data_ptr(), level.ec.data_ptr(),
-                                                             dw.data_ptr(), _lib.ptr(db), ws.data_ptr(), B, E, Cin, Cout,
-                                                             side.cuda_stream), 'mcnn_meshconv_bwd_weight_tc')
+                    _lib.check(L.mcnn_meshconv_bwd_weight_tc_p(dout.data_ptr(), x.data_ptr(), level.gemm.data_ptr(), level.ec.data_ptr(),
+                                                               dw.data_ptr(), _lib.ptr(db), ws.data_ptr(), B, E, Cin, Cout, ctx.prec,
+                                                               side.cuda_stream), 'mcnn_meshconv_bwd_weight_tc')
                 else:
                     _lib.check(L.mcnn_meshconv_bwd_weight(dout.data_ptr(), x.data_ptr(), level.gemm.data_ptr(), level.ec.data_ptr(),
                                                           dw.data_ptr(), _lib.ptr(db), B, E, Cin, Cout, side.cuda_stream),
@@ -178,9 +194,9 @@ class MeshConvFn(torch.autograd.Function):
                 pre = ctx.img is not None
                 wtb = ctx.img[1] if pre else torch.empty(2 * 5 * Cin, Cout, dtype=torch.float32, device=x.device)
                 with profiler.span('meshconv_bwd_data_tc', B=B, E=E, Cin=Cin, Cout=Cout):
-                    _lib.check(L.mcnn_meshconv_bwd_data_tc_signs(dout.data_ptr(), x.data_ptr(), _lib.ptr(ctx.signs), level.gemm.data_ptr(),
-                                                                 level.ec.data_ptr(), None if pre else w.data_ptr(), dx.data_ptr(),
-                                                                 wtb.data_ptr(), B, E, Cin, Cout, st), 'mcnn_meshconv_bwd_data_tc')
+                    _lib.check(L.mcnn_meshconv_bwd_data_tc_signs_p(dout.data_ptr(), x.data_ptr(), _lib.ptr(ctx.signs), level.gemm.data_ptr(),
+                                                                   level.ec.data_ptr(), None if pre else w.data_ptr(), dx.data_ptr(),
+                                                                   wtb.data_ptr(), B, E, Cin, Cout, ctx.prec, st), 'mcnn_meshconv_bwd_data_tc')
             else:
                 with profiler.span('meshconv_bwd_data', B=B, E=E, Cin=Cin, Cout=Cout):
                     _lib.check(L.mcnn_meshconv_bwd_data(dout.data_ptr(), x.data_ptr(), level.gemm.data_ptr(), level.ec.data_ptr(),
@@ -196,8 +212,8 @@ class MeshConvFn(torch.autograd.Function):
                     db = torch.empty(Cout, dtype=torch.float32, device=x.device) if ctx.has_bias else None
                 ws = torch.empty(L.mcnn_meshconv_bwd_weight_tc_ws(B, E, Cin, Cout), dtype=torch.float32, device=x.device)
                 with profiler.span('meshconv_bwd_weight_tc', B=B, E=E, Cin=Cin, Cout=Cout):
-                    _lib.check(L.mcnn_meshconv_bwd_weight_tc(dout.data_ptr(), x.data_ptr(), level.gemm.data_ptr(), level.ec.data_ptr(),
-                                                             dw.data_ptr(), _lib.ptr(db), ws.data_ptr(), B, E, Cin, Cout, st),
+                    _lib.check(L.mcnn_meshconv_bwd_weight_tc_p(dout.data_ptr(), x.data_ptr(), level.gemm.data_ptr(), level.ec.data_ptr(),
+                                                               dw.data_ptr(), _lib.ptr(db), ws.data_ptr(), B, E, Cin, Cout, ctx.prec, st),
                                'mcnn_meshconv_bwd_weight_tc')
             else:
                 if direct is not None:

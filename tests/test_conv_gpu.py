@@ -322,3 +322,38 @@ def test_conv_stream_k_at_bench_tile_counts(cin, cout, B):
         Fn.USE_SK = True
     assert close(y2.cpu().numpy(), y1.cpu().numpy(), 2e-5)
     assert close(g2.cpu().numpy(), g1.cpu().numpy(), 1e-5)
+
+
+@pytest.mark.parametrize('cin,cout,B', [(64, 64, 8), (128, 256, 9), (256, 256, 20)])
+def test_conv_single_pass_tf32_mode_is_within_the_reduced_precision_tolerance(cin, cout, B):
+    """Opt-in reduced precision (meshcnn_b200.set_precision('tf32'): ONE TF32 MMA per product instead of three): forward,
+    data gradient and weight gradient against the default fp32-accurate kernels.  BASELINE.json allows a reduced-precision
+    path 2e-2 relative; TF32 operands (10 mantissa bits) with fp32 accumulation land near 5e-4.  The lower bound proves the
+    switch really changes the arithmetic."""
+    from meshcnn_b200 import synth
+    from meshcnn_b200 import functional as Fn
+    from meshcnn_b200.mesh_conv import MeshConv
+    from tests.gpu_util import DEV, product_mesh
+    meshes = [product_mesh(*synth.make('ico' if s % 3 else 'torus', s, **(dict(nu=5) if s % 3 else dict(m=10, n=25)))) for s in range(B)]
+    torch.manual_seed(cin + cout + B)
+    conv = MeshConv(cin, cout, bias=True).to(DEV)
+    x = torch.randn(B, cin, 750, device=DEV)
+    dy = torch.randn(B, cout, 750, 1, device=DEV)
+
+    def run():
+        conv.zero_grad()
+        xg = x.clone().requires_grad_(True)
+        y = conv(xg, meshes)
+        y.backward(dy)
+        torch.cuda.synchronize()
+        return [t.detach().clone() for t in (y, xg.grad, conv.conv.weight.grad, conv.conv.bias.grad)]
+    try:
+        ref = run()
+        Fn.set_precision('tf32')
+        got = run()
+    finally:
+        Fn.set_precision('fp32')
+    errs = [float((a - b).abs().max() / b.abs().max()) for a, b in zip(got, ref)]
+    assert all(e <= 2e-2 for e in errs), errs
+    assert all(e <= 5e-3 for e in errs), errs                  # what single-pass TF32 actually delivers
+    assert min(errs[:3]) > 2e-6, errs                          # the mode is really on
