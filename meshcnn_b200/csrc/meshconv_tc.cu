@@ -1907,13 +1907,22 @@ struct BwaSmem {
     static constexpr uint32_t LBO = 4096;
 };
 
+// Warp roles (17 warps): 0-7 feed the A operand (warp w: output tile w / 4 [OT == 2] or edge half w / 4 [OT == 1], TMEM lane
+// quarter w % 4) and run the epilogue; 8-15 build the gathered B operand in shared memory; 16 issues the MMAs.  A producer
+// thread retires roughly one dependent instruction per 5 cycles, so the per-K-block chain of a warp that did BOTH operands
+// (~250 instructions, two such warps per scheduler) was the kernel's period, not the tensor pipe (51 % active): two
+// specialised warp sets halve the chain and put four warps on every scheduler.
+constexpr int BWA_A_WARPS = 8, BWA_B_WARPS = 8;
+constexpr int BWA_THREADS = (BWA_A_WARPS + BWA_B_WARPS + 1) * 32;
+
 template <int OT>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(BWA_THREADS, 1)
 meshconv_bwd_weight_tca_kernel(const float* __restrict__ dout, const float* __restrict__ x, const int32_t* __restrict__ gemm,
                                const int32_t* __restrict__ ec, float* __restrict__ ws, int B, int E, int Cin, int Cout,
                                int rows_per_split, int one_pass) {
     using S = BwaSmem<OT>;
-    constexpr int AV = 16 * OT;                              // dout values per thread and K block (OT == 1: half of the edges)
+    constexpr int AV = 16 * OT;                              // dout values per A thread and K block (OT == 1: half of the edges)
+    constexpr int MMA_WARP = BWA_A_WARPS + BWA_B_WARPS;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* full_b = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
@@ -1929,9 +1938,9 @@ meshconv_bwd_weight_tca_kernel(const float* __restrict__ dout, const float* __re
     const int mbeg = split * rows_per_split, mend = min(M, mbeg + rows_per_split);
     const int num_kb = (mend > mbeg) ? (mend - mbeg + 31) >> 5 : 0;
 
-    if (warp == TC_PRODUCER_WARPS) {
+    if (warp == MMA_WARP) {
         if (lane == 0) {
-            for (int s = 0; s < S::STAGES; ++s) { tc::mbar_init(full_b + s, TC_PRODUCER_WARPS); tc::mbar_init(empty_b + s, 1); }
+            for (int s = 0; s < S::STAGES; ++s) { tc::mbar_init(full_b + s, BWA_B_WARPS); tc::mbar_init(empty_b + s, 1); }
             for (int s = 0; s < S::A_SLOTS; ++s) { tc::mbar_init(full_a + s, OT == 2 ? 4 : 8); tc::mbar_init(empty_a + s, 1); }
             tc::mbar_init(accum_bar, 1);
             tc::fence_barrier_init();
@@ -1944,115 +1953,53 @@ meshconv_bwd_weight_tca_kernel(const float* __restrict__ dout, const float* __re
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp < TC_PRODUCER_WARPS) {
-        const int pt = tid;
-        struct Idx { int s0, s1, s2, s3, s4; };
-        struct Data { float av[AV]; float4 f[5]; };
-        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        const int bk = pt >> 3, bq = pt & 7;                                // this thread's edge-in-block and channel chunk (B operand)
-        // A operand: this thread's output channel and its share of the K block's edges
+    if (warp < BWA_A_WARPS) {
+        // ======================================== A producers: dout^T into tensor memory ==============================
         const int a_tile = OT == 2 ? (warp >> 2) : 0;                       // OT == 2: warps 0-3 feed tile 0, warps 4-7 tile 1
         const int a_e0 = OT == 2 ? 0 : (warp >> 2) * 16;                    // OT == 1: the two warp groups split the 32 edges
-        const int a_o = o0 + a_tile * 128 + (warp & 3) * 32 + lane;
+        const int a_o = o0 + a_tile * 128 + (warp & 3) * 32 + lane;         // this thread's output channel = its TMEM lane
         const uint32_t a_lane = (uint32_t)((warp & 3) * 32) << 16;
-        int nb_b = (mbeg + bk) / E, nb_e = (mbeg + bk) - nb_b * E;
-        auto load_idx = [&](int kb) {
-            Idx I; I.s0 = I.s1 = I.s2 = I.s3 = I.s4 = -1;
-            const int m = mbeg + (kb << 5) + bk;
-            const int b = nb_b, e = nb_e;
-            nb_e += 32;
-            while (nb_e >= E) { nb_e -= E; ++nb_b; }
-            if (m < mend) {
-                if (e >= __ldg(ec + b)) { I.s0 = I.s1 = I.s2 = I.s3 = I.s4 = b * E; }
-                else {
-                    const int4 g4 = __ldg(reinterpret_cast<const int4*>(gemm + (size_t)m * 4));
-                    I.s0 = m;
-                    I.s1 = g4.x < 0 ? -1 : b * E + g4.x; I.s2 = g4.y < 0 ? -1 : b * E + g4.y;
-                    I.s3 = g4.z < 0 ? -1 : b * E + g4.z; I.s4 = g4.w < 0 ? -1 : b * E + g4.w;
-                }
-            }
-            return I;
-        };
-        auto load_data = [&](int kb, const Idx& I) {
-            Data D;
+        struct AData { float av[AV]; };
+        auto load_a = [&](int kb) {
+            AData D;
             const int mb = mbeg + (kb << 5) + a_e0;
             const float* ap = dout + (size_t)mb * Cout + a_o;
 #pragma unroll
             for (int j = 0; j < AV; ++j)
                 D.av[j] = (mb + j < mend && a_o < Cout) ? __ldg(ap + (size_t)j * Cout) : 0.f;
-            const int c = cb * 32 + (bq << 2);
-            D.f[0] = I.s0 >= 0 ? __ldg(reinterpret_cast<const float4*>(x + (size_t)I.s0 * Cin + c)) : z;
-            D.f[1] = I.s1 >= 0 ? __ldg(reinterpret_cast<const float4*>(x + (size_t)I.s1 * Cin + c)) : z;
-            D.f[2] = I.s2 >= 0 ? __ldg(reinterpret_cast<const float4*>(x + (size_t)I.s2 * Cin + c)) : z;
-            D.f[3] = I.s3 >= 0 ? __ldg(reinterpret_cast<const float4*>(x + (size_t)I.s3 * Cin + c)) : z;
-            D.f[4] = I.s4 >= 0 ? __ldg(reinterpret_cast<const float4*>(x + (size_t)I.s4 * Cin + c)) : z;
             return D;
         };
-        auto store_block = [&](int kb, const Data& D) {
-            // ---- B: the gathered operand into shared memory (all eight warps) ----
-            {
-                const int s = kb % S::STAGES;
-                const uint32_t ph = (kb / S::STAGES) & 1;
-                if (lane == 0) tc::mbar_wait(empty_b + s, ph ^ 1);        // one poller per warp
-                __syncwarp();
-                const uint32_t b_hi = tc::smem_u32(smem + s * S::STAGE_BYTES);
-                const uint32_t b_lo = b_hi + S::B_BYTES;
-                const float4 f0 = D.f[0], f1 = D.f[1], f2 = D.f[2], f3 = D.f[3], f4 = D.f[4];
-                float4 gk[5];
-                gk[0] = f0;
-                gk[1] = make_float4(f1.x + f3.x, f1.y + f3.y, f1.z + f3.z, f1.w + f3.w);
-                gk[2] = make_float4(f2.x + f4.x, f2.y + f4.y, f2.z + f4.z, f2.w + f4.w);
-                gk[3] = make_float4(fabsf(f1.x - f3.x), fabsf(f1.y - f3.y), fabsf(f1.z - f3.z), fabsf(f1.w - f3.w));
-                gk[4] = make_float4(fabsf(f2.x - f4.x), fabsf(f2.y - f4.y), fabsf(f2.z - f4.z), fabsf(f2.w - f4.w));
+        auto store_a = [&](int kb, const AData& D) {
+            const int u = kb * OT + a_tile;                                // (K block, output tile) unit -> A slot
+            const uint32_t slot = (uint32_t)(u % S::A_SLOTS), ph = (uint32_t)((u / S::A_SLOTS) & 1);
+            if (lane == 0) tc::mbar_wait(empty_a + slot, ph ^ 1);
+            __syncwarp();
+            tc::tc_fence_after();
+            const uint32_t c_hi = tmem_base + a_lane + bdp_a_hi_col(slot) + (uint32_t)a_e0;
+            const uint32_t c_lo = tmem_base + a_lane + bdp_a_lo_col(slot) + (uint32_t)a_e0;
 #pragma unroll
-                for (int k5 = 0; k5 < 5; ++k5) {
-                    float4 hi, lo;
-                    tc::split4(gk[k5], hi, lo);
-                    const uint32_t off = tc::sw128_mn_off(bk, k5 * 8 + bq, S::LBO);
-                    tc::sts128(b_hi + off, hi);
-                    if (!one_pass) tc::sts128(b_lo + off, lo);
-                }
-                tc::fence_proxy_async_smem();                              // every writer fences its own stores ...
-                __syncwarp();
-                if (lane == 0) tc::mbar_arrive(full_b + s);                // ... then one arrival per warp
+            for (int h = 0; h < AV / 16; ++h) {
+                float hi[16], lo[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) tc::split_tf32(D.av[16 * h + j], hi[j], lo[j]);
+                tc::tmem_st_32x32b_x16(c_hi + 16 * h, hi);
+                if (!one_pass) tc::tmem_st_32x32b_x16(c_lo + 16 * h, lo);
             }
-            // ---- A: this thread's output channel x its edges of the block, straight into its TMEM lane ----
-            {
-                const int u = kb * OT + a_tile;                            // (K block, output tile) unit -> A slot
-                const uint32_t slot = (uint32_t)(u % S::A_SLOTS), ph = (uint32_t)((u / S::A_SLOTS) & 1);
-                if (lane == 0) tc::mbar_wait(empty_a + slot, ph ^ 1);
-                __syncwarp();
-                tc::tc_fence_after();
-                const uint32_t c_hi = tmem_base + a_lane + bdp_a_hi_col(slot) + (uint32_t)a_e0;
-                const uint32_t c_lo = tmem_base + a_lane + bdp_a_lo_col(slot) + (uint32_t)a_e0;
-#pragma unroll
-                for (int h = 0; h < AV / 16; ++h) {
-                    float hi[16], lo[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) tc::split_tf32(D.av[16 * h + j], hi[j], lo[j]);
-                    tc::tmem_st_32x32b_x16(c_hi + 16 * h, hi);
-                    if (!one_pass) tc::tmem_st_32x32b_x16(c_lo + 16 * h, lo);
-                }
-                tc::tmem_wait_st();
-                tc::tc_fence_before();
-                __syncwarp();
-                if (lane == 0) tc::mbar_arrive(full_a + slot);
-            }
+            tc::tmem_wait_st();
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(full_a + slot);
         };
         if (num_kb > 0) {
-            Data D0 = load_data(0, load_idx(0));
-            Data D1;
-            if (num_kb > 1) D1 = load_data(1, load_idx(1));
-            Idx In;
-            if (num_kb > 2) In = load_idx(2);
+            AData D0 = load_a(0);
+            AData D1;
+            if (num_kb > 1) D1 = load_a(1);
             for (int kb = 0; kb < num_kb; kb += 2) {
-                store_block(kb, D0);
-                if (kb + 2 < num_kb) D0 = load_data(kb + 2, In);
-                if (kb + 3 < num_kb) In = load_idx(kb + 3);
+                store_a(kb, D0);
+                if (kb + 2 < num_kb) D0 = load_a(kb + 2);
                 if (kb + 1 < num_kb) {
-                    store_block(kb + 1, D1);
-                    if (kb + 3 < num_kb) D1 = load_data(kb + 3, In);
-                    if (kb + 4 < num_kb) In = load_idx(kb + 4);
+                    store_a(kb + 1, D1);
+                    if (kb + 3 < num_kb) D1 = load_a(kb + 3);
                 }
             }
         }
@@ -2092,7 +2039,87 @@ meshconv_bwd_weight_tca_kernel(const float* __restrict__ dout, const float* __re
             }
         }
         tc::tc_fence_before();
+    } else if (warp < MMA_WARP) {
+        // ======================================== B producers: the gathered operand into shared memory ==================
+        const int pt = tid - BWA_A_WARPS * 32;                              // 0 .. 255
+        struct Idx { int s0, s1, s2, s3, s4; };
+        struct BData { float4 f[5]; };
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int bk = pt >> 3, bq = pt & 7;                                // this thread's edge-in-block and channel chunk
+        int nb_b = (mbeg + bk) / E, nb_e = (mbeg + bk) - nb_b * E;
+        auto load_idx = [&](int kb) {
+            Idx I; I.s0 = I.s1 = I.s2 = I.s3 = I.s4 = -1;
+            const int m = mbeg + (kb << 5) + bk;
+            const int b = nb_b, e = nb_e;
+            nb_e += 32;
+            while (nb_e >= E) { nb_e -= E; ++nb_b; }
+            if (m < mend) {
+                if (e >= __ldg(ec + b)) { I.s0 = I.s1 = I.s2 = I.s3 = I.s4 = b * E; }
+                else {
+                    const int4 g4 = __ldg(reinterpret_cast<const int4*>(gemm + (size_t)m * 4));
+                    I.s0 = m;
+                    I.s1 = g4.x < 0 ? -1 : b * E + g4.x; I.s2 = g4.y < 0 ? -1 : b * E + g4.y;
+                    I.s3 = g4.z < 0 ? -1 : b * E + g4.z; I.s4 = g4.w < 0 ? -1 : b * E + g4.w;
+                }
+            }
+            return I;
+        };
+        auto load_b = [&](const Idx& I) {
+            BData D;
+            const int c = cb * 32 + (bq << 2);
+            D.f[0] = I.s0 >= 0 ? __ldg(reinterpret_cast<const float4*>(x + (size_t)I.s0 * Cin + c)) : z;
+            D.f[1] = I.s1 >= 0 ? __ldg(reinterpret_cast<const float4*>(x + (size_t)I.s1 * Cin + c)) : z;
+            D.f[2] = I.s2 >= 0 ? __ldg(reinterpret_cast<const float4*>(x + (size_t)I.s2 * Cin + c)) : z;
+            D.f[3] = I.s3 >= 0 ? __ldg(reinterpret_cast<const float4*>(x + (size_t)I.s3 * Cin + c)) : z;
+            D.f[4] = I.s4 >= 0 ? __ldg(reinterpret_cast<const float4*>(x + (size_t)I.s4 * Cin + c)) : z;
+            return D;
+        };
+        auto store_b = [&](int kb, const BData& D) {
+            const int s = kb % S::STAGES;
+            const uint32_t ph = (kb / S::STAGES) & 1;
+            if (lane == 0) tc::mbar_wait(empty_b + s, ph ^ 1);            // one poller per warp
+            __syncwarp();
+            const uint32_t b_hi = tc::smem_u32(smem + s * S::STAGE_BYTES);
+            const uint32_t b_lo = b_hi + S::B_BYTES;
+            const float4 f0 = D.f[0], f1 = D.f[1], f2 = D.f[2], f3 = D.f[3], f4 = D.f[4];
+            float4 gk[5];
+            gk[0] = f0;
+            gk[1] = make_float4(f1.x + f3.x, f1.y + f3.y, f1.z + f3.z, f1.w + f3.w);
+            gk[2] = make_float4(f2.x + f4.x, f2.y + f4.y, f2.z + f4.z, f2.w + f4.w);
+            gk[3] = make_float4(fabsf(f1.x - f3.x), fabsf(f1.y - f3.y), fabsf(f1.z - f3.z), fabsf(f1.w - f3.w));
+            gk[4] = make_float4(fabsf(f2.x - f4.x), fabsf(f2.y - f4.y), fabsf(f2.z - f4.z), fabsf(f2.w - f4.w));
+#pragma unroll
+            for (int k5 = 0; k5 < 5; ++k5) {
+                float4 hi, lo;
+                tc::split4(gk[k5], hi, lo);
+                const uint32_t off = tc::sw128_mn_off(bk, k5 * 8 + bq, S::LBO);
+                tc::sts128(b_hi + off, hi);
+                if (!one_pass) tc::sts128(b_lo + off, lo);
+            }
+            tc::fence_proxy_async_smem();                                  // every writer fences its own stores ...
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(full_b + s);                    // ... then one arrival per warp
+        };
+        if (num_kb > 0) {
+            // the gather is two dependent global loads (one-ring ids, then five rows): ids run three K blocks ahead, rows two
+            BData D0 = load_b(load_idx(0));
+            BData D1;
+            if (num_kb > 1) D1 = load_b(load_idx(1));
+            Idx In;
+            if (num_kb > 2) In = load_idx(2);
+            for (int kb = 0; kb < num_kb; kb += 2) {
+                store_b(kb, D0);
+                if (kb + 2 < num_kb) D0 = load_b(In);
+                if (kb + 3 < num_kb) In = load_idx(kb + 3);
+                if (kb + 1 < num_kb) {
+                    store_b(kb + 1, D1);
+                    if (kb + 3 < num_kb) D1 = load_b(In);
+                    if (kb + 4 < num_kb) In = load_idx(kb + 4);
+                }
+            }
+        }
     } else {
+        // ======================================== MMA issuer ============================================================
         constexpr uint32_t idesc = tc::make_idesc_tf32_bmn(BD_N);
         for (int kb = 0; kb < num_kb; ++kb) {
             const int s = kb % S::STAGES;
@@ -2127,7 +2154,7 @@ meshconv_bwd_weight_tca_kernel(const float* __restrict__ dout, const float* __re
         tc::tc_fence_before();
     }
     __syncthreads();
-    if (warp == TC_PRODUCER_WARPS) {
+    if (warp == MMA_WARP) {
         tc::tc_fence_after();
         tc::tmem_dealloc<512>(tmem_base);
     }
@@ -2351,12 +2378,12 @@ extern "C" int mcnn_meshconv_bwd_weight_tc_p(const float* dout, const float* x, 
             static DynSmemGuard cfg2;
             if (int grc = cfg2.ensure(meshconv_bwd_weight_tca_kernel<2>, BwaSmem<2>::TOTAL)) return grc;
             dim3 grid(S, ceil_div(Cout, 256), Cin / 32);
-            meshconv_bwd_weight_tca_kernel<2><<<grid, TC_THREADS, BwaSmem<2>::TOTAL, st>>>(dout, x, gemm, ec, ws, B, E, Cin, Cout, rows, one_pass);
+            meshconv_bwd_weight_tca_kernel<2><<<grid, BWA_THREADS, BwaSmem<2>::TOTAL, st>>>(dout, x, gemm, ec, ws, B, E, Cin, Cout, rows, one_pass);
         } else {
             static DynSmemGuard cfg1;
             if (int grc = cfg1.ensure(meshconv_bwd_weight_tca_kernel<1>, BwaSmem<1>::TOTAL)) return grc;
             dim3 grid(S, ceil_div(Cout, 128), Cin / 32);
-            meshconv_bwd_weight_tca_kernel<1><<<grid, TC_THREADS, BwaSmem<1>::TOTAL, st>>>(dout, x, gemm, ec, ws, B, E, Cin, Cout, rows, one_pass);
+            meshconv_bwd_weight_tca_kernel<1><<<grid, BWA_THREADS, BwaSmem<1>::TOTAL, st>>>(dout, x, gemm, ec, ws, B, E, Cin, Cout, rows, one_pass);
         }
     } else if (bw_ot(Cout) == 2) {
         static DynSmemGuard configured2;
