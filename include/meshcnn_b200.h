@@ -253,6 +253,18 @@ int mcnn_unpool_bwd(const float* dout, const int32_t* grp_rowptr, const int32_t*
  * s1 / s2: [nblocks][G] scratch.
  * ------------------------------------------------------------------------------------------------------ */
 size_t mcnn_norm_ws(int nblocks, int rows_per_block, int C, int G);
+/* The stages on their own, for statistics that cross processes (SyncBN for MResConv.bn, networks.py:167): the
+ * caller reduces the slab partials `part` [nblocks][slabs][2][C] (slabs = mcnn_norm_slabs; [0] = sum z / sum dyh, [1] = sum z^2 /
+ * sum dyh*xhat per channel), all-reduces them, and hands mean / rstd (forward: mcnn_norm_fwd with stats_given = 1) or
+ * s1 = gamma*A/n, s2 = gamma*B/n per (block, group) (backward) back in. */
+int mcnn_norm_slabs(int nblocks, int rows_per_block, int C, int G);
+int mcnn_norm_stats(const float* x, const float* a, float* part, int nblocks, int rows_per_block, int C, int G, int pre_relu,
+                    void* stream);
+int mcnn_norm_bwd_stats(const float* dy, const float* y, const float* x, const float* a, const float* mean, const float* rstd,
+                        float* part, int nblocks, int rows_per_block, int C, int G, int pre_relu, int post_relu, void* stream);
+int mcnn_norm_bwd_apply(const float* dy, const float* y, const float* x, const float* a, const float* gamma, const float* mean,
+                        const float* rstd, const float* s1, const float* s2, float* dx, float* dr, int nblocks,
+                        int rows_per_block, int C, int G, int pre_relu, int post_relu, void* stream);
 int mcnn_norm_fwd(const float* x, const float* a, const float* r, const float* gamma, const float* beta, float* y,
                   float* mean, float* rstd, float* part, float* running_mean, float* running_var, float momentum,
                   float eps, int nblocks, int rows_per_block, int C, int G, int pre_relu, int post_relu, int stats_given,

@@ -61,6 +61,10 @@ SIGNATURES = {
     'mcnn_segmean_bwd': (_c_int, [_c_vp] * 6 + [_c_int] * 5 + [_c_vp]),
     'mcnn_unpool_fwd': (_c_int, [_c_vp] * 6 + [_c_int] * 6 + [_c_vp]),
     'mcnn_norm_ws': (_c_sz, [_c_int] * 4),
+    'mcnn_norm_slabs': (_c_int, [_c_int] * 4),
+    'mcnn_norm_stats': (_c_int, [_c_vp] * 3 + [_c_int] * 5 + [_c_vp]),
+    'mcnn_norm_bwd_stats': (_c_int, [_c_vp] * 7 + [_c_int] * 6 + [_c_vp]),
+    'mcnn_norm_bwd_apply': (_c_int, [_c_vp] * 11 + [_c_int] * 6 + [_c_vp]),
     'mcnn_norm_fwd': (_c_int, [_c_vp] * 11 + [ctypes.c_float, ctypes.c_float] + [_c_int] * 7 + [_c_vp]),
     'mcnn_norm_bwd': (_c_int, [_c_vp] * 14 + [_c_int] * 6 + [_c_vp]),
     'mcnn_adam_flat': (_c_int, [_c_vp] * 4 + [ctypes.c_longlong] + [ctypes.c_float] * 5 + [_c_int, _c_vp]),

@@ -705,6 +705,42 @@ extern "C" int mcnn_norm_bwd(const float* dy, const float* y, const float* x, co
     return after_launch();
 }
 
+/* ---- the statistics and apply stages on their own: what a cross-rank (SyncBN) reduction sits between ------------------ */
+extern "C" int mcnn_norm_slabs(int nblocks, int rows_per_block, int C, int G) {
+    if (!norm_args_ok(nblocks, rows_per_block, C, G)) return 0;
+    return make_shape(nblocks, rows_per_block, C, G).slabs;
+}
+
+extern "C" int mcnn_norm_stats(const float* x, const float* a, float* part, int nblocks, int rows_per_block, int C, int G,
+                               int pre_relu, void* stream) {
+    if (!x || !part || !norm_args_ok(nblocks, rows_per_block, C, G)) return MCNN_E_BADARG;
+    const NormShape s = make_shape(nblocks, rows_per_block, C, G);
+    const size_t smem = (size_t)(NT / (C / 4)) * 2 * C * sizeof(float);
+    norm_stats_kernel<<<dim3(nblocks, s.slabs), NT, smem, (cudaStream_t)stream>>>(x, a, pre_relu, part, s);
+    return after_launch();
+}
+
+extern "C" int mcnn_norm_bwd_stats(const float* dy, const float* y, const float* x, const float* a, const float* mean,
+                                   const float* rstd, float* part, int nblocks, int rows_per_block, int C, int G, int pre_relu,
+                                   int post_relu, void* stream) {
+    if (!dy || !x || !mean || !rstd || !part || !norm_args_ok(nblocks, rows_per_block, C, G)) return MCNN_E_BADARG;
+    if (post_relu && !y) return MCNN_E_BADARG;
+    const NormShape s = make_shape(nblocks, rows_per_block, C, G);
+    const size_t smem = (size_t)(NT / (C / 4)) * 2 * C * sizeof(float);
+    norm_bwd_stats_kernel<<<dim3(nblocks, s.slabs), NT, smem, (cudaStream_t)stream>>>(dy, y, x, a, mean, rstd, pre_relu, post_relu, part, s);
+    return after_launch();
+}
+
+extern "C" int mcnn_norm_bwd_apply(const float* dy, const float* y, const float* x, const float* a, const float* gamma,
+                                   const float* mean, const float* rstd, const float* s1, const float* s2, float* dx, float* dr,
+                                   int nblocks, int rows_per_block, int C, int G, int pre_relu, int post_relu, void* stream) {
+    if (!dy || !x || !mean || !rstd || !s1 || !s2 || !dx || !norm_args_ok(nblocks, rows_per_block, C, G)) return MCNN_E_BADARG;
+    if (post_relu && !y) return MCNN_E_BADARG;
+    const NormShape s = make_shape(nblocks, rows_per_block, C, G);
+    norm_bwd_apply_kernel<<<dim3(nblocks, s.slabs), NT, 0, (cudaStream_t)stream>>>(dy, y, x, a, gamma, mean, rstd, s1, s2, dx, dr, pre_relu, post_relu, s);
+    return after_launch();
+}
+
 extern "C" int mcnn_debug_set_norm_fused(int on) { g_norm_fused = on ? 1 : 0; return MCNN_OK; }
 
 extern "C" int mcnn_adam_flat_state(float* p, const float* g, float* m, float* v, long long n, float* state, void* stream) {

@@ -23,6 +23,15 @@ def broadcast_parameters(net, src=0):
         dist.broadcast(t.data, src)
 
 
+def enable_sync_batchnorm(on=True, local_items=None, global_items=None):
+    """Batch statistics of every BatchNorm2d (MResConv.bn, networks.py:167) over the rows of ALL ranks instead of the local
+    shard: the forward all-reduces (sum, sum of squares, count) per channel, the backward (sum dy, sum dy * xhat).
+    For uneven shards pass this rank's and the global mesh count, as to FlatGradReducer."""
+    from . import functional as Fn
+    Fn.SYNC_BN = bool(on)
+    Fn.SYNC_BN_WEIGHT = None if local_items is None else float(local_items) / float(global_items)
+
+
 class FlatGradReducer:
     def __init__(self, net, local_items=None, global_items=None):
         self.params = [p for p in net.parameters() if p.requires_grad]

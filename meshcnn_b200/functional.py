@@ -359,6 +359,92 @@ class FusedNormFn(torch.autograd.Function):
         return dx, (dx if a is not None else None), dr, dgamma, dbeta, None
 
 
+# Cross-rank batch statistics for BatchNorm2d (MResConv.bn, networks.py:167; SURVEY 8e "optional SyncBN"): off by default, like
+# any DDP run without SyncBN.  ddp.enable_sync_batchnorm() / MESHCNN_B200_SYNC_BN=1 switch it on.
+SYNC_BN = os.environ.get('MESHCNN_B200_SYNC_BN', '0') == '1'
+SYNC_BN_WEIGHT = None        # this rank's share of the global batch when the shards are uneven (None: equal shards)
+
+
+class SyncBatchNormFn(torch.autograd.Function):
+    """BatchNorm2d (training) with statistics over the rows of ALL ranks: the per-slab partial sums of the local rows
+    (mcnn_norm_stats) are reduced here, all-reduced (one small NCCL call: 2C + 1 doubles), and handed back to the apply kernel
+    (mcnn_norm_fwd with stats_given); the backward does the same with (sum dyh, sum dyh * xhat) between mcnn_norm_bwd_stats and
+    mcnn_norm_bwd_apply.  dgamma / dbeta stay local sums: the flat gradient all-reduce averages them like every other parameter."""
+
+    @staticmethod
+    def forward(ctx, x, a, r, gamma, beta, cfg):
+        import torch.distributed as dist
+        _chk_cuda(x, a, r, gamma, beta)
+        x = x.contiguous()
+        a = None if a is None else a.contiguous()
+        r = None if r is None else r.contiguous()
+        B, E, C = x.shape
+        rows = B * E
+        L = _lib.lib()
+        st = _lib.current_stream()
+        slabs = L.mcnn_norm_slabs(1, rows, C, C)
+        part = torch.empty(slabs * 2 * C, dtype=torch.float32, device=x.device)
+        _lib.check(L.mcnn_norm_stats(x.data_ptr(), _lib.ptr(a), part.data_ptr(), 1, rows, C, C, int(cfg['pre_relu']), st), 'mcnn_norm_stats')
+        buf = torch.cat([part.view(slabs, 2, C).double().sum(0).reshape(-1), torch.full((1,), float(rows), dtype=torch.float64, device=x.device)])
+        dist.all_reduce(buf)
+        n = buf[2 * C]
+        mean = buf[:C] / n
+        var = (buf[C:2 * C] / n - mean * mean).clamp_(min=0.0)
+        rstd = torch.rsqrt(var + float(cfg['eps']))
+        rm, rv = cfg.get('running_mean'), cfg.get('running_var')
+        if rm is not None:
+            mom = float(cfg.get('momentum', 0.1))
+            with torch.no_grad():
+                rm.mul_(1.0 - mom).add_(mean.to(rm.dtype), alpha=mom)
+                rv.mul_(1.0 - mom).add_((var * n / (n - 1.0).clamp(min=1.0)).to(rv.dtype), alpha=mom)
+        mean32, rstd32 = mean.float().contiguous(), rstd.float().contiguous()
+        y = torch.empty_like(x)
+        _lib.check(L.mcnn_norm_fwd(x.data_ptr(), _lib.ptr(a), _lib.ptr(r), _lib.ptr(gamma), _lib.ptr(beta), y.data_ptr(),
+                                   mean32.data_ptr(), rstd32.data_ptr(), part.data_ptr(), None, None, 0.0, float(cfg['eps']), 1, rows, C, C,
+                                   int(cfg['pre_relu']), int(cfg['post_relu']), 1, st), 'mcnn_norm_fwd')
+        ctx.save_for_backward(x, a, gamma, mean32, rstd32, y, n)
+        ctx.cfg = (rows, C, slabs, int(cfg['pre_relu']), int(cfg['post_relu']), r is not None)
+        ctx.params = (gamma, beta)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        import torch.distributed as dist
+        x, a, gamma, mean, rstd, y, n = ctx.saved_tensors
+        rows, C, slabs, pre_relu, post_relu, has_r = ctx.cfg
+        dy = dy.contiguous()
+        L = _lib.lib()
+        st = _lib.current_stream()
+        part = torch.empty(slabs * 2 * C, dtype=torch.float32, device=dy.device)
+        _lib.check(L.mcnn_norm_bwd_stats(dy.data_ptr(), y.data_ptr(), x.data_ptr(), _lib.ptr(a), mean.data_ptr(), rstd.data_ptr(),
+                                         part.data_ptr(), 1, rows, C, C, pre_relu, post_relu, st), 'mcnn_norm_bwd_stats')
+        ab = part.view(slabs, 2, C).double().sum(0)                      # local sum dyh, sum dyh * xhat per channel
+        dbeta, dgamma = ab[0].float(), ab[1].float()
+        w = SYNC_BN_WEIGHT
+        tot = ab.clone() if w is None else ab * float(w)                 # uneven shards: the global loss weighs rank r by its share
+        dist.all_reduce(tot)
+        if w is not None:
+            tot = tot / float(w)
+        gm = gamma.double() if gamma is not None else torch.ones(C, dtype=torch.float64, device=dy.device)
+        s1 = (gm * tot[0] / n).float().contiguous()
+        s2 = (gm * tot[1] / n).float().contiguous()
+        dx = torch.empty_like(x)
+        dr = torch.empty_like(x) if has_r else None
+        _lib.check(L.mcnn_norm_bwd_apply(dy.data_ptr(), y.data_ptr(), x.data_ptr(), _lib.ptr(a), _lib.ptr(gamma), mean.data_ptr(),
+                                         rstd.data_ptr(), s1.data_ptr(), s2.data_ptr(), dx.data_ptr(), _lib.ptr(dr), 1, rows, C, C,
+                                         pre_relu, post_relu, st), 'mcnn_norm_bwd_apply')
+        if gamma is None:
+            dgamma = dbeta = None
+        return dx, (dx if a is not None else None), dr, dgamma, dbeta, None
+
+
+def _sync_bn_active():
+    if not SYNC_BN:
+        return False
+    import torch.distributed as dist
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
 def fused_norm(x, norm, pre_add=None, pre_relu=False, post_add=None, post_relu=False):
     """Apply a torch norm module (BatchNorm2d / GroupNorm / InstanceNorm2d, the three the reference's networks use) to
     edge-major x [B, E, C] with the surrounding add / relu fused in.  Returns None if `norm` is not one of those."""
@@ -385,6 +471,8 @@ def fused_norm(x, norm, pre_add=None, pre_relu=False, post_add=None, post_relu=F
                     return None
                 cfg.update(running_mean=norm.running_mean, running_var=norm.running_var, momentum=norm.momentum)
                 norm.num_batches_tracked.add_(1)
+            if _sync_bn_active():
+                return SyncBatchNormFn.apply(x, pre_add, post_add, gamma, beta, cfg)
         else:
             cfg.update(mean=norm.running_mean, rstd=torch.rsqrt(norm.running_var + norm.eps))
     else:
