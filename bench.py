@@ -179,7 +179,7 @@ class ClockSampler:
         while not self._stop.is_set():
             if not self.sample():
                 return
-            time.sleep(0.002)
+            time.sleep(0.01)
 
     def stop(self):
         self._stop.set()
@@ -311,6 +311,7 @@ def main():
     ap.add_argument('--batch', type=int, default=0, help='override the per-GPU batch size')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-flush', action='store_true', help='diagnostics: no L2 flush between timed steps (the number is then not a bench value)')
     ap.add_argument('--no-graph', action='store_true', help='launch the step kernel by kernel instead of replaying a CUDA graph')
     ap.add_argument('--precision', default='fp32', choices=['fp32', 'tf32'],
                     help="arithmetic of the tensor-core MeshConv kernels: fp32 = 3xTF32 (the headline), tf32 = one TF32 MMA per product "
@@ -403,14 +404,21 @@ def main():
         step()
     torch.cuda.synchronize()
     batch.check()
+    # the clock sampler (NVML init: a few ms on rank 0 only) must exist BEFORE the barrier: started after it, rank 0 entered the
+    # timed region late and every other rank's first timed step waited ~4 ms for it at the all-reduce -- 0.2-0.3 ms per step
+    # of a 20-step run, which is what rounds 1 and 2 had been reading as a multi-GPU scaling loss
+    sampler = ClockSampler(local) if rank == 0 else None
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local) if rank == 0 else None
     launches0 = _lib.launch_count()
     evs = []
+    import gc
+    gc.collect()
+    gc.disable()                                                        # a collector pause on one rank stalls every rank at the all-reduce
     for _ in range(args.steps):
-        flush.fill_(1)                                                  # L2 flush between timed steps (not timed)
+        if not args.no_flush:
+            flush.fill_(1)                                              # L2 flush between timed steps (not timed)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         step()
@@ -419,12 +427,20 @@ def main():
         if sampler is not None and (len(evs) & 3) == 0:
             sampler.sample()                                            # GPU is busy with this step; the call is not timed
     torch.cuda.synchronize()
+    gc.enable()
     if world > 1:
         dist.barrier()
     clocks = sampler.stop() if sampler is not None else None
     launches = (_lib.launch_count() - launches0) if gs is None else launches_per_step * args.steps
     batch.check()
-    total_ms = sum(a.elapsed_time(b) for a, b in evs)
+    per_step = sorted(a.elapsed_time(b) for a, b in evs)
+    total_ms = sum(per_step)
+    spread = torch.tensor([per_step[0], per_step[len(per_step) // 2], per_step[-1], total_ms / len(per_step)], dtype=torch.float64, device=dev)
+    spreads = [spread]
+    if world > 1:
+        spreads = [torch.zeros_like(spread) for _ in range(world)]
+        dist.all_gather(spreads, spread)
+    step_spread = [{'min': float(t[0]), 'median': float(t[1]), 'max': float(t[2]), 'mean': float(t[3])} for t in spreads]
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -488,7 +504,7 @@ def main():
                 ev0.append((ea, eb))
             torch.cuda.synchronize()
             own = sum(ea.elapsed_time(eb) for ea, eb in ev0) / len(ev0)
-            gs0.graph = None
+            gs0.close()
             del gs0
         finally:
             reducer.enabled = True
@@ -587,7 +603,7 @@ def main():
         import gc
         for g in [gs] + (list(ge_holder[0].slots) if ge_holder[0] is not None else []):
             if g is not None:
-                g.graph = None
+                g.close()
         gc.collect()
         torch.cuda.synchronize()
         if world > 1:
@@ -668,12 +684,14 @@ def main():
                                        'note': 'reference: wall time inside MeshPool.forward (host); ours: CUDA-event time of the pool kernels in the eager attribution pass'}
 
     line = {'metric': 'train meshes/sec (fwd+bwd+pool)', 'value': value, 'unit': 'meshes/s', 'n_gpus': world, 'steps': args.steps,
-            'warmup': args.warmup, 'ms_per_step': total_ms / args.steps, 'higher_is_better': True, 'scaling': args.scaling,
+            'warmup': args.warmup, 'ms_per_step': total_ms / args.steps,
+            'ms_per_step_by_rank': step_spread,
+            'higher_is_better': True, 'scaling': args.scaling,
             'vs_baseline': None, 'dtype': 'f32' if args.precision == 'fp32' else 'tf32 (single-pass TF32 MMAs in the MeshConv kernels, fp32 everywhere else; opt-in)', 'data': 'synthetic',
             'config': {'workload': workload_name(args.config, cfg) + (' [GLOBAL batch, sharded]' if args.scaling == 'strong' else ''),
                        'global_batch': B_global,
                        'parallelism': 'dp%d (meshes sharded, one flat NCCL gradient allreduce)' % world,
-                       'l2': 'flushed between timed steps (256 MiB write, untimed); per-step CUDA events, max over ranks',
+                       'l2': ('flushed between timed steps (256 MiB write, untimed)' if not args.no_flush else 'NOT flushed (diagnostic run)') + '; per-step CUDA events, max over ranks',
                        'optimizer': 'Adam (in the timed region)', 'launch': mode},
             'roofline': roofline, 'pool_collapse': pool_info, 'cpu_baseline': cpu, 'e2e': e2e, 'multi_gpu_attribution': attribution, 'gpu_launches': int(launches), 'clocks': clocks}
     _finish(out, line, cleanup)

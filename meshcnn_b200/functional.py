@@ -37,6 +37,7 @@ def set_precision(name):
 _SIDE = {}
 _SK_WS = {}
 STEP_TOKEN = -1          # >= 0 while a step prepared with begin_step() is being enqueued
+GRAD_REDUCER = None      # ddp.FlatGradReducer that wants to start its tail all-reduce from inside backward (multi-GPU steps)
 _NEXT_TOKEN = 0
 
 
@@ -226,6 +227,8 @@ class MeshConvFn(torch.autograd.Function):
                                                           dw.data_ptr(), _lib.ptr(db), B, E, Cin, Cout, st), 'mcnn_meshconv_bwd_weight')
         if direct is not None:
             dw = db = None                                   # already in weight.grad / bias.grad
+            if GRAD_REDUCER is not None and want_w:
+                GRAD_REDUCER.conv_backward_launched(ctx.params[0])
         return dx, dw, db, None, None, None
 
 

@@ -15,6 +15,8 @@ once and replays it.  Per step the host packs the next batch of meshes into the 
     for meshes, x, y in loader:
         loss = step(meshes, x, y)          # tensor on the device; .item() when the value is wanted
 """
+import os
+
 import numpy as np
 import torch
 
@@ -23,13 +25,25 @@ from .mesh import MeshBatch
 
 
 class GraphedTrainStep:
-    def __init__(self, net, criterion, reducer, optimizer, meshes, x, y, E, source='host', V_cap=0, ve_cap=0, warmup=3):
+    def __init__(self, net, criterion, reducer, optimizer, meshes, x, y, E, source='host', V_cap=0, ve_cap=0, warmup=3,
+                 collective='auto'):
         """meshes / x / y: a first batch that fixes the shapes (x: [B, C, E] fp32 host array or tensor, y: labels).
         source='host': every replay starts with the host->device copies of the staged batch;
         source='device': the batch given here stays resident and every replay restores its pristine topology
         (benchmarking the device-side step alone)."""
         if source not in ('host', 'device'):
             raise ValueError(source)
+        # Where the gradient all-reduce sits (world > 1).  'in-graph': one graph, the NCCL kernel is a node of it.
+        # 'between': TWO graphs -- [copies, forward, backward] and [Adam, loss read-back] -- with the all-reduce launched
+        # between them.  Measured on 2 x B200: the NCCL node costs the step 0.29-0.33 ms inside the graph of ~140 kernel nodes
+        # but 47 us inside a graph of 8 (tools/ar_in_step_probe.py) and 39 us back to back -- i.e. ~2 us per node of the graph
+        # it sits in, not NCCL time.  'auto' = 'between' when the reducer really reduces.
+        if collective not in ('auto', 'in-graph', 'between'):
+            raise ValueError(collective)
+        multi = getattr(reducer, 'world', 1) > 1 and getattr(reducer, 'enabled', True)
+        if collective == 'auto':
+            collective = os.environ.get('MESHCNN_B200_COLLECTIVE', 'between' if multi else 'in-graph')
+        self.collective = collective if multi else 'in-graph'
         self.net, self.criterion, self.reducer, self.opt, self.source = net, criterion, reducer, optimizer, source
         dev = reducer.flat.device
         self.device = dev
@@ -57,6 +71,7 @@ class GraphedTrainStep:
         self.loss_host = torch.zeros((), dtype=torch.float32).pin_memory()   # the step's result, copied out by the graph itself
         self.done = torch.cuda.Event()
         self.graph = None
+        self.graph_tail = None
         self._capture(warmup)
 
     # the work of one step, enqueued on the current stream
@@ -80,10 +95,16 @@ class GraphedTrainStep:
         finally:
             Fn.end_step()                           # also on an exception: a dangling step token would make later backward
                                                     # passes write straight into p.grad
-        self.reducer.allreduce()
+        if self.collective == 'in-graph':
+            self._enqueue_tail(loss)
+        return loss
+
+    def _enqueue_tail(self, loss):
+        """What follows backward: gradient all-reduce (world > 1), optimiser step, loss read-back."""
+        if self.collective == 'in-graph':
+            self.reducer.allreduce()
         self.opt.step_state()
         self.loss_host.copy_(loss.detach(), non_blocking=True)
-        return loss
 
     def _capture(self, warmup):
         """Warm-up (allocator, lazy kernel configuration, NCCL) on a side stream, then capture.  The warm-up steps are real
@@ -93,15 +114,24 @@ class GraphedTrainStep:
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream()
         side.wait_stream(cur)
+        between = self.collective == 'between'
         with torch.cuda.stream(side):
             for _ in range(max(1, warmup)):
-                self._enqueue()
+                loss = self._enqueue()
+                if between:
+                    self.reducer.allreduce()
+                    self._enqueue_tail(loss)
         cur.wait_stream(side)
         torch.cuda.synchronize()
         self.batch.check()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.loss = self._enqueue()
+        self.graph_tail = None
+        if between:
+            self.graph_tail = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_tail, pool=self.graph.pool()):
+                self._enqueue_tail(self.loss)
         self.warmup_steps = max(1, warmup)
         self._restore_training_state(saved)
         torch.cuda.synchronize()
@@ -143,9 +173,17 @@ class GraphedTrainStep:
         """Replay the captured step; returns the (device) loss tensor of the graph's static output."""
         self.opt.sync_lr()
         self.graph.replay()
+        if self.graph_tail is not None:
+            self.reducer.allreduce()                # one NCCL launch between the two graphs
+            self.graph_tail.replay()
         self.done.record()
         self.batch.version += 1                     # host mirrors of the meshes refresh lazily from the new state
         return self.loss
+
+    def close(self):
+        """Release the captured graphs (before the NCCL communicator they may reference is destroyed)."""
+        self.graph = None
+        self.graph_tail = None
 
     def result(self):
         """Loss of the most recent run() as a Python float; waits for THAT replay only (later work keeps running)."""

@@ -186,3 +186,75 @@ def test_sync_batchnorm_makes_the_sharded_step_equal_the_whole_batch_step():
     np.testing.assert_allclose(res[True][0][6], bn.running_var.cpu().numpy(), rtol=1e-4, atol=1e-7)
     unsynced_out = np.concatenate([r[3] for r in res[False]], 0)
     assert rel(unsynced_out, whole_out) > 1e-3                       # per-rank statistics: a different function
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the graphed multi-GPU step: tail bucket all-reduced from inside backward, head bucket at the end
+# ---------------------------------------------------------------------------------------------------------------------
+def _graph_worker(rank, world, port, q, mode):
+    import torch.distributed as dist
+    from meshcnn_b200 import ddp
+    from meshcnn_b200.graphed import GraphedTrainStep
+    from meshcnn_b200.mesh import Mesh
+    from meshcnn_b200.optim import FlatAdam
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dev = torch.device('cuda', rank)
+    torch.cuda.set_device(dev)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
+    net, datas, x, y, E, B = _net_and_data()
+    net = net.to(dev).train()
+    ddp.broadcast_parameters(net)
+    lo, hi = ddp.shard_range(B, rank, world)
+    red = ddp.FlatGradReducer(net, local_items=hi - lo, global_items=B, early_tail=True)
+    assert red.split is not None and 0 < red.split < red.flat.numel()
+    opt = FlatAdam(red, lr=0.0)                                     # lr 0: the parameters stay put, the gradients are what we compare
+    crit = torch.nn.CrossEntropyLoss(ignore_index=-1)
+    step = GraphedTrainStep(net, crit, red, opt, [Mesh(data=d, hold_history=True) for d in datas[lo:hi]], x[lo:hi], y[lo:hi], E,
+                            collective=mode)
+    step([Mesh(data=d, hold_history=True) for d in datas[lo:hi]], x[lo:hi], y[lo:hi])
+    torch.cuda.synchronize()
+    q.put((rank, red.split, red.flat.cpu().numpy()))
+    dist.barrier()
+    step.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs')
+@pytest.mark.parametrize('mode', ['between', 'in-graph'])
+def test_graphed_multi_gpu_step_reduces_the_same_gradient(mode):
+    """The captured multi-GPU step in both forms: 'between' (the default: two graphs with the NCCL all-reduce launched
+    between them) and 'in-graph' (one graph; with early_tail the tail of the flat buffer -- the late layers -- is reduced
+    on a side stream as soon as those gradients are final, the head at the end).  The reduced gradient must equal the
+    weighted sum of the shard gradients computed in one process (2e-5), on both ranks, on both sides of the split."""
+    import torch.multiprocessing as mp
+    from meshcnn_b200 import ddp
+    from meshcnn_b200.mesh import Mesh
+    world = 2
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_graph_worker, args=(r, world, port, q, mode)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = sorted((q.get(timeout=900) for _ in range(world)), key=lambda r: r[0])
+    for p in ps:
+        p.join(120)
+        assert p.exitcode == 0
+    np.testing.assert_array_equal(res[0][2], res[1][2])
+    dev = torch.device('cuda', 0)
+
+    def grad_of(lo, hi):
+        net, datas, x, y, E, B = _net_and_data()
+        net = net.to(dev).train()
+        red = ddp.FlatGradReducer(net)
+        red.zero()
+        out = net(torch.from_numpy(x[lo:hi]).to(dev), [Mesh(data=d, hold_history=True) for d in datas[lo:hi]])
+        torch.nn.CrossEntropyLoss(ignore_index=-1)(out, torch.from_numpy(y[lo:hi]).to(dev)).backward()
+        return red.flat.double().cpu().numpy()
+
+    want = (2.0 / 3.0) * grad_of(0, 2) + (1.0 / 3.0) * grad_of(2, 3)
+    got, split = res[0][2].astype(np.float64), res[0][1]
+    scale = float(np.abs(want).max())
+    assert float(np.abs(got[:split] - want[:split]).max()) <= 2e-5 * scale
+    assert float(np.abs(got[split:] - want[split:]).max()) <= 2e-5 * scale
