@@ -408,14 +408,14 @@ def main():
     # timed region late and every other rank's first timed step waited ~4 ms for it at the all-reduce -- 0.2-0.3 ms per step
     # of a 20-step run, which is what rounds 1 and 2 had been reading as a multi-GPU scaling loss
     sampler = ClockSampler(local) if rank == 0 else None
+    import gc
+    gc.collect()                                                        # (before the barrier, like everything that takes time)
+    gc.disable()                                                        # a collector pause on one rank stalls every rank at the all-reduce
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     launches0 = _lib.launch_count()
     evs = []
-    import gc
-    gc.collect()
-    gc.disable()                                                        # a collector pause on one rank stalls every rank at the all-reduce
     for _ in range(args.steps):
         if not args.no_flush:
             flush.fill_(1)                                              # L2 flush between timed steps (not timed)
@@ -489,6 +489,7 @@ def main():
     if world > 1 and gs is not None:
         reducer.enabled = False
         saved_state = gs._training_state()                            # these replays update with un-reduced gradients: undone below
+        own, err = float('nan'), None
         try:
             gs0 = GraphedTrainStep(net, crit, reducer, opt, [Mesh(data=d, hold_history=hold) for d in datas], x, labels, E, source='device')
             for _ in range(3):
@@ -506,6 +507,8 @@ def main():
             own = sum(ea.elapsed_time(eb) for ea, eb in ev0) / len(ev0)
             gs0.close()
             del gs0
+        except Exception as e:                                       # noqa: BLE001  (diagnostics must not cost the bench line)
+            err = str(e)[:200]
         finally:
             reducer.enabled = True
             gs._restore_training_state(saved_state)
@@ -515,10 +518,11 @@ def main():
         dist.all_gather(allr, mine)
         own_r = [float(t[0]) for t in allr]
         step_ms = total_ms / args.steps
-        attribution = {'own_step_ms_per_rank': own_r, 'step_ms_with_allreduce': step_ms,
+        attribution = {'error': err} if any(v != v for v in own_r) else {'own_step_ms_per_rank': own_r, 'step_ms_with_allreduce': step_ms,
                        'slowest_rank_ms': max(own_r), 'mean_rank_ms': sum(own_r) / world,
                        'straggler_ms': max(own_r) - sum(own_r) / world,
                        'allreduce_and_skew_ms': step_ms - max(own_r),
+                       'allreduce_and_skew_ms_by_median_step': max(r['median'] for r in step_spread) - max(own_r),
                        'note': 'device time (CUDA events) of the step replayed as a graph: per rank without the all-reduce node '
                                '(ranks run alone) vs the timed region with it.  straggler = slowest rank - mean rank (every '
                                'rank has other meshes: its pool kernels last as long as its slowest mesh); the rest of the '

@@ -52,11 +52,8 @@ __device__ __forceinline__ void slab_colsums(const NormShape s, float* __restric
             u[0] += a.x; u[1] += a.y; u[2] += a.z; u[3] += a.w;
             v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
         }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            sm[(ty * 2 + 0) * s.C + (tx << 2) + j] = u[j];
-            sm[(ty * 2 + 1) * s.C + (tx << 2) + j] = v[j];
-        }
+        *reinterpret_cast<float4*>(sm + (ty * 2 + 0) * s.C + (tx << 2)) = make_float4(u[0], u[1], u[2], u[3]);
+        *reinterpret_cast<float4*>(sm + (ty * 2 + 1) * s.C + (tx << 2)) = make_float4(v[0], v[1], v[2], v[3]);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < 2 * s.C; i += NT) {
@@ -320,11 +317,10 @@ struct FusedShape { int nblocks, rows, C, G, CW; };
 __device__ __forceinline__ void fused_reduce_columns(float* red, float* tot, const float (&u)[4], const float (&v)[4], int tx, int ty,
                                                      int rl, int CW) {
     // red[ty][2][CW] -> tot[2][CW]
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        red[(ty * 2 + 0) * CW + (tx << 2) + j] = u[j];
-        red[(ty * 2 + 1) * CW + (tx << 2) + j] = v[j];
-    }
+    // one 16-byte store per thread and quantity: a quarter warp writes 128 contiguous bytes (the scalar form put the four
+    // rows of a warp on the same banks: 4-way conflicts on every store)
+    *reinterpret_cast<float4*>(red + (ty * 2 + 0) * CW + (tx << 2)) = make_float4(u[0], u[1], u[2], u[3]);
+    *reinterpret_cast<float4*>(red + (ty * 2 + 1) * CW + (tx << 2)) = make_float4(v[0], v[1], v[2], v[3]);
     __syncthreads();
     for (int i = threadIdx.x; i < 2 * CW; i += NT) {
         const int which = i / CW, c = i - which * CW;

@@ -23,6 +23,8 @@ import torch
 from . import functional as Fn
 from .mesh import MeshBatch
 
+_CAPTURE_STREAM = {}     # device -> the stream every GraphedTrainStep warms up and captures on
+
 
 class GraphedTrainStep:
     def __init__(self, net, criterion, reducer, optimizer, meshes, x, y, E, source='host', V_cap=0, ve_cap=0, warmup=3,
@@ -95,7 +97,8 @@ class GraphedTrainStep:
         finally:
             Fn.end_step()                           # also on an exception: a dangling step token would make later backward
                                                     # passes write straight into p.grad
-        if self.collective == 'in-graph':
+        loss = loss.detach()                        # drop the autograd graph: it would keep the parameters' AccumulateGrad nodes
+        if self.collective == 'in-graph':           # (and the stream they were created on) alive between objects
             self._enqueue_tail(loss)
         return loss
 
@@ -104,7 +107,7 @@ class GraphedTrainStep:
         if self.collective == 'in-graph':
             self.reducer.allreduce()
         self.opt.step_state()
-        self.loss_host.copy_(loss.detach(), non_blocking=True)
+        self.loss_host.copy_(loss, non_blocking=True)
 
     def _capture(self, warmup):
         """Warm-up (allocator, lazy kernel configuration, NCCL) on a side stream, then capture.  The warm-up steps are real
@@ -112,7 +115,14 @@ class GraphedTrainStep:
         BatchNorm running statistics -- is undone afterwards, so building a GraphedTrainStep does not train."""
         saved = self._training_state()
         cur = torch.cuda.current_stream()
-        side = torch.cuda.Stream()
+        # warm-up AND capture on ONE side stream per device, shared by every object: autograd remembers the stream an
+        # AccumulateGrad node was created on and the engine, at the end of backward, makes the caller's stream wait for each of
+        # them -- even when the kernels wrote the gradient directly and handed autograd None.  With a different stream per
+        # object the second capture waits on a stream that is not part of it ("dependency created on uncaptured work in another
+        # stream", hit by the second GraphedTrainStep of a U-Net, which has no fc head to pull that stream into the capture).
+        side = self._stream = _CAPTURE_STREAM.get(self.device)
+        if side is None:
+            side = self._stream = _CAPTURE_STREAM[self.device] = torch.cuda.Stream(device=self.device)
         side.wait_stream(cur)
         between = self.collective == 'between'
         with torch.cuda.stream(side):
@@ -125,12 +135,12 @@ class GraphedTrainStep:
         torch.cuda.synchronize()
         self.batch.check()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph, stream=side):
             self.loss = self._enqueue()
         self.graph_tail = None
         if between:
             self.graph_tail = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph_tail, pool=self.graph.pool()):
+            with torch.cuda.graph(self.graph_tail, pool=self.graph.pool(), stream=side):
                 self._enqueue_tail(self.loss)
         self.warmup_steps = max(1, warmup)
         self._restore_training_state(saved)
