@@ -53,6 +53,10 @@ int mcnn_debug_set_norm_fused(int on);
  * of the incoming level (sequential up to 1000 edges, rounds above), 1 = always the round kernel, 2 = always the sequential one */
 int mcnn_debug_set_pool_mode(int mode);
 
+/* diagnostics only: programmatic dependent launch of every kernel of the library (default off; MESHCNN_B200_PDL=1): 0 = plain
+ * stream-ordered launches */
+int mcnn_debug_set_pdl(int on);
+
 #ifdef __cplusplus
 }
 #endif

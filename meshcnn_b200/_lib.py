@@ -79,6 +79,7 @@ DEBUG_SIGNATURES = {
     'mcnn_debug_set_tc_bw_ot': (_c_int, [_c_int]),
     'mcnn_debug_set_tc_bw_tmem_a': (_c_int, [_c_int]),
     'mcnn_debug_set_pool_mode': (_c_int, [_c_int]),
+    'mcnn_debug_set_pdl': (_c_int, [_c_int]),
     'mcnn_debug_sk_prof': (_c_int, [_c_vp, _c_int]),
     'mcnn_debug_sk_cta_times': (_c_int, [_c_vp]),
     'mcnn_debug_set_tc': (_c_int, [_c_int]),

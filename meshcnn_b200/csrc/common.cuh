@@ -24,6 +24,33 @@ inline int after_launch() {
 
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// Programmatic dependent launch.  A training step is a chain of ~140 short dependent kernels; with the attribute below the
+// next kernel of a stream is launched (CTAs scheduled, as far as the SM resources allow) while its predecessor still runs, and
+// its threads block in pdl_enter() until the predecessor grid has completed and its memory is visible.  Every kernel calls
+// pdl_enter() as its FIRST statement, so nothing is read or written early: only launch latency and CTA ramp-up overlap.
+// Without the attribute both instructions are no-ops.  OFF by default: measured on the cubes step it changes nothing (2.71 ms
+// with and without -- the replayed graph has no launch gaps worth hiding; the step is the sum of its kernels' durations).
+// mcnn_debug_set_pdl(1) / MESHCNN_B200_PDL=1 switch it on.
+extern int g_pdl;
+__device__ __forceinline__ void pdl_enter() {
+    asm volatile("griddepcontrol.launch_dependents;\n\tgriddepcontrol.wait;" ::: "memory");
+}
+
+template <class... KArgs, class... Args>
+inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_pdl ? 1 : 0;
+    (void)cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);     // errors are picked up by after_launch()
+}
+
 // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute of a kernel: one guard per launch site remembers what
 // has been configured on each device, so a process that drives several GPUs (or several host threads) configures every one.
 // Racing threads may both set the attribute; that is idempotent.

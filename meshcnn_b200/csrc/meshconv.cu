@@ -89,6 +89,7 @@ __device__ __forceinline__ void build_g_tile(float* Gs, int ld, const int (*nb)[
 
 // weight [Cout][Cin*5] -> wt [Cin*5][Cout]
 __global__ void weight_kmajor_kernel(const float* __restrict__ w, float* __restrict__ wt, int K, int Cout) {
+    pdl_enter();
     __shared__ float t[32][33];
     int k0 = blockIdx.x * 32, o0 = blockIdx.y * 32;
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -106,6 +107,7 @@ __global__ void __launch_bounds__(NTHREADS)
 meshconv_fwd_kernel(const float* __restrict__ x, const int32_t* __restrict__ gemm, const int32_t* __restrict__ ec,
                     const float* __restrict__ wt, const float* __restrict__ bias, float* __restrict__ out,
                     int B, int E, int Cin, int Cout) {
+    pdl_enter();
     __shared__ int nb[TM][5];
     __shared__ __align__(16) float As[KK * LDT];
     __shared__ __align__(16) float Ws[KK * (TN + 4)];
@@ -188,6 +190,7 @@ __global__ void __launch_bounds__(NTHREADS)
 meshconv_bwd_data_kernel(const float* __restrict__ dout, const float* __restrict__ x, const int32_t* __restrict__ gemm,
                          const int32_t* __restrict__ ec, const float* __restrict__ w, float* __restrict__ dx,
                          int B, int E, int Cin, int Cout) {
+    pdl_enter();
     __shared__ int nb[TM][5];
     __shared__ __align__(16) float As[OK * LDT];          // dout tile, [oo][r]
     __shared__ float Ws[OK * (KK + 1)];                    // weight tile, [oo][cl*5+k]
@@ -286,6 +289,7 @@ __global__ void __launch_bounds__(NTHREADS)
 meshconv_bwd_weight_kernel(const float* __restrict__ dout, const float* __restrict__ x, const int32_t* __restrict__ gemm,
                            const int32_t* __restrict__ ec, float* __restrict__ dw, float* __restrict__ dbias,
                            int B, int E, int Cin, int Cout, int msplit) {
+    pdl_enter();
     __shared__ int nb[TM][5];
     __shared__ __align__(16) float As[TM * (TN + 4)];     // dout tile [mm][oo]
     __shared__ float Gs[TM * (KK + 1)];                   // G tile    [mm][cl*5+k]
@@ -362,11 +366,11 @@ extern "C" int mcnn_meshconv_fwd(const float* x, const int32_t* gemm, const int3
     if (!x || !gemm || !ec || !weight || !out || !wt_ws || B <= 0 || E <= 0 || Cin <= 0 || Cout <= 0) return MCNN_E_BADARG;
     cudaStream_t st = (cudaStream_t)stream;
     const int K = Cin * 5;
-    weight_kmajor_kernel<<<dim3(ceil_div(K, 32), ceil_div(Cout, 32)), dim3(32, 8), 0, st>>>(weight, wt_ws, K, Cout);
+    launch_k(weight_kmajor_kernel, dim3(ceil_div(K, 32), ceil_div(Cout, 32)), dim3(32, 8), 0, st, weight, wt_ws, K, Cout);
     int rc = after_launch();
     if (rc) return rc;
     dim3 grid(ceil_div(B * E, TM), ceil_div(Cout, TN));
-    meshconv_fwd_kernel<<<grid, NTHREADS, 0, st>>>(x, gemm, ec, wt_ws, bias, out, B, E, Cin, Cout);
+    launch_k(meshconv_fwd_kernel, grid, NTHREADS, 0, st, x, gemm, ec, wt_ws, bias, out, B, E, Cin, Cout);
     return after_launch();
 }
 
@@ -374,7 +378,7 @@ extern "C" int mcnn_meshconv_bwd_data(const float* dout, const float* x, const i
                                       const float* weight, float* dx, int B, int E, int Cin, int Cout, void* stream) {
     if (!dout || !x || !gemm || !ec || !weight || !dx || B <= 0 || E <= 0 || Cin <= 0 || Cout <= 0) return MCNN_E_BADARG;
     dim3 grid(ceil_div(B * E, TM), ceil_div(Cin, CK));
-    meshconv_bwd_data_kernel<<<grid, NTHREADS, 0, (cudaStream_t)stream>>>(dout, x, gemm, ec, weight, dx, B, E, Cin, Cout);
+    launch_k(meshconv_bwd_data_kernel, grid, NTHREADS, 0, (cudaStream_t)stream, dout, x, gemm, ec, weight, dx, B, E, Cin, Cout);
     return after_launch();
 }
 
@@ -387,6 +391,6 @@ extern "C" int mcnn_meshconv_bwd_weight(const float* dout, const float* x, const
     int msplit = ceil_div(ceil_div(B * E, max(1, 296 / tiles)), TM) * TM;
     msplit = min(MSPLIT_MAX, max(TM, msplit));
     dim3 grid(ceil_div(B * E, msplit), ceil_div(Cout, TN), ceil_div(Cin, CK));
-    meshconv_bwd_weight_kernel<<<grid, NTHREADS, 0, (cudaStream_t)stream>>>(dout, x, gemm, ec, dweight, dbias, B, E, Cin, Cout, msplit);
+    launch_k(meshconv_bwd_weight_kernel, grid, NTHREADS, 0, (cudaStream_t)stream, dout, x, gemm, ec, dweight, dbias, B, E, Cin, Cout, msplit);
     return after_launch();
 }

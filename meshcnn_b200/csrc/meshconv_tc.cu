@@ -61,6 +61,7 @@ __host__ __device__ constexpr int fw_kpos(int blk, int p) {
 // The rows n0 .. n0+N_TILE of one K block are N_TILE*128 contiguous bytes, so a CTA fetches its B tile with one bulk copy
 // per half instead of pushing it through registers.
 __global__ void weight_tc_layout_kernel(const float* __restrict__ w, float* __restrict__ img, int Cin, int Cout) {
+    pdl_enter();
     const int K = 5 * Cin;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= Cout * K) return;
@@ -110,6 +111,7 @@ __global__ void __launch_bounds__((PW + 1) * 32, 1)
 meshconv_fwd_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ gemm, const int32_t* __restrict__ ec,
                        const float* __restrict__ wt, const float* __restrict__ bias, float* __restrict__ out,
                        int8_t* __restrict__ signs, int B, int E, int Cin, int Cout) {
+    pdl_enter();
     using S = TcSmem<N_TILE>;
     constexpr int NTHREADS = (PW + 1) * 32;      // PW producer / epilogue warps + the MMA warp
     constexpr int PT = PW * 32;                  // producer threads
@@ -475,6 +477,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1)
 meshconv_fwd_tc_sk_kernel(const float* __restrict__ x, const int32_t* __restrict__ gemm, const int32_t* __restrict__ ec,
                           const float* __restrict__ wt, const float* __restrict__ bias, float* __restrict__ out,
                           int8_t* __restrict__ signs, float* part, int* flags, int B, int E, int Cin, int Cout, int one_pass) {
+    pdl_enter();
     using S = SkSmem<N_TILE>;
     using SS = SkSmem<N_TILE>;
     constexpr int PW = TC_PRODUCER_WARPS, PT = PW * 32;
@@ -878,6 +881,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 meshconv_fwd_tc2_kernel(const float* __restrict__ x, const int32_t* __restrict__ gemm, const int32_t* __restrict__ ec,
                         const float* __restrict__ wt, const float* __restrict__ bias, float* __restrict__ out,
                         int8_t* __restrict__ signs, int B, int E, int Cin, int Cout) {
+    pdl_enter();
     using S = Tc2Smem;
     constexpr int N_TILE = 256;
     extern __shared__ unsigned char smem_raw[];
@@ -1098,7 +1102,7 @@ static int launch_fwd_tc2(const float* x, const int32_t* gemm, const int32_t* ec
     if (int grc = configured.ensure(meshconv_fwd_tc2_kernel, S::TOTAL)) return grc;
     const int mtiles = ceil_div(B * E, TC_M);
     dim3 grid(2 * ceil_div(mtiles, 2), Cout / 256);          // whole CTA pairs; a surplus CTA works on rows >= M (all zero)
-    meshconv_fwd_tc2_kernel<<<grid, TC_THREADS, S::TOTAL, st>>>(x, gemm, ec, wt, bias, out, signs, B, E, Cin, Cout);
+    launch_k(meshconv_fwd_tc2_kernel, grid, TC_THREADS, S::TOTAL, st, x, gemm, ec, wt, bias, out, signs, B, E, Cin, Cout);
     return after_launch();
 }
 
@@ -1109,7 +1113,7 @@ static int launch_fwd_tc(const float* x, const int32_t* gemm, const int32_t* ec,
     static DynSmemGuard configured;
     if (int grc = configured.ensure(meshconv_fwd_tc_kernel<N_TILE, PW>, S::TOTAL)) return grc;
     dim3 grid(ceil_div(B * E, TC_M), ceil_div(Cout, N_TILE));
-    meshconv_fwd_tc_kernel<N_TILE, PW><<<grid, (PW + 1) * 32, S::TOTAL, st>>>(x, gemm, ec, wt, bias, out, signs, B, E, Cin, Cout);
+    launch_k(meshconv_fwd_tc_kernel<N_TILE, PW>, grid, (PW + 1) * 32, S::TOTAL, st, x, gemm, ec, wt, bias, out, signs, B, E, Cin, Cout);
     return after_launch();
 }
 
@@ -1128,7 +1132,7 @@ static int launch_fwd_tc_sk(const float* x, const int32_t* gemm, const int32_t* 
     if (g_tc_sk_ctas > 0) G = min((long long)g_tc_sk_ctas, total);
     int* flags = reinterpret_cast<int*>(sk_ws);
     float* part = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(sk_ws) + SK_FLAG_BYTES);
-    meshconv_fwd_tc_sk_kernel<N_TILE><<<(int)G, SK_THREADS, S::TOTAL, st>>>(x, gemm, ec, wt, bias, out, signs, part, flags, B, E, Cin, Cout, one_pass);
+    launch_k(meshconv_fwd_tc_sk_kernel<N_TILE>, (int)G, SK_THREADS, S::TOTAL, st, x, gemm, ec, wt, bias, out, signs, part, flags, B, E, Cin, Cout, one_pass);
     return after_launch();
 }
 
@@ -1163,6 +1167,7 @@ struct BdSmem {
 // weight [Cout][Cin][5] -> B operand image of the data-gradient GEMM, TF32 head / remainder:
 //   img[hi|lo][cb][kb][160 rows x 128 bytes swizzled],  row n = k5*32 + bd_col(cl) (c = cb*32 + cl),  K = output channels
 __global__ void weight_tc_bwd_layout_kernel(const float* __restrict__ w, float* __restrict__ img, int Cin, int Cout) {
+    pdl_enter();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= 5 * Cin * Cout) return;
     const int row = idx / Cout, o = idx - row * Cout;
@@ -1182,6 +1187,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 meshconv_bwd_data_tc_kernel(const float* __restrict__ dout, const float* __restrict__ x, const int32_t* __restrict__ gemm,
                             const int32_t* __restrict__ ec, const float* __restrict__ wtb, float* __restrict__ dx,
                             const int8_t* __restrict__ signs, int B, int E, int Cin, int Cout) {
+    pdl_enter();
     using S = BdSmem;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -1377,6 +1383,7 @@ __global__ void __launch_bounds__(BDP_THREADS, 1)
 meshconv_bwd_data_tc_p_kernel(const float* __restrict__ dout, const int32_t* __restrict__ gemm, const int32_t* __restrict__ ec,
                               const float* __restrict__ wtb, float* __restrict__ dx, const int8_t* __restrict__ signs,
                               int B, int E, int Cin, int Cout, int one_pass) {
+    pdl_enter();
     using S = BdpSmem;
     constexpr int PW = BDP_PRODUCER_WARPS, PT = PW * 32, ET = BDP_EPI_WARPS * 32;
     static_assert(PW == 8, "two producer warps per TMEM lane quarter");
@@ -1668,6 +1675,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 meshconv_bwd_weight_tc_kernel(const float* __restrict__ dout, const float* __restrict__ x, const int32_t* __restrict__ gemm,
                               const int32_t* __restrict__ ec, float* __restrict__ ws, int B, int E, int Cin, int Cout,
                               int rows_per_split) {
+    pdl_enter();
     using S = BwSmem<OT>;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -1920,6 +1928,7 @@ __global__ void __launch_bounds__(BWA_THREADS, 1)
 meshconv_bwd_weight_tca_kernel(const float* __restrict__ dout, const float* __restrict__ x, const int32_t* __restrict__ gemm,
                                const int32_t* __restrict__ ec, float* __restrict__ ws, int B, int E, int Cin, int Cout,
                                int rows_per_split, int one_pass) {
+    pdl_enter();
     using S = BwaSmem<OT>;
     constexpr int AV = 16 * OT;                              // dout values per A thread and K block (OT == 1: half of the edges)
     constexpr int MMA_WARP = BWA_A_WARPS + BWA_B_WARPS;
@@ -2162,6 +2171,7 @@ meshconv_bwd_weight_tca_kernel(const float* __restrict__ dout, const float* __re
 
 // dW[i] = sum_s ws[s][i]
 __global__ void reduce_splits_kernel(const float* __restrict__ ws, float* __restrict__ dst, int n, int splits) {
+    pdl_enter();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float acc = 0.f;
@@ -2172,6 +2182,7 @@ __global__ void reduce_splits_kernel(const float* __restrict__ ws, float* __rest
 // column sums of dout [M][Cout] in two deterministic stages: part[p][o], then reduce_splits_kernel
 constexpr int COLSUM_PARTS = 64;
 __global__ void colsum_part_kernel(const float* __restrict__ dout, float* __restrict__ part, int M, int Cout) {
+    pdl_enter();
     __shared__ float red[8][33];
     const int o = blockIdx.x * 32 + threadIdx.x;
     const int p = blockIdx.y;
@@ -2223,11 +2234,11 @@ extern "C" int mcnn_meshconv_tc_weight_images(const float* weight, float* fwd_im
     const int total = Cout * 5 * Cin;
     int rc = MCNN_OK;
     if (fwd_img != nullptr) {
-        weight_tc_layout_kernel<<<ceil_div(total, 256), 256, 0, st>>>(weight, fwd_img, Cin, Cout);
+        launch_k(weight_tc_layout_kernel, ceil_div(total, 256), 256, 0, st, weight, fwd_img, Cin, Cout);
         if ((rc = after_launch())) return rc;
     }
     if (bwd_img != nullptr) {
-        weight_tc_bwd_layout_kernel<<<ceil_div(total, 256), 256, 0, st>>>(weight, bwd_img, Cin, Cout);
+        launch_k(weight_tc_bwd_layout_kernel, ceil_div(total, 256), 256, 0, st, weight, bwd_img, Cin, Cout);
         rc = after_launch();
     }
     return rc;
@@ -2248,7 +2259,7 @@ extern "C" int mcnn_meshconv_fwd_tc_signs(const float* x, const int32_t* gemm, c
     const int total = Cout * 5 * Cin;
     int rc = MCNN_OK;
     if (weight != nullptr) {                                 // NULL: wt_ws already holds the image (mcnn_meshconv_tc_weight_images)
-        weight_tc_layout_kernel<<<ceil_div(total, 256), 256, 0, st>>>(weight, wt_ws, Cin, Cout);
+        launch_k(weight_tc_layout_kernel, ceil_div(total, 256), 256, 0, st, weight, wt_ws, Cin, Cout);
         if ((rc = after_launch())) return rc;
     }
     const int mtiles = ceil_div(B * E, TC_M);
@@ -2279,7 +2290,7 @@ extern "C" int mcnn_meshconv_fwd_tc_sk_p(const float* x, const int32_t* gemm, co
     cudaStream_t st = (cudaStream_t)stream;
     int rc = MCNN_OK;
     if (weight != nullptr) {
-        weight_tc_layout_kernel<<<ceil_div(Cout * 5 * Cin, 256), 256, 0, st>>>(weight, wt_ws, Cin, Cout);
+        launch_k(weight_tc_layout_kernel, ceil_div(Cout * 5 * Cin, 256), 256, 0, st, weight, wt_ws, Cin, Cout);
         if ((rc = after_launch())) return rc;
     }
     int nt = (Cout % 256 == 0) ? 256 : ((Cout % 128 == 0) ? 128 : 64);
@@ -2329,7 +2340,7 @@ extern "C" int mcnn_meshconv_bwd_data_tc_signs_p(const float* dout, const float*
     const int total = Cout * 5 * Cin;
     int rc = MCNN_OK;
     if (weight != nullptr) {                                 // NULL: wtb_ws already holds the image
-        weight_tc_bwd_layout_kernel<<<ceil_div(total, 256), 256, 0, st>>>(weight, wtb_ws, Cin, Cout);
+        launch_k(weight_tc_bwd_layout_kernel, ceil_div(total, 256), 256, 0, st, weight, wtb_ws, Cin, Cout);
         if ((rc = after_launch())) return rc;
     }
     static DynSmemGuard configured;
@@ -2339,11 +2350,11 @@ extern "C" int mcnn_meshconv_bwd_data_tc_signs_p(const float* dout, const float*
         if (int grc = configured_p.ensure(meshconv_bwd_data_tc_p_kernel, BdpSmem::TOTAL)) return grc;
         const long long items = (long long)ceil_div(B * E, TC_M) * (Cin / 32);
         const int G = (int)min((long long)sm_count(), items);
-        meshconv_bwd_data_tc_p_kernel<<<G, BDP_THREADS, BdpSmem::TOTAL, st>>>(dout, gemm, ec, wtb_ws, dx, signs, B, E, Cin, Cout, one_pass);
+        launch_k(meshconv_bwd_data_tc_p_kernel, G, BDP_THREADS, BdpSmem::TOTAL, st, dout, gemm, ec, wtb_ws, dx, signs, B, E, Cin, Cout, one_pass);
         return after_launch();
     }
     dim3 grid(ceil_div(B * E, TC_M), Cin / 32);
-    meshconv_bwd_data_tc_kernel<<<grid, TC_THREADS, BdSmem::TOTAL, st>>>(dout, x, gemm, ec, wtb_ws, dx, signs, B, E, Cin, Cout);
+    launch_k(meshconv_bwd_data_tc_kernel, grid, TC_THREADS, BdSmem::TOTAL, st, dout, x, gemm, ec, wtb_ws, dx, signs, B, E, Cin, Cout);
     return after_launch();
 }
 
@@ -2378,36 +2389,36 @@ extern "C" int mcnn_meshconv_bwd_weight_tc_p(const float* dout, const float* x, 
             static DynSmemGuard cfg2;
             if (int grc = cfg2.ensure(meshconv_bwd_weight_tca_kernel<2>, BwaSmem<2>::TOTAL)) return grc;
             dim3 grid(S, ceil_div(Cout, 256), Cin / 32);
-            meshconv_bwd_weight_tca_kernel<2><<<grid, BWA_THREADS, BwaSmem<2>::TOTAL, st>>>(dout, x, gemm, ec, ws, B, E, Cin, Cout, rows, one_pass);
+            launch_k(meshconv_bwd_weight_tca_kernel<2>, grid, BWA_THREADS, BwaSmem<2>::TOTAL, st, dout, x, gemm, ec, ws, B, E, Cin, Cout, rows, one_pass);
         } else {
             static DynSmemGuard cfg1;
             if (int grc = cfg1.ensure(meshconv_bwd_weight_tca_kernel<1>, BwaSmem<1>::TOTAL)) return grc;
             dim3 grid(S, ceil_div(Cout, 128), Cin / 32);
-            meshconv_bwd_weight_tca_kernel<1><<<grid, BWA_THREADS, BwaSmem<1>::TOTAL, st>>>(dout, x, gemm, ec, ws, B, E, Cin, Cout, rows, one_pass);
+            launch_k(meshconv_bwd_weight_tca_kernel<1>, grid, BWA_THREADS, BwaSmem<1>::TOTAL, st, dout, x, gemm, ec, ws, B, E, Cin, Cout, rows, one_pass);
         }
     } else if (bw_ot(Cout) == 2) {
         static DynSmemGuard configured2;
         if (int grc = configured2.ensure(meshconv_bwd_weight_tc_kernel<2>, BwSmem<2>::TOTAL)) return grc;
         dim3 grid(S, ceil_div(Cout, 256), Cin / 32);
-        meshconv_bwd_weight_tc_kernel<2><<<grid, TC_THREADS, BwSmem<2>::TOTAL, st>>>(dout, x, gemm, ec, ws, B, E, Cin, Cout, rows);
+        launch_k(meshconv_bwd_weight_tc_kernel<2>, grid, TC_THREADS, BwSmem<2>::TOTAL, st, dout, x, gemm, ec, ws, B, E, Cin, Cout, rows);
     } else {
         static DynSmemGuard configured;
         if (int grc = configured.ensure(meshconv_bwd_weight_tc_kernel<1>, BwSmem<1>::TOTAL)) return grc;
         dim3 grid(S, ceil_div(Cout, 128), Cin / 32);
-        meshconv_bwd_weight_tc_kernel<1><<<grid, TC_THREADS, BwSmem<1>::TOTAL, st>>>(dout, x, gemm, ec, ws, B, E, Cin, Cout, rows);
+        launch_k(meshconv_bwd_weight_tc_kernel<1>, grid, TC_THREADS, BwSmem<1>::TOTAL, st, dout, x, gemm, ec, ws, B, E, Cin, Cout, rows);
     }
     int rc = after_launch();
     if (rc) return rc;
     const int n = Cout * Cin * 5;
-    reduce_splits_kernel<<<ceil_div(n, 256), 256, 0, st>>>(ws, dweight, n, S);
+    launch_k(reduce_splits_kernel, ceil_div(n, 256), 256, 0, st, ws, dweight, n, S);
     rc = after_launch();
     if (rc) return rc;
     if (dbias != nullptr) {
         float* part = ws + (size_t)S * n;
-        colsum_part_kernel<<<dim3(ceil_div(Cout, 32), COLSUM_PARTS), dim3(32, 8), 0, st>>>(dout, part, M, Cout);
+        launch_k(colsum_part_kernel, dim3(ceil_div(Cout, 32), COLSUM_PARTS), dim3(32, 8), 0, st, dout, part, M, Cout);
         rc = after_launch();
         if (rc) return rc;
-        reduce_splits_kernel<<<ceil_div(Cout, 256), 256, 0, st>>>(part, dbias, Cout, COLSUM_PARTS);
+        launch_k(reduce_splits_kernel, ceil_div(Cout, 256), 256, 0, st, part, dbias, Cout, COLSUM_PARTS);
         rc = after_launch();
     }
     return rc;

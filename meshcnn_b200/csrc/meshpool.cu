@@ -614,6 +614,7 @@ struct RoundCtl {                       // shared by the warps of the CTA
 
 template <class P>
 __global__ void __launch_bounds__(P::THREADS, 1) pool_collapse_kernel(const mcnn_pool_args a) {
+    pdl_enter();
     typedef typename P::idx_t idx_t;
     typedef typename P::uidx_t uidx_t;
     typedef typename P::pair_t pair_t;
@@ -1352,6 +1353,7 @@ __global__ void __launch_bounds__(P::THREADS, 1) pool_collapse_kernel(const mcnn
 // squared feature norm of every edge row (the collapse priority, mesh_pool.py:197).  Eight lanes per row: a row is read as
 // contiguous 128-byte pieces; the eight partial sums are combined in a fixed butterfly order (deterministic).
 __global__ void pool_norms_kernel(const float* __restrict__ x, float* __restrict__ norms, int M, int C) {
+    pdl_enter();
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int m = (int)(t >> 3), l = (int)(t & 7);
     float s = 0.f;
@@ -1414,6 +1416,7 @@ __global__ void segment_kernel(const float* __restrict__ in, float* __restrict__
                                const int32_t* __restrict__ idx, const int32_t* __restrict__ aux_ptr,
                                const float* __restrict__ occ, const int32_t* __restrict__ valid, int B, int R_out,
                                int R_in, int ptr_stride, int aux_stride, int occ_stride, int C, int nnz_cap) {
+    pdl_enter();
     // grid (row blocks, meshes); a CTA covers 256 / cq rows, one thread per (row, channel quad).  32-bit index arithmetic
     // only (the flat 64-bit thread id of the first version cost three 64-bit divisions per thread).
     const int cq = (C + 3) >> 2;
@@ -1468,10 +1471,10 @@ static int launch_segment(const float* in, float* out, const int32_t* ptr, const
     const int rpc = threads / cq;
     dim3 grid((unsigned)ceil_div(R_out, rpc), (unsigned)B);
     if ((C & 3) == 0)
-        segment_kernel<MODE, true><<<grid, threads, 0, st>>>(in, out, ptr, idx, aux_ptr, occ, valid, B, R_out, R_in,
+        launch_k(segment_kernel<MODE, true>, grid, threads, 0, st, in, out, ptr, idx, aux_ptr, occ, valid, B, R_out, R_in,
                                                              ptr_stride, aux_stride, occ_stride, C, nnz_cap);
     else
-        segment_kernel<MODE, false><<<grid, threads, 0, st>>>(in, out, ptr, idx, aux_ptr, occ, valid, B, R_out, R_in,
+        launch_k(segment_kernel<MODE, false>, grid, threads, 0, st, in, out, ptr, idx, aux_ptr, occ, valid, B, R_out, R_in,
                                                               ptr_stride, aux_stride, occ_stride, C, nnz_cap);
     return after_launch();
 }
@@ -1503,7 +1506,7 @@ extern "C" size_t mcnn_pool_smem_limit(void) { return 227 * 1024 - 9 * 1024; }  
 extern "C" int mcnn_pool_norms(const float* x, float* norms, int B, int E, int C, void* stream) {
     if (!x || !norms || B <= 0 || E <= 0 || C <= 0) return MCNN_E_BADARG;
     const int M = B * E;
-    pool_norms_kernel<<<ceil_div(M, 32), 256, 0, (cudaStream_t)stream>>>(x, norms, M, C);
+    launch_k(pool_norms_kernel, ceil_div(M, 32), 256, 0, (cudaStream_t)stream, x, norms, M, C);
     return after_launch();
 }
 
@@ -1519,13 +1522,13 @@ extern "C" int mcnn_pool_collapse(const mcnn_pool_args* a, void* stream) {
         if (g_pool_mode == 2 || (g_pool_mode == 0 && a->E_in <= POOL_SEQ_MAX_EDGES)) return seq::launch(a, nullptr, (cudaStream_t)stream, false);
         static DynSmemGuard configured;
         if (int grc = configured.ensure(pool_collapse_kernel<Narrow>, smem)) return grc;
-        pool_collapse_kernel<Narrow><<<a->B, Narrow::THREADS, smem, (cudaStream_t)stream>>>(*a);
+        launch_k(pool_collapse_kernel<Narrow>, a->B, Narrow::THREADS, smem, (cudaStream_t)stream, *a);
         return after_launch();
     }
     // large meshes: the same algorithm with 32-bit ids on a global-memory workspace (one slice per mesh)
     if (a->workspace == nullptr) return MCNN_E_TOO_LARGE;
     if ((size_t)a->workspace_stride < mcnn_pool_workspace_bytes(a->E_in, a->V, a->ve_cap, a->vs != nullptr)) return MCNN_E_BADARG;
-    pool_collapse_kernel<Wide><<<a->B, Wide::THREADS, 0, (cudaStream_t)stream>>>(*a);
+    launch_k(pool_collapse_kernel<Wide>, a->B, Wide::THREADS, 0, (cudaStream_t)stream, *a);
     return after_launch();
 }
 

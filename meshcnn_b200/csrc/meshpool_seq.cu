@@ -126,7 +126,7 @@ struct WarpCtx {
     int bump, bump_end;        // free room behind the lists (entries), used by wop_repack
 };
 
-enum { WOP_EXIT = 0, WOP_ONE_RING = 1, WOP_REMOVE_SCAN = 2 };
+enum { WOP_EXIT = 0, WOP_ONE_RING = 1, WOP_REMOVE_SCAN = 2, WOP_MERGE = 3 };
 constexpr int WQ_CAP = 32;
 
 struct WorkQueue {
@@ -196,6 +196,51 @@ __device__ __forceinline__ void wop_repack(WarpCtx<P>& w, int lane, int v) {
     }
     w.bump = out + total;
     __syncwarp();
+}
+
+// ve[v0].extend(ve[v1]) (mesh.py:35), posted by the collapse thread WITHOUT waiting: the helper builds the merged list while
+// thread 0 goes on to the next candidate (whose one-ring request queues up behind this operation; thread 0 touches no list
+// state before it has collected that answer).  Common case -- both lists are single slabs of <= 32 entries: both are read in
+// one go and written, tombstones dropped, as ONE slab into the free room, so the one-ring walks never meet a chain.
+// Otherwise: link the chains (O(1)) and re-pack if there is room.
+template <class P>
+__device__ __forceinline__ void wop_merge(WarpCtx<P>& w, int lane, int v0, int v1) {
+    typedef typename P::uidx_t uidx_t;
+    const unsigned n0 = (unsigned)w.slab_next[v0], n1 = (unsigned)w.slab_next[v1];
+    const int s0 = w.slab_start[v0], l0 = w.slab_len[v0], s1 = w.slab_start[v1], l1 = w.slab_len[v1];
+    if (n0 == P::NIL && n1 == P::NIL && l0 <= 32 && l1 <= 32 && w.bump + l0 + l1 <= w.bump_end) {
+        const unsigned x0 = (lane < l0) ? (unsigned)w.ve[s0 + lane] : P::NIL;
+        const unsigned x1 = (lane < l1) ? (unsigned)w.ve[s1 + lane] : P::NIL;
+        const unsigned lt = (1u << lane) - 1u;
+        const unsigned m0 = __ballot_sync(0xffffffffu, x0 != P::NIL), m1 = __ballot_sync(0xffffffffu, x1 != P::NIL);
+        const int out = w.bump, c0 = __popc(m0), c1 = __popc(m1);
+        if (x0 != P::NIL) {
+            const int dst = out + __popc(m0 & lt);
+            w.ve[dst] = (uidx_t)x0;
+            if (x0 != 0u) {
+                if ((int)w.eposa[x0] == s0 + lane) w.eposa[x0] = (uidx_t)dst;
+                else if ((int)w.eposb[x0] == s0 + lane) w.eposb[x0] = (uidx_t)dst;
+            }
+        }
+        if (x1 != P::NIL) {
+            const int dst = out + c0 + __popc(m1 & lt);
+            w.ve[dst] = (uidx_t)x1;
+            if (x1 != 0u) {
+                if ((int)w.eposa[x1] == s1 + lane) w.eposa[x1] = (uidx_t)dst;
+                else if ((int)w.eposb[x1] == s1 + lane) w.eposb[x1] = (uidx_t)dst;
+            }
+        }
+        if (lane == 0) { w.slab_start[v0] = (uidx_t)out; w.slab_len[v0] = (uidx_t)(c0 + c1); }
+        w.bump = out + c0 + c1;
+        __syncwarp();
+        return;
+    }
+    if (lane == 0) {
+        w.slab_next[(unsigned)w.chain_tail[v0]] = (uidx_t)v1;
+        w.chain_tail[v0] = w.chain_tail[v1];
+    }
+    __syncwarp();
+    wop_repack<P>(w, lane, v0);
 }
 
 // __is_one_ring_valid (mesh_pool.py:95-100); the lists may hold stale / dead edge ids.  stamp[w] = tagA marks w as an
@@ -321,9 +366,11 @@ __device__ void helper_warp_loop(WarpCtx<P>& w, WorkQueue* q, int lane, long lon
 #ifdef MCNN_POOL_PROF
         const long long th_ = clock64();
 #endif
-        int r;
+        int r = 0;
         if (rq.x == WOP_ONE_RING) {
             r = wop_one_ring<P>(w, lane, rq.y, rq.z, (uint32_t)rq.w, hprof ? hprof + 3 : nullptr);
+        } else if (rq.x == WOP_MERGE) {                      // nobody waits for this one
+            wop_merge<P>(w, lane, rq.y, rq.z);
         } else {                                             // WOP_REMOVE_SCAN: x leaves ve[a], then ve[b] (mesh.py:42-48)
             r = wop_list_remove<P>(w, lane, rq.z, rq.y) ? 1 : 0;
             if (r) r = wop_list_remove<P>(w, lane, rq.w, rq.y) ? 1 : 0;
@@ -557,30 +604,42 @@ struct Collapse {
         int v0, v1;
         ends(e, v0, v1);
         if (v0 == v1) { status = MCNN_ST_DEGENERATE; return; }
+        // ve[v0].extend(ve[v1]) : the helper warp moves v1's list behind v0's (ve[v1] is unreachable once every row holding v1
+        // reads v0); not waited for -- the next list operation is queued behind it
+        post(WOP_MERGE, v0, v1, 0);
         if (vs != nullptr) {
 #pragma unroll
             for (int k = 0; k < 3; ++k) vs[3 * v0 + k] = (vs[3 * v0 + k] + vs[3 * v1 + k]) / 2;
         }
         vmask[v1] = 0;
-        // ve[v0].extend(ve[v1]) : v1's chain moves behind v0's (ve[v1] is unreachable once every row holding v1 reads v0)
-        slab_next[(unsigned)chain_tail[v0]] = (uidx_t)v1;
-        chain_tail[v0] = chain_tail[v1];
         rep[v1] = (uidx_t)v0;         // edges[edges == v1] = v0 over every row
     }
 
-    // __pool_edge (mesh_pool.py:58-72)
-    __device__ int pool_edge(int e) {
-        bool r, side2 = false;
+    // __pool_edge (mesh_pool.py:58-72), general form
+    __device__ int pool_edge_generic(int e) {
+        bool r;
         PROF_T(0, r = has_boundaries(e));
         if (r) return MCNN_POP_REJ_BOUNDARY;
+        // the one-ring walk is the long pole of an attempt: it goes to the helper warp before the side cleaning.  An attempt that
+        // the side cleaning rejects does not collect the answer (every answer carries its sequence number; the next supersedes it)
         PROF_T(2, one_ring_request(e));
+        return pool_edge_tail(e);
+    }
+
+    // the same from the side cleaning on (the one-ring request is on its way)
+    __device__ int pool_edge_tail(int e) {
+        bool r, side2 = false;
         PROF_T(1, r = clean_side(e, 0));
         if (r) PROF_T(1, r = clean_side(e, 2) ? true : (side2 = true, false));
-        // nothing writes the one-ring tables between here and __pool_side(0): fetch its face record under the wait
-        const Face f0 = r ? face_info(e, 0) : Face();
-        const bool ring_ok = wait_result() == 2;             // always collected: the ring has one result slot
         if (!r) return side2 ? MCNN_POP_REJ_SIDE2 : MCNN_POP_REJ_SIDE0;
+        // nothing writes the one-ring tables between here and __pool_side(0): fetch its face record under the wait
+        const Face f0 = face_info(e, 0);
+        const bool ring_ok = wait_result() == 2;
         if (!ring_ok) return MCNN_POP_REJ_ONE_RING;
+        return commit_generic(e, f0);
+    }
+
+    __device__ int commit_generic(int e, const Face& f0) {
         PROF_T(3, pool_side(e, 0, f0));
         if (status) return MCNN_POP_COLLAPSED;
         PROF_T(3, pool_side(e, 2));
@@ -589,10 +648,159 @@ struct Collapse {
         ec -= 1;
         return MCNN_POP_COLLAPSED;
     }
+
+    // 16-bit ids: a one-ring row is ONE 64-bit word, its side row one 32-bit word
+    __device__ __forceinline__ static int rg(unsigned long long row, int j) { return (int)((row >> (16 * j)) & 0xFFFFull); }
+    __device__ __forceinline__ static int rs(uint32_t sd, int j) { return (int)((sd >> (8 * j)) & 0xFFu); }
+
+    // face record of side S (0 / 2) from words that are already in registers
+    template <int S>
+    __device__ __forceinline__ static Face face_from(unsigned long long rowe, uint32_t sde, unsigned long long rowka,
+                                                     unsigned long long rowkb) {
+        Face f;
+        f.ka = rg(rowe, S);
+        f.kb = rg(rowe, S + 1);
+        f.sa = rs(sde, S);
+        f.sb = rs(sde, S + 1);
+        f.osa = (f.sa - (f.sa & 1) + 2) & 3;
+        f.osb = (f.sb - (f.sb & 1) + 2) & 3;
+        f.oka0 = rg(rowka, f.osa);
+        f.oka1 = rg(rowka, f.osa + 1);
+        f.okb0 = rg(rowkb, f.osb);
+        f.okb1 = rg(rowkb, f.osb + 1);
+        return f;
+    }
+    __device__ __forceinline__ static bool shares(const Face& f) {
+        return f.oka0 == f.okb0 || f.oka0 == f.okb1 || f.oka1 == f.okb0 || f.oka1 == f.okb1;
+    }
+
+    // __pool_edge for 16-bit ids, arranged around what a single thread is bound by -- dependent shared-memory round trips:
+    //  * the row of e and, in ONE further round trip, the rows of its four neighbours give has_boundaries, both face records
+    //    (mesh_pool.py:160-170) and both shared-edge tests of __get_invalids; the endpoints of e are resolved alongside, so the
+    //    one-ring request leaves two round trips after the pop;
+    //  * an attempt whose sides are clean (94 % of them) never calls __clean_side; everything the commit will need that the
+    //    helper warp cannot change -- the side words of the two key_b rows, the vertex coordinates -- is fetched while the
+    //    one-ring answer is awaited, and the nine rows involved are checked to be distinct (then no store of the commit can
+    //    change a word another part of it reads, and the reference's read-after-write order is immaterial);
+    //  * the commit is then stores only, plus the six list positions of the three dying edges fetched together.
+    // Anything else (a shared edge, rows that coincide, a list entry that is not where it was recorded) takes the general code.
+    __device__ int pool_edge_narrow(int e) {
+#ifdef MCNN_POOL_PROF
+        const long long t0_ = clock64();
+#endif
+        const unsigned long long HI = 0x8000800080008000ULL;
+        const unsigned long long rowe = *reinterpret_cast<const unsigned long long*>(gemm + 4 * e);
+        const uint32_t sde = *reinterpret_cast<const uint32_t*>(sides + 4 * e);
+        const pair_t we = evp[e];
+        if ((rowe & HI) != 0ULL) return MCNN_POP_REJ_BOUNDARY;
+        const int n0 = rg(rowe, 0), n1 = rg(rowe, 1), n2 = rg(rowe, 2), n3 = rg(rowe, 3);
+        const unsigned long long r0 = *reinterpret_cast<const unsigned long long*>(gemm + 4 * n0);
+        const unsigned long long r1 = *reinterpret_cast<const unsigned long long*>(gemm + 4 * n1);
+        const unsigned long long r2 = *reinterpret_cast<const unsigned long long*>(gemm + 4 * n2);
+        const unsigned long long r3 = *reinterpret_cast<const unsigned long long*>(gemm + 4 * n3);
+        const uint32_t d1 = *reinterpret_cast<const uint32_t*>(sides + 4 * n1);
+        const uint32_t d3 = *reinterpret_cast<const uint32_t*>(sides + 4 * n3);
+        const int ea = pr_lo<P>(we), eb = pr_hi<P>(we);
+        const int ra = (int)rep[ea], rb = (int)rep[eb];
+        if (((r0 | r1 | r2 | r3) & HI) != 0ULL) return MCNN_POP_REJ_BOUNDARY;
+        const int v0 = (ra == ea) ? ea : uf_find(rep, ea);
+        const int v1 = (rb == eb) ? eb : uf_find(rep, eb);
+#ifdef MCNN_POOL_PROF
+        const long long t1_ = clock64();
+        prof[0] += t1_ - t0_;
+#endif
+        ++stamp_id;
+        post(WOP_ONE_RING, v0, v1, (int)(stamp_id << 1));
+#ifdef MCNN_POOL_PROF
+        const long long t2_ = clock64();
+        prof[2] += t2_ - t1_;
+#endif
+        const Face f0 = face_from<0>(rowe, sde, r0, r1), f2 = face_from<2>(rowe, sde, r2, r3);
+        if (shares(f0) || shares(f2)) return pool_edge_tail(e);          // rewiring around a valence-3 vertex: general code
+        // ---- under the wait for the one-ring answer ----
+        const int ssb00 = rs(d1, f0.osb), ssb01 = rs(d1, f0.osb + 1), ssb20 = rs(d3, f2.osb), ssb21 = rs(d3, f2.osb + 1);
+        bool distinct;
+        {
+            const int q[9] = {e, f0.ka, f0.kb, f0.okb0, f0.okb1, f2.ka, f2.kb, f2.okb0, f2.okb1};
+            bool same = false;
+#pragma unroll
+            for (int i = 0; i < 9; ++i)
+#pragma unroll
+                for (int j = i + 1; j < 9; ++j) same |= (q[i] == q[j]);
+            distinct = !same && v0 != v1;
+        }
+        double p0[3] = {0.0, 0.0, 0.0}, p1[3] = {0.0, 0.0, 0.0};
+        if (vs != nullptr && distinct) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { p0[k] = vs[3 * v0 + k]; p1[k] = vs[3 * v1 + k]; }
+        }
+#ifdef MCNN_POOL_PROF
+        prof[1] += clock64() - t2_;
+#endif
+        const bool ring_ok = wait_result() == 2;
+        if (!ring_ok) return MCNN_POP_REJ_ONE_RING;
+        if (!distinct) return commit_generic(e, f0);
+#ifdef MCNN_POOL_PROF
+        const long long t3_ = clock64();
+#endif
+        // ---- commit: __pool_side(0), __pool_side(2) (mesh_pool.py:102-113), merge_vertices (mesh.py:26-37) ----
+        {
+            const int b0 = f0.sa - (f0.sa & 1), b2 = f2.sa - (f2.sa & 1);
+            redirect(f0.ka, b0, f0.okb0, ssb00);
+            redirect(f0.ka, b0 + 1, f0.okb1, ssb01);
+            redirect(f2.ka, b2, f2.okb0, ssb20);
+            redirect(f2.ka, b2 + 1, f2.okb1, ssb21);
+        }
+        group_union(f0.kb, f0.ka);
+        group_union(e, f0.ka);
+        group_union(f2.kb, f2.ka);
+        group_union(e, f2.ka);
+        mask[f0.kb] = 0; mask[f2.kb] = 0; mask[e] = 0;
+        ec -= 3;
+        {   // Mesh.remove_edge x 3 (mesh.py:42-48): the six list positions together, then the six entries
+            const int x[3] = {f0.kb, f2.kb, e};
+            unsigned ia[3], ib[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { ia[k] = eposa[x[k]]; ib[k] = eposb[x[k]]; }
+            int ta[3], tb[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                ta[k] = (ia[k] != P::NIL) ? (int)ve[ia[k]] : -1;
+                tb[k] = (ib[k] != P::NIL) ? (int)ve[ib[k]] : -1;
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                if (x[k] != 0 && ta[k] == x[k] && tb[k] == x[k]) {
+                    ve[ia[k]] = (uidx_t)P::NIL;
+                    ve[ib[k]] = (uidx_t)P::NIL;
+                } else {
+                    remove_edge(x[k]);                           // id 0 / stale position: search, as the general code does
+                }
+            }
+        }
+        if (status) return MCNN_POP_COLLAPSED;
+        post(WOP_MERGE, v0, v1, 0);                              // ve[v0].extend(ve[v1]) on the helper warp, not waited for
+        if (vs != nullptr) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) vs[3 * v0 + k] = (p0[k] + p1[k]) / 2;
+        }
+        vmask[v1] = 0;
+        rep[v1] = (uidx_t)v0;
+#ifdef MCNN_POOL_PROF
+        prof[3] += clock64() - t3_;
+#endif
+        return MCNN_POP_COLLAPSED;
+    }
+
+    __device__ __forceinline__ int pool_edge(int e) {
+        if constexpr (P::WIDE) return pool_edge_generic(e);
+        else return pool_edge_narrow(e);
+    }
 };
 
 template <class P>
 __global__ void __launch_bounds__(P::THREADS, 1) pool_collapse_kernel(const mcnn_pool_args a) {
+    pdl_enter();
     typedef typename P::idx_t idx_t;
     typedef typename P::uidx_t uidx_t;
     typedef typename P::pair_t pair_t;
@@ -1037,7 +1245,7 @@ int launch(const mcnn_pool_args* a, size_t* smem_needed, cudaStream_t st, bool q
     if (query_only) return MCNN_OK;
     static DynSmemGuard configured;
     if (int grc = configured.ensure(pool_collapse_kernel<Narrow>, smem)) return grc;
-    pool_collapse_kernel<Narrow><<<a->B, Narrow::THREADS, smem, st>>>(*a);
+    launch_k(pool_collapse_kernel<Narrow>, a->B, Narrow::THREADS, smem, st, *a);
     return after_launch();
 }
 

@@ -66,6 +66,7 @@ __device__ __forceinline__ void slab_colsums(const NormShape s, float* __restric
 
 __global__ void __launch_bounds__(NT) norm_stats_kernel(const float* __restrict__ x, const float* __restrict__ a, int pre_relu,
                                                         float* __restrict__ part, NormShape s) {
+    pdl_enter();
     slab_colsums(s, part, [&](size_t off, int, float4& u, float4& v) {
         float4 z = ld4(x + off);
         if (a != nullptr) { const float4 t = ld4(a + off); z.x += t.x; z.y += t.y; z.z += t.z; z.w += t.w; }
@@ -84,6 +85,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 // mean / rstd per (block, group) from the slab partials, in fp64 (one warp per output); optional BatchNorm running-stat update
 __global__ void norm_finalize_kernel(const float* __restrict__ part, float* __restrict__ mean, float* __restrict__ rstd,
                                      float* running_mean, float* running_var, float momentum, float eps, NormShape s) {
+    pdl_enter();
     const int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (idx >= s.nblocks * s.G) return;
@@ -121,6 +123,7 @@ __global__ void __launch_bounds__(NT) norm_apply_kernel(const float* __restrict_
                                                         const float* __restrict__ beta, const float* __restrict__ mean,
                                                         const float* __restrict__ rstd, float* __restrict__ y, int pre_relu,
                                                         int post_relu, NormShape s) {
+    pdl_enter();
     const int cq = s.C >> 2;
     const int rpp = NT / cq;
     const int tx = threadIdx.x % cq, ty = threadIdx.x / cq;
@@ -177,6 +180,7 @@ __global__ void __launch_bounds__(NT) norm_bwd_stats_kernel(const float* __restr
                                                             const float* __restrict__ x, const float* __restrict__ a,
                                                             const float* __restrict__ mean, const float* __restrict__ rstd,
                                                             int pre_relu, int post_relu, float* __restrict__ part, NormShape s) {
+    pdl_enter();
     const int cpg = s.C / s.G;
     const int blk = blockIdx.x;
     slab_colsums(s, part, [&](size_t off, int c, float4& u, float4& v) {
@@ -204,6 +208,7 @@ __global__ void __launch_bounds__(NT) norm_bwd_stats_kernel(const float* __restr
 // then dgamma[c] = sum_blocks Bc, dbeta[c] = sum_blocks A
 __global__ void norm_bwd_finalize_kernel(const float* __restrict__ part, const float* __restrict__ gamma, float* __restrict__ s1,
                                          float* __restrict__ s2, float* __restrict__ dgamma, float* __restrict__ dbeta, NormShape s) {
+    pdl_enter();
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     const int cpg = s.C / s.G;
@@ -249,6 +254,7 @@ __global__ void __launch_bounds__(NT) norm_bwd_apply_kernel(const float* __restr
                                                             const float* __restrict__ rstd, const float* __restrict__ s1,
                                                             const float* __restrict__ s2, float* __restrict__ dx,
                                                             float* __restrict__ dr, int pre_relu, int post_relu, NormShape s) {
+    pdl_enter();
     const int cq = s.C >> 2;
     const int rpp = NT / cq;
     const int tx = threadIdx.x % cq, ty = threadIdx.x / cq;
@@ -336,6 +342,7 @@ __global__ void __launch_bounds__(NT) norm_fused_fwd_kernel(const float* __restr
                                                             const float* __restrict__ beta, float* __restrict__ y,
                                                             float* __restrict__ mean, float* __restrict__ rstd, float eps,
                                                             int pre_relu, int post_relu, FusedShape s) {
+    pdl_enter();
     extern __shared__ float sm[];
     const int CW = s.CW, cq = CW >> 2, rl = NT / cq;
     float* zs = sm;                                   // [rows][CW]
@@ -430,6 +437,7 @@ __global__ void __launch_bounds__(NT) norm_fused_bwd_kernel(const float* __restr
                                                             const float* __restrict__ rstd, float* __restrict__ dx,
                                                             float* __restrict__ dr, float* __restrict__ part, int pre_relu,
                                                             int post_relu, FusedShape s) {
+    pdl_enter();
     extern __shared__ float sm[];
     const int CW = s.CW, cq = CW >> 2, rl = NT / cq;
     float* zs = sm;
@@ -571,6 +579,7 @@ static int fused_cw(int nblocks, int rows, int C, int G, size_t* smem_bytes) {
 // ---- flat Adam over contiguous parameter / gradient / moment buffers (torch.optim.Adam semantics, no amsgrad) ----------
 __global__ void adam_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                                  long long n, float lr, float beta1, float beta2, float eps, float weight_decay, float bc1, float bc2_sqrt) {
+    pdl_enter();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float gi = g[i];
@@ -588,6 +597,7 @@ __global__ void adam_flat_kernel(float* __restrict__ p, const float* __restrict_
 // valid when the learning rate changes or the step count advances.   state = {lr, beta1, beta2, eps, weight_decay, step,
 // 1 - beta1^step, sqrt(1 - beta2^step)}
 __global__ void adam_tick_kernel(float* __restrict__ state) {
+    pdl_enter();
     const float step = state[5] + 1.f;
     state[5] = step;
     state[6] = 1.f - powf(state[1], step);
@@ -595,6 +605,7 @@ __global__ void adam_tick_kernel(float* __restrict__ state) {
 }
 __global__ void adam_flat_state_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                                        long long n, const float* __restrict__ state) {
+    pdl_enter();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float lr = state[0], beta1 = state[1], beta2 = state[2], eps = state[3], weight_decay = state[4];
@@ -653,16 +664,16 @@ extern "C" int mcnn_norm_fwd(const float* x, const float* a, const float* r, con
         static DynSmemGuard configured;
         if (int grc = configured.ensure(norm_fused_fwd_kernel, 200 * 1024)) return grc;
         FusedShape f; f.nblocks = nblocks; f.rows = rows_per_block; f.C = C; f.G = G; f.CW = cw;
-        norm_fused_fwd_kernel<<<dim3(nblocks, C / cw), NT, fsm, st>>>(x, a, r, gamma, beta, y, mean, rstd, eps, pre_relu, post_relu, f);
+        launch_k(norm_fused_fwd_kernel, dim3(nblocks, C / cw), NT, fsm, st, x, a, r, gamma, beta, y, mean, rstd, eps, pre_relu, post_relu, f);
         return after_launch();
     }
     if (!stats_given) {
-        norm_stats_kernel<<<dim3(nblocks, s.slabs), NT, smem, st>>>(x, a, pre_relu, part, s);
+        launch_k(norm_stats_kernel, dim3(nblocks, s.slabs), NT, smem, st, x, a, pre_relu, part, s);
         if ((rc = after_launch())) return rc;
-        norm_finalize_kernel<<<ceil_div(nblocks * G * 32, 256), 256, 0, st>>>(part, mean, rstd, running_mean, running_var, momentum, eps, s);
+        launch_k(norm_finalize_kernel, ceil_div(nblocks * G * 32, 256), 256, 0, st, part, mean, rstd, running_mean, running_var, momentum, eps, s);
         if ((rc = after_launch())) return rc;
     }
-    norm_apply_kernel<<<dim3(nblocks, s.slabs), NT, 0, st>>>(x, a, r, gamma, beta, mean, rstd, y, pre_relu, post_relu, s);
+    launch_k(norm_apply_kernel, dim3(nblocks, s.slabs), NT, 0, st, x, a, r, gamma, beta, mean, rstd, y, pre_relu, post_relu, s);
     return after_launch();
 }
 
@@ -682,22 +693,22 @@ extern "C" int mcnn_norm_bwd(const float* dy, const float* y, const float* x, co
         static DynSmemGuard configured;
         if (int grc = configured.ensure(norm_fused_bwd_kernel, 200 * 1024)) return grc;
         FusedShape f; f.nblocks = nblocks; f.rows = rows_per_block; f.C = C; f.G = G; f.CW = cw;
-        norm_fused_bwd_kernel<<<dim3(nblocks, C / cw), NT, fsm, st>>>(dy, y, x, a, gamma, mean, rstd, dx, dr, part, pre_relu, post_relu, f);
+        launch_k(norm_fused_bwd_kernel, dim3(nblocks, C / cw), NT, fsm, st, dy, y, x, a, gamma, mean, rstd, dx, dr, part, pre_relu, post_relu, f);
         if ((rc = after_launch())) return rc;
         if (dgamma != nullptr) {                               // dgamma / dbeta: the per-mesh column sums reduced over the meshes
             NormShape s1s = s; s1s.slabs = 1; s1s.rows_per_slab = rows_per_block;
             const int nfin1 = nblocks * G + C;
-            norm_bwd_finalize_kernel<<<ceil_div(nfin1 * 32, 256), 256, 0, st>>>(part, gamma, s1, s2, dgamma, dbeta, s1s);
+            launch_k(norm_bwd_finalize_kernel, ceil_div(nfin1 * 32, 256), 256, 0, st, part, gamma, s1, s2, dgamma, dbeta, s1s);
             rc = after_launch();
         }
         return rc;
     }
-    norm_bwd_stats_kernel<<<dim3(nblocks, s.slabs), NT, smem, st>>>(dy, y, x, a, mean, rstd, pre_relu, post_relu, part, s);
+    launch_k(norm_bwd_stats_kernel, dim3(nblocks, s.slabs), NT, smem, st, dy, y, x, a, mean, rstd, pre_relu, post_relu, part, s);
     if ((rc = after_launch())) return rc;
     const int nfin = nblocks * G + C;
-    norm_bwd_finalize_kernel<<<ceil_div(nfin * 32, 256), 256, 0, st>>>(part, gamma, s1, s2, dgamma, dbeta, s);
+    launch_k(norm_bwd_finalize_kernel, ceil_div(nfin * 32, 256), 256, 0, st, part, gamma, s1, s2, dgamma, dbeta, s);
     if ((rc = after_launch())) return rc;
-    norm_bwd_apply_kernel<<<dim3(nblocks, s.slabs), NT, 0, st>>>(dy, y, x, a, gamma, mean, rstd, s1, s2, dx, dr, pre_relu, post_relu, s);
+    launch_k(norm_bwd_apply_kernel, dim3(nblocks, s.slabs), NT, 0, st, dy, y, x, a, gamma, mean, rstd, s1, s2, dx, dr, pre_relu, post_relu, s);
     return after_launch();
 }
 
@@ -712,7 +723,7 @@ extern "C" int mcnn_norm_stats(const float* x, const float* a, float* part, int 
     if (!x || !part || !norm_args_ok(nblocks, rows_per_block, C, G)) return MCNN_E_BADARG;
     const NormShape s = make_shape(nblocks, rows_per_block, C, G);
     const size_t smem = (size_t)(NT / (C / 4)) * 2 * C * sizeof(float);
-    norm_stats_kernel<<<dim3(nblocks, s.slabs), NT, smem, (cudaStream_t)stream>>>(x, a, pre_relu, part, s);
+    launch_k(norm_stats_kernel, dim3(nblocks, s.slabs), NT, smem, (cudaStream_t)stream, x, a, pre_relu, part, s);
     return after_launch();
 }
 
@@ -723,7 +734,7 @@ extern "C" int mcnn_norm_bwd_stats(const float* dy, const float* y, const float*
     if (post_relu && !y) return MCNN_E_BADARG;
     const NormShape s = make_shape(nblocks, rows_per_block, C, G);
     const size_t smem = (size_t)(NT / (C / 4)) * 2 * C * sizeof(float);
-    norm_bwd_stats_kernel<<<dim3(nblocks, s.slabs), NT, smem, (cudaStream_t)stream>>>(dy, y, x, a, mean, rstd, pre_relu, post_relu, part, s);
+    launch_k(norm_bwd_stats_kernel, dim3(nblocks, s.slabs), NT, smem, (cudaStream_t)stream, dy, y, x, a, mean, rstd, pre_relu, post_relu, part, s);
     return after_launch();
 }
 
@@ -733,7 +744,7 @@ extern "C" int mcnn_norm_bwd_apply(const float* dy, const float* y, const float*
     if (!dy || !x || !mean || !rstd || !s1 || !s2 || !dx || !norm_args_ok(nblocks, rows_per_block, C, G)) return MCNN_E_BADARG;
     if (post_relu && !y) return MCNN_E_BADARG;
     const NormShape s = make_shape(nblocks, rows_per_block, C, G);
-    norm_bwd_apply_kernel<<<dim3(nblocks, s.slabs), NT, 0, (cudaStream_t)stream>>>(dy, y, x, a, gamma, mean, rstd, s1, s2, dx, dr, pre_relu, post_relu, s);
+    launch_k(norm_bwd_apply_kernel, dim3(nblocks, s.slabs), NT, 0, (cudaStream_t)stream, dy, y, x, a, gamma, mean, rstd, s1, s2, dx, dr, pre_relu, post_relu, s);
     return after_launch();
 }
 
@@ -741,10 +752,10 @@ extern "C" int mcnn_debug_set_norm_fused(int on) { g_norm_fused = on ? 1 : 0; re
 
 extern "C" int mcnn_adam_flat_state(float* p, const float* g, float* m, float* v, long long n, float* state, void* stream) {
     if (!p || !g || !m || !v || !state || n <= 0) return MCNN_E_BADARG;
-    adam_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state);
+    launch_k(adam_tick_kernel, 1, 1, 0, (cudaStream_t)stream, state);
     int rc = after_launch();
     if (rc) return rc;
-    adam_flat_state_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, state);
+    launch_k(adam_flat_state_kernel, (unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream, p, g, m, v, n, state);
     return after_launch();
 }
 
@@ -753,7 +764,7 @@ extern "C" int mcnn_adam_flat(float* p, const float* g, float* m, float* v, long
     if (!p || !g || !m || !v || n <= 0 || step <= 0) return MCNN_E_BADARG;
     const float bc1 = 1.f - powf(beta1, (float)step);
     const float bc2 = 1.f - powf(beta2, (float)step);
-    adam_flat_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay,
+    launch_k(adam_flat_kernel, (unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream, p, g, m, v, n, lr, beta1, beta2, eps, weight_decay,
                                                                                      bc1, sqrtf(bc2));
     return after_launch();
 }
