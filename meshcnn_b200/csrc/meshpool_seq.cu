@@ -39,6 +39,10 @@ template <class P> __device__ __forceinline__ typename P::pair_t pr_pack(int a, 
 template <class P> __device__ __forceinline__ int pr_lo(typename P::pair_t w) { return (int)(typename P::uidx_t)w; }
 template <class P> __device__ __forceinline__ int pr_hi(typename P::pair_t w) { return (int)(typename P::uidx_t)(w >> P::SHIFT); }
 
+// release / acquire between the warps of a CTA that talk through shared memory (__threadfence_block() is the sequentially
+// consistent MEMBAR.SC.CTA; the hand-over protocol below only needs acquire-release ordering)
+__device__ __forceinline__ void cta_fence() { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
+
 constexpr int POOL_BFS_CAP = 96;         // members of one MeshUnion row / column walked per thread (implementation limit)
 
 struct PoolLayout {
@@ -130,11 +134,12 @@ enum { WOP_EXIT = 0, WOP_ONE_RING = 1, WOP_REMOVE_SCAN = 2, WOP_MERGE = 3 };
 constexpr int WQ_CAP = 32;
 
 struct WorkQueue {
-    int ent[WQ_CAP][4];       // op, a0, a1, a2
-    int head;                 // entries posted   (written by the collapse thread)
-    int done;                 // entries finished (written by the helper warp)
-    int res;                  // result of the most recent operation
-    int res_seq;              // sequence number (1-based) that `res` belongs to
+    // one 64-bit word per operation, written with ONE store and polled by the helper warp itself:
+    //   bits 0..3 op | 4..15 sequence number (1-based, mod 4096) | 16..31 a0 | 32..47 a1 | 48..63 a2     (16-bit ids)
+    unsigned long long ent[WQ_CAP];
+    // the helper's answer: (sequence number << 2) | result -- one word, so the collapse thread needs one poll and no fence pair;
+    // every operation publishes (also the ones nobody waits for): the same word is the ring's flow control
+    unsigned res;
 };
 
 template <class U>
@@ -214,21 +219,29 @@ __device__ __forceinline__ void wop_merge(WarpCtx<P>& w, int lane, int v0, int v
         const unsigned lt = (1u << lane) - 1u;
         const unsigned m0 = __ballot_sync(0xffffffffu, x0 != P::NIL), m1 = __ballot_sync(0xffffffffu, x1 != P::NIL);
         const int out = w.bump, c0 = __popc(m0), c1 = __popc(m1);
+        // all dependent loads of both lists side by side (unconditional, with a safe index)
+        const unsigned i0 = x0 != P::NIL ? x0 : 0u, i1 = x1 != P::NIL ? x1 : 0u;
+        const int pa0 = (int)w.eposa[i0], pb0 = (int)w.eposb[i0], pa1 = (int)w.eposa[i1], pb1 = (int)w.eposb[i1];
+        const typename P::pair_t w1 = w.evp[i1];
         if (x0 != P::NIL) {
             const int dst = out + __popc(m0 & lt);
             w.ve[dst] = (uidx_t)x0;
             if (x0 != 0u) {
-                if ((int)w.eposa[x0] == s0 + lane) w.eposa[x0] = (uidx_t)dst;
-                else if ((int)w.eposb[x0] == s0 + lane) w.eposb[x0] = (uidx_t)dst;
+                if (pa0 == s0 + lane) w.eposa[x0] = (uidx_t)dst;
+                else if (pb0 == s0 + lane) w.eposb[x0] = (uidx_t)dst;
             }
         }
         if (x1 != P::NIL) {
             const int dst = out + c0 + __popc(m1 & lt);
             w.ve[dst] = (uidx_t)x1;
             if (x1 != 0u) {
-                if ((int)w.eposa[x1] == s1 + lane) w.eposa[x1] = (uidx_t)dst;
-                else if ((int)w.eposb[x1] == s1 + lane) w.eposb[x1] = (uidx_t)dst;
+                if (pa1 == s1 + lane) w.eposa[x1] = (uidx_t)dst;
+                else if (pb1 == s1 + lane) w.eposb[x1] = (uidx_t)dst;
             }
+            // edges[edges == v1] = v0 (mesh.py:33) applied to the stored endpoints of v1's edges right away: later walks then find
+            // roots at the first look-up (the union-find stays authoritative; an entry that is stale or already redirected keeps its word)
+            const int lo = pr_lo<P>(w1), hi = pr_hi<P>(w1);
+            if (lo == v1 || hi == v1) w.evp[x1] = pr_pack<P>(lo == v1 ? v0 : lo, hi == v1 ? v0 : hi);
         }
         if (lane == 0) { w.slab_start[v0] = (uidx_t)out; w.slab_len[v0] = (uidx_t)(c0 + c1); }
         w.bump = out + c0 + c1;
@@ -263,12 +276,13 @@ __device__ __forceinline__ int wop_one_ring(WarpCtx<P>& w, int lane, int v0, int
     // the two dependent chains (entry -> endpoints -> union-find roots) run side by side: unconditional loads with a safe index
     const typename P::pair_t w0 = w.evp[x0 != P::NIL ? x0 : 0u], w1 = w.evp[x1 != P::NIL ? x1 : 0u];
     int a0 = pr_lo<P>(w0), b0 = pr_hi<P>(w0), a1 = pr_lo<P>(w1), b1 = pr_hi<P>(w1);
-    {
+    // the four roots together, one round trip per level of the union-find forest for the whole warp (four separate find loops
+    // serialise: each is a divergent chain of three dependent loads)
+    while (true) {
         const int ra0 = (int)w.rep[a0], rb0 = (int)w.rep[b0], ra1 = (int)w.rep[a1], rb1 = (int)w.rep[b1];
-        if (ra0 != a0) a0 = uf_find(w.rep, a0);
-        if (rb0 != b0) b0 = uf_find(w.rep, b0);
-        if (ra1 != a1) a1 = uf_find(w.rep, a1);
-        if (rb1 != b1) b1 = uf_find(w.rep, b1);
+        const bool fixed = (ra0 == a0) & (rb0 == b0) & (ra1 == a1) & (rb1 == b1);
+        a0 = ra0; b0 = rb0; a1 = ra1; b1 = rb1;
+        if (__all_sync(0xffffffffu, fixed)) break;
     }
     if (x0 != P::NIL) { w.stamp[a0] = tagA; w.stamp[b0] = tagA; }
 #ifdef MCNN_POOL_PROF
@@ -352,38 +366,36 @@ __device__ __forceinline__ bool wop_list_remove(const WarpCtx<P>& w, int lane, i
 // Service loop of the helper warp: executes the posted operations in order until WOP_EXIT.
 template <class P>
 __device__ void helper_warp_loop(WarpCtx<P>& w, WorkQueue* q, int lane, long long* hprof) {
-    volatile int* vhead = &q->head;
-    int seq = 0;                                             // operations finished so far
+    static_assert(!P::WIDE, "the operation ring packs 16-bit ids");
+    unsigned seq = 0;                                        // operations finished so far
     while (true) {
-        while (*vhead == seq) {}                             // all lanes poll the same word: no divergence
-        __syncwarp();
-        __threadfence_block();
-        volatile int* ep = q->ent[seq % WQ_CAP];
-        int4 rq;
-        rq.x = ep[0]; rq.y = ep[1]; rq.z = ep[2]; rq.w = ep[3];
+        const unsigned want = (seq + 1u) & 0xFFFu;
+        volatile unsigned long long* ep = &q->ent[seq % WQ_CAP];
+        unsigned long long rq;
+        do { rq = *ep; } while ((((unsigned)rq >> 4) & 0xFFFu) != want);      // all lanes poll the same word: no divergence
+        cta_fence();
         ++seq;
-        if (rq.x == WOP_EXIT) break;
+        const int op = (int)(rq & 15ull), a0 = (int)((rq >> 16) & 0xFFFFull), a1 = (int)((rq >> 32) & 0xFFFFull), a2 = (int)(rq >> 48);
+        if (op == WOP_EXIT) break;
 #ifdef MCNN_POOL_PROF
         const long long th_ = clock64();
 #endif
         int r = 0;
-        if (rq.x == WOP_ONE_RING) {
-            r = wop_one_ring<P>(w, lane, rq.y, rq.z, (uint32_t)rq.w, hprof ? hprof + 3 : nullptr);
-        } else if (rq.x == WOP_MERGE) {                      // nobody waits for this one
-            wop_merge<P>(w, lane, rq.y, rq.z);
+        if (op == WOP_ONE_RING) {                            // tags: two per operation, never reused within a launch
+            r = min(wop_one_ring<P>(w, lane, a0, a1, seq << 1, hprof ? hprof + 3 : nullptr), 3);    // 2 = valid (mesh_pool.py:99)
+        } else if (op == WOP_MERGE) {                        // nobody waits for this one
+            wop_merge<P>(w, lane, a0, a1);
         } else {                                             // WOP_REMOVE_SCAN: x leaves ve[a], then ve[b] (mesh.py:42-48)
-            r = wop_list_remove<P>(w, lane, rq.z, rq.y) ? 1 : 0;
-            if (r) r = wop_list_remove<P>(w, lane, rq.w, rq.y) ? 1 : 0;
-        }
-        if (lane == 0) {
-            *(volatile int*)&q->res = r;
-            __threadfence_block();
-            *(volatile int*)&q->res_seq = seq;
+            r = wop_list_remove<P>(w, lane, a1, a0) ? 1 : 0;
+            if (r) r = wop_list_remove<P>(w, lane, a2, a0) ? 1 : 0;
         }
         __syncwarp();
-        if (lane == 0) { __threadfence_block(); *(volatile int*)&q->done = seq; }
+        if (lane == 0) {
+            cta_fence();                           // the list writes above before the answer
+            *(volatile unsigned*)&q->res = (seq << 2) | (unsigned)r;
+        }
 #ifdef MCNN_POOL_PROF
-        if (lane == 0 && hprof) hprof[rq.x - 1] += clock64() - th_;
+        if (lane == 0 && hprof) hprof[op - 1] += clock64() - th_;
 #endif
     }
 }
@@ -395,7 +407,7 @@ struct Collapse {
     typedef typename P::uidx_t uidx_t;
     typedef typename P::pair_t pair_t;
     WorkQueue* q;             // list walks go to the helper warp
-    int posted;
+    unsigned posted;
     idx_t* gemm;
     uidx_t *rep, *slab_next, *chain_tail, *ve, *eposa, *eposb;
     pair_t *evp, *ulog;
@@ -407,7 +419,6 @@ struct Collapse {
     int union_cap;
     int nunions, ulog_cap;
     int ec, T, status;
-    unsigned stamp_id;
 
 #ifdef MCNN_POOL_PROF
     long long prof[7] = {0, 0, 0, 0, 0, 0, 0};
@@ -418,14 +429,16 @@ struct Collapse {
     __device__ __forceinline__ void ends(int e, int& v0, int& v1) { edge_ends<P>(evp, rep, e, v0, v1); }
 
     __device__ __forceinline__ void post(int op, int a0, int a1, int a2) {
-        while (posted - *(volatile int*)&q->done >= WQ_CAP) {}
+        while (posted - (*(volatile unsigned*)&q->res >> 2) >= (unsigned)WQ_CAP) {}
 #ifdef MCNN_POOL_PROF
         const long long tp_ = clock64();
 #endif
-        volatile int* ep = q->ent[posted % WQ_CAP];
-        ep[0] = op; ep[1] = a0; ep[2] = a1; ep[3] = a2;
-        __threadfence_block();
-        *(volatile int*)&q->head = ++posted;
+        const unsigned slot = posted % WQ_CAP;
+        ++posted;
+        cta_fence();                               // everything this thread wrote before the operation becomes visible
+        *(volatile unsigned long long*)&q->ent[slot] = (unsigned long long)(unsigned)op | ((unsigned long long)(posted & 0xFFFu) << 4) |
+            ((unsigned long long)(unsigned)(a0 & 0xFFFF) << 16) | ((unsigned long long)(unsigned)(a1 & 0xFFFF) << 32) |
+            ((unsigned long long)(unsigned)(a2 & 0xFFFF) << 48);
 #ifdef MCNN_POOL_PROF
         prof[5] += clock64() - tp_;
 #endif
@@ -550,12 +563,13 @@ struct Collapse {
 #ifdef MCNN_POOL_PROF
         const long long tw_ = clock64();
 #endif
-        while (*(volatile int*)&q->res_seq != posted) {}
-        __threadfence_block();
+        unsigned r;
+        do { r = *(volatile unsigned*)&q->res; } while ((r >> 2) != posted);
+        cta_fence();
 #ifdef MCNN_POOL_PROF
         prof[6] += clock64() - tw_;
 #endif
-        return *(volatile int*)&q->res;
+        return (int)(r & 3u);
     }
 
     // __is_one_ring_valid (mesh_pool.py:95-100), walked by the helper warp.  The answer depends on the vertex lists, the
@@ -564,8 +578,7 @@ struct Collapse {
     __device__ void one_ring_request(int e) {
         int v0, v1;
         ends(e, v0, v1);
-        ++stamp_id;
-        post(WOP_ONE_RING, v0, v1, (int)(stamp_id << 1));
+        post(WOP_ONE_RING, v0, v1, 0);
     }
 
     // Mesh.remove_edge (mesh.py:42-48): both list entries of x become tombstones
@@ -709,8 +722,7 @@ struct Collapse {
         const long long t1_ = clock64();
         prof[0] += t1_ - t0_;
 #endif
-        ++stamp_id;
-        post(WOP_ONE_RING, v0, v1, (int)(stamp_id << 1));
+        post(WOP_ONE_RING, v0, v1, 0);
 #ifdef MCNN_POOL_PROF
         const long long t2_ = clock64();
         prof[2] += t2_ - t1_;
@@ -947,17 +959,18 @@ __global__ void __launch_bounds__(P::THREADS, 1) pool_collapse_kernel(const mcnn
     if (clk && tid == 0) clk[2] = clock64();
     // ---- phase D: the sequential collapse (mesh_pool.py:41-53) on thread 0; warp 1 serves the list operations ----------
     __shared__ WorkQueue s_queue;
-    if (tid == 0) { s_queue.head = 0; s_queue.done = 0; s_queue.res = 0; s_queue.res_seq = 0; }
+    if (tid < WQ_CAP) s_queue.ent[tid] = 0ull;
+    if (tid == 0) s_queue.res = 0u;
     __syncthreads();
     if (tid == 0) {
         Collapse<P> c;
-        c.q = &s_queue; c.posted = 0;
+        c.q = &s_queue; c.posted = 0u;
         c.gemm = gemm; c.rep = rep; c.slab_next = slab_next; c.chain_tail = chain_tail; c.ve = ve; c.eposa = eposa; c.eposb = eposb;
         c.evp = evp; c.ulog = ulog;
         c.sides = sides; c.mask = mask; c.vs = vs_s; c.vmask = vmask_s;
         c.log_unions = a.log_unions ? a.log_unions + (size_t)b * a.log_cap * 8 * 2 : nullptr;
         c.union_cap = a.log_cap * 8; c.nunions = 0; c.ulog_cap = L.ulog_cap;
-        c.ec = n; c.T = T; c.status = 0; c.stamp_id = 0;
+        c.ec = n; c.T = T; c.status = 0;
         int32_t* lp = a.log_pops ? a.log_pops + (size_t)b * a.log_cap : nullptr;
         int8_t* lo = a.log_outcome ? a.log_outcome + (size_t)b * a.log_cap : nullptr;
         int p = 0;
