@@ -1,5 +1,8 @@
+"""Per-stage clocks of the SEQUENTIAL collapse kernel (thread 0's stages and the helper warp's operations) on the cubes pool
+chain.  Needs the diagnostics build:  make -C meshcnn_b200/csrc prof;
+MESHCNN_B200_LIB=$PWD/meshcnn_b200/libmeshcnn_b200_prof.so python tools/pool_seq_profile.py"""
 import os, sys
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch, bench
 from meshcnn_b200.mesh import Mesh, MeshBatch
 cfg = bench.CONFIGS['cubes']; dev = torch.device('cuda:0'); B, E = cfg['B'], cfg['E']
