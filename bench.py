@@ -211,6 +211,8 @@ def algorithmic_bytes(name, m):
         return 2 * n if name == 'norm_fwd' else 4 * n
     if name == 'adam_flat':
         return 28 * m['n']
+    if name in ('head_fwd', 'head_bwd'):                       # the activation read (fwd) / its gradient written (bwd) + both weight matrices
+        return 4 * m['B'] * m['E'] * m['C'] + 4 * (m['C'] * m['H'] + m['H'] * m['K']) * (1 if name == 'head_fwd' else 2)
     return 0
 
 

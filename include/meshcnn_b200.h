@@ -282,6 +282,18 @@ int mcnn_adam_flat(float* p, const float* g, float* m, float* v, long long n, fl
  * first advances step (and the two bias corrections), then applies the update. */
 int mcnn_adam_flat_state(float* p, const float* g, float* m, float* v, long long n, float* state, void* stream);
 
+/* ----------------------------------------------------------------------------------------------------------
+ * Classifier head of MeshConvNet (models/networks.py:143-157): AvgPool1d over the edge axis, fc1 + relu, fc2.
+ *     pooled[b][c] = mean_e x[b][e][c];  h = relu(W1 pooled + b1);  logits = W2 h + b2
+ * x: [B][E][C] edge-major (the whole, zero-padded edge axis is averaged, as AvgPool1d(res[-1]) does); W1: [H][C], W2: [K][H]
+ * (torch.nn.Linear layout); pooled [B][C] and h [B][H] are kept for the backward.  Backward: dx (NULL to skip), dW1, db1
+ * (NULL ok), dW2, db2 (NULL ok) are OVERWRITTEN; dh: [B][H] scratch.  One forward and two backward launches, deterministic.
+ * ---------------------------------------------------------------------------------------------------------- */
+int mcnn_head_fwd(const float* x, const float* w1, const float* b1, const float* w2, const float* b2, float* pooled, float* h,
+                  float* logits, int B, int E, int C, int H, int K, void* stream);
+int mcnn_head_bwd(const float* dlogits, const float* pooled, const float* h, const float* w1, const float* w2, float* dh,
+                  float* dx, float* dw1, float* db1, float* dw2, float* db2, int B, int E, int C, int H, int K, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -362,6 +362,54 @@ class FusedNormFn(torch.autograd.Function):
         return dx, (dx if a is not None else None), dr, dgamma, dbeta, None
 
 
+class ClassifierHeadFn(torch.autograd.Function):
+    """AvgPool1d over the edge axis -> fc1 -> relu -> fc2 (MeshConvNet.forward, models/networks.py:152-156) on the edge-major
+    activation [B, E, C]: mcnn_head_fwd / mcnn_head_bwd, three launches per step instead of ~17 torch kernels."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2):
+        _chk_cuda(x, w1, b1, w2, b2)
+        x = x.contiguous()
+        B, E, C = x.shape
+        H, K = w1.shape[0], w2.shape[0]
+        dev = x.device
+        pooled = torch.empty(B, C, dtype=torch.float32, device=dev)
+        h = torch.empty(B, H, dtype=torch.float32, device=dev)
+        logits = torch.empty(B, K, dtype=torch.float32, device=dev)
+        with profiler.span('head_fwd', B=B, E=E, C=C, H=H, K=K):
+            _lib.check(_lib.lib().mcnn_head_fwd(x.data_ptr(), w1.data_ptr(), _lib.ptr(b1), w2.data_ptr(), _lib.ptr(b2),
+                                                pooled.data_ptr(), h.data_ptr(), logits.data_ptr(), B, E, C, H, K,
+                                                _lib.current_stream()), 'mcnn_head_fwd')
+        ctx.save_for_backward(pooled, h, w1, w2)
+        ctx.params = (w1, b1, w2, b2)
+        ctx.dims = (B, E, C, H, K)
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        pooled, h, w1, w2 = ctx.saved_tensors
+        B, E, C, H, K = ctx.dims
+        dev = dlogits.device
+        dlogits = dlogits.contiguous()
+        _, b1, _, b2 = ctx.params
+        direct = _direct_grad(*ctx.params) if all(ctx.needs_input_grad[i] for i, p in enumerate(ctx.params, 1) if p is not None) else None
+        if direct is not None:
+            dw1, db1, dw2, db2 = direct
+        else:
+            dw1, dw2 = torch.empty_like(w1), torch.empty_like(w2)
+            db1 = torch.empty_like(b1) if b1 is not None else None
+            db2 = torch.empty_like(b2) if b2 is not None else None
+        dx = torch.empty(B, E, C, dtype=torch.float32, device=dev) if ctx.needs_input_grad[0] else None
+        dh = torch.empty(B, H, dtype=torch.float32, device=dev)
+        with profiler.span('head_bwd', B=B, E=E, C=C, H=H, K=K):
+            _lib.check(_lib.lib().mcnn_head_bwd(dlogits.data_ptr(), pooled.data_ptr(), h.data_ptr(), w1.data_ptr(), w2.data_ptr(),
+                                                dh.data_ptr(), _lib.ptr(dx), dw1.data_ptr(), _lib.ptr(db1), dw2.data_ptr(),
+                                                _lib.ptr(db2), B, E, C, H, K, _lib.current_stream()), 'mcnn_head_bwd')
+        if direct is not None:
+            return dx, None, None, None, None
+        return dx, dw1, db1, dw2, db2
+
+
 # Cross-rank batch statistics for BatchNorm2d (MResConv.bn, networks.py:167; SURVEY 8e "optional SyncBN"): off by default, like
 # any DDP run without SyncBN.  ddp.enable_sync_batchnorm() / MESHCNN_B200_SYNC_BN=1 switch it on.
 SYNC_BN = os.environ.get('MESHCNN_B200_SYNC_BN', '0') == '1'

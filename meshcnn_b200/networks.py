@@ -20,7 +20,7 @@ import torch.nn.functional as F
 from torch.nn import init
 from torch.optim import lr_scheduler
 
-from .functional import fused_norm
+from .functional import ClassifierHeadFn, fused_norm
 from .layout import as_bce, as_bce1, to_edge_major
 from .mesh import MeshBatch
 from .mesh_conv import MeshConv
@@ -197,9 +197,8 @@ class MeshConvNet(nn.Module):
             x, skip = getattr(self, 'conv%d' % i).forward_em(x, batch, defer_tail=True)
             x = _norm_em(getattr(self, 'norm%d' % i), x, pre_add=skip, pre_relu=True, post_relu=True)
             x = getattr(self, 'pool%d' % i).forward_em(x, batch)
-        x = x.mean(dim=1)                       # AvgPool1d(res[-1]) over the whole (zero-padded) edge axis
-        x = F.relu(self.fc1(x))
-        return self.fc2(x)
+        # AvgPool1d(res[-1]) over the whole (zero-padded) edge axis, fc1 + relu, fc2: one fused kernel
+        return ClassifierHeadFn.apply(x, self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias)
 
 
 # ---------------------------------------------------------------------------------------------------------------
