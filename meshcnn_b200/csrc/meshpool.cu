@@ -314,12 +314,13 @@ __device__ __forceinline__ int warp_one_ring_fast(const PoolState<P>& w, uint16_
     const unsigned x1 = (lane < len1) ? (unsigned)w.ve[start1 + lane] : P::NIL;
     const typename P::pair_t w0 = w.evp[x0 != P::NIL ? x0 : 0u], w1 = w.evp[x1 != P::NIL ? x1 : 0u];   // unconditional, safe index
     a0 = pr_lo<P>(w0); b0 = pr_hi<P>(w0); a1 = pr_lo<P>(w1); b1 = pr_hi<P>(w1);
-    {
+    // the four roots together, one round trip per level of the union-find forest for the whole warp (four separate find loops
+    // are four divergent chains of three dependent loads each)
+    while (true) {
         const int ra0 = (int)w.rep[a0], rb0 = (int)w.rep[b0], ra1 = (int)w.rep[a1], rb1 = (int)w.rep[b1];
-        if (ra0 != a0) a0 = uf_find(w.rep, a0);
-        if (rb0 != b0) b0 = uf_find(w.rep, b0);
-        if (ra1 != a1) a1 = uf_find(w.rep, a1);
-        if (rb1 != b1) b1 = uf_find(w.rep, b1);
+        const bool fixed = (ra0 == a0) & (rb0 == b0) & (ra1 == a1) & (rb1 == b1);
+        a0 = ra0; b0 = rb0; a1 = ra1; b1 = rb1;
+        if (__all_sync(0xffffffffu, fixed)) break;
     }
     if (x0 != P::NIL) { stamp[a0] = tA; stamp[b0] = tA; } else { a0 = (int)P::NIL; b0 = (int)P::NIL; }
     if (x1 == P::NIL) { a1 = (int)P::NIL; b1 = (int)P::NIL; }
@@ -341,8 +342,8 @@ __device__ __forceinline__ int warp_one_ring_fast(const PoolState<P>& w, uint16_
 // The committing warp's re-pack of a list it has just merged, for two single-slab lists (see warp_one_ring_fast): the live
 // entries of the slab of v0, then those of v1, go to fresh room as one slab of v0.  Falls back to the general chain walk.
 template <class P>
-__device__ __forceinline__ void warp_repack_pair(const PoolState<P>& w, int lane, int v0, int start0, int len0, int start1, int len1,
-                                                 int& priv_bump, int priv_end) {
+__device__ __forceinline__ void warp_repack_pair(const PoolState<P>& w, int lane, int v0, int v1, int start0, int len0, int start1,
+                                                 int len1, int& priv_bump, int priv_end) {
     typedef typename P::uidx_t uidx_t;
     const unsigned lt = (1u << lane) - 1u;
     const unsigned x0 = (lane < len0) ? (unsigned)w.ve[start0 + lane] : P::NIL;
@@ -376,6 +377,11 @@ __device__ __forceinline__ void warp_repack_pair(const PoolState<P>& w, int lane
             if ((int)w.eposa[x1] == start1 + lane) w.eposa[x1] = (uidx_t)dst;
             else if ((int)w.eposb[x1] == start1 + lane) w.eposb[x1] = (uidx_t)dst;
         }
+        // edges[edges == v1] = v0 (mesh.py:33) applied to the stored endpoints of v1's edges right away, so that later walks find
+        // roots at the first look-up (the union-find stays authoritative; only this candidate's reservation covers these words)
+        const typename P::pair_t w1 = w.evp[x1];
+        const int lo = pr_lo<P>(w1), hi = pr_hi<P>(w1);
+        if (lo == v1 || hi == v1) w.evp[x1] = pr_pack<P>(lo == v1 ? v0 : lo, hi == v1 ? v0 : hi);
     }
     if (lane == 0) {
         w.slab_start[v0] = (uidx_t)out;
@@ -1060,7 +1066,7 @@ __global__ void __launch_bounds__(P::THREADS, 1) pool_collapse_kernel(const mcnn
                 merged = __shfl_sync(0xffffffffu, merged, 0);
                 if (clk) s_c2 = clock64();
                 if (merged >= 0) {                               // keep the merged list one slab (see warp_one_ring_fast)
-                    if (!alone_round && fast_lists) warp_repack_pair<P>(S, lane, merged, ls0, ll0, ls1, ll1, priv_bump, priv_end);
+                    if (!alone_round && fast_lists) warp_repack_pair<P>(S, lane, merged, v1, ls0, ll0, ls1, ll1, priv_bump, priv_end);
                     else warp_repack<P>(S, lane, merged);
                 }
                 if (lane == 0) {
