@@ -1417,54 +1417,97 @@ __device__ __forceinline__ void store_row(float* __restrict__ p, int C, int c, f
 //   MODE 1 (segmean bwd) : seg = CSC column j, w = 1/len(row),   scale = 1,       valid j < ec_in
 //   MODE 2 (unpool fwd)  : seg = CSC column i, w = 1,            scale = 1/occ_i, valid i < ec_hi
 //   MODE 3 (unpool bwd)  : seg = CSR row r,    w = 1/occ(col),   scale = 1,       valid r < ec_lo
+constexpr int SEG_NR = 4;      // rows per thread, their dependent load chains (ptr -> idx -> weight -> data) issued side by side
+
 template <int MODE, bool VEC>
 __global__ void segment_kernel(const float* __restrict__ in, float* __restrict__ out, const int32_t* __restrict__ ptr,
                                const int32_t* __restrict__ idx, const int32_t* __restrict__ aux_ptr,
                                const float* __restrict__ occ, const int32_t* __restrict__ valid, int B, int R_out,
                                int R_in, int ptr_stride, int aux_stride, int occ_stride, int C, int nnz_cap) {
     pdl_enter();
-    // grid (row blocks, meshes); a CTA covers 256 / cq rows, one thread per (row, channel quad).  32-bit index arithmetic
-    // only (the flat 64-bit thread id of the first version cost three 64-bit divisions per thread).
+    // grid (row blocks, meshes); a CTA covers SEG_NR * (256 / cq) rows, one thread per (SEG_NR rows, channel quad).  A row's
+    // segment is 1-3 entries long, so a thread is a chain of four dependent global loads; with one row per thread the kernel
+    // was bound by that latency (three waves of CTAs, each a full chain) -- four rows per thread run their chains together.
     const int cq = (C + 3) >> 2;
-    const int rpc = blockDim.x / cq;                             // rows per CTA
+    const int rpc = blockDim.x / cq;                             // rows per CTA and pass
     const int lr = threadIdx.x / cq, q = threadIdx.x - lr * cq;
-    const int b = blockIdx.y, r = blockIdx.x * rpc + lr;
-    if (lr >= rpc || r >= R_out) return;
+    const int b = blockIdx.y;
+    if (lr >= rpc) return;
     const int c = q * 4;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (r < __ldg(valid + b) && r < ptr_stride - 1) {
-        const int32_t* pp = ptr + (size_t)b * ptr_stride;
-        const int beg = __ldg(pp + r), end = __ldg(pp + r + 1);
-        const int32_t* ii = idx + (size_t)b * nnz_cap;
-        const float* src = in + (size_t)b * R_in * C;
-        auto weight_of = [&](int j) -> float {
-            if (MODE == 1) {
-                const int32_t* ap = aux_ptr + (size_t)b * aux_stride;
-                return 1.f / (float)(__ldg(ap + j + 1) - __ldg(ap + j));
-            }
-            if (MODE == 3) return 1.f / __ldg(occ + (size_t)b * occ_stride + j);
-            return 1.f;
-        };
-        int p = beg;
-        for (; p + 1 < end; p += 2) {                           // two independent rows in flight (segments are short: 1-3 entries)
-            const int j0 = __ldg(ii + p), j1 = __ldg(ii + p + 1);
-            const float w0 = weight_of(j0), w1 = weight_of(j1);
-            float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
-            acc_row<VEC>(a0, src + (size_t)j0 * C, C, c, w0);
-            acc_row<VEC>(a1, src + (size_t)j1 * C, C, c, w1);
-            acc.x += a0.x; acc.y += a0.y; acc.z += a0.z; acc.w += a0.w;      // same order as the one-at-a-time loop
-            acc.x += a1.x; acc.y += a1.y; acc.z += a1.z; acc.w += a1.w;
+    const int nvalid = __ldg(valid + b);
+    const int32_t* pp = ptr + (size_t)b * ptr_stride;
+    const int32_t* ii = idx + (size_t)b * nnz_cap;
+    const float* src = in + (size_t)b * R_in * C;
+    auto weight_of = [&](int j) -> float {
+        if (MODE == 1) {
+            const int32_t* ap = aux_ptr + (size_t)b * aux_stride;
+            return 1.f / (float)(__ldg(ap + j + 1) - __ldg(ap + j));
         }
-        if (p < end) {
-            const int j = __ldg(ii + p);
-            acc_row<VEC>(acc, src + (size_t)j * C, C, c, weight_of(j));
-        }
-        float s = 1.f;
-        if (MODE == 0) s = 1.f / (float)(end - beg);
-        if (MODE == 2) s = 1.f / __ldg(occ + (size_t)b * occ_stride + r);
-        acc.x *= s; acc.y *= s; acc.z *= s; acc.w *= s;
+        if (MODE == 3) return 1.f / __ldg(occ + (size_t)b * occ_stride + j);
+        return 1.f;
+    };
+    int r[SEG_NR], beg[SEG_NR], end[SEG_NR];
+#pragma unroll
+    for (int k = 0; k < SEG_NR; ++k) {
+        r[k] = (blockIdx.x * SEG_NR + k) * rpc + lr;
+        const bool live = r[k] < R_out && r[k] < nvalid && r[k] < ptr_stride - 1;
+        beg[k] = live ? __ldg(pp + r[k]) : 0;
+        end[k] = live ? __ldg(pp + r[k] + 1) : 0;
     }
-    store_row<VEC>(out + ((size_t)b * R_out + r) * C, C, c, acc);
+    int j0[SEG_NR], j1[SEG_NR];
+#pragma unroll
+    for (int k = 0; k < SEG_NR; ++k) {
+        j0[k] = (beg[k] < end[k]) ? __ldg(ii + beg[k]) : 0;
+        j1[k] = (beg[k] + 1 < end[k]) ? __ldg(ii + beg[k] + 1) : 0;
+    }
+    float w0[SEG_NR], w1[SEG_NR];
+#pragma unroll
+    for (int k = 0; k < SEG_NR; ++k) {
+        w0[k] = (beg[k] < end[k]) ? weight_of(j0[k]) : 0.f;
+        w1[k] = (beg[k] + 1 < end[k]) ? weight_of(j1[k]) : 0.f;
+    }
+    float4 a0[SEG_NR], a1[SEG_NR];
+#pragma unroll
+    for (int k = 0; k < SEG_NR; ++k) {
+        a0[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        a1[k] = a0[k];
+        if (beg[k] < end[k]) acc_row<VEC>(a0[k], src + (size_t)j0[k] * C, C, c, w0[k]);
+        if (beg[k] + 1 < end[k]) acc_row<VEC>(a1[k], src + (size_t)j1[k] * C, C, c, w1[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < SEG_NR; ++k) {
+        if (r[k] >= R_out) continue;
+        // the summation order of the one-row-at-a-time form: pairs (0 + a, 0 + b) added in turn, a trailing single entry directly
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int len = end[k] - beg[k];
+        if (len >= 2) {
+            acc.x += a0[k].x; acc.y += a0[k].y; acc.z += a0[k].z; acc.w += a0[k].w;
+            acc.x += a1[k].x; acc.y += a1[k].y; acc.z += a1[k].z; acc.w += a1[k].w;
+            int p = beg[k] + 2;
+            for (; p + 1 < end[k]; p += 2) {
+                const int ja = __ldg(ii + p), jb = __ldg(ii + p + 1);
+                const float wa = weight_of(ja), wb = weight_of(jb);
+                float4 ta = make_float4(0.f, 0.f, 0.f, 0.f), tb = ta;
+                acc_row<VEC>(ta, src + (size_t)ja * C, C, c, wa);
+                acc_row<VEC>(tb, src + (size_t)jb * C, C, c, wb);
+                acc.x += ta.x; acc.y += ta.y; acc.z += ta.z; acc.w += ta.w;
+                acc.x += tb.x; acc.y += tb.y; acc.z += tb.z; acc.w += tb.w;
+            }
+            if (p < end[k]) {
+                const int j = __ldg(ii + p);
+                acc_row<VEC>(acc, src + (size_t)j * C, C, c, weight_of(j));
+            }
+        } else if (len == 1) {
+            acc = a0[k];                                          // == 0 + w * v, what acc_row on a zero accumulator gives
+        }
+        if (len > 0) {
+            float s = 1.f;
+            if (MODE == 0) s = 1.f / (float)len;
+            if (MODE == 2) s = 1.f / __ldg(occ + (size_t)b * occ_stride + r[k]);
+            acc.x *= s; acc.y *= s; acc.z *= s; acc.w *= s;
+        }
+        store_row<VEC>(out + ((size_t)b * R_out + r[k]) * C, C, c, acc);
+    }
 }
 
 template <int MODE>
@@ -1475,7 +1518,7 @@ static int launch_segment(const float* in, float* out, const int32_t* ptr, const
     const int threads = cq <= 256 ? 256 : ((cq + 31) / 32) * 32;
     if (threads > 1024) return MCNN_E_BADARG;
     const int rpc = threads / cq;
-    dim3 grid((unsigned)ceil_div(R_out, rpc), (unsigned)B);
+    dim3 grid((unsigned)ceil_div(R_out, rpc * SEG_NR), (unsigned)B);
     if ((C & 3) == 0)
         launch_k(segment_kernel<MODE, true>, grid, threads, 0, st, in, out, ptr, idx, aux_ptr, occ, valid, B, R_out, R_in,
                                                              ptr_stride, aux_stride, occ_stride, C, nnz_cap);
