@@ -111,8 +111,12 @@ class MeshConvFn(torch.autograd.Function):
     """Fused MeshConv (mesh_conv.py:20-26) with the backward of SURVEY.md Appendix A."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, level, wt_ws, img=None):
+    def forward(ctx, x, weight, bias, level, wt_ws, img=None, pass_input=False):
+        """pass_input=True returns (out, x): the caller uses the second output wherever it needs x again (the residual branch
+        of DownConv / UpConv, networks.py:222-233 / :276-288).  Both gradients of x then arrive HERE, and the data-gradient
+        kernel scatters straight into the residual's gradient instead of into zeros: no zero fill and no gradient add."""
         _chk_cuda(x, weight, bias)
+        x_in = x
         B, E, Cin = x.shape
         Cout = weight.shape[0]
         x = x.contiguous()
@@ -151,10 +155,13 @@ class MeshConvFn(torch.autograd.Function):
         ctx.img = img if use_tc else None
         ctx.level = level
         ctx.has_bias = bias is not None
+        ctx.pass_input = bool(pass_input)
+        if pass_input:
+            return out, x_in
         return out
 
     @staticmethod
-    def backward(ctx, dout):
+    def backward(ctx, dout, dpass=None):
         x, w = ctx.saved_tensors
         level = ctx.level
         B, E, Cin = x.shape
@@ -190,7 +197,11 @@ class MeshConvFn(torch.autograd.Function):
                                                           dw.data_ptr(), _lib.ptr(db), B, E, Cin, Cout, side.cuda_stream),
                                'mcnn_meshconv_bwd_weight')
         if ctx.needs_input_grad[0]:
-            dx = torch.zeros_like(x)
+            # the gradient that reached x through the pass-through output: scatter into it (it is this node's to keep: the norm
+            # block allocated it for this edge alone); anything unusual is added afterwards instead
+            seed = dpass if (dpass is not None and dpass.dtype == torch.float32 and dpass.shape == x.shape and dpass.is_contiguous()
+                             and dpass._base is None and dpass.data_ptr() != dout.data_ptr()) else None
+            dx = seed if seed is not None else torch.zeros_like(x)
             if tc_ok and Cout % 32 == 0:
                 pre = ctx.img is not None
                 wtb = ctx.img[1] if pre else torch.empty(2 * 5 * Cin, Cout, dtype=torch.float32, device=x.device)
@@ -229,7 +240,11 @@ class MeshConvFn(torch.autograd.Function):
             dw = db = None                                   # already in weight.grad / bias.grad
             if GRAD_REDUCER is not None and want_w:
                 GRAD_REDUCER.conv_backward_launched(ctx.params[0])
-        return dx, dw, db, None, None, None
+        if dpass is not None and dx is not None and dx is not dpass:
+            dx = dx + dpass
+        elif dpass is not None and dx is None and ctx.needs_input_grad[0]:
+            dx = dpass
+        return dx, dw, db, None, None, None, None
 
 
 def pool_norms(x):

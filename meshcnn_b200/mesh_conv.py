@@ -49,11 +49,14 @@ class MeshConv(nn.Module):
             self._img[2].record(stream)
         self._img[3] = token
 
-    def forward_em(self, x_em, batch):
-        """Edge-major entry used by meshcnn_b200.networks: [B, E, Cin] -> [B, E, Cout]."""
+    def forward_em(self, x_em, batch, pass_input=False):
+        """Edge-major entry used by meshcnn_b200.networks: [B, E, Cin] -> [B, E, Cout]; pass_input=True: (out, x_em), see
+        MeshConvFn.forward."""
         w = self.conv.weight
         if self._wt_ws is None or self._wt_ws.device != x_em.device:
             self._wt_ws = torch.empty(2 * w.shape[1] * 5, w.shape[0], dtype=torch.float32, device=x_em.device)
         from . import functional as Fn
         img = self._img if (self._img is not None and self._img[3] == Fn.STEP_TOKEN and Fn.STEP_TOKEN >= 0) else None
+        if pass_input:
+            return MeshConvFn.apply(x_em, w, self.conv.bias, batch.level(x_em.shape[1]), self._wt_ws, img, True)
         return MeshConvFn.apply(x_em, w, self.conv.bias, batch.level(x_em.shape[1]), self._wt_ws, img)

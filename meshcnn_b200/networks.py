@@ -24,6 +24,11 @@ from .functional import ClassifierHeadFn, fused_norm
 from .layout import as_bce, as_bce1, to_edge_major
 from .mesh import MeshBatch
 from .mesh_conv import MeshConv
+
+import os
+# residual branches hand their gradient to the conv's data-gradient kernel as its starting value (MeshConvFn pass_input);
+# MESHCNN_B200_RES_PASS=0: plain autograd accumulation (A/B switch)
+RES_PASS = os.environ.get('MESHCNN_B200_RES_PASS', '1') != '0'
 from .mesh_pool import MeshPool
 from .mesh_unpool import MeshUnpool
 
@@ -222,7 +227,11 @@ class DownConv(nn.Module):
     def forward_em(self, x, batch):
         x1 = _norm_em(self.bn[0], self.conv1.forward_em(x, batch), post_relu=True)
         for idx, conv in enumerate(self.conv2):
-            x1 = _norm_em(self.bn[idx + 1], conv.forward_em(x1, batch), post_add=x1, post_relu=True)
+            if RES_PASS:
+                x2, res = conv.forward_em(x1, batch, pass_input=True)   # res is x1: both of its gradients meet in the conv's backward
+            else:
+                x2, res = conv.forward_em(x1, batch), x1
+            x1 = _norm_em(self.bn[idx + 1], x2, post_add=res, post_relu=True)
         before_pool = None
         if self.pool is not None:
             before_pool = x1
@@ -255,8 +264,11 @@ class UpConv(nn.Module):
         x1 = self.conv1.forward_em(x1, batch)
         x1 = _norm_em(self.bn[0], x1, post_relu=True) if len(self.bn) else F.relu(x1)
         for idx, conv in enumerate(self.conv2):
-            x2 = conv.forward_em(x1, batch)
-            res = x1 if self.residual else None
+            if self.residual and len(self.bn) and RES_PASS:
+                x2, res = conv.forward_em(x1, batch, pass_input=True)   # res is x1: both of its gradients meet in the conv's backward
+            else:
+                x2 = conv.forward_em(x1, batch)
+                res = x1 if self.residual else None
             if len(self.bn):
                 x1 = _norm_em(self.bn[idx + 1], x2, post_add=res, post_relu=True)
             else:
