@@ -272,6 +272,12 @@ int mcnn_norm_fwd(const float* x, const float* a, const float* r, const float* g
 int mcnn_norm_bwd(const float* dy, const float* y, const float* x, const float* a, const float* gamma, const float* mean,
                   const float* rstd, float* dx, float* dr, float* dgamma, float* dbeta, float* part, float* s1, float* s2,
                   int nblocks, int rows_per_block, int C, int G, int pre_relu, int post_relu, void* stream);
+/* mcnn_norm_bwd with dx = (gradient through the block) + dacc (dacc NULL: identical to mcnn_norm_bwd): x also feeds another
+ * branch -- the residual of MResConv, networks.py:171-179 -- whose gradient is already known; saves the separate add. */
+int mcnn_norm_bwd_acc(const float* dy, const float* y, const float* x, const float* a, const float* gamma, const float* mean,
+                      const float* rstd, const float* dacc, float* dx, float* dr, float* dgamma, float* dbeta, float* part,
+                      float* s1, float* s2, int nblocks, int rows_per_block, int C, int G, int pre_relu, int post_relu,
+                      void* stream);
 
 /* torch.optim.Adam step (no amsgrad) over flat fp32 buffers: parameters, gradients, exp_avg, exp_avg_sq (mesh_classifier.py:38) */
 int mcnn_adam_flat(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,

@@ -67,6 +67,7 @@ SIGNATURES = {
     'mcnn_norm_bwd_apply': (_c_int, [_c_vp] * 11 + [_c_int] * 6 + [_c_vp]),
     'mcnn_norm_fwd': (_c_int, [_c_vp] * 11 + [ctypes.c_float, ctypes.c_float] + [_c_int] * 7 + [_c_vp]),
     'mcnn_norm_bwd': (_c_int, [_c_vp] * 14 + [_c_int] * 6 + [_c_vp]),
+    'mcnn_norm_bwd_acc': (_c_int, [_c_vp] * 15 + [_c_int] * 6 + [_c_vp]),
     'mcnn_adam_flat': (_c_int, [_c_vp] * 4 + [ctypes.c_longlong] + [ctypes.c_float] * 5 + [_c_int, _c_vp]),
     'mcnn_adam_flat_state': (_c_int, [_c_vp] * 4 + [ctypes.c_longlong, _c_vp, _c_vp]),
     'mcnn_unpool_bwd': (_c_int, [_c_vp] * 6 + [_c_int] * 6 + [_c_vp]),

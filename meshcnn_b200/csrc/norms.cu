@@ -253,7 +253,8 @@ __global__ void __launch_bounds__(NT) norm_bwd_apply_kernel(const float* __restr
                                                             const float* __restrict__ gamma, const float* __restrict__ mean,
                                                             const float* __restrict__ rstd, const float* __restrict__ s1,
                                                             const float* __restrict__ s2, float* __restrict__ dx,
-                                                            float* __restrict__ dr, int pre_relu, int post_relu, NormShape s) {
+                                                            float* __restrict__ dr, const float* __restrict__ dacc, int pre_relu,
+                                                            int post_relu, NormShape s) {
     pdl_enter();
     const int cq = s.C >> 2;
     const int rpp = NT / cq;
@@ -290,6 +291,10 @@ __global__ void __launch_bounds__(NT) norm_bwd_apply_kernel(const float* __restr
             o[j] = dz;
         }
         if (dr != nullptr) *reinterpret_cast<float4*>(dr + off) = make_float4(d[0], d[1], d[2], d[3]);
+        if (dacc != nullptr) {                                   // a second gradient of x (it also feeds a residual branch)
+            const float4 t = ld4(dacc + off);
+            o[0] += t.x; o[1] += t.y; o[2] += t.z; o[3] += t.w;
+        }
         *reinterpret_cast<float4*>(dx + off) = make_float4(o[0], o[1], o[2], o[3]);
     };
     int row = r0 + ty;
@@ -677,10 +682,24 @@ extern "C" int mcnn_norm_fwd(const float* x, const float* a, const float* r, con
     return after_launch();
 }
 
+extern "C" int mcnn_norm_bwd_acc(const float* dy, const float* y, const float* x, const float* a, const float* gamma,
+                                 const float* mean, const float* rstd, const float* dacc, float* dx, float* dr, float* dgamma,
+                                 float* dbeta, float* part, float* s1, float* s2, int nblocks, int rows_per_block, int C, int G,
+                                 int pre_relu, int post_relu, void* stream);
+
 extern "C" int mcnn_norm_bwd(const float* dy, const float* y, const float* x, const float* a, const float* gamma,
                              const float* mean, const float* rstd, float* dx, float* dr, float* dgamma, float* dbeta,
                              float* part, float* s1, float* s2, int nblocks, int rows_per_block, int C, int G, int pre_relu,
                              int post_relu, void* stream) {
+    return mcnn_norm_bwd_acc(dy, y, x, a, gamma, mean, rstd, nullptr, dx, dr, dgamma, dbeta, part, s1, s2, nblocks, rows_per_block, C, G,
+                             pre_relu, post_relu, stream);
+}
+
+/* the same with dx = (gradient through the block) + dacc: x also feeds another branch whose gradient is already known */
+extern "C" int mcnn_norm_bwd_acc(const float* dy, const float* y, const float* x, const float* a, const float* gamma,
+                                 const float* mean, const float* rstd, const float* dacc, float* dx, float* dr, float* dgamma,
+                                 float* dbeta, float* part, float* s1, float* s2, int nblocks, int rows_per_block, int C, int G,
+                                 int pre_relu, int post_relu, void* stream) {
     if (!dy || !x || !mean || !rstd || !dx || !part || !s1 || !s2 || !norm_args_ok(nblocks, rows_per_block, C, G)) return MCNN_E_BADARG;
     if (post_relu && !y) return MCNN_E_BADARG;
     cudaStream_t st = (cudaStream_t)stream;
@@ -688,7 +707,7 @@ extern "C" int mcnn_norm_bwd(const float* dy, const float* y, const float* x, co
     const size_t smem = (size_t)(NT / (C / 4)) * 2 * C * sizeof(float);
     int rc;
     size_t fsm = 0;
-    const int cw = fused_cw(nblocks, rows_per_block, C, G, &fsm);
+    const int cw = dacc != nullptr ? 0 : fused_cw(nblocks, rows_per_block, C, G, &fsm);   // the one-launch form has no dacc input
     if (cw) {
         static DynSmemGuard configured;
         if (int grc = configured.ensure(norm_fused_bwd_kernel, 200 * 1024)) return grc;
@@ -708,7 +727,7 @@ extern "C" int mcnn_norm_bwd(const float* dy, const float* y, const float* x, co
     const int nfin = nblocks * G + C;
     launch_k(norm_bwd_finalize_kernel, ceil_div(nfin * 32, 256), 256, 0, st, part, gamma, s1, s2, dgamma, dbeta, s);
     if ((rc = after_launch())) return rc;
-    launch_k(norm_bwd_apply_kernel, dim3(nblocks, s.slabs), NT, 0, st, dy, y, x, a, gamma, mean, rstd, s1, s2, dx, dr, pre_relu, post_relu, s);
+    launch_k(norm_bwd_apply_kernel, dim3(nblocks, s.slabs), NT, 0, st, dy, y, x, a, gamma, mean, rstd, s1, s2, dx, dr, dacc, pre_relu, post_relu, s);
     return after_launch();
 }
 
@@ -744,7 +763,7 @@ extern "C" int mcnn_norm_bwd_apply(const float* dy, const float* y, const float*
     if (!dy || !x || !mean || !rstd || !s1 || !s2 || !dx || !norm_args_ok(nblocks, rows_per_block, C, G)) return MCNN_E_BADARG;
     if (post_relu && !y) return MCNN_E_BADARG;
     const NormShape s = make_shape(nblocks, rows_per_block, C, G);
-    launch_k(norm_bwd_apply_kernel, dim3(nblocks, s.slabs), NT, 0, (cudaStream_t)stream, dy, y, x, a, gamma, mean, rstd, s1, s2, dx, dr, pre_relu, post_relu, s);
+    launch_k(norm_bwd_apply_kernel, dim3(nblocks, s.slabs), NT, 0, (cudaStream_t)stream, dy, y, x, a, gamma, mean, rstd, s1, s2, dx, dr, (const float*)nullptr, pre_relu, post_relu, s);
     return after_launch();
 }
 

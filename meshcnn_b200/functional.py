@@ -320,7 +320,11 @@ class FusedNormFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, a, r, gamma, beta, cfg):
+        """cfg['pass_input']: returns (y, x) -- the caller uses the second output wherever it needs x again (the residual of
+        MResConv, networks.py:171-179), so that both gradients of x arrive in this node's backward and the apply kernel adds
+        them (mcnn_norm_bwd_acc) instead of a separate torch add."""
         _chk_cuda(x, a, r, gamma, beta)
+        x_in = x
         x = x.contiguous()
         a = None if a is None else a.contiguous()
         r = None if r is None else r.contiguous()
@@ -346,10 +350,12 @@ class FusedNormFn(torch.autograd.Function):
         ctx.save_for_backward(x, a, gamma, mean, rstd, y)
         ctx.params = (gamma, beta)
         ctx.cfg = (nblocks, rows, C, G, int(cfg['pre_relu']), int(cfg['post_relu']), stats_given, r is not None)
+        if cfg.get('pass_input'):
+            return y, x_in
         return y
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, dpass=None):
         x, a, gamma, mean, rstd, y = ctx.saved_tensors
         nblocks, rows, C, G, pre_relu, post_relu, stats_given, has_r = ctx.cfg
         if stats_given:
@@ -367,14 +373,21 @@ class FusedNormFn(torch.autograd.Function):
             dbeta = torch.empty_like(gamma) if gamma is not None else None
         part = torch.empty(max(1, L.mcnn_norm_ws(nblocks, rows, C, G)), dtype=torch.float32, device=dev)
         s12 = torch.empty(2, nblocks * G, dtype=torch.float32, device=dev)
+        # the gradient that reached x through the pass-through output is added inside the apply kernel -- unless x + a share dx
+        dacc = None
+        if dpass is not None and a is None and dpass.dtype == torch.float32 and dpass.shape == x.shape:
+            dacc = dpass.contiguous()
         with profiler.span('norm_bwd', nblocks=nblocks, rows=rows, C=C, G=G):
-            _lib.check(L.mcnn_norm_bwd(dy.data_ptr(), y.data_ptr(), x.data_ptr(), _lib.ptr(a), _lib.ptr(gamma), mean.data_ptr(),
-                                       rstd.data_ptr(), dx.data_ptr(), _lib.ptr(dr), _lib.ptr(dgamma), _lib.ptr(dbeta),
-                                       part.data_ptr(), s12[0].data_ptr(), s12[1].data_ptr(), nblocks, rows, C, G, pre_relu,
-                                       post_relu, _lib.current_stream()), 'mcnn_norm_bwd')
+            _lib.check(L.mcnn_norm_bwd_acc(dy.data_ptr(), y.data_ptr(), x.data_ptr(), _lib.ptr(a), _lib.ptr(gamma), mean.data_ptr(),
+                                           rstd.data_ptr(), _lib.ptr(dacc), dx.data_ptr(), _lib.ptr(dr), _lib.ptr(dgamma),
+                                           _lib.ptr(dbeta), part.data_ptr(), s12[0].data_ptr(), s12[1].data_ptr(), nblocks, rows,
+                                           C, G, pre_relu, post_relu, _lib.current_stream()), 'mcnn_norm_bwd')
         if direct is not None:
             dgamma = dbeta = None                            # already in gamma.grad / beta.grad
-        return dx, (dx if a is not None else None), dr, dgamma, dbeta, None
+        da = dx if a is not None else None
+        if dpass is not None and dacc is None:
+            dx = dx + dpass
+        return dx, da, dr, dgamma, dbeta, None
 
 
 class ClassifierHeadFn(torch.autograd.Function):
@@ -511,7 +524,7 @@ def _sync_bn_active():
     return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
 
 
-def fused_norm(x, norm, pre_add=None, pre_relu=False, post_add=None, post_relu=False):
+def fused_norm(x, norm, pre_add=None, pre_relu=False, post_add=None, post_relu=False, pass_input=False):
     """Apply a torch norm module (BatchNorm2d / GroupNorm / InstanceNorm2d, the three the reference's networks use) to
     edge-major x [B, E, C] with the surrounding add / relu fused in.  Returns None if `norm` is not one of those."""
     import torch.nn as nn
@@ -538,11 +551,14 @@ def fused_norm(x, norm, pre_add=None, pre_relu=False, post_add=None, post_relu=F
                 cfg.update(running_mean=norm.running_mean, running_var=norm.running_var, momentum=norm.momentum)
                 norm.num_batches_tracked.add_(1)
             if _sync_bn_active():
-                return SyncBatchNormFn.apply(x, pre_add, post_add, gamma, beta, cfg)
+                y = SyncBatchNormFn.apply(x, pre_add, post_add, gamma, beta, cfg)
+                return (y, x) if pass_input else y
         else:
             cfg.update(mean=norm.running_mean, rstd=torch.rsqrt(norm.running_var + norm.eps))
     else:
         return None
     if (gamma is None) != (beta is None):
         return None
+    if pass_input:
+        cfg['pass_input'] = True
     return FusedNormFn.apply(x, pre_add, post_add, gamma, beta, cfg)

@@ -137,10 +137,10 @@ def define_loss(opt):
 # ---------------------------------------------------------------------------------------------------------------
 # edge-major helpers
 # ---------------------------------------------------------------------------------------------------------------
-def _norm_em(norm, x, pre_add=None, pre_relu=False, post_add=None, post_relu=False):
+def _norm_em(norm, x, pre_add=None, pre_relu=False, post_add=None, post_relu=False, pass_input=False):
     """post(norm(pre(x [+ pre_add])) [+ post_add]) on edge-major data.  BatchNorm2d / GroupNorm / InstanceNorm2d run as one
     fused CUDA block (mcnn_norm_fwd); anything else goes through torch on the [B, C, E, 1] channels_last view."""
-    y = fused_norm(x, norm, pre_add, pre_relu, post_add, post_relu)
+    y = fused_norm(x, norm, pre_add, pre_relu, post_add, post_relu, pass_input)     # pass_input: (y, x), see FusedNormFn.forward
     if y is not None:
         return y
     z = x if pre_add is None else x + pre_add
@@ -149,7 +149,8 @@ def _norm_em(norm, x, pre_add=None, pre_relu=False, post_add=None, post_relu=Fal
     y = to_edge_major(norm(as_bce1(z)))
     if post_add is not None:
         y = y + post_add
-    return F.relu(y) if post_relu else y
+    y = F.relu(y) if post_relu else y
+    return (y, x) if pass_input else y
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -169,7 +170,10 @@ class MResConv(nn.Module):
         x = self.conv0.forward_em(x, batch)
         skip = x
         for i in range(1, self.skips + 1):
-            x = _norm_em(getattr(self, 'bn%d' % i), x, pre_relu=True)
+            if i == 1 and RES_PASS:          # skip is conv0's output again: both of its gradients meet in bn1's backward kernel
+                x, skip = _norm_em(getattr(self, 'bn%d' % i), x, pre_relu=True, pass_input=True)
+            else:
+                x = _norm_em(getattr(self, 'bn%d' % i), x, pre_relu=True)
             x = getattr(self, 'conv%d' % i).forward_em(x, batch)
         if defer_tail:
             return x, skip
