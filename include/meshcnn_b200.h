@@ -289,6 +289,20 @@ int mcnn_adam_flat(float* p, const float* g, float* m, float* v, long long n, fl
 int mcnn_adam_flat_state(float* p, const float* g, float* m, float* v, long long n, float* state, void* stream);
 
 /* ----------------------------------------------------------------------------------------------------------
+ * Host-side topology builder (no device work): the sequential parts of the reference's mesh
+ * preparation, models/layers/mesh_prepare.py:90-113 (remove_non_manifolds) and :116-161 (build_gemm).  All pointers are HOST
+ * memory.  faces [nf][3] int64; face_areas [nf] double.
+ *   mcnn_host_drop_non_manifold: keep[f] = 1 for faces that survive (non-zero area, no directed edge already used by an
+ *     accepted face); returns the number kept.
+ *   mcnn_host_build_gemm: edges in order of first appearance; outputs sized for E = 3 nf: edges [3nf][2] int32, gemm / sides
+ *     [3nf][4] int64 (-1 = boundary), ve_ptr [nv + 1] / ve_idx [6 nf] int32 (vertex -> incident edges, creation order),
+ *     edge_area_sum [3nf] double (face_area / 3 accumulated in face order).  Returns E; -100: an edge with more than two faces.
+ * ---------------------------------------------------------------------------------------------------------- */
+int mcnn_host_drop_non_manifold(const int64_t* faces, const double* face_areas, int nf, int nv, uint8_t* keep);
+int mcnn_host_build_gemm(const int64_t* faces, const double* face_areas, int nf, int nv, int32_t* edges, int64_t* gemm,
+                         int64_t* sides, int32_t* ve_ptr, int32_t* ve_idx, double* edge_area_sum);
+
+/* ----------------------------------------------------------------------------------------------------------
  * Classifier head of MeshConvNet (models/networks.py:143-157): AvgPool1d over the edge axis, fc1 + relu, fc2.
  *     pooled[b][c] = mean_e x[b][e][c];  h = relu(W1 pooled + b1);  logits = W2 h + b2
  * x: [B][E][C] edge-major (the whole, zero-padded edge axis is averaged, as AvgPool1d(res[-1]) does); W1: [H][C], W2: [K][H]

@@ -16,6 +16,8 @@ first-occurrence ``np.unique`` over packed vertex-pair keys and the slot tables 
 """
 import ntpath
 
+import os
+
 import numpy as np
 
 
@@ -53,9 +55,29 @@ def face_areas_of(vs, faces):
     return 0.5 * np.sqrt((n ** 2).sum(1))
 
 
+# The sequential parts (the face sweep and build_gemm) run in the library's host-side C++ (csrc/mesh_topology.cu); the NumPy /
+# Python formulations below are the same algorithm and stay as the cross-check (tests/test_mesh_prepare.py) and for
+# MESHCNN_B200_NATIVE_PREPARE=0.
+NATIVE = os.environ.get('MESHCNN_B200_NATIVE_PREPARE', '1') != '0'
+
+
 def drop_non_manifold(vs, faces):
     """Drop zero-area faces and faces repeating an already-used *directed* edge (mesh_prepare.py:90-113).
     The acceptance of a face depends on the faces accepted before it, so this is a sequential sweep."""
+    if not NATIVE:
+        return drop_non_manifold_py(vs, faces)
+    from . import _lib
+    faces = np.ascontiguousarray(faces, dtype=np.int64)
+    areas = np.ascontiguousarray(face_areas_of(vs, faces), dtype=np.float64) if len(faces) else np.zeros(0)
+    keep = np.zeros(len(faces), dtype=np.uint8)
+    rc = _lib.lib().mcnn_host_drop_non_manifold(faces.ctypes.data, areas.ctypes.data, len(faces), int(vs.shape[0]), keep.ctypes.data)
+    if rc < 0:
+        raise RuntimeError('mcnn_host_drop_non_manifold failed (%d)' % rc)
+    keep = keep.astype(bool)
+    return faces[keep], areas[keep]
+
+
+def drop_non_manifold_py(vs, faces):
     areas = face_areas_of(vs, faces)
     keep = np.ones(len(faces), dtype=bool)
     seen = set()
@@ -76,6 +98,36 @@ def drop_non_manifold(vs, faces):
 def build_topology(vs, faces, face_areas=None):
     """Returns edges[E,2] int32, gemm_edges[E,4] int64, sides[E,4] int64, ve (list of lists),
     edge_areas[E] float32."""
+    if not NATIVE:
+        return build_topology_py(vs, faces, face_areas)
+    from . import _lib
+    faces = np.ascontiguousarray(faces, dtype=np.int64)
+    nf, nv = len(faces), int(vs.shape[0])
+    if face_areas is None:
+        face_areas = face_areas_of(vs, faces)
+    face_areas = np.ascontiguousarray(face_areas, dtype=np.float64)
+    cap = max(1, 3 * nf)
+    edges = np.empty((cap, 2), dtype=np.int32)
+    gemm = np.empty((cap, 4), dtype=np.int64)
+    sides = np.empty((cap, 4), dtype=np.int64)
+    ve_ptr = np.empty(nv + 1, dtype=np.int32)
+    ve_idx = np.empty(2 * cap, dtype=np.int32)
+    ea = np.empty(cap, dtype=np.float64)
+    E = _lib.lib().mcnn_host_build_gemm(faces.ctypes.data, face_areas.ctypes.data, nf, nv, edges.ctypes.data, gemm.ctypes.data,
+                                        sides.ctypes.data, ve_ptr.ctypes.data, ve_idx.ctypes.data, ea.ctypes.data)
+    if E == -100:
+        raise ValueError('edge shared by more than two faces (non-manifold input)')
+    if E < 0:
+        raise RuntimeError('mcnn_host_build_gemm failed (%d)' % E)
+    idx = ve_idx[:2 * E].tolist()
+    ptr = ve_ptr.tolist()
+    ve = [idx[ptr[v]:ptr[v + 1]] for v in range(nv)]
+    # float32 array / float64 scalar: the result dtype follows numpy's promotion rules, as in the reference
+    edge_areas = ea[:E].astype(np.float32) / np.sum(face_areas)
+    return edges[:E].copy(), gemm[:E].copy(), sides[:E].copy(), ve, edge_areas
+
+
+def build_topology_py(vs, faces, face_areas=None):
     nf = len(faces)
     if face_areas is None:
         face_areas = face_areas_of(vs, faces)

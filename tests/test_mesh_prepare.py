@@ -71,3 +71,33 @@ def test_mesh_honours_opt_and_cache(tmp_path):
     for _ in range(12):                                                   # other slots get their own files (at most num_aug)
         Mesh(file=p, opt=opt)
     assert 2 <= len(os.listdir(tmp_path / 'cache')) <= 3
+
+
+def test_native_topology_builder_matches_the_numpy_formulation():
+    """csrc/mesh_topology.cu (mcnn_host_drop_non_manifold / mcnn_host_build_gemm) against the NumPy / Python formulation of the
+    same steps, on clean meshes, on input with zero-area and directed-edge-repeating faces, and on the >2-faces-per-edge error."""
+    import numpy as np
+    from meshcnn_b200 import mesh_prepare, synth
+    cases = [synth.make('ico', 1, nu=5), synth.make('torus', 2, m=10, n=25), synth.make('torus', 5, m=7, n=9)]
+    vs, faces = synth.make('ico', 3, nu=3)
+    faces = np.concatenate([faces, faces[:5], faces[7:9][:, ::-1], np.array([[0, 0, 1], [2, 3, 3]])])   # repeats, flips, zero area
+    cases.append((vs, faces))
+    vs, faces = synth.make('torus', 4, m=6, n=8)
+    cases.append((vs, faces[:-17]))                                                                    # an open mesh (boundaries)
+    for vs, faces in cases:
+        vs = np.asarray(vs, dtype=np.float64)
+        faces = np.asarray(faces, dtype=np.int64)
+        f1, a1 = mesh_prepare.drop_non_manifold(vs, faces)
+        f0, a0 = mesh_prepare.drop_non_manifold_py(vs, faces)
+        assert np.array_equal(f1, f0) and np.array_equal(a1, a0)
+        t1 = mesh_prepare.build_topology(vs, f1, a1)
+        t0 = mesh_prepare.build_topology_py(vs, f0, a0)
+        for x, y in zip(t1[:3], t0[:3]):
+            assert x.dtype == y.dtype and np.array_equal(x, y)
+        assert t1[3] == t0[3]
+        assert t1[4].dtype == t0[4].dtype and np.array_equal(t1[4], t0[4])
+    vs = np.array([[0., 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1], [1, 1, 1]])
+    fan = np.array([[0, 1, 2], [1, 0, 3], [0, 1, 4]])              # the undirected edge (0, 1) in three faces
+    for fn in (mesh_prepare.build_topology, mesh_prepare.build_topology_py):
+        with pytest.raises(ValueError):
+            fn(vs, fan)
