@@ -185,3 +185,62 @@ def test_bench_size_network_vs_fp64_oracle(name, B):
     assert _rel(out.detach().cpu().numpy(), o64.detach().numpy()) <= 1e-4
     assert not bad, bad
     assert float(np.median(ratios)) <= 2.5, float(np.median(ratios))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Switches that must not change results
+# ---------------------------------------------------------------------------------------------------------------------
+def _grads_of(kind, d, hold, tweak):
+    from meshcnn_b200 import networks as N
+    torch.manual_seed(0)
+    if kind == 'mconvnet':
+        net = N.MeshConvNet(N.get_norm_layer('group', 4), 5, [8, 16], 4, 270, [200, 150], 10, 1)
+        loss_fn = torch.nn.CrossEntropyLoss()
+    else:
+        net = N.MeshEncoderDecoder([270, 200, 150], [5, 8, 16, 32], [32, 16, 8, 3], blocks=1)
+        loss_fn = torch.nn.CrossEntropyLoss(ignore_index=-1)
+    with tweak():
+        net, meshes, x, out, loss = _run_product(net, d, loss_fn, hold)
+    torch.cuda.synchronize()
+    return [out.detach().cpu().numpy(), x.grad.cpu().numpy()] + [p.grad.cpu().numpy() for p in net.parameters()]
+
+
+@pytest.mark.parametrize('kind,gold,hold', [('mconvnet', 'net_mconvnet_tiny', False), ('meshunet', 'net_meshunet_tiny', True)])
+def test_residual_gradient_pass_through_equals_plain_autograd(kind, gold, hold):
+    """RES_PASS (the residual branch's gradient enters the conv's scatter / bn1's backward kernel) vs autograd's own
+    accumulation: same numbers up to fp32 summation order."""
+    import contextlib
+    from meshcnn_b200 import networks as N
+
+    @contextlib.contextmanager
+    def off():
+        old, N.RES_PASS = N.RES_PASS, False
+        try:
+            yield
+        finally:
+            N.RES_PASS = old
+    d = golden(gold)
+    a = _grads_of(kind, d, hold, contextlib.nullcontext)
+    b = _grads_of(kind, d, hold, off)
+    for u, v in zip(a, b):
+        assert close(u, v, 1e-5, 2e-6)        # atol: conv biases in front of an InstanceNorm have a mathematically zero gradient (1e-7 of noise)
+
+
+def test_programmatic_dependent_launch_does_not_change_results():
+    """mcnn_debug_set_pdl(1): every kernel launched with the programmatic-stream-serialisation attribute and entering through
+    griddepcontrol.wait -- same numbers as plain stream order."""
+    import contextlib
+    from meshcnn_b200 import _lib
+
+    @contextlib.contextmanager
+    def pdl():
+        _lib.lib().mcnn_debug_set_pdl(1)
+        try:
+            yield
+        finally:
+            _lib.lib().mcnn_debug_set_pdl(0)
+    d = golden('net_meshunet_tiny')
+    a = _grads_of('meshunet', d, True, contextlib.nullcontext)
+    b = _grads_of('meshunet', d, True, pdl)
+    for u, v in zip(a, b):
+        assert close(u, v, 1e-5, 2e-6)        # atol: conv biases in front of an InstanceNorm have a mathematically zero gradient (1e-7 of noise)
