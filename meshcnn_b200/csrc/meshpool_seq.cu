@@ -406,8 +406,11 @@ struct Collapse {
     typedef typename P::idx_t idx_t;
     typedef typename P::uidx_t uidx_t;
     typedef typename P::pair_t pair_t;
-    WorkQueue* q;             // list walks go to the helper warp
+    WorkQueue* q;             // list walks (one-ring tests, searches) go to helper warp R ...
     unsigned posted;
+    WorkQueue* qm;            // ... list merges to helper warp M, which nobody waits for unless the next operation needs its result
+    unsigned posted_m;
+    int last_mv0;             // the vertex whose list the most recent merge writes (-1: none yet)
     idx_t* gemm;
     uidx_t *rep, *slab_next, *chain_tail, *ve, *eposa, *eposb;
     pair_t *evp, *ulog;
@@ -428,20 +431,40 @@ struct Collapse {
 #endif
     __device__ __forceinline__ void ends(int e, int& v0, int& v1) { edge_ends<P>(evp, rep, e, v0, v1); }
 
-    __device__ __forceinline__ void post(int op, int a0, int a1, int a2) {
-        while (posted - (*(volatile unsigned*)&q->res >> 2) >= (unsigned)WQ_CAP) {}
+    __device__ __forceinline__ void post_to(WorkQueue* qq, unsigned& cnt, int op, int a0, int a1, int a2) {
+        while (cnt - (*(volatile unsigned*)&qq->res >> 2) >= (unsigned)WQ_CAP) {}
 #ifdef MCNN_POOL_PROF
         const long long tp_ = clock64();
 #endif
-        const unsigned slot = posted % WQ_CAP;
-        ++posted;
+        const unsigned slot = cnt % WQ_CAP;
+        ++cnt;
         cta_fence();                               // everything this thread wrote before the operation becomes visible
-        *(volatile unsigned long long*)&q->ent[slot] = (unsigned long long)(unsigned)op | ((unsigned long long)(posted & 0xFFFu) << 4) |
+        *(volatile unsigned long long*)&qq->ent[slot] = (unsigned long long)(unsigned)op | ((unsigned long long)(cnt & 0xFFFu) << 4) |
             ((unsigned long long)(unsigned)(a0 & 0xFFFF) << 16) | ((unsigned long long)(unsigned)(a1 & 0xFFFF) << 32) |
             ((unsigned long long)(unsigned)(a2 & 0xFFFF) << 48);
 #ifdef MCNN_POOL_PROF
         prof[5] += clock64() - tp_;
 #endif
+    }
+    __device__ __forceinline__ void post(int op, int a0, int a1, int a2) { post_to(q, posted, op, a0, a1, a2); }
+
+    // Two helper warps.  M builds the merged list of a committed collapse while R already walks the one-ring of the next
+    // candidate: the walk reads the lists of the candidate's two endpoints only (plus evp / rep words, where the merge's
+    // redirection and the union-find agree), the merge writes the list of ITS surviving vertex and the entry positions of edges
+    // incident to it -- so the two may overlap unless the candidate touches that vertex (then the request waits for the merge).
+    // Everything thread 0 itself does to the lists (tombstones of the next commit, searches) waits for the merge first; by then
+    // it has long finished.  At most one merge is in flight.
+    __device__ __forceinline__ void wait_merges() {
+        while ((*(volatile unsigned*)&qm->res >> 2) != posted_m) {}
+        cta_fence();
+    }
+    __device__ __forceinline__ void post_merge(int v0, int v1) {
+        post_to(qm, posted_m, WOP_MERGE, v0, v1, 0);
+        last_mv0 = v0;
+    }
+    __device__ __forceinline__ void post_ring(int v0, int v1) {
+        if (v0 == last_mv0 || v1 == last_mv0) wait_merges();
+        post(WOP_ONE_RING, v0, v1, 0);
     }
 
     // MeshUnion.union (mesh_union.py:11-12) is only logged here; the rows are evaluated after the collapse
@@ -578,7 +601,7 @@ struct Collapse {
     __device__ void one_ring_request(int e) {
         int v0, v1;
         ends(e, v0, v1);
-        post(WOP_ONE_RING, v0, v1, 0);
+        post_ring(v0, v1);
     }
 
     // Mesh.remove_edge (mesh.py:42-48): both list entries of x become tombstones
@@ -619,7 +642,7 @@ struct Collapse {
         if (v0 == v1) { status = MCNN_ST_DEGENERATE; return; }
         // ve[v0].extend(ve[v1]) : the helper warp moves v1's list behind v0's (ve[v1] is unreachable once every row holding v1
         // reads v0); not waited for -- the next list operation is queued behind it
-        post(WOP_MERGE, v0, v1, 0);
+        post_merge(v0, v1);
         if (vs != nullptr) {
 #pragma unroll
             for (int k = 0; k < 3; ++k) vs[3 * v0 + k] = (vs[3 * v0 + k] + vs[3 * v1 + k]) / 2;
@@ -649,6 +672,7 @@ struct Collapse {
         const Face f0 = face_info(e, 0);
         const bool ring_ok = wait_result() == 2;
         if (!ring_ok) return MCNN_POP_REJ_ONE_RING;
+        wait_merges();                                           // the commit edits lists and entry positions itself
         return commit_generic(e, f0);
     }
 
@@ -722,7 +746,7 @@ struct Collapse {
         const long long t1_ = clock64();
         prof[0] += t1_ - t0_;
 #endif
-        post(WOP_ONE_RING, v0, v1, 0);
+        post_ring(v0, v1);
 #ifdef MCNN_POOL_PROF
         const long long t2_ = clock64();
         prof[2] += t2_ - t1_;
@@ -751,6 +775,7 @@ struct Collapse {
 #endif
         const bool ring_ok = wait_result() == 2;
         if (!ring_ok) return MCNN_POP_REJ_ONE_RING;
+        wait_merges();                                           // the commit edits lists and entry positions itself
         if (!distinct) return commit_generic(e, f0);
 #ifdef MCNN_POOL_PROF
         const long long t3_ = clock64();
@@ -791,7 +816,7 @@ struct Collapse {
             }
         }
         if (status) return MCNN_POP_COLLAPSED;
-        post(WOP_MERGE, v0, v1, 0);                              // ve[v0].extend(ve[v1]) on the helper warp, not waited for
+        post_merge(v0, v1);                                      // ve[v0].extend(ve[v1]) on helper warp M, not waited for
         if (vs != nullptr) {
 #pragma unroll
             for (int k = 0; k < 3; ++k) vs[3 * v0 + k] = (p0[k] + p1[k]) / 2;
@@ -958,13 +983,13 @@ __global__ void __launch_bounds__(P::THREADS, 1) pool_collapse_kernel(const mcnn
     __syncthreads();
     if (clk && tid == 0) clk[2] = clock64();
     // ---- phase D: the sequential collapse (mesh_pool.py:41-53) on thread 0; warp 1 serves the list operations ----------
-    __shared__ WorkQueue s_queue;
-    if (tid < WQ_CAP) s_queue.ent[tid] = 0ull;
-    if (tid == 0) s_queue.res = 0u;
+    __shared__ WorkQueue s_queue, s_queue_m;
+    if (tid < WQ_CAP) { s_queue.ent[tid] = 0ull; s_queue_m.ent[tid] = 0ull; }
+    if (tid == 0) { s_queue.res = 0u; s_queue_m.res = 0u; }
     __syncthreads();
     if (tid == 0) {
         Collapse<P> c;
-        c.q = &s_queue; c.posted = 0u;
+        c.q = &s_queue; c.posted = 0u; c.qm = &s_queue_m; c.posted_m = 0u; c.last_mv0 = -1;
         c.gemm = gemm; c.rep = rep; c.slab_next = slab_next; c.chain_tail = chain_tail; c.ve = ve; c.eposa = eposa; c.eposb = eposb;
         c.evp = evp; c.ulog = ulog;
         c.sides = sides; c.mask = mask; c.vs = vs_s; c.vmask = vmask_s;
@@ -984,6 +1009,7 @@ __global__ void __launch_bounds__(P::THREADS, 1) pool_collapse_kernel(const mcnn
             if (c.status) break;
         }
         c.post(WOP_EXIT, 0, 0, 0);
+        c.post_to(c.qm, c.posted_m, WOP_EXIT, 0, 0, 0);
         if (a.log_npops) a.log_npops[b] = p;
         if (a.log_nunions) a.log_nunions[b] = c.nunions;
         s_status = c.status;
@@ -997,12 +1023,16 @@ __global__ void __launch_bounds__(P::THREADS, 1) pool_collapse_kernel(const mcnn
             clk[6] = c.prof[6];
 #endif
         }
-    } else if (tid >= 32 && tid < 64) {
+    } else if (tid >= 32 && tid < 96) {
+        // warp 1 = R (one-ring walks, searches), warp 2 = M (merges); each re-packs lists into its own part of the spare room
+        const bool is_m = tid >= 64;
         WarpCtx<P> w;
         w.ve = ve; w.slab_start = slab_start; w.slab_len = slab_len; w.slab_next = slab_next; w.chain_tail = chain_tail;
         w.rep = rep; w.evp = evp; w.stamp = stamp; w.eposa = eposa; w.eposb = eposb;
-        w.bump = min(g_ve_ptr[V], a.ve_cap); w.bump_end = a.ve_cap + 2 * E_in;
-        helper_warp_loop<P>(w, &s_queue, tid - 32, clk ? clk + 13 : nullptr);
+        const int room0 = min(g_ve_ptr[V], a.ve_cap), room1 = a.ve_cap + 2 * E_in;
+        const int cut = room1 - (room1 - room0) / 4;             // M: [room0, cut), R: [cut, room1)
+        w.bump = is_m ? room0 : cut; w.bump_end = is_m ? cut : room1;
+        helper_warp_loop<P>(w, is_m ? &s_queue_m : &s_queue, tid & 31, clk ? clk + 13 : nullptr);
     }
     __syncthreads();
     int status = s_status;
