@@ -310,11 +310,18 @@ __device__ __forceinline__ int wop_one_ring(WarpCtx<P>& w, int lane, int v0, int
 #ifdef MCNN_POOL_PROF
     const long long t2_ = clock64();
 #endif
-    bool ha = false, hb = false;
-    if (x1 != P::NIL) {
-        if (a1 != v0 && a1 != v1) ha = atomicCAS(&w.stamp[a1], tagA, tagB) == tagA;
-        if (b1 != v0 && b1 != v1) hb = atomicCAS(&w.stamp[b1], tagA, tagB) == tagA;
-    }
+    // every lane tests its two endpoints; each hitting (lane, endpoint) then writes its own mark over the stamp and the one mark
+    // that survives per vertex counts it: distinct vertices are counted once without atomics (tags are multiples of 128, marks
+    // have bit 6 set, so a marked vertex fails the compare-and-swap of the remainder walk below: counted once there too)
+    bool ha = (x1 != P::NIL) && a1 != v0 && a1 != v1 && w.stamp[a1] == tagA;
+    bool hb = (x1 != P::NIL) && b1 != v0 && b1 != v1 && w.stamp[b1] == tagA;
+    __syncwarp();
+    const uint32_t mark = tagA | 64u | (uint32_t)(2 * lane);
+    if (ha) w.stamp[a1] = mark;
+    if (hb) w.stamp[b1] = mark | 1u;
+    __syncwarp();
+    ha = ha && w.stamp[a1] == mark;
+    hb = hb && w.stamp[b1] == (mark | 1u);
     int shared = __popc(__ballot_sync(0xffffffffu, ha)) + __popc(__ballot_sync(0xffffffffu, hb));
 #ifdef MCNN_POOL_PROF
     const long long t3_ = clock64();
@@ -381,8 +388,8 @@ __device__ void helper_warp_loop(WarpCtx<P>& w, WorkQueue* q, int lane, long lon
         const long long th_ = clock64();
 #endif
         int r = 0;
-        if (op == WOP_ONE_RING) {                            // tags: two per operation, never reused within a launch
-            r = min(wop_one_ring<P>(w, lane, a0, a1, seq << 1, hprof ? hprof + 3 : nullptr), 3);    // 2 = valid (mesh_pool.py:99)
+        if (op == WOP_ONE_RING) {                            // tags: multiples of 128, never reused within a launch (< 2^25 operations)
+            r = min(wop_one_ring<P>(w, lane, a0, a1, seq << 7, hprof ? hprof + 3 : nullptr), 3);    // 2 = valid (mesh_pool.py:99)
         } else if (op == WOP_MERGE) {                        // nobody waits for this one
             wop_merge<P>(w, lane, a0, a1);
         } else {                                             // WOP_REMOVE_SCAN: x leaves ve[a], then ve[b] (mesh.py:42-48)
