@@ -1,5 +1,5 @@
-// MeshPool collapse, SEQUENTIAL form: one CTA per mesh, thread 0 runs the reference's pop loop one candidate at a time and a
-// helper warp serves the vertex-list walks (the round-1 kernel).  Kept for SMALL meshes only: the round-based kernel in
+// MeshPool collapse, SEQUENTIAL form: one CTA per mesh, thread 0 runs the reference's pop loop one candidate at a time and two
+// helper warps serve the vertex-list work (R: one-ring walks and searches, M: list merges).  Used for SMALL meshes: the round-based kernel in
 // meshpool.cu commits the conflict-free prefix of a window of candidates per round, and on a 750-edge mesh that prefix is
 // ~2 candidates (measured: 2.4 / 1.9 / 1.9 / 1.9 per round on the cubes pool chain) while a round costs ~2x a sequential
 // pop -- break-even.  From ~1000 edges up the window fills (3.9 per round at 2280 edges, ~15 at 170 k) and the round kernel
@@ -120,8 +120,9 @@ __device__ __forceinline__ int block_scan_excl(int v, int* scratch, int& total) 
 
 
 // The sequential collapse runs on thread 0.  Walks over vertex -> edge lists (the one-ring test, and the rare search for
-// the first occurrence of id 0) are handed to a helper warp (warp 1) through a small shared-memory ring: it walks a list 32
-// entries at a time and the collapse thread waits for the answer.
+// the first occurrence of id 0) are handed to helper warp R (warp 1) through a small shared-memory ring: it walks a list 32
+// entries at a time and the collapse thread waits for the answer; list merges go to helper warp M (warp 2) through a second
+// ring and are not waited for (see Collapse::wait_merges).
 template <class P>
 struct WarpCtx {
     typename P::uidx_t *ve, *slab_start, *slab_len, *slab_next, *chain_tail, *rep, *eposa, *eposb;
@@ -989,7 +990,7 @@ __global__ void __launch_bounds__(P::THREADS, 1) pool_collapse_kernel(const mcnn
     if (tid == 0) { s_cursor = 0; s_flag = 0; s_ndead = 0; }
     __syncthreads();
     if (clk && tid == 0) clk[2] = clock64();
-    // ---- phase D: the sequential collapse (mesh_pool.py:41-53) on thread 0; warp 1 serves the list operations ----------
+    // ---- phase D: the sequential collapse (mesh_pool.py:41-53) on thread 0; warps 1 and 2 serve the list operations ------
     __shared__ WorkQueue s_queue, s_queue_m;
     if (tid < WQ_CAP) { s_queue.ent[tid] = 0ull; s_queue_m.ent[tid] = 0ull; }
     if (tid == 0) { s_queue.res = 0u; s_queue_m.res = 0u; }
