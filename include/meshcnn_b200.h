@@ -298,6 +298,12 @@ int mcnn_adam_flat_state(float* p, const float* g, float* m, float* v, long long
  *     [3nf][4] int64 (-1 = boundary), ve_ptr [nv + 1] / ve_idx [6 nf] int32 (vertex -> incident edges, creation order),
  *     edge_area_sum [3nf] double (face_area / 3 accumulated in face order).  Returns E; -100: an edge with more than two faces.
  * ---------------------------------------------------------------------------------------------------------- */
+/*   mcnn_host_edge_features: the five input features of mesh_prepare.py:303-427 up to their arccos -- edge lengths [E], the
+ *     clipped cosine of the dihedral angle [E], the clipped cosines of the two opposite angles [2][E], the two height / base
+ *     ratios [2][E] -- same operations in the same order as the NumPy formulation (bit-identical; arccos stays in NumPy).
+ *     Returns 0; -101 where NumPy's errstate(divide='raise') would raise (the reference's "bad features"). */
+int mcnn_host_edge_features(const double* vs, int nv, const int32_t* edges, const int64_t* gemm, int E, double* lengths,
+                            double* dih_arg, double* opp_arg, double* ratio);
 int mcnn_host_drop_non_manifold(const int64_t* faces, const double* face_areas, int nf, int nv, uint8_t* keep);
 int mcnn_host_build_gemm(const int64_t* faces, const double* face_areas, int nf, int nv, int32_t* edges, int64_t* gemm,
                          int64_t* sides, int32_t* ve_ptr, int32_t* ve_idx, double* edge_area_sum);

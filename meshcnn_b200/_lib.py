@@ -72,6 +72,7 @@ SIGNATURES = {
     'mcnn_adam_flat_state': (_c_int, [_c_vp] * 4 + [ctypes.c_longlong, _c_vp, _c_vp]),
     'mcnn_unpool_bwd': (_c_int, [_c_vp] * 6 + [_c_int] * 6 + [_c_vp]),
     'mcnn_host_drop_non_manifold': (_c_int, [_c_vp, _c_vp, _c_int, _c_int, _c_vp]),
+    'mcnn_host_edge_features': (_c_int, [_c_vp, _c_int, _c_vp, _c_vp, _c_int] + [_c_vp] * 4),
     'mcnn_host_build_gemm': (_c_int, [_c_vp, _c_vp, _c_int, _c_int] + [_c_vp] * 6),
     'mcnn_head_fwd': (_c_int, [_c_vp] * 8 + [_c_int] * 5 + [_c_vp]),
     'mcnn_head_bwd': (_c_int, [_c_vp] * 11 + [_c_int] * 5 + [_c_vp]),

@@ -95,3 +95,71 @@ extern "C" int mcnn_host_build_gemm(const int64_t* faces, const double* face_are
     }
     return E;
 }
+
+// ---- edge features up to the arccos (models/layers/mesh_prepare.py:303-427) -------------------------------------------------
+// Same operations in the same order as the NumPy formulation in meshcnn_b200/mesh_prepare.py (products, then left-to-right sums
+// of three terms; IEEE division and square root are correctly rounded in both), so the results are bit-identical; the arccos
+// itself stays in NumPy, whose implementation differs between machines.  Compiled without FMA contraction (Makefile).
+#include <math.h>
+
+namespace {
+struct V3 { double x, y, z; };
+inline V3 ld(const double* vs, int i) { return V3{vs[3 * i], vs[3 * i + 1], vs[3 * i + 2]}; }
+inline V3 sub(V3 a, V3 b) { return V3{a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline double dot3(V3 a, V3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+inline double norm3(V3 a) { return sqrt((a.x * a.x + a.y * a.y) + a.z * a.z); }
+inline V3 cross3(V3 a, V3 b) { return V3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+inline V3 divs(V3 a, double d) { return V3{a.x / d, a.y / d, a.z / d}; }
+inline double clip1(double v) { return v < -1.0 ? -1.0 : (v > 1.0 ? 1.0 : v); }   // NaN passes through, as np.clip does
+}  // namespace
+
+// edges [E][2] int32, gemm [E][4] int64, vs [nv][3] double.  Outputs (all [E] double unless noted): lengths; dih_arg = clipped
+// cosine between the two face normals; opp_arg [2][E] = clipped cosines of the two opposite angles; ratio [2][E] = height / base
+// of the two faces.  Returns 0, MCNN_E_BADARG, or -101 when a division NumPy would flag under errstate(divide='raise') occurs
+// (a non-zero numerator over a zero base length).
+extern "C" int mcnn_host_edge_features(const double* vs, int nv, const int32_t* edges, const int64_t* gemm, int E, double* lengths,
+                                       double* dih_arg, double* opp_arg, double* ratio) {
+    if (!vs || !edges || !gemm || !lengths || !dih_arg || !opp_arg || !ratio || nv <= 0 || E < 0) return MCNN_E_BADARG;
+    int flagged = 0;
+    for (int e = 0; e < E; ++e) {
+        const int64_t* g = gemm + 4 * (size_t)e;
+        // get_edge_points (mesh_prepare.py:361-399): boundary edges take the face that exists for both sides
+        const int64_t b_id = g[0] == -1 ? g[2] : g[0], c_id = g[0] == -1 ? g[3] : g[1];
+        const int64_t d_id = g[2] == -1 ? g[0] : g[2], e_id = g[2] == -1 ? g[1] : g[3];
+        if (b_id < 0 || c_id < 0 || d_id < 0 || e_id < 0 || b_id >= E || c_id >= E || d_id >= E || e_id >= E) return MCNN_E_BADARG;
+        const int32_t *ea = edges + 2 * (size_t)e, *eb = edges + 2 * b_id, *ec = edges + 2 * c_id, *ed = edges + 2 * d_id,
+                      *ee = edges + 2 * e_id;
+        const int first = (ea[1] == eb[0] || ea[1] == eb[1]) ? 1 : 0;
+        const int second = (eb[1] == ec[0] || eb[1] == ec[1]) ? 1 : 0;
+        const int third = (ed[1] == ee[0] || ed[1] == ee[1]) ? 1 : 0;
+        const int p[4] = {ea[first], ea[1 - first], eb[second], ed[third]};
+        for (int k = 0; k < 4; ++k)
+            if (p[k] < 0 || p[k] >= nv) return MCNN_E_BADARG;
+        const V3 P0 = ld(vs, p[0]), P1 = ld(vs, p[1]);
+        lengths[e] = norm3(sub(P0, P1));
+        V3 nrm[2];
+        for (int s = 0; s < 2; ++s) {
+            const V3 Ps = ld(vs, p[s]), Po = ld(vs, p[s + 2]), Pt = ld(vs, p[1 - s]);
+            // face normal of side s
+            const V3 n = cross3(sub(Po, Ps), sub(Pt, Ps));
+            nrm[s] = divs(n, norm3(n) + 0.1);
+            // opposite angle: between the two edges that meet at the opposite vertex
+            V3 ua = sub(Ps, Po), ub = sub(Pt, Po);
+            ua = divs(ua, norm3(ua) + 0.1);
+            ub = divs(ub, norm3(ub) + 0.1);
+            opp_arg[(size_t)s * E + e] = clip1(dot3(ua, ub));
+            // height / base ratio
+            const double base_len = norm3(sub(Ps, Pt));
+            const V3 ab = sub(Pt, Ps);
+            const double proj = dot3(ab, sub(Po, Ps)) / (norm3(ab) + 0.1);
+            if (base_len == 0.0 && proj != 0.0 && proj == proj) flagged = 1;
+            const double t = proj / base_len;
+            const V3 closest = V3{Ps.x + t * ab.x, Ps.y + t * ab.y, Ps.z + t * ab.z};
+            const double h = norm3(sub(Po, closest));
+            if (base_len == 0.0 && h != 0.0 && h == h) flagged = 1;
+            ratio[(size_t)s * E + e] = h / base_len;
+        }
+        dih_arg[e] = clip1(dot3(nrm[0], nrm[1]));
+    }
+    return flagged ? -101 : 0;
+}

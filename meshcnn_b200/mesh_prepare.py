@@ -203,6 +203,36 @@ def edge_points(edges, gemm):
 
 def extract_features(vs, edges, gemm):
     """[5, E] float64 features + edge lengths (mesh_prepare.py:303-427)."""
+    if NATIVE:
+        return extract_features_native(vs, edges, gemm)
+    return extract_features_py(vs, edges, gemm)
+
+
+def extract_features_native(vs, edges, gemm):
+    """Everything up to the arccos in the library's host-side C++ (mcnn_host_edge_features: same operations in the same order,
+    bit-identical); arccos, the pair sorts and the stacking in NumPy."""
+    from . import _lib
+    vs = np.ascontiguousarray(vs, dtype=np.float64)
+    edges = np.ascontiguousarray(edges, dtype=np.int32)
+    gemm = np.ascontiguousarray(gemm, dtype=np.int64)
+    E = len(edges)
+    lengths = np.empty(E, dtype=np.float64)
+    dih = np.empty(E, dtype=np.float64)
+    opp = np.empty((2, E), dtype=np.float64)
+    rat = np.empty((2, E), dtype=np.float64)
+    rc = _lib.lib().mcnn_host_edge_features(vs.ctypes.data, int(vs.shape[0]), edges.ctypes.data, gemm.ctypes.data, E,
+                                            lengths.ctypes.data, dih.ctypes.data, opp.ctypes.data, rat.ctypes.data)
+    if rc == -101:
+        raise ValueError('bad features')
+    if rc != 0:
+        raise RuntimeError('mcnn_host_edge_features failed (%d)' % rc)
+    dihedral = (np.pi - np.arccos(dih))[None]
+    ang = np.sort(np.arccos(opp), axis=0)
+    rat = np.sort(rat, axis=0)
+    return np.concatenate([dihedral, ang, rat], 0), lengths
+
+
+def extract_features_py(vs, edges, gemm):
     ep = edge_points(edges, gemm)
     lengths = np.linalg.norm(vs[ep[:, 0]] - vs[ep[:, 1]], axis=1)
 

@@ -96,8 +96,33 @@ def test_native_topology_builder_matches_the_numpy_formulation():
             assert x.dtype == y.dtype and np.array_equal(x, y)
         assert t1[3] == t0[3]
         assert t1[4].dtype == t0[4].dtype and np.array_equal(t1[4], t0[4])
+        # the features: everything up to the arccos natively (mcnn_host_edge_features), bit-identical to the NumPy formulation
+        f1, l1 = mesh_prepare.extract_features_native(vs, t1[0], t1[1])
+        f0, l0 = mesh_prepare.extract_features_py(vs, t0[0], t0[1])
+        assert f1.dtype == f0.dtype and f1.shape == f0.shape and np.array_equal(f1, f0, equal_nan=True)
+        assert np.array_equal(l1, l0)
     vs = np.array([[0., 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1], [1, 1, 1]])
     fan = np.array([[0, 1, 2], [1, 0, 3], [0, 1, 4]])              # the undirected edge (0, 1) in three faces
     for fn in (mesh_prepare.build_topology, mesh_prepare.build_topology_py):
         with pytest.raises(ValueError):
             fn(vs, fan)
+
+
+def test_native_features_match_numpy_on_a_collapsed_edge():
+    """An edge whose endpoints coincide: base length 0 and projection 0, so the height / base ratio is 0 / 0 -- NaN, not a
+    divide error -- in the NumPy formulation; the native path must produce the same NaNs in the same places."""
+    import warnings
+    import numpy as np
+    from meshcnn_b200 import mesh_prepare, synth
+    vs, faces = synth.make('ico', 1, nu=3)
+    vs = np.asarray(vs, dtype=np.float64)
+    f, a = mesh_prepare.drop_non_manifold(vs, np.asarray(faces, dtype=np.int64))
+    edges, gemm = mesh_prepare.build_topology(vs, f, a)[:2]
+    vs = vs.copy()
+    vs[edges[5, 1]] = vs[edges[5, 0]]
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        f1, l1 = mesh_prepare.extract_features_native(vs, edges, gemm)
+        f0, l0 = mesh_prepare.extract_features_py(vs, edges, gemm)
+    assert np.isnan(f0).any()
+    assert np.array_equal(f1, f0, equal_nan=True) and np.array_equal(l1, l0)
