@@ -50,7 +50,7 @@ int mcnn_debug_tc_prof(long long* out16_host, int reset);
 int mcnn_debug_set_norm_fused(int on);
 
 /* diagnostics only: which collapse kernel mcnn_pool_collapse launches for a mesh that fits on chip: 0 (default) = by the size
- * of the incoming level (sequential up to 1000 edges, rounds above), 1 = always the round kernel, 2 = always the sequential one */
+ * of the incoming level (sequential up to 3000 edges, rounds above), 1 = always the round kernel, 2 = always the sequential one */
 int mcnn_debug_set_pool_mode(int mode);
 
 /* diagnostics only: programmatic dependent launch of every kernel of the library (default off; MESHCNN_B200_PDL=1): 0 = plain

@@ -1532,9 +1532,11 @@ static int launch_segment(const float* in, float* out, const int32_t* ptr, const
 
 namespace mcnn {
 namespace seq { int launch(const mcnn_pool_args* a, size_t* smem_needed, cudaStream_t st, bool query_only); }   // meshpool_seq.cu
-// Below this many edges in the incoming level the sequential kernel is used: the window of the round kernel holds ~2
-// committable candidates on such a mesh, which only pays for the rounds' fixed cost (numbers in meshpool_seq.cu).
-constexpr int POOL_SEQ_MAX_EDGES = 1000;
+// Up to this many edges in the incoming level the sequential kernel is used.  On 750-edge meshes the window of the round
+// kernel holds ~2 committable candidates, which only pays for the rounds' fixed cost; at 2280 edges (human-seg / COSEG, real
+// conv features) the reworked sequential kernel -- two helper warps, DESIGN 4.3 -- is 3 % of the step ahead as well (4.82 vs
+// 4.97 ms, tools/pool_mode_ab.py).  Above, the window fills and the rounds win (2.6x at 170 k edges).
+constexpr int POOL_SEQ_MAX_EDGES = 3000;
 static int g_pool_mode = 0;                // debug: 0 = by size, 1 = always the round kernel, 2 = always the sequential kernel (on chip)
 }  // namespace mcnn
 

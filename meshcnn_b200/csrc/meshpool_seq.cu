@@ -1,10 +1,10 @@
 // MeshPool collapse, SEQUENTIAL form: one CTA per mesh, thread 0 runs the reference's pop loop one candidate at a time and two
-// helper warps serve the vertex-list work (R: one-ring walks and searches, M: list merges).  Used for SMALL meshes: the round-based kernel in
-// meshpool.cu commits the conflict-free prefix of a window of candidates per round, and on a 750-edge mesh that prefix is
-// ~2 candidates (measured: 2.4 / 1.9 / 1.9 / 1.9 per round on the cubes pool chain) while a round costs ~2x a sequential
-// pop -- break-even.  From ~1000 edges up the window fills (3.9 per round at 2280 edges, ~15 at 170 k) and the round kernel
-// wins (1.5x at 2280 edges, 2.6x at 170 k).  mcnn_pool_collapse picks by the size of the incoming level.  Same results bit
-// for bit (tests/test_pool_gpu.py runs every golden chain through both).
+// helper warps serve the vertex-list work (R: one-ring walks and searches, M: list merges).  Used for meshes of up to 3000
+// edges: the round-based kernel in meshpool.cu commits the conflict-free prefix of a window of candidates per round, and on a
+// 750-edge mesh that prefix is ~2 candidates (measured: 2.4 / 1.9 / 1.9 / 1.9 per round on the cubes pool chain) while a round
+// costs ~3x a sequential pop; at 2280 edges (3.9 / 3.2 / 2.4 per round) this kernel is still ahead on real conv features.  Where
+// the window fills (~15 per round at 170 k edges) the round kernel wins (2.6x).  mcnn_pool_collapse picks by the size of the
+// incoming level.  Same results bit for bit (tests/test_pool_gpu.py runs every golden chain through both).
 //
 // Everything below lives in namespace mcnn::seq; the data structures are described in meshpool.cu.
 #include "common.cuh"
